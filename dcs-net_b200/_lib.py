@@ -1,0 +1,151 @@
+"""ctypes binding of libdcsnet_sm100a.so (include/dcsnet.h).  No torch types cross this boundary: only raw
+device pointers (`tensor.data_ptr()`), sizes and the current CUDA stream handle.
+
+The library is mandatory: there is NO CPU / PyTorch fallback.  `lib()` raises if the shared object is missing or
+does not export every symbol declared in include/dcsnet.h.
+"""
+import ctypes as C
+import os
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libdcsnet_sm100a.so")
+
+F32, BF16 = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+COMBINE_DCS, COMBINE_DC = 0, 1
+MAX_TAPS = 64
+
+_vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
+
+
+class StftParams(C.Structure):
+    _fields_ = [("audio", _vp), ("spec", _vp), ("batch", _i), ("length", _i), ("n_frames", _i),
+                ("bn_affine", _vp), ("bn_out", _vp), ("bn_dtype", _i)]
+
+
+class IstftParams(C.Structure):
+    _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i)]
+
+
+class CbnParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("affine", _vp), ("n_pix", _i64), ("channels", _i), ("act", _i),
+                ("in_dtype", _i), ("out_dtype", _i)]
+
+
+class CconvParams(C.Structure):
+    _fields_ = [("src0", _vp), ("src1", _vp), ("c0", _i), ("c1", _i),
+                ("batch", _i), ("in_h", _i), ("in_w", _i),
+                ("out_h", _i), ("out_w", _i), ("cout", _i),
+                ("up_h", _i), ("up_w", _i), ("stride_h", _i), ("stride_w", _i),
+                ("ntaps", _i), ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS),
+                ("weight", _vp), ("bias", _vp), ("act", _i),
+                ("dst", _vp), ("in_dtype", _i), ("out_dtype", _i),
+                ("pool_sums", _vp)]
+
+
+class ChanPoolParams(C.Structure):
+    _fields_ = [("x", _vp), ("sums", _vp), ("batch", _i), ("hw", _i), ("channels", _i), ("dtype", _i)]
+
+
+class ChanGateParams(C.Structure):
+    _fields_ = [("sums", _vp), ("inv_hw", _f), ("gate", _vp), ("batch", _i), ("channels", _i), ("reduced", _i),
+                ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp)]
+
+
+class SpatStatsParams(C.Structure):
+    _fields_ = [("x", _vp), ("chan_gate", _vp), ("stats", _vp), ("batch", _i), ("h", _i), ("w", _i),
+                ("channels", _i), ("dtype", _i)]
+
+
+class SpatApplyParams(C.Structure):
+    _fields_ = [("x", _vp), ("chan_gate", _vp), ("stats", _vp), ("w7", _vp), ("y", _vp),
+                ("batch", _i), ("h", _i), ("w", _i), ("channels", _i), ("in_dtype", _i), ("out_dtype", _i)]
+
+
+class ClstmParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("in_dtype", _i),
+                ("w_ih0", _vp), ("w_ih1", _vp), ("w_hh", _vp), ("bias", _vp),
+                ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
+class MaskCombineParams(C.Structure):
+    _fields_ = [("net_raw", _vp), ("noisy_spec", _vp), ("net_out", _vp), ("mask", _vp), ("noise_spec", _vp),
+                ("clean_spec", _vp), ("n", _i64), ("atan2_eps", _f), ("combine", _i), ("exact_polar", _i)]
+
+
+# symbol -> (restype, argtypes); must list EVERY entry of include/dcsnet.h (tests/test_abi.py checks both ways)
+SYMBOLS = {
+    "dcs_abi_version": (_i, []),
+    "dcs_last_error_string": (C.c_char_p, []),
+    "dcs_launch_count": (C.c_uint64, []),
+    "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
+    "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),
+    "dcs_cbn_apply": (_i, [C.POINTER(CbnParams), _vp]),
+    "dcs_cconv2d_fwd": (_i, [C.POINTER(CconvParams), _vp]),
+    "dcs_cconv2d_tc_fwd": (_i, [C.POINTER(CconvParams), _vp]),
+    "dcs_chan_pool": (_i, [C.POINTER(ChanPoolParams), _vp]),
+    "dcs_chan_gate": (_i, [C.POINTER(ChanGateParams), _vp]),
+    "dcs_spat_stats": (_i, [C.POINTER(SpatStatsParams), _vp]),
+    "dcs_spat_apply": (_i, [C.POINTER(SpatApplyParams), _vp]),
+    "dcs_clstm_workspace_bytes": (_i64, [_i, _i, _i]),
+    "dcs_clstm_fwd": (_i, [C.POINTER(ClstmParams), _vp]),
+    "dcs_mask_combine": (_i, [C.POINTER(MaskCombineParams), _vp]),
+    "dcs_convert": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the CDLL.  Raises RuntimeError when the native library is unavailable."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python dcs-net_b200/build.py` "
+                "(or __graft_entry__.build()).  dcsnet_b200 has no CPU / PyTorch fallback.")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            try:
+                fn = getattr(l, name)
+            except AttributeError as e:
+                raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild it") from e
+            fn.restype, fn.argtypes = res, args
+        if l.dcs_abi_version() != 1:
+            raise RuntimeError("libdcsnet_sm100a.so ABI version mismatch; rebuild it")
+        _lib = l
+    return _lib
+
+
+def launch_count():
+    return int(lib().dcs_launch_count())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().dcs_last_error_string()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else ''}")
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("dcsnet_b200 runs on CUDA tensors only (sm_100a kernels; no CPU fallback)")
+
+
+def dtype_code(t):
+    if t.dtype in (torch.float32, torch.complex64):
+        return F32
+    if t.dtype == torch.bfloat16:
+        return BF16
+    raise RuntimeError(f"unsupported activation dtype {t.dtype}")

@@ -1,0 +1,222 @@
+// attention.cu — CBAM-style complex channel / spatial attention (bandwidth-bound passes).
+//
+// Reference: ComplexChannelAttention /root/reference/c_network.py:53-69 (pools network_functions.py:114-138 —
+// the "max" pool is an average pool, so gate = sigmoid_c(2*fc(avg))), ComplexSpatialAttention c_network.py:71-84,
+// ComplexSigmoid network_functions.py:107-112; applied with full complex products at c_network.py:208-211,219-220.
+//
+// Passes over a (B,H,W,C) channels-last complex tensor x:
+//   1. chan_pool : sums[b][c]  = sum_hw x                      (read x once)          [fused into the conv epilogue
+//   2. chan_gate : g_c[b][c]   = sigmoid_c(2 W2 crelu(W1 avg)) (tiny)                  on the tcgen05 path]
+//   3. spat_stats: st[b][h][w] = {mean_c(g_c x), max_c Re, max_c Im}   (read x once, write 16 B / pixel)
+//   4. spat_apply: y = sigmoid_c(conv7x7(st)) * (g_c x)                (read x once, write y once)
+#include "common.cuh"
+
+namespace dcs {
+
+// ---------------------------------------------------------------- 1. global average pool (sums)
+template <typename T>
+__global__ void __launch_bounds__(256) chan_pool_kernel(const T* __restrict__ x, float* __restrict__ sums, int hw, int C,
+                                                        int pix_per_cta) {
+  __shared__ float2 red[256];
+  const int b = blockIdx.y;
+  const int lanes = 256 / C;            // pixel lanes (C <= 256, power of two)
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, hw);
+  float2 acc = make_float2(0.f, 0.f);
+  if (pl < lanes) {
+    const T* xb = x + (int64_t)b * hw * C * 2;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const float2 v = Elem<T>::ldc(xb, (int64_t)p * C + c);
+      acc.x += v.x; acc.y += v.y;
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float2 s = make_float2(0.f, 0.f);
+    for (int l = 0; l < lanes; ++l) { const float2 v = red[l * C + threadIdx.x]; s.x += v.x; s.y += v.y; }
+    atomicAdd(sums + ((int64_t)b * C + threadIdx.x) * 2 + 0, s.x);
+    atomicAdd(sums + ((int64_t)b * C + threadIdx.x) * 2 + 1, s.y);
+  }
+}
+
+// ---------------------------------------------------------------- 2. the squeeze/excite MLP on (B, C) complex
+__global__ void __launch_bounds__(128) chan_gate_kernel(const dcs_chan_gate_params p) {
+  __shared__ float2 avg[256];
+  __shared__ float2 hid[16];
+  const int b = blockIdx.x, C = p.channels, R = p.reduced;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    avg[c] = make_float2(p.sums[((int64_t)b * C + c) * 2] * p.inv_hw, p.sums[((int64_t)b * C + c) * 2 + 1] * p.inv_hw);
+  }
+  __syncthreads();
+  // hidden r: one warp per r (C <= 256), complex 1x1 conv without bias then ComplexReLU
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = warp; r < R; r += blockDim.x >> 5) {
+    float re = 0.f, im = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wr = p.w1_r[r * C + c], wi = p.w1_i[r * C + c];
+      re += wr * avg[c].x - wi * avg[c].y;
+      im += wr * avg[c].y + wi * avg[c].x;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+    if (lane == 0) hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float re = 0.f, im = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float wr = p.w2_r[c * R + r], wi = p.w2_i[c * R + r];
+      re += wr * hid[r].x - wi * hid[r].y;
+      im += wr * hid[r].y + wi * hid[r].x;
+    }
+    // fc(avg) + fc("max" = avg) = 2 fc(avg)
+    p.gate[((int64_t)b * C + c) * 2 + 0] = sigmoidf_(2.f * re);
+    p.gate[((int64_t)b * C + c) * 2 + 1] = sigmoidf_(2.f * im);
+  }
+}
+
+// ---------------------------------------------------------------- 3. per-pixel channel statistics of u = g_c * x
+template <typename T>
+__global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x, const float* __restrict__ gate,
+                                                         float4* __restrict__ stats, int hw, int C, int G) {
+  // G lanes cooperate on one pixel (G = min(32, C)); each lane strides over channels
+  __shared__ float2 gs[256];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) gs[c] = reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c];
+  __syncthreads();
+  const int sub = threadIdx.x % G, grp = threadIdx.x / G, groups = 256 / G;
+  const T* xb = x + (int64_t)b * hw * C * 2;
+  const float invC = 1.f / (float)C;
+  for (int pbase = blockIdx.x * groups; pbase < hw; pbase += gridDim.x * groups) {  // CTA-uniform trip count (shuffles)
+    const int p = pbase + grp;
+    float sr = 0.f, si = 0.f, mr = -INFINITY, mi = -INFINITY;
+    for (int c = sub; c < C && p < hw; c += G) {
+      const float2 u = cmul(gs[c], Elem<T>::ldc(xb, (int64_t)p * C + c));
+      sr += u.x; si += u.y;
+      mr = fmaxf(mr, u.x); mi = fmaxf(mi, u.y);
+    }
+    for (int o = G >> 1; o; o >>= 1) {
+      sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o);
+      mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+    }
+    if (sub == 0 && p < hw) stats[(int64_t)b * hw + p] = make_float4(sr * invC, si * invC, mr, mi);
+  }
+}
+
+// ---------------------------------------------------------------- 4. 7x7 complex conv on the stats, sigmoid, apply
+constexpr int kSaTH = 4, kSaTW = 64, kSaK = 7, kSaR = 3;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gate,
+                                                         const float4* __restrict__ stats, const float* __restrict__ w7,
+                                                         TO* __restrict__ y, int H, int W, int C) {
+  __shared__ float4 st[kSaTH + 2 * kSaR][kSaTW + 2 * kSaR];
+  __shared__ float2 sg[kSaTH][kSaTW];
+  __shared__ float2 gs[256];
+  __shared__ float wsm[2 * 2 * 49];
+  const int b = blockIdx.z;
+  const int y0 = blockIdx.y * kSaTH, x0 = blockIdx.x * kSaTW;
+  for (int i = threadIdx.x; i < 196; i += 256) wsm[i] = w7[i];
+  for (int c = threadIdx.x; c < C; c += 256) gs[c] = reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c];
+  for (int i = threadIdx.x; i < (kSaTH + 2 * kSaR) * (kSaTW + 2 * kSaR); i += 256) {
+    const int r = i / (kSaTW + 2 * kSaR), cidx = i % (kSaTW + 2 * kSaR);
+    const int yy = y0 + r - kSaR, xx = x0 + cidx - kSaR;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) v = stats[((int64_t)b * H + yy) * W + xx];
+    st[r][cidx] = v;
+  }
+  __syncthreads();
+  {  // one thread per tile pixel: ComplexConv2d(2,1,7,padding=3,bias=False) then ComplexSigmoid
+    const int r = threadIdx.x / kSaTW, cidx = threadIdx.x % kSaTW;
+    float re = 0.f, im = 0.f;
+    const float* wr = wsm;        // conv_r.weight (1,2,7,7): [ch][ky][kx]
+    const float* wi = wsm + 98;   // conv_i.weight
+#pragma unroll
+    for (int ky = 0; ky < kSaK; ++ky) {
+#pragma unroll
+      for (int kx = 0; kx < kSaK; ++kx) {
+        const float4 s = st[r + ky][cidx + kx];
+        const float a0 = wr[ky * 7 + kx], a1 = wr[49 + ky * 7 + kx];
+        const float b0 = wi[ky * 7 + kx], b1 = wi[49 + ky * 7 + kx];
+        re += a0 * s.x + a1 * s.z - b0 * s.y - b1 * s.w;
+        im += a0 * s.y + a1 * s.w + b0 * s.x + b1 * s.z;
+      }
+    }
+    sg[r][cidx] = make_float2(sigmoidf_(re), sigmoidf_(im));
+  }
+  __syncthreads();
+  for (int r = 0; r < kSaTH; ++r) {
+    const int yy = y0 + r;
+    if (yy >= H) break;
+    const int wvalid = min(kSaTW, W - x0);
+    const int64_t base = (((int64_t)b * H + yy) * W + x0) * C;
+    for (int i = threadIdx.x; i < wvalid * C; i += 256) {
+      const int px = i / C, c = i - px * C;
+      const float2 u = cmul(gs[c], Elem<TI>::ldc(x, base + i));
+      Elem<TO>::stc(y, base + i, cmul(sg[r][px], u));
+    }
+  }
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+static bool pow2(int v) { return v > 0 && (v & (v - 1)) == 0; }
+
+extern "C" int dcs_chan_pool(const dcs_chan_pool_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->sums, "dcs_chan_pool: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->hw > 0 && pow2(p->channels) && p->channels <= 256, "dcs_chan_pool: channels must be a power of two <= 256");
+  const int lanes = 256 / p->channels;
+  int ctas = (p->hw + lanes * 8 - 1) / (lanes * 8);            // >= 8 pixels per lane
+  const int cap = max(1, 8 * num_sms() / p->batch);
+  ctas = min(ctas, cap);
+  const int ppc = (p->hw + ctas - 1) / ctas;
+  dim3 grid((p->hw + ppc - 1) / ppc, p->batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->dtype == DCS_BF16) chan_pool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, p->sums, p->hw, p->channels, ppc);
+  else chan_pool_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, p->sums, p->hw, p->channels, ppc);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_chan_gate(const dcs_chan_gate_params* p, void* stream) {
+  DCS_REQUIRE(p && p->sums && p->gate && p->w1_r && p->w1_i && p->w2_r && p->w2_i, "dcs_chan_gate: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->channels > 0 && p->channels <= 256 && p->reduced > 0 && p->reduced <= 16, "dcs_chan_gate: bad shape");
+  chan_gate_kernel<<<p->batch, 128, 0, (cudaStream_t)stream>>>(*p);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->chan_gate && p->stats, "dcs_spat_stats: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && pow2(p->channels) && p->channels <= 256, "dcs_spat_stats: bad shape");
+  const int hw = p->h * p->w;
+  const int G = min(32, p->channels), groups = 256 / G;
+  int ctas = (hw + groups - 1) / groups;
+  ctas = min(ctas, max(1, 16 * num_sms() / p->batch));
+  dim3 grid(ctas, p->batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (p->dtype == DCS_BF16) spat_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G);
+  else spat_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->chan_gate && p->stats && p->w7 && p->y, "dcs_spat_apply: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && p->channels > 0 && p->channels <= 256, "dcs_spat_apply: bad shape");
+  DCS_REQUIRE(p->batch <= 65535, "dcs_spat_apply: batch too large for grid.z");
+  dim3 grid((p->w + kSaTW - 1) / kSaTW, (p->h + kSaTH - 1) / kSaTH, p->batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float4* st = (const float4*)p->stats;
+#define DCS_SA(TI, TO) spat_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, p->h, p->w, p->channels)
+  if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_SA(float, float);
+  else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_SA(float, __nv_bfloat16);
+  else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_SA(__nv_bfloat16, float);
+  else DCS_SA(__nv_bfloat16, __nv_bfloat16);
+#undef DCS_SA
+  DCS_LAUNCHED();
+  return 0;
+}

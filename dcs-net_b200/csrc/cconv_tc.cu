@@ -1,0 +1,418 @@
+// cconv_tc.cu — complex convolution as a real implicit GEMM on the 5th-generation tensor cores (sm_100a):
+// tcgen05.mma (kind::f16, bf16 operands, fp32 accumulators in TMEM), operands staged by TMA, persistent
+// warp-specialised CTAs.  This is the "bf16 mode" GEMM of every conv layer with 2*Cin % 16 == 0.
+//
+// Replaces apply_complex(conv_r, conv_i) / apply_complex(conv_tran_r, conv_tran_i) (complexPyTorch 0.3) at
+// /root/reference/c_network.py:107-112 (encoder) and 135-147 (decoder) with the preceding torch.cat +
+// complex_upsample (c_network.py:214-216) folded in; bias rule, eval-mode BN, ReLU / LReLU in the epilogue.
+//
+// GEMM view (include/dcsnet.h):  D[pixel, n] = sum_{tap, c} A[pixel + offset(tap), c] * W[n, tap, c]
+//   M tile  = 128 output pixels of ONE sub-pixel phase = NB images x TH rows x TW cols of the phase grid
+//   N       = n_pad = max(16, 2*Cout) <= 256 : one UMMA N, accumulator = n_pad TMEM columns, double-buffered
+//   K step  = 64 bf16 = 128 bytes of K: 64/CK TMA boxes of the channels-last activations (CK = min(64, 2*C_src)
+//             channels of one tap; zero padding and image borders come from TMA out-of-bounds fill, conv stride
+//             from the tensor map's elementStrides, the channel concat from switching tensor maps) + one TMA box
+//             of the K-major weight matrix (SWIZZLE_128B).
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (TMEM -> registers -> bias/activation -> bf16 -> global, plus optional per-(image, channel) pooling sums).
+#include <cuda.h>
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+
+namespace dcs {
+
+int validate_conv(const dcs_cconv_params* p, const char* who);
+
+constexpr int kTileM = 128;
+constexpr int kKStep = 64;               // bf16 elements of K per pipeline stage (= one 128-byte swizzle row)
+constexpr int kTcThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr uint32_t kSpinLimit = 1u << 26;  // mbarrier spin cap: trap instead of hanging the GPU
+
+struct TcArgs {
+  int PH, PW;                 // phase grid
+  int TW, TH, NB;             // tile shape, TW*TH*NB = 128
+  int tiles_w, tiles_h, tiles_b, tiles_per_phase, n_tiles;
+  int phases, ntaps, up_h, up_w, stride_h, stride_w;
+  int C2, C2_src0, CK, ksteps, n_stages;
+  int n_pad, n_real, act, out_f32;
+  int batch, out_h, out_w;
+  int8_t dy[DCS_MAX_TAPS], dx[DCS_MAX_TAPS];
+  const float* bias;
+  void* dst;
+  float* pool;
+};
+
+// ------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > kSpinLimit) __trap();  // a broken pipeline must fault, never hang the device
+  }
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 |
+// version=1 <<46 | layout_type <<61.  Rows are `row_bytes` (= swizzle span) apart, 8-row groups SBO = 8*row_bytes.
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_bytes) {
+  const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);  // SWIZZLE_128B / 64B / 32B
+  uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;                               // LBO (ignored for swizzled K-major)
+  d |= (uint64_t)((8u * row_bytes) >> 4) << 32;         // SBO
+  d |= (uint64_t)1 << 46;                               // descriptor version (Blackwell)
+  d |= layout << 61;
+  return d;
+}
+
+struct __align__(8) TcBarriers {
+  uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // layout: [stage][A 16 KB | B n_pad*128 B] (1024-aligned), then barriers
+  const uint32_t a_bytes = kTileM * kKStep * 2, b_bytes = (uint32_t)a.n_pad * kKStep * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;  // multiple of 1024 (n_pad % 16 == 0 -> b_bytes % 2048 == 0)
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  TcBarriers* bars = reinterpret_cast<TcBarriers*>(base + (size_t)a.n_stages * stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t tmem_cols = a.n_pad <= 16 ? 32u : (a.n_pad <= 32 ? 64u : (a.n_pad <= 64 ? 128u : (a.n_pad <= 128 ? 256u : 512u)));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.n_stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+  const int sub_per_step = kKStep / a.CK;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase_bit = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int ph_idx = tile / a.tiles_per_phase;
+        int r = tile - ph_idx * a.tiles_per_phase;
+        const int bt = r / (a.tiles_h * a.tiles_w);
+        r -= bt * a.tiles_h * a.tiles_w;
+        const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
+        const int b0 = bt * a.NB, j0 = ht * a.TH, i0 = wt * a.TW;
+        for (int ks = 0; ks < a.ksteps; ++ks) {
+          mbar_wait(smem_u32(&bars->empty[stage]), phase_bit ^ 1);
+          const uint32_t full = smem_u32(&bars->full[stage]);
+          mbar_expect_tx(full, stage_bytes);
+          const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
+          for (int g = 0; g < sub_per_step; ++g) {
+            const int e = (ks * sub_per_step + g) * a.CK;  // flattened (tap, channel) offset
+            int tap = e / a.C2;
+            int c = e - tap * a.C2;
+            if (tap >= a.ntaps) { tap = a.ntaps - 1; }       // K padding: finite data x zero weights
+            const int y = j0 * a.stride_h + a.dy[ph_idx * a.ntaps + tap];
+            const int x = i0 * a.stride_w + a.dx[ph_idx * a.ntaps + tap];
+            const uint32_t dst = sa + (uint32_t)g * (kTileM * a.CK * 2);
+            if (c < a.C2_src0) tma_load_4d(dst, &tmA0, full, c, x, y, b0);
+            else tma_load_4d(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
+          }
+          tma_load_2d(sa + a_bytes, &tmB, full, ks * kKStep, ph_idx * a.n_pad);
+          if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (one thread)
+    if (lane == 0) {
+      // instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 @17, M>>4 @24
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t a_row_bytes = (uint32_t)a.CK * 2;
+      uint32_t stage = 0, phase_bit = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&bars->acc_empty[acc]), acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_pad;
+        for (int ks = 0; ks < a.ksteps; ++ks) {
+          mbar_wait(smem_u32(&bars->full[stage]), phase_bit);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+#pragma unroll
+          for (int i = 0; i < kKStep / 16; ++i) {
+            const int g = (16 * i) / a.CK, j = (16 * i - g * a.CK) / 16;
+            const uint64_t ad = umma_desc(sa + (uint32_t)g * (kTileM * a.CK * 2) + (uint32_t)j * 32, a_row_bytes);
+            const uint64_t bd = umma_desc(sb + (uint32_t)i * 32, 128);
+            tc_mma_bf16(d_tmem, ad, bd, idesc, (ks | i) != 0);
+          }
+          tc_commit(smem_u32(&bars->empty[stage]));  // frees the smem stage once these MMAs have read it
+          if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
+        }
+        tc_commit(smem_u32(&bars->acc_full[acc]));   // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps = 128 TMEM lanes)
+    const int quad = warp & 3;                // TMEM lane quadrant this warp may access
+    const int m = quad * 32 + lane;           // tile row = TMEM lane
+    const int hw_tile = a.TH * a.TW;
+    const int nb = m / hw_tile, rr = (m - nb * hw_tile) / a.TW, cc = m % a.TW;
+    const bool warp_uniform_image = (hw_tile % 32) == 0;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      const int ph_idx = tile / a.tiles_per_phase;
+      int r = tile - ph_idx * a.tiles_per_phase;
+      const int bt = r / (a.tiles_h * a.tiles_w);
+      r -= bt * a.tiles_h * a.tiles_w;
+      const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
+      const int b = bt * a.NB + nb, j = ht * a.TH + rr, i = wt * a.TW + cc;
+      const bool valid = b < a.batch && j < a.PH && i < a.PW;
+      const int oy = j * a.up_h + ph_idx / a.up_w, ox = i * a.up_w + ph_idx % a.up_w;
+      const int64_t pix = ((int64_t)b * a.out_h + oy) * a.out_w + ox;
+      mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)a.n_pad;
+      for (int n0 = 0; n0 < a.n_pad; n0 += 16) {
+        uint32_t rg[16];
+        tc_ld16(taddr + (uint32_t)n0, rg);
+        tc_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) v[q] = act_apply(__uint_as_float(rg[q]) + __ldg(a.bias + n0 + q), a.act);
+        if (valid) {
+          if (a.out_f32) {
+            float* o = reinterpret_cast<float*>(a.dst) + pix * a.n_real + n0;
+            if (n0 + 16 <= a.n_real) {
+#pragma unroll
+              for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+            } else {
+              for (int q = 0; q < 16; ++q) if (n0 + q < a.n_real) o[q] = v[q];
+            }
+          } else {
+            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dst) + pix * a.n_real + n0;
+            if (n0 + 16 <= a.n_real) {
+              uint32_t pk[8];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                pk[q] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+              for (int q = 0; q < 16; ++q) if (n0 + q < a.n_real) o[q] = __float2bfloat16_rn(v[q]);
+            }
+          }
+        }
+        if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:219)
+#pragma unroll
+          for (int q = 0; q < 16; ++q) {
+            float s = valid ? v[q] : 0.f;
+            if (warp_uniform_image) {
+#pragma unroll
+              for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+              if (lane == 0 && b < a.batch && n0 + q < a.n_real) atomicAdd(a.pool + (int64_t)b * a.n_real + n0 + q, s);
+            } else if (valid && n0 + q < a.n_real) {
+              atomicAdd(a.pool + (int64_t)b * a.n_real + n0 + q, s);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int row_bytes) {
+  return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// activations: channels-last complex bf16 (B, H, W, C2) -> 4-D map, box (CK, TW*sx, TH*sy, NB), element strides (1,sx,sy,1)
+static int make_act_map(CUtensorMap* m, const void* ptr, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy) {
+  EncodeTiledFn fn = encode_fn();
+  DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[4] = {(cuuint64_t)C2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C2 * 2, (cuuint64_t)W * C2 * 2, (cuuint64_t)H * W * C2 * 2};
+  cuuint32_t box[4] = {(cuuint32_t)CK, (cuuint32_t)(TW * sx), (cuuint32_t)(TH * sy), (cuuint32_t)NB};
+  cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
+  DCS_REQUIRE(box[1] <= 256 && box[2] <= 256, "TMA box too large (%u x %u)", box[1], box[2]);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with CUresult %d (C2=%d W=%d H=%d B=%d box=%d,%d,%d,%d)",
+              (int)r, C2, W, H, B, CK, TW * sx, TH * sy, NB);
+  return 0;
+}
+
+static int make_weight_map(CUtensorMap* m, const void* ptr, int Kpad, int rows, int n_pad) {
+  EncodeTiledFn fn = encode_fn();
+  DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kKStep, (cuuint32_t)n_pad};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
+  return 0;
+}
+
+static int pick_pow2_tile(int extent, int max_tile) {
+  // largest power of two <= max_tile whose padding waste is within 4 % of the best achievable
+  double best = 1e9;
+  for (int t = max_tile; t >= 1; t >>= 1) best = std::min(best, (double)((extent + t - 1) / t * t) / extent);
+  for (int t = max_tile; t >= 1; t >>= 1)
+    if ((double)((extent + t - 1) / t * t) / extent <= best * 1.04) return t;
+  return 1;
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
+  if (int e = validate_conv(p, "dcs_cconv2d_tc_fwd")) return e;
+  DCS_REQUIRE(p->in_dtype == DCS_BF16, "dcs_cconv2d_tc_fwd: activations must be bf16");
+  const int C2s0 = 2 * p->c0, C2s1 = 2 * p->c1, C2 = C2s0 + C2s1;
+  DCS_REQUIRE(C2s0 % 16 == 0 && (p->c1 == 0 || C2s1 == C2s0 || (C2s0 % 64 == 0 && C2s1 % 64 == 0)),
+              "dcs_cconv2d_tc_fwd: unsupported channel split (%d, %d); use dcs_cconv2d_fwd", p->c0, p->c1);
+  const int CK = C2s0 >= 64 ? 64 : C2s0;
+  DCS_REQUIRE(CK == 16 || CK == 32 || CK == 64, "dcs_cconv2d_tc_fwd: 2*c0 must be 16, 32 or a multiple of 64 (got %d)", C2s0);
+  DCS_REQUIRE(C2s0 % CK == 0 && C2s1 % CK == 0, "dcs_cconv2d_tc_fwd: channel counts must be multiples of %d", CK);
+  const int N = 2 * p->cout, n_pad = (N + 15) / 16 * 16;
+  DCS_REQUIRE(n_pad <= 256, "dcs_cconv2d_tc_fwd: 2*cout must be <= 256 (got %d)", N);
+  DCS_REQUIRE(((uintptr_t)p->src0 % 16 == 0) && ((uintptr_t)p->src1 % 16 == 0) && ((uintptr_t)p->weight % 16 == 0),
+              "dcs_cconv2d_tc_fwd: pointers must be 16-byte aligned");
+
+  TcArgs a;
+  memset(&a, 0, sizeof(a));
+  a.PH = p->out_h / p->up_h;
+  a.PW = p->out_w / p->up_w;
+  a.TW = pick_pow2_tile(a.PW, std::min(kTileM, 256 / p->stride_w));  // TMA box dim (TW*stride) <= 256
+  a.TH = pick_pow2_tile(a.PH, std::min(kTileM / a.TW, 256 / p->stride_h));
+  a.NB = kTileM / (a.TW * a.TH);
+  a.tiles_w = (a.PW + a.TW - 1) / a.TW;
+  a.tiles_h = (a.PH + a.TH - 1) / a.TH;
+  a.tiles_b = (p->batch + a.NB - 1) / a.NB;
+  a.tiles_per_phase = a.tiles_w * a.tiles_h * a.tiles_b;
+  a.phases = p->up_h * p->up_w;
+  a.n_tiles = a.tiles_per_phase * a.phases;
+  a.ntaps = p->ntaps; a.up_h = p->up_h; a.up_w = p->up_w; a.stride_h = p->stride_h; a.stride_w = p->stride_w;
+  a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK;
+  const int K = p->ntaps * C2;
+  a.ksteps = (K + kKStep - 1) / kKStep;
+  a.n_pad = n_pad; a.n_real = N; a.act = p->act; a.out_f32 = p->out_dtype == DCS_F32;
+  a.batch = p->batch; a.out_h = p->out_h; a.out_w = p->out_w;
+  memcpy(a.dy, p->dy, sizeof(a.dy));
+  memcpy(a.dx, p->dx, sizeof(a.dx));
+  DCS_REQUIRE(p->bias, "dcs_cconv2d_tc_fwd: bias is required (pass zeros)");
+  a.bias = p->bias; a.dst = p->dst; a.pool = p->pool_sums;
+
+  const size_t stage_bytes = (size_t)kTileM * kKStep * 2 + (size_t)n_pad * kKStep * 2;
+  int n_stages = (int)((200 * 1024) / stage_bytes);
+  n_stages = std::max(2, std::min(n_stages, kMaxStages));
+  a.n_stages = n_stages;
+  const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers);
+
+  CUtensorMap tmA0, tmA1, tmB;
+  if (int e = make_act_map(&tmA0, p->src0, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+  if (p->c1) {
+    if (int e = make_act_map(&tmA1, p->src1, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+  } else {
+    tmA1 = tmA0;
+  }
+  if (int e = make_weight_map(&tmB, p->weight, a.ksteps * kKStep, a.phases * n_pad, n_pad)) return e;
+
+  DCS_CUDA(cudaFuncSetAttribute(cconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const int grid = std::min(a.n_tiles, num_sms());
+  cconv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, a);
+  DCS_LAUNCHED();
+  return 0;
+}

@@ -1,0 +1,77 @@
+// common.cuh — shared host/device helpers for libdcsnet_sm100a.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <atomic>
+
+#include "../../include/dcsnet.h"
+
+namespace dcs {
+
+// ---- error plumbing (include/dcsnet.h: 0 = ok, <0 argument error, >0 cudaError_t)
+char* err_buf();
+int set_error(int code, const char* fmt, ...);
+extern std::atomic<uint64_t> g_launches;
+
+#define DCS_REQUIRE(cond, ...)                                   \
+  do {                                                           \
+    if (!(cond)) return ::dcs::set_error(-1, __VA_ARGS__);       \
+  } while (0)
+
+#define DCS_CUDA(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      return ::dcs::set_error((int)e__, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+  } while (0)
+
+// every kernel launch goes through this so dcs_launch_count() is an honest count
+#define DCS_LAUNCHED()                                                                  \
+  do {                                                                                  \
+    ::dcs::g_launches.fetch_add(1, std::memory_order_relaxed);                          \
+    cudaError_t e__ = cudaPeekAtLastError();                                            \
+    if (e__ != cudaSuccess)                                                             \
+      return ::dcs::set_error((int)e__, "kernel launch failed: %s", cudaGetErrorString(e__)); \
+  } while (0)
+
+static inline int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+// ---- element access for the two activation storage types (complex element = 2 scalars)
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+  using pair_t = float2;
+  static __device__ __forceinline__ float2 ldc(const float* p, int64_t i) { return reinterpret_cast<const float2*>(p)[i]; }
+  static __device__ __forceinline__ void stc(float* p, int64_t i, float2 v) { reinterpret_cast<float2*>(p)[i] = v; }
+};
+template <> struct Elem<__nv_bfloat16> {
+  using pair_t = __nv_bfloat162;
+  static __device__ __forceinline__ float2 ldc(const __nv_bfloat16* p, int64_t i) {
+    return __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(p)[i]);
+  }
+  static __device__ __forceinline__ void stc(__nv_bfloat16* p, int64_t i, float2 v) {
+    reinterpret_cast<__nv_bfloat162*>(p)[i] = __float22bfloat162_rn(v);
+  }
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == DCS_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == DCS_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
+
+}  // namespace dcs

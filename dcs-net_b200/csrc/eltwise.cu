@@ -1,0 +1,145 @@
+// eltwise.cu — bandwidth-bound element-wise stages: folded eval-mode ComplexBatchNorm2d (+activation), the
+// bound_cRM x2 / mask (.) Y / subtraction tail, dtype conversion, library bookkeeping.
+//
+// Reference call sites: ComplexBatchNorm2d (complexPyTorch 0.3) at /root/reference/c_network.py:101,113,148;
+// bound_cRM network_functions.py:77-88 (called at c_network.py:225 and again at network_functions.py:394);
+// complex_mat_mult network_functions.py:90-96; combine network_functions.py:396-397 (dcs), 434 (dc).
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace dcs {
+
+std::atomic<uint64_t> g_launches{0};
+
+char* err_buf() {
+  static thread_local char buf[512] = {0};
+  return buf;
+}
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(err_buf(), 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+template <typename TI, typename TO>
+__global__ void cbn_kernel(const TI* __restrict__ x, TO* __restrict__ y, const float* __restrict__ aff, int64_t n, int C,
+                           int act) {
+  // n = total complex elements (pixels * C)
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float* a = aff + 6 * c;
+    const float2 v = Elem<TI>::ldc(x, i);
+    const float re = act_apply(a[0] * v.x + a[1] * v.y + a[4], act);
+    const float im = act_apply(a[2] * v.x + a[3] * v.y + a[5], act);
+    Elem<TO>::stc(y, i, make_float2(re, im));
+  }
+}
+
+// bound_cRM (network_functions.py:77-88).  `exact` evaluates the reference's transcendental sequence literally.
+__device__ __forceinline__ float2 bound_crm(float2 m, float eps, bool exact) {
+  const float t = tanhf(sqrtf(m.x * m.x + m.y * m.y));
+  if (exact) {
+    const float th1 = atan2f(m.y, m.x + eps);
+    const float r1 = t * cosf(th1), i1 = t * sinf(th1);
+    const float th2 = atan2f(i1, r1 + eps);
+    return make_float2(t * cosf(th2), t * sinf(th2));
+  }
+  // cos(atan2(y, x)) = x / hypot(x, y), sin(atan2(y, x)) = y / hypot(x, y);  atan2(0, 0) = 0
+  float x1 = m.x + eps, h1 = sqrtf(x1 * x1 + m.y * m.y);
+  float r1, i1;
+  if (h1 == 0.f) { r1 = t; i1 = 0.f; } else { const float s = t / h1; r1 = x1 * s; i1 = m.y * s; }
+  float x2 = r1 + eps, h2 = sqrtf(x2 * x2 + i1 * i1);
+  if (h2 == 0.f) return make_float2(t, 0.f);
+  const float s2 = t / h2;
+  return make_float2(x2 * s2, i1 * s2);
+}
+
+__global__ void mask_combine_kernel(const dcs_mask_combine_params p) {
+  const float2* raw = reinterpret_cast<const float2*>(p.net_raw);
+  const float2* Y = reinterpret_cast<const float2*>(p.noisy_spec);
+  float2* o_net = reinterpret_cast<float2*>(p.net_out);
+  float2* o_mask = reinterpret_cast<float2*>(p.mask);
+  float2* o_noise = reinterpret_cast<float2*>(p.noise_spec);
+  float2* o_clean = reinterpret_cast<float2*>(p.clean_spec);
+  const bool exact = p.exact_polar != 0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < p.n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 m1 = bound_crm(__ldg(raw + i), p.atan2_eps, exact);  // C_NETWORK.forward's own bound (c_network.py:225)
+    const float2 m2 = bound_crm(m1, p.atan2_eps, exact);              // the step function's bound (network_functions.py:394)
+    const float2 y = __ldg(Y + i);
+    const float2 prod = cmul(y, m2);
+    if (o_net) o_net[i] = m1;
+    if (o_mask) o_mask[i] = m2;
+    if (p.combine == DCS_COMBINE_DCS) {
+      if (o_noise) o_noise[i] = prod;
+      if (o_clean) o_clean[i] = make_float2(y.x - prod.x, y.y - prod.y);
+    } else {
+      if (o_clean) o_clean[i] = prod;
+    }
+  }
+}
+
+template <typename TI, typename TO>
+__global__ void convert_kernel(const TI* __restrict__ s, TO* __restrict__ d, int64_t n2) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
+    Elem<TO>::stc(d, i, Elem<TI>::ldc(s, i));
+}
+
+static inline int ew_grid(int64_t n, int threads) {
+  int64_t b = (n + threads - 1) / threads;
+  const int64_t cap = (int64_t)num_sms() * 16;
+  return (int)(b < cap ? (b > 0 ? b : 1) : cap);
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+extern "C" int dcs_abi_version(void) { return DCS_ABI_VERSION; }
+extern "C" const char* dcs_last_error_string(void) { return err_buf(); }
+extern "C" uint64_t dcs_launch_count(void) { return g_launches.load(); }
+
+extern "C" int dcs_cbn_apply(const dcs_cbn_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->y && p->affine, "dcs_cbn_apply: null pointer");
+  DCS_REQUIRE(p->n_pix > 0 && p->channels > 0, "dcs_cbn_apply: bad shape");
+  const int64_t n = p->n_pix * p->channels;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = ew_grid(n, 256);
+  if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32)
+    cbn_kernel<float, float><<<g, 256, 0, s>>>((const float*)p->x, (float*)p->y, p->affine, n, p->channels, p->act);
+  else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16)
+    cbn_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)p->x, (__nv_bfloat16*)p->y, p->affine, n, p->channels, p->act);
+  else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32)
+    cbn_kernel<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->y, p->affine, n, p->channels, p->act);
+  else
+    cbn_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, p->affine, n, p->channels, p->act);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_mask_combine(const dcs_mask_combine_params* p, void* stream) {
+  DCS_REQUIRE(p && p->net_raw && p->noisy_spec && p->clean_spec, "dcs_mask_combine: null pointer");
+  DCS_REQUIRE(p->n > 0, "dcs_mask_combine: empty input");
+  DCS_REQUIRE(p->combine == DCS_COMBINE_DCS || p->combine == DCS_COMBINE_DC, "dcs_mask_combine: bad combine mode %d", p->combine);
+  mask_combine_kernel<<<ew_grid(p->n, 256), 256, 0, (cudaStream_t)stream>>>(*p);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_dtype, int out_dtype, void* stream) {
+  DCS_REQUIRE(src && dst && n_floats > 0 && n_floats % 2 == 0, "dcs_convert: bad arguments");
+  const int64_t n2 = n_floats / 2;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int g = ew_grid(n2, 256);
+  if (in_dtype == DCS_F32 && out_dtype == DCS_BF16)
+    convert_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n2);
+  else if (in_dtype == DCS_BF16 && out_dtype == DCS_F32)
+    convert_kernel<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n2);
+  else if (in_dtype == DCS_F32 && out_dtype == DCS_F32)
+    convert_kernel<float, float><<<g, 256, 0, s>>>((const float*)src, (float*)dst, n2);
+  else
+    convert_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n2);
+  DCS_LAUNCHED();
+  return 0;
+}

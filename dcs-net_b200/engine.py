@@ -1,0 +1,213 @@
+"""ForwardPlan — the fused DCS-Net inference path: STFT -> C_NETWORK.forward -> bound_cRM x2 -> mask (.) Y
+[-> Y - N] -> iSTFT, as a fixed sequence of sm_100a kernels over pre-allocated HBM buffers, replayable as a
+CUDA graph.  It follows /root/reference/c_network.py:187-226 and network_functions.py:393-401 step by step
+(eval mode: dropout is the identity, BN uses running statistics).
+
+Memory plan (per plan instance, B utterances of T frames, everything resident in HBM):
+  Y          (B,256,T)      complex64   noisy spectrogram (reference layout, T contiguous)
+  bn0        (B,256,T,1,2)  act dtype   initial_batchnorm output = encoder input
+  enc[i]     (B,H_i,W_i,C_i,2) act      encoder outputs, channels-last complex
+  lat / fc   (B,2,T/8,128,2)            ComplexLSTM output (fp32) and ComplexLinear output (act dtype)
+  skip[i], dec[i], datt[i]              attended skips, decoder conv outputs, attended decoder outputs
+  raw        (B,256,T) complex64        decoder[6] output;   S / N / M / net_out outputs, audio (B, 32(T-1))
+act dtype = float32 in the 'fp32' mode (CUDA-core FFMA GEMMs, <=1e-5) and bfloat16 in the 'bf16' mode
+(tcgen05 tensor-core GEMMs with fp32 accumulation, <=2e-3); attention, LSTM, masks, FFTs are fp32 in both.
+"""
+import torch
+
+from . import _lib as L
+from . import ops, packing
+
+KERNEL_E = [7, 7, 5, 5, 3, 3, 3]                                            # config.py:83
+STRIDE_E = [(2, 2), (2, 2), (2, 2), (2, 1), (2, 1), (2, 1), (2, 1)]          # config.py:99
+UPSAMPLE = [(2, 1), (2, 1), (2, 1), (2, 1), (2, 2), (2, 2), (2, 2)]          # config.py:105
+
+
+def _sd_tensor_dict(model_or_sd):
+    sd = model_or_sd.state_dict() if hasattr(model_or_sd, "state_dict") else model_or_sd
+    return {k: v.detach() for k, v in sd.items()}
+
+
+class PackedNet:
+    """All GEMM-ready operands of a C_NETWORK state_dict for one device and mode."""
+
+    def __init__(self, model_or_sd, device, mode="fp32", no_of_layers=7):
+        sd = _sd_tensor_dict(model_or_sd)
+        assert mode in ("fp32", "bf16")
+        self.mode, self.device, self.L = mode, device, no_of_layers
+        bf = mode == "bf16"
+        Lr = no_of_layers
+        self.bn0 = packing.affine6(*packing.bn_affine_from_sd(sd, "initial_batchnorm.")).to(device)
+        self.enc, self.dec, self.skip_ca, self.skip_sa, self.dec_ca, self.dec_sa = [], [], [], [], [], []
+        for i in range(Lr):
+            p = f"encoder.{i}.0."
+            self.enc.append(packing.PackedConv(
+                sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], sd[p + "conv_r.bias"], sd[p + "conv_i.bias"],
+                bn=packing.bn_affine_from_sd(sd, f"encoder.{i}.1."), stride=STRIDE_E[i], act=L.ACT_RELU,
+                device=device, want_bf16=bf))
+        for i in range(Lr):
+            last = i == Lr - 1
+            p = f"decoder.{i}." if last else f"decoder.{i}.0."
+            self.dec.append(packing.PackedConv(
+                sd[p + "conv_tran_r.weight"], sd[p + "conv_tran_i.weight"], sd[p + "conv_tran_r.bias"],
+                sd[p + "conv_tran_i.bias"], bn=None if last else packing.bn_affine_from_sd(sd, f"decoder.{i}.1."),
+                transposed=True, up=UPSAMPLE[i], act=L.ACT_NONE if last else L.ACT_LRELU, device=device, want_bf16=bf))
+            self.skip_ca.append(packing.pack_channel_attention(sd, f"skip_attention.{2 * i}.", device))
+            self.skip_sa.append(packing.pack_spatial_attention(sd, f"skip_attention.{2 * i + 1}.", device))
+            if not last:  # decoder_attention[12], [13] never run (c_network.py:218)
+                self.dec_ca.append(packing.pack_channel_attention(sd, f"decoder_attention.{2 * i}.", device))
+                self.dec_sa.append(packing.pack_spatial_attention(sd, f"decoder_attention.{2 * i + 1}.", device))
+        self.lstm = packing.pack_lstm(sd, "lstm.", device)
+        w_r, w_i = sd["fc.fc_r.weight"], sd["fc.fc_i.weight"]
+        self.fc = packing.PackedConv(w_r[:, :, None, None], w_i[:, :, None, None], sd["fc.fc_r.bias"], sd["fc.fc_i.bias"],
+                                     device=device, want_bf16=bf)
+
+
+class ForwardPlan:
+    def __init__(self, packed, batch, n_frames, n_bins=256, variant="dcs", atan2_eps=10e-7, exact_polar=False,
+                 keep_taps=False, want_aux=True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dcsnet_b200.ForwardPlan needs a CUDA device (sm_100a); there is no CPU fallback")
+        L.lib()
+        assert variant in ("dcs", "dc")
+        if n_frames % 8 or n_bins % 128:
+            raise ValueError(f"C_NETWORK needs T % 8 == 0 and F % 128 == 0 (got F={n_bins}, T={n_frames}); "
+                             "the reference fails at the skip torch.cat (c_network.py:214)")
+        self.pk, self.B, self.T, self.F = packed, batch, n_frames, n_bins
+        self.variant, self.eps, self.exact = variant, float(atan2_eps), bool(exact_polar)
+        self.keep_taps, self.want_aux = keep_taps, want_aux
+        dev, Lr = packed.device, packed.L
+        self.tc = packed.mode == "bf16"
+        adt = torch.bfloat16 if self.tc else torch.float32
+        self.adt = adt
+        B, T, F = batch, n_frames, n_bins
+        new = lambda *s, dtype=adt: torch.empty(*s, dtype=dtype, device=dev)
+        self.Y = new(B, F, T, dtype=torch.complex64)
+        self.bn0 = new(B, F, T, 1, 2)
+        self.enc = []
+        H, W = F, T
+        for i in range(Lr):
+            H, W = ops.conv_out_hw(packed.enc[i], H, W)
+            self.enc.append(new(B, H, W, packed.enc[i].cout, 2))
+        S = H * W
+        self.S = S
+        self.lat = new(B, H, W, 128, 2, dtype=torch.float32)
+        self.lstm_ws = torch.empty(ops.clstm_workspace_bytes(B, S) // 4, dtype=torch.float32, device=dev)
+        self.fc = new(B, H, W, packed.fc.cout, 2)
+        self.skip, self.dec, self.datt = [], [], []
+        max_c, max_hw = 128, 0
+        for i in range(Lr):
+            src = self.enc[Lr - 1 - i]
+            self.skip.append(new(*src.shape))
+            H, W = src.shape[1] * UPSAMPLE[i][0], src.shape[2] * UPSAMPLE[i][1]
+            last = i == Lr - 1
+            self.dec.append(new(B, H, W, packed.dec[i].cout, 2, dtype=torch.float32 if last else adt))
+            self.datt.append(None if last else new(B, H, W, packed.dec[i].cout, 2))
+            max_hw = max(max_hw, src.shape[1] * src.shape[2], 0 if last else H * W)
+        self.sums = new(B, max_c, 2, dtype=torch.float32)
+        self.gate = new(B, max_c, 2, dtype=torch.float32)
+        self.stats = new(B, max_hw, 4, dtype=torch.float32)
+        self.clean_spec = new(B, F, T, dtype=torch.complex64)
+        self.noise_spec = new(B, F, T, dtype=torch.complex64) if (want_aux and variant == "dcs") else None
+        self.mask = new(B, F, T, dtype=torch.complex64) if want_aux else None
+        self.net_out = new(B, F, T, dtype=torch.complex64) if want_aux else None
+        self.audio_in = new(B, 32 * (T - 1), dtype=torch.float32)
+        self.audio_out = new(B, 32 * (T - 1), dtype=torch.float32)
+        self.noise_audio = new(B, 32 * (T - 1), dtype=torch.float32) if self.noise_spec is not None else None
+        self.graph = None
+        self.taps = {}
+
+    # ------------------------------------------------------------------ building blocks
+    def _attention(self, x, ca, sa_w7, y):
+        """y = SA(CA(x) * x) * (CA(x) * x)   (c_network.py:208-211 / 219-220)."""
+        B, H, W, Cn, _ = x.shape
+        sums, gate = self.sums[:, :Cn], self.gate[:, :Cn]
+        if not (sums.is_contiguous() and gate.is_contiguous()):
+            sums, gate = self.sums.view(-1)[: B * Cn * 2].view(B, Cn, 2), self.gate.view(-1)[: B * Cn * 2].view(B, Cn, 2)
+        stats = self.stats.view(-1)[: B * H * W * 4].view(B, H * W, 4)
+        sums.zero_()
+        ops.chan_pool(x, sums)
+        ops.chan_gate(sums, H * W, ca, gate)
+        ops.spat_stats(x, gate, stats)
+        ops.spat_apply(x, gate, stats, sa_w7, y)
+        return y
+
+    def _conv(self, pk, src0, src1, dst):
+        use_tc = self.tc and pk.w_tc is not None and (2 * pk.cin) % 16 == 0 and src0.dtype == torch.bfloat16
+        return ops.cconv(pk, src0, src1, dst, use_tc=use_tc)
+
+    def _tap(self, name, t):
+        if self.keep_taps:
+            self.taps[name] = t
+
+    # ------------------------------------------------------------------ the kernel sequence
+    def _network(self):
+        """bn0 -> ... -> decoder[6] raw output (c_network.py:193-222)."""
+        pk, Lr = self.pk, self.pk.L
+        x = self.bn0
+        for i in range(Lr):
+            x = self._conv(pk.enc[i], x, None, self.enc[i])
+            self._tap(f"enc{i}", x)
+        B, H, W, _, _ = x.shape
+        ops.clstm(x.view(B, H * W, x.shape[3], 2), self.lat.view(B, H * W, 128, 2), pk.lstm, self.lstm_ws)
+        self._tap("lstm", self.lat)
+        d = self._conv(pk.fc, self.lat.view(B, 1, H * W, 128, 2), None, self.fc.view(B, 1, H * W, 128, 2)).view(self.fc.shape)
+        self._tap("fc", d)
+        for i in range(Lr):
+            skip = self._attention(self.enc[Lr - 1 - i], pk.skip_ca[i], pk.skip_sa[i], self.skip[i])
+            self._tap(f"skip{i}", skip)
+            d = self._conv(pk.dec[i], d, skip, self.dec[i])
+            if i != Lr - 1:
+                self._tap(f"dec{i}_act", d)
+                d = self._attention(d, pk.dec_ca[i], pk.dec_sa[i], self.datt[i])
+            self._tap(f"dec{i}", d)
+        return d
+
+    def _tail(self, raw):
+        ops.mask_combine(raw, self.Y, self.clean_spec, net_out=self.net_out, mask=self.mask, noise_spec=self.noise_spec,
+                         atan2_eps=self.eps, combine=L.COMBINE_DCS if self.variant == "dcs" else L.COMBINE_DC,
+                         exact_polar=self.exact)
+
+    def _enqueue_from_audio(self, with_noise_audio=False):
+        ops.stft(self.audio_in, self.Y, bn_affine=self.pk.bn0, bn_out=self.bn0)
+        self._tail(self._network())
+        ops.istft(self.clean_spec, self.audio_out, self.eps, self.exact)
+        if with_noise_audio and self.noise_audio is not None:
+            ops.istft(self.noise_spec, self.noise_audio, self.eps, self.exact)
+
+    def _enqueue_from_spec(self):
+        ops.cbn_apply(torch.view_as_real(self.Y).view(self.B, self.F, self.T, 1, 2), self.pk.bn0, self.bn0)
+        self._tail(self._network())
+
+    # ------------------------------------------------------------------ public
+    def capture(self):
+        """Capture the audio->audio pipeline into a CUDA graph (one launch per step afterwards)."""
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            self._enqueue_from_audio()  # warm-up: cudaFuncSetAttribute, lazy module load
+        torch.cuda.current_stream().wait_stream(s)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        before = L.launch_count()
+        with torch.cuda.graph(g):
+            self._enqueue_from_audio()
+        self.graph_launches = L.launch_count() - before
+        self.graph = g
+        return self
+
+    def enhance_audio(self, audio=None):
+        """audio (B, 32(T-1)) fp32 on device (or already in self.audio_in) -> enhanced audio (view of plan buffer)."""
+        if audio is not None:
+            self.audio_in.copy_(audio, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+        else:
+            self._enqueue_from_audio()
+        return self.audio_out
+
+    def enhance_spec(self, spec):
+        """noisy spectrogram (B,F,T) complex64 -> dict of spectrogram-domain outputs (views of plan buffers)."""
+        self.Y.copy_(spec)
+        self._enqueue_from_spec()
+        return dict(net_out=self.net_out, mask=self.mask, noise_spec=self.noise_spec, clean_spec=self.clean_spec)

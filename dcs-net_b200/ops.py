@@ -1,0 +1,142 @@
+"""Thin tensor-level wrappers over the C ABI (include/dcsnet.h).  Every function enqueues sm_100a kernels on the
+current CUDA stream and returns immediately; nothing here computes on the host or falls back to PyTorch ops.
+
+Activation tensors are channels-last complex: a float32 / bfloat16 tensor of shape (B, H, W, C, 2).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import F32, BF16, ACT_NONE, ACT_RELU, ACT_LRELU  # noqa: F401
+
+N_FFT, HOP, BINS = 512, 32, 256
+
+
+def _code(t):
+    return L.dtype_code(t)
+
+
+def stft(audio, spec=None, bn_affine=None, bn_out=None):
+    """(B, L) fp32 -> (B, 256, T) complex64 [data.py:112-134]; optionally also the folded initial BN output."""
+    L.require_cuda(audio)
+    assert audio.dtype == torch.float32 and audio.dim() == 2 and audio.is_contiguous()
+    B, n = audio.shape
+    T = n // HOP + 1
+    if spec is None:
+        spec = torch.empty(B, BINS, T, dtype=torch.complex64, device=audio.device)
+    p = L.StftParams(L.ptr(audio), L.ptr(spec), B, n, T, L.ptr(bn_affine), L.ptr(bn_out),
+                     _code(bn_out) if bn_out is not None else F32)
+    L.check(L.lib().dcs_stft_fwd(C.byref(p), L.stream_ptr()), "dcs_stft_fwd")
+    return spec
+
+
+def istft(spec, audio=None, atan2_eps=1e-6, exact_polar=False):
+    """(B, 256, T) complex64 -> (B, 32 (T-1)) fp32 [network_functions.py:398-401 + 140-150]."""
+    L.require_cuda(spec)
+    assert spec.dtype == torch.complex64 and spec.dim() == 3 and spec.shape[1] == BINS and spec.is_contiguous()
+    B, _, T = spec.shape
+    if audio is None:
+        audio = torch.empty(B, HOP * (T - 1), dtype=torch.float32, device=spec.device)
+    p = L.IstftParams(L.ptr(spec), L.ptr(audio), B, T, float(atan2_eps), int(exact_polar))
+    L.check(L.lib().dcs_istft_fwd(C.byref(p), L.stream_ptr()), "dcs_istft_fwd")
+    return audio
+
+
+def cbn_apply(x, affine, y=None, act=ACT_NONE, out_dtype=None):
+    """Folded eval-mode ComplexBatchNorm2d (+activation) on a channels-last complex tensor (..., C, 2)."""
+    L.require_cuda(x, affine)
+    Cn = x.shape[-2]
+    if y is None:
+        y = torch.empty(x.shape, dtype=out_dtype or x.dtype, device=x.device)
+    p = L.CbnParams(L.ptr(x), L.ptr(y), L.ptr(affine), x.numel() // (2 * Cn), Cn, act, _code(x), _code(y))
+    L.check(L.lib().dcs_cbn_apply(C.byref(p), L.stream_ptr()), "dcs_cbn_apply")
+    return y
+
+
+def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
+    """Complex convolution with packed operands `pk` (packing.PackedConv).  src*: (B,H,W,C,2), dst: (B,OH,OW,Cout,2)."""
+    L.require_cuda(src0, dst)
+    B, H, W, c0, _ = src0.shape
+    c1 = 0 if src1 is None else src1.shape[3]
+    assert c0 + c1 == pk.cin, (c0, c1, pk.cin)
+    _, OH, OW, co, _ = dst.shape
+    assert co == pk.cout
+    p = L.CconvParams()
+    p.src0, p.src1, p.c0, p.c1 = L.ptr(src0), L.ptr(src1), c0, c1
+    p.batch, p.in_h, p.in_w = B, H, W
+    p.out_h, p.out_w, p.cout = OH, OW, co
+    p.up_h, p.up_w = pk.up
+    p.stride_h, p.stride_w = pk.stride
+    p.ntaps = pk.ntaps
+    for i, (a, b) in enumerate(zip(pk.dy, pk.dx)):
+        p.dy[i], p.dx[i] = a, b
+    p.weight = L.ptr(pk.w_tc if use_tc else pk.w_ffma)
+    p.bias = L.ptr(pk.bias)
+    p.act = pk.act
+    p.dst, p.in_dtype, p.out_dtype = L.ptr(dst), _code(src0), _code(dst)
+    p.pool_sums = L.ptr(pool_sums)
+    fn = L.lib().dcs_cconv2d_tc_fwd if use_tc else L.lib().dcs_cconv2d_fwd
+    L.check(fn(C.byref(p), L.stream_ptr()), "dcs_cconv2d_tc_fwd" if use_tc else "dcs_cconv2d_fwd")
+    return dst
+
+
+def conv_out_hw(pk, H, W):
+    if pk.up != (1, 1):
+        return H * pk.up[0], W * pk.up[1]
+    return (H + 2 * (pk.kh // 2) - pk.kh) // pk.stride[0] + 1, (W + 2 * (pk.kw // 2) - pk.kw) // pk.stride[1] + 1
+
+
+def chan_pool(x, sums):
+    B, H, W, Cn, _ = x.shape
+    p = L.ChanPoolParams(L.ptr(x), L.ptr(sums), B, H * W, Cn, _code(x))
+    L.check(L.lib().dcs_chan_pool(C.byref(p), L.stream_ptr()), "dcs_chan_pool")
+
+
+def chan_gate(sums, hw, ca, gate):
+    B = sums.shape[0]
+    p = L.ChanGateParams(L.ptr(sums), 1.0 / hw, L.ptr(gate), B, ca["channels"], ca["reduced"],
+                         L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]))
+    L.check(L.lib().dcs_chan_gate(C.byref(p), L.stream_ptr()), "dcs_chan_gate")
+
+
+def spat_stats(x, gate, stats):
+    B, H, W, Cn, _ = x.shape
+    p = L.SpatStatsParams(L.ptr(x), L.ptr(gate), L.ptr(stats), B, H, W, Cn, _code(x))
+    L.check(L.lib().dcs_spat_stats(C.byref(p), L.stream_ptr()), "dcs_spat_stats")
+
+
+def spat_apply(x, gate, stats, w7, y):
+    B, H, W, Cn, _ = x.shape
+    p = L.SpatApplyParams(L.ptr(x), L.ptr(gate), L.ptr(stats), L.ptr(w7), L.ptr(y), B, H, W, Cn, _code(x), _code(y))
+    L.check(L.lib().dcs_spat_apply(C.byref(p), L.stream_ptr()), "dcs_spat_apply")
+
+
+def clstm_workspace_bytes(B, S, hidden=64):
+    n = L.lib().dcs_clstm_workspace_bytes(B, S, hidden)
+    if n < 0:
+        raise RuntimeError("dcs_clstm_workspace_bytes: unsupported shape")
+    return int(n)
+
+
+def clstm(x, y, w, workspace):
+    """x (B,S,D,2) -> y (B,S,2*hidden,2) fp32.  w = packing.pack_lstm(...)."""
+    B, S, D, _ = x.shape
+    p = L.ClstmParams(L.ptr(x), L.ptr(y), B, S, D, y.shape[2] // 2, _code(x), L.ptr(w["w_ih0"]), L.ptr(w["w_ih1"]),
+                      L.ptr(w["w_hh"]), L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size())
+    L.check(L.lib().dcs_clstm_fwd(C.byref(p), L.stream_ptr()), "dcs_clstm_fwd")
+    return y
+
+
+def mask_combine(net_raw, noisy_spec, clean_spec, net_out=None, mask=None, noise_spec=None, atan2_eps=1e-6,
+                 combine=L.COMBINE_DCS, exact_polar=False):
+    n = noisy_spec.numel()
+    p = L.MaskCombineParams(L.ptr(net_raw), L.ptr(noisy_spec), L.ptr(net_out), L.ptr(mask), L.ptr(noise_spec),
+                            L.ptr(clean_spec), n, float(atan2_eps), combine, int(exact_polar))
+    L.check(L.lib().dcs_mask_combine(C.byref(p), L.stream_ptr()), "dcs_mask_combine")
+    return clean_spec
+
+
+def convert(src, dst):
+    L.check(L.lib().dcs_convert(L.ptr(src), L.ptr(dst), src.numel(), _code(src), _code(dst), L.stream_ptr()), "dcs_convert")
+    return dst

@@ -1,0 +1,139 @@
+"""Host-side weight packing: reference-format parameters -> GEMM-ready operands.
+
+Done once per (state_dict, mode) in float64 on the host, then moved to the device.  Every fold is exact algebra:
+  * complex conv -> real block matrix [[Wr, -Wi], [Wi, Wr]] over interleaved (re, im) channels, with the
+    complexPyTorch bias rule (b_r - b_i, b_r + b_i)                               (apply_complex, Appendix A1)
+  * ConvTranspose2d(k3, s1, p1) -> flipped, in/out-swapped convolution            (c_network.py:135-147)
+  * eval-mode ComplexBatchNorm2d -> per-channel 2x2 affine folded into W and bias (Appendix A3)
+  * nearest up-sampling in front of a 3x3 conv -> sub-pixel phases with pre-summed taps (c_network.py:215)
+"""
+import math
+
+import torch
+
+BN_EPS = 1e-5
+
+
+def bn_affine(weight, bias, running_mean, running_covar, eps=BN_EPS):
+    """Eval-mode ComplexBatchNorm2d as y = A [re; im] + c.  Returns (A (C,2,2), c (C,2)) in float64."""
+    w, b = weight.double(), bias.double()
+    cov = running_covar.double()
+    mu = torch.stack([running_mean.real.double(), running_mean.imag.double()], dim=1)
+    Crr, Cii, Cri = cov[:, 0] + eps, cov[:, 1] + eps, cov[:, 2]
+    s = torch.sqrt(Crr * Cii - Cri * Cri)
+    t = torch.sqrt(Crr + Cii + 2 * s)
+    ist = 1.0 / (s * t)
+    R = torch.stack([torch.stack([(Cii + s) * ist, -Cri * ist], 1), torch.stack([-Cri * ist, (Crr + s) * ist], 1)], 1)
+    Wm = torch.stack([torch.stack([w[:, 0], w[:, 2]], 1), torch.stack([w[:, 2], w[:, 1]], 1)], 1)
+    A = Wm @ R
+    c = b - (A @ mu[:, :, None])[:, :, 0]
+    return A, c
+
+
+def bn_affine_from_sd(sd, prefix):
+    return bn_affine(sd[prefix + "weight"], sd[prefix + "bias"], sd[prefix + "running_mean"], sd[prefix + "running_covar"])
+
+
+def affine6(A, c):
+    """(C,2,2),(C,2) -> (C,6) fp32 rows A00 A01 A10 A11 c0 c1 (dcs_cbn_apply / dcs_stft_fwd.bn_affine)."""
+    return torch.cat([A.reshape(-1, 4), c], dim=1).float().contiguous()
+
+
+def _phase_taps(k, up):
+    """Rows of a k-tap 1-D kernel (pad k//2) applied after nearest x`up`: per phase, {source offset: [taps]}."""
+    pad = k // 2
+    out = []
+    for ph in range(up):
+        groups = {}
+        for kk in range(k):
+            d = math.floor((ph + kk - pad) / up)
+            groups.setdefault(d, []).append(kk)
+        out.append(sorted(groups.items()))
+    return out
+
+
+class PackedConv:
+    """GEMM operands of one complex convolution layer (see include/dcsnet.h: dcs_cconv_params)."""
+
+    def __init__(self, w_r, w_i, b_r=None, b_i=None, bn=None, transposed=False, stride=(1, 1), up=(1, 1),
+                 act=0, device="cpu", want_bf16=False):
+        w_r, w_i = w_r.detach().double().cpu(), w_i.detach().double().cpu()
+        if transposed:  # (Cin, Cout, k, k) -> equivalent conv weight (Cout, Cin, k, k), spatially flipped
+            w_r = w_r.permute(1, 0, 2, 3).flip(2, 3)
+            w_i = w_i.permute(1, 0, 2, 3).flip(2, 3)
+        cout, cin, kh, kw = w_r.shape
+        # real block weight M[(co,ro), (ci,ri), ky, kx]
+        M = torch.zeros(cout, 2, cin, 2, kh, kw, dtype=torch.float64)
+        M[:, 0, :, 0], M[:, 0, :, 1] = w_r, -w_i
+        M[:, 1, :, 0], M[:, 1, :, 1] = w_i, w_r
+        bias = torch.zeros(cout, 2, dtype=torch.float64)
+        if b_r is not None:
+            b_r, b_i = b_r.detach().double().cpu(), b_i.detach().double().cpu()
+            bias[:, 0], bias[:, 1] = b_r - b_i, b_r + b_i
+        if bn is not None:
+            A, c = bn
+            M = torch.einsum("oab,obcdyx->oacdyx", A, M)
+            bias = torch.einsum("oab,ob->oa", A, bias) + c
+        self.cin, self.cout, self.kh, self.kw = cin, cout, kh, kw
+        self.stride, self.up, self.act = tuple(stride), tuple(up), act
+        rows, cols = _phase_taps(kh, up[0]), _phase_taps(kw, up[1])
+        self.phases = up[0] * up[1]
+        self.ntaps = len(rows[0]) * len(cols[0])
+        assert self.phases * self.ntaps <= 64
+        dy, dx, mats = [], [], []
+        for ph in range(up[0]):
+            for pw in range(up[1]):
+                for d_y, kys in rows[ph]:
+                    for d_x, kxs in cols[pw]:
+                        dy.append(d_y)
+                        dx.append(d_x)
+                        mats.append(M[:, :, :, :, kys][..., kxs].sum(dim=(4, 5)))  # (co,2,ci,2)
+        self.dy, self.dx = dy, dx
+        N, C2 = 2 * cout, 2 * cin
+        self.n_pad = (N + 15) // 16 * 16
+        Wt = torch.stack(mats, 0).reshape(self.phases, self.ntaps, N, C2)  # [p][t][n][k]
+        Wp = torch.zeros(self.phases, self.ntaps, self.n_pad, C2, dtype=torch.float64)
+        Wp[:, :, :N] = Wt
+        # FFMA operand: [p][t][k][n_pad] fp32 ;  tcgen05 operand: [p][n_pad][t*C2 + k] bf16 (K contiguous)
+        self.w_ffma = Wp.permute(0, 1, 3, 2).contiguous().float().to(device)
+        self.w_tc = None
+        if want_bf16:
+            K = self.ntaps * C2
+            self.k_pad = (K + 63) // 64 * 64  # one pipeline stage of the tcgen05 kernel = 64 bf16 of K
+            wt = torch.zeros(self.phases, self.n_pad, self.k_pad, dtype=torch.float64)
+            wt[:, :, :K] = Wp.permute(0, 2, 1, 3).reshape(self.phases, self.n_pad, K)
+            self.w_tc = wt.to(torch.bfloat16).contiguous().to(device)
+        b = torch.zeros(self.n_pad, dtype=torch.float64)
+        b[:N] = bias.reshape(-1)
+        self.bias = b.float().to(device)
+
+
+def pack_lstm(sd, prefix, device, hidden=64, layers=2):
+    """ComplexLSTM weights (c_network.py:17-20) -> (w_ih0 [D][1024], w_ih1 [2][128][512], w_hh [2][2][2][256][64],
+    bias [1024 + 2*512]) as consumed by dcs_clstm_fwd.  Column order n = lstm*512 + dir*256 + gate."""
+    assert layers == 2
+    names = ("real_lstm", "imag_lstm")
+    sfx = ("", "_reverse")
+    g = lambda k: sd[prefix + k].detach().double().cpu()
+    w0 = torch.cat([g(f"{n}.weight_ih_l0{s}") for n in names for s in sfx], 0)           # (1024, D)
+    b0 = torch.cat([g(f"{n}.bias_ih_l0{s}") + g(f"{n}.bias_hh_l0{s}") for n in names for s in sfx], 0)
+    w1 = torch.stack([torch.cat([g(f"{n}.weight_ih_l1{s}") for s in sfx], 0).t() for n in names], 0)  # (2,128,512)
+    b1 = torch.cat([g(f"{n}.bias_ih_l1{s}") + g(f"{n}.bias_hh_l1{s}") for n in names for s in sfx], 0)
+    whh = torch.stack([torch.stack([torch.stack([g(f"{n}.weight_hh_l{l}{s}") for s in sfx], 0) for n in names], 0)
+                       for l in range(2)], 0)                                                # (2,2,2,256,64)
+    f = lambda t: t.contiguous().float().to(device)
+    return dict(w_ih0=f(w0.t()), w_ih1=f(w1), w_hh=f(whh), bias=f(torch.cat([b0, b1], 0)))
+
+
+def pack_channel_attention(sd, prefix, device):
+    f = lambda k: sd[prefix + k].detach().float().reshape(sd[prefix + k].shape[0], -1).contiguous().to(device)
+    d = dict(w1_r=f("fc.0.conv_r.weight"), w1_i=f("fc.0.conv_i.weight"),
+             w2_r=f("fc.2.conv_r.weight"), w2_i=f("fc.2.conv_i.weight"))
+    d["reduced"], d["channels"] = d["w1_r"].shape
+    return d
+
+
+def pack_spatial_attention(sd, prefix, device):
+    wr, wi = sd[prefix + "conv1.conv_r.weight"], sd[prefix + "conv1.conv_i.weight"]
+    assert tuple(wr.shape) == (1, 2, 7, 7), "only spatial_attention_kernel_size = 7 is built"
+    return torch.cat([wr.detach().float().reshape(-1), wi.detach().float().reshape(-1)]).contiguous().to(device)

@@ -1,0 +1,157 @@
+/*
+ * dcsnet.h — C ABI of libdcsnet_sm100a.so, the B200-native (sm_100a) replacement for the DCS-Net forward
+ * hot path:  STFT -> complex encoder/decoder (C_NETWORK.forward) -> bounded mask / subtraction -> iSTFT.
+ *
+ * The reference (jackhwalters/DCS-Net) is pure Python/PyTorch and has NO FFI of its own; every GPU op on this
+ * path is a torch-1.9 ATen dispatch (cuDNN / cuFFT / eltwise).  Each entry point below therefore cites the
+ * reference *call site* whose ATen dispatches it replaces (file:line under /root/reference), and
+ * INTEGRATION.md shows the ctypes stub a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain pointers + sizes only; every pointer is a DEVICE pointer owned by the caller (PyTorch allocates);
+ *     the library allocates nothing persistent on the device and never synchronises.
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); entries are CUDA-graph capturable.
+ *   - return 0 on success; non-zero = error (negative: argument/shape error, positive: cudaError_t);
+ *     message via dcs_last_error_string() (thread-local).  There is no CPU fallback.
+ *   - activation tensors are "channels-last complex": (B, H, W, C, 2) with the (re, im) pair innermost, which
+ *     is the memory of a torch complex64 NCHW tensor in torch.channels_last format (dtype DCS_F32) or its
+ *     bf16 twin (dtype DCS_BF16, used by the tcgen05 tensor-core mode).
+ *   - spectrograms at the boundary use the reference layout (B, F=256, T) complex64, T contiguous.
+ */
+#ifndef DCSNET_H_
+#define DCSNET_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCS_ABI_VERSION 1
+
+enum { DCS_F32 = 0, DCS_BF16 = 1 };
+enum { DCS_ACT_NONE = 0, DCS_ACT_RELU = 1, DCS_ACT_LRELU = 2 }; /* ComplexReLU / ComplexLReLU(0.01) */
+enum { DCS_COMBINE_DCS = 0, DCS_COMBINE_DC = 1 };                /* S = Y - Y*M   |   S = Y*M */
+
+#define DCS_MAX_TAPS 64
+
+int dcs_abi_version(void);
+const char* dcs_last_error_string(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+uint64_t dcs_launch_count(void);
+
+/* ---- a1: STFT front-end.  Replaces torch.stft(n_fft=512, hop=32, win=512, hann, normalized, center) [1:257]
+ *      at data.py:112-134 (config.py:72-77).  audio (B, L) fp32 -> spec (B, 256, T) complex64, T = L/32 + 1.
+ *      If bn_affine != NULL (6 floats A00 A01 A10 A11 c0 c1: the folded eval-mode `initial_batchnorm`,
+ *      c_network.py:190) a second tensor bn_out (B,256,T,1) of dtype bn_dtype receives A*[re;im]+c. */
+typedef struct {
+  const float* audio; float* spec; int batch; int length; int n_frames;
+  const float* bn_affine; void* bn_out; int bn_dtype;
+} dcs_stft_params;
+int dcs_stft_fwd(const dcs_stft_params* p, void* stream);
+
+/* ---- a15: iSTFT back-end.  Replaces the polar round trip (network_functions.py:398-401) + mag_phase_2_wave
+ *      (network_functions.py:140-150): abs / atan2(im, re+eps) / mag*cos / mag*sin, zero row appended at the END
+ *      of the frequency axis, torch.istft(n_fft=512, hop=32, hann, normalized).  spec (B,256,T) complex64 ->
+ *      audio (B, 32*(T-1)) fp32.  exact_polar=1 evaluates atan2f/cosf/sinf literally, 0 uses the algebraically
+ *      identical (re+eps, im)/hypot form. */
+typedef struct {
+  const float* spec; float* audio; int batch; int n_frames; float atan2_eps; int exact_polar;
+} dcs_istft_params;
+int dcs_istft_fwd(const dcs_istft_params* p, void* stream);
+
+/* ---- a3: ComplexBatchNorm2d, eval mode, folded to a per-channel 2x2 affine (complexPyTorch 0.3; used at
+ *      c_network.py:101,113,148) + optional activation (a5).  x,y channels-last complex, n_pix = B*H*W.
+ *      affine: C x 6 floats (A00 A01 A10 A11 c0 c1). */
+typedef struct {
+  const void* x; void* y; const float* affine; int64_t n_pix; int channels; int act; int in_dtype; int out_dtype;
+} dcs_cbn_params;
+int dcs_cbn_apply(const dcs_cbn_params* p, void* stream);
+
+/* ---- a4 / a12 / a8 / a11: complex convolution as ONE real implicit GEMM  (M = pixels, N = 2*Cout,
+ *      K = taps * 2*Cin).  Replaces apply_complex over nn.Conv2d (encoder, c_network.py:107-112), over
+ *      nn.ConvTranspose2d k3 s1 p1 (decoder, c_network.py:135-147; expressed as the flipped convolution), over
+ *      nn.Linear (fc, c_network.py:202, as a 1x1 convolution), together with the skip torch.cat and
+ *      complex_upsample that precede each decoder layer (c_network.py:214-216): the K loop walks the two
+ *      sources src0 | src1 so the concatenation never exists, and nearest up-sampling is folded into
+ *      `phases` sub-pixel classes with pre-summed taps.  Bias rule (b_r-b_i, b_r+b_i), the eval-mode BN
+ *      affine and the activation are folded into `weight`/`bias`/`act` by the host-side packer.
+ *
+ *      Geometry: output pixel (oy, ox) = (j*up_h + ph, i*up_w + pw) for phase p = ph*up_w + pw and
+ *      (j, i) in [0,out_h/up_h) x [0,out_w/up_w); tap t of phase p reads source pixel
+ *      (j*stride_h + dy[p*ntaps+t], i*stride_w + dx[p*ntaps+t]), zero outside [0,in_h) x [0,in_w).
+ *      weight: FFMA path  fp32 [phases][ntaps][2*(c0+c1)][2*cout]   (N contiguous)
+ *              tcgen05    bf16 [phases][n_pad][ntaps*2*(c0+c1)]      (K contiguous), n_pad = max(16, 2*cout)
+ *      bias:   fp32 [2*cout] added before `act`.
+ *      pool_sums (optional, fp32 [B][2*cout], pre-zeroed): per-(b, channel) sums of the epilogue output, i.e. the
+ *      numerator of ComplexAdaptiveAvgPool2d(1) for the channel attention that follows (c_network.py:219). */
+typedef struct {
+  const void* src0; const void* src1; int c0; int c1;
+  int batch; int in_h; int in_w;
+  int out_h; int out_w; int cout;
+  int up_h; int up_w; int stride_h; int stride_w;
+  int ntaps; int8_t dy[DCS_MAX_TAPS]; int8_t dx[DCS_MAX_TAPS];
+  const void* weight; const float* bias; int act;
+  void* dst; int in_dtype; int out_dtype;
+  float* pool_sums;
+} dcs_cconv_params;
+int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream);    /* fp32 CUDA-core path (<=1e-5 mode) */
+int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (bf16 mode)  */
+
+/* ---- a9: ComplexChannelAttention (c_network.py:53-69; pools network_functions.py:114-138 — the "max" pool is
+ *      an average pool, so the gate is sigmoid_c(2*fc(avg))).
+ *      dcs_chan_pool: sums[b][c] (complex) = sum over H*W of x (channels-last).  sums must be pre-zeroed.
+ *      dcs_chan_gate: gate[b][c] = sigmoid_c( 2 * W2 * crelu( W1 * (sums/hw) ) ), W1: (Cr,C) W2: (C,Cr) complex,
+ *      given as separate real/imag fp32 matrices (the conv_r / conv_i 1x1 weights, no bias). */
+typedef struct { const void* x; float* sums; int batch; int hw; int channels; int dtype; } dcs_chan_pool_params;
+int dcs_chan_pool(const dcs_chan_pool_params* p, void* stream);
+typedef struct {
+  const float* sums; float inv_hw; float* gate; int batch; int channels; int reduced;
+  const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i;
+} dcs_chan_gate_params;
+int dcs_chan_gate(const dcs_chan_gate_params* p, void* stream);
+
+/* ---- a10: ComplexSpatialAttention (c_network.py:71-84) applied to u = gate_c * x (complex product, c_network.py
+ *      :209,219).  dcs_spat_stats: stats[b][h][w] = { mean_c(u) (complex), max_c Re(u), max_c Im(u) } (4 floats).
+ *      dcs_spat_apply: g = sigmoid_c( conv7x7_complex(stats) ), y = g * u (c_network.py:210-211, 220).
+ *      w7: fp32 [2 (r,i)][2 (in ch: mean,max)][7][7]  = conv1.conv_r.weight, conv1.conv_i.weight. */
+typedef struct {
+  const void* x; const float* chan_gate; float* stats; int batch; int h; int w; int channels; int dtype;
+} dcs_spat_stats_params;
+int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream);
+typedef struct {
+  const void* x; const float* chan_gate; const float* stats; const float* w7; void* y;
+  int batch; int h; int w; int channels; int in_dtype; int out_dtype;
+} dcs_spat_apply_params;
+int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream);
+
+/* ---- a7: ComplexLSTM (c_network.py:12-51): real_lstm / imag_lstm = nn.LSTM(128->64, 2 layers, bidirectional),
+ *      out = (R(re) - I(im)) + j (R(im) + I(re)).  x (B,S,D) complex channels-last (the latent, sequence index
+ *      = h*W'+w, c_network.py:200) -> y (B,S,2*hidden) complex fp32.
+ *      Weights: per lstm l in {real,imag}, layer in {0,1}, dir in {fwd,rev}: w_ih (4H, Din), w_hh (4H, H),
+ *      bias (4H) = b_ih + b_hh; packed contiguously as [layer][lstm][dir].  workspace: see dcs_clstm_workspace_bytes. */
+typedef struct {
+  const void* x; float* y; int batch; int seq; int in_dim; int hidden; int in_dtype;
+  const float* w_ih0; const float* w_ih1; const float* w_hh; const float* bias;
+  void* workspace; int64_t workspace_bytes;
+} dcs_clstm_params;
+int64_t dcs_clstm_workspace_bytes(int batch, int seq, int hidden);
+int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream);
+
+/* ---- a13 / a14: tail.  net_raw = decoder[6] output (B,256,T) complex64 (c_network.py:216,224);
+ *      mask1 = bound_cRM(net_raw) (c_network.py:225) ; mask2 = bound_cRM(mask1) (network_functions.py:394);
+ *      prod = Y (.) mask2 (complex_mat_mult, network_functions.py:90-96,396); dcs: S = Y - prod (397),
+ *      dc: S = prod (434).  Any of net_out / mask / noise_spec may be NULL. */
+typedef struct {
+  const float* net_raw; const float* noisy_spec; float* net_out; float* mask; float* noise_spec; float* clean_spec;
+  int64_t n; float atan2_eps; int combine; int exact_polar;
+} dcs_mask_combine_params;
+int dcs_mask_combine(const dcs_mask_combine_params* p, void* stream);
+
+/* ---- layout helpers for the layer-wise drop-in modules: fp32 <-> bf16 copies of channels-last activations */
+int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_dtype, int out_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DCSNET_H_ */

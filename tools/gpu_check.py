@@ -1,0 +1,163 @@
+"""Per-stage parity report of the CUDA path against the oracle (developer tool; run on a B200 via gpurun).
+
+    python tools/gpu_check.py stft|istft|fp32|bf16|tcunit|time [B] [T]
+
+Each part is meant to run in its own process (a faulting kernel poisons the CUDA context).
+"""
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import dcsnet_b200 as D  # noqa: E402
+from dcsnet_b200 import ops, packing  # noqa: E402
+from oracle import dcsnet_oracle as O, synthetic_weights as SW  # noqa: E402
+
+
+def rel(a, b):
+    a, b = a.detach().cpu(), b.detach().cpu()
+    if a.is_complex():
+        a, b = torch.view_as_real(a), torch.view_as_real(b)
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def cl_to_nchw(t):
+    """(B,H,W,C,2) real -> complex NCHW on CPU"""
+    return torch.view_as_complex(t.detach().float().cpu().contiguous()).permute(0, 3, 1, 2)
+
+
+def part_stft(B, T):
+    L = 32 * (T - 1)
+    _, _, noisy = O.synthetic_audio(B, L)
+    ref = O.stft(noisy)
+    got = ops.stft(noisy.cuda())
+    torch.cuda.synchronize()
+    print(json.dumps({"part": "stft", "B": B, "T": T, "rel": rel(got, ref)}))
+
+
+def part_istft(B, T):
+    g = torch.Generator().manual_seed(3)
+    spec = torch.complex(torch.randn(B, 256, T, generator=g), torch.randn(B, 256, T, generator=g)) * 0.3
+    ref = O.spec_to_wave(spec)
+    for exact in (False, True):
+        got = ops.istft(spec.cuda(), atan2_eps=O.HPARAMS["atan2_eps"], exact_polar=exact)
+        torch.cuda.synchronize()
+        print(json.dumps({"part": "istft", "exact": exact, "B": B, "T": T, "rel": rel(got, ref)}))
+
+
+def part_net(mode, B, T):
+    sd = SW.make_state_dict(0)
+    L = 32 * (T - 1)
+    _, _, noisy = O.synthetic_audio(B, L)
+    taps = {}
+    spec = O.stft(noisy)
+    ref = O.enhance_spec(sd, spec, taps=taps)
+    ref_audio = O.spec_to_wave(ref["clean_spec"])
+    pk = D.PackedNet(sd, "cuda", mode)
+    plan = D.ForwardPlan(pk, B, T, keep_taps=True)
+    out = plan.enhance_audio(noisy.cuda())
+    torch.cuda.synchronize()
+    res = {"part": mode, "B": B, "T": T}
+    res["Y"] = rel(plan.Y, spec)
+    res["bn0"] = rel(cl_to_nchw(plan.bn0), taps["bn0"])
+    for k, v in plan.taps.items():
+        if k in ("lstm", "fc"):
+            t = torch.view_as_complex(v.detach().float().cpu().contiguous())
+            t = t.reshape(B, -1, 128)
+            res[k] = rel(t, taps[k])
+        else:
+            res[k] = rel(cl_to_nchw(v), taps[k])
+    squeeze = lambda t: t.squeeze(0) if B == 1 else t
+    res["net_out"] = rel(squeeze(plan.net_out), ref["net_out"])
+    res["mask"] = rel(squeeze(plan.mask), ref["mask"])
+    res["clean_spec"] = rel(plan.clean_spec, ref["clean_spec"])
+    res["noise_spec"] = rel(plan.noise_spec, ref["noise_spec"])
+    res["clean_audio"] = rel(out, ref_audio)
+    clean = O.synthetic_audio(B, L)[0]
+    res["d_sisdr_db"] = abs(float(O.si_snr(clean, out.cpu()) - O.si_snr(clean, ref_audio)))
+    print(json.dumps(res))
+
+
+def part_tcunit(B, T):
+    """tcgen05 conv vs the FFMA conv on identical bf16 inputs, layer by layer (isolates the tensor-core kernel)."""
+    sd = SW.make_state_dict(0)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    g = torch.Generator().manual_seed(5)
+    H, W = 256, T
+    shapes = []
+    for i in range(7):
+        cin = pk.enc[i].cin
+        shapes.append(("enc%d" % i, pk.enc[i], (B, H, W, cin), None))
+        H, W = ops.conv_out_hw(pk.enc[i], H, W)
+    Hs, Ws = [256, 128, 64, 32, 16, 8, 4, 2], None
+    H, W = 2, T // 8
+    for i in range(7):
+        c = pk.dec[i].cin // 2
+        shapes.append(("dec%d" % i, pk.dec[i], (B, H, W, c), (B, H, W, c)))
+        H, W = H * pk.dec[i].up[0], W * pk.dec[i].up[1]
+    for name, p, s0, s1 in shapes:
+        if (2 * p.cin) % 16 or (2 * s0[3]) % 16:
+            print(json.dumps({"part": "tcunit", "layer": name, "skipped": "2*Cin not a multiple of 16"}))
+            continue
+        x0 = torch.randn(*s0, 2, generator=g).cuda().bfloat16()
+        x1 = torch.randn(*s1, 2, generator=g).cuda().bfloat16() if s1 else None
+        oh, ow = ops.conv_out_hw(p, s0[1], s0[2])
+        ref = torch.empty(B, oh, ow, p.cout, 2, device="cuda", dtype=torch.float32)
+        got = torch.full((B, oh, ow, p.cout, 2), float("nan"), device="cuda", dtype=torch.float32 if name == "dec6" else torch.bfloat16)
+        ops.cconv(p, x0, x1, ref, use_tc=False)
+        # the FFMA reference uses fp32 weights; round them like the tensor-core operand for an apples-to-apples check
+        ops.cconv(p, x0, x1, got, use_tc=True)
+        torch.cuda.synchronize()
+        print(json.dumps({"part": "tcunit", "layer": name, "rel": rel(got.float(), ref), "nan": int(torch.isnan(got.float()).sum())}))
+
+
+def part_time(mode, B, T):
+    sd = SW.make_state_dict(0)
+    pk = D.PackedNet(sd, "cuda", mode)
+    plan = D.ForwardPlan(pk, B, T, want_aux=False)
+    _, _, noisy = O.synthetic_audio(B, 32 * (T - 1))
+    plan.audio_in.copy_(noisy.cuda())
+    for _ in range(2):
+        plan.enhance_audio()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    n = 5
+    for _ in range(n):
+        plan.enhance_audio()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(json.dumps({"part": "time", "mode": mode, "B": B, "T": T, "ms": ms, "audio_s_per_s": B * O.audio_seconds(T) / (ms / 1e3)}))
+    plan.capture()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(n):
+        plan.enhance_audio()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    print(json.dumps({"part": "time_graph", "mode": mode, "B": B, "T": T, "ms": ms, "launches": plan.graph_launches,
+                      "audio_s_per_s": B * O.audio_seconds(T) / (ms / 1e3)}))
+
+
+if __name__ == "__main__":
+    part = sys.argv[1]
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    T = int(sys.argv[3]) if len(sys.argv) > 3 else 256
+    t0 = time.time()
+    if part == "stft":
+        part_stft(B, T)
+    elif part == "istft":
+        part_istft(B, T)
+    elif part in ("fp32", "bf16"):
+        part_net(part, B, T)
+    elif part == "tcunit":
+        part_tcunit(B, T)
+    elif part.startswith("time"):
+        part_time(part.split("_")[1], B, T)
+    print(f"# {part} done in {time.time() - t0:.1f}s", file=sys.stderr)
