@@ -3,8 +3,18 @@
 
 Host code is Python/PyTorch (device memory, streams, torch.distributed plumbing); all arithmetic on the path runs in
 hand-written CUDA kernels reached through the C ABI in include/dcsnet.h.  There is no CPU or PyTorch-op fallback.
-"""
-from . import _lib, ops, packing, engine  # noqa: F401
-from .engine import ForwardPlan, PackedNet  # noqa: F401
 
-__all__ = ["ops", "packing", "engine", "ForwardPlan", "PackedNet"]
+Reference-facing modules (same names as the reference's files):
+    dcsnet_b200.complexLayers / complexFunctions   <- complexPyTorch 0.3 (c_network.py:5-7)
+    dcsnet_b200.network_functions                  <- network_functions.py (layer / mask / iSTFT part)
+    dcsnet_b200.c_network                          <- c_network.py (ComplexLSTM, attention, C_NETWORK)
+    dcsnet_b200.config                             <- config.py (hparams, Config)
+"""
+from . import _lib, ops, packing, engine, pipeline  # noqa: F401
+from .engine import ForwardPlan, PackedNet  # noqa: F401
+from .pipeline import Enhancer, shard_range, split_windows, frames_for, WINDOW_4S, WINDOW_REF  # noqa: F401
+from . import complexFunctions, complexLayers, network_functions, config, c_network  # noqa: F401
+from .c_network import C_NETWORK  # noqa: F401
+
+__all__ = ["ops", "packing", "engine", "pipeline", "ForwardPlan", "PackedNet", "Enhancer", "C_NETWORK",
+           "complexLayers", "complexFunctions", "network_functions", "c_network", "config"]

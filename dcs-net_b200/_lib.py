@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcsnet_sm100a.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_RELU, ACT_LRELU = 0, 1, 2
+ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 COMBINE_DCS, COMBINE_DC = 0, 1
 MAX_TAPS = 64
 
@@ -26,7 +26,8 @@ class StftParams(C.Structure):
 
 
 class IstftParams(C.Structure):
-    _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i)]
+    _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
+                ("mag", _vp), ("phase", _vp)]
 
 
 class CbnParams(C.Structure):
@@ -61,7 +62,8 @@ class SpatStatsParams(C.Structure):
 
 class SpatApplyParams(C.Structure):
     _fields_ = [("x", _vp), ("chan_gate", _vp), ("stats", _vp), ("w7", _vp), ("y", _vp),
-                ("batch", _i), ("h", _i), ("w", _i), ("channels", _i), ("in_dtype", _i), ("out_dtype", _i)]
+                ("batch", _i), ("h", _i), ("w", _i), ("channels", _i), ("in_dtype", _i), ("out_dtype", _i),
+                ("gate_out", _vp)]
 
 
 class ClstmParams(C.Structure):
@@ -92,6 +94,10 @@ SYMBOLS = {
     "dcs_clstm_workspace_bytes": (_i64, [_i, _i, _i]),
     "dcs_clstm_fwd": (_i, [C.POINTER(ClstmParams), _vp]),
     "dcs_mask_combine": (_i, [C.POINTER(MaskCombineParams), _vp]),
+    "dcs_bound_crm": (_i, [_vp, _vp, _i64, _f, _i, _vp]),
+    "dcs_cmul": (_i, [_vp, _vp, _vp, _i64, _vp]),
+    "dcs_crm": (_i, [_vp, _vp, _vp, _i64, _f, _vp]),
+    "dcs_upsample_nearest": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_convert": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
 }
 

@@ -83,7 +83,8 @@ __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x
   // G lanes cooperate on one pixel (G = min(32, C)); each lane strides over channels
   __shared__ float2 gs[256];
   const int b = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) gs[c] = reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c];
+  for (int c = threadIdx.x; c < C; c += blockDim.x)
+    gs[c] = gate ? reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c] : make_float2(1.f, 0.f);
   __syncthreads();
   const int sub = threadIdx.x % G, grp = threadIdx.x / G, groups = 256 / G;
   const T* xb = x + (int64_t)b * hw * C * 2;
@@ -110,7 +111,7 @@ constexpr int kSaTH = 4, kSaTW = 64, kSaK = 7, kSaR = 3;
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gate,
                                                          const float4* __restrict__ stats, const float* __restrict__ w7,
-                                                         TO* __restrict__ y, int H, int W, int C) {
+                                                         TO* __restrict__ y, float2* __restrict__ gate_out, int H, int W, int C) {
   __shared__ float4 st[kSaTH + 2 * kSaR][kSaTW + 2 * kSaR];
   __shared__ float2 sg[kSaTH][kSaTW];
   __shared__ float2 gs[256];
@@ -118,7 +119,8 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * kSaTH, x0 = blockIdx.x * kSaTW;
   for (int i = threadIdx.x; i < 196; i += 256) wsm[i] = w7[i];
-  for (int c = threadIdx.x; c < C; c += 256) gs[c] = reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c];
+  for (int c = threadIdx.x; c < C; c += 256)
+    gs[c] = gate ? reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c] : make_float2(1.f, 0.f);
   for (int i = threadIdx.x; i < (kSaTH + 2 * kSaR) * (kSaTW + 2 * kSaR); i += 256) {
     const int r = i / (kSaTW + 2 * kSaR), cidx = i % (kSaTW + 2 * kSaR);
     const int yy = y0 + r - kSaR, xx = x0 + cidx - kSaR;
@@ -143,8 +145,11 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
         im += a0 * s.y + a1 * s.w + b0 * s.x + b1 * s.z;
       }
     }
-    sg[r][cidx] = make_float2(sigmoidf_(re), sigmoidf_(im));
+    const float2 gv = make_float2(sigmoidf_(re), sigmoidf_(im));
+    sg[r][cidx] = gv;
+    if (gate_out && y0 + r < H && x0 + cidx < W) gate_out[((int64_t)b * H + y0 + r) * W + x0 + cidx] = gv;
   }
+  if (!y) return;
   __syncthreads();
   for (int r = 0; r < kSaTH; ++r) {
     const int yy = y0 + r;
@@ -190,7 +195,7 @@ extern "C" int dcs_chan_gate(const dcs_chan_gate_params* p, void* stream) {
 }
 
 extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
-  DCS_REQUIRE(p && p->x && p->chan_gate && p->stats, "dcs_spat_stats: null pointer");
+  DCS_REQUIRE(p && p->x && p->stats, "dcs_spat_stats: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && pow2(p->channels) && p->channels <= 256, "dcs_spat_stats: bad shape");
   const int hw = p->h * p->w;
   const int G = min(32, p->channels), groups = 256 / G;
@@ -205,13 +210,13 @@ extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
 }
 
 extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
-  DCS_REQUIRE(p && p->x && p->chan_gate && p->stats && p->w7 && p->y, "dcs_spat_apply: null pointer");
+  DCS_REQUIRE(p && p->x && p->stats && p->w7 && (p->y || p->gate_out), "dcs_spat_apply: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && p->channels > 0 && p->channels <= 256, "dcs_spat_apply: bad shape");
   DCS_REQUIRE(p->batch <= 65535, "dcs_spat_apply: batch too large for grid.z");
   dim3 grid((p->w + kSaTW - 1) / kSaTW, (p->h + kSaTH - 1) / kSaTH, p->batch);
   cudaStream_t s = (cudaStream_t)stream;
   const float4* st = (const float4*)p->stats;
-#define DCS_SA(TI, TO) spat_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, p->h, p->w, p->channels)
+#define DCS_SA(TI, TO) spat_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels)
   if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_SA(float, float);
   else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_SA(float, __nv_bfloat16);
   else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_SA(__nv_bfloat16, float);

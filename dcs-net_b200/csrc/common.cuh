@@ -67,11 +67,12 @@ template <> struct Elem<__nv_bfloat16> {
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }
+__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == DCS_ACT_RELU) return fmaxf(v, 0.f);
   if (act == DCS_ACT_LRELU) return v > 0.f ? v : 0.01f * v;
+  if (act == DCS_ACT_SIGMOID) return sigmoidf_(v);
   return v;
 }
-__device__ __forceinline__ float sigmoidf_(float v) { return 1.f / (1.f + expf(-v)); }
 
 }  // namespace dcs

@@ -80,6 +80,35 @@ __global__ void mask_combine_kernel(const dcs_mask_combine_params p) {
   }
 }
 
+__global__ void bound_crm_kernel(const float2* __restrict__ x, float2* __restrict__ y, int64_t n, float eps, int exact) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = bound_crm(__ldg(x + i), eps, exact != 0);
+}
+__global__ void cmul_kernel(const float2* __restrict__ a, const float2* __restrict__ b, float2* __restrict__ y, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = cmul(__ldg(a + i), __ldg(b + i));
+}
+// cRM (network_functions.py:62-75): M = S * conj(Y) / (|Y|^2 + eps)
+__global__ void crm_kernel(const float2* __restrict__ s, const float2* __restrict__ yn, float2* __restrict__ m, int64_t n, float eps) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 S = __ldg(s + i), Y = __ldg(yn + i);
+    const float den = Y.x * Y.x + Y.y * Y.y + eps;
+    m[i] = make_float2((Y.x * S.x + Y.y * S.y) / den, (Y.x * S.y - Y.y * S.x) / den);
+  }
+}
+template <typename T>
+__global__ void upsample_kernel(const T* __restrict__ x, T* __restrict__ y, int B, int H, int W, int C, int uh, int uw) {
+  const int64_t n = (int64_t)B * H * uh * W * uw * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int ox = (int)(r % (W * uw)); r /= (W * uw);
+    const int oy = (int)(r % (H * uh));
+    const int b = (int)(r / (H * uh));
+    Elem<T>::stc(y, i, Elem<T>::ldc(x, (((int64_t)b * H + oy / uh) * W + ox / uw) * C + c));
+  }
+}
+
 template <typename TI, typename TO>
 __global__ void convert_kernel(const TI* __restrict__ s, TO* __restrict__ d, int64_t n2) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n2; i += (int64_t)gridDim.x * blockDim.x)
@@ -140,6 +169,35 @@ extern "C" int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_
     convert_kernel<float, float><<<g, 256, 0, s>>>((const float*)src, (float*)dst, n2);
   else
     convert_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n2);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_bound_crm(const float* x, float* y, int64_t n, float atan2_eps, int exact_polar, void* stream) {
+  DCS_REQUIRE(x && y && n > 0, "dcs_bound_crm: bad arguments");
+  bound_crm_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)x, (float2*)y, n, atan2_eps, exact_polar);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_cmul(const float* a, const float* b, float* y, int64_t n, void* stream) {
+  DCS_REQUIRE(a && b && y && n > 0, "dcs_cmul: bad arguments");
+  cmul_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)a, (const float2*)b, (float2*)y, n);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_crm(const float* s, const float* y_noisy, float* m, int64_t n, float eps, void* stream) {
+  DCS_REQUIRE(s && y_noisy && m && n > 0, "dcs_crm: bad arguments");
+  crm_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)s, (const float2*)y_noisy, (float2*)m, n, eps);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_upsample_nearest(const void* x, void* y, int batch, int h, int w, int channels, int up_h, int up_w,
+                                    int dtype, void* stream) {
+  DCS_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && channels > 0 && up_h >= 1 && up_w >= 1, "dcs_upsample_nearest: bad arguments");
+  const int64_t n = (int64_t)batch * h * up_h * w * up_w * channels;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (dtype == DCS_BF16) upsample_kernel<__nv_bfloat16><<<ew_grid(n, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, h, w, channels, up_h, up_w);
+  else upsample_kernel<float><<<ew_grid(n, 256), 256, 0, s>>>((const float*)x, (float*)y, batch, h, w, channels, up_h, up_w);
   DCS_LAUNCHED();
   return 0;
 }

@@ -191,6 +191,10 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(const float* __restrict_
   }
 }
 
+// chunks needed so that every output sample n' < 256 + 32 (T-1) is finalised (a chunk finalises 512 samples);
+// when T % 16 == 0 this adds one frame-less flush chunk.
+__host__ __device__ inline int istft_chunks(int T) { return (T + 7 + kChunk - 1) / kChunk; }
+
 struct IstftSmem {
   FftTables tab;
   float2 tr[kChunk][16 * kTrStride];
@@ -213,14 +217,15 @@ __device__ __forceinline__ float2 polar_roundtrip(float2 s, float eps, bool exac
   return make_float2(xr * inv, s.y * inv);
 }
 
-__global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restrict__ spec, float* __restrict__ audio,
+__global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restrict__ spec, const float* __restrict__ mag,
+                                                         const float* __restrict__ phase, float* __restrict__ audio,
                                                          int T, int chunks_per_cta, float eps, int exact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   IstftSmem& sm = *reinterpret_cast<IstftSmem*>(smem_raw);
   const int b = blockIdx.y;
   const int tid = threadIdx.x;
   const int h = tid >> 4, l = tid & 15;
-  const int n_chunks = (T + kChunk - 1) / kChunk;
+  const int n_chunks = istft_chunks(T);
   const int c_begin = blockIdx.x * chunks_per_cta;
   const int c_end = min(c_begin + chunks_per_cta, n_chunks);
   const int Lout = kHop * (T - 1);
@@ -229,7 +234,9 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
   // unnormalised 256-pt inverse DFT with the 1/2 of the even/odd split already applied: remaining 1/256 of the
   // irfft, times sqrt(512) for normalized=True  ->  sqrt(512)/256
   const float scale = 0.08838834764831845f;
-  const float2* sp = spec + (int64_t)b * kBins * T;
+  const float2* sp = spec ? spec + (int64_t)b * kBins * T : nullptr;
+  const float* mg = mag ? mag + (int64_t)b * kBins * T : nullptr;
+  const float* phs = phase ? phase + (int64_t)b * kBins * T : nullptr;
 
   for (int c = max(c_begin - 1, 0); c < c_end; ++c) {
     const bool emit = c >= c_begin;
@@ -241,7 +248,10 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
       for (int i = 0; i < 16; ++i) {
         const int k = (tid >> 4) + 16 * i;
         float2 s = make_float2(0.f, 0.f);
-        if (t < T) s = polar_roundtrip(__ldg(sp + (int64_t)k * T + t), eps, exact != 0);
+        if (t < T) {
+          if (sp) s = polar_roundtrip(__ldg(sp + (int64_t)k * T + t), eps, exact != 0);
+          else { const float m_ = __ldg(mg + (int64_t)k * T + t), p_ = __ldg(phs + (int64_t)k * T + t); s = make_float2(m_ * cosf(p_), m_ * sinf(p_)); }
+        }
         sm.stage[k][f] = s;
       }
     }
@@ -331,16 +341,16 @@ extern "C" int dcs_stft_fwd(const dcs_stft_params* p, void* stream) {
 }
 
 extern "C" int dcs_istft_fwd(const dcs_istft_params* p, void* stream) {
-  DCS_REQUIRE(p && p->spec && p->audio, "dcs_istft_fwd: null pointer");
+  DCS_REQUIRE(p && p->audio && (p->spec || (p->mag && p->phase)), "dcs_istft_fwd: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->n_frames >= 2, "dcs_istft_fwd: bad batch/n_frames (%d, %d)", p->batch, p->n_frames);
-  const int n_chunks = (p->n_frames + kChunk - 1) / kChunk;
+  const int n_chunks = istft_chunks(p->n_frames);
   int cpc = max(4, (n_chunks * p->batch) / (2 * num_sms()));  // >= 4 keeps the halo re-compute <= 25 %
   cpc = min(cpc, 32);
   dim3 grid((n_chunks + cpc - 1) / cpc, p->batch);
   const size_t smem = sizeof(IstftSmem);
   DCS_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  istft_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>((const float2*)p->spec, p->audio, p->n_frames, cpc,
-                                                               p->atan2_eps, p->exact_polar);
+  istft_kernel<<<grid, kThreads, smem, (cudaStream_t)stream>>>((const float2*)p->spec, p->mag, p->phase, p->audio,
+                                                               p->n_frames, cpc, p->atan2_eps, p->exact_polar);
   DCS_LAUNCHED();
   return 0;
 }

@@ -38,7 +38,20 @@ def istft(spec, audio=None, atan2_eps=1e-6, exact_polar=False):
     B, _, T = spec.shape
     if audio is None:
         audio = torch.empty(B, HOP * (T - 1), dtype=torch.float32, device=spec.device)
-    p = L.IstftParams(L.ptr(spec), L.ptr(audio), B, T, float(atan2_eps), int(exact_polar))
+    p = L.IstftParams(L.ptr(spec), L.ptr(audio), B, T, float(atan2_eps), int(exact_polar), None, None)
+    L.check(L.lib().dcs_istft_fwd(C.byref(p), L.stream_ptr()), "dcs_istft_fwd")
+    return audio
+
+
+def istft_mag_phase(mag, phase, audio=None):
+    """mag_phase_2_wave (network_functions.py:140-150) on explicit fp32 (B,256,T) magnitude / phase arrays."""
+    L.require_cuda(mag, phase)
+    assert mag.dtype == torch.float32 and phase.dtype == torch.float32 and mag.shape == phase.shape
+    assert mag.dim() == 3 and mag.shape[1] == BINS and mag.is_contiguous() and phase.is_contiguous()
+    B, _, T = mag.shape
+    if audio is None:
+        audio = torch.empty(B, HOP * (T - 1), dtype=torch.float32, device=mag.device)
+    p = L.IstftParams(None, L.ptr(audio), B, T, 0.0, 1, L.ptr(mag), L.ptr(phase))
     L.check(L.lib().dcs_istft_fwd(C.byref(p), L.stream_ptr()), "dcs_istft_fwd")
     return audio
 
@@ -106,9 +119,10 @@ def spat_stats(x, gate, stats):
     L.check(L.lib().dcs_spat_stats(C.byref(p), L.stream_ptr()), "dcs_spat_stats")
 
 
-def spat_apply(x, gate, stats, w7, y):
+def spat_apply(x, gate, stats, w7, y, gate_out=None):
     B, H, W, Cn, _ = x.shape
-    p = L.SpatApplyParams(L.ptr(x), L.ptr(gate), L.ptr(stats), L.ptr(w7), L.ptr(y), B, H, W, Cn, _code(x), _code(y))
+    p = L.SpatApplyParams(L.ptr(x), L.ptr(gate), L.ptr(stats), L.ptr(w7), L.ptr(y), B, H, W, Cn, _code(x),
+                          _code(y) if y is not None else F32, L.ptr(gate_out))
     L.check(L.lib().dcs_spat_apply(C.byref(p), L.stream_ptr()), "dcs_spat_apply")
 
 
@@ -140,3 +154,36 @@ def mask_combine(net_raw, noisy_spec, clean_spec, net_out=None, mask=None, noise
 def convert(src, dst):
     L.check(L.lib().dcs_convert(L.ptr(src), L.ptr(dst), src.numel(), _code(src), _code(dst), L.stream_ptr()), "dcs_convert")
     return dst
+
+
+def bound_crm(x, atan2_eps=1e-6, exact_polar=True):
+    """bound_cRM (network_functions.py:77-88) on a complex64 tensor."""
+    L.require_cuda(x)
+    x = x.contiguous()
+    y = torch.empty_like(x)
+    L.check(L.lib().dcs_bound_crm(L.ptr(x), L.ptr(y), x.numel(), float(atan2_eps), int(exact_polar), L.stream_ptr()), "dcs_bound_crm")
+    return y
+
+
+def cmul(a, b):
+    L.require_cuda(a, b)
+    a, b = a.contiguous(), b.contiguous()
+    assert a.shape == b.shape and a.dtype == torch.complex64 and b.dtype == torch.complex64
+    y = torch.empty_like(a)
+    L.check(L.lib().dcs_cmul(L.ptr(a), L.ptr(b), L.ptr(y), a.numel(), L.stream_ptr()), "dcs_cmul")
+    return y
+
+
+def crm(S, Y, eps=1e-8):
+    L.require_cuda(S, Y)
+    S, Y = S.contiguous(), Y.contiguous()
+    m = torch.empty_like(S)
+    L.check(L.lib().dcs_crm(L.ptr(S), L.ptr(Y), L.ptr(m), S.numel(), float(eps), L.stream_ptr()), "dcs_crm")
+    return m
+
+
+def upsample_nearest(x, up):
+    B, H, W, Cn, _ = x.shape
+    y = torch.empty(B, H * up[0], W * up[1], Cn, 2, dtype=x.dtype, device=x.device)
+    L.check(L.lib().dcs_upsample_nearest(L.ptr(x), L.ptr(y), B, H, W, Cn, up[0], up[1], _code(x), L.stream_ptr()), "dcs_upsample_nearest")
+    return y

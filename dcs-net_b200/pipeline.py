@@ -1,0 +1,101 @@
+"""Public inference API: noisy audio in, enhanced audio out (the call a user of train.py/test.py's model makes when
+they only want the enhanced waveform).  Host buffers are pinned; each call does H2D -> one CUDA-graph replay of the
+fused kernel plan (STFT -> C_NETWORK -> bound_cRM x2 -> mask/subtract -> iSTFT) -> D2H on the current stream.
+
+Long-form audio: the reference defines no overlap/stitching — it only ever enhances one crop of
+`integer_win_size - hop` samples (config.py:110-111, data.py:91-104) — so long audio is cut into independent windows
+of `window` samples (T = window/32 + 1 frames, T % 8 == 0), the last one zero-padded, enhanced as a batch and
+concatenated in order.  Multi-GPU = contiguous shards of the window list, one process per GPU, no
+data-path collective.
+"""
+import torch
+
+from . import _lib as L
+from .engine import ForwardPlan, PackedNet
+
+HOP = 32
+WINDOW_4S = 63968   # 32 * (2000 - 1): "4 s" utterance with T = 2000 frames (T % 8 == 0)
+WINDOW_REF = 8160   # 32 * (256 - 1): the reference's native 0.51 s crop (config.py:110-111)
+
+
+def frames_for(n_samples):
+    if n_samples % HOP:
+        raise ValueError(f"window length must be a multiple of hop={HOP} (got {n_samples})")
+    T = n_samples // HOP + 1
+    if T % 8:
+        raise ValueError(f"window of {n_samples} samples gives T={T} frames; C_NETWORK needs T % 8 == 0 "
+                         f"(use n_samples = 32*(8k-1), e.g. {WINDOW_REF} or {WINDOW_4S})")
+    return T
+
+
+def shard_range(n_items, rank, world):
+    """Contiguous [start, stop) of `n_items` owned by `rank` out of `world` (ceil split, trailing ranks may be empty)."""
+    per = (n_items + world - 1) // world
+    start = min(rank * per, n_items)
+    return start, min(start + per, n_items)
+
+
+def split_windows(audio_1d, window):
+    """1-D waveform -> (n_windows, window) with the tail zero-padded; returns (windows, original_length)."""
+    n = audio_1d.numel()
+    n_win = max(1, (n + window - 1) // window)
+    out = audio_1d.new_zeros(n_win * window)
+    out[:n] = audio_1d
+    return out.view(n_win, window), n
+
+
+class Enhancer:
+    """Fixed-shape enhancer: `batch` windows of `n_samples` samples per call."""
+
+    def __init__(self, model_or_sd, batch, n_samples=WINDOW_4S, mode="bf16", variant="dcs", device=None, graph=True,
+                 atan2_eps=10e-7, exact_polar=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("dcsnet_b200.Enhancer needs a CUDA device (sm_100a); there is no CPU fallback")
+        L.lib()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.batch, self.n_samples, self.T = batch, n_samples, frames_for(n_samples)
+        with torch.cuda.device(self.device):
+            self.packed = model_or_sd if isinstance(model_or_sd, PackedNet) else PackedNet(model_or_sd, self.device, mode)
+            self.plan = ForwardPlan(self.packed, batch, self.T, variant=variant, atan2_eps=atan2_eps,
+                                    exact_polar=exact_polar, want_aux=False)
+            if graph:
+                self.plan.capture()
+        self.host_in = torch.empty(batch, n_samples, dtype=torch.float32, pin_memory=True)
+        self.host_out = torch.empty(batch, n_samples, dtype=torch.float32, pin_memory=True)
+        self.h2d_bytes = self.host_in.numel() * 4
+        self.d2h_bytes = self.host_out.numel() * 4
+
+    def enhance_device(self, audio_dev=None):
+        """Device-resident path: audio (batch, n_samples) on the GPU (or already in plan.audio_in) -> device tensor."""
+        return self.plan.enhance_audio(audio_dev)
+
+    def enhance_pinned(self):
+        """host_in (pinned) -> H2D -> graph -> D2H -> host_out (pinned).  Asynchronous on the current stream."""
+        self.plan.audio_in.copy_(self.host_in, non_blocking=True)
+        self.plan.enhance_audio()
+        self.host_out.copy_(self.plan.audio_out, non_blocking=True)
+        return self.host_out
+
+    def __call__(self, noisy_audio):
+        """noisy_audio: (n, n_samples) CPU or CUDA float32, n <= batch.  Returns enhanced audio on the same device."""
+        n = noisy_audio.shape[0]
+        if noisy_audio.shape[1] != self.n_samples or n > self.batch:
+            raise ValueError(f"expected (<= {self.batch}, {self.n_samples}) audio, got {tuple(noisy_audio.shape)}")
+        with torch.cuda.device(self.device):
+            if noisy_audio.is_cuda:
+                if n < self.batch:
+                    self.plan.audio_in[n:].zero_()
+                self.plan.audio_in[:n].copy_(noisy_audio)
+                return self.plan.enhance_audio()[:n].clone()
+            self.host_in[:n].copy_(noisy_audio)
+            if n < self.batch:
+                self.host_in[n:].zero_()
+            self.enhance_pinned()
+            torch.cuda.current_stream().synchronize()
+            return self.host_out[:n].clone()
+
+    def enhance_long(self, audio_1d):
+        """Arbitrary-length 1-D waveform -> enhanced waveform of the same length (independent windows, in order)."""
+        wins, n = split_windows(audio_1d.detach().float().cpu(), self.n_samples)
+        outs = [self(wins[i:i + self.batch]) for i in range(0, wins.shape[0], self.batch)]
+        return torch.cat(outs, 0).reshape(-1)[:n]

@@ -30,7 +30,7 @@ extern "C" {
 #define DCS_ABI_VERSION 1
 
 enum { DCS_F32 = 0, DCS_BF16 = 1 };
-enum { DCS_ACT_NONE = 0, DCS_ACT_RELU = 1, DCS_ACT_LRELU = 2 }; /* ComplexReLU / ComplexLReLU(0.01) */
+enum { DCS_ACT_NONE = 0, DCS_ACT_RELU = 1, DCS_ACT_LRELU = 2, DCS_ACT_SIGMOID = 3 }; /* ComplexReLU / ComplexLReLU(0.01) / ComplexSigmoid */
 enum { DCS_COMBINE_DCS = 0, DCS_COMBINE_DC = 1 };                /* S = Y - Y*M   |   S = Y*M */
 
 #define DCS_MAX_TAPS 64
@@ -57,6 +57,9 @@ int dcs_stft_fwd(const dcs_stft_params* p, void* stream);
  *      identical (re+eps, im)/hypot form. */
 typedef struct {
   const float* spec; float* audio; int batch; int n_frames; float atan2_eps; int exact_polar;
+  /* mag_phase_2_wave(mag, phase, config) called directly (network_functions.py:140): if spec == NULL the input is
+   * the pair of fp32 (B,256,T) arrays mag / phase and the kernel forms mag*cos(phase), mag*sin(phase) itself. */
+  const float* mag; const float* phase;
 } dcs_istft_params;
 int dcs_istft_fwd(const dcs_istft_params* p, void* stream);
 
@@ -114,6 +117,7 @@ int dcs_chan_gate(const dcs_chan_gate_params* p, void* stream);
 /* ---- a10: ComplexSpatialAttention (c_network.py:71-84) applied to u = gate_c * x (complex product, c_network.py
  *      :209,219).  dcs_spat_stats: stats[b][h][w] = { mean_c(u) (complex), max_c Re(u), max_c Im(u) } (4 floats).
  *      dcs_spat_apply: g = sigmoid_c( conv7x7_complex(stats) ), y = g * u (c_network.py:210-211, 220).
+ *      chan_gate may be NULL (u = x); y may be NULL when only gate_out is wanted.
  *      w7: fp32 [2 (r,i)][2 (in ch: mean,max)][7][7]  = conv1.conv_r.weight, conv1.conv_i.weight. */
 typedef struct {
   const void* x; const float* chan_gate; float* stats; int batch; int h; int w; int channels; int dtype;
@@ -122,6 +126,7 @@ int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream);
 typedef struct {
   const void* x; const float* chan_gate; const float* stats; const float* w7; void* y;
   int batch; int h; int w; int channels; int in_dtype; int out_dtype;
+  float* gate_out; /* optional (B,H,W) complex64: the spatial gate itself (ComplexSpatialAttention.forward's return) */
 } dcs_spat_apply_params;
 int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream);
 
@@ -147,6 +152,17 @@ typedef struct {
   int64_t n; float atan2_eps; int combine; int exact_polar;
 } dcs_mask_combine_params;
 int dcs_mask_combine(const dcs_mask_combine_params* p, void* stream);
+
+/* ---- stand-alone element-wise functions of network_functions.py (used by the step functions outside forward):
+ *      bound_cRM (77-88), complex_mat_mult (90-96), cRM (62-75, eps inside both denominators). n complex elements. */
+int dcs_bound_crm(const float* x, float* y, int64_t n, float atan2_eps, int exact_polar, void* stream);
+int dcs_cmul(const float* a, const float* b, float* y, int64_t n, void* stream);
+int dcs_crm(const float* s, const float* y_noisy, float* m, int64_t n, float eps, void* stream);
+
+/* ---- a11 stand-alone: complex_upsample(mode='nearest') (complexPyTorch; c_network.py:215) on channels-last complex.
+ *      (The fused path never materialises this: see dcs_cconv_params.up_h/up_w.) */
+int dcs_upsample_nearest(const void* x, void* y, int batch, int h, int w, int channels, int up_h, int up_w, int dtype,
+                         void* stream);
 
 /* ---- layout helpers for the layer-wise drop-in modules: fp32 <-> bf16 copies of channels-last activations */
 int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_dtype, int out_dtype, void* stream);

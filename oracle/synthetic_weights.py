@@ -85,3 +85,39 @@ def make_state_dict(seed=0):
         sd[f"fc.{n}.weight"] = _xavier(g, (128, 128))
         sd[f"fc.{n}.bias"] = _u(g, (128,), 1.0 / math.sqrt(128))
     return sd
+
+
+def randomise_bn_state(sd, seed=7):
+    """In-place seeded non-trivial BN buffers/affine on a reference-format state_dict: covariance kept
+    SPD (Crr, Cii in [0.5, 1.5], |Cri| <= 0.3).  Iterates keys in state_dict order, so it is reproducible for both the
+    reference's and the product's C_NETWORK (identical key order)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for k in list(sd.keys()):
+            if k.endswith("running_covar"):
+                c = sd[k].shape[0]
+                base = k[: -len("running_covar")]
+                sd[k][:, 0] = 0.5 + torch.rand(c, generator=g)
+                sd[k][:, 1] = 0.5 + torch.rand(c, generator=g)
+                sd[k][:, 2] = 0.6 * torch.rand(c, generator=g) - 0.3
+                sd[base + "running_mean"].copy_(torch.complex(0.2 * torch.randn(c, generator=g), 0.2 * torch.randn(c, generator=g)))
+                w = sd[base + "weight"]
+                w[:, 0] = 1.0 + 0.5 * torch.rand(c, generator=g)
+                w[:, 1] = 1.0 + 0.5 * torch.rand(c, generator=g)
+                w[:, 2] = 0.4 * torch.rand(c, generator=g) - 0.2
+                sd[base + "bias"].copy_(0.1 * torch.randn(c, 2, generator=g))
+    return sd
+
+
+def state_dict_digest(sd):
+    """sha256 over keys, shapes and raw bytes — pins 'identical random-init weights' between reference and product."""
+    import hashlib
+    h = hashlib.sha256()
+    for k in sd:
+        t = sd[k].detach().cpu().contiguous()
+        h.update(k.encode())
+        h.update(str(tuple(t.shape)).encode())
+        if t.is_complex():
+            t = torch.view_as_real(t)
+        h.update(t.numpy().tobytes())
+    return h.hexdigest()

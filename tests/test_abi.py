@@ -1,0 +1,67 @@
+"""CPU: the C-ABI shared library loads and exports exactly the symbols include/dcsnet.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import dcsnet_b200 as D
+from dcsnet_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "dcsnet.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return set(re.findall(r"\b(dcs_[a-z0-9_]+)\s*\(", txt))
+
+
+def test_header_and_binding_agree():
+    hs = header_symbols()
+    assert hs == set(L.SYMBOLS), hs ^ set(L.SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.lib()  # raises if the .so is missing or a symbol is absent: no fallback
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    assert lib.dcs_abi_version() == 1
+
+
+def test_exports_are_plain_c():
+    out = subprocess.run(["nm", "-D", "--defined-only", L.LIB_PATH], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert header_symbols() <= exported
+
+
+def test_struct_sizes_match_header():
+    """ctypes mirrors of the POD parameter structs must have the C compiler's layout."""
+    src = '#include <stdio.h>\n#include "dcsnet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+          'sizeof(dcs_stft_params),sizeof(dcs_istft_params),sizeof(dcs_cbn_params),sizeof(dcs_cconv_params),' \
+          'sizeof(dcs_chan_pool_params),sizeof(dcs_chan_gate_params),sizeof(dcs_spat_stats_params),' \
+          'sizeof(dcs_spat_apply_params),sizeof(dcs_clstm_params),sizeof(dcs_mask_combine_params));return 0;}'
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = list(map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split()))
+    mine = [ctypes.sizeof(t) for t in (L.StftParams, L.IstftParams, L.CbnParams, L.CconvParams, L.ChanPoolParams,
+                                       L.ChanGateParams, L.SpatStatsParams, L.SpatApplyParams, L.ClstmParams,
+                                       L.MaskCombineParams)]
+    assert sizes == mine
+
+
+def test_argument_errors_are_reported_not_swallowed():
+    """Validation happens before any CUDA call, so it is testable without a GPU."""
+    lib = L.lib()
+    p = L.StftParams()
+    rc = lib.dcs_stft_fwd(ctypes.byref(p), None)
+    assert rc != 0 and b"null pointer" in lib.dcs_last_error_string()
+    q = L.CconvParams()
+    assert lib.dcs_cconv2d_tc_fwd(ctypes.byref(q), None) != 0
+    assert lib.dcs_clstm_workspace_bytes(2, 10, 32) < 0  # only hidden=64 is built
+    assert lib.dcs_clstm_workspace_bytes(2, 10, 64) > 0

@@ -1,0 +1,253 @@
+"""GPU (B200): parity of the CUDA path, called through the C ABI, against (i) the golden vectors produced by
+executing the reference and (ii) the oracle restatement on the same seeded inputs.
+
+Tolerances (north_star / SURVEY §8d), 'rel' = max|a-b| / max|b|:
+  fp32 mode  : <= 1e-5 on the enhanced spectrogram S
+  bf16 mode  : <= 2e-3 on S for the reference's own random-init weights (C_NETWORK(config,hparams,seed=0)),
+               |dSI-SDR| <= 0.01 dB
+  STFT/iSTFT : <= 2e-6 (fp32 FFT round-off)
+"""
+import pytest
+import torch
+
+import dcsnet_b200 as D
+from dcsnet_b200 import ops, network_functions as NF, complexFunctions as CF, c_network as CN
+from oracle import dcsnet_oracle as O, synthetic_weights as SW
+from conftest import load_golden, rel_err, build_product_net
+
+pytestmark = pytest.mark.gpu
+EPS = O.HPARAMS["atan2_eps"]
+TOL_FP32, TOL_BF16, TOL_FFT = 1e-5, 2e-3, 2e-6
+
+
+def cl_to_nchw(t):
+    return torch.view_as_complex(t.detach().float().cpu().contiguous()).permute(0, 3, 1, 2)
+
+
+# ------------------------------------------------------------------ front / back end
+def test_library_is_loaded_and_counts_launches():
+    before = D._lib.launch_count()
+    ops.stft(torch.zeros(1, 512, device="cuda"))
+    torch.cuda.synchronize()
+    assert D._lib.launch_count() == before + 1
+
+
+@pytest.mark.parametrize("key", ["a", "b", "c"])
+def test_stft_golden(key):
+    c = load_golden("stft_istft.pt")[key]
+    got = ops.stft(c["audio"].cuda())
+    assert got.shape == c["spec"].shape
+    assert rel_err(got, c["spec"]) <= TOL_FFT
+
+
+@pytest.mark.parametrize("key", ["a", "b", "c"])
+@pytest.mark.parametrize("exact", [False, True])
+def test_istft_golden(key, exact):
+    c = load_golden("stft_istft.pt")[key]
+    got = ops.istft(c["ispec"].cuda(), atan2_eps=EPS, exact_polar=exact)
+    assert got.shape == c["iwave"].shape
+    assert rel_err(got, c["iwave"]) <= TOL_FFT
+
+
+@pytest.mark.parametrize("B,T", [(1, 17), (3, 256), (2, 2000)])
+def test_stft_istft_vs_oracle_ragged_and_full_length(B, T):
+    _, _, noisy = O.synthetic_audio(B, 32 * (T - 1), seed=T)
+    spec = O.stft(noisy)
+    assert rel_err(ops.stft(noisy.cuda()), spec) <= TOL_FFT
+    assert rel_err(ops.istft(spec.cuda(), atan2_eps=EPS), O.spec_to_wave(spec)) <= TOL_FFT
+
+
+def test_mag_phase_2_wave_dropin():
+    from dcsnet_b200 import config as cfg
+    g = torch.Generator().manual_seed(1)
+    s = torch.complex(torch.randn(2, 256, 40, generator=g), torch.randn(2, 256, 40, generator=g))
+    mag, ph = torch.abs(s), torch.atan2(s.imag, s.real + EPS)
+    got = NF.mag_phase_2_wave(mag.cuda(), ph.cuda(), cfg.config)
+    assert rel_err(got, O.spec_to_wave(s)) <= TOL_FFT
+
+
+def test_stft_linearity_property_full_size():
+    g = torch.Generator().manual_seed(4)
+    a, b = torch.randn(8, 63968, generator=g).cuda(), torch.randn(8, 63968, generator=g).cuda()
+    lhs = ops.stft(a + b)
+    rhs = ops.stft(a) + ops.stft(b)
+    assert rel_err(lhs, rhs) <= 5e-6
+
+
+# ------------------------------------------------------------------ the network, golden vectors from the reference
+@pytest.mark.parametrize("name", ["cnet_dcs_default_B2_T64.pt", "cnet_dcs_randbn_B2_T64.pt",
+                                  "cnet_dcs_randbn_B1_T32.pt", "cnet_dc_randbn_B2_T32.pt"])
+def test_fp32_mode_matches_reference_golden(name):
+    g = load_golden(name)
+    net = build_product_net(g["state"])
+    assert SW.state_dict_digest(net.state_dict()) == g["weights_sha256"]
+    pk = D.PackedNet(net, "cuda", "fp32")
+    plan = D.ForwardPlan(pk, g["B"], g["T"], variant=g["variant"])
+    audio = plan.enhance_audio(g["noisy_audio"].cuda())
+    torch.cuda.synchronize()
+    assert rel_err(plan.clean_spec, g["clean_spec"]) <= TOL_FP32
+    net_out = plan.net_out.squeeze(0) if g["B"] == 1 else plan.net_out
+    assert rel_err(net_out, g["net_out"]) <= TOL_FP32
+    assert rel_err(audio, g["clean_audio"]) <= TOL_FP32
+
+
+def test_bf16_mode_matches_reference_golden_default_init():
+    g = load_golden("cnet_dcs_default_B2_T64.pt")
+    net = build_product_net("default")
+    pk = D.PackedNet(net, "cuda", "bf16")
+    plan = D.ForwardPlan(pk, g["B"], g["T"])
+    audio = plan.enhance_audio(g["noisy_audio"].cuda())
+    torch.cuda.synchronize()
+    assert rel_err(plan.clean_spec, g["clean_spec"]) <= TOL_BF16
+    clean = O.synthetic_audio(g["B"], 32 * (g["T"] - 1))[0]
+    d = abs(float(O.si_snr(clean, audio.cpu()) - O.si_snr(clean, g["clean_audio"])))
+    assert d <= 0.01
+
+
+def test_module_forward_dropin_api():
+    """C_NETWORK.forward(x) (the call c_network.py:187 serves): same shape conventions incl. the B=1 squeeze."""
+    g = load_golden("cnet_dcs_randbn_B1_T32.pt")
+    net = build_product_net("randbn").cuda()
+    spec = O.stft(g["noisy_audio"])
+    out = net(spec.cuda())
+    assert out.shape == g["net_out"].shape == (256, 32)
+    assert rel_err(out, g["net_out"]) <= TOL_FP32
+    r = NF.enhance_batch(net, spec.cuda(), "dcs")
+    assert rel_err(r["predict_clean_data"], g["clean_spec"]) <= TOL_FP32
+    assert rel_err(r["predict_clean_audio"], g["clean_audio"]) <= TOL_FP32
+
+
+# ------------------------------------------------------------------ per-layer taps vs the oracle (randomised BN)
+@pytest.mark.parametrize("mode,tol", [("fp32", 1e-5), ("bf16", 2.5e-2)])
+def test_layer_taps_vs_oracle(mode, tol):
+    sd = SW.make_state_dict(0)
+    B, T = 2, 64
+    _, _, noisy = O.synthetic_audio(B, 32 * (T - 1))
+    taps = {}
+    O.enhance_spec(sd, O.stft(noisy), taps=taps)
+    plan = D.ForwardPlan(D.PackedNet(sd, "cuda", mode), B, T, keep_taps=True)
+    plan.enhance_audio(noisy.cuda())
+    torch.cuda.synchronize()
+    assert rel_err(cl_to_nchw(plan.bn0), taps["bn0"]) <= max(tol, 4e-3 if mode == "bf16" else 0)
+    for k, v in plan.taps.items():
+        if k in ("lstm", "fc"):
+            got = torch.view_as_complex(v.detach().float().cpu().contiguous()).reshape(B, -1, 128)
+        else:
+            got = cl_to_nchw(v)
+        assert rel_err(got, taps[k]) <= tol, k
+
+
+def test_tensor_core_conv_equals_cuda_core_conv_on_same_operands():
+    """tcgen05 kernel vs the FFMA kernel fed the SAME bf16-rounded activations and weights: only the fp32 summation
+    order differs, so agreement must be ~1e-5 (isolates descriptor / swizzle / phase / two-source logic)."""
+    sd = SW.make_state_dict(1)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    g = torch.Generator().manual_seed(5)
+    B, T = 2, 64
+    cases = [(pk.enc[i], (B, 256 >> i, max(T >> i, T // 8), pk.enc[i].cin), False) for i in range(1, 7)]
+    cases += [(pk.dec[i], (B, 2 << i, T // 8 if i < 4 else (T // 8) << (i - 4), pk.dec[i].cin // 2), True) for i in range(7)]
+    for p, s0, two in cases:
+        x0 = torch.randn(*s0, 2, generator=g).cuda().bfloat16()
+        x1 = torch.randn(*s0, 2, generator=g).cuda().bfloat16() if two else None
+        oh, ow = ops.conv_out_hw(p, s0[1], s0[2])
+        ref = torch.empty(B, oh, ow, p.cout, 2, device="cuda")
+        got = torch.empty(B, oh, ow, p.cout, 2, device="cuda")
+        w_keep = p.w_ffma
+        K = p.ntaps * 2 * p.cin
+        p.w_ffma = p.w_tc.float()[:, :, :K].reshape(p.phases, p.n_pad, p.ntaps, 2 * p.cin).permute(0, 2, 3, 1).contiguous()
+        ops.cconv(p, x0, x1, ref, use_tc=False)
+        p.w_ffma = w_keep
+        # fp32 output from the tensor-core path only exists for the last decoder layer; compare bf16-rounded otherwise
+        if p is pk.dec[6]:
+            ops.cconv(p, x0, x1, got, use_tc=True)
+            tol = 2e-5
+        else:
+            gb = torch.empty(B, oh, ow, p.cout, 2, device="cuda", dtype=torch.bfloat16)
+            ops.cconv(p, x0, x1, gb, use_tc=True)
+            got, ref, tol = gb.float(), ref.bfloat16().float(), 8e-3  # one bf16 ulp of the largest value
+        torch.cuda.synchronize()
+        assert not torch.isnan(got).any()
+        assert rel_err(got, ref) <= tol, (p.cin, p.cout, p.up, p.stride)
+
+
+# ------------------------------------------------------------------ properties at BASELINE size (B=64 x 4 s)
+@pytest.mark.parametrize("mode,tol", [("fp32", TOL_FP32), ("bf16", 5e-3)])
+def test_full_size_batch_subset_vs_oracle_and_batch_independence(mode, tol):
+    sd = SW.make_state_dict(0)
+    B, T = 64, 2000
+    _, _, noisy = O.synthetic_audio(B, 32 * (T - 1))
+    pk = D.PackedNet(sd, "cuda", mode)
+    plan = D.ForwardPlan(pk, B, T, want_aux=False)
+    full = plan.enhance_audio(noisy.cuda()).clone()
+    spec_full = plan.clean_spec.clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(full).all()
+    # (i) direct parity of two utterances of the full-size batch against the oracle
+    idx = [0, 63]
+    ref = O.enhance_audio(sd, noisy[idx])
+    assert rel_err(spec_full[idx], ref["clean_spec"]) <= tol
+    # (ii) the reference's own CheckBatchGradient idea (network_functions.py:517-532): samples are independent —
+    # permuting the batch permutes the output
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    out_p = plan.enhance_audio(noisy[perm].cuda())
+    torch.cuda.synchronize()
+    assert rel_err(out_p, full[perm.cuda()]) <= 1e-5
+    del plan
+
+
+# ------------------------------------------------------------------ layer-wise drop-in classes
+def test_layer_classes_match_oracle_functions():
+    net = build_product_net("randbn").cuda()
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    g = torch.Generator().manual_seed(8)
+    rc = lambda *s: torch.complex(torch.randn(*s, generator=g), torch.randn(*s, generator=g))
+    x = rc(2, 16, 32, 24)
+    # ComplexConv2d + ComplexBatchNorm2d + ComplexReLU (encoder block 2)
+    ref = O.crelu(O.cbn_eval(O.cconv2d(x, sd, "encoder.2.0.", (2, 2), 2), sd, "encoder.2.1."))
+    assert rel_err(net.encoder[2](x.cuda()), ref) <= 1e-5
+    # ComplexConvTranspose2d (decoder 5 conv) on an explicit cat+upsample input
+    u = O.cupsample_nearest(rc(2, 32, 8, 6), (2, 2))
+    assert rel_err(CF.complex_upsample(rc(1, 4, 3, 5).cuda(), scale_factor=(2, 1)).shape, torch.Size([1, 4, 6, 5])) == 0
+    assert rel_err(net.decoder[5][0](u.cuda()), O.cconvT2d(u, sd, "decoder.5.0.", 1, 1)) <= 1e-5
+    # attention gates
+    y = rc(2, 64, 16, 12)
+    assert rel_err(net.skip_attention[6](y.cuda()), O.channel_attention(y, sd, "skip_attention.6.")) <= 1e-5
+    assert rel_err(net.skip_attention[7](y.cuda()), O.spatial_attention(y, sd, "skip_attention.7.")) <= 1e-5
+    # ComplexLSTM, ComplexLinear
+    z = rc(2, 12, 128)
+    assert rel_err(net.lstm(z.cuda()), O.complex_lstm(z, sd, "lstm.", explicit=True)) <= 1e-5
+    assert rel_err(net.fc(z.cuda()), O.clinear(z, sd, "fc.")) <= 1e-5
+    # element-wise functions of network_functions.py
+    m = rc(2, 256, 16)
+    assert rel_err(NF.bound_cRM(m.cuda(), net.hparams), O.bound_crm(m)) <= 2e-6
+    assert rel_err(NF.complex_mat_mult(m.cuda(), m.flip(0).cuda()), m * m.flip(0)) <= 2e-6
+    assert rel_err(NF.complex_sigmoid(m.cuda()), O.csigmoid(m)) <= 2e-6
+    assert rel_err(NF.complex_lrelu(y.cuda()), O.clrelu(y)) <= 1e-7
+    avg = torch.complex(y.real.mean((2, 3), keepdim=True), y.imag.mean((2, 3), keepdim=True))
+    assert rel_err(NF.ComplexAdaptiveMaxPool2d(1)(y.cuda()), avg) <= 2e-6   # the "max" pool is an average pool
+
+
+def test_shape_contract_errors():
+    sd = SW.make_state_dict(0)
+    pk = D.PackedNet(sd, "cuda", "fp32")
+    with pytest.raises(ValueError):
+        D.ForwardPlan(pk, 1, 260)       # T % 8 != 0
+    with pytest.raises(ValueError):
+        D.ForwardPlan(pk, 1, 64, n_bins=192)  # F % 128 != 0
+    with pytest.raises(RuntimeError):
+        ops.stft(torch.zeros(1, 100, device="cuda"))  # shorter than the reflect pad
+
+
+def test_enhancer_public_api_and_graph():
+    sd = SW.make_state_dict(0)
+    _, _, noisy = O.synthetic_audio(3, 8160)
+    ref = O.enhance_audio(sd, noisy)["clean_audio"]
+    enh = D.Enhancer(sd, batch=4, n_samples=8160, mode="fp32")
+    out = enh(noisy)                       # host in, host out, through the CUDA graph
+    assert not out.is_cuda and rel_err(out, ref) <= 1e-5
+    out2 = enh(noisy.cuda())
+    assert out2.is_cuda and rel_err(out2, ref) <= 1e-5
+    long = torch.cat([noisy[0], noisy[1], noisy[2][:1000]])
+    got = enh.enhance_long(long)
+    assert got.shape == long.shape
+    assert rel_err(got[:16320], ref[:2].reshape(-1)) <= 1e-5

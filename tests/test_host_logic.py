@@ -1,0 +1,107 @@
+"""CPU: host-side logic — window splitting, rank sharding (world_size-2 gloo), shape contract, loud failure without CUDA."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import dcsnet_b200 as D
+from dcsnet_b200 import pipeline
+from conftest import build_product_net
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_frames_and_window_contract():
+    assert pipeline.frames_for(8160) == 256 and pipeline.frames_for(63968) == 2000
+    with pytest.raises(ValueError):
+        pipeline.frames_for(64000)   # T = 2001: the reference fails at the skip torch.cat (c_network.py:214)
+    with pytest.raises(ValueError):
+        pipeline.frames_for(8161)
+
+
+def test_split_windows_pads_tail_and_keeps_order():
+    a = torch.arange(1, 20, dtype=torch.float32)
+    w, n = pipeline.split_windows(a, 8)
+    assert w.shape == (3, 8) and n == 19
+    assert torch.equal(w.reshape(-1)[:19], a) and torch.all(w.reshape(-1)[19:] == 0)
+    w, n = pipeline.split_windows(torch.zeros(0), 8)   # empty input -> one all-zero window, length 0
+    assert w.shape == (1, 8) and n == 0
+
+
+@pytest.mark.parametrize("n,world", [(901, 8), (901, 2), (5, 8), (0, 4), (64, 1)])
+def test_shard_range_partitions_everything_once(n, world):
+    got = []
+    for r in range(world):
+        a, b = pipeline.shard_range(n, r, world)
+        assert 0 <= a <= b <= n
+        got += list(range(a, b))
+    assert got == list(range(n))
+
+
+def test_no_cpu_fallback():
+    net = build_product_net()
+    x = torch.zeros(1, 256, 8, dtype=torch.complex64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net(x)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        net.encoder[0][0](torch.zeros(1, 1, 16, 16, dtype=torch.complex64))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            D.Enhancer(net, 1, 8160)
+        with pytest.raises(RuntimeError, match="CUDA"):
+            D.ForwardPlan(D.PackedNet(net, "cpu", "fp32"), 1, 8)
+
+
+def test_train_mode_is_refused_loudly():
+    net = build_product_net().train()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 256, 8, dtype=torch.complex64))
+
+
+def test_state_dict_roundtrip_and_ckpt_keys():
+    net = build_product_net("randbn")
+    sd = net.state_dict()
+    assert len(sd) == 246 and sum(p.numel() for p in net.parameters()) == 2912707
+    assert sd["decoder.6.conv_tran_r.weight"].shape == (16, 1, 3, 3)
+    assert sd["encoder.0.1.running_mean"].dtype == torch.complex64
+    other = build_product_net("default")
+    other.load_state_dict(sd)   # Lightning .ckpt['state_dict'] loads the same way (strict)
+    for k, v in other.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def _gloo_worker(rank, world, port, n_windows, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from dcsnet_b200 import pipeline as P
+    a, b = P.shard_range(n_windows, rank, world)
+    # stand-in for the per-rank enhancement: each rank tags its windows; the sharded path has no data collective,
+    # only the timing reduction (max over ranks) and an optional gather of results on rank 0
+    local = torch.arange(a, b, dtype=torch.float32)[:, None].repeat(1, 4)
+    t = torch.tensor([float(rank + 1)])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    if rank == 0:
+        q.put((float(t), torch.cat(gathered, 0)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_with_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, 7, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    tmax, cat = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert tmax == 2.0
+    assert torch.equal(cat[:, 0], torch.arange(7, dtype=torch.float32))

@@ -1,0 +1,98 @@
+"""CPU: host-side weight packing (BN fold, bias rule, flipped transposed conv, sub-pixel phases, two-source K order,
+LSTM / attention layouts) checked through a torch emulation of the kernel-side definitions against the oracle."""
+import pytest
+import torch
+
+import dcsnet_b200 as D
+from dcsnet_b200 import packing, ops
+from oracle import dcsnet_oracle as O, synthetic_weights as SW
+from emulate import conv_geometry, nchw_to_cl, cl_to_nchw, lstm_dataflow
+from conftest import rel_err
+
+
+@pytest.fixture(scope="module")
+def packed():
+    sd = SW.make_state_dict(0)
+    return sd, D.PackedNet(sd, "cpu", "bf16")
+
+
+def _rand_c(g, *shape):
+    return torch.complex(torch.randn(*shape, generator=g), torch.randn(*shape, generator=g))
+
+
+@pytest.mark.parametrize("i", range(7))
+def test_encoder_layer_packing(packed, i):
+    sd, pk = packed
+    g = torch.Generator().manual_seed(i)
+    p = pk.enc[i]
+    x = _rand_c(g, 2, p.cin, 16, 24)
+    ref = O.crelu(O.cbn_eval(O.cconv2d(x, sd, f"encoder.{i}.0.", O.STRIDE_E[i], O.KERNEL_E[i] // 2), sd, f"encoder.{i}.1."))
+    got = cl_to_nchw(conv_geometry(p, nchw_to_cl(x), None, ops.conv_out_hw(p, 16, 24)))
+    assert got.shape == ref.shape
+    assert rel_err(got, ref) <= 5e-6
+
+
+@pytest.mark.parametrize("i", range(7))
+def test_decoder_layer_packing(packed, i):
+    """cat(d, skip) -> nearest upsample -> ConvTranspose2d(k3,s1,p1) [-> BN -> LReLU]  ==  phase-decomposed two-source GEMM."""
+    sd, pk = packed
+    g = torch.Generator().manual_seed(10 + i)
+    p = pk.dec[i]
+    c = p.cin // 2
+    d, s = _rand_c(g, 2, c, 4, 6), _rand_c(g, 2, c, 4, 6)
+    u = O.cupsample_nearest(torch.cat((d, s), 1), O.UPSAMPLE[i])
+    if i == 6:
+        ref = O.cconvT2d(u, sd, "decoder.6.", 1, 1)
+    else:
+        ref = O.clrelu(O.cbn_eval(O.cconvT2d(u, sd, f"decoder.{i}.0.", 1, 1), sd, f"decoder.{i}.1."))
+    got = cl_to_nchw(conv_geometry(p, nchw_to_cl(d), nchw_to_cl(s), ref.shape[2:]))
+    assert rel_err(got, ref) <= 5e-6
+    # executed MACs drop by 1.5x / 2.25x with the pre-summed taps
+    assert p.phases * p.ntaps == {(2, 1): 12, (2, 2): 16}[p.up]
+
+
+def test_tc_operand_is_rounded_ffma_operand(packed):
+    _, pk = packed
+    for p in pk.enc[1:] + pk.dec:
+        K = p.ntaps * 2 * p.cin
+        assert p.w_tc.shape == (p.phases, p.n_pad, (K + 63) // 64 * 64)
+        assert torch.all(p.w_tc[:, :, K:] == 0)
+        wt = p.w_tc.float()[:, :, :K].reshape(p.phases, p.n_pad, p.ntaps, 2 * p.cin).permute(0, 2, 3, 1)
+        assert torch.equal(wt, p.w_ffma.to(torch.bfloat16).float())
+
+
+def test_fc_packing(packed):
+    sd, pk = packed
+    g = torch.Generator().manual_seed(5)
+    x = _rand_c(g, 2, 10, 128)
+    ref = O.clinear(x, sd, "fc.")
+    got = conv_geometry(pk.fc, torch.view_as_real(x).reshape(2, 1, 10, 128, 2), None, (1, 10))
+    got = torch.view_as_complex(got.float().contiguous()).reshape(2, 10, 128)
+    assert rel_err(got, ref) <= 5e-6
+
+
+def test_bn_fold_is_eval_bn(packed):
+    sd, _ = packed
+    g = torch.Generator().manual_seed(6)
+    x = _rand_c(g, 2, 16, 5, 7)
+    A, c = packing.bn_affine_from_sd(sd, "encoder.1.1.")
+    xr = torch.stack([x.real, x.imag], -1).double()                       # (B,C,H,W,2)
+    y = torch.einsum("cab,nchwb->nchwa", A, xr) + c[None, :, None, None, :]
+    ref = O.cbn_eval(x, sd, "encoder.1.1.")
+    assert rel_err(torch.complex(y[..., 0], y[..., 1]).to(torch.complex64), ref) <= 5e-6
+
+
+def test_lstm_packing_and_dataflow(packed):
+    sd, pk = packed
+    g = torch.Generator().manual_seed(2)
+    x = _rand_c(g, 3, 7, 128)
+    ref = O.complex_lstm(x, sd, "lstm.", explicit=True)
+    assert rel_err(lstm_dataflow(pk.lstm, x), ref) <= 5e-6
+
+
+def test_bias_rule_quirk():
+    """complexPyTorch's apply_complex gives the effective bias (b_r - b_i) + j (b_r + b_i), not b_r + j b_i."""
+    wr, wi = torch.zeros(3, 2, 1, 1), torch.zeros(3, 2, 1, 1)
+    br, bi = torch.tensor([1.0, 2.0, 3.0]), torch.tensor([0.5, -1.0, 4.0])
+    p = packing.PackedConv(wr, wi, br, bi)
+    assert torch.allclose(p.bias[:6].view(3, 2), torch.stack([br - bi, br + bi], 1))
