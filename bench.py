@@ -275,7 +275,7 @@ def measure_roofline(plan, args, B, T):
         setattr(ops, name, inner)
 
     wrap("cconv", lambda pk, s0, s1, dst, use_tc=False, pool_sums=None: "conv_tc" if use_tc else "conv_ffma")
-    for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "clstm", "mask_combine"):
+    for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "clstm", "mask_combine", "enc0", "dec6_tail"):
         wrap(n, lambda *a, _n=n, **k: _n)
     steps = max(3, min(args.steps, 10))
     try:
@@ -290,7 +290,7 @@ def measure_roofline(plan, args, B, T):
             setattr(ops, n, fn)
     stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in acc.items()}
     fl = conv_flops_per_utterance(T)
-    tc_layers = [k for k in fl if k != "enc0"] if args.mode == "bf16" else []
+    tc_layers = [k for k in fl if k not in ("enc0", "dec6")] if args.mode == "bf16" else []
     n_tc = len(acc.get("conv_tc", [])) // steps
     roof = None
     if args.mode == "bf16" and n_tc:
@@ -301,7 +301,7 @@ def measure_roofline(plan, args, B, T):
         if not peak:
             peak, which = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
         ach = flops / t / 1e12
-        roof = {"bound": "tensor", "kernel": "dcs::cconv_tc_kernel (13 launches/step: enc1..enc6, dec0..dec6)",
+        roof = {"bound": "tensor", "kernel": "dcs::cconv_tc_kernel (13 launches/step: enc1..enc6, dec0..dec5 bf16 + fc tf32)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": which,
                 "algorithmic_flops_per_step": flops, "avg_launch_ms": stage_ms["conv_tc"] / n_tc, "launches_per_step": n_tc,

@@ -69,12 +69,24 @@ class SpatApplyParams(C.Structure):
 class ClstmParams(C.Structure):
     _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("in_dtype", _i),
                 ("w_ih0", _vp), ("w_ih1", _vp), ("w_hh", _vp), ("bias", _vp),
-                ("workspace", _vp), ("workspace_bytes", _i64)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("w_ih0_t", _vp), ("w_ih1_t", _vp)]
 
 
 class MaskCombineParams(C.Structure):
     _fields_ = [("net_raw", _vp), ("noisy_spec", _vp), ("net_out", _vp), ("mask", _vp), ("noise_spec", _vp),
                 ("clean_spec", _vp), ("n", _i64), ("atan2_eps", _f), ("combine", _i), ("exact_polar", _i)]
+
+
+class Enc0Params(C.Structure):
+    _fields_ = [("spec", _vp), ("bn_affine", _vp), ("weight", _vp), ("bias", _vp), ("dst", _vp), ("out_dtype", _i),
+                ("batch", _i), ("h", _i), ("w", _i)]
+
+
+class Dec6TailParams(C.Structure):
+    _fields_ = [("d", _vp), ("skip", _vp), ("in_dtype", _i), ("batch", _i), ("h", _i), ("w", _i),
+                ("weight", _vp), ("bias_re", _f), ("bias_im", _f),
+                ("noisy_spec", _vp), ("net_raw", _vp), ("net_out", _vp), ("mask", _vp), ("noise_spec", _vp),
+                ("clean_spec", _vp), ("atan2_eps", _f), ("combine", _i), ("exact_polar", _i)]
 
 
 # symbol -> (restype, argtypes); must list EVERY entry of include/dcsnet.h (tests/test_abi.py checks both ways)
@@ -94,10 +106,13 @@ SYMBOLS = {
     "dcs_clstm_workspace_bytes": (_i64, [_i, _i, _i]),
     "dcs_clstm_fwd": (_i, [C.POINTER(ClstmParams), _vp]),
     "dcs_mask_combine": (_i, [C.POINTER(MaskCombineParams), _vp]),
+    "dcs_dec6_tail_fwd": (_i, [C.POINTER(Dec6TailParams), _vp]),
+    "dcs_enc0_fwd": (_i, [C.POINTER(Enc0Params), _vp]),
     "dcs_bound_crm": (_i, [_vp, _vp, _i64, _f, _i, _vp]),
     "dcs_cmul": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "dcs_crm": (_i, [_vp, _vp, _vp, _i64, _f, _vp]),
     "dcs_upsample_nearest": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_tc_set_debug_buffer": (_i, [_vp]),
     "dcs_convert": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
 }
 

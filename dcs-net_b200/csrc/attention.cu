@@ -13,6 +13,34 @@
 
 namespace dcs {
 
+// 16-byte vector access: VEC complex elements per lane (4 for bf16, 2 for fp32)
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+  static constexpr int N = 2;
+  static __device__ __forceinline__ void ld(const float* p, int64_t cidx, float2 (&v)[2]) {
+    const float4 q = __ldg(reinterpret_cast<const float4*>(p + 2 * cidx));
+    v[0] = make_float2(q.x, q.y); v[1] = make_float2(q.z, q.w);
+  }
+  static __device__ __forceinline__ void st(float* p, int64_t cidx, const float2 (&v)[2]) {
+    *reinterpret_cast<float4*>(p + 2 * cidx) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+  }
+};
+template <> struct Vec16<__nv_bfloat16> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, int64_t cidx, float2 (&v)[4]) {
+    const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + 2 * cidx));
+    const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, int64_t cidx, const float2 (&v)[4]) {
+    uint32_t w[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __float22bfloat162_rn(v[i]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+    *reinterpret_cast<uint4*>(p + 2 * cidx) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+};
+
 // ---------------------------------------------------------------- 1. global average pool (sums)
 template <typename T>
 __global__ void __launch_bounds__(256) chan_pool_kernel(const T* __restrict__ x, float* __restrict__ sums, int hw, int C,
@@ -80,7 +108,8 @@ __global__ void __launch_bounds__(128) chan_gate_kernel(const dcs_chan_gate_para
 template <typename T>
 __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x, const float* __restrict__ gate,
                                                          float4* __restrict__ stats, int hw, int C, int G) {
-  // G lanes cooperate on one pixel (G = min(32, C)); each lane strides over channels
+  // G lanes cooperate on one pixel; each lane strides over the channels in 16-byte vectors (G = min(32, C / VEC))
+  constexpr int V = Vec16<T>::N;
   __shared__ float2 gs[256];
   const int b = blockIdx.y;
   for (int c = threadIdx.x; c < C; c += blockDim.x)
@@ -92,10 +121,17 @@ __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x
   for (int pbase = blockIdx.x * groups; pbase < hw; pbase += gridDim.x * groups) {  // CTA-uniform trip count (shuffles)
     const int p = pbase + grp;
     float sr = 0.f, si = 0.f, mr = -INFINITY, mi = -INFINITY;
-    for (int c = sub; c < C && p < hw; c += G) {
-      const float2 u = cmul(gs[c], Elem<T>::ldc(xb, (int64_t)p * C + c));
-      sr += u.x; si += u.y;
-      mr = fmaxf(mr, u.x); mi = fmaxf(mi, u.y);
+    if (p < hw) {
+      for (int c = sub * V; c < C; c += G * V) {
+        float2 v[V];
+        Vec16<T>::ld(xb, (int64_t)p * C + c, v);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float2 u = cmul(gs[c + e], v[e]);
+          sr += u.x; si += u.y;
+          mr = fmaxf(mr, u.x); mi = fmaxf(mi, u.y);
+        }
+      }
     }
     for (int o = G >> 1; o; o >>= 1) {
       sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o);
@@ -106,19 +142,20 @@ __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x
 }
 
 // ---------------------------------------------------------------- 4. 7x7 complex conv on the stats, sigmoid, apply
-constexpr int kSaTH = 4, kSaTW = 64, kSaK = 7, kSaR = 3;
+constexpr int kSaTW = 64, kSaK = 7, kSaR = 3;  // tile = kSaTH x 64 pixels, kSaTH in {4, 16} (template)
 
-template <typename TI, typename TO>
+template <typename TI, typename TO, int kSaTH>
 __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gate,
                                                          const float4* __restrict__ stats, const float* __restrict__ w7,
                                                          TO* __restrict__ y, float2* __restrict__ gate_out, int H, int W, int C) {
   __shared__ float4 st[kSaTH + 2 * kSaR][kSaTW + 2 * kSaR];
   __shared__ float2 sg[kSaTH][kSaTW];
   __shared__ float2 gs[256];
-  __shared__ float wsm[2 * 2 * 49];
+  __shared__ float4 wq[49];
   const int b = blockIdx.z;
   const int y0 = blockIdx.y * kSaTH, x0 = blockIdx.x * kSaTW;
-  for (int i = threadIdx.x; i < 196; i += 256) wsm[i] = w7[i];
+  // w7 = [conv_r (1,2,7,7) | conv_i (1,2,7,7)]: regroup per tap as (Wr[mean], Wr[max], Wi[mean], Wi[max])
+  for (int i = threadIdx.x; i < 49; i += 256) wq[i] = make_float4(w7[i], w7[49 + i], w7[98 + i], w7[147 + i]);
   for (int c = threadIdx.x; c < C; c += 256)
     gs[c] = gate ? reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c] : make_float2(1.f, 0.f);
   for (int i = threadIdx.x; i < (kSaTH + 2 * kSaR) * (kSaTW + 2 * kSaR); i += 256) {
@@ -129,25 +166,33 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
     st[r][cidx] = v;
   }
   __syncthreads();
-  {  // one thread per tile pixel: ComplexConv2d(2,1,7,padding=3,bias=False) then ComplexSigmoid
-    const int r = threadIdx.x / kSaTW, cidx = threadIdx.x % kSaTW;
-    float re = 0.f, im = 0.f;
-    const float* wr = wsm;        // conv_r.weight (1,2,7,7): [ch][ky][kx]
-    const float* wi = wsm + 98;   // conv_i.weight
+  if (threadIdx.x < kSaTH * (kSaTW / 4)) {  // kSaTH = 16: every thread; kSaTH = 4 (short images): 2 warps
+    // ComplexConv2d(2,1,7,padding=3,bias=False) then ComplexSigmoid.  A thread owns 4 adjacent pixels of one tile row:
+    // per kernel row it loads the 10 stats vectors it needs once and walks the 7 taps from registers.
+    const int r = threadIdx.x / (kSaTW / 4), c4 = (threadIdx.x % (kSaTW / 4)) * 4;
+    float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int ky = 0; ky < kSaK; ++ky) {
+      float4 sv[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) sv[j] = st[r + ky][c4 + j];
 #pragma unroll
       for (int kx = 0; kx < kSaK; ++kx) {
-        const float4 s = st[r + ky][cidx + kx];
-        const float a0 = wr[ky * 7 + kx], a1 = wr[49 + ky * 7 + kx];
-        const float b0 = wi[ky * 7 + kx], b1 = wi[49 + ky * 7 + kx];
-        re += a0 * s.x + a1 * s.z - b0 * s.y - b1 * s.w;
-        im += a0 * s.y + a1 * s.w + b0 * s.x + b1 * s.z;
+        const float4 wv = wq[ky * 7 + kx];  // (a0, a1, b0, b1) = (Wr[mean], Wr[max], Wi[mean], Wi[max])
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 sq = sv[q + kx];
+          re[q] += wv.x * sq.x + wv.y * sq.z - wv.z * sq.y - wv.w * sq.w;
+          im[q] += wv.x * sq.y + wv.y * sq.w + wv.z * sq.x + wv.w * sq.z;
+        }
       }
     }
-    const float2 gv = make_float2(sigmoidf_(re), sigmoidf_(im));
-    sg[r][cidx] = gv;
-    if (gate_out && y0 + r < H && x0 + cidx < W) gate_out[((int64_t)b * H + y0 + r) * W + x0 + cidx] = gv;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 gv = make_float2(sigmoidf_(re[q]), sigmoidf_(im[q]));
+      sg[r][c4 + q] = gv;
+      if (gate_out && y0 + r < H && x0 + c4 + q < W) gate_out[((int64_t)b * H + y0 + r) * W + x0 + c4 + q] = gv;
+    }
   }
   if (!y) return;
   __syncthreads();
@@ -156,10 +201,23 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
     if (yy >= H) break;
     const int wvalid = min(kSaTW, W - x0);
     const int64_t base = (((int64_t)b * H + yy) * W + x0) * C;
-    for (int i = threadIdx.x; i < wvalid * C; i += 256) {
-      const int px = i / C, c = i - px * C;
-      const float2 u = cmul(gs[c], Elem<TI>::ldc(x, base + i));
-      Elem<TO>::stc(y, base + i, cmul(sg[r][px], u));
+    if constexpr (sizeof(TI) == sizeof(TO)) {  // same storage type: 16-byte vectors
+      constexpr int V = Vec16<TI>::N;
+      for (int i = threadIdx.x * V; i < wvalid * C; i += 256 * V) {
+        const int px = i / C, c = i - px * C;
+        float2 v[V];
+        Vec16<TI>::ld(x, base + i, v);
+        const float2 g = sg[r][px];
+#pragma unroll
+        for (int e = 0; e < V; ++e) v[e] = cmul(g, cmul(gs[c + e], v[e]));
+        Vec16<TO>::st(y, base + i, v);
+      }
+    } else {
+      for (int i = threadIdx.x; i < wvalid * C; i += 256) {
+        const int px = i / C, c = i - px * C;
+        const float2 u = cmul(gs[c], Elem<TI>::ldc(x, base + i));
+        Elem<TO>::stc(y, base + i, cmul(sg[r][px], u));
+      }
     }
   }
 }
@@ -198,7 +256,9 @@ extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
   DCS_REQUIRE(p && p->x && p->stats, "dcs_spat_stats: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && pow2(p->channels) && p->channels <= 256, "dcs_spat_stats: bad shape");
   const int hw = p->h * p->w;
-  const int G = min(32, p->channels), groups = 256 / G;
+  const int vec = p->dtype == DCS_BF16 ? 4 : 2;
+  DCS_REQUIRE(p->channels % vec == 0, "dcs_spat_stats: channels must be a multiple of %d", vec);
+  const int G = min(32, p->channels / vec), groups = 256 / G;
   int ctas = (hw + groups - 1) / groups;
   ctas = min(ctas, max(1, 16 * num_sms() / p->batch));
   dim3 grid(ctas, p->batch);
@@ -213,10 +273,16 @@ extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
   DCS_REQUIRE(p && p->x && p->stats && p->w7 && (p->y || p->gate_out), "dcs_spat_apply: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && p->channels > 0 && p->channels <= 256, "dcs_spat_apply: bad shape");
   DCS_REQUIRE(p->batch <= 65535, "dcs_spat_apply: batch too large for grid.z");
-  dim3 grid((p->w + kSaTW - 1) / kSaTW, (p->h + kSaTH - 1) / kSaTH, p->batch);
+  DCS_REQUIRE(p->channels % 4 == 0, "dcs_spat_apply: channels must be a multiple of 4");
+  const int th = p->h >= 16 ? 16 : 4;
+  dim3 grid((p->w + kSaTW - 1) / kSaTW, (p->h + th - 1) / th, p->batch);
   cudaStream_t s = (cudaStream_t)stream;
   const float4* st = (const float4*)p->stats;
-#define DCS_SA(TI, TO) spat_apply_kernel<TI, TO><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels)
+#define DCS_SA(TI, TO)                                                                                                             \
+  do {                                                                                                                             \
+    if (th == 16) spat_apply_kernel<TI, TO, 16><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels); \
+    else spat_apply_kernel<TI, TO, 4><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels);        \
+  } while (0)
   if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_SA(float, float);
   else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_SA(float, __nv_bfloat16);
   else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_SA(__nv_bfloat16, float);

@@ -13,7 +13,7 @@
 //             channels of one tap; zero padding and image borders come from TMA out-of-bounds fill, conv stride
 //             from the tensor map's elementStrides, the channel concat from switching tensor maps) + one TMA box
 //             of the K-major weight matrix (SWIZZLE_128B).
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// Warp roles (320 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..9 = epilogue
 // (TMEM -> registers -> bias/activation -> bf16 -> global, plus optional per-(image, channel) pooling sums).
 #include <cuda.h>
 #include <string.h>
@@ -25,8 +25,8 @@ namespace dcs {
 int validate_conv(const dcs_cconv_params* p, const char* who);
 
 constexpr int kTileM = 128;
-constexpr int kKStep = 64;               // bf16 elements of K per pipeline stage (= one 128-byte swizzle row)
-constexpr int kTcThreads = 192;
+constexpr int kKStepBytes = 128;         // bytes of K per pipeline stage (= one 128-byte swizzle row): 64 bf16 or 32 tf32
+constexpr int kTcThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;  // mbarrier spin cap: trap instead of hanging the GPU
 
@@ -36,12 +36,14 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_b, tiles_per_phase, n_tiles;
   int phases, ntaps, up_h, up_w, stride_h, stride_w;
   int C2, C2_src0, CK, ksteps, n_stages;
+  int esz;                    // operand element size: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32)
   int n_pad, n_real, act, out_f32;
   int batch, out_h, out_w;
   int8_t dy[DCS_MAX_TAPS], dx[DCS_MAX_TAPS];
   const float* bias;
   void* dst;
   float* pool;
+  unsigned long long* dbg;    // optional per-CTA wait-cycle counters (dcs_tc_set_debug_buffer), 8 words per CTA
 };
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
@@ -56,7 +58,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, unsigned long long* waited = nullptr) {
+  const long long t0 = waited ? clock64() : 0;
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
@@ -69,6 +72,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) break;
     if (++spins > kSpinLimit) __trap();  // a broken pipeline must fault, never hang the device
   }
+  if (waited) *waited += (unsigned long long)(clock64() - t0);
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
@@ -82,6 +86,18 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+// One elected lane of a converged warp (CUTLASS elect_one_sync).  The single-thread roles keep the WHOLE warp in the
+// control loop (warp-uniform values stay in uniform registers, which UTCHMMA / UTMALDG take as operands) and only
+// predicate the issue itself; an `if (lane == 0)` loop instead forces per-lane "waterfall" code around every MMA.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -92,6 +108,14 @@ __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t a_desc, ui
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
@@ -119,6 +143,7 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_b
 struct __align__(8) TcBarriers {
   uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
   uint32_t tmem_base;
+  float bias[256];
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -126,7 +151,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [stage][A 16 KB | B n_pad*128 B] (1024-aligned), then barriers
-  const uint32_t a_bytes = kTileM * kKStep * 2, b_bytes = (uint32_t)a.n_pad * kKStep * 2;
+  const uint32_t a_bytes = kTileM * kKStepBytes, b_bytes = (uint32_t)a.n_pad * kKStepBytes;
   const uint32_t stage_bytes = a_bytes + b_bytes;  // multiple of 1024 (n_pad % 16 == 0 -> b_bytes % 2048 == 0)
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(base + (size_t)a.n_stages * stage_bytes);
@@ -135,7 +160,8 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.n_stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    const uint32_t n_epi_warps = (a.n_pad % 32) == 0 ? 8u : 4u;
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), n_epi_warps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
@@ -145,16 +171,24 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
+  for (int i = threadIdx.x; i < a.n_pad; i += kTcThreads) bars->bias[i] = a.bias[i];
+  const float* bias_s = bars->bias;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const int sub_per_step = kKStep / a.CK;
+  const int kstep_elems = kKStepBytes / a.esz;
+  const int sub_per_step = kstep_elems / a.CK;
 
   if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (lane == 0) {
+    // ===================================================================== TMA producer (whole warp loops, one lane issues)
+    {
       uint32_t stage = 0, phase_bit = 0;
+      const uint32_t smem_base = smem_u32(base), bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t sub_bytes = (uint32_t)(kTileM * a.CK * a.esz);
+      unsigned long long w_empty = 0;
+      unsigned long long* dw = a.dbg ? &w_empty : nullptr;
+      const long long t_start = clock64();
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
         const int ph_idx = tile / a.tiles_per_phase;
         int r = tile - ph_idx * a.tiles_per_phase;
@@ -162,129 +196,200 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         r -= bt * a.tiles_h * a.tiles_w;
         const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
         const int b0 = bt * a.NB, j0 = ht * a.TH, i0 = wt * a.TW;
+        // Single-thread control loop: keep it free of divisions / 64-bit math (every instruction is latency-exposed).
+        const int8_t* dyp = a.dy + ph_idx * a.ntaps;
+        const int8_t* dxp = a.dx + ph_idx * a.ntaps;
+        const int ybase = j0 * a.stride_h, xbase = i0 * a.stride_w;
+        const int wrow = ph_idx * a.n_pad;
+        int tap = 0, c = 0, kcol = 0;                       // running (tap, channel) position and weight column
+        int y = ybase + dyp[0], x = xbase + dxp[0];
         for (int ks = 0; ks < a.ksteps; ++ks) {
-          mbar_wait(smem_u32(&bars->empty[stage]), phase_bit ^ 1);
-          const uint32_t full = smem_u32(&bars->full[stage]);
-          mbar_expect_tx(full, stage_bytes);
-          const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
+          mbar_wait(bar_empty0 + 8u * stage, phase_bit ^ 1, dw);
+          const uint32_t full = bar_full0 + 8u * stage;
+          const bool leader = elect_one();
+          if (leader) mbar_expect_tx(full, stage_bytes);
+          uint32_t dst = smem_base + stage * stage_bytes;
           for (int g = 0; g < sub_per_step; ++g) {
-            const int e = (ks * sub_per_step + g) * a.CK;  // flattened (tap, channel) offset
-            int tap = e / a.C2;
-            int c = e - tap * a.C2;
-            if (tap >= a.ntaps) { tap = a.ntaps - 1; }       // K padding: finite data x zero weights
-            const int y = j0 * a.stride_h + a.dy[ph_idx * a.ntaps + tap];
-            const int x = i0 * a.stride_w + a.dx[ph_idx * a.ntaps + tap];
-            const uint32_t dst = sa + (uint32_t)g * (kTileM * a.CK * 2);
-            if (c < a.C2_src0) tma_load_4d(dst, &tmA0, full, c, x, y, b0);
-            else tma_load_4d(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
+            if (leader) {
+              if (c < a.C2_src0) tma_load_4d(dst, &tmA0, full, c, x, y, b0);
+              else tma_load_4d(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
+            }
+            dst += sub_bytes;
+            c += a.CK;
+            if (c == a.C2) {                                 // next tap (K padding repeats the last tap: finite x 0)
+              c = 0;
+              if (tap + 1 < a.ntaps) { ++tap; y = ybase + dyp[tap]; x = xbase + dxp[tap]; }
+            }
           }
-          tma_load_2d(sa + a_bytes, &tmB, full, ks * kKStep, ph_idx * a.n_pad);
+          if (leader) tma_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, full, kcol, wrow);
+          __syncwarp();
+          kcol += kstep_elems;
           if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
         }
       }
+      if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 0] = w_empty; a.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_start); }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer (one thread)
-    if (lane == 0) {
-      // instruction descriptor: D=F32, A=B=BF16, both K-major, N>>3 @17, M>>4 @24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t a_row_bytes = (uint32_t)a.CK * 2;
+    // ===================================================================== MMA issuer (whole warp loops, one lane issues)
+    {
+      // instruction descriptor: D=F32, A=B=BF16 (1) or TF32 (2), both K-major, N>>3 @17, M>>4 @24
+      const uint32_t fmt = a.esz == 2 ? 1u : 2u;
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t a_row_bytes = (uint32_t)(a.CK * a.esz);
+      // Descriptors = constant high word + (start address >> 4) in the low word; per-MMA byte offsets inside a stage
+      // are precomputed once so the issue loop is a handful of 32-bit adds per MMA (single latency-exposed thread).
+      const uint64_t a_desc0 = umma_desc(0, a_row_bytes), b_desc0 = umma_desc(0, 128);
+      uint32_t a_off[kKStepBytes / 32];
+#pragma unroll
+      for (int i = 0; i < kKStepBytes / 32; ++i) {
+        const uint32_t g = (32u * i) / a_row_bytes, j = (32u * i - g * a_row_bytes) / 32u;
+        a_off[i] = (g * (kTileM * a_row_bytes) + j * 32u) >> 4;
+      }
+      const uint32_t smem_base = smem_u32(base), bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t bar_accf0 = smem_u32(&bars->acc_full[0]), bar_acce0 = smem_u32(&bars->acc_empty[0]);
       uint32_t stage = 0, phase_bit = 0, acc = 0, acc_phase = 0;
+      unsigned long long w_full = 0, w_acc = 0;
+      unsigned long long *dwf = a.dbg ? &w_full : nullptr, *dwa = a.dbg ? &w_acc : nullptr;
+      const long long t_start = clock64();
       for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        mbar_wait(smem_u32(&bars->acc_empty[acc]), acc_phase ^ 1);
+        mbar_wait(bar_acce0 + 8u * acc, acc_phase ^ 1, dwa);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * (uint32_t)a.n_pad;
         for (int ks = 0; ks < a.ksteps; ++ks) {
-          mbar_wait(smem_u32(&bars->full[stage]), phase_bit);
+          mbar_wait(bar_full0 + 8u * stage, phase_bit, dwf);
           tc_fence_after();
-          const uint32_t sa = smem_u32(base + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
+          const uint32_t sa16 = ((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4;  // stage start, 16-byte units
+          const uint32_t sb16 = sa16 + (a_bytes >> 4);
+          if (elect_one()) {
 #pragma unroll
-          for (int i = 0; i < kKStep / 16; ++i) {
-            const int g = (16 * i) / a.CK, j = (16 * i - g * a.CK) / 16;
-            const uint64_t ad = umma_desc(sa + (uint32_t)g * (kTileM * a.CK * 2) + (uint32_t)j * 32, a_row_bytes);
-            const uint64_t bd = umma_desc(sb + (uint32_t)i * 32, 128);
-            tc_mma_bf16(d_tmem, ad, bd, idesc, (ks | i) != 0);
+            for (int i = 0; i < kKStepBytes / 32; ++i) {  // one MMA per 32 bytes of K (16 bf16 / 8 tf32)
+              const uint64_t ad = a_desc0 + (uint64_t)(sa16 + a_off[i]);
+              const uint64_t bd = b_desc0 + (uint64_t)(sb16 + 2u * i);
+              if (a.esz == 2) tc_mma_bf16(d_tmem, ad, bd, idesc, (ks | i) != 0);
+              else tc_mma_tf32(d_tmem, ad, bd, idesc, (ks | i) != 0);
+            }
+            tc_commit(bar_empty0 + 8u * stage);     // frees the smem stage once these MMAs have read it
+            if (ks == a.ksteps - 1) tc_commit(bar_accf0 + 8u * acc);  // accumulator complete -> epilogue
           }
-          tc_commit(smem_u32(&bars->empty[stage]));  // frees the smem stage once these MMAs have read it
+          __syncwarp();
           if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
         }
-        tc_commit(smem_u32(&bars->acc_full[acc]));   // accumulator complete -> epilogue
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 2] = w_full; a.dbg[blockIdx.x * 8 + 3] = w_acc; a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_start); }
     }
   } else {
-    // ===================================================================== epilogue (4 warps = 128 TMEM lanes)
-    const int quad = warp & 3;                // TMEM lane quadrant this warp may access
-    const int m = quad * 32 + lane;           // tile row = TMEM lane
+    // ===================================================================== epilogue (8 warps)
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the accumulator columns.
+    const int ew = warp - 2;
+    const int quad = warp & 3;
+    const bool split = (a.n_pad % 32) == 0;          // n_pad = 16 (or an odd multiple of 16): one warp per quadrant
+    const int half = ew >> 2;
+    const int ncols = split ? a.n_pad / 2 : a.n_pad;
+    const int col0 = split ? half * ncols : 0;
+    const bool active = split || half == 0;
+    const int m = quad * 32 + lane;                  // tile row = TMEM lane
     const int hw_tile = a.TH * a.TW;
     const int nb = m / hw_tile, rr = (m - nb * hw_tile) / a.TW, cc = m % a.TW;
     const bool warp_uniform_image = (hw_tile % 32) == 0;
     uint32_t acc = 0, acc_phase = 0;
+    unsigned long long w_epi = 0;
+    unsigned long long* dwe = (a.dbg && ew == 0 && lane == 0) ? &w_epi : nullptr;
+    const long long t_start = clock64();
+    int n_my_tiles = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      const int ph_idx = tile / a.tiles_per_phase;
-      int r = tile - ph_idx * a.tiles_per_phase;
-      const int bt = r / (a.tiles_h * a.tiles_w);
-      r -= bt * a.tiles_h * a.tiles_w;
-      const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
-      const int b = bt * a.NB + nb, j = ht * a.TH + rr, i = wt * a.TW + cc;
-      const bool valid = b < a.batch && j < a.PH && i < a.PW;
-      const int oy = j * a.up_h + ph_idx / a.up_w, ox = i * a.up_w + ph_idx % a.up_w;
-      const int64_t pix = ((int64_t)b * a.out_h + oy) * a.out_w + ox;
-      mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)a.n_pad;
-      for (int n0 = 0; n0 < a.n_pad; n0 += 16) {
-        uint32_t rg[16];
-        tc_ld16(taddr + (uint32_t)n0, rg);
-        tc_ld_wait();
-        float v[16];
+      ++n_my_tiles;
+      if (active) {
+        const int ph_idx = tile / a.tiles_per_phase;
+        int r = tile - ph_idx * a.tiles_per_phase;
+        const int bt = r / (a.tiles_h * a.tiles_w);
+        r -= bt * a.tiles_h * a.tiles_w;
+        const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
+        const int b = bt * a.NB + nb, j = ht * a.TH + rr, i = wt * a.TW + cc;
+        const bool valid = b < a.batch && j < a.PH && i < a.PW;
+        const int oy = j * a.up_h + ph_idx / a.up_w, ox = i * a.up_w + ph_idx % a.up_w;
+        const int64_t pix = ((int64_t)b * a.out_h + oy) * a.out_w + ox;
+        mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase, dwe);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)a.n_pad + (uint32_t)col0;
+        for (int c = 0; c < ncols; c += 32) {
+          const int nblk = min(32, ncols - c);        // 32, or a trailing 16
+          const int n0 = col0 + c;
+          uint32_t rg0[16], rg1[16];
+          tc_ld16(taddr + (uint32_t)c, rg0);
+          if (nblk == 32) tc_ld16(taddr + (uint32_t)c + 16, rg1);
+          tc_ld_wait();
+          float v[32];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) v[q] = act_apply(__uint_as_float(rg[q]) + __ldg(a.bias + n0 + q), a.act);
-        if (valid) {
-          if (a.out_f32) {
-            float* o = reinterpret_cast<float*>(a.dst) + pix * a.n_real + n0;
-            if (n0 + 16 <= a.n_real) {
+          for (int q = 0; q < 16; ++q) v[q] = act_apply(__uint_as_float(rg0[q]) + bias_s[n0 + q], a.act);
+          if (nblk == 32) {
 #pragma unroll
-              for (int q = 0; q < 16; q += 4) *reinterpret_cast<float4*>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
-            } else {
-              for (int q = 0; q < 16; ++q) if (n0 + q < a.n_real) o[q] = v[q];
-            }
+            for (int q = 0; q < 16; ++q) v[16 + q] = act_apply(__uint_as_float(rg1[q]) + bias_s[n0 + 16 + q], a.act);
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dst) + pix * a.n_real + n0;
-            if (n0 + 16 <= a.n_real) {
-              uint32_t pk[8];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                pk[q] = *reinterpret_cast<uint32_t*>(&t);
+            for (int q = 0; q < 16; ++q) v[16 + q] = 0.f;
+          }
+          if (valid) {
+            if (a.out_f32) {
+              float* o = reinterpret_cast<float*>(a.dst) + pix * a.n_real + n0;
+              if (n0 + nblk <= a.n_real) {
+#pragma unroll
+                for (int q = 0; q < 32; q += 4)
+                  if (q < nblk) *reinterpret_cast<float4*>(o + q) = make_float4(v[q], v[q + 1], v[q + 2], v[q + 3]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) o[q] = v[q];
               }
-              *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             } else {
-              for (int q = 0; q < 16; ++q) if (n0 + q < a.n_real) o[q] = __float2bfloat16_rn(v[q]);
+              __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(a.dst) + pix * a.n_real + n0;
+              if (n0 + nblk <= a.n_real) {
+                uint32_t pk[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                  __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                  pk[q] = *reinterpret_cast<uint32_t*>(&t);
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (8 * q < nblk) *reinterpret_cast<uint4*>(o + 8 * q) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) o[q] = __float2bfloat16_rn(v[q]);
+              }
             }
           }
-        }
-        if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:219)
-#pragma unroll
-          for (int q = 0; q < 16; ++q) {
-            float s = valid ? v[q] : 0.f;
+          if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:219)
             if (warp_uniform_image) {
+              // recursive-halving transpose-reduce: 31 shuffles turn 32 columns x 32 lanes into one column sum per lane
+              if (!valid) {
 #pragma unroll
-              for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-              if (lane == 0 && b < a.batch && n0 + q < a.n_real) atomicAdd(a.pool + (int64_t)b * a.n_real + n0 + q, s);
-            } else if (valid && n0 + q < a.n_real) {
-              atomicAdd(a.pool + (int64_t)b * a.n_real + n0 + q, s);
+                for (int q = 0; q < 32; ++q) v[q] = 0.f;
+              }
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int q = 0; q < off; ++q) {
+                  const float send = up ? v[q] : v[q + off];
+                  const float keep = up ? v[q + off] : v[q];
+                  v[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+                }
+              }
+              const int bw = __shfl_sync(0xffffffffu, b, 0);
+              if (lane < nblk && bw < a.batch && n0 + lane < a.n_real) atomicAdd(a.pool + (int64_t)bw * a.n_real + n0 + lane, v[0]);
+            } else if (valid) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) atomicAdd(a.pool + (int64_t)b * a.n_real + n0 + q, v[q]);
             }
           }
         }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (dwe) { a.dbg[blockIdx.x * 8 + 5] = w_epi; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start); a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)n_my_tiles; }
   }
   tc_fence_before();
   __syncthreads();
@@ -314,35 +419,37 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 // activations: channels-last complex bf16 (B, H, W, C2) -> 4-D map, box (CK, TW*sx, TH*sy, NB), element strides (1,sx,sy,1)
-static int make_act_map(CUtensorMap* m, const void* ptr, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C2 * 2, (cuuint64_t)W * C2 * 2, (cuuint64_t)H * W * C2 * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)C2 * esz, (cuuint64_t)W * C2 * esz, (cuuint64_t)H * W * C2 * esz};
   cuuint32_t box[4] = {(cuuint32_t)CK, (cuuint32_t)(TW * sx), (cuuint32_t)(TH * sy), (cuuint32_t)NB};
   cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
   DCS_REQUIRE(box[1] <= 256 && box[2] <= 256, "TMA box too large (%u x %u)", box[1], box[2]);
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CK * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+  CUresult r = fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CK * esz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with CUresult %d (C2=%d W=%d H=%d B=%d box=%d,%d,%d,%d)",
               (int)r, C2, W, H, B, CK, TW * sx, TH * sy, NB);
   return 0;
 }
 
-static int make_weight_map(CUtensorMap* m, const void* ptr, int Kpad, int rows, int n_pad) {
+static int make_weight_map(CUtensorMap* m, const void* ptr, int esz, int Kpad, int rows, int n_pad) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)Kpad * 2};
-  cuuint32_t box[2] = {(cuuint32_t)kKStep, (cuuint32_t)n_pad};
+  cuuint64_t strides[1] = {(cuuint64_t)Kpad * esz};
+  cuuint32_t box[2] = {(cuuint32_t)(kKStepBytes / esz), (cuuint32_t)n_pad};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
   return 0;
 }
+
+static unsigned long long* g_tc_dbg = nullptr;
 
 static int pick_pow2_tile(int extent, int max_tile) {
   // largest power of two <= max_tile whose padding waste is within 4 % of the best achievable
@@ -359,12 +466,12 @@ using namespace dcs;
 
 extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   if (int e = validate_conv(p, "dcs_cconv2d_tc_fwd")) return e;
-  DCS_REQUIRE(p->in_dtype == DCS_BF16, "dcs_cconv2d_tc_fwd: activations must be bf16");
+  const int esz = p->in_dtype == DCS_BF16 ? 2 : 4;  // bf16 operands (kind::f16) or fp32 operands read as tf32
+  const int kstep_elems = kKStepBytes / esz;
   const int C2s0 = 2 * p->c0, C2s1 = 2 * p->c1, C2 = C2s0 + C2s1;
-  DCS_REQUIRE(C2s0 % 16 == 0 && (p->c1 == 0 || C2s1 == C2s0 || (C2s0 % 64 == 0 && C2s1 % 64 == 0)),
-              "dcs_cconv2d_tc_fwd: unsupported channel split (%d, %d); use dcs_cconv2d_fwd", p->c0, p->c1);
-  const int CK = C2s0 >= 64 ? 64 : C2s0;
-  DCS_REQUIRE(CK == 16 || CK == 32 || CK == 64, "dcs_cconv2d_tc_fwd: 2*c0 must be 16, 32 or a multiple of 64 (got %d)", C2s0);
+  const int CK = C2s0 >= kstep_elems ? kstep_elems : C2s0;
+  DCS_REQUIRE(CK * esz == 32 || CK * esz == 64 || CK * esz == 128,
+              "dcs_cconv2d_tc_fwd: 2*c0*sizeof(elem) must be 32, 64 or a multiple of 128 bytes (got %d); use dcs_cconv2d_fwd", C2s0 * esz);
   DCS_REQUIRE(C2s0 % CK == 0 && C2s1 % CK == 0, "dcs_cconv2d_tc_fwd: channel counts must be multiples of %d", CK);
   const int N = 2 * p->cout, n_pad = (N + 15) / 16 * 16;
   DCS_REQUIRE(n_pad <= 256, "dcs_cconv2d_tc_fwd: 2*cout must be <= 256 (got %d)", N);
@@ -385,34 +492,42 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   a.phases = p->up_h * p->up_w;
   a.n_tiles = a.tiles_per_phase * a.phases;
   a.ntaps = p->ntaps; a.up_h = p->up_h; a.up_w = p->up_w; a.stride_h = p->stride_h; a.stride_w = p->stride_w;
-  a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK;
+  a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK; a.esz = esz;
   const int K = p->ntaps * C2;
-  a.ksteps = (K + kKStep - 1) / kKStep;
+  a.ksteps = (K + kstep_elems - 1) / kstep_elems;
   a.n_pad = n_pad; a.n_real = N; a.act = p->act; a.out_f32 = p->out_dtype == DCS_F32;
   a.batch = p->batch; a.out_h = p->out_h; a.out_w = p->out_w;
   memcpy(a.dy, p->dy, sizeof(a.dy));
   memcpy(a.dx, p->dx, sizeof(a.dx));
   DCS_REQUIRE(p->bias, "dcs_cconv2d_tc_fwd: bias is required (pass zeros)");
-  a.bias = p->bias; a.dst = p->dst; a.pool = p->pool_sums;
+  a.bias = p->bias; a.dst = p->dst; a.pool = p->pool_sums; a.dbg = g_tc_dbg;
 
-  const size_t stage_bytes = (size_t)kTileM * kKStep * 2 + (size_t)n_pad * kKStep * 2;
+  const size_t stage_bytes = (size_t)kTileM * kKStepBytes + (size_t)n_pad * kKStepBytes;
   int n_stages = (int)((200 * 1024) / stage_bytes);
   n_stages = std::max(2, std::min(n_stages, kMaxStages));
   a.n_stages = n_stages;
   const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers);
 
   CUtensorMap tmA0, tmA1, tmB;
-  if (int e = make_act_map(&tmA0, p->src0, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+  if (int e = make_act_map(&tmA0, p->src0, esz, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
   if (p->c1) {
-    if (int e = make_act_map(&tmA1, p->src1, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+    if (int e = make_act_map(&tmA1, p->src1, esz, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
   } else {
     tmA1 = tmA0;
   }
-  if (int e = make_weight_map(&tmB, p->weight, a.ksteps * kKStep, a.phases * n_pad, n_pad)) return e;
+  if (int e = make_weight_map(&tmB, p->weight, esz, a.ksteps * kstep_elems, a.phases * n_pad, n_pad)) return e;
 
   DCS_CUDA(cudaFuncSetAttribute(cconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(a.n_tiles, num_sms());
   cconv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, a);
   DCS_LAUNCHED();
+  return 0;
+}
+
+// Developer aid: when set to a device buffer of >= 8 * 148 uint64, every dcs_cconv2d_tc_fwd launch records per-CTA
+// cycle counters {producer wait-empty, producer total, mma wait-full, mma wait-acc, mma total, epilogue wait, epilogue
+// total, tiles}.  NULL (default) disables it.
+extern "C" int dcs_tc_set_debug_buffer(void* dev_ptr) {
+  g_tc_dbg = reinterpret_cast<unsigned long long*>(dev_ptr);
   return 0;
 }

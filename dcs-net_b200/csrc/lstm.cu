@@ -29,11 +29,11 @@ __global__ void lstm_deinterleave_kernel(const T* __restrict__ x, float* __restr
   }
 }
 
-// pre: gate pre-activations (bias included).  Row (part*B + b)*S + t, row stride `ld`, column offset `col0`
-// selects (lstm, dir).  hout: [q][S][2*kH], this direction writes columns dir*kH...
+// pre: gate pre-activations (bias included).  Row (part*B + b)*S + t with row stride `ld`; the (lstm, dir) block
+// starts at pre0 + lstm*stride_lstm + dir*stride_dir.  hout: [q][S][2*kH], this direction writes columns dir*kH...
 template <int NSEQ>
-__global__ void __launch_bounds__(256, 1) lstm_recurrent_kernel(const float* __restrict__ pre0, int64_t pre_lstm_stride,
-                                                                int ld, int col_lstm, const float* __restrict__ whh,
+__global__ void __launch_bounds__(256, 2) lstm_recurrent_kernel(const float* __restrict__ pre0, int64_t stride_lstm,
+                                                                int64_t stride_dir, int ld, const float* __restrict__ whh,
                                                                 float* __restrict__ hout, int B, int S) {
   // grid.x = (4B / NSEQ), grid.y = dir
   __shared__ __align__(16) float hs[NSEQ][kH];
@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent_kernel(const float* __r
     const float4 t = __ldg(reinterpret_cast<const float4*>(wrow + k));
     w[k] = t.x; w[k + 1] = t.y; w[k + 2] = t.z; w[k + 3] = t.w;
   }
-  const float* pre = pre0 + lstm * pre_lstm_stride + lstm * col_lstm + dir * kG + tid;
+  const float* pre = pre0 + lstm * stride_lstm + dir * stride_dir + tid;
   int64_t prow[NSEQ];
 #pragma unroll
   for (int s = 0; s < NSEQ; ++s) {
@@ -61,22 +61,32 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent_kernel(const float* __r
   const int cs = tid / kH, cu = tid % kH;
   float c_state = 0.f;
   for (int i = tid; i < NSEQ * kH; i += 256) (&hs[0][0])[i] = 0.f;
-  float pn[NSEQ];
-  {
-    const int t = dir ? S - 1 : 0;
+  // register prefetch queue: the pre-activations of steps t+1 .. t+kPF are in flight while step t is computed
+  // (an HBM round trip is ~2-3 recurrence steps long)
+  constexpr int kPF = 4;
+  float pq[kPF][NSEQ];
 #pragma unroll
-    for (int s = 0; s < NSEQ; ++s) pn[s] = __ldg(pre + (prow[s] + t) * ld);
+  for (int d = 0; d < kPF; ++d) {
+    const int st = min(d, S - 1);
+    const int t = dir ? S - 1 - st : st;
+#pragma unroll
+    for (int s = 0; s < NSEQ; ++s) pq[d][s] = __ldg(pre + (prow[s] + t) * ld);
   }
   __syncthreads();
   for (int step = 0; step < S; ++step) {
     const int t = dir ? S - 1 - step : step;
-    float acc[NSEQ];
+    float acc[NSEQ], acc2[NSEQ];  // two partial sums per sequence: halves the dependent-FMA chain length
 #pragma unroll
-    for (int s = 0; s < NSEQ; ++s) acc[s] = pn[s];
-    if (step + 1 < S) {
-      const int tn = dir ? t - 1 : t + 1;
+    for (int s = 0; s < NSEQ; ++s) { acc[s] = pq[0][s]; acc2[s] = 0.f; }
 #pragma unroll
-      for (int s = 0; s < NSEQ; ++s) pn[s] = __ldg(pre + (prow[s] + tn) * ld);
+    for (int d = 0; d + 1 < kPF; ++d)
+#pragma unroll
+      for (int s = 0; s < NSEQ; ++s) pq[d][s] = pq[d + 1][s];
+    {
+      const int st = min(step + kPF, S - 1);
+      const int tn = dir ? S - 1 - st : st;
+#pragma unroll
+      for (int s = 0; s < NSEQ; ++s) pq[kPF - 1][s] = __ldg(pre + (prow[s] + tn) * ld);
     }
 #pragma unroll
     for (int k = 0; k < kH; k += 4) {
@@ -84,21 +94,21 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent_kernel(const float* __r
       for (int s = 0; s < NSEQ; ++s) {
         const float4 h4 = *reinterpret_cast<const float4*>(&hs[s][k]);
         acc[s] = fmaf(w[k], h4.x, acc[s]);
-        acc[s] = fmaf(w[k + 1], h4.y, acc[s]);
+        acc2[s] = fmaf(w[k + 1], h4.y, acc2[s]);
         acc[s] = fmaf(w[k + 2], h4.z, acc[s]);
-        acc[s] = fmaf(w[k + 3], h4.w, acc[s]);
+        acc2[s] = fmaf(w[k + 3], h4.w, acc2[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < NSEQ; ++s) gs[s][tid] = acc[s];
+    for (int s = 0; s < NSEQ; ++s) gs[s][tid] = acc[s] + acc2[s];
     __syncthreads();
     if (cs < NSEQ) {
-      const float ig = sigmoidf_(gs[cs][cu]);
-      const float fg = sigmoidf_(gs[cs][kH + cu]);
-      const float gg = tanhf(gs[cs][2 * kH + cu]);
-      const float og = sigmoidf_(gs[cs][3 * kH + cu]);
+      const float ig = fast_sigmoid(gs[cs][cu]);
+      const float fg = fast_sigmoid(gs[cs][kH + cu]);
+      const float gg = fast_tanh(gs[cs][2 * kH + cu]);
+      const float og = fast_sigmoid(gs[cs][3 * kH + cu]);
       c_state = fg * c_state + ig * gg;
-      const float h = og * tanhf(c_state);
+      const float h = og * fast_tanh(c_state);
       hs[cs][cu] = h;
       hout[((int64_t)(q0 + cs) * S + t) * (2 * kH) + dir * kH + cu] = h;
     }
@@ -140,11 +150,22 @@ static int gemm_rows(const float* a, int64_t rows, int K, const float* w, const 
   return dcs_cconv2d_fwd(&c, stream);
 }
 
-template <int NSEQ>
-static void launch_rec(const float* pre, int64_t pre_lstm_stride, int ld, int col_lstm, const float* whh, float* hout, int B,
-                       int S, cudaStream_t s) {
-  dim3 grid(4 * B / NSEQ, 2);
-  lstm_recurrent_kernel<NSEQ><<<grid, 256, 0, s>>>(pre, pre_lstm_stride, ld, col_lstm, whh, hout, B, S);
+static void launch_rec(int nseq, const float* pre, int64_t stride_lstm, int64_t stride_dir, int ld, const float* whh,
+                       float* hout, int B, int S, cudaStream_t s) {
+  dim3 grid(4 * B / nseq, 2);
+  if (nseq == 4) lstm_recurrent_kernel<4><<<grid, 256, 0, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+  else lstm_recurrent_kernel<2><<<grid, 256, 0, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+}
+
+// tensor-core input projection (tf32 operands read from fp32 memory): out[rows][256] = a[rows][K] * w[256][K]^T + bias
+static int gemm_rows_tc(const float* a, int64_t rows, int K, const float* w_t, const float* bias, float* out, void* stream) {
+  dcs_cconv_params c;
+  memset(&c, 0, sizeof(c));
+  c.src0 = a; c.c0 = K / 2; c.c1 = 0;
+  c.batch = 1; c.in_h = 1; c.in_w = (int)rows; c.out_h = 1; c.out_w = (int)rows; c.cout = kG / 2;
+  c.up_h = c.up_w = 1; c.stride_h = c.stride_w = 1; c.ntaps = 1;
+  c.weight = w_t; c.bias = bias; c.act = DCS_ACT_NONE; c.dst = out; c.in_dtype = DCS_F32; c.out_dtype = DCS_F32;
+  return dcs_cconv2d_tc_fwd(&c, stream);
 }
 
 }  // namespace dcs
@@ -176,21 +197,33 @@ extern "C" int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream) {
   // NSEQ must divide 2B; 2 sequences per CTA (two co-resident CTAs per SM) unless that overflows the machine
   int nseq = 2;
   if ((2 * B) % 4 == 0 && (4 * B / 2) * 2 > 2 * num_sms()) nseq = 4;
-  // ---- layer 0: pre[(part,b,s)][lstm][dir][4H]
-  if (int e = gemm_rows(w.xp, 2 * rows, D, p->w_ih0, p->bias, 4 * kG, w.pre, stream)) return e;
-  if (nseq == 4) launch_rec<4>(w.pre, 0, 4 * kG, 2 * kG, p->w_hh, w.h0, B, S, s);
-  else launch_rec<2>(w.pre, 0, 4 * kG, 2 * kG, p->w_hh, w.h0, B, S, s);
-  DCS_LAUNCHED();
-  // ---- layer 1: per lstm, rows (part,b,s) of h0[lstm] -> pre1[lstm][(part,b,s)][dir][4H]
-  for (int l = 0; l < 2; ++l) {
-    if (int e = gemm_rows(w.h0 + (int64_t)l * 2 * rows * 2 * kH, 2 * rows, 2 * kH, p->w_ih1 + (int64_t)l * 2 * kH * 2 * kG,
-                          p->bias + 4 * kG + l * 2 * kG, 2 * kG, w.pre + (int64_t)l * 2 * rows * 2 * kG, stream))
-      return e;
-  }
   const float* whh1 = p->w_hh + (int64_t)4 * kG * kH;
-  if (nseq == 4) launch_rec<4>(w.pre, 2 * rows * 2 * kG, 2 * kG, 0, whh1, w.h1, B, S, s);
-  else launch_rec<2>(w.pre, 2 * rows * 2 * kG, 2 * kG, 0, whh1, w.h1, B, S, s);
-  DCS_LAUNCHED();
+  const int64_t rows2 = 2 * rows;
+  if (p->w_ih0_t && p->w_ih1_t) {
+    // ---- tensor-core (tf32) input projections: pre[(lstm,dir)][(part,b,s)][4H], eight N=256 GEMMs
+    for (int sl = 0; sl < 4; ++sl)
+      if (int e = gemm_rows_tc(w.xp, rows2, D, p->w_ih0_t + (int64_t)sl * kG * D, p->bias + sl * kG, w.pre + sl * rows2 * kG, stream)) return e;
+    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, p->w_hh, w.h0, B, S, s);
+    DCS_LAUNCHED();
+    for (int sl = 0; sl < 4; ++sl)
+      if (int e = gemm_rows_tc(w.h0 + (int64_t)(sl / 2) * rows2 * 2 * kH, rows2, 2 * kH, p->w_ih1_t + (int64_t)sl * kG * 2 * kH,
+                               p->bias + 4 * kG + sl * kG, w.pre + sl * rows2 * kG, stream)) return e;
+    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, whh1, w.h1, B, S, s);
+    DCS_LAUNCHED();
+  } else {
+    // ---- fp32 CUDA-core projections.  layer 0: pre[(part,b,s)][lstm][dir][4H]
+    if (int e = gemm_rows(w.xp, rows2, D, p->w_ih0, p->bias, 4 * kG, w.pre, stream)) return e;
+    launch_rec(nseq, w.pre, 2 * kG, kG, 4 * kG, p->w_hh, w.h0, B, S, s);
+    DCS_LAUNCHED();
+    // layer 1: per lstm, rows (part,b,s) of h0[lstm] -> pre1[lstm][(part,b,s)][dir][4H]
+    for (int l = 0; l < 2; ++l) {
+      if (int e = gemm_rows(w.h0 + (int64_t)l * rows2 * 2 * kH, rows2, 2 * kH, p->w_ih1 + (int64_t)l * 2 * kH * 2 * kG,
+                            p->bias + 4 * kG + l * 2 * kG, 2 * kG, w.pre + (int64_t)l * rows2 * 2 * kG, stream))
+        return e;
+    }
+    launch_rec(nseq, w.pre, rows2 * 2 * kG, kG, 2 * kG, whh1, w.h1, B, S, s);
+    DCS_LAUNCHED();
+  }
   {
     const int64_t n = rows * 2 * kH;
     const int g = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);

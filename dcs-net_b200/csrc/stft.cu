@@ -344,8 +344,9 @@ extern "C" int dcs_istft_fwd(const dcs_istft_params* p, void* stream) {
   DCS_REQUIRE(p && p->audio && (p->spec || (p->mag && p->phase)), "dcs_istft_fwd: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->n_frames >= 2, "dcs_istft_fwd: bad batch/n_frames (%d, %d)", p->batch, p->n_frames);
   const int n_chunks = istft_chunks(p->n_frames);
-  int cpc = max(4, (n_chunks * p->batch) / (2 * num_sms()));  // >= 4 keeps the halo re-compute <= 25 %
-  cpc = min(cpc, 32);
+  // chunks per CTA: 8 keeps the halo re-compute at 12.5 % while giving many more CTAs than resident slots, so
+  // the last wave is short (a single CTA per utterance for short inputs)
+  int cpc = min(8, n_chunks);
   dim3 grid((n_chunks + cpc - 1) / cpc, p->batch);
   const size_t smem = sizeof(IstftSmem);
   DCS_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

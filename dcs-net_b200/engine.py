@@ -60,7 +60,7 @@ class PackedNet:
         self.lstm = packing.pack_lstm(sd, "lstm.", device)
         w_r, w_i = sd["fc.fc_r.weight"], sd["fc.fc_i.weight"]
         self.fc = packing.PackedConv(w_r[:, :, None, None], w_i[:, :, None, None], sd["fc.fc_r.bias"], sd["fc.fc_i.bias"],
-                                     device=device, want_bf16=bf)
+                                     device=device, want_bf16=bf, want_tf32=bf)
 
 
 class ForwardPlan:
@@ -104,6 +104,16 @@ class ForwardPlan:
             self.dec.append(new(B, H, W, packed.dec[i].cout, 2, dtype=torch.float32 if last else adt))
             self.datt.append(None if last else new(B, H, W, packed.dec[i].cout, 2))
             max_hw = max(max_hw, src.shape[1] * src.shape[2], 0 if last else H * W)
+        # per-tensor pooling accumulators (numerators of ComplexAdaptiveAvgPool2d(1)), zeroed once per step; the
+        # tcgen05 conv epilogue accumulates into them so the attended tensors are not re-read for the pooling
+        self.fuse_pool = self.tc
+        chans = [t.shape[3] for t in self.enc] + [t.shape[3] for t in self.dec[:-1]]
+        self.pool_all = new(B * 2 * sum(chans), dtype=torch.float32)
+        views, off = [], 0
+        for c in chans:
+            views.append(self.pool_all[off:off + B * c * 2].view(B, c, 2))
+            off += B * c * 2
+        self.pool_enc, self.pool_dec = views[:len(self.enc)], views[len(self.enc):]
         self.sums = new(B, max_c, 2, dtype=torch.float32)
         self.gate = new(B, max_c, 2, dtype=torch.float32)
         self.stats = new(B, max_hw, 4, dtype=torch.float32)
@@ -118,23 +128,28 @@ class ForwardPlan:
         self.taps = {}
 
     # ------------------------------------------------------------------ building blocks
-    def _attention(self, x, ca, sa_w7, y):
-        """y = SA(CA(x) * x) * (CA(x) * x)   (c_network.py:208-211 / 219-220)."""
+    def _attention(self, x, ca, sa_w7, y, sums=None):
+        """y = SA(CA(x) * x) * (CA(x) * x)   (c_network.py:208-211 / 219-220).  `sums`: pooling numerators already
+        accumulated by the kernel that produced x; otherwise they are computed here."""
         B, H, W, Cn, _ = x.shape
-        sums, gate = self.sums[:, :Cn], self.gate[:, :Cn]
-        if not (sums.is_contiguous() and gate.is_contiguous()):
-            sums, gate = self.sums.view(-1)[: B * Cn * 2].view(B, Cn, 2), self.gate.view(-1)[: B * Cn * 2].view(B, Cn, 2)
+        gate = self.gate.view(-1)[: B * Cn * 2].view(B, Cn, 2)
         stats = self.stats.view(-1)[: B * H * W * 4].view(B, H * W, 4)
-        sums.zero_()
-        ops.chan_pool(x, sums)
+        if sums is None:
+            sums = self.sums.view(-1)[: B * Cn * 2].view(B, Cn, 2)
+            sums.zero_()
+            ops.chan_pool(x, sums)
         ops.chan_gate(sums, H * W, ca, gate)
         ops.spat_stats(x, gate, stats)
         ops.spat_apply(x, gate, stats, sa_w7, y)
         return y
 
-    def _conv(self, pk, src0, src1, dst):
-        use_tc = self.tc and pk.w_tc is not None and (2 * pk.cin) % 16 == 0 and src0.dtype == torch.bfloat16
-        return ops.cconv(pk, src0, src1, dst, use_tc=use_tc)
+    def _conv(self, pk, src0, src1, dst, pool=None):
+        """Returns (dst, pooled): pooled is True when the kernel accumulated the pooling sums into `pool`."""
+        use_tc = self.tc and (2 * pk.cin) % 16 == 0 and (
+            (src0.dtype == torch.bfloat16 and pk.w_tc is not None) or (src0.dtype == torch.float32 and pk.w_tc32 is not None))
+        fused = use_tc and self.fuse_pool and pool is not None
+        ops.cconv(pk, src0, src1, dst, use_tc=use_tc, pool_sums=pool if fused else None)
+        return dst, fused
 
     def _tap(self, name, t):
         if self.keep_taps:
@@ -144,39 +159,61 @@ class ForwardPlan:
     def _network(self):
         """bn0 -> ... -> decoder[6] raw output (c_network.py:193-222)."""
         pk, Lr = self.pk, self.pk.L
+        e0 = pk.enc[0]
+        fused_first = (e0.cin, e0.cout, e0.kh, e0.kw, e0.stride) == (1, 8, 7, 7, (2, 2))
+        if self.keep_taps or not fused_first:
+            ops.cbn_apply(torch.view_as_real(self.Y).view(self.B, self.F, self.T, 1, 2), pk.bn0, self.bn0)
         x = self.bn0
+        if self.fuse_pool:
+            self.pool_all.zero_()
+        enc_pooled = [False] * Lr
         for i in range(Lr):
-            x = self._conv(pk.enc[i], x, None, self.enc[i])
+            if i == 0 and fused_first:  # initial_batchnorm + encoder[0] straight from the spectrogram
+                x = ops.enc0(e0, self.Y, pk.bn0, self.enc[0])
+            else:
+                x, enc_pooled[i] = self._conv(pk.enc[i], x, None, self.enc[i], self.pool_enc[i])
             self._tap(f"enc{i}", x)
         B, H, W, _, _ = x.shape
-        ops.clstm(x.view(B, H * W, x.shape[3], 2), self.lat.view(B, H * W, 128, 2), pk.lstm, self.lstm_ws)
+        ops.clstm(x.view(B, H * W, x.shape[3], 2), self.lat.view(B, H * W, 128, 2), pk.lstm, self.lstm_ws, use_tc=self.tc)
         self._tap("lstm", self.lat)
-        d = self._conv(pk.fc, self.lat.view(B, 1, H * W, 128, 2), None, self.fc.view(B, 1, H * W, 128, 2)).view(self.fc.shape)
+        self._conv(pk.fc, self.lat.view(B, 1, H * W, 128, 2), None, self.fc.view(B, 1, H * W, 128, 2))
+        d = self.fc
         self._tap("fc", d)
         for i in range(Lr):
-            skip = self._attention(self.enc[Lr - 1 - i], pk.skip_ca[i], pk.skip_sa[i], self.skip[i])
+            e = Lr - 1 - i
+            skip = self._attention(self.enc[e], pk.skip_ca[i], pk.skip_sa[i], self.skip[i],
+                                   sums=self.pool_enc[e] if enc_pooled[e] else None)
             self._tap(f"skip{i}", skip)
-            d = self._conv(pk.dec[i], d, skip, self.dec[i])
-            if i != Lr - 1:
-                self._tap(f"dec{i}_act", d)
-                d = self._attention(d, pk.dec_ca[i], pk.dec_sa[i], self.datt[i])
+            if i == Lr - 1:
+                return d, skip  # decoder[6] is fused with the mask tail (dcs_dec6_tail_fwd)
+            d, pooled = self._conv(pk.dec[i], d, skip, self.dec[i], self.pool_dec[i])
+            self._tap(f"dec{i}_act", d)
+            d = self._attention(d, pk.dec_ca[i], pk.dec_sa[i], self.datt[i], sums=self.pool_dec[i] if pooled else None)
             self._tap(f"dec{i}", d)
-        return d
 
-    def _tail(self, raw):
-        ops.mask_combine(raw, self.Y, self.clean_spec, net_out=self.net_out, mask=self.mask, noise_spec=self.noise_spec,
-                         atan2_eps=self.eps, combine=L.COMBINE_DCS if self.variant == "dcs" else L.COMBINE_DC,
-                         exact_polar=self.exact)
+    def _tail(self, d_skip):
+        d, skip = d_skip
+        combine = L.COMBINE_DCS if self.variant == "dcs" else L.COMBINE_DC
+        pk6 = self.pk.dec[self.pk.L - 1]
+        if pk6.w_tail is not None:
+            raw = self.dec[-1] if self.keep_taps else None
+            ops.dec6_tail(pk6, d, skip, self.Y, self.clean_spec, net_raw=raw, net_out=self.net_out, mask=self.mask,
+                          noise_spec=self.noise_spec, atan2_eps=self.eps, combine=combine, exact_polar=self.exact)
+            if self.keep_taps:
+                self._tap(f"dec{self.pk.L - 1}", raw)
+        else:  # non-default channel configuration: un-fused last layer + tail
+            raw, _ = self._conv(pk6, d, skip, self.dec[-1])
+            ops.mask_combine(raw, self.Y, self.clean_spec, net_out=self.net_out, mask=self.mask,
+                             noise_spec=self.noise_spec, atan2_eps=self.eps, combine=combine, exact_polar=self.exact)
 
     def _enqueue_from_audio(self, with_noise_audio=False):
-        ops.stft(self.audio_in, self.Y, bn_affine=self.pk.bn0, bn_out=self.bn0)
+        ops.stft(self.audio_in, self.Y)
         self._tail(self._network())
         ops.istft(self.clean_spec, self.audio_out, self.eps, self.exact)
         if with_noise_audio and self.noise_audio is not None:
             ops.istft(self.noise_spec, self.noise_audio, self.eps, self.exact)
 
     def _enqueue_from_spec(self):
-        ops.cbn_apply(torch.view_as_real(self.Y).view(self.B, self.F, self.T, 1, 2), self.pk.bn0, self.bn0)
         self._tail(self._network())
 
     # ------------------------------------------------------------------ public

@@ -34,7 +34,8 @@ def stft(audio, spec=None, bn_affine=None, bn_out=None):
 def istft(spec, audio=None, atan2_eps=1e-6, exact_polar=False):
     """(B, 256, T) complex64 -> (B, 32 (T-1)) fp32 [network_functions.py:398-401 + 140-150]."""
     L.require_cuda(spec)
-    assert spec.dtype == torch.complex64 and spec.dim() == 3 and spec.shape[1] == BINS and spec.is_contiguous()
+    assert spec.dtype == torch.complex64 and spec.dim() == 3 and spec.shape[1] == BINS
+    spec = spec.contiguous()
     B, _, T = spec.shape
     if audio is None:
         audio = torch.empty(B, HOP * (T - 1), dtype=torch.float32, device=spec.device)
@@ -84,7 +85,12 @@ def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
     p.ntaps = pk.ntaps
     for i, (a, b) in enumerate(zip(pk.dy, pk.dx)):
         p.dy[i], p.dx[i] = a, b
-    p.weight = L.ptr(pk.w_tc if use_tc else pk.w_ffma)
+    if use_tc:
+        w = pk.w_tc if src0.dtype == torch.bfloat16 else pk.w_tc32
+        assert w is not None, "PackedConv was not packed for this tensor-core operand type"
+    else:
+        w = pk.w_ffma
+    p.weight = L.ptr(w)
     p.bias = L.ptr(pk.bias)
     p.act = pk.act
     p.dst, p.in_dtype, p.out_dtype = L.ptr(dst), _code(src0), _code(dst)
@@ -133,11 +139,12 @@ def clstm_workspace_bytes(B, S, hidden=64):
     return int(n)
 
 
-def clstm(x, y, w, workspace):
-    """x (B,S,D,2) -> y (B,S,2*hidden,2) fp32.  w = packing.pack_lstm(...)."""
+def clstm(x, y, w, workspace, use_tc=False):
+    """x (B,S,D,2) -> y (B,S,2*hidden,2) fp32.  w = packing.pack_lstm(...).  use_tc: tf32 tensor-core projections."""
     B, S, D, _ = x.shape
     p = L.ClstmParams(L.ptr(x), L.ptr(y), B, S, D, y.shape[2] // 2, _code(x), L.ptr(w["w_ih0"]), L.ptr(w["w_ih1"]),
-                      L.ptr(w["w_hh"]), L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size())
+                      L.ptr(w["w_hh"]), L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size(),
+                      L.ptr(w["w_ih0_t"]) if use_tc else None, L.ptr(w["w_ih1_t"]) if use_tc else None)
     L.check(L.lib().dcs_clstm_fwd(C.byref(p), L.stream_ptr()), "dcs_clstm_fwd")
     return y
 
@@ -148,6 +155,27 @@ def mask_combine(net_raw, noisy_spec, clean_spec, net_out=None, mask=None, noise
     p = L.MaskCombineParams(L.ptr(net_raw), L.ptr(noisy_spec), L.ptr(net_out), L.ptr(mask), L.ptr(noise_spec),
                             L.ptr(clean_spec), n, float(atan2_eps), combine, int(exact_polar))
     L.check(L.lib().dcs_mask_combine(C.byref(p), L.stream_ptr()), "dcs_mask_combine")
+    return clean_spec
+
+
+def enc0(pk, spec, bn_affine, dst):
+    """initial_batchnorm + encoder[0] (+BN+ReLU) straight from the complex64 spectrogram (B,F,T)."""
+    B, F, T = spec.shape
+    assert (pk.cin, pk.cout, pk.kh, pk.kw, pk.stride) == (1, 8, 7, 7, (2, 2)) and pk.act == ACT_RELU
+    p = L.Enc0Params(L.ptr(spec), L.ptr(bn_affine), L.ptr(pk.w_ffma), L.ptr(pk.bias), L.ptr(dst), _code(dst), B, F, T)
+    L.check(L.lib().dcs_enc0_fwd(C.byref(p), L.stream_ptr()), "dcs_enc0_fwd")
+    return dst
+
+
+def dec6_tail(pk, d, skip, noisy_spec, clean_spec, net_raw=None, net_out=None, mask=None, noise_spec=None,
+              atan2_eps=1e-6, combine=L.COMBINE_DCS, exact_polar=False):
+    """decoder[6] + bound_cRM x2 + combine in one kernel.  pk: PackedConv of decoder[6] (has .w_tail, .bias)."""
+    B, H, W, Cn, _ = d.shape
+    assert Cn == 8 and skip.shape == d.shape and pk.cout == 1 and pk.up == (2, 2)
+    p = L.Dec6TailParams(L.ptr(d), L.ptr(skip), _code(d), B, H, W, L.ptr(pk.w_tail), float(pk.bias_host[0]),
+                         float(pk.bias_host[1]), L.ptr(noisy_spec), L.ptr(net_raw), L.ptr(net_out), L.ptr(mask),
+                         L.ptr(noise_spec), L.ptr(clean_spec), float(atan2_eps), combine, int(exact_polar))
+    L.check(L.lib().dcs_dec6_tail_fwd(C.byref(p), L.stream_ptr()), "dcs_dec6_tail_fwd")
     return clean_spec
 
 

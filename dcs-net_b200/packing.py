@@ -16,8 +16,9 @@ BN_EPS = 1e-5
 
 def bn_affine(weight, bias, running_mean, running_covar, eps=BN_EPS):
     """Eval-mode ComplexBatchNorm2d as y = A [re; im] + c.  Returns (A (C,2,2), c (C,2)) in float64."""
-    w, b = weight.double(), bias.double()
-    cov = running_covar.double()
+    w, b = weight.detach().cpu().double(), bias.detach().cpu().double()
+    cov = running_covar.detach().cpu().double()
+    running_mean = running_mean.detach().cpu()
     mu = torch.stack([running_mean.real.double(), running_mean.imag.double()], dim=1)
     Crr, Cii, Cri = cov[:, 0] + eps, cov[:, 1] + eps, cov[:, 2]
     s = torch.sqrt(Crr * Cii - Cri * Cri)
@@ -39,6 +40,14 @@ def affine6(A, c):
     return torch.cat([A.reshape(-1, 4), c], dim=1).float().contiguous()
 
 
+def round_tf32(t):
+    """fp32 -> nearest tf32 (10-bit mantissa, ties to even), returned as fp32: the tensor core truncates the low 13
+    mantissa bits of fp32 operands, so weights are pre-rounded on the host."""
+    i = t.detach().float().contiguous().view(torch.int32)
+    i = (i + 0xFFF + ((i >> 13) & 1)) & ~0x1FFF
+    return i.view(torch.float32)
+
+
 def _phase_taps(k, up):
     """Rows of a k-tap 1-D kernel (pad k//2) applied after nearest x`up`: per phase, {source offset: [taps]}."""
     pad = k // 2
@@ -56,7 +65,7 @@ class PackedConv:
     """GEMM operands of one complex convolution layer (see include/dcsnet.h: dcs_cconv_params)."""
 
     def __init__(self, w_r, w_i, b_r=None, b_i=None, bn=None, transposed=False, stride=(1, 1), up=(1, 1),
-                 act=0, device="cpu", want_bf16=False):
+                 act=0, device="cpu", want_bf16=False, want_tf32=False):
         w_r, w_i = w_r.detach().double().cpu(), w_i.detach().double().cpu()
         if transposed:  # (Cin, Cout, k, k) -> equivalent conv weight (Cout, Cin, k, k), spatially flipped
             w_r = w_r.permute(1, 0, 2, 3).flip(2, 3)
@@ -103,9 +112,22 @@ class PackedConv:
             wt = torch.zeros(self.phases, self.n_pad, self.k_pad, dtype=torch.float64)
             wt[:, :, :K] = Wp.permute(0, 2, 1, 3).reshape(self.phases, self.n_pad, K)
             self.w_tc = wt.to(torch.bfloat16).contiguous().to(device)
+        self.w_tc32 = None
+        if want_tf32:
+            K = self.ntaps * C2
+            k_pad = (K + 31) // 32 * 32  # one pipeline stage = 128 bytes of K = 32 fp32
+            wt = torch.zeros(self.phases, self.n_pad, k_pad, dtype=torch.float64)
+            wt[:, :, :K] = Wp.permute(0, 2, 1, 3).reshape(self.phases, self.n_pad, K)
+            self.w_tc32 = round_tf32(wt.float()).contiguous().to(device)
         b = torch.zeros(self.n_pad, dtype=torch.float64)
         b[:N] = bias.reshape(-1)
         self.bias = b.float().to(device)
+        self.bias_host = b.float().tolist()
+        self.w_tail = None
+        if cout == 1 and tuple(up) == (2, 2) and cin == 16:
+            # dcs_dec6_tail_fwd operand: [phase][tap][ci][(M00 M01 M10 M11)]
+            self.w_tail = Wp[:, :, :2].reshape(self.phases, self.ntaps, 2, cin, 2).permute(0, 1, 3, 2, 4) \
+                .contiguous().float().to(device)
 
 
 def pack_lstm(sd, prefix, device, hidden=64, layers=2):
@@ -122,7 +144,11 @@ def pack_lstm(sd, prefix, device, hidden=64, layers=2):
     whh = torch.stack([torch.stack([torch.stack([g(f"{n}.weight_hh_l{l}{s}") for s in sfx], 0) for n in names], 0)
                        for l in range(2)], 0)                                                # (2,2,2,256,64)
     f = lambda t: t.contiguous().float().to(device)
-    return dict(w_ih0=f(w0.t()), w_ih1=f(w1), w_hh=f(whh), bias=f(torch.cat([b0, b1], 0)))
+    # tensor-core operands: K-major slices [lstm*2+dir][4H][K], pre-rounded to tf32
+    w0_t = round_tf32(w0.float().reshape(4, 4 * hidden, -1))
+    w1_t = round_tf32(w1.permute(0, 2, 1).float().reshape(4, 4 * hidden, 2 * hidden))
+    return dict(w_ih0=f(w0.t()), w_ih1=f(w1), w_hh=f(whh), bias=f(torch.cat([b0, b1], 0)),
+                w_ih0_t=f(w0_t), w_ih1_t=f(w1_t))
 
 
 def pack_channel_attention(sd, prefix, device):

@@ -84,7 +84,8 @@ int dcs_cbn_apply(const dcs_cbn_params* p, void* stream);
  *      (j, i) in [0,out_h/up_h) x [0,out_w/up_w); tap t of phase p reads source pixel
  *      (j*stride_h + dy[p*ntaps+t], i*stride_w + dx[p*ntaps+t]), zero outside [0,in_h) x [0,in_w).
  *      weight: FFMA path  fp32 [phases][ntaps][2*(c0+c1)][2*cout]   (N contiguous)
- *              tcgen05    bf16 [phases][n_pad][ntaps*2*(c0+c1)]      (K contiguous), n_pad = max(16, 2*cout)
+ *              tcgen05    bf16 (in_dtype BF16, kind::f16) or fp32 pre-rounded to tf32 (in_dtype F32, kind::tf32)
+ *                         [phases][n_pad][K padded to 128 bytes]     (K contiguous), n_pad = max(16, 2*cout)
  *      bias:   fp32 [2*cout] added before `act`.
  *      pool_sums (optional, fp32 [B][2*cout], pre-zeroed): per-(b, channel) sums of the epilogue output, i.e. the
  *      numerator of ComplexAdaptiveAvgPool2d(1) for the channel attention that follows (c_network.py:219). */
@@ -139,6 +140,9 @@ typedef struct {
   const void* x; float* y; int batch; int seq; int in_dim; int hidden; int in_dtype;
   const float* w_ih0; const float* w_ih1; const float* w_hh; const float* bias;
   void* workspace; int64_t workspace_bytes;
+  /* optional tensor-core input projections (tf32 operands, kind::tf32): K-major weight slices [4 = lstm*2+dir][4H][D]
+   * for layer 0 and [4][4H][2H] for layer 1, pre-rounded to tf32.  NULL -> fp32 CUDA-core GEMMs. */
+  const float* w_ih0_t; const float* w_ih1_t;
 } dcs_clstm_params;
 int64_t dcs_clstm_workspace_bytes(int batch, int seq, int hidden);
 int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream);
@@ -153,6 +157,29 @@ typedef struct {
 } dcs_mask_combine_params;
 int dcs_mask_combine(const dcs_mask_combine_params* p, void* stream);
 
+/* ---- a3 (initial_batchnorm) + a4 (encoder[0]) + a5 fused: ComplexConv2d(1 -> 8, k7, stride (2,2), pad 3) on
+ *      initial_batchnorm(x) (c_network.py:190, 107-114), eval BN + ComplexReLU folded.  spec: (B, h, w) complex64
+ *      (the spectrogram itself); bn_affine: 6 floats (folded initial_batchnorm) applied on load, padding stays 0;
+ *      weight: fp32 [49 taps][2 (re,im of the input)][16] (same layout as the FFMA operand); dst (B, h/2, w/2, 8). */
+typedef struct {
+  const float* spec; const float* bn_affine; const float* weight; const float* bias;
+  void* dst; int out_dtype; int batch; int h; int w;
+} dcs_enc0_params;
+int dcs_enc0_fwd(const dcs_enc0_params* p, void* stream);
+
+/* ---- a12 (last layer) + a13 + a14 fused: decoder[6] = ComplexConvTranspose2d(16 -> 1, k3 s1 p1) applied to
+ *      cat(d, skip_sa) up-sampled (2,2) (c_network.py:214-216, 134-140), then the whole tail of dcs_mask_combine.
+ *      d, skip: (B, h, w, 8) channels-last complex of in_dtype; outputs (B, 2h, 2w) complex64.  N = 2 cannot feed a
+ *      tensor core, so this is a CUDA-core kernel; decoder[6]'s raw output never reaches HBM (net_raw optional).
+ *      weight: fp32 [4 phases][4 taps][16 ci][4] = the real 2x2 block (M00 M01 M10 M11) of each pre-summed tap. */
+typedef struct {
+  const void* d; const void* skip; int in_dtype; int batch; int h; int w;
+  const float* weight; float bias_re; float bias_im;
+  const float* noisy_spec; float* net_raw; float* net_out; float* mask; float* noise_spec; float* clean_spec;
+  float atan2_eps; int combine; int exact_polar;
+} dcs_dec6_tail_params;
+int dcs_dec6_tail_fwd(const dcs_dec6_tail_params* p, void* stream);
+
 /* ---- stand-alone element-wise functions of network_functions.py (used by the step functions outside forward):
  *      bound_cRM (77-88), complex_mat_mult (90-96), cRM (62-75, eps inside both denominators). n complex elements. */
 int dcs_bound_crm(const float* x, float* y, int64_t n, float atan2_eps, int exact_polar, void* stream);
@@ -163,6 +190,9 @@ int dcs_crm(const float* s, const float* y_noisy, float* m, int64_t n, float eps
  *      (The fused path never materialises this: see dcs_cconv_params.up_h/up_w.) */
 int dcs_upsample_nearest(const void* x, void* y, int batch, int h, int w, int channels, int up_h, int up_w, int dtype,
                          void* stream);
+
+/* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */
+int dcs_tc_set_debug_buffer(void* dev_ptr);
 
 /* ---- layout helpers for the layer-wise drop-in modules: fp32 <-> bf16 copies of channels-last activations */
 int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_dtype, int out_dtype, void* stream);

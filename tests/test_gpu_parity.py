@@ -52,7 +52,7 @@ def test_istft_golden(key, exact):
 @pytest.mark.parametrize("B,T", [(1, 17), (3, 256), (2, 2000)])
 def test_stft_istft_vs_oracle_ragged_and_full_length(B, T):
     _, _, noisy = O.synthetic_audio(B, 32 * (T - 1), seed=T)
-    spec = O.stft(noisy)
+    spec = O.stft(noisy).contiguous()
     assert rel_err(ops.stft(noisy.cuda()), spec) <= TOL_FFT
     assert rel_err(ops.istft(spec.cuda(), atan2_eps=EPS), O.spec_to_wave(spec)) <= TOL_FFT
 
@@ -191,7 +191,8 @@ def test_full_size_batch_subset_vs_oracle_and_batch_independence(mode, tol):
     perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
     out_p = plan.enhance_audio(noisy[perm].cuda())
     torch.cuda.synchronize()
-    assert rel_err(out_p, full[perm.cuda()]) <= 1e-5
+    # fp32: only the atomic pooling order differs; bf16: a 1-ulp flip of a stored activation is 4e-3 of its value
+    assert rel_err(out_p, full[perm.cuda()]) <= (1e-5 if mode == "fp32" else 2e-3)
     del plan
 
 
@@ -207,7 +208,8 @@ def test_layer_classes_match_oracle_functions():
     assert rel_err(net.encoder[2](x.cuda()), ref) <= 1e-5
     # ComplexConvTranspose2d (decoder 5 conv) on an explicit cat+upsample input
     u = O.cupsample_nearest(rc(2, 32, 8, 6), (2, 2))
-    assert rel_err(CF.complex_upsample(rc(1, 4, 3, 5).cuda(), scale_factor=(2, 1)).shape, torch.Size([1, 4, 6, 5])) == 0
+    v = rc(1, 4, 3, 5)
+    assert torch.equal(CF.complex_upsample(v.cuda(), scale_factor=(2, 1)).cpu(), O.cupsample_nearest(v, (2, 1)))
     assert rel_err(net.decoder[5][0](u.cuda()), O.cconvT2d(u, sd, "decoder.5.0.", 1, 1)) <= 1e-5
     # attention gates
     y = rc(2, 64, 16, 12)

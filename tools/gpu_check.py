@@ -115,6 +115,93 @@ def part_tcunit(B, T):
         print(json.dumps({"part": "tcunit", "layer": name, "rel": rel(got.float(), ref), "nan": int(torch.isnan(got.float()).sum())}))
 
 
+def part_layers(B, T):
+    """per-layer timing of the tcgen05 conv (and the FFMA layers) at full size"""
+    sd = SW.make_state_dict(0)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    plan = D.ForwardPlan(pk, B, T, want_aux=False)
+    _, _, noisy = O.synthetic_audio(B, 32 * (T - 1))
+    plan.enhance_audio(noisy.cuda())
+    torch.cuda.synchronize()
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    fl = bench.conv_flops_per_utterance(T)
+    Lr = 7
+    jobs = []
+    x = plan.bn0
+    for i in range(Lr):
+        jobs.append((f"enc{i}", pk.enc[i], x, None, plan.enc[i]))
+        x = plan.enc[i]
+    d = plan.fc
+    for i in range(Lr):
+        jobs.append((f"dec{i}", pk.dec[i], d, plan.skip[i], plan.dec[i]))
+        d = plan.datt[i]
+    def timeit(label, fn, extra=None):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        d = {"op": label, "ms": round(e0.elapsed_time(e1) / 5, 4)}
+        d.update(extra or {})
+        print(json.dumps(d))
+
+    Hh, Ww = plan.enc[6].shape[1], plan.enc[6].shape[2]
+    timeit("stft", lambda: ops.stft(plan.audio_in, plan.Y))
+    timeit("enc0", lambda: ops.enc0(pk.enc[0], plan.Y, pk.bn0, plan.enc[0]))
+    timeit("clstm", lambda: ops.clstm(plan.enc[6].view(B, Hh * Ww, 128, 2), plan.lat.view(B, Hh * Ww, 128, 2), pk.lstm, plan.lstm_ws, use_tc=True))
+    timeit("fc", lambda: ops.cconv(pk.fc, plan.lat.view(B, 1, Hh * Ww, 128, 2), None, plan.fc.view(B, 1, Hh * Ww, 128, 2), use_tc=True))
+    timeit("dec6_tail", lambda: ops.dec6_tail(pk.dec[6], plan.datt[5], plan.skip[6], plan.Y, plan.clean_spec))
+    timeit("istft", lambda: ops.istft(plan.clean_spec, plan.audio_out))
+    for i in range(7):
+        x = plan.enc[6 - i]
+        timeit(f"skip_att{i}", lambda: plan._attention(x, pk.skip_ca[i], pk.skip_sa[i], plan.skip[i]),
+               {"C": x.shape[3], "MB": round(x.numel() * x.element_size() / 1e6, 1)})
+    for i in range(6):
+        x = plan.dec[i]
+        timeit(f"dec_att{i}", lambda: plan._attention(x, pk.dec_ca[i], pk.dec_sa[i], plan.datt[i]),
+               {"C": x.shape[3], "MB": round(x.numel() * x.element_size() / 1e6, 1)})
+    x = plan.dec[5]
+    st = plan.stats.view(-1)[: B * x.shape[1] * x.shape[2] * 4].view(B, -1, 4)
+    gt = plan.gate.view(-1)[: B * 8 * 2].view(B, 8, 2)
+    timeit("dec_att5.stats", lambda: ops.spat_stats(x, gt, st))
+    timeit("dec_att5.apply", lambda: ops.spat_apply(x, gt, st, pk.dec_sa[5], plan.datt[5]))
+    dbg = torch.zeros(148 * 8, dtype=torch.int64, device="cuda")
+    for name, p, s0, s1, dst in jobs:
+        if name in ("enc0", "dec6"):
+            continue
+        use_tc = (2 * p.cin) % 16 == 0
+        D._lib.lib().dcs_tc_set_debug_buffer(D._lib.ptr(dbg))
+        dbg.zero_()
+        ops.cconv(p, s0, s1, dst, use_tc=use_tc)
+        torch.cuda.synchronize()
+        D._lib.lib().dcs_tc_set_debug_buffer(None)
+        d = dbg.view(148, 8).double()
+        act = d[:, 7] > 0
+        m = d[act].mean(0)
+        print(json.dumps({"layer": name, "dbg_kcycles": {"prod_wait_empty": round(float(m[0]) / 1e3, 1), "prod_total": round(float(m[1]) / 1e3, 1),
+              "mma_wait_full": round(float(m[2]) / 1e3, 1), "mma_wait_acc": round(float(m[3]) / 1e3, 1), "mma_total": round(float(m[4]) / 1e3, 1),
+              "epi_wait": round(float(m[5]) / 1e3, 1), "epi_total": round(float(m[6]) / 1e3, 1), "tiles_per_cta": round(float(m[7]), 1)}}))
+        for _ in range(2):
+            ops.cconv(p, s0, s1, dst, use_tc=use_tc)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n = 5
+        e0.record()
+        for _ in range(n):
+            ops.cconv(p, s0, s1, dst, use_tc=use_tc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / n
+        in_bytes = s0.numel() * s0.element_size() + (s1.numel() * s1.element_size() if s1 is not None else 0)
+        out_bytes = dst.numel() * dst.element_size()
+        print(json.dumps({"layer": name, "tc": use_tc, "ms": round(ms, 4), "tflops_ref": round(B * fl[name] / ms / 1e9, 1),
+                          "N": 2 * p.cout, "K": p.ntaps * 2 * p.cin * p.phases, "in_MB": round(in_bytes / 1e6, 1), "out_MB": round(out_bytes / 1e6, 1),
+                          "GBps_min": round((in_bytes + out_bytes) / ms / 1e6, 1)}))
+
+
 def part_time(mode, B, T):
     sd = SW.make_state_dict(0)
     pk = D.PackedNet(sd, "cuda", mode)
@@ -158,6 +245,8 @@ if __name__ == "__main__":
         part_net(part, B, T)
     elif part == "tcunit":
         part_tcunit(B, T)
+    elif part == "layers":
+        part_layers(B, T)
     elif part.startswith("time"):
         part_time(part.split("_")[1], B, T)
     print(f"# {part} done in {time.time() - t0:.1f}s", file=sys.stderr)
