@@ -69,7 +69,8 @@ class SpatApplyParams(C.Structure):
 class ClstmParams(C.Structure):
     _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("in_dtype", _i),
                 ("w_ih0", _vp), ("w_ih1", _vp), ("w_hh", _vp), ("bias", _vp),
-                ("workspace", _vp), ("workspace_bytes", _i64), ("w_ih0_t", _vp), ("w_ih1_t", _vp)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("w_ih0_t", _vp), ("w_ih1_t", _vp),
+                ("seqs_per_cta", _i)]
 
 
 class MaskCombineParams(C.Structure):

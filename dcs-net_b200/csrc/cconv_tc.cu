@@ -17,6 +17,7 @@
 // (TMEM -> registers -> bias/activation -> bf16 -> global, plus optional per-(image, channel) pooling sums).
 #include <cuda.h>
 #include <string.h>
+#include <stdlib.h>
 #include <algorithm>
 #include "common.cuh"
 
@@ -26,7 +27,8 @@ int validate_conv(const dcs_cconv_params* p, const char* who);
 
 constexpr int kTileM = 128;
 constexpr int kKStepBytes = 128;         // bytes of K per pipeline stage (= one 128-byte swizzle row): 64 bf16 or 32 tf32
-constexpr int kTcThreads = 320;    // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kTcThreads = 448;    // warp 0 TMA, warp 1 MMA, warps 2..5 A-gather (cp.async), warps 6..13 epilogue
+constexpr int kGatherThreads = 128;
 constexpr int kMaxStages = 8;
 constexpr uint32_t kSpinLimit = 1u << 26;  // mbarrier spin cap: trap instead of hanging the GPU
 
@@ -37,6 +39,11 @@ struct TcArgs {
   int phases, ntaps, up_h, up_w, stride_h, stride_w;
   int C2, C2_src0, CK, ksteps, n_stages;
   int esz;                    // operand element size: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32)
+  int gather;                 // 1: A tiles are gathered by 4 warps with 16-byte cp.async (rows shorter than 128 B or
+                              //    small N, where the per-row cost of TMA boxes dominates); 0: A tiles come from TMA boxes
+  int tw_log2, th_log2;       // tile extents are powers of two
+  int in_h, in_w;
+  const void* src0; const void* src1;
   int n_pad, n_real, act, out_f32;
   int batch, out_h, out_w;
   int8_t dy[DCS_MAX_TAPS], dx[DCS_MAX_TAPS];
@@ -85,6 +92,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
+}
+// 16-byte global->shared async copy, zero-filled when src_bytes == 0 (image border / K padding)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+// arrive on `bar` once all cp.async issued so far by this thread have landed (the arrival is pre-counted at init)
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 // One elected lane of a converged warp (CUTLASS elect_one_sync).  The single-thread roles keep the WHOLE warp in the
 // control loop (warp-uniform values stay in uniform registers, which UTCHMMA / UTMALDG take as operands) and only
@@ -159,7 +174,8 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   const uint32_t tmem_cols = a.n_pad <= 16 ? 32u : (a.n_pad <= 32 ? 64u : (a.n_pad <= 64 ? 128u : (a.n_pad <= 128 ? 256u : 512u)));
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.n_stages; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    const uint32_t full_count = a.gather ? 1u + kGatherThreads : 1u;  // B-TMA expect_tx arrive (+ one per gather thread)
+    for (int s = 0; s < a.n_stages; ++s) { mbar_init(smem_u32(&bars->full[s]), full_count); mbar_init(smem_u32(&bars->empty[s]), 1); }
     const uint32_t n_epi_warps = (a.n_pad % 32) == 0 ? 8u : 4u;
     for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), n_epi_warps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -207,9 +223,9 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           mbar_wait(bar_empty0 + 8u * stage, phase_bit ^ 1, dw);
           const uint32_t full = bar_full0 + 8u * stage;
           const bool leader = elect_one();
-          if (leader) mbar_expect_tx(full, stage_bytes);
+          if (leader) mbar_expect_tx(full, a.gather ? b_bytes : stage_bytes);
           uint32_t dst = smem_base + stage * stage_bytes;
-          for (int g = 0; g < sub_per_step; ++g) {
+          for (int g = 0; g < (a.gather ? 0 : sub_per_step); ++g) {
             if (leader) {
               if (c < a.C2_src0) tma_load_4d(dst, &tmA0, full, c, x, y, b0);
               else tma_load_4d(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
@@ -235,7 +251,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       // instruction descriptor: D=F32, A=B=BF16 (1) or TF32 (2), both K-major, N>>3 @17, M>>4 @24
       const uint32_t fmt = a.esz == 2 ? 1u : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-      const uint32_t a_row_bytes = (uint32_t)(a.CK * a.esz);
+      const uint32_t a_row_bytes = a.gather ? 128u : (uint32_t)(a.CK * a.esz);  // gathered tiles are always 128 x 128 B, SWIZZLE_128B
       // Descriptors = constant high word + (start address >> 4) in the low word; per-MMA byte offsets inside a stage
       // are precomputed once so the issue loop is a handful of 32-bit adds per MMA (single latency-exposed thread).
       const uint64_t a_desc0 = umma_desc(0, a_row_bytes), b_desc0 = umma_desc(0, 128);
@@ -278,10 +294,69 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       }
       if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 2] = w_full; a.dbg[blockIdx.x * 8 + 3] = w_acc; a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_start); }
     }
+  } else if (warp < 6) {
+    // ===================================================================== A gather producers (4 warps, cp.async)
+    // Thread g owns 16-byte chunk (g & 7) of tile rows (g >> 3) + 16*i, i = 0..7: eight lanes cover the 128 bytes of
+    // K of one pixel (full 32-byte sectors), and the chunk -> (tap, channel) mapping is uniform per thread.
+    if (a.gather) {
+      const int g = threadIdx.x - 64;
+      const int chunk = g & 7, r8 = g >> 3;
+      const int epc = 16 / a.esz;                                   // elements per 16-byte chunk
+      const uint32_t smem_base = smem_u32(base), bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
+      const uint32_t dst_thread = (uint32_t)(r8 * 128 + ((chunk ^ (r8 & 7)) << 4));  // SWIZZLE_128B: chunk ^= row & 7
+      const char* s0 = reinterpret_cast<const char*>(a.src0);
+      const char* s1 = reinterpret_cast<const char*>(a.src1);
+      const int C2s1 = a.C2 - a.C2_src0;
+      uint32_t stage = 0, phase_bit = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        const int ph_idx = tile / a.tiles_per_phase;
+        int r = tile - ph_idx * a.tiles_per_phase;
+        const int bt = r / (a.tiles_h * a.tiles_w);
+        r -= bt * a.tiles_h * a.tiles_w;
+        const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
+        int pix0[8];                                                 // source pixel index of tap (0,0) per owned row
+        int ys[8], xs[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = r8 + 16 * i;
+          const int cc = m & (a.TW - 1), rr = (m >> a.tw_log2) & (a.TH - 1), nb = m >> (a.tw_log2 + a.th_log2);
+          const int b = bt * a.NB + nb, j = ht * a.TH + rr, ii = wt * a.TW + cc;
+          const bool ok = b < a.batch && j < a.PH && ii < a.PW;
+          ys[i] = ok ? j * a.stride_h : -(1 << 20);                  // invalid rows fail every bounds check -> zero fill
+          xs[i] = ii * a.stride_w;
+          pix0[i] = (b * a.in_h + j * a.stride_h) * a.in_w + ii * a.stride_w;
+        }
+        const int8_t* dyp = a.dy + ph_idx * a.ntaps;
+        const int8_t* dxp = a.dx + ph_idx * a.ntaps;
+        int c = chunk * epc, tap = 0;                                // this thread's (tap, channel) position in K
+        while (c >= a.C2) { c -= a.C2; ++tap; }
+        for (int ks = 0; ks < a.ksteps; ++ks) {
+          mbar_wait(bar_empty0 + 8u * stage, phase_bit ^ 1);
+          const uint32_t dst0 = smem_base + stage * stage_bytes + dst_thread;
+          const bool tap_ok = tap < a.ntaps;                         // K padding beyond the last tap: zeros
+          const int dy = tap_ok ? dyp[tap] : 0, dx = tap_ok ? dxp[tap] : 0;
+          const bool from0 = c < a.C2_src0;
+          const char* sp = from0 ? s0 : s1;
+          const int cs = from0 ? a.C2_src0 : C2s1, co = from0 ? c : c - a.C2_src0;
+          const int dpix = dy * a.in_w + dx;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int y = ys[i] + dy, x = xs[i] + dx;
+            const bool ok = tap_ok && (unsigned)y < (unsigned)a.in_h && (unsigned)x < (unsigned)a.in_w;
+            const int64_t off = ok ? ((int64_t)(pix0[i] + dpix) * cs + co) * a.esz : 0;
+            cp_async16(dst0 + (uint32_t)(i * 16 * 128), sp + off, ok ? 16u : 0u);
+          }
+          cp_async_arrive_noinc(bar_full0 + 8u * stage);
+          c += kstep_elems;
+          while (c >= a.C2) { c -= a.C2; ++tap; }
+          if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
+        }
+      }
+    }
   } else {
     // ===================================================================== epilogue (8 warps)
     // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the accumulator columns.
-    const int ew = warp - 2;
+    const int ew = warp - 6;
     const int quad = warp & 3;
     const bool split = (a.n_pad % 32) == 0;          // n_pad = 16 (or an odd multiple of 16): one warp per quadrant
     const int half = ew >> 2;
@@ -470,9 +545,17 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   const int kstep_elems = kKStepBytes / esz;
   const int C2s0 = 2 * p->c0, C2s1 = 2 * p->c1, C2 = C2s0 + C2s1;
   const int CK = C2s0 >= kstep_elems ? kstep_elems : C2s0;
-  DCS_REQUIRE(CK * esz == 32 || CK * esz == 64 || CK * esz == 128,
+  const int N_ = 2 * p->cout;
+  // A-operand path: TMA boxes cost ~2 cycles per box row regardless of the row length, so short rows (few channels per
+  // tap: several boxes per K step) are gathered with 16-byte cp.async instead (measured: enc1 1.09 -> 0.78 ms; layers
+  // with full 128-byte rows are faster through TMA).  DCS_TC_AMODE=tma|gather overrides.
+  int gather = (CK * esz < 64) ? 1 : 0;
+  (void)N_;
+  if (const char* e = getenv("DCS_TC_AMODE")) { if (!strcmp(e, "tma")) gather = 0; else if (!strcmp(e, "gather")) gather = 1; }
+  if (C2s0 % (16 / esz) || C2s1 % (16 / esz)) gather = 0;
+  DCS_REQUIRE(gather || CK * esz == 32 || CK * esz == 64 || CK * esz == 128,
               "dcs_cconv2d_tc_fwd: 2*c0*sizeof(elem) must be 32, 64 or a multiple of 128 bytes (got %d); use dcs_cconv2d_fwd", C2s0 * esz);
-  DCS_REQUIRE(C2s0 % CK == 0 && C2s1 % CK == 0, "dcs_cconv2d_tc_fwd: channel counts must be multiples of %d", CK);
+  DCS_REQUIRE(gather || (C2s0 % CK == 0 && C2s1 % CK == 0), "dcs_cconv2d_tc_fwd: channel counts must be multiples of %d", CK);
   const int N = 2 * p->cout, n_pad = (N + 15) / 16 * 16;
   DCS_REQUIRE(n_pad <= 256, "dcs_cconv2d_tc_fwd: 2*cout must be <= 256 (got %d)", N);
   DCS_REQUIRE(((uintptr_t)p->src0 % 16 == 0) && ((uintptr_t)p->src1 % 16 == 0) && ((uintptr_t)p->weight % 16 == 0),
@@ -492,7 +575,9 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   a.phases = p->up_h * p->up_w;
   a.n_tiles = a.tiles_per_phase * a.phases;
   a.ntaps = p->ntaps; a.up_h = p->up_h; a.up_w = p->up_w; a.stride_h = p->stride_h; a.stride_w = p->stride_w;
-  a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK; a.esz = esz;
+  a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK; a.esz = esz; a.gather = gather;
+  a.tw_log2 = __builtin_ctz(a.TW); a.th_log2 = __builtin_ctz(a.TH);
+  a.in_h = p->in_h; a.in_w = p->in_w; a.src0 = p->src0; a.src1 = p->src1;
   const int K = p->ntaps * C2;
   a.ksteps = (K + kstep_elems - 1) / kstep_elems;
   a.n_pad = n_pad; a.n_real = N; a.act = p->act; a.out_f32 = p->out_dtype == DCS_F32;
@@ -509,13 +594,17 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers);
 
   CUtensorMap tmA0, tmA1, tmB;
-  if (int e = make_act_map(&tmA0, p->src0, esz, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
-  if (p->c1) {
-    if (int e = make_act_map(&tmA1, p->src1, esz, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
-  } else {
-    tmA1 = tmA0;
-  }
   if (int e = make_weight_map(&tmB, p->weight, esz, a.ksteps * kstep_elems, a.phases * n_pad, n_pad)) return e;
+  if (gather) {
+    tmA0 = tmB; tmA1 = tmB;  // unused by the kernel in gather mode (kept valid for the descriptor prefetch)
+  } else {
+    if (int e = make_act_map(&tmA0, p->src0, esz, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+    if (p->c1) {
+      if (int e = make_act_map(&tmA1, p->src1, esz, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+    } else {
+      tmA1 = tmA0;
+    }
+  }
 
   DCS_CUDA(cudaFuncSetAttribute(cconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(a.n_tiles, num_sms());

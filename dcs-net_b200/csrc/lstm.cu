@@ -197,6 +197,8 @@ extern "C" int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream) {
   // NSEQ must divide 2B; 2 sequences per CTA (two co-resident CTAs per SM) unless that overflows the machine
   int nseq = 2;
   if ((2 * B) % 4 == 0 && (4 * B / 2) * 2 > 2 * num_sms()) nseq = 4;
+  if (p->seqs_per_cta == 4 && (2 * B) % 4 == 0) nseq = 4;  // one CTA per SM: leaves room for kernels on other streams
+  if (p->seqs_per_cta == 2) nseq = 2;
   const float* whh1 = p->w_hh + (int64_t)4 * kG * kH;
   const int64_t rows2 = 2 * rows;
   if (p->w_ih0_t && p->w_ih1_t) {

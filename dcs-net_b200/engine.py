@@ -126,6 +126,11 @@ class ForwardPlan:
         self.noise_audio = new(B, 32 * (T - 1), dtype=torch.float32) if self.noise_spec is not None else None
         self.graph = None
         self.taps = {}
+        # the skip attentions depend only on encoder outputs, so they can run on a side stream concurrently with the
+        # ComplexLSTM + fc (fork / join is captured into the CUDA graph as parallel branches).  Measured on B200 at
+        # batch 64 x 4 s: no gain (9.73 vs 9.72 ms) — the recurrence is issue-bound on 128 SMs, so it stays off.
+        self.overlap = False
+        self.side = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------ building blocks
     def _attention(self, x, ca, sa_w7, y, sums=None):
@@ -174,15 +179,28 @@ class ForwardPlan:
                 x, enc_pooled[i] = self._conv(pk.enc[i], x, None, self.enc[i], self.pool_enc[i])
             self._tap(f"enc{i}", x)
         B, H, W, _, _ = x.shape
-        ops.clstm(x.view(B, H * W, x.shape[3], 2), self.lat.view(B, H * W, 128, 2), pk.lstm, self.lstm_ws, use_tc=self.tc)
+
+        def skip_attention(i):
+            e = Lr - 1 - i
+            return self._attention(self.enc[e], pk.skip_ca[i], pk.skip_sa[i], self.skip[i],
+                                   sums=self.pool_enc[e] if enc_pooled[e] else None)
+
+        main = torch.cuda.current_stream()
+        if self.overlap:
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                for i in range(Lr):
+                    skip_attention(i)
+        ops.clstm(x.view(B, H * W, x.shape[3], 2), self.lat.view(B, H * W, 128, 2), pk.lstm, self.lstm_ws, use_tc=self.tc,
+                  seqs_per_cta=4 if self.overlap else 0)
         self._tap("lstm", self.lat)
         self._conv(pk.fc, self.lat.view(B, 1, H * W, 128, 2), None, self.fc.view(B, 1, H * W, 128, 2))
         d = self.fc
         self._tap("fc", d)
+        if self.overlap:
+            main.wait_stream(self.side)
         for i in range(Lr):
-            e = Lr - 1 - i
-            skip = self._attention(self.enc[e], pk.skip_ca[i], pk.skip_sa[i], self.skip[i],
-                                   sums=self.pool_enc[e] if enc_pooled[e] else None)
+            skip = self.skip[i] if self.overlap else skip_attention(i)
             self._tap(f"skip{i}", skip)
             if i == Lr - 1:
                 return d, skip  # decoder[6] is fused with the mask tail (dcs_dec6_tail_fwd)

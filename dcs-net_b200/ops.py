@@ -139,12 +139,12 @@ def clstm_workspace_bytes(B, S, hidden=64):
     return int(n)
 
 
-def clstm(x, y, w, workspace, use_tc=False):
+def clstm(x, y, w, workspace, use_tc=False, seqs_per_cta=0):
     """x (B,S,D,2) -> y (B,S,2*hidden,2) fp32.  w = packing.pack_lstm(...).  use_tc: tf32 tensor-core projections."""
     B, S, D, _ = x.shape
     p = L.ClstmParams(L.ptr(x), L.ptr(y), B, S, D, y.shape[2] // 2, _code(x), L.ptr(w["w_ih0"]), L.ptr(w["w_ih1"]),
                       L.ptr(w["w_hh"]), L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size(),
-                      L.ptr(w["w_ih0_t"]) if use_tc else None, L.ptr(w["w_ih1_t"]) if use_tc else None)
+                      L.ptr(w["w_ih0_t"]) if use_tc else None, L.ptr(w["w_ih1_t"]) if use_tc else None, seqs_per_cta)
     L.check(L.lib().dcs_clstm_fwd(C.byref(p), L.stream_ptr()), "dcs_clstm_fwd")
     return y
 

@@ -143,6 +143,7 @@ typedef struct {
   /* optional tensor-core input projections (tf32 operands, kind::tf32): K-major weight slices [4 = lstm*2+dir][4H][D]
    * for layer 0 and [4][4H][2H] for layer 1, pre-rounded to tf32.  NULL -> fp32 CUDA-core GEMMs. */
   const float* w_ih0_t; const float* w_ih1_t;
+  int seqs_per_cta; /* 0 = auto, 2 or 4 sequences per recurrent CTA (4 => one CTA per SM, co-residency with other streams) */
 } dcs_clstm_params;
 int64_t dcs_clstm_workspace_bytes(int batch, int seq, int hidden);
 int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream);
