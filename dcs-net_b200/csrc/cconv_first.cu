@@ -54,30 +54,31 @@ __global__ void __launch_bounds__(kF_Threads, 2) enc0_kernel(const dcs_enc0_para
   const int warp = tid >> 5, lane = tid & 31;
   const int lx = (warp & 1) * 32 + lane;       // local output column
   const int ly = (warp >> 1) * 4;              // first of 4 local output rows
-  float acc[4][kF_N];
+  float2 acc[4][kF_N / 2];  // (n, n+1) pairs: packed fp32x2 FMA halves the FMA instruction count
 #pragma unroll
   for (int q = 0; q < 4; ++q)
 #pragma unroll
-    for (int n = 0; n < kF_N; ++n) acc[q][n] = 0.f;
+    for (int n = 0; n < kF_N / 2; ++n) acc[q][n] = make_float2(0.f, 0.f);
 
 #pragma unroll 1
   for (int ky = 0; ky < kF_K; ++ky) {
 #pragma unroll
     for (int kx = 0; kx < kF_K; ++kx) {
-      float wr[kF_N], wi[kF_N];
+      float2 wr[kF_N / 2], wi[kF_N / 2];
       const float4* wp = sm.w + (ky * kF_K + kx) * 8;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float4 a = wp[j], c = wp[4 + j];
-        wr[4 * j] = a.x; wr[4 * j + 1] = a.y; wr[4 * j + 2] = a.z; wr[4 * j + 3] = a.w;
-        wi[4 * j] = c.x; wi[4 * j + 1] = c.y; wi[4 * j + 2] = c.z; wi[4 * j + 3] = c.w;
+        wr[2 * j] = make_float2(a.x, a.y); wr[2 * j + 1] = make_float2(a.z, a.w);
+        wi[2 * j] = make_float2(c.x, c.y); wi[2 * j + 1] = make_float2(c.z, c.w);
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int r = 2 * (ly + q) + ky;
         const float2 x = (kx & 1) ? sm.od[r][lx + (kx >> 1)] : sm.ev[r][lx + (kx >> 1)];
+        const float2 xr = make_float2(x.x, x.x), xi = make_float2(x.y, x.y);
 #pragma unroll
-        for (int n = 0; n < kF_N; ++n) acc[q][n] = fmaf(wr[n], x.x, fmaf(wi[n], x.y, acc[q][n]));
+        for (int n = 0; n < kF_N / 2; ++n) { ffma2(acc[q][n], wi[n], xi); ffma2(acc[q][n], wr[n], xr); }
       }
     }
   }
@@ -91,7 +92,10 @@ __global__ void __launch_bounds__(kF_Threads, 2) enc0_kernel(const dcs_enc0_para
     if (oy >= OH) continue;
     float v[kF_N];
 #pragma unroll
-    for (int n = 0; n < kF_N; ++n) v[n] = fmaxf(acc[q][n] + __ldg(p.bias + n), 0.f);
+    for (int n = 0; n < kF_N / 2; ++n) {
+      v[2 * n] = fmaxf(acc[q][n].x + __ldg(p.bias + 2 * n), 0.f);
+      v[2 * n + 1] = fmaxf(acc[q][n].y + __ldg(p.bias + 2 * n + 1), 0.f);
+    }
     TOUT* o = dst + (((int64_t)b * OH + oy) * OW + ox) * kF_N;
     if constexpr (sizeof(TOUT) == 2) {
       uint32_t pk[8];

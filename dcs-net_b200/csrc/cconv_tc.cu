@@ -155,8 +155,31 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t row_b
   return d;
 }
 
+constexpr int kMaxAcc = 4;  // accumulator stages in TMEM: 4 when 4*n_pad <= 256 columns, else 2
+
+// Division-free walk over this CTA's tiles: tile = ((phase*tiles_b + bt)*tiles_h + ht)*tiles_w + wt, advanced by a
+// fixed step kept as mixed-radix digits (the per-tile divisions were a visible cost in the latency-exposed roles).
+struct TileIter {
+  int ph, bt, ht, wt, tile;
+  int sp, sb, sh, sw, step;
+  __device__ __forceinline__ void init(const TcArgs& a, int first, int stride) {
+    tile = first; step = stride;
+    int r = first;
+    wt = r % a.tiles_w; r /= a.tiles_w; ht = r % a.tiles_h; r /= a.tiles_h; bt = r % a.tiles_b; ph = r / a.tiles_b;
+    r = stride;
+    sw = r % a.tiles_w; r /= a.tiles_w; sh = r % a.tiles_h; r /= a.tiles_h; sb = r % a.tiles_b; sp = r / a.tiles_b;
+  }
+  __device__ __forceinline__ void next(const TcArgs& a) {
+    tile += step;
+    wt += sw; if (wt >= a.tiles_w) { wt -= a.tiles_w; ++ht; }
+    ht += sh; if (ht >= a.tiles_h) { ht -= a.tiles_h; ++bt; }
+    bt += sb; if (bt >= a.tiles_b) { bt -= a.tiles_b; ++ph; }
+    ph += sp;
+  }
+};
+
 struct __align__(8) TcBarriers {
-  uint64_t full[kMaxStages], empty[kMaxStages], acc_full[2], acc_empty[2];
+  uint64_t full[kMaxStages], empty[kMaxStages], acc_full[kMaxAcc], acc_empty[kMaxAcc];
   uint32_t tmem_base;
   float bias[256];
 };
@@ -171,13 +194,17 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(base + (size_t)a.n_stages * stage_bytes);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t tmem_cols = a.n_pad <= 16 ? 32u : (a.n_pad <= 32 ? 64u : (a.n_pad <= 64 ? 128u : (a.n_pad <= 128 ? 256u : 512u)));
+  // small N: 4 accumulator stages and the two epilogue warp sets alternate TILES; large N: 2 stages, the sets split COLUMNS
+  const bool tile_split = a.n_pad <= 64;
+  const uint32_t n_acc = tile_split ? 4u : 2u;
+  uint32_t tmem_cols = 32;
+  while (tmem_cols < n_acc * (uint32_t)a.n_pad) tmem_cols <<= 1;
 
   if (threadIdx.x == 0) {
     const uint32_t full_count = a.gather ? 1u + kGatherThreads : 1u;  // B-TMA expect_tx arrive (+ one per gather thread)
     for (int s = 0; s < a.n_stages; ++s) { mbar_init(smem_u32(&bars->full[s]), full_count); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    const uint32_t n_epi_warps = (a.n_pad % 32) == 0 ? 8u : 4u;
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), n_epi_warps); }
+    const uint32_t n_epi_warps = tile_split ? 4u : ((a.n_pad % 32) == 0 ? 8u : 4u);
+    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), n_epi_warps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
@@ -205,13 +232,11 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       unsigned long long w_empty = 0;
       unsigned long long* dw = a.dbg ? &w_empty : nullptr;
       const long long t_start = clock64();
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int ph_idx = tile / a.tiles_per_phase;
-        int r = tile - ph_idx * a.tiles_per_phase;
-        const int bt = r / (a.tiles_h * a.tiles_w);
-        r -= bt * a.tiles_h * a.tiles_w;
-        const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
-        const int b0 = bt * a.NB, j0 = ht * a.TH, i0 = wt * a.TW;
+      TileIter it;
+      it.init(a, blockIdx.x, gridDim.x);
+      for (; it.tile < a.n_tiles; it.next(a)) {
+        const int ph_idx = it.ph;
+        const int b0 = it.bt * a.NB, j0 = it.ht * a.TH, i0 = it.wt * a.TW;
         // Single-thread control loop: keep it free of divisions / 64-bit math (every instruction is latency-exposed).
         const int8_t* dyp = a.dy + ph_idx * a.ntaps;
         const int8_t* dxp = a.dx + ph_idx * a.ntaps;
@@ -290,7 +315,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           __syncwarp();
           if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == n_acc) { acc = 0; acc_phase ^= 1; }
       }
       if (a.dbg && lane == 0) { a.dbg[blockIdx.x * 8 + 2] = w_full; a.dbg[blockIdx.x * 8 + 3] = w_acc; a.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_start); }
     }
@@ -308,12 +333,10 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       const char* s1 = reinterpret_cast<const char*>(a.src1);
       const int C2s1 = a.C2 - a.C2_src0;
       uint32_t stage = 0, phase_bit = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        const int ph_idx = tile / a.tiles_per_phase;
-        int r = tile - ph_idx * a.tiles_per_phase;
-        const int bt = r / (a.tiles_h * a.tiles_w);
-        r -= bt * a.tiles_h * a.tiles_w;
-        const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
+      TileIter it;
+      it.init(a, blockIdx.x, gridDim.x);
+      for (; it.tile < a.n_tiles; it.next(a)) {
+        const int ph_idx = it.ph, bt = it.bt, ht = it.ht, wt = it.wt;
         int pix0[8];                                                 // source pixel index of tap (0,0) per owned row
         int ys[8], xs[8];
 #pragma unroll
@@ -358,31 +381,31 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the accumulator columns.
     const int ew = warp - 6;
     const int quad = warp & 3;
-    const bool split = (a.n_pad % 32) == 0;          // n_pad = 16 (or an odd multiple of 16): one warp per quadrant
-    const int half = ew >> 2;
+    const int set = ew >> 2;                          // two sets of four warps (one warp per TMEM lane quadrant each)
+    const bool split = !tile_split && (a.n_pad % 32) == 0;  // large N: the sets split the accumulator columns
     const int ncols = split ? a.n_pad / 2 : a.n_pad;
-    const int col0 = split ? half * ncols : 0;
-    const bool active = split || half == 0;
+    const int col0 = split ? set * ncols : 0;
+    const bool active = tile_split || split || set == 0;
     const int m = quad * 32 + lane;                  // tile row = TMEM lane
-    const int hw_tile = a.TH * a.TW;
-    const int nb = m / hw_tile, rr = (m - nb * hw_tile) / a.TW, cc = m % a.TW;
-    const bool warp_uniform_image = (hw_tile % 32) == 0;
-    uint32_t acc = 0, acc_phase = 0;
+    const int cc = m & (a.TW - 1), rr = (m >> a.tw_log2) & (a.TH - 1), nb = m >> (a.tw_log2 + a.th_log2);
+    const bool warp_uniform_image = ((a.TH * a.TW) % 32) == 0;
+    // tile-split: set s takes this CTA's tiles s, s+2, s+4, ... (accumulator stage = local tile index % 4)
+    const int t_first = tile_split ? set : 0, t_step = tile_split ? 2 : 1;
+    uint32_t acc = (uint32_t)t_first, acc_phase = 0;
     unsigned long long w_epi = 0;
     unsigned long long* dwe = (a.dbg && ew == 0 && lane == 0) ? &w_epi : nullptr;
     const long long t_start = clock64();
     int n_my_tiles = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    TileIter it;
+    it.init(a, blockIdx.x + t_first * gridDim.x, t_step * gridDim.x);
+    for (; it.tile < a.n_tiles; it.next(a)) {
       ++n_my_tiles;
       if (active) {
-        const int ph_idx = tile / a.tiles_per_phase;
-        int r = tile - ph_idx * a.tiles_per_phase;
-        const int bt = r / (a.tiles_h * a.tiles_w);
-        r -= bt * a.tiles_h * a.tiles_w;
-        const int ht = r / a.tiles_w, wt = r - ht * a.tiles_w;
-        const int b = bt * a.NB + nb, j = ht * a.TH + rr, i = wt * a.TW + cc;
+        const int ph_idx = it.ph;
+        const int b = it.bt * a.NB + nb, j = it.ht * a.TH + rr, i = it.wt * a.TW + cc;
         const bool valid = b < a.batch && j < a.PH && i < a.PW;
-        const int oy = j * a.up_h + ph_idx / a.up_w, ox = i * a.up_w + ph_idx % a.up_w;
+        const int ph_h = a.up_w == 2 ? (ph_idx >> 1) : ph_idx, ph_w = a.up_w == 2 ? (ph_idx & 1) : 0;
+        const int oy = j * a.up_h + ph_h, ox = i * a.up_w + ph_w;
         const int64_t pix = ((int64_t)b * a.out_h + oy) * a.out_w + ox;
         mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase, dwe);
         tc_fence_after();
@@ -462,7 +485,8 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      acc += (uint32_t)t_step;
+      if (acc >= n_acc) { acc -= n_acc; acc_phase ^= 1; }
     }
     if (dwe) { a.dbg[blockIdx.x * 8 + 5] = w_epi; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start); a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)n_my_tiles; }
   }

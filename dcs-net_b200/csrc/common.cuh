@@ -64,6 +64,16 @@ template <> struct Elem<__nv_bfloat16> {
   }
 };
 
+// Packed fp32x2 FMA (sm_100: FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, two IEEE fma.rn in ONE issue slot.
+// The CUDA-core kernels here are issue-bound (FFMA + LDS share the schedulers), so halving the FMA instruction count is
+// the lever; results are bit-identical to two scalar fmaf.
+__device__ __forceinline__ void ffma2(float2& acc, const float2 a, const float2 b) {
+  unsigned long long ra = *reinterpret_cast<const unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<const unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&acc);
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(rc) : "l"(ra), "l"(rb));
+  acc = *reinterpret_cast<float2*>(&rc);
+}
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
   return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
 }

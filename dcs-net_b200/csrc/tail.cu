@@ -65,7 +65,7 @@ template <typename T>
 __global__ void __launch_bounds__(kTlThreads) dec6_tail_kernel(const dcs_dec6_tail_params p) {
   using E = typename SmemC<T>::type;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float4* wsm = reinterpret_cast<float4*>(smem_raw);                         // [ci][phase][tap] (M00 M01 M10 M11)
+  float4* wsm = reinterpret_cast<float4*>(smem_raw);                         // [ci][phase][tap] (M00 M10 M01 M11)
   E* tile = reinterpret_cast<E*>(smem_raw + kTlCi * 16 * sizeof(float4));    // [ci][row 0..5][kTlPitch]
   const int tid = threadIdx.x;
   const int b = blockIdx.z, r0 = blockIdx.y * kTlRows, c0 = blockIdx.x * kTlCols;
@@ -137,14 +137,15 @@ __global__ void __launch_bounds__(kTlThreads) dec6_tail_kernel(const dcs_dec6_ta
 #pragma unroll
           for (int sx = 0; sx < 3; ++sx) {  // source col offset sx - 1 relative to pixel q -> xin[q + sx]
             const float2 x = xin[q + sx];
+            const float2 xr = make_float2(x.x, x.x), xi = make_float2(x.y, x.y);
 #pragma unroll
             for (int pw = 0; pw < 2; ++pw) {
               const int tx = sx - pw;
               if (tx < 0 || tx > 1) continue;
-              const float4 m = w[(ph * 2 + pw) * 4 + ty * 2 + tx];
+              const float4 m = w[(ph * 2 + pw) * 4 + ty * 2 + tx];  // (M00, M10, M01, M11): column pairs of the 2x2 block
               float2& a = acc[q][ph * 2 + pw];
-              a.x = fmaf(m.x, x.x, fmaf(m.y, x.y, a.x));
-              a.y = fmaf(m.z, x.x, fmaf(m.w, x.y, a.y));
+              ffma2(a, make_float2(m.z, m.w), xi);   // (re, im) += (M01, M11) * x.im
+              ffma2(a, make_float2(m.x, m.y), xr);   // (re, im) += (M00, M10) * x.re
             }
           }
         }

@@ -125,8 +125,8 @@ class PackedConv:
         self.bias_host = b.float().tolist()
         self.w_tail = None
         if cout == 1 and tuple(up) == (2, 2) and cin == 16:
-            # dcs_dec6_tail_fwd operand: [phase][tap][ci][(M00 M01 M10 M11)]
-            self.w_tail = Wp[:, :, :2].reshape(self.phases, self.ntaps, 2, cin, 2).permute(0, 1, 3, 2, 4) \
+            # dcs_dec6_tail_fwd operand: [phase][tap][ci][(M00 M10 M01 M11)]  (M[n][ri], stored by columns)
+            self.w_tail = Wp[:, :, :2].reshape(self.phases, self.ntaps, 2, cin, 2).permute(0, 1, 3, 4, 2) \
                 .contiguous().float().to(device)
 
 

@@ -172,7 +172,8 @@ int dcs_enc0_fwd(const dcs_enc0_params* p, void* stream);
  *      cat(d, skip_sa) up-sampled (2,2) (c_network.py:214-216, 134-140), then the whole tail of dcs_mask_combine.
  *      d, skip: (B, h, w, 8) channels-last complex of in_dtype; outputs (B, 2h, 2w) complex64.  N = 2 cannot feed a
  *      tensor core, so this is a CUDA-core kernel; decoder[6]'s raw output never reaches HBM (net_raw optional).
- *      weight: fp32 [4 phases][4 taps][16 ci][4] = the real 2x2 block (M00 M01 M10 M11) of each pre-summed tap. */
+ *      weight: fp32 [4 phases][4 taps][16 ci][4] = the real 2x2 block of each pre-summed tap stored by columns
+ *      (M00 M10 M01 M11), out.re = M00 x.re + M01 x.im, out.im = M10 x.re + M11 x.im. */
 typedef struct {
   const void* d; const void* skip; int in_dtype; int batch; int h; int w;
   const float* weight; float bias_re; float bias_im;
