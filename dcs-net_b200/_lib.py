@@ -46,6 +46,27 @@ class CconvParams(C.Structure):
                 ("pool_sums", _vp)]
 
 
+STRIP_MAX_GROUPS = 2
+
+
+class StripGroup(C.Structure):
+    _fields_ = [("item0", _i), ("n_items", _i), ("dy_min", _i), ("n_dy", _i), ("ph0", _i), ("n_ph", _i), ("x_min", _i),
+                ("w_bytes", _i), ("w_off", _i64)]
+
+
+class CstripParams(C.Structure):
+    _fields_ = [("src0", _vp), ("src1", _vp), ("c0", _i), ("c1", _i),
+                ("batch", _i), ("in_h", _i), ("in_w", _i),
+                ("out_h", _i), ("out_w", _i), ("cout", _i),
+                ("up_h", _i), ("up_w", _i), ("stride_h", _i), ("stride_w", _i),
+                ("n_groups", _i), ("group", StripGroup * STRIP_MAX_GROUPS),
+                ("items", _vp), ("n_items_total", _i),
+                ("weights", _vp),
+                ("box_units", _i), ("n_mma", _i), ("cols", _i),
+                ("bias", _vp), ("act", _i),
+                ("dst", _vp), ("pool_sums", _vp)]
+
+
 class ChanPoolParams(C.Structure):
     _fields_ = [("x", _vp), ("sums", _vp), ("batch", _i), ("hw", _i), ("channels", _i), ("dtype", _i)]
 
@@ -100,6 +121,7 @@ SYMBOLS = {
     "dcs_cbn_apply": (_i, [C.POINTER(CbnParams), _vp]),
     "dcs_cconv2d_fwd": (_i, [C.POINTER(CconvParams), _vp]),
     "dcs_cconv2d_tc_fwd": (_i, [C.POINTER(CconvParams), _vp]),
+    "dcs_cconv2d_strip_fwd": (_i, [C.POINTER(CstripParams), _vp]),
     "dcs_chan_pool": (_i, [C.POINTER(ChanPoolParams), _vp]),
     "dcs_chan_gate": (_i, [C.POINTER(ChanGateParams), _vp]),
     "dcs_spat_stats": (_i, [C.POINTER(SpatStatsParams), _vp]),

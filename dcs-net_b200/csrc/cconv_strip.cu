@@ -1,0 +1,408 @@
+// cconv_strip.cu — "row-strip" implicit-GEMM complex convolution for the few-channel layers (encoder[1], decoder[4],
+// decoder[5]) on the 5th-generation tensor cores: tcgen05.mma (bf16, fp32 accumulators in TMEM), TMA, mbarriers.
+//
+// Replaces apply_complex(conv_r, conv_i) / apply_complex(conv_tran_r, conv_tran_i) (complexPyTorch 0.3) at
+// /root/reference/c_network.py:107-112 and 135-147 together with torch.cat + complex_upsample (c_network.py:214-216),
+// eval-mode ComplexBatchNorm2d and ComplexReLU / ComplexLReLU, for layers whose per-pixel K slice is short.
+//
+// Why a second tensor-core kernel: the general kernel (cconv_tc.cu) re-stages the A operand once per tap and per
+// sub-pixel phase (an im2col in shared memory), so a layer with C2 = 16..64 moves 16..49x its input through the
+// L2 -> SM path and is bound by it.  Here ONE TMA box per source row — a strip of 128 (+halo) pixels, channels-last,
+// so a strip row IS a GEMM A row — serves every tap that touches that row:
+//   * a horizontal tap offset dx is the SAME strip read through a UMMA descriptor whose start address is shifted by
+//     dx rows (the 32/64/128-byte swizzle is a function of the absolute shared-memory address, so a row-shifted
+//     descriptor reads exactly what TMA wrote — probed on hardware by tools/umma_shift_test.cu);
+//   * stride 2 pairs two pixels into one strip row, the tap parity selects the 32-byte K slice inside the row;
+//   * a vertical tap offset dy is another slot of a ring of source rows: walking down the image, each source row is
+//     loaded once per (column strip, phase group) and reused by every output row that needs it;
+//   * the weights of the whole layer stay resident in shared memory (one bulk copy per CTA).
+// The host (dcs-net_b200/packing.py: StripConv) flattens the layer into a table of MMA "items"
+// {ring row, A descriptor offset, B block, accumulator column, first}; the issuing warp just walks the table.
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
+// (TMEM lane quadrant = warp % 4): bias + activation + bf16 + per-(image, channel) pooling sums.
+#include <cuda.h>
+#include <string.h>
+#include <algorithm>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dcs {
+
+int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_units, int h, int b, int box_units);
+
+constexpr int kStripM = 128;
+constexpr int kStripThreads = 192;
+constexpr int kStripMaxRing = 16;
+constexpr int kStripMaxItems = 64;    // MMA items of one phase group; the table travels in the kernel parameters
+
+struct StripGroup {   // one phase group = one launch
+  int dy_min, n_dy, ph0, x_min;
+  uint32_t w_bytes;
+  const unsigned char* w_ptr;
+};
+
+struct StripArgs {
+  int batch, PH, PW;
+  int out_h, out_w, up_h, up_w, n_real, run_log2;
+  int s_h;
+  int n_strips, n_chunks, chunk_rows, n_units;
+  StripGroup grp;
+  int R;
+  uint32_t slot_bytes, src1_off, tx_bytes, w_smem_bytes;
+  int has_src1;
+  uint32_t row_bytes0, row_bytes1;
+  int n_mma, act;
+  const float* bias;
+  __nv_bfloat16* dst;
+  float* pool;
+  // The item table lives in the constant bank (kernel parameters) and the issue loop is fully unrolled (kNdy ring
+  // rows x kIpr items per row are template parameters), so every item field is a constant-bank operand of a uniform
+  // add: ~6 instructions per MMA on the single issuing warp.  (Walking a table in shared memory cost ~40 dependent
+  // instructions, ~200 cycles, per MMA and made the issuing warp the bottleneck.)
+  uint4 items[kStripMaxItems];        // [drow][kIpr] {a_off16, b_off16, d_col | drow << 16 | flags << 24, -}
+};
+
+struct __align__(8) StripBarriers {
+  uint64_t full[kStripMaxRing], empty[kStripMaxRing], acc_full[2], acc_empty[2], wbar;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// recursive-halving transpose-reduce: 31 shuffles turn 32 columns x 32 lanes into one column sum per lane
+__device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
+#pragma unroll
+  for (int off = 16; off >= 1; off >>= 1) {
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int q = 0; q < off; ++q) {
+      const float send = up ? v[q] : v[q + off];
+      const float keep = up ? v[q + off] : v[q];
+      v[q] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0];
+}
+
+struct UnitIter {  // unit u of a phase group -> (image, column strip, row chunk)
+  int b, x0, j0, j1;
+  __device__ __forceinline__ void set(const StripArgs& a, int u) {
+    const int chunk = u % a.n_chunks, t = u / a.n_chunks;
+    const int strip = t % a.n_strips;
+    b = t / a.n_strips;
+    x0 = strip * kStripM;
+    j0 = chunk * a.chunk_rows;
+    j1 = min(a.PH, j0 + a.chunk_rows);
+  }
+};
+
+template <int kCols, int kNdy, int kIpr>
+__global__ void __launch_bounds__(kStripThreads, 1)
+cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const StripArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  // layout: [ring: R slots][weights][items][column bias][barriers]
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
+  unsigned char* w_s = base + (size_t)a.R * a.slot_bytes;
+  float* bias_col = reinterpret_cast<float*>(w_s + a.w_smem_bytes);
+  StripBarriers* bars = reinterpret_cast<StripBarriers*>(bias_col + kCols);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cta_in_grp = blockIdx.x, ctas_in_grp = gridDim.x;
+  const StripGroup& G = a.grp;
+  constexpr uint32_t tmem_cols = 2 * kCols < 32 ? 32u : (uint32_t)(2 * kCols);  // kCols is a power of two
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.R; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    mbar_init(smem_u32(&bars->wbar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int c = threadIdx.x; c < kCols; c += kStripThreads) bias_col[c] = a.bias[c & (a.n_real - 1)];
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    const bool leader = elect_one();
+    if (leader) {  // the layer's weights: one bulk copy per CTA (<= 32 KB pieces)
+      mbar_expect_tx(smem_u32(&bars->wbar), G.w_bytes);
+      for (uint32_t off = 0; off < G.w_bytes; off += 32768u)
+        bulk_g2s(smem_u32(w_s) + off, G.w_ptr + off, min(32768u, G.w_bytes - off), smem_u32(&bars->wbar));
+    }
+    __syncwarp();
+    uint32_t slot = 0, par = 0;
+    const uint32_t ring = smem_u32(base), bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
+    UnitIter un;
+    for (int u = cta_in_grp; u < a.n_units; u += ctas_in_grp) {
+      un.set(a, u);
+      const int nrows = (un.j1 - 1 - un.j0) * a.s_h + kNdy;
+      const int y0 = un.j0 * a.s_h + G.dy_min, x = un.x0 + G.x_min;
+      for (int r = 0; r < nrows; ++r) {
+        mbar_wait(bar_empty0 + 8u * slot, par ^ 1);
+        if (elect_one()) {
+          const uint32_t full = bar_full0 + 8u * slot, dst = ring + slot * a.slot_bytes;
+          mbar_expect_tx(full, a.tx_bytes);
+          tma_load_4d(dst, &tmA0, full, 0, x, y0 + r, un.b);
+          if (a.has_src1) tma_load_4d(dst + a.src1_off, &tmA1, full, 0, x, y0 + r, un.b);
+        }
+        __syncwarp();
+        if (++slot == (uint32_t)a.R) { slot = 0; par ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (whole warp loops, one lane issues)
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_mma >> 3) << 17) | ((uint32_t)(kStripM >> 4) << 24);
+    const uint64_t a_desc_c0 = umma_desc(0, a.row_bytes0), a_desc_c1 = umma_desc(0, a.row_bytes1), b_desc_c = umma_desc(0, 32);
+    const uint32_t ring16 = (smem_u32(base) & 0x3FFFFu) >> 4, slot16 = a.slot_bytes >> 4, w16 = (smem_u32(w_s) & 0x3FFFFu) >> 4;
+    const uint32_t bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
+    const uint32_t R = (uint32_t)a.R;
+    uint32_t ws = 0, wp = 0;      // next full barrier to wait on (slot, parity)
+    uint32_t gw = 0, glo = 0;     // rows waited so far / ring row index of the first row of the current output row
+    uint32_t slot_lo = 0, fs = 0; // slot of row glo / next slot to free
+    uint32_t acc = 0, accp = 0;
+    mbar_wait(smem_u32(&bars->wbar), 0);
+    UnitIter un;
+    for (int u = cta_in_grp; u < a.n_units; u += ctas_in_grp) {
+      un.set(a, u);
+      for (int j = un.j0; j < un.j1; ++j) {
+        mbar_wait(smem_u32(&bars->acc_empty[acc]), accp ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * (uint32_t)kCols;
+        // items are sorted by ring row (drow): wait for a source row once, then issue its MMAs back to back
+#pragma unroll
+        for (int dg = 0; dg < kNdy; ++dg) {
+          const uint32_t need = glo + (uint32_t)dg;
+          if (gw <= need) {
+            while (gw <= need) {
+              mbar_wait(bar_full0 + 8u * ws, wp);
+              if (++ws == R) { ws = 0; wp ^= 1; }
+              ++gw;
+            }
+            tc_fence_after();
+          }
+          uint32_t s = slot_lo + (uint32_t)dg;
+          if (s >= R) s -= R;
+          const uint32_t a16 = ring16 + s * slot16;
+          if (elect_one()) {
+#pragma unroll
+            for (int q = 0; q < kIpr; ++q) {
+              const uint4 item = a.items[dg * kIpr + q];
+              const uint32_t flags = item.z >> 24, d_col = item.z & 0xffffu;
+              const uint64_t ad = ((flags & 2u) ? a_desc_c1 : a_desc_c0) + (uint64_t)(a16 + item.x);
+              const uint64_t bd = b_desc_c + (uint64_t)(w16 + item.y);
+              tc_mma_bf16(d_tmem + d_col, ad, bd, idesc, (flags & 1u) ? 0u : 1u);
+            }
+          }
+          __syncwarp();
+        }
+        const uint32_t nfree = (j == un.j1 - 1) ? (uint32_t)kNdy : (uint32_t)a.s_h;
+        if (elect_one()) {
+          tc_commit(smem_u32(&bars->acc_full[acc]));
+          uint32_t f = fs;
+          for (uint32_t i = 0; i < nfree; ++i) { tc_commit(bar_empty0 + 8u * f); if (++f == R) f = 0; }
+        }
+        __syncwarp();
+        fs += nfree; while (fs >= R) fs -= R;
+        slot_lo += nfree; while (slot_lo >= R) slot_lo -= R;
+        glo += nfree;
+        if (++acc == 2) { acc = 0; accp ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (4 warps, one TMEM lane quadrant each)
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int run_len = 1 << a.run_log2;                 // columns of one output row run = up_w * n_real
+    uint32_t acc = 0, accp = 0;
+    UnitIter un;
+    for (int u = cta_in_grp; u < a.n_units; u += ctas_in_grp) {
+      un.set(a, u);
+      const int x = un.x0 + m;
+      const bool valid = x < a.PW;
+      float pool_acc[kCols];
+#pragma unroll
+      for (int c = 0; c < kCols; ++c) pool_acc[c] = 0.f;
+      for (int j = un.j0; j < un.j1; ++j) {
+        mbar_wait(smem_u32(&bars->acc_full[acc]), accp);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)kCols;
+        uint32_t rg[kCols / 16][16];
+#pragma unroll
+        for (int cb = 0; cb < kCols / 16; ++cb) tc_ld16(taddr + 16u * cb, rg[cb]);
+        tc_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));   // accumulator is in registers: release it
+        const int64_t row0 = ((int64_t)un.b * a.out_h + (int64_t)j * a.up_h + G.ph0) * a.out_w + (int64_t)x * a.up_w;
+#pragma unroll
+        for (int s8 = 0; s8 < kCols / 8; ++s8) {
+          float v[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const int c = 8 * s8 + q;
+            v[q] = act_apply(__uint_as_float(rg[c / 16][c % 16]) + bias_col[c], a.act);
+            if (valid) pool_acc[c] += v[q];
+          }
+          if (valid) {
+            const int c0 = 8 * s8, run = c0 >> a.run_log2, off = c0 & (run_len - 1);
+            __nv_bfloat16* o = a.dst + (row0 + (int64_t)run * a.out_w) * a.n_real + off;
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+              pk[q] = *reinterpret_cast<uint32_t*>(&t);
+            }
+            *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        if (++acc == 2) { acc = 0; accp ^= 1; }
+      }
+      if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
+        if constexpr (kCols >= 32) {
+#pragma unroll
+          for (int blk = 0; blk < kCols / 32; ++blk) {
+            float v[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = pool_acc[blk * 32 + q];
+            const float sum = transpose_reduce32(v, lane);
+            atomicAdd(a.pool + (int64_t)un.b * a.n_real + ((blk * 32 + lane) & (a.n_real - 1)), sum);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCols; ++c) {
+            float sum = pool_acc[c];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) atomicAdd(a.pool + (int64_t)un.b * a.n_real + (c & (a.n_real - 1)), sum);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+static int ilog2_exact(int v) { return (v > 0 && (v & (v - 1)) == 0) ? __builtin_ctz(v) : -1; }
+
+extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
+  DCS_REQUIRE(p && p->src0 && p->dst && p->weights && p->items && p->bias, "dcs_cconv2d_strip_fwd: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->cout > 0, "dcs_cconv2d_strip_fwd: bad shape");
+  DCS_REQUIRE(p->stride_w == 1 || p->stride_w == 2, "dcs_cconv2d_strip_fwd: stride_w must be 1 or 2");
+  DCS_REQUIRE(p->in_w % p->stride_w == 0, "dcs_cconv2d_strip_fwd: in_w must be a multiple of stride_w");
+  DCS_REQUIRE(p->n_groups >= 1 && p->n_groups <= DCS_STRIP_MAX_GROUPS, "dcs_cconv2d_strip_fwd: bad n_groups");
+  DCS_REQUIRE((p->c1 == 0) == (p->src1 == nullptr), "dcs_cconv2d_strip_fwd: src1 / c1 mismatch");
+  const int P0 = 4 * p->c0 * p->stride_w, P1 = p->c1 ? 4 * p->c1 * p->stride_w : P0;   // strip row bytes (bf16 complex)
+  DCS_REQUIRE((P0 == 32 || P0 == 64 || P0 == 128) && (P1 == 32 || P1 == 64 || P1 == 128),
+              "dcs_cconv2d_strip_fwd: strip rows must be 32, 64 or 128 bytes (got %d, %d)", P0, P1);
+  DCS_REQUIRE(p->box_units >= kStripM && p->box_units <= 256, "dcs_cconv2d_strip_fwd: box_units must be in [128, 256]");
+  const int N = 2 * p->cout;
+  DCS_REQUIRE(ilog2_exact(N) >= 3, "dcs_cconv2d_strip_fwd: 2*cout must be a power of two >= 8");
+  DCS_REQUIRE(p->cols == 32 || p->cols == 64, "dcs_cconv2d_strip_fwd: cols must be 32 or 64");
+  DCS_REQUIRE(p->n_mma % 16 == 0 && p->n_mma >= 16 && p->n_mma <= p->cols, "dcs_cconv2d_strip_fwd: bad n_mma");
+  const int run = p->up_w * N;
+  DCS_REQUIRE(ilog2_exact(run) >= 3 && p->cols % run == 0, "dcs_cconv2d_strip_fwd: cols must be a multiple of up_w*2*cout");
+  DCS_REQUIRE(((uintptr_t)p->src0 % 16 == 0) && ((uintptr_t)p->src1 % 16 == 0) && ((uintptr_t)p->weights % 16 == 0) &&
+              ((uintptr_t)p->dst % 16 == 0), "dcs_cconv2d_strip_fwd: pointers must be 16-byte aligned");
+
+  {  // the item table is read on the host (it is copied into the kernel parameters): refuse a device pointer
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p->items) == cudaSuccess)
+      DCS_REQUIRE(at.type != cudaMemoryTypeDevice, "dcs_cconv2d_strip_fwd: items must be a HOST pointer");
+    else
+      cudaGetLastError();
+  }
+  StripArgs a;
+  memset(&a, 0, sizeof(a));
+  a.batch = p->batch;
+  a.PH = p->out_h / p->up_h; a.PW = p->out_w / p->up_w;
+  a.out_h = p->out_h; a.out_w = p->out_w; a.up_h = p->up_h; a.up_w = p->up_w; a.n_real = N; a.run_log2 = ilog2_exact(run);
+  a.s_h = p->stride_h;
+  a.n_strips = (a.PW + kStripM - 1) / kStripM;
+  const uint32_t strip0 = ((uint32_t)(p->box_units * P0) + 1023u) & ~1023u;
+  const uint32_t strip1 = p->c1 ? (((uint32_t)(p->box_units * P1) + 1023u) & ~1023u) : 0u;
+  a.slot_bytes = strip0 + strip1; a.src1_off = strip0; a.has_src1 = p->c1 ? 1 : 0;
+  a.tx_bytes = (uint32_t)(p->box_units * P0 + (p->c1 ? p->box_units * P1 : 0));
+  a.row_bytes0 = (uint32_t)P0; a.row_bytes1 = (uint32_t)P1;
+  a.n_mma = p->n_mma; a.act = p->act;
+  a.bias = p->bias; a.dst = reinterpret_cast<__nv_bfloat16*>(p->dst); a.pool = p->pool_sums;
+
+  CUtensorMap tmA0, tmA1;
+  const int w_units = p->in_w / p->stride_w;
+  if (int e = make_act_map_generic(&tmA0, p->src0, P0 / 2, w_units, p->in_h, p->batch, p->box_units)) return e;
+  if (p->c1) { if (int e = make_act_map_generic(&tmA1, p->src1, P1 / 2, w_units, p->in_h, p->batch, p->box_units)) return e; }
+  else tmA1 = tmA0;
+  cudaStream_t st = (cudaStream_t)stream;
+
+  for (int g = 0; g < p->n_groups; ++g) {   // one launch per phase group (its weights stay resident in shared memory)
+    const auto& s = p->group[g];
+    DCS_REQUIRE(s.n_items > 0 && s.n_items <= kStripMaxItems && s.item0 >= 0 && s.item0 + s.n_items <= p->n_items_total,
+                "dcs_cconv2d_strip_fwd: bad item range");
+    DCS_REQUIRE(s.n_dy <= kStripMaxRing && s.n_dy >= p->stride_h && s.w_bytes > 0 && s.w_bytes % 16 == 0 && s.w_off % 16 == 0,
+                "dcs_cconv2d_strip_fwd: bad group");
+    DCS_REQUIRE(s.n_ph * run == p->cols, "dcs_cconv2d_strip_fwd: group phase rows x up_w x 2*cout must equal cols");
+    DCS_REQUIRE(s.n_items % s.n_dy == 0, "dcs_cconv2d_strip_fwd: every ring row must carry the same number of items");
+    const int ipr = s.n_items / s.n_dy;
+    for (int i = 0; i < s.n_items; ++i)   // items sorted by drow, ipr per row: the kernel indexes them [drow][ipr]
+      DCS_REQUIRE((int)p->items[s.item0 + i].drow == i / ipr, "dcs_cconv2d_strip_fwd: items must be sorted by drow, %d per ring row", ipr);
+    a.grp.dy_min = s.dy_min; a.grp.n_dy = s.n_dy; a.grp.ph0 = s.ph0; a.grp.x_min = s.x_min; a.grp.w_bytes = (uint32_t)s.w_bytes;
+    a.grp.w_ptr = reinterpret_cast<const unsigned char*>(p->weights) + s.w_off;
+    memcpy(a.items, p->items + s.item0, (size_t)s.n_items * sizeof(uint4));
+    a.w_smem_bytes = ((uint32_t)s.w_bytes + 1023u) & ~1023u;
+    const size_t fixed = 1024 + a.w_smem_bytes + (size_t)p->cols * sizeof(float) + sizeof(StripBarriers);
+    const size_t budget = 227 * 1024;
+    DCS_REQUIRE(fixed + (size_t)(s.n_dy + p->stride_h) * a.slot_bytes <= budget,
+                "dcs_cconv2d_strip_fwd: weights (%u B) + ring (%d x %u B) exceed shared memory", a.w_smem_bytes, s.n_dy + p->stride_h, a.slot_bytes);
+    a.R = (int)std::min<size_t>(kStripMaxRing, (budget - fixed) / a.slot_bytes);
+    const size_t smem = fixed + (size_t)a.R * a.slot_bytes;
+
+    // row chunking: units = images x column strips x row chunks, statically striped over the CTAs.  A unit re-loads
+    // (n_dy - s_h) halo rows, so pick the chunk count that minimises waves x (rows + halo cost).
+    const int ctas = num_sms();
+    double best = 1e30;
+    for (int nc = 1; nc <= a.PH; ++nc) {
+      const int rows = (a.PH + nc - 1) / nc;
+      if ((a.PH + rows - 1) / rows != nc) continue;
+      const int64_t units = (int64_t)p->batch * a.n_strips * nc;
+      const int64_t waves = (units + ctas - 1) / ctas;
+      const double cost = (double)waves * (rows + 0.5 * (s.n_dy - p->stride_h) + 1.0);
+      if (cost < best) { best = cost; a.n_chunks = nc; a.chunk_rows = rows; }
+    }
+    a.n_units = p->batch * a.n_strips * a.n_chunks;
+    const int grid = std::min(ctas, a.n_units);
+
+#define DCS_STRIP_LAUNCH(COLS, NDY, IPR)                                                                                          \
+    do {                                                                                                                          \
+      DCS_CUDA(cudaFuncSetAttribute(cconv_strip_kernel<COLS, NDY, IPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      cconv_strip_kernel<COLS, NDY, IPR><<<grid, kStripThreads, smem, st>>>(tmA0, tmA1, a);                                       \
+    } while (0)
+    // instantiated shapes (accumulator columns, ring rows per output row, MMA items per ring row)
+    if (p->cols == 32 && s.n_dy == 7 && ipr == 7) DCS_STRIP_LAUNCH(32, 7, 7);          // encoder[1]: k7 s(2,2), 1 source
+    else if (p->cols == 64 && s.n_dy == 3 && ipr == 12) DCS_STRIP_LAUNCH(64, 3, 12);   // decoder[5] merged phases
+    else if (p->cols == 64 && s.n_dy == 2 && ipr == 32) DCS_STRIP_LAUNCH(64, 2, 32);   // decoder[4], one phase row per launch
+    else if (p->cols == 64 && s.n_dy == 2 && ipr == 24) DCS_STRIP_LAUNCH(64, 2, 24);   // decoder[4] merged pw
+    else DCS_REQUIRE(false, "dcs_cconv2d_strip_fwd: no kernel instance for cols=%d n_dy=%d items/row=%d", p->cols, s.n_dy, ipr);
+#undef DCS_STRIP_LAUNCH
+    DCS_LAUNCHED();
+  }
+  return 0;
+}

@@ -13,6 +13,8 @@ Memory plan (per plan instance, B utterances of T frames, everything resident in
 act dtype = float32 in the 'fp32' mode (CUDA-core FFMA GEMMs, <=1e-5) and bfloat16 in the 'bf16' mode
 (tcgen05 tensor-core GEMMs with fp32 accumulation, <=2e-3); attention, LSTM, masks, FFTs are fp32 in both.
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -57,6 +59,14 @@ class PackedNet:
             if not last:  # decoder_attention[12], [13] never run (c_network.py:218)
                 self.dec_ca.append(packing.pack_channel_attention(sd, f"decoder_attention.{2 * i}.", device))
                 self.dec_sa.append(packing.pack_spatial_attention(sd, f"decoder_attention.{2 * i + 1}.", device))
+        # few-channel layers: row-strip tensor-core kernel (csrc/cconv_strip.cu); {layer: (c0, c1, merged, groups)}
+        self.strip = {}
+        if bf and os.environ.get("DCS_STRIP", "1") != "0":
+            want = {("enc", 1): (8, 0, True, 1), ("dec", 4): (32, 32, False, 2), ("dec", 5): (16, 16, True, 1)}
+            for (kind, i), (c0, c1, merged, groups) in want.items():
+                pc = (self.enc if kind == "enc" else self.dec)[i] if i < Lr else None
+                if pc is not None and pc.cin == c0 + c1 and (2 * pc.cout) in (16, 32):
+                    self.strip[(kind, i)] = packing.StripConv(pc, c0, c1, merged=merged, groups=groups, device=device)
         self.lstm = packing.pack_lstm(sd, "lstm.", device)
         w_r, w_i = sd["fc.fc_r.weight"], sd["fc.fc_i.weight"]
         self.fc = packing.PackedConv(w_r[:, :, None, None], w_i[:, :, None, None], sd["fc.fc_r.bias"], sd["fc.fc_i.bias"],
@@ -148,8 +158,12 @@ class ForwardPlan:
         ops.spat_apply(x, gate, stats, sa_w7, y)
         return y
 
-    def _conv(self, pk, src0, src1, dst, pool=None):
+    def _conv(self, pk, src0, src1, dst, pool=None, strip=None):
         """Returns (dst, pooled): pooled is True when the kernel accumulated the pooling sums into `pool`."""
+        if strip is not None and self.tc and src0.dtype == torch.bfloat16 and src0.shape[2] % pk.stride[1] == 0:
+            fused = self.fuse_pool and pool is not None
+            ops.cconv_strip(strip, src0, src1, dst, pool_sums=pool if fused else None)
+            return dst, fused
         use_tc = self.tc and (2 * pk.cin) % 16 == 0 and (
             (src0.dtype == torch.bfloat16 and pk.w_tc is not None) or (src0.dtype == torch.float32 and pk.w_tc32 is not None))
         fused = use_tc and self.fuse_pool and pool is not None
@@ -176,7 +190,7 @@ class ForwardPlan:
             if i == 0 and fused_first:  # initial_batchnorm + encoder[0] straight from the spectrogram
                 x = ops.enc0(e0, self.Y, pk.bn0, self.enc[0])
             else:
-                x, enc_pooled[i] = self._conv(pk.enc[i], x, None, self.enc[i], self.pool_enc[i])
+                x, enc_pooled[i] = self._conv(pk.enc[i], x, None, self.enc[i], self.pool_enc[i], pk.strip.get(("enc", i)))
             self._tap(f"enc{i}", x)
         B, H, W, _, _ = x.shape
 
@@ -204,7 +218,7 @@ class ForwardPlan:
             self._tap(f"skip{i}", skip)
             if i == Lr - 1:
                 return d, skip  # decoder[6] is fused with the mask tail (dcs_dec6_tail_fwd)
-            d, pooled = self._conv(pk.dec[i], d, skip, self.dec[i], self.pool_dec[i])
+            d, pooled = self._conv(pk.dec[i], d, skip, self.dec[i], self.pool_dec[i], pk.strip.get(("dec", i)))
             self._tap(f"dec{i}_act", d)
             d = self._attention(d, pk.dec_ca[i], pk.dec_sa[i], self.datt[i], sums=self.pool_dec[i] if pooled else None)
             self._tap(f"dec{i}", d)

@@ -100,6 +100,34 @@ def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
     return dst
 
 
+def cconv_strip(sp, src0, src1, dst, pool_sums=None):
+    """Row-strip tensor-core convolution (bf16) with operands `sp` (packing.StripConv).  Same tensors as cconv()."""
+    L.require_cuda(src0, dst)
+    pk = sp.pk
+    B, H, W, c0, _ = src0.shape
+    c1 = 0 if src1 is None else src1.shape[3]
+    assert (c0, c1) == (sp.c0, sp.c1) and src0.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16
+    _, OH, OW, co, _ = dst.shape
+    assert co == pk.cout
+    p = L.CstripParams()
+    p.src0, p.src1, p.c0, p.c1 = L.ptr(src0), L.ptr(src1), c0, c1
+    p.batch, p.in_h, p.in_w = B, H, W
+    p.out_h, p.out_w, p.cout = OH, OW, co
+    p.up_h, p.up_w = pk.up
+    p.stride_h, p.stride_w = pk.stride
+    p.n_groups = len(sp.groups)
+    for i, g in enumerate(sp.groups):
+        for k, v in g.items():
+            setattr(p.group[i], k, v)
+    p.items, p.n_items_total = L.ptr(sp.item_table), sp.item_table.shape[0]
+    p.weights = L.ptr(sp.w_image)
+    p.box_units, p.n_mma, p.cols = sp.box_units, sp.n_mma, sp.cols
+    p.bias, p.act = L.ptr(pk.bias), pk.act
+    p.dst, p.pool_sums = L.ptr(dst), L.ptr(pool_sums)
+    L.check(L.lib().dcs_cconv2d_strip_fwd(C.byref(p), L.stream_ptr()), "dcs_cconv2d_strip_fwd")
+    return dst
+
+
 def conv_out_hw(pk, H, W):
     if pk.up != (1, 1):
         return H * pk.up[0], W * pk.up[1]

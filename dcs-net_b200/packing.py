@@ -103,6 +103,7 @@ class PackedConv:
         Wt = torch.stack(mats, 0).reshape(self.phases, self.ntaps, N, C2)  # [p][t][n][k]
         Wp = torch.zeros(self.phases, self.ntaps, self.n_pad, C2, dtype=torch.float64)
         Wp[:, :, :N] = Wt
+        self.w_ptnk = Wp                                          # [p][t][n_pad][C2] float64, CPU
         # FFMA operand: [p][t][k][n_pad] fp32 ;  tcgen05 operand: [p][n_pad][t*C2 + k] bf16 (K contiguous)
         self.w_ffma = Wp.permute(0, 1, 3, 2).contiguous().float().to(device)
         self.w_tc = None
@@ -128,6 +129,123 @@ class PackedConv:
             # dcs_dec6_tail_fwd operand: [phase][tap][ci][(M00 M10 M01 M11)]  (M[n][ri], stored by columns)
             self.w_tail = Wp[:, :, :2].reshape(self.phases, self.ntaps, 2, cin, 2).permute(0, 1, 3, 4, 2) \
                 .contiguous().float().to(device)
+
+
+STRIP_M = 128  # pixels (strip rows) per M tile of the row-strip kernel (csrc/cconv_strip.cu)
+
+
+class StripConv:
+    """Operands of dcs_cconv2d_strip_fwd (include/dcsnet.h) derived from a PackedConv: the layer flattened into a
+    table of MMA items over row strips + the resident weight image.
+
+    merged=True : all sub-pixel phases of a group form ONE accumulator (columns (ph, pw, n)), one MMA per
+                  (source row dy, source, dx, 16-channel K slice) with zero blocks where a phase has no such tap
+                  (fewer, wider MMAs: the A operand read from shared memory is what bounds small-N MMAs).
+    merged=False: one MMA per (phase, pre-summed tap, source, K slice) with N = 2*cout.
+    groups      : 1, or 2 = one phase row (ph) per CTA group (halves the resident weights and the ring depth).
+    """
+
+    def __init__(self, pk, c0, c1, merged=True, groups=1, device="cpu"):
+        assert c0 + c1 == pk.cin
+        uh, uw = pk.up
+        sh, sw = pk.stride
+        N = 2 * pk.cout
+        assert N & (N - 1) == 0 and N >= 8
+        assert groups in (1, 2) and (groups == 1 or uh == 2)
+        self.pk, self.c0, self.c1 = pk, c0, c1
+        Wp = pk.w_ptnk
+        T = pk.ntaps
+        dy = [[pk.dy[p * T + t] for t in range(T)] for p in range(pk.phases)]
+        dx = [[pk.dx[p * T + t] for t in range(T)] for p in range(pk.phases)]
+        Pb = [4 * c0, 4 * c1]                              # bytes of one pixel per source (bf16 complex)
+        P = [b * sw for b in Pb]                           # strip row bytes (pixel pairs when stride_w = 2)
+        for s in range(2 if c1 else 1):
+            assert P[s] in (32, 64, 128), f"strip rows must be 32/64/128 bytes, got {P[s]}"
+        unit = lambda d: d // sw                           # strip row (floor) and parity of a tap offset
+        half = lambda d: d % sw
+        all_dx = sorted({d for row in dx for d in row})
+        self.x_min = min(unit(d) for d in all_dx)
+        self.box_units = STRIP_M + max(unit(d) for d in all_dx) - self.x_min
+        strip_off = [0, (self.box_units * P[0] + 1023) // 1024 * 1024]
+        koff = [0, 2 * c0]
+        run = uw * N
+        ph_sets = [list(range(uh))] if groups == 1 else [[0], [1]]
+        self.cols = len(ph_sets[0]) * run
+        assert self.cols in (16, 32, 64), f"accumulator columns per row tile must be 16/32/64, got {self.cols}"
+        self.n_mma = (self.cols + 15) // 16 * 16 if merged else N
+        assert self.n_mma % 16 == 0 and self.n_mma <= self.cols
+        items, blocks, self.groups = [], [], []
+        w_off = 0
+        for phs in ph_sets:
+            plist = [(pl, ph, pw) for pl, ph in enumerate(phs) for pw in range(uw)]
+            dys = sorted({dy[ph * uw + pw][t] for _, ph, pw in plist for t in range(T)})
+            dy_min, n_dy = dys[0], dys[-1] - dys[0] + 1
+            g_items, g_blocks = [], []
+
+            def add(drow, s, d_x, ks, d_col, blk):
+                a_off = strip_off[s] + (unit(d_x) - self.x_min) * P[s] + half(d_x) * Pb[s] + ks * 32
+                g_items.append(dict(a_off16=a_off // 16, b_off16=len(g_blocks) * self.n_mma * 32 // 16, d_col=d_col,
+                                    drow=drow, src=s))
+                g_blocks.append(blk)
+
+            for s in range(2 if c1 else 1):
+                assert Pb[s] % 32 == 0
+            if merged:
+                for d_y in dys:
+                    for s in range(2 if c1 else 1):
+                        for d_x in all_dx:
+                            taps = [(pl, pw, ph * uw + pw, t) for pl, ph, pw in plist for t in range(T)
+                                    if dy[ph * uw + pw][t] == d_y and dx[ph * uw + pw][t] == d_x]
+                            if not taps:
+                                continue
+                            for ks in range(Pb[s] // 32):
+                                blk = torch.zeros(self.n_mma, 16, dtype=torch.float64)
+                                k0 = koff[s] + ks * 16
+                                for pl, pw, p, t in taps:
+                                    c = (pl * uw + pw) * N
+                                    blk[c:c + N] += Wp[p, t, :N, k0:k0 + 16]
+                                add(d_y - dy_min, s, d_x, ks, 0, blk)
+            else:
+                for pl, ph, pw in plist:
+                    p = ph * uw + pw
+                    for t in range(T):
+                        for s in range(2 if c1 else 1):
+                            for ks in range(Pb[s] // 32):
+                                k0 = koff[s] + ks * 16
+                                add(dy[p][t] - dy_min, s, dx[p][t], ks, (pl * uw + pw) * N, Wp[p, t, :N, k0:k0 + 16].clone())
+                order = sorted(range(len(g_items)), key=lambda i: g_items[i]["drow"])   # stable: oldest ring rows first
+                g_items = [g_items[i] for i in order]
+            seen = set()
+            for it in g_items:
+                it["first"] = it["d_col"] not in seen
+                seen.add(it["d_col"])
+            w_bytes = len(g_blocks) * self.n_mma * 32
+            self.groups.append(dict(item0=len(items), n_items=len(g_items), dy_min=dy_min, n_dy=n_dy, ph0=phs[0],
+                                    n_ph=len(phs), x_min=self.x_min, w_bytes=w_bytes, w_off=w_off))
+            w_off += (w_bytes + 1023) // 1024 * 1024
+            items += g_items
+            blocks.append(g_blocks)
+        self.items = items
+        # item table: uint32 x 4 per item {a_off16, b_off16, d_col | drow << 16 | flags << 24, 0}
+        tab = torch.zeros(len(items), 4, dtype=torch.int64)
+        for i, it in enumerate(items):
+            flags = (1 if it["first"] else 0) | (2 if it["src"] else 0)
+            tab[i, 0], tab[i, 1] = it["a_off16"], it["b_off16"]
+            tab[i, 2] = it["d_col"] | (it["drow"] << 16) | (flags << 24)
+        self.item_table = tab.to(torch.int32).contiguous()     # HOST table: it travels in the kernel parameters
+        # weight image: per group, blocks of [n_mma][16] bf16, rows of 32 bytes with the SWIZZLE_32B pattern
+        # (16-byte halves of a row swap when bit 7 of the byte offset is set)
+        img = torch.zeros(w_off // 2, dtype=torch.bfloat16)
+        for g, g_blocks in zip(self.groups, blocks):
+            for bi, blk in enumerate(g_blocks):
+                base = g["w_off"] + bi * self.n_mma * 32
+                n = torch.arange(self.n_mma)[:, None]
+                k = torch.arange(16)[None, :]
+                off = n * 32 + k * 2
+                off = off ^ (((off >> 7) & 1) << 4)
+                img[(base + off) // 2] = blk.to(torch.bfloat16)
+        self.w_image = img.contiguous().to(device)
+        self.smem_weight_bytes = max(g["w_bytes"] for g in self.groups)
 
 
 def pack_lstm(sd, prefix, device, hidden=64, layers=2):

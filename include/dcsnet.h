@@ -102,6 +102,40 @@ typedef struct {
 int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream);    /* fp32 CUDA-core path (<=1e-5 mode) */
 int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (bf16 mode)  */
 
+/* ---- a4 / a12 / a11 (few-channel layers: encoder[1], decoder[4], decoder[5]): "row-strip" tensor-core convolution.
+ *      Same math and reference call sites as dcs_cconv2d_tc_fwd (c_network.py:107-112, 135-147, 214-216); different
+ *      data movement: one TMA box per SOURCE ROW (a strip of `box_units` strip rows; a strip row = one pixel, or a
+ *      pixel pair when stride_w = 2, of 32 / 64 / 128 bytes) is loaded once into a ring of rows in shared memory and
+ *      every tap that touches it is issued as a row-shifted / K-sliced UMMA descriptor over that strip; the layer's
+ *      weights stay resident in shared memory.  The layer is described by a host-built table of MMA items
+ *      (dcs-net_b200/packing.py: StripConv):
+ *        a_off16  (strip_offset + shift*row_bytes + kslice*32) / 16, strip_offset = 0 for src0 and
+ *                 round_up(box_units*row_bytes0, 1024) for src1
+ *        b_off16  offset/16 of the item's [n_mma][16] bf16 weight block (rows of 32 B, SWIZZLE_32B image) in the group's
+ *                 weight image
+ *        d_col    first accumulator column; columns are ordered (phase row, phase col, n) so that one phase row is a
+ *                 contiguous run of up_w*2*cout output elements
+ *        drow     ring row relative to the first source row of the output row: source row = j*stride_h + dy_min + drow
+ *        flags    bit 0: first MMA into its accumulator columns (overwrite), bit 1: reads src1
+ *      Phase groups: group g owns output phase rows ph0 .. ph0+n_ph-1 of every up_h block and is served by its own
+ *      CTAs (weights of one group resident per CTA).  bf16 in / bf16 out only. */
+#define DCS_STRIP_MAX_GROUPS 2
+typedef struct { uint32_t a_off16; uint32_t b_off16; uint16_t d_col; uint8_t drow; uint8_t flags; uint32_t reserved; } dcs_strip_item;
+typedef struct { int item0; int n_items; int dy_min; int n_dy; int ph0; int n_ph; int x_min; int w_bytes; int64_t w_off; } dcs_strip_group;
+typedef struct {
+  const void* src0; const void* src1; int c0; int c1;
+  int batch; int in_h; int in_w;
+  int out_h; int out_w; int cout;
+  int up_h; int up_w; int stride_h; int stride_w;
+  int n_groups; dcs_strip_group group[DCS_STRIP_MAX_GROUPS];
+  const dcs_strip_item* items; int n_items_total;   /* HOST pointer: the table is copied into the kernel parameters */
+  const void* weights;
+  int box_units; int n_mma; int cols;
+  const float* bias; int act;
+  void* dst; float* pool_sums;
+} dcs_cstrip_params;
+int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream);
+
 /* ---- a9: ComplexChannelAttention (c_network.py:53-69; pools network_functions.py:114-138 — the "max" pool is
  *      an average pool, so the gate is sigmoid_c(2*fc(avg))).
  *      dcs_chan_pool: sums[b][c] (complex) = sum over H*W of x (channels-last).  sums must be pre-zeroed.

@@ -75,3 +75,65 @@ def lstm_dataflow(lw, x, hidden=64):
     n = rows * 2 * H
     f = h1.reshape(-1)
     return torch.complex(f[:n] - f[3 * n:4 * n], f[n:2 * n] + f[2 * n:3 * n]).reshape(B, S, 2 * H)
+
+
+def strip_geometry(sp, src0, src1, out_hw):
+    """dcs_cconv2d_strip_fwd's data flow (csrc/cconv_strip.cu) in torch: ring rows, row-shifted / K-sliced strip views,
+    swizzled weight image, accumulator columns (ph, pw, n), epilogue scatter.  Consumes sp.item_table / sp.w_image
+    exactly as the kernel does (bf16 weights, fp64 accumulation here)."""
+    pk = sp.pk
+    uh, uw = pk.up
+    sh, sw = pk.stride
+    N = 2 * pk.cout
+    srcs = [src0] + ([src1] if src1 is not None else [])
+    B, H, W = src0.shape[:3]
+    assert W % sw == 0
+    Pb = [4 * sp.c0, 4 * sp.c1]
+    P = [b * sw for b in Pb]
+    strip_off = [0, (sp.box_units * P[0] + 1023) // 1024 * 1024]
+    # strips as the TMA box delivers them: (B, H, W/sw, P/2 bf16 elements)
+    rows = [s.reshape(B, H, W // sw, -1).double() for s in srcs]
+    OH, OW = out_hw
+    PH, PW = OH // uh, OW // uw
+    out = torch.zeros(B, OH, OW, N, dtype=torch.float64)
+    img = sp.w_image.cpu()
+    tab = sp.item_table.cpu().to(torch.int64)
+    n_strips = (PW + 127) // 128
+    run = uw * N
+    for g in sp.groups:
+        items = tab[g["item0"]:g["item0"] + g["n_items"]]
+        for strip in range(n_strips):
+            x0 = strip * 128
+            for j in range(PH):
+                acc = torch.full((B, 128, sp.cols), float("nan"), dtype=torch.float64)
+                for a16, b16, z, _ in items.tolist():
+                    d_col, drow, flags = z & 0xffff, (z >> 16) & 0xff, (z >> 24) & 0xff
+                    s = 1 if flags & 2 else 0
+                    rel = a16 * 16 - strip_off[s]
+                    shift, within = rel // P[s], rel % P[s]
+                    assert 0 <= shift and shift + 128 <= sp.box_units and within % 32 == 0
+                    y = j * sh + g["dy_min"] + drow
+                    ux = x0 + g["x_min"] + shift + torch.arange(128)
+                    ok = (ux >= 0) & (ux < W // sw) & (0 <= y < H)
+                    A = rows[s][:, min(max(y, 0), H - 1)][:, ux.clamp(0, W // sw - 1)][..., within // 2:within // 2 + 16]
+                    A = A * ok[None, :, None]
+                    n = torch.arange(sp.n_mma)[:, None]
+                    k = torch.arange(16)[None, :]
+                    off = n * 32 + k * 2
+                    off = off ^ (((off >> 7) & 1) << 4)
+                    Wb = img[(g["w_off"] + b16 * 16 + off) // 2].double()          # [n_mma][16]
+                    part = A @ Wb.t()
+                    if flags & 1:
+                        acc[:, :, d_col:d_col + sp.n_mma] = part
+                    else:
+                        acc[:, :, d_col:d_col + sp.n_mma] += part
+                acc = acc + pk.bias.double()[torch.arange(sp.cols) % N]
+                if pk.act == 1:
+                    acc = acc.clamp_min(0)
+                elif pk.act == 2:
+                    acc = torch.where(acc > 0, acc, 0.01 * acc)
+                nx = min(128, PW - x0)
+                for c0 in range(0, sp.cols, run):
+                    oy = j * uh + g["ph0"] + c0 // run
+                    out[:, oy, x0 * uw:(x0 + nx) * uw] = acc[:, :nx, c0:c0 + run].reshape(B, nx * uw, N)
+    return out.reshape(B, OH, OW, pk.cout, 2)

@@ -170,6 +170,36 @@ def test_tensor_core_conv_equals_cuda_core_conv_on_same_operands():
         assert rel_err(got, ref) <= tol, (p.cin, p.cout, p.up, p.stride)
 
 
+@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("dec5", True, 1), ("dec4", False, 2), ("dec4", True, 2)])
+@pytest.mark.parametrize("B,H,W", [(2, 8, 66), (3, 20, 300)])
+def test_strip_conv_equals_cuda_core_conv_on_same_operands(layer, merged, groups, B, H, W):
+    """Row-strip tcgen05 kernel (ring of source rows, row-shifted descriptors, resident weights) vs the FFMA kernel on
+    the SAME bf16 activations; ragged widths (partial strips), several row chunks, fused pooling sums."""
+    from dcsnet_b200 import packing
+    sd = SW.make_state_dict(1)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    p = {"enc1": pk.enc[1], "dec4": pk.dec[4], "dec5": pk.dec[5]}[layer]
+    g = torch.Generator().manual_seed(7)
+    if layer == "enc1":
+        c0, c1 = p.cin, 0
+        x0, x1 = torch.randn(B, H, 2 * W, c0, 2, generator=g).cuda().bfloat16(), None
+    else:
+        c0 = c1 = p.cin // 2
+        x0 = torch.randn(B, H, W, c0, 2, generator=g).cuda().bfloat16()
+        x1 = torch.randn(B, H, W, c1, 2, generator=g).cuda().bfloat16()
+    sp = packing.StripConv(p, c0, c1, merged=merged, groups=groups, device="cuda")
+    oh, ow = ops.conv_out_hw(p, x0.shape[1], x0.shape[2])
+    ref = torch.empty(B, oh, ow, p.cout, 2, device="cuda")
+    ops.cconv(p, x0, x1, ref, use_tc=False)
+    got = torch.full((B, oh, ow, p.cout, 2), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pool = torch.zeros(B, p.cout, 2, device="cuda")
+    ops.cconv_strip(sp, x0, x1, got, pool_sums=pool)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got.float()).any()
+    assert rel_err(got.float(), ref) <= 1.5e-2          # bf16 weights + bf16 output rounding
+    assert rel_err(pool, ref.sum(dim=(1, 2))) <= 1.5e-2
+
+
 # ------------------------------------------------------------------ properties at BASELINE size (B=64 x 4 s)
 @pytest.mark.parametrize("mode,tol", [("fp32", TOL_FP32), ("bf16", 5e-3)])
 def test_full_size_batch_subset_vs_oracle_and_batch_independence(mode, tol):

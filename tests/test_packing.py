@@ -6,7 +6,7 @@ import torch
 import dcsnet_b200 as D
 from dcsnet_b200 import packing, ops
 from oracle import dcsnet_oracle as O, synthetic_weights as SW
-from emulate import conv_geometry, nchw_to_cl, cl_to_nchw, lstm_dataflow
+from emulate import conv_geometry, strip_geometry, nchw_to_cl, cl_to_nchw, lstm_dataflow
 from conftest import rel_err
 
 
@@ -96,3 +96,31 @@ def test_bias_rule_quirk():
     br, bi = torch.tensor([1.0, 2.0, 3.0]), torch.tensor([0.5, -1.0, 4.0])
     p = packing.PackedConv(wr, wi, br, bi)
     assert torch.allclose(p.bias[:6].view(3, 2), torch.stack([br - bi, br + bi], 1))
+
+
+@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("dec5", True, 1), ("dec5", False, 1), ("dec4", False, 2),
+                                                 ("dec4", True, 2)])
+def test_strip_packing(packed, layer, merged, groups):
+    """The row-strip kernel's item table + swizzled weight image (packing.StripConv) describe the same convolution as
+    the per-tap operands (conv_geometry), up to the bf16 rounding of the weights."""
+    _, pk = packed
+    p = {"enc1": pk.enc[1], "dec4": pk.dec[4], "dec5": pk.dec[5], "dec6": pk.dec[6]}[layer]
+    g = torch.Generator().manual_seed(31)
+    if layer == "enc1":
+        H, W = 6, 260                      # W/2 = 130 output columns: two strips, ragged
+        srcs = [torch.randn(2, H, W, p.cin, 2, generator=g), None]
+        c0, c1 = p.cin, 0
+    else:
+        H, W = 3, 131
+        c = p.cin // 2
+        srcs = [torch.randn(2, H, W, c, 2, generator=g), torch.randn(2, H, W, c, 2, generator=g)]
+        c0, c1 = c, c
+    srcs = [None if s is None else s.to(torch.bfloat16).float() for s in srcs]
+    sp = packing.StripConv(p, c0, c1, merged=merged, groups=groups)
+    out_hw = ops.conv_out_hw(p, H, W)
+    ref = conv_geometry(p, srcs[0], srcs[1], out_hw, weights="tc")
+    got = strip_geometry(sp, srcs[0], srcs[1], out_hw)
+    assert not torch.isnan(got).any()
+    assert rel_err(got, ref) <= 1e-2     # merged blocks sum bf16-rounded pre-summed taps in a different order: bf16-level
+    # and against the unrounded operands at bf16 accuracy
+    assert rel_err(got, conv_geometry(p, srcs[0], srcs[1], out_hw)) <= 2e-2

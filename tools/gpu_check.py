@@ -115,6 +115,41 @@ def part_tcunit(B, T):
         print(json.dumps({"part": "tcunit", "layer": name, "rel": rel(got.float(), ref), "nan": int(torch.isnan(got.float()).sum())}))
 
 
+def part_stripunit(B, T):
+    """row-strip tcgen05 conv vs the FFMA conv on identical bf16 inputs + timing against the general tcgen05 kernel"""
+    sd = SW.make_state_dict(0)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    g = torch.Generator().manual_seed(5)
+    cases = [("enc1", pk.enc[1], (B, 128, T // 2, 8), None, True, 1), ("dec4", pk.dec[4], (B, 32, T // 8, 32), True, False, 2),
+             ("dec4m", pk.dec[4], (B, 32, T // 8, 32), True, True, 2), ("dec5", pk.dec[5], (B, 64, T // 4, 16), True, True, 1)]
+    for name, p, s0, two, merged, groups in cases:
+        x0 = torch.randn(*s0, 2, generator=g).cuda().bfloat16()
+        x1 = torch.randn(*s0, 2, generator=g).cuda().bfloat16() if two else None
+        c0 = s0[3]
+        sp = packing.StripConv(p, c0, c0 if two else 0, merged=merged, groups=groups, device="cuda")
+        oh, ow = ops.conv_out_hw(p, s0[1], s0[2])
+        ref = torch.empty(B, oh, ow, p.cout, 2, device="cuda", dtype=torch.bfloat16)
+        got = torch.full((B, oh, ow, p.cout, 2), float("nan"), device="cuda", dtype=torch.bfloat16)
+        pool_ref = torch.zeros(B, p.cout, 2, device="cuda")
+        pool = torch.zeros(B, p.cout, 2, device="cuda")
+        ops.cconv(p, x0, x1, ref, use_tc=True, pool_sums=pool_ref)
+        ops.cconv_strip(sp, x0, x1, got, pool_sums=pool)
+        torch.cuda.synchronize()
+        res = {"part": "stripunit", "layer": name, "rel": rel(got.float(), ref.float()), "pool_rel": rel(pool, pool_ref),
+               "nan": int(torch.isnan(got.float()).sum())}
+        for label, fn in (("ms_strip", lambda: ops.cconv_strip(sp, x0, x1, got)), ("ms_tc", lambda: ops.cconv(p, x0, x1, ref, use_tc=True))):
+            for _ in range(2):
+                fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(5):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            res[label] = round(e0.elapsed_time(e1) / 5, 4)
+        print(json.dumps(res), flush=True)
+
+
 def part_layers(B, T):
     """per-layer timing of the tcgen05 conv (and the FFMA layers) at full size"""
     sd = SW.make_state_dict(0)
@@ -245,6 +280,8 @@ if __name__ == "__main__":
         part_net(part, B, T)
     elif part == "tcunit":
         part_tcunit(B, T)
+    elif part == "stripunit":
+        part_stripunit(B, T)
     elif part == "layers":
         part_layers(B, T)
     elif part.startswith("time"):
