@@ -275,7 +275,8 @@ def measure_roofline(plan, args, B, T):
         setattr(ops, name, inner)
 
     wrap("cconv", lambda pk, s0, s1, dst, use_tc=False, pool_sums=None: "conv_tc" if use_tc else "conv_ffma")
-    for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "clstm", "mask_combine", "enc0", "dec6_tail"):
+    wrap("cconv_strip", lambda *a, **k: "conv_strip")
+    for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "attention_fused", "clstm", "mask_combine", "enc0", "dec6_tail"):
         wrap(n, lambda *a, _n=n, **k: _n)
     steps = max(3, min(args.steps, 10))
     try:
@@ -291,20 +292,22 @@ def measure_roofline(plan, args, B, T):
     stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in acc.items()}
     fl = conv_flops_per_utterance(T)
     tc_layers = [k for k in fl if k not in ("enc0", "dec6")] if args.mode == "bf16" else []
-    n_tc = len(acc.get("conv_tc", [])) // steps
+    n_tc = (len(acc.get("conv_tc", [])) + len(acc.get("conv_strip", []))) // steps
     roof = None
     if args.mode == "bf16" and n_tc:
         flops = B * sum(fl[k] for k in tc_layers)
-        t = stage_ms["conv_tc"] / 1e3
+        t_ms = stage_ms.get("conv_tc", 0.0) + stage_ms.get("conv_strip", 0.0)
+        t = t_ms / 1e3
         peak = peaks.get("bf16_tflops_sustained")
         which = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
         if not peak:
             peak, which = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
         ach = flops / t / 1e12
-        roof = {"bound": "tensor", "kernel": "dcs::cconv_tc_kernel (13 launches/step: enc1..enc6, dec0..dec5 bf16 + fc tf32)",
+        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM complex convs: dcs::cconv_tc_kernel (enc2..enc6, dec0..dec3 bf16, fc tf32) + "
+                                             "dcs::cconv_strip_kernel (enc1, dec4, dec5 bf16)",
                 "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
                 "peak_source": which,
-                "algorithmic_flops_per_step": flops, "avg_launch_ms": stage_ms["conv_tc"] / n_tc, "launches_per_step": n_tc,
+                "algorithmic_flops_per_step": flops, "avg_launch_ms": t_ms / n_tc, "launches_per_step": n_tc,
                 "note": "reference dense formulation FLOPs (SURVEY Appendix C); executed FLOPs are 1.5x/2.25x lower in the decoder (pre-summed sub-pixel taps)"}
     elif args.mode == "fp32":
         flops = B * sum(fl.values())

@@ -87,11 +87,17 @@ class SpatApplyParams(C.Structure):
                 ("gate_out", _vp)]
 
 
+class AttentionParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("sums", _vp), ("batch", _i), ("h", _i), ("w", _i), ("channels", _i),
+                ("reduced", _i), ("in_dtype", _i), ("out_dtype", _i),
+                ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp), ("w7", _vp)]
+
+
 class ClstmParams(C.Structure):
     _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("in_dtype", _i),
                 ("w_ih0", _vp), ("w_ih1", _vp), ("w_hh", _vp), ("bias", _vp),
                 ("workspace", _vp), ("workspace_bytes", _i64), ("w_ih0_t", _vp), ("w_ih1_t", _vp),
-                ("seqs_per_cta", _i)]
+                ("seqs_per_cta", _i), ("w_hh_frag", _vp)]
 
 
 class MaskCombineParams(C.Structure):
@@ -126,6 +132,7 @@ SYMBOLS = {
     "dcs_chan_gate": (_i, [C.POINTER(ChanGateParams), _vp]),
     "dcs_spat_stats": (_i, [C.POINTER(SpatStatsParams), _vp]),
     "dcs_spat_apply": (_i, [C.POINTER(SpatApplyParams), _vp]),
+    "dcs_attention_fused": (_i, [C.POINTER(AttentionParams), _vp]),
     "dcs_clstm_workspace_bytes": (_i64, [_i, _i, _i]),
     "dcs_clstm_fwd": (_i, [C.POINTER(ClstmParams), _vp]),
     "dcs_mask_combine": (_i, [C.POINTER(MaskCombineParams), _vp]),

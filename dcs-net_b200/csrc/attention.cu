@@ -222,6 +222,198 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
   }
 }
 
+
+// ---------------------------------------------------------------- fused: channel gate MLP + spatial attention, ONE pass
+// y = SA(u) * u with u = CA(x) * x  (c_network.py:208-211 / 219-220) for one (TH x TW) pixel tile per CTA:
+//   0. the squeeze/excite MLP on this image's pooled sums (recomputed per CTA: C*R complex MACs, negligible)
+//   1. x tile + 3-pixel halo -> shared memory (the only HBM read of x; halo re-reads are L2 hits)
+//   2. per-pixel channel statistics of u over tile + halo -> shared (zero outside the image = the conv's zero padding)
+//   3. 7x7 complex conv + ComplexSigmoid -> spatial gate of the inner tile
+//   4. y = gate_s * gate_c * x from the shared tile -> HBM
+// HBM traffic: x once in, y once out (the separate stats / apply kernels read x twice and round-trip 16 B / pixel of
+// statistics).  TH, TW are runtime (TW % 4 == 0, TW * TH <= 1024); channels C = 1 << clog2.
+constexpr int kFaR = 3, kFaThreads = 256;
+
+struct FusedAttArgs {
+  const void* x; void* y;
+  const float* sums; float inv_hw;
+  const float *w1_r, *w1_i, *w2_r, *w2_i, *w7;
+  int H, W, C, clog2, R, TH, TW;
+};
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kFaThreads, 2) attention_fused_kernel(const FusedAttArgs a) {
+  extern __shared__ __align__(16) unsigned char fa_smem[];
+  constexpr int VI = Vec16<TI>::N;                 // complex elements per 16-byte vector of the input type
+  const int C = a.C, TH = a.TH, TW = a.TW;
+  const int PH = TH + 2 * kFaR, PW = TW + 2 * kFaR;
+  TI* xs = reinterpret_cast<TI*>(fa_smem);                                             // [PH][PW][C][2]
+  float4* st = reinterpret_cast<float4*>(fa_smem + (size_t)PH * PW * C * 2 * sizeof(TI));   // [PH][PW]
+  float2* sg = reinterpret_cast<float2*>(st + PH * PW);                                  // [TH][TW]
+  float2* gs = sg + TH * TW;                                                             // [C] channel gate
+  float2* avg = gs + C;                                                                  // [C]
+  float2* hid = avg + C;                                                                 // [16]
+  float4* wq = reinterpret_cast<float4*>(hid + 16);                                      // [49]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z, y0 = blockIdx.y * TH, x0 = blockIdx.x * TW;
+  const TI* xb = reinterpret_cast<const TI*>(a.x) + (int64_t)b * a.H * a.W * C * 2;
+
+  // ---- 1. issue the tile loads first (they overlap the gate MLP): 16-byte vectors, zero outside the image
+  const int vec_per_px = C / VI;
+  const int n_vec = PH * PW * vec_per_px;
+  const int vlog2 = a.clog2 - (VI == 4 ? 2 : 1);
+  for (int i = tid; i < n_vec; i += kFaThreads) {
+    const int px = i >> vlog2, cv = i & (vec_per_px - 1);
+    const int r = px / PW, c = px - r * PW;
+    const int yy = y0 + r - kFaR, xx = x0 + c - kFaR;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if ((unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W)
+      v = __ldg(reinterpret_cast<const uint4*>(xb + (((int64_t)yy * a.W + xx) * C + cv * VI) * 2));
+    reinterpret_cast<uint4*>(xs)[i] = v;
+  }
+  // ---- 0. channel gate (ComplexChannelAttention: sigmoid_c(2 W2 crelu(W1 avg)))
+  for (int i = tid; i < 49; i += kFaThreads) wq[i] = make_float4(a.w7[i], a.w7[49 + i], a.w7[98 + i], a.w7[147 + i]);
+  for (int c = tid; c < C; c += kFaThreads)
+    avg[c] = make_float2(a.sums[((int64_t)b * C + c) * 2] * a.inv_hw, a.sums[((int64_t)b * C + c) * 2 + 1] * a.inv_hw);
+  __syncthreads();
+  for (int r = warp; r < a.R; r += kFaThreads / 32) {
+    float re = 0.f, im = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wr = a.w1_r[r * C + c], wi = a.w1_i[r * C + c];
+      re += wr * avg[c].x - wi * avg[c].y;
+      im += wr * avg[c].y + wi * avg[c].x;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+    if (lane == 0) hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kFaThreads) {
+    float re = 0.f, im = 0.f;
+    for (int r = 0; r < a.R; ++r) {
+      const float wr = a.w2_r[c * a.R + r], wi = a.w2_i[c * a.R + r];
+      re += wr * hid[r].x - wi * hid[r].y;
+      im += wr * hid[r].y + wi * hid[r].x;
+    }
+    gs[c] = make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
+  }
+  __syncthreads();
+  // ---- 2. channel statistics of u = g_c * x per pixel of tile + halo; G lanes share a pixel
+  {
+    const int G = min(32, vec_per_px), glog2 = 31 - __clz(G);
+    const int sub = tid & (G - 1), grp = tid >> glog2, groups = kFaThreads >> glog2;
+    const float invC = 1.f / (float)C;
+    for (int pbase = 0; pbase < PH * PW; pbase += groups) {   // CTA-uniform trip count (shuffles)
+      const int p = pbase + grp;
+      float sr = 0.f, si = 0.f, mr = -INFINITY, mi = -INFINITY;
+      if (p < PH * PW) {
+        for (int c = sub * VI; c < C; c += G * VI) {
+          float2 v[VI];
+          const uint4 q = *reinterpret_cast<const uint4*>(xs + ((int64_t)p * C + c) * 2);
+          if constexpr (VI == 4) {
+            const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = make_float2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u));
+          } else {
+            v[0] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+            v[1] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
+          }
+#pragma unroll
+          for (int e = 0; e < VI; ++e) {
+            const float2 u = cmul(gs[c + e], v[e]);
+            sr += u.x; si += u.y;
+            mr = fmaxf(mr, u.x); mi = fmaxf(mi, u.y);
+          }
+        }
+      }
+      for (int o = G >> 1; o; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o);
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+      }
+      if (sub == 0 && p < PH * PW) {
+        const int r = p / PW, c = p - r * PW;
+        const int yy = y0 + r - kFaR, xx = x0 + c - kFaR;
+        const bool in = (unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W;   // zero padding of the 7x7 conv
+        st[p] = in ? make_float4(sr * invC, si * invC, mr, mi) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 3. ComplexConv2d(2,1,7,padding=3,bias=False) + ComplexSigmoid.  A thread owns NR vertically adjacent pixels of
+  //         one tile column: consecutive lanes read consecutive 16-byte statistics (conflict-free LDS.128; owning
+  //         horizontally adjacent pixels puts the lanes 64 bytes apart, a 4-way bank conflict), and each loaded
+  //         value is reused by up to NR x 7 taps from registers.
+  {
+    const int NR = min(4, TH), twlog = 31 - __clz(TW);
+    for (int t = tid; t < (TH / NR) * TW; t += kFaThreads) {
+      const int col = t & (TW - 1), r = (t >> twlog) * NR;
+      float2 acc[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        float4 sv[10];
+#pragma unroll
+        for (int j = 0; j < 10; ++j) sv[j] = (j < NR + 6) ? st[(r + j) * PW + col + kx] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < 7; ++ky) {
+          const float4 wv = wq[ky * 7 + kx];  // (Wr[mean], Wr[max], Wi[mean], Wi[max])
+          const float2 w_mean = make_float2(wv.x, wv.z), w_mean_j = make_float2(-wv.z, wv.x);   // w, j*w
+          const float2 w_max = make_float2(wv.y, wv.w), w_max_j = make_float2(-wv.w, wv.y);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 sq = sv[q + ky];     // (mean.re, mean.im, max.re, max.im)
+            ffma2(acc[q], w_mean, make_float2(sq.x, sq.x));
+            ffma2(acc[q], w_mean_j, make_float2(sq.y, sq.y));
+            ffma2(acc[q], w_max, make_float2(sq.z, sq.z));
+            ffma2(acc[q], w_max_j, make_float2(sq.w, sq.w));
+          }
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (q < NR) sg[(r + q) * TW + col] = make_float2(sigmoidf_(acc[q].x), sigmoidf_(acc[q].y));
+    }
+  }
+  __syncthreads();
+  // ---- 4. y = gate_s * (gate_c * x), inner tile, from the shared copy
+  {
+    TO* yb = reinterpret_cast<TO*>(a.y) + (int64_t)b * a.H * a.W * C * 2;
+    const int n_inner = TH * TW * vec_per_px;
+    const int twlog = 31 - __clz(TW);
+    for (int i = tid; i < n_inner; i += kFaThreads) {
+      const int px = i >> vlog2, cv = i & (vec_per_px - 1);
+      const int r = px >> twlog, c = px & (TW - 1);
+      const int yy = y0 + r, xx = x0 + c;
+      if (yy >= a.H || xx >= a.W) continue;
+      const int p = (r + kFaR) * PW + c + kFaR;
+      const uint4 q = *reinterpret_cast<const uint4*>(xs + ((int64_t)p * C + cv * VI) * 2);
+      float2 v[VI];
+      if constexpr (VI == 4) {
+        const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = make_float2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u));
+      } else {
+        v[0] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
+        v[1] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
+      }
+      const float2 g = sg[r * TW + c];
+#pragma unroll
+      for (int e = 0; e < VI; ++e) v[e] = cmul(g, cmul(gs[cv * VI + e], v[e]));
+      const int64_t o = ((int64_t)yy * a.W + xx) * C + cv * VI;
+      if constexpr (sizeof(TO) == sizeof(TI)) {
+        Vec16<TO>::st(yb, o, v);
+      } else if constexpr (sizeof(TO) == 2) {          // fp32 in, bf16 out: 2 complex = 8 bytes
+        __nv_bfloat162 t0 = __float22bfloat162_rn(v[0]), t1 = __float22bfloat162_rn(v[1]);
+        *reinterpret_cast<uint2*>(yb + 2 * o) = make_uint2(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1));
+      } else {                                         // bf16 in, fp32 out: 4 complex = 32 bytes
+        *reinterpret_cast<float4*>(yb + 2 * o) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+        *reinterpret_cast<float4*>(yb + 2 * o + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
+      }
+    }
+  }
+}
+
 }  // namespace dcs
 
 using namespace dcs;
@@ -288,6 +480,45 @@ extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
   else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_SA(__nv_bfloat16, float);
   else DCS_SA(__nv_bfloat16, __nv_bfloat16);
 #undef DCS_SA
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_attention_fused(const dcs_attention_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->y && p->sums && p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->w7, "dcs_attention_fused: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0, "dcs_attention_fused: bad shape");
+  DCS_REQUIRE(pow2(p->channels) && p->channels >= 4 && p->channels <= 256 && p->reduced > 0 && p->reduced <= 16,
+              "dcs_attention_fused: channels must be a power of two in [4, 256], reduced <= 16");
+  const int C = p->channels;
+  const size_t esz = p->in_dtype == DCS_BF16 ? 2 : 4;
+  // tile: full image height when it is short (no vertical halo), else 16 rows; the widest power-of-two TW whose
+  // x tile + halo stays under ~92 KB (two CTAs per SM)
+  const int TH = p->h <= 32 ? p->h : 16;
+  DCS_REQUIRE(TH <= 2 || TH % 4 == 0, "dcs_attention_fused: image height must be 1, 2 or a multiple of 4 (got %d)", p->h);
+  int TW = 64;
+  auto bytes = [&](int tw) {
+    const size_t ph = TH + 2 * kFaR, pw = tw + 2 * kFaR;
+    return ph * pw * C * 2 * esz + ph * pw * sizeof(float4) + (size_t)TH * tw * sizeof(float2) + (size_t)(2 * C + 16) * sizeof(float2) + 49 * sizeof(float4);
+  };
+  while (TW > 4 && (bytes(TW) > 100 * 1024 || TH * TW > 1024)) TW >>= 1;
+  const size_t smem = bytes(TW);
+  DCS_REQUIRE(smem <= 227 * 1024, "dcs_attention_fused: tile does not fit shared memory (C=%d H=%d)", C, p->h);
+  FusedAttArgs a;
+  a.x = p->x; a.y = p->y; a.sums = p->sums; a.inv_hw = 1.f / ((float)p->h * (float)p->w);
+  a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
+  a.H = p->h; a.W = p->w; a.C = C; a.clog2 = __builtin_ctz(C); a.R = p->reduced; a.TH = TH; a.TW = TW;
+  dim3 grid((p->w + TW - 1) / TW, (p->h + TH - 1) / TH, p->batch);
+  cudaStream_t s = (cudaStream_t)stream;
+#define DCS_FA(TI, TO)                                                                                                   \
+  do {                                                                                                                   \
+    DCS_CUDA(cudaFuncSetAttribute(attention_fused_kernel<TI, TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    attention_fused_kernel<TI, TO><<<grid, kFaThreads, smem, s>>>(a);                                                    \
+  } while (0)
+  if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_FA(float, float);
+  else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_FA(float, __nv_bfloat16);
+  else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_FA(__nv_bfloat16, float);
+  else DCS_FA(__nv_bfloat16, __nv_bfloat16);
+#undef DCS_FA
   DCS_LAUNCHED();
   return 0;
 }

@@ -68,11 +68,6 @@ struct __align__(8) StripBarriers {
   uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-
 // recursive-halving transpose-reduce: 31 shuffles turn 32 columns x 32 lanes into one column sum per lane
 __device__ __forceinline__ float transpose_reduce32(float (&v)[32], int lane) {
 #pragma unroll

@@ -12,6 +12,7 @@
 #include <string.h>
 #include <algorithm>
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace dcs {
 
@@ -116,6 +117,281 @@ __global__ void __launch_bounds__(256, 2) lstm_recurrent_kernel(const float* __r
   }
 }
 
+// Recurrent kernel, 4 sequences per CTA, split-K: thread = (hidden unit u = tid / 4, K quarter kq = tid % 4) keeps the
+// 4 gate rows x 16 columns of W_hh it needs in registers (64 floats) and computes, for each of the 4 sequences, the 4
+// partial gate sums of its quarter with packed fp32x2 FMAs (even / odd k in the two halves).  A 12-shuffle transposing
+// reduce over the 4 lanes of a unit then leaves lane kq with the complete i, f, g, o pre-activations of (unit u,
+// sequence kq): every lane runs one cell update (c stays in a register), h goes to a double-buffered shared array —
+// ONE __syncthreads per step, no gate exchange through shared memory, no idle lanes in the activation phase.
+constexpr int kRec4Smem = 3 * 4 * (8 * kG + 8) * (int)sizeof(float);   // lstm_recurrent4_kernel's pre-activation ring
+
+// kDbg (tools/lstm_probe.cu only; the product instantiates 0): 1 = no pre-activation loads, 2 = no h stores to HBM,
+// 4 = no transcendental cell update, 8 = no recurrent FMAs, 16 = no shuffles.
+template <int kDbg>
+__global__ void __launch_bounds__(256, 1) lstm_recurrent4_kernel(const float* __restrict__ pre0, int64_t stride_lstm,
+                                                                 int64_t stride_dir, int ld, const float* __restrict__ whh,
+                                                                 float* __restrict__ hout, int B, int S) {
+  __shared__ __align__(16) float hs[2][4][kH];
+  const int tid = threadIdx.x, u = tid >> 2, kq = tid & 3;
+  const int dir = blockIdx.y;
+  const int q0 = blockIdx.x * 4;
+  const int lstm = q0 / (2 * B);
+  float2 w[4][8];                                   // [gate][k pair] = W_hh[gate*64 + u][16*kq + 2*i, +1]
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    const float* wrow = whh + ((int64_t)(lstm * 2 + dir) * kG + g * kH + u) * kH + 16 * kq;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(wrow) + i);
+      w[g][2 * i] = make_float2(t.x, t.y);
+      w[g][2 * i + 1] = make_float2(t.z, t.w);
+    }
+  }
+  // this lane's cell: (unit u, sequence kq)
+  float* hq = hout + (int64_t)(q0 + kq) * S * (2 * kH) + dir * kH + u;
+  float c_state = 0.f;
+  for (int i = tid; i < 2 * 4 * kH; i += 256) (&hs[0][0][0])[i] = 0.f;
+  // Input pre-activations: blocks of kBlk time steps x 4 sequences are pulled into a 3-stage shared-memory ring with
+  // 1 KB bulk copies (one per (sequence, step) row, issued by warp 0, completion on an mbarrier).  Per-thread 4-byte
+  // loads of the same data — registers or cp.async, any prefetch depth — took 1.2 us per step (tools/lstm_probe.cu:
+  // 0.585 ms per layer with them, 0.13 ms without): 32-byte sector requests scattered over 512 streams.
+  constexpr int kBlk = 8, kStg = 3, kSeqPitch = kBlk * kG + 8;      // +8 floats: the 4 sequences land on distinct banks
+  extern __shared__ __align__(16) float pre_s[];                     // [kStg][4][kSeqPitch]
+  __shared__ uint64_t full_bar[kStg];
+  const int n_blocks = (S + kBlk - 1) / kBlk;
+  const float* pre_cta = pre0 + lstm * stride_lstm + dir * stride_dir;
+  auto issue_block = [&](int blk) {                                  // whole warp 0: lane i copies row i of the block
+    const int s0 = blk * kBlk, n = min(kBlk, S - s0);
+    const int t_lo = dir ? S - s0 - n : s0;
+    const uint32_t bar = smem_u32(&full_bar[blk % kStg]);
+    const int lane = tid & 31;
+    if (lane == 0 && !(kDbg & 1)) mbar_expect_tx(bar, (uint32_t)(n * 4 * kG * sizeof(float)));
+    __syncwarp();
+    if (!(kDbg & 1) && lane < 4 * n) {
+      const int sq = lane / n, r = lane - sq * n;
+      const int pbq = (q0 + sq) % (2 * B);
+      bulk_g2s(smem_u32(pre_s + ((blk % kStg) * 4 + sq) * kSeqPitch + r * kG), pre_cta + ((int64_t)pbq * S + t_lo + r) * ld,
+               (uint32_t)(kG * sizeof(float)), bar);
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kStg; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32)
+    for (int blk = 0; blk < min(kStg, n_blocks); ++blk) issue_block(blk);
+  const bool hi = (kq & 2) != 0, lo = (kq & 1) != 0;
+  for (int step = 0; step < S; ++step) {
+    const int t = dir ? S - 1 - step : step;
+    const int cur = step & 1;
+    const int blk = step / kBlk, stage = blk % kStg;
+    const int s0 = blk * kBlk, nb = min(kBlk, S - s0);
+    const int t_lo = dir ? S - s0 - nb : s0;
+    if (step == s0 && !(kDbg & 1)) mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)((blk / kStg) & 1));
+    float pcur[4];
+    {
+      const float* pr = pre_s + (stage * 4 + kq) * kSeqPitch + (t - t_lo) * kG + u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pcur[g] = (kDbg & 1) ? 0.f : pr[g * kH];
+    }
+    // all 16 h vectors of this thread's K quarter first (one shared-memory latency per step, not one per use)
+    float4 hreg[4][4];
+#pragma unroll
+    for (int sq = 0; sq < 4; ++sq) {
+      const float4* hp = reinterpret_cast<const float4*>(&hs[cur][sq][16 * kq]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hreg[sq][i] = hp[i];
+    }
+    float2 acc[4][4];                               // [gate][sequence] (even-k, odd-k) partial sums
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+#pragma unroll
+      for (int sq = 0; sq < 4; ++sq) acc[g][sq] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (kDbg & 8) break;
+#pragma unroll
+      for (int sq = 0; sq < 4; ++sq) {
+        const float4 h4 = hreg[sq][i];
+        const float2 ha = make_float2(h4.x, h4.y), hb = make_float2(h4.z, h4.w);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          ffma2(acc[g][sq], w[g][2 * i], ha);
+          ffma2(acc[g][sq], w[g][2 * i + 1], hb);
+        }
+      }
+    }
+    // transposing reduce over the 4 lanes of the unit: lane kq ends up with the sums of sequence kq
+    float r[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float p[4];
+#pragma unroll
+      for (int sq = 0; sq < 4; ++sq) p[sq] = acc[g][sq].x + acc[g][sq].y;
+      float qv[2];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const float send = hi ? p[j] : p[2 + j];
+        const float keep = hi ? p[2 + j] : p[j];
+        qv[j] = keep + ((kDbg & 16) ? send : __shfl_xor_sync(0xffffffffu, send, 2));
+      }
+      const float send = lo ? qv[0] : qv[1];
+      const float keep = lo ? qv[1] : qv[0];
+      r[g] = keep + ((kDbg & 16) ? send : __shfl_xor_sync(0xffffffffu, send, 1)) + pcur[g];
+    }
+    float h;
+    if (kDbg & 4) {
+      c_state = r[1] * c_state + r[0] * r[2];
+      h = r[3] * c_state;
+    } else {
+      const float ig = quick_sigmoid(r[0]);
+      const float fg = quick_sigmoid(r[1]);
+      const float gg = quick_tanh(r[2]);
+      const float og = quick_sigmoid(r[3]);
+      c_state = fg * c_state + ig * gg;
+      h = og * quick_tanh(c_state);
+    }
+    hs[cur ^ 1][kq][u] = h;
+    if (!(kDbg & 2)) hq[(int64_t)t * (2 * kH)] = h;
+    __syncthreads();
+    if (tid < 32 && step == s0 + nb - 1 && blk + kStg < n_blocks) issue_block(blk + kStg);   // every thread is past this block
+  }
+  if (kDbg & 2) hq[0] = c_state;
+}
+
+// Tensor-core recurrent kernel (bf16 / TF32 mode only): the per-step product W_hh (256 x 64) x h (64 x 4 sequences) as
+// mma.sync.m16n8k8 TF32 (fp32 accumulate; N = 8 columns, the upper 4 are zero padding).  The FFMA kernel above is bound
+// by the FP32 pipe (128 FFMA2 per thread per step, ~1000 cycles); here a warp issues 16 MMAs per step.
+//   warp w owns hidden units 8w .. 8w+7 as two M tiles: rows 0-7 / 8-15 = gates (i, f) resp. (g, o) of those units, so
+//   the accumulator fragment of lane l holds i, f, g, o of unit 8w + l/4 for sequences 2(l%4), 2(l%4)+1 — no gate
+//   exchange.  Lanes with l%4 >= 2 (padding columns) take over the odd sequence of lane l-2 (4 shuffles): one cell per
+//   thread.  W_hh lives in registers in A-fragment order (w_hh_frag, packed + tf32-rounded by the host); h is kept in
+//   shared memory, tf32-rounded, in a K order that makes a lane's 16 B-fragment values contiguous (4 LDS.128).
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma_kernel(const float* __restrict__ pre0, int64_t stride_lstm,
+                                                                     int64_t stride_dir, int ld, const float* __restrict__ whh_frag,
+                                                                     float* __restrict__ hout, int B, int S) {
+  __shared__ __align__(16) float hs[2][4][kH];     // [buffer][sequence][permuted k], tf32-rounded
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const int q0 = blockIdx.x * 4;
+  const int lstm = q0 / (2 * B);
+  // A fragments: [lstm][dir][warp][tile][kstep][lane] float4
+  uint4 af[2][8];
+  {
+    const uint4* wf = reinterpret_cast<const uint4*>(whh_frag) + ((int64_t)(lstm * 2 + dir) * 8 + warp) * 2 * 8 * 32 + lane;
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) af[tl][ks] = __ldg(wf + (tl * 8 + ks) * 32);
+  }
+  const int u = 8 * warp + (lane >> 2);                                   // this thread's hidden unit
+  const int l4 = lane & 3;
+  const int seq = l4 < 2 ? 2 * l4 : 2 * (l4 - 2) + 1;                     // this thread's cell: (u, seq)
+  const int nb = lane >> 2;                                               // B-fragment column = sequence (real if < 4)
+  const int hpos = (u & 3) * 16 + (u >> 3) * 2 + ((u >> 2) & 1);          // where logical k = u lives in hs[.][.]
+  float* hq = hout + (int64_t)(q0 + seq) * S * (2 * kH) + dir * kH + u;
+  float c_state = 0.f;
+  for (int i = tid; i < 2 * 4 * kH; i += 256) (&hs[0][0][0])[i] = 0.f;
+
+  constexpr int kBlk = 8, kStg = 3, kSeqPitch = kBlk * kG + 8;
+  extern __shared__ __align__(16) float pre_s[];                          // [kStg][4][kSeqPitch]
+  __shared__ uint64_t full_bar[kStg];
+  const int n_blocks = (S + kBlk - 1) / kBlk;
+  const float* pre_cta = pre0 + lstm * stride_lstm + dir * stride_dir;
+  auto issue_block = [&](int blk) {
+    const int s0 = blk * kBlk, n = min(kBlk, S - s0);
+    const int t_lo = dir ? S - s0 - n : s0;
+    const uint32_t bar = smem_u32(&full_bar[blk % kStg]);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * 4 * kG * sizeof(float)));
+    __syncwarp();
+    if (lane < 4 * n) {
+      const int sq = lane / n, r = lane - sq * n;
+      const int pbq = (q0 + sq) % (2 * B);
+      bulk_g2s(smem_u32(pre_s + ((blk % kStg) * 4 + sq) * kSeqPitch + r * kG), pre_cta + ((int64_t)pbq * S + t_lo + r) * ld,
+               (uint32_t)(kG * sizeof(float)), bar);
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kStg; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32)
+    for (int blk = 0; blk < min(kStg, n_blocks); ++blk) issue_block(blk);
+
+  for (int step = 0; step < S; ++step) {
+    const int t = dir ? S - 1 - step : step;
+    const int cur = step & 1;
+    const int blk = step / kBlk, stage = blk % kStg;
+    const int s0 = blk * kBlk, nbk = min(kBlk, S - s0);
+    const int t_lo = dir ? S - s0 - nbk : s0;
+    // B fragments: h of sequence nb, this lane's 16 k values (k = 8 ks + l4 + 4 half  <->  position l4*16 + 2 ks + half)
+    uint4 hb[4];
+    if (nb < 4) {
+      const uint4* hp = reinterpret_cast<const uint4*>(&hs[cur][nb][l4 * 16]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hb[i] = hp[i];
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) hb[i] = make_uint4(0, 0, 0, 0);
+    }
+    if (step == s0) mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)((blk / kStg) & 1));
+    float pcur[4];
+    {
+      const float* pr = pre_s + (stage * 4 + seq) * kSeqPitch + (t - t_lo) * kG + u;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pcur[g] = pr[g * kH];
+    }
+    // two independent accumulation chains per tile (even / odd k steps) to halve the dependent-MMA latency
+    float d[2][2][4];
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+      for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) d[tl][c][j] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint4 hv = hb[ks >> 1];
+      const uint32_t b0 = (ks & 1) ? hv.z : hv.x, b1 = (ks & 1) ? hv.w : hv.y;
+      mma_tf32(d[0][ks & 1], af[0][ks], b0, b1);
+      mma_tf32(d[1][ks & 1], af[1][ks], b0, b1);
+    }
+    // fragment: [0],[1] = rows 0-7 (gate i resp. g) for sequences 2 l4, 2 l4 + 1; [2],[3] = rows 8-15 (gate f resp. o)
+    float gi[2], gf[2], gg[2], go[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      gi[e] = d[0][0][e] + d[0][1][e];
+      gf[e] = d[0][0][2 + e] + d[0][1][2 + e];
+      gg[e] = d[1][0][e] + d[1][1][e];
+      go[e] = d[1][0][2 + e] + d[1][1][2 + e];
+    }
+    // lanes l4 >= 2 hold padding columns: they take the odd sequence of lane l - 2
+    const int src = lane & ~2;
+    const float oi = __shfl_sync(0xffffffffu, gi[1], src), of = __shfl_sync(0xffffffffu, gf[1], src);
+    const float og_ = __shfl_sync(0xffffffffu, gg[1], src), oo = __shfl_sync(0xffffffffu, go[1], src);
+    const bool odd = l4 >= 2;
+    const float ri = (odd ? oi : gi[0]) + pcur[0], rf = (odd ? of : gf[0]) + pcur[1];
+    const float rg = (odd ? og_ : gg[0]) + pcur[2], ro = (odd ? oo : go[0]) + pcur[3];
+    const float ig = quick_sigmoid(ri), fg = quick_sigmoid(rf), gt = quick_tanh(rg), ot = quick_sigmoid(ro);
+    c_state = fg * c_state + ig * gt;
+    const float h = ot * quick_tanh(c_state);
+    uint32_t h_tf32;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h_tf32) : "f"(h));
+    reinterpret_cast<uint32_t*>(&hs[cur ^ 1][seq][0])[hpos] = h_tf32;
+    hq[(int64_t)t * (2 * kH)] = h;
+    __syncthreads();
+    if (tid < 32 && step == s0 + nbk - 1 && blk + kStg < n_blocks) issue_block(blk + kStg);
+  }
+}
+
 __global__ void lstm_combine_kernel(const float* __restrict__ h1, float2* __restrict__ y, int64_t n_per_q4) {
   // h1: [lstm][part][B*S*2H];  out.re = R(re) - I(im), out.im = R(im) + I(re)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_per_q4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -151,9 +427,15 @@ static int gemm_rows(const float* a, int64_t rows, int K, const float* w, const 
 }
 
 static void launch_rec(int nseq, const float* pre, int64_t stride_lstm, int64_t stride_dir, int ld, const float* whh,
-                       float* hout, int B, int S, cudaStream_t s) {
+                       float* hout, int B, int S, cudaStream_t s, const float* whh_frag = nullptr) {
   dim3 grid(4 * B / nseq, 2);
-  if (nseq == 4) lstm_recurrent_kernel<4><<<grid, 256, 0, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+  if (nseq == 4 && whh_frag) {
+    cudaFuncSetAttribute(lstm_recurrent4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
+    lstm_recurrent4_mma_kernel<<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh_frag, hout, B, S);
+  } else if (nseq == 4) {
+    cudaFuncSetAttribute(lstm_recurrent4_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
+    lstm_recurrent4_kernel<0><<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+  }
   else lstm_recurrent_kernel<2><<<grid, 256, 0, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
 }
 
@@ -195,9 +477,8 @@ extern "C" int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream) {
     DCS_LAUNCHED();
   }
   // NSEQ must divide 2B; 2 sequences per CTA (two co-resident CTAs per SM) unless that overflows the machine
-  int nseq = 2;
-  if ((2 * B) % 4 == 0 && (4 * B / 2) * 2 > 2 * num_sms()) nseq = 4;
-  if (p->seqs_per_cta == 4 && (2 * B) % 4 == 0) nseq = 4;  // one CTA per SM: leaves room for kernels on other streams
+  // 4 sequences per CTA (split-K kernel) whenever a CTA's sequences share one lstm (2B % 4 == 0); else the 2-sequence kernel
+  int nseq = (2 * B) % 4 == 0 ? 4 : 2;
   if (p->seqs_per_cta == 2) nseq = 2;
   const float* whh1 = p->w_hh + (int64_t)4 * kG * kH;
   const int64_t rows2 = 2 * rows;
@@ -205,12 +486,13 @@ extern "C" int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream) {
     // ---- tensor-core (tf32) input projections: pre[(lstm,dir)][(part,b,s)][4H], eight N=256 GEMMs
     for (int sl = 0; sl < 4; ++sl)
       if (int e = gemm_rows_tc(w.xp, rows2, D, p->w_ih0_t + (int64_t)sl * kG * D, p->bias + sl * kG, w.pre + sl * rows2 * kG, stream)) return e;
-    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, p->w_hh, w.h0, B, S, s);
+    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, p->w_hh, w.h0, B, S, s, p->w_hh_frag);
     DCS_LAUNCHED();
     for (int sl = 0; sl < 4; ++sl)
       if (int e = gemm_rows_tc(w.h0 + (int64_t)(sl / 2) * rows2 * 2 * kH, rows2, 2 * kH, p->w_ih1_t + (int64_t)sl * kG * 2 * kH,
                                p->bias + 4 * kG + sl * kG, w.pre + sl * rows2 * kG, stream)) return e;
-    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, whh1, w.h1, B, S, s);
+    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, whh1, w.h1, B, S, s,
+               p->w_hh_frag ? p->w_hh_frag + (int64_t)4 * kG * kH : nullptr);
     DCS_LAUNCHED();
   } else {
     // ---- fp32 CUDA-core projections.  layer 0: pre[(part,b,s)][lstm][dir][4H]

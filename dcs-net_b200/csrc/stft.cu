@@ -238,21 +238,38 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
   const float* mg = mag ? mag + (int64_t)b * kBins * T : nullptr;
   const float* phs = phase ? phase + (int64_t)b * kBins * T : nullptr;
 
+  // The spectrogram rows of chunk c+1 are fetched into registers while chunk c is transformed (one HBM round trip
+  // per chunk was fully exposed before: two CTAs per SM cannot hide it).
+  const int f_ld = tid & 15, k_ld = tid >> 4;
+  float2 nx[16];
+  auto fetch = [&](int c) {
+    const int t = c * kChunk + f_ld;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      nx[i] = make_float2(0.f, 0.f);
+      if (t < T) nx[i] = __ldg(sp + (int64_t)(k_ld + 16 * i) * T + t);
+    }
+  };
+  if (sp) fetch(max(c_begin - 1, 0));
   for (int c = max(c_begin - 1, 0); c < c_end; ++c) {
     const bool emit = c >= c_begin;
     const int t0 = c * kChunk;
     __syncthreads();
-    {  // load [256 rfft rows][16 frames]; row k of the iSTFT input is spectrogram row k (zero row appended at 256)
-      const int f = tid & 15, t = t0 + f;
+    {  // stage [256 rfft rows][16 frames]; row k of the iSTFT input is spectrogram row k (zero row appended at 256)
+      const int f = f_ld, t = t0 + f;
+      if (sp) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          sm.stage[k_ld + 16 * i][f] = t < T ? polar_roundtrip(nx[i], eps, exact != 0) : make_float2(0.f, 0.f);
+        if (c + 1 < c_end) fetch(c + 1);
+      } else {
 #pragma unroll 4
-      for (int i = 0; i < 16; ++i) {
-        const int k = (tid >> 4) + 16 * i;
-        float2 s = make_float2(0.f, 0.f);
-        if (t < T) {
-          if (sp) s = polar_roundtrip(__ldg(sp + (int64_t)k * T + t), eps, exact != 0);
-          else { const float m_ = __ldg(mg + (int64_t)k * T + t), p_ = __ldg(phs + (int64_t)k * T + t); s = make_float2(m_ * cosf(p_), m_ * sinf(p_)); }
+        for (int i = 0; i < 16; ++i) {
+          const int k = k_ld + 16 * i;
+          float2 s = make_float2(0.f, 0.f);
+          if (t < T) { const float m_ = __ldg(mg + (int64_t)k * T + t), p_ = __ldg(phs + (int64_t)k * T + t); s = make_float2(m_ * cosf(p_), m_ * sinf(p_)); }
+          sm.stage[k][f] = s;
         }
-        sm.stage[k][f] = s;
       }
     }
     __syncthreads();

@@ -140,6 +140,10 @@ class ForwardPlan:
         # ComplexLSTM + fc (fork / join is captured into the CUDA graph as parallel branches).  Measured on B200 at
         # batch 64 x 4 s: no gain (9.73 vs 9.72 ms) — the recurrence is issue-bound on 128 SMs, so it stays off.
         self.overlap = False
+        # channel gate + spatial statistics + 7x7 gate conv + product in one kernel per attended tensor
+        # (opt-in with DCS_FUSED_ATTENTION=1: measured slower than the three separate kernels on B200 — its load / stats / conv /
+        # apply phases serialise inside a CTA; kept for the next round's TMA-pipelined version)
+        self.fused_attention = os.environ.get("DCS_FUSED_ATTENTION", "0") == "1"
         self.side = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------ building blocks
@@ -153,6 +157,8 @@ class ForwardPlan:
             sums = self.sums.view(-1)[: B * Cn * 2].view(B, Cn, 2)
             sums.zero_()
             ops.chan_pool(x, sums)
+        if self.fused_attention and Cn >= 4:
+            return ops.attention_fused(x, sums, ca, sa_w7, y)
         ops.chan_gate(sums, H * W, ca, gate)
         ops.spat_stats(x, gate, stats)
         ops.spat_apply(x, gate, stats, sa_w7, y)

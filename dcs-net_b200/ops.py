@@ -160,6 +160,16 @@ def spat_apply(x, gate, stats, w7, y, gate_out=None):
     L.check(L.lib().dcs_spat_apply(C.byref(p), L.stream_ptr()), "dcs_spat_apply")
 
 
+def attention_fused(x, sums, ca, w7, y):
+    """y = SA(CA(x) * x) * (CA(x) * x) in one pass; sums (B,C,2) = sum over H*W of x; ca = pack_channel_attention()."""
+    L.require_cuda(x, sums, y)
+    B, H, W, Cn, _ = x.shape
+    p = L.AttentionParams(L.ptr(x), L.ptr(y), L.ptr(sums), B, H, W, Cn, ca["reduced"], _code(x), _code(y),
+                          L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(w7))
+    L.check(L.lib().dcs_attention_fused(C.byref(p), L.stream_ptr()), "dcs_attention_fused")
+    return y
+
+
 def clstm_workspace_bytes(B, S, hidden=64):
     n = L.lib().dcs_clstm_workspace_bytes(B, S, hidden)
     if n < 0:
@@ -172,7 +182,8 @@ def clstm(x, y, w, workspace, use_tc=False, seqs_per_cta=0):
     B, S, D, _ = x.shape
     p = L.ClstmParams(L.ptr(x), L.ptr(y), B, S, D, y.shape[2] // 2, _code(x), L.ptr(w["w_ih0"]), L.ptr(w["w_ih1"]),
                       L.ptr(w["w_hh"]), L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size(),
-                      L.ptr(w["w_ih0_t"]) if use_tc else None, L.ptr(w["w_ih1_t"]) if use_tc else None, seqs_per_cta)
+                      L.ptr(w["w_ih0_t"]) if use_tc else None, L.ptr(w["w_ih1_t"]) if use_tc else None, seqs_per_cta,
+                      L.ptr(w["w_hh_frag"]) if use_tc else None)
     L.check(L.lib().dcs_clstm_fwd(C.byref(p), L.stream_ptr()), "dcs_clstm_fwd")
     return y
 

@@ -266,7 +266,27 @@ def pack_lstm(sd, prefix, device, hidden=64, layers=2):
     w0_t = round_tf32(w0.float().reshape(4, 4 * hidden, -1))
     w1_t = round_tf32(w1.permute(0, 2, 1).float().reshape(4, 4 * hidden, 2 * hidden))
     return dict(w_ih0=f(w0.t()), w_ih1=f(w1), w_hh=f(whh), bias=f(torch.cat([b0, b1], 0)),
-                w_ih0_t=f(w0_t), w_ih1_t=f(w1_t))
+                w_ih0_t=f(w0_t), w_ih1_t=f(w1_t), w_hh_frag=f(lstm_whh_fragments(whh.float(), hidden)))
+
+
+def lstm_whh_fragments(whh, hidden=64):
+    """W_hh (layer, lstm, dir, 4H, H) -> tf32 A fragments of mma.sync.m16n8k8 for lstm_recurrent4_mma_kernel:
+    [layer][lstm][dir][warp 8][tile 2][kstep 8][lane 32][4].  Warp w owns units 8w..8w+7; tile 0 rows 0-7 / 8-15 are the
+    gates (i, f) of those units, tile 1 the gates (g, o); fragment register j of lane l is row l/4 + 8 (j & 1),
+    column l%4 + 4 (j >> 1) of the 16 x 8 tile of k-step ks (logical k = 8 ks + column)."""
+    H = hidden
+    warp = torch.arange(8).view(8, 1, 1, 1, 1)
+    tile = torch.arange(2).view(1, 2, 1, 1, 1)
+    ks = torch.arange(8).view(1, 1, 8, 1, 1)
+    lane = torch.arange(32).view(1, 1, 1, 32, 1)
+    j = torch.arange(4).view(1, 1, 1, 1, 4)
+    row = lane // 4 + 8 * (j & 1)
+    gate = 2 * tile + (row >= 8).long()
+    unit = 8 * warp + row % 8
+    k = 8 * ks + lane % 4 + 4 * (j >> 1)
+    r = (gate * H + unit).expand(8, 2, 8, 32, 4)
+    c = k.expand(8, 2, 8, 32, 4)
+    return round_tf32(whh[:, :, :, r, c]).contiguous()
 
 
 def pack_channel_attention(sd, prefix, device):

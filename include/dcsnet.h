@@ -165,6 +165,17 @@ typedef struct {
 } dcs_spat_apply_params;
 int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream);
 
+/* ---- a9 + a10 fused: y = SA(u) * u with u = CA(x) * x (c_network.py:208-211, 219-220) in ONE pass over x: the
+ *      channel-gate MLP of dcs_chan_gate on the pooled `sums` (B,C) complex (sum over H*W of x, e.g. the conv
+ *      epilogue's pool_sums), then per pixel tile: x tile + halo -> shared memory, statistics of dcs_spat_stats, the 7x7
+ *      gate conv of dcs_spat_apply, and the product.  x is read once, y written once. */
+typedef struct {
+  const void* x; void* y; const float* sums;
+  int batch; int h; int w; int channels; int reduced; int in_dtype; int out_dtype;
+  const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; const float* w7;
+} dcs_attention_params;
+int dcs_attention_fused(const dcs_attention_params* p, void* stream);
+
 /* ---- a7: ComplexLSTM (c_network.py:12-51): real_lstm / imag_lstm = nn.LSTM(128->64, 2 layers, bidirectional),
  *      out = (R(re) - I(im)) + j (R(im) + I(re)).  x (B,S,D) complex channels-last (the latent, sequence index
  *      = h*W'+w, c_network.py:200) -> y (B,S,2*hidden) complex fp32.
@@ -177,7 +188,11 @@ typedef struct {
   /* optional tensor-core input projections (tf32 operands, kind::tf32): K-major weight slices [4 = lstm*2+dir][4H][D]
    * for layer 0 and [4][4H][2H] for layer 1, pre-rounded to tf32.  NULL -> fp32 CUDA-core GEMMs. */
   const float* w_ih0_t; const float* w_ih1_t;
-  int seqs_per_cta; /* 0 = auto, 2 or 4 sequences per recurrent CTA (4 => one CTA per SM, co-residency with other streams) */
+  int seqs_per_cta; /* 0 = auto (4 when 2*batch % 4 == 0), or 2 */
+  /* optional (tensor-core mode, with w_ih*_t): W_hh pre-rounded to tf32 in mma.sync m16n8k8 A-fragment order
+   * [layer][lstm][dir][warp 8][tile 2][kstep 8][lane 32][4] (packing.pack_lstm); the recurrence then runs on the tensor
+   * cores (TF32 products, fp32 accumulation).  NULL -> fp32 CUDA-core recurrence. */
+  const float* w_hh_frag;
 } dcs_clstm_params;
 int64_t dcs_clstm_workspace_bytes(int batch, int seq, int hidden);
 int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream);

@@ -200,6 +200,34 @@ def test_strip_conv_equals_cuda_core_conv_on_same_operands(layer, merged, groups
     assert rel_err(pool, ref.sum(dim=(1, 2))) <= 1.5e-2
 
 
+@pytest.mark.parametrize("C,H,W", [(128, 2, 70), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 75), (8, 128, 130)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_attention_equals_separate_kernels(C, H, W, dtype):
+    """dcs_attention_fused (gate MLP + statistics + 7x7 gate conv + product in one pass, tile + halo in shared memory)
+    vs the chan_pool -> chan_gate -> spat_stats -> spat_apply sequence; ragged widths, every layer geometry."""
+    from dcsnet_b200 import packing
+    sd = SW.make_state_dict(1)
+    i = {128: 0, 64: 3, 32: 4, 16: 5, 8: 6}[C]
+    ca = packing.pack_channel_attention(sd, f"skip_attention.{2 * i}.", "cuda")
+    w7 = packing.pack_spatial_attention(sd, f"skip_attention.{2 * i + 1}.", "cuda")
+    g = torch.Generator().manual_seed(C + H)
+    B = 2
+    x = torch.randn(B, H, W, C, 2, generator=g).cuda().to(dtype)
+    sums = torch.zeros(B, C, 2, device="cuda")
+    ops.chan_pool(x, sums)
+    gate = torch.empty(B, C, 2, device="cuda")
+    stats = torch.empty(B, H * W, 4, device="cuda")
+    ref = torch.empty_like(x)
+    ops.chan_gate(sums, H * W, ca, gate)
+    ops.spat_stats(x, gate, stats)
+    ops.spat_apply(x, gate, stats, w7, ref)
+    got = torch.full_like(x, float("nan"))
+    ops.attention_fused(x, sums, ca, w7, got)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got.float()).any()
+    assert rel_err(got.float(), ref.float()) <= (2e-6 if dtype == torch.float32 else 8e-3)
+
+
 # ------------------------------------------------------------------ properties at BASELINE size (B=64 x 4 s)
 @pytest.mark.parametrize("mode,tol", [("fp32", TOL_FP32), ("bf16", 5e-3)])
 def test_full_size_batch_subset_vs_oracle_and_batch_independence(mode, tol):
