@@ -166,53 +166,73 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
     st[r][cidx] = v;
   }
   __syncthreads();
-  if (threadIdx.x < kSaTH * (kSaTW / 4)) {  // kSaTH = 16: every thread; kSaTH = 4 (short images): 2 warps
-    // ComplexConv2d(2,1,7,padding=3,bias=False) then ComplexSigmoid.  A thread owns 4 adjacent pixels of one tile row:
-    // per kernel row it loads the 10 stats vectors it needs once and walks the 7 taps from registers.
-    const int r = threadIdx.x / (kSaTW / 4), c4 = (threadIdx.x % (kSaTW / 4)) * 4;
-    float re[4] = {0.f, 0.f, 0.f, 0.f}, im[4] = {0.f, 0.f, 0.f, 0.f};
+  if (threadIdx.x < (kSaTH / 4) * kSaTW) {
+    // ComplexConv2d(2,1,7,padding=3,bias=False) then ComplexSigmoid.  A thread owns 4 VERTICALLY adjacent pixels of one
+    // tile column: consecutive lanes read consecutive 16-byte statistics (conflict-free LDS.128 — four horizontally
+    // adjacent pixels per thread put the lanes 64 bytes apart: a 4-way bank conflict, 58 M conflicts per launch at
+    // C = 8 in the r01b profile), each loaded value feeds up to 4 x 7 taps from registers, complex MACs as packed
+    // fp32x2 FMAs.
+    const int col = threadIdx.x % kSaTW, r = (threadIdx.x / kSaTW) * 4;
+    float2 acc[4];
 #pragma unroll
-    for (int ky = 0; ky < kSaK; ++ky) {
+    for (int q = 0; q < 4; ++q) acc[q] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int kx = 0; kx < kSaK; ++kx) {
       float4 sv[10];
 #pragma unroll
-      for (int j = 0; j < 10; ++j) sv[j] = st[r + ky][c4 + j];
+      for (int j = 0; j < 10; ++j) sv[j] = st[r + j][col + kx];
 #pragma unroll
-      for (int kx = 0; kx < kSaK; ++kx) {
-        const float4 wv = wq[ky * 7 + kx];  // (a0, a1, b0, b1) = (Wr[mean], Wr[max], Wi[mean], Wi[max])
+      for (int ky = 0; ky < kSaK; ++ky) {
+        const float4 wv = wq[ky * 7 + kx];  // (Wr[mean], Wr[max], Wi[mean], Wi[max])
+        const float2 w_mean = make_float2(wv.x, wv.z), w_mean_j = make_float2(-wv.z, wv.x);   // w and j*w
+        const float2 w_max = make_float2(wv.y, wv.w), w_max_j = make_float2(-wv.w, wv.y);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float4 sq = sv[q + kx];
-          re[q] += wv.x * sq.x + wv.y * sq.z - wv.z * sq.y - wv.w * sq.w;
-          im[q] += wv.x * sq.y + wv.y * sq.w + wv.z * sq.x + wv.w * sq.z;
+          const float4 sq = sv[q + ky];     // (mean.re, mean.im, max.re, max.im)
+          ffma2(acc[q], w_mean, make_float2(sq.x, sq.x));
+          ffma2(acc[q], w_mean_j, make_float2(sq.y, sq.y));
+          ffma2(acc[q], w_max, make_float2(sq.z, sq.z));
+          ffma2(acc[q], w_max_j, make_float2(sq.w, sq.w));
         }
       }
     }
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const float2 gv = make_float2(sigmoidf_(re[q]), sigmoidf_(im[q]));
-      sg[r][c4 + q] = gv;
-      if (gate_out && y0 + r < H && x0 + c4 + q < W) gate_out[((int64_t)b * H + y0 + r) * W + x0 + c4 + q] = gv;
+      const float2 gv = make_float2(sigmoidf_(acc[q].x), sigmoidf_(acc[q].y));
+      sg[r + q][col] = gv;
+      if (gate_out && y0 + r + q < H && x0 + col < W) gate_out[((int64_t)b * H + y0 + r + q) * W + x0 + col] = gv;
     }
   }
   if (!y) return;
   __syncthreads();
-  for (int r = 0; r < kSaTH; ++r) {
-    const int yy = y0 + r;
-    if (yy >= H) break;
-    const int wvalid = min(kSaTW, W - x0);
-    const int64_t base = (((int64_t)b * H + yy) * W + x0) * C;
-    if constexpr (sizeof(TI) == sizeof(TO)) {  // same storage type: 16-byte vectors
-      constexpr int V = Vec16<TI>::N;
-      for (int i = threadIdx.x * V; i < wvalid * C; i += 256 * V) {
-        const int px = i / C, c = i - px * C;
+  const int wvalid = min(kSaTW, W - x0), hvalid = min(kSaTH, H - y0);
+  if constexpr (sizeof(TI) == sizeof(TO)) {  // same storage type: 16-byte vectors, one flat loop over the tile
+    constexpr int V = Vec16<TI>::N;
+    const int clog2 = 31 - __clz(C);         // C is a power of two (checked on the host)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // warps stream tile rows (contiguous wvalid*C complex values); short tiles split each row over several warps
+    auto apply_row = [&](int r, int iv0, int step) {
+      const int64_t base = (((int64_t)b * H + y0 + r) * W + x0) * C;
+#pragma unroll 4
+      for (int iv = iv0; iv < wvalid * C; iv += step) {
+        const int px = iv >> clog2, c = iv & (C - 1);
         float2 v[V];
-        Vec16<TI>::ld(x, base + i, v);
+        Vec16<TI>::ld(x, base + iv, v);
         const float2 g = sg[r][px];
 #pragma unroll
         for (int e = 0; e < V; ++e) v[e] = cmul(g, cmul(gs[c + e], v[e]));
-        Vec16<TO>::st(y, base + i, v);
+        Vec16<TO>::st(y, base + iv, v);
       }
+    };
+    if (hvalid >= 8) {
+      for (int r = warp; r < hvalid; r += 8) apply_row(r, lane * V, 32 * V);
     } else {
+      const int segs = 8 / hvalid, seg = warp / hvalid;
+      if (seg < segs) apply_row(warp - seg * hvalid, (seg * 32 + lane) * V, segs * 32 * V);
+    }
+  } else {
+    for (int r = 0; r < hvalid; ++r) {
+      const int64_t base = (((int64_t)b * H + y0 + r) * W + x0) * C;
       for (int i = threadIdx.x; i < wvalid * C; i += 256) {
         const int px = i / C, c = i - px * C;
         const float2 u = cmul(gs[c], Elem<TI>::ldc(x, base + i));
@@ -221,7 +241,6 @@ __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ 
     }
   }
 }
-
 
 // ---------------------------------------------------------------- fused: channel gate MLP + spatial attention, ONE pass
 // y = SA(u) * u with u = CA(x) * x  (c_network.py:208-211 / 219-220) for one (TH x TW) pixel tile per CTA:
@@ -465,7 +484,7 @@ extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
   DCS_REQUIRE(p && p->x && p->stats && p->w7 && (p->y || p->gate_out), "dcs_spat_apply: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && p->channels > 0 && p->channels <= 256, "dcs_spat_apply: bad shape");
   DCS_REQUIRE(p->batch <= 65535, "dcs_spat_apply: batch too large for grid.z");
-  DCS_REQUIRE(p->channels % 4 == 0, "dcs_spat_apply: channels must be a multiple of 4");
+  DCS_REQUIRE(pow2(p->channels) && p->channels >= 4, "dcs_spat_apply: channels must be a power of two >= 4");
   const int th = p->h >= 16 ? 16 : 4;
   dim3 grid((p->w + kSaTW - 1) / kSaTW, (p->h + th - 1) / th, p->batch);
   cudaStream_t s = (cudaStream_t)stream;

@@ -225,57 +225,59 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       un.set(a, u);
       const int x = un.x0 + m;
       const bool valid = x < a.PW;
-      float pool_acc[kCols];
+      // columns are processed in chunks of kChunk = min(kCols, 32); n_real divides kChunk, so column c always maps to
+      // channel (c % kChunk) % n_real and the pooling partial sums need only kChunk registers
+      constexpr int kChunk = kCols < 32 ? kCols : 32;
+      float pool_acc[kChunk];
 #pragma unroll
-      for (int c = 0; c < kCols; ++c) pool_acc[c] = 0.f;
+      for (int c = 0; c < kChunk; ++c) pool_acc[c] = 0.f;
       for (int j = un.j0; j < un.j1; ++j) {
         mbar_wait(smem_u32(&bars->acc_full[acc]), accp);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)kCols;
-        uint32_t rg[kCols / 16][16];
-#pragma unroll
-        for (int cb = 0; cb < kCols / 16; ++cb) tc_ld16(taddr + 16u * cb, rg[cb]);
-        tc_ld_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));   // accumulator is in registers: release it
         const int64_t row0 = ((int64_t)un.b * a.out_h + (int64_t)j * a.up_h + G.ph0) * a.out_w + (int64_t)x * a.up_w;
 #pragma unroll
-        for (int s8 = 0; s8 < kCols / 8; ++s8) {
-          float v[8];
+        for (int ch = 0; ch < kCols / kChunk; ++ch) {
+          uint32_t rg[kChunk / 16][16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int c = 8 * s8 + q;
-            v[q] = act_apply(__uint_as_float(rg[c / 16][c % 16]) + bias_col[c], a.act);
-            if (valid) pool_acc[c] += v[q];
+          for (int cb = 0; cb < kChunk / 16; ++cb) tc_ld16(taddr + (uint32_t)(ch * kChunk + 16 * cb), rg[cb]);
+          tc_ld_wait();
+          if (ch == kCols / kChunk - 1) {   // the whole accumulator has been read: release it to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
           }
-          if (valid) {
-            const int c0 = 8 * s8, run = c0 >> a.run_log2, off = c0 & (run_len - 1);
-            __nv_bfloat16* o = a.dst + (row0 + (int64_t)run * a.out_w) * a.n_real + off;
-            uint32_t pk[4];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-              pk[q] = *reinterpret_cast<uint32_t*>(&t);
+          for (int s8 = 0; s8 < kChunk / 8; ++s8) {
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const int cl = 8 * s8 + q;
+              v[q] = act_apply(__uint_as_float(rg[cl / 16][cl % 16]) + bias_col[ch * kChunk + cl], a.act);
+              if (valid) pool_acc[cl] += v[q];
             }
-            *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            if (valid) {
+              const int c0 = ch * kChunk + 8 * s8, run = c0 >> a.run_log2, off = c0 & (run_len - 1);
+              __nv_bfloat16* o = a.dst + (row0 + (int64_t)run * a.out_w) * a.n_real + off;
+              uint32_t pk[4];
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                pk[q] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
           }
         }
         if (++acc == 2) { acc = 0; accp ^= 1; }
       }
       if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
-        if constexpr (kCols >= 32) {
-#pragma unroll
-          for (int blk = 0; blk < kCols / 32; ++blk) {
-            float v[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) v[q] = pool_acc[blk * 32 + q];
-            const float sum = transpose_reduce32(v, lane);
-            atomicAdd(a.pool + (int64_t)un.b * a.n_real + ((blk * 32 + lane) & (a.n_real - 1)), sum);
-          }
+        if constexpr (kChunk == 32) {
+          const float sum = transpose_reduce32(pool_acc, lane);
+          atomicAdd(a.pool + (int64_t)un.b * a.n_real + (lane & (a.n_real - 1)), sum);
         } else {
 #pragma unroll
-          for (int c = 0; c < kCols; ++c) {
+          for (int c = 0; c < kChunk; ++c) {
             float sum = pool_acc[c];
 #pragma unroll
             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
@@ -312,7 +314,8 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   DCS_REQUIRE(p->box_units >= kStripM && p->box_units <= 256, "dcs_cconv2d_strip_fwd: box_units must be in [128, 256]");
   const int N = 2 * p->cout;
   DCS_REQUIRE(ilog2_exact(N) >= 3, "dcs_cconv2d_strip_fwd: 2*cout must be a power of two >= 8");
-  DCS_REQUIRE(p->cols == 32 || p->cols == 64, "dcs_cconv2d_strip_fwd: cols must be 32 or 64");
+  DCS_REQUIRE(p->cols == 32 || p->cols == 64 || p->cols == 128, "dcs_cconv2d_strip_fwd: cols must be 32, 64 or 128");
+  DCS_REQUIRE(N <= 32, "dcs_cconv2d_strip_fwd: 2*cout must be <= 32 (wider layers use dcs_cconv2d_tc_fwd)");
   DCS_REQUIRE(p->n_mma % 16 == 0 && p->n_mma >= 16 && p->n_mma <= p->cols, "dcs_cconv2d_strip_fwd: bad n_mma");
   const int run = p->up_w * N;
   DCS_REQUIRE(ilog2_exact(run) >= 3 && p->cols % run == 0, "dcs_cconv2d_strip_fwd: cols must be a multiple of up_w*2*cout");
@@ -395,6 +398,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
     else if (p->cols == 64 && s.n_dy == 3 && ipr == 12) DCS_STRIP_LAUNCH(64, 3, 12);   // decoder[5] merged phases
     else if (p->cols == 64 && s.n_dy == 2 && ipr == 32) DCS_STRIP_LAUNCH(64, 2, 32);   // decoder[4], one phase row per launch
     else if (p->cols == 64 && s.n_dy == 2 && ipr == 24) DCS_STRIP_LAUNCH(64, 2, 24);   // decoder[4] merged pw
+    else if (p->cols == 128 && s.n_dy == 7 && ipr == 4) DCS_STRIP_LAUNCH(128, 7, 4);   // encoder[0]: Toeplitz blocks, 16-pixel strip rows
     else DCS_REQUIRE(false, "dcs_cconv2d_strip_fwd: no kernel instance for cols=%d n_dy=%d items/row=%d", p->cols, s.n_dy, ipr);
 #undef DCS_STRIP_LAUNCH
     DCS_LAUNCHED();

@@ -62,6 +62,9 @@ class PackedNet:
         # few-channel layers: row-strip tensor-core kernel (csrc/cconv_strip.cu); {layer: (c0, c1, merged, groups)}
         self.strip = {}
         if bf and os.environ.get("DCS_STRIP", "1") != "0":
+            e0 = self.enc[0]
+            if (e0.cin, e0.cout, e0.kh, e0.kw, tuple(e0.stride)) == (1, 8, 7, 7, (2, 2)) and os.environ.get("DCS_STRIP_ENC0", "1") != "0":
+                self.strip[("enc", 0)] = packing.StripEnc0(e0, device=device)
             want = {("enc", 1): (8, 0, True, 1), ("dec", 4): (32, 32, False, 2), ("dec", 5): (16, 16, True, 1)}
             for (kind, i), (c0, c1, merged, groups) in want.items():
                 pc = (self.enc if kind == "enc" else self.dec)[i] if i < Lr else None
@@ -181,19 +184,25 @@ class ForwardPlan:
             self.taps[name] = t
 
     # ------------------------------------------------------------------ the kernel sequence
-    def _network(self):
+    def _network(self, bn0_ready=False):
         """bn0 -> ... -> decoder[6] raw output (c_network.py:193-222)."""
         pk, Lr = self.pk, self.pk.L
         e0 = pk.enc[0]
         fused_first = (e0.cin, e0.cout, e0.kh, e0.kw, e0.stride) == (1, 8, 7, 7, (2, 2))
-        if self.keep_taps or not fused_first:
+        # encoder[0] on the tensor cores (row-strip kernel, Toeplitz blocks) reads the bf16 initial_batchnorm output
+        strip0 = pk.strip.get(("enc", 0)) if (self.tc and self.T % 16 == 0) else None
+        if (self.keep_taps or not fused_first or strip0 is not None) and not bn0_ready:
             ops.cbn_apply(torch.view_as_real(self.Y).view(self.B, self.F, self.T, 1, 2), pk.bn0, self.bn0)
         x = self.bn0
         if self.fuse_pool:
             self.pool_all.zero_()
         enc_pooled = [False] * Lr
         for i in range(Lr):
-            if i == 0 and fused_first:  # initial_batchnorm + encoder[0] straight from the spectrogram
+            if i == 0 and strip0 is not None:
+                x = ops.cconv_strip(strip0, packing.StripEnc0.view_src(self.bn0), None, self.enc[0],
+                                    pool_sums=self.pool_enc[0] if self.fuse_pool else None)
+                enc_pooled[0] = self.fuse_pool
+            elif i == 0 and fused_first:  # initial_batchnorm + encoder[0] straight from the spectrogram
                 x = ops.enc0(e0, self.Y, pk.bn0, self.enc[0])
             else:
                 x, enc_pooled[i] = self._conv(pk.enc[i], x, None, self.enc[i], self.pool_enc[i], pk.strip.get(("enc", i)))
@@ -245,8 +254,12 @@ class ForwardPlan:
                              noise_spec=self.noise_spec, atan2_eps=self.eps, combine=combine, exact_polar=self.exact)
 
     def _enqueue_from_audio(self, with_noise_audio=False):
-        ops.stft(self.audio_in, self.Y)
-        self._tail(self._network())
+        strip0 = self.tc and self.T % 16 == 0 and ("enc", 0) in self.pk.strip
+        if strip0:  # the STFT kernel also emits the folded initial_batchnorm output (bf16) that encoder[0] reads by TMA
+            ops.stft(self.audio_in, self.Y, bn_affine=self.pk.bn0, bn_out=self.bn0)
+        else:
+            ops.stft(self.audio_in, self.Y)
+        self._tail(self._network(bn0_ready=strip0))
         ops.istft(self.clean_spec, self.audio_out, self.eps, self.exact)
         if with_noise_audio and self.noise_audio is not None:
             ops.istft(self.noise_spec, self.noise_audio, self.eps, self.exact)

@@ -113,8 +113,8 @@ def cconv_strip(sp, src0, src1, dst, pool_sums=None):
     p.src0, p.src1, p.c0, p.c1 = L.ptr(src0), L.ptr(src1), c0, c1
     p.batch, p.in_h, p.in_w = B, H, W
     p.out_h, p.out_w, p.cout = OH, OW, co
-    p.up_h, p.up_w = pk.up
-    p.stride_h, p.stride_w = pk.stride
+    p.up_h, p.up_w = sp.up
+    p.stride_h, p.stride_w = sp.stride
     p.n_groups = len(sp.groups)
     for i, g in enumerate(sp.groups):
         for k, v in g.items():

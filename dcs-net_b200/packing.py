@@ -153,6 +153,7 @@ class StripConv:
         assert N & (N - 1) == 0 and N >= 8
         assert groups in (1, 2) and (groups == 1 or uh == 2)
         self.pk, self.c0, self.c1 = pk, c0, c1
+        self.up, self.stride = tuple(pk.up), tuple(pk.stride)
         Wp = pk.w_ptnk
         T = pk.ntaps
         dy = [[pk.dy[p * T + t] for t in range(T)] for p in range(pk.phases)]
@@ -226,26 +227,80 @@ class StripConv:
             items += g_items
             blocks.append(g_blocks)
         self.items = items
-        # item table: uint32 x 4 per item {a_off16, b_off16, d_col | drow << 16 | flags << 24, 0}
-        tab = torch.zeros(len(items), 4, dtype=torch.int64)
-        for i, it in enumerate(items):
-            flags = (1 if it["first"] else 0) | (2 if it["src"] else 0)
-            tab[i, 0], tab[i, 1] = it["a_off16"], it["b_off16"]
-            tab[i, 2] = it["d_col"] | (it["drow"] << 16) | (flags << 24)
-        self.item_table = tab.to(torch.int32).contiguous()     # HOST table: it travels in the kernel parameters
-        # weight image: per group, blocks of [n_mma][16] bf16, rows of 32 bytes with the SWIZZLE_32B pattern
-        # (16-byte halves of a row swap when bit 7 of the byte offset is set)
-        img = torch.zeros(w_off // 2, dtype=torch.bfloat16)
-        for g, g_blocks in zip(self.groups, blocks):
-            for bi, blk in enumerate(g_blocks):
-                base = g["w_off"] + bi * self.n_mma * 32
-                n = torch.arange(self.n_mma)[:, None]
-                k = torch.arange(16)[None, :]
-                off = n * 32 + k * 2
-                off = off ^ (((off >> 7) & 1) << 4)
-                img[(base + off) // 2] = blk.to(torch.bfloat16)
-        self.w_image = img.contiguous().to(device)
+        self.item_table = _strip_item_table(items)
+        self.w_image = _strip_weight_image(self.groups, blocks, self.n_mma, w_off).to(device)
         self.smem_weight_bytes = max(g["w_bytes"] for g in self.groups)
+
+
+def _strip_item_table(items):
+    """uint32 x 4 per item {a_off16, b_off16, d_col | drow << 16 | flags << 24, 0}; HOST table (kernel parameters)."""
+    tab = torch.zeros(len(items), 4, dtype=torch.int64)
+    for i, it in enumerate(items):
+        flags = (1 if it["first"] else 0) | (2 if it["src"] else 0)
+        tab[i, 0], tab[i, 1] = it["a_off16"], it["b_off16"]
+        tab[i, 2] = it["d_col"] | (it["drow"] << 16) | (flags << 24)
+    return tab.to(torch.int32).contiguous()
+
+
+def _strip_weight_image(groups, blocks, n_mma, total_bytes):
+    """Per group, blocks of [n_mma][16] bf16 as rows of 32 bytes with the SWIZZLE_32B pattern (the 16-byte halves of a row
+    swap when bit 7 of the byte offset is set): the exact shared-memory image, bulk-copied by the kernel."""
+    img = torch.zeros(total_bytes // 2, dtype=torch.bfloat16)
+    n = torch.arange(n_mma)[:, None]
+    k = torch.arange(16)[None, :]
+    off = n * 32 + k * 2
+    off = off ^ (((off >> 7) & 1) << 4)
+    for g, g_blocks in zip(groups, blocks):
+        for bi, blk in enumerate(g_blocks):
+            img[(g["w_off"] + bi * n_mma * 32 + off) // 2] = blk.to(torch.bfloat16)
+    return img.contiguous()
+
+
+class StripEnc0:
+    """encoder[0] (ComplexConv2d 1 -> 8, k7, stride (2,2), on the initial_batchnorm output) for dcs_cconv2d_strip_fwd.
+
+    One complex input channel gives K = 2 per tap, far below an MMA's K = 16, so K is taken from SPACE: a strip row is
+    16 consecutive source pixels (64 bytes) and the 8 output pixels whose windows start in it form N = 8 x 16 columns;
+    a K slice is 8 source pixels, and each (kernel row dy, slice) item multiplies by a Toeplitz block holding the taps
+    dx = 8 (s - 1) + p - 2 j  (source pixel p of slice s, output pixel j).  4 slices x 7 rows = 28 MMAs (N = 128) per
+    1024 output pixels.  The kernel is told a reinterpreted geometry: source (B, F, T/8, 8 "channels"), stride_w 2
+    (a strip row = 2 such pixels), up_w = 8 (8 output pixels per strip row), cout 8."""
+
+    def __init__(self, pk, device="cpu"):
+        assert (pk.cin, pk.cout, pk.kh, pk.kw, tuple(pk.stride), tuple(pk.up)) == (1, 8, 7, 7, (2, 2), (1, 1))
+        self.pk, self.c0, self.c1 = pk, 8, 0
+        self.up, self.stride = (1, 8), (2, 2)
+        N = 16
+        Wp = pk.w_ptnk                                     # [1][49][16][2]
+        tap = {(pk.dy[t], pk.dx[t]): t for t in range(pk.ntaps)}
+        self.x_min, self.box_units, self.cols, self.n_mma = -1, STRIP_M + 2, 8 * N, 8 * N
+        shift, koff = [0, 1, 1, 2], [32, 0, 32, 0]        # slice s: strip row v - 1 + shift[s], byte offset in the row
+        items, blocks = [], []
+        for d_y in range(-3, 4):
+            for sl in range(4):
+                blk = torch.zeros(self.n_mma, 16, dtype=torch.float64)
+                for j in range(8):
+                    for p_ in range(8):
+                        d_x = 8 * (sl - 1) + p_ - 2 * j
+                        if -3 <= d_x <= 3:
+                            blk[j * N:(j + 1) * N, 2 * p_:2 * p_ + 2] = Wp[0, tap[(d_y, d_x)], :N, :]
+                items.append(dict(a_off16=(shift[sl] * 64 + koff[sl]) // 16, b_off16=len(blocks) * self.n_mma * 32 // 16,
+                                  d_col=0, drow=d_y + 3, src=0, first=not items))
+                blocks.append(blk)
+        w_bytes = len(blocks) * self.n_mma * 32
+        self.groups = [dict(item0=0, n_items=len(items), dy_min=-3, n_dy=7, ph0=0, n_ph=1, x_min=self.x_min,
+                            w_bytes=w_bytes, w_off=0)]
+        self.items = items
+        self.item_table = _strip_item_table(items)
+        self.w_image = _strip_weight_image(self.groups, [blocks], self.n_mma, w_bytes).to(device)
+        self.smem_weight_bytes = w_bytes
+
+    @staticmethod
+    def view_src(bn0):
+        """(B, F, T, 1, 2) bf16 initial_batchnorm output -> the (B, F, T/8, 8, 2) view the kernel is given."""
+        B, F, T = bn0.shape[:3]
+        assert T % 16 == 0
+        return bn0.view(B, F, T // 8, 8, 2)
 
 
 def pack_lstm(sd, prefix, device, hidden=64, layers=2):

@@ -82,8 +82,8 @@ def strip_geometry(sp, src0, src1, out_hw):
     swizzled weight image, accumulator columns (ph, pw, n), epilogue scatter.  Consumes sp.item_table / sp.w_image
     exactly as the kernel does (bf16 weights, fp64 accumulation here)."""
     pk = sp.pk
-    uh, uw = pk.up
-    sh, sw = pk.stride
+    uh, uw = sp.up
+    sh, sw = sp.stride
     N = 2 * pk.cout
     srcs = [src0] + ([src1] if src1 is not None else [])
     B, H, W = src0.shape[:3]

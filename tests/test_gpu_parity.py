@@ -200,6 +200,29 @@ def test_strip_conv_equals_cuda_core_conv_on_same_operands(layer, merged, groups
     assert rel_err(pool, ref.sum(dim=(1, 2))) <= 1.5e-2
 
 
+@pytest.mark.parametrize("B,F,T", [(2, 16, 48), (3, 256, 272)])
+def test_strip_enc0_equals_cuda_core_conv(B, F, T):
+    """encoder[0] on the tensor cores (Toeplitz blocks over 16-pixel strip rows) vs the FFMA conv on the same bf16
+    initial_batchnorm output, with the fused pooling sums."""
+    from dcsnet_b200 import packing
+    sd = SW.make_state_dict(1)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    p = pk.enc[0]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, F, T, 1, 2, generator=g).cuda().bfloat16()
+    sp = packing.StripEnc0(p, device="cuda")
+    oh, ow = ops.conv_out_hw(p, F, T)
+    ref = torch.empty(B, oh, ow, p.cout, 2, device="cuda")
+    ops.cconv(p, x, None, ref, use_tc=False)
+    got = torch.full((B, oh, ow, p.cout, 2), float("nan"), device="cuda", dtype=torch.bfloat16)
+    pool = torch.zeros(B, p.cout, 2, device="cuda")
+    ops.cconv_strip(sp, packing.StripEnc0.view_src(x), None, got, pool_sums=pool)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got.float()).any()
+    assert rel_err(got.float(), ref) <= 1.5e-2
+    assert rel_err(pool, ref.sum(dim=(1, 2))) <= 1.5e-2
+
+
 @pytest.mark.parametrize("C,H,W", [(128, 2, 70), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 75), (8, 128, 130)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fused_attention_equals_separate_kernels(C, H, W, dtype):

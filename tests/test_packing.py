@@ -124,3 +124,18 @@ def test_strip_packing(packed, layer, merged, groups):
     assert rel_err(got, ref) <= 1e-2     # merged blocks sum bf16-rounded pre-summed taps in a different order: bf16-level
     # and against the unrounded operands at bf16 accuracy
     assert rel_err(got, conv_geometry(p, srcs[0], srcs[1], out_hw)) <= 2e-2
+
+
+def test_strip_enc0_toeplitz_packing(packed):
+    """encoder[0] on the row-strip kernel: K taken from space (16-pixel strip rows, Toeplitz weight blocks)."""
+    _, pk = packed
+    p = pk.enc[0]
+    g = torch.Generator().manual_seed(3)
+    B, F, T = 2, 12, 48
+    x = torch.randn(B, F, T, 1, 2, generator=g).to(torch.bfloat16).float()
+    sp = packing.StripEnc0(p)
+    out_hw = ops.conv_out_hw(p, F, T)
+    ref = conv_geometry(p, x, None, out_hw)
+    got = strip_geometry(sp, packing.StripEnc0.view_src(x), None, out_hw)
+    assert not torch.isnan(got).any()
+    assert rel_err(got, ref) <= 1e-2

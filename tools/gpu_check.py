@@ -122,6 +122,22 @@ def part_stripunit(B, T):
     g = torch.Generator().manual_seed(5)
     cases = [("enc1", pk.enc[1], (B, 128, T // 2, 8), None, True, 1), ("dec4", pk.dec[4], (B, 32, T // 8, 32), True, False, 2),
              ("dec4m", pk.dec[4], (B, 32, T // 8, 32), True, True, 2), ("dec5", pk.dec[5], (B, 64, T // 4, 16), True, True, 1)]
+    # encoder[0]: Toeplitz strip kernel vs the FFMA enc0 kernel (which reads the fp32 spectrogram)
+    x = torch.randn(B, 256, T, 1, 2, generator=g).cuda().bfloat16()
+    sp0 = packing.StripEnc0(pk.enc[0], device="cuda")
+    ref0 = torch.empty(B, 128, T // 2, 8, 2, device="cuda")
+    got0 = torch.empty(B, 128, T // 2, 8, 2, device="cuda", dtype=torch.bfloat16)
+    ops.cconv(pk.enc[0], x, None, ref0, use_tc=False)
+    ops.cconv_strip(sp0, packing.StripEnc0.view_src(x), None, got0)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.cconv_strip(sp0, packing.StripEnc0.view_src(x), None, got0)
+    e1.record()
+    torch.cuda.synchronize()
+    print(json.dumps({"part": "stripunit", "layer": "enc0", "rel": rel(got0.float(), ref0), "ms_strip": round(e0.elapsed_time(e1) / 5, 4)}), flush=True)
+    del x, ref0, got0
     for name, p, s0, two, merged, groups in cases:
         x0 = torch.randn(*s0, 2, generator=g).cuda().bfloat16()
         x1 = torch.randn(*s0, 2, generator=g).cuda().bfloat16() if two else None
