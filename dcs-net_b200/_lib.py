@@ -54,6 +54,11 @@ class StripGroup(C.Structure):
                 ("w_bytes", _i), ("w_off", _i64)]
 
 
+class StripTail(C.Structure):
+    _fields_ = [("noisy_spec", _vp), ("net_raw", _vp), ("net_out", _vp), ("mask", _vp), ("noise_spec", _vp),
+                ("clean_spec", _vp), ("bias_re", _f), ("bias_im", _f), ("atan2_eps", _f), ("combine", _i), ("exact_polar", _i)]
+
+
 class CstripParams(C.Structure):
     _fields_ = [("src0", _vp), ("src1", _vp), ("c0", _i), ("c1", _i),
                 ("batch", _i), ("in_h", _i), ("in_w", _i),
@@ -64,7 +69,7 @@ class CstripParams(C.Structure):
                 ("weights", _vp),
                 ("box_units", _i), ("n_mma", _i), ("cols", _i),
                 ("bias", _vp), ("act", _i),
-                ("dst", _vp), ("pool_sums", _vp)]
+                ("dst", _vp), ("pool_sums", _vp), ("tail", C.POINTER(StripTail))]
 
 
 class ChanPoolParams(C.Structure):

@@ -32,7 +32,9 @@ namespace dcs {
 int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_units, int h, int b, int box_units);
 
 constexpr int kStripM = 128;
-constexpr int kStripThreads = 192;
+constexpr int kStripThreads = 192;        // warp 0 TMA, warp 1 MMA, 4 epilogue warps
+constexpr int kStripTailEpiWarps = 16;    // the tail epilogue is transcendental-heavy: 4 warps per TMEM lane quadrant
+constexpr int kStripTailThreads = 64 + 32 * kStripTailEpiWarps;
 constexpr int kStripMaxRing = 16;
 constexpr int kStripMaxItems = 64;    // MMA items of one phase group; the table travels in the kernel parameters
 
@@ -56,6 +58,7 @@ struct StripArgs {
   const float* bias;
   __nv_bfloat16* dst;
   float* pool;
+  dcs_strip_tail tail;  // kTail instances only: decoder[6] + bound_cRM x2 + mask combine epilogue
   // The item table lives in the constant bank (kernel parameters) and the issue loop is fully unrolled (kNdy ring
   // rows x kIpr items per row are template parameters), so every item field is a constant-bank operand of a uniform
   // add: ~6 instructions per MMA on the single issuing warp.  (Walking a table in shared memory cost ~40 dependent
@@ -95,8 +98,8 @@ struct UnitIter {  // unit u of a phase group -> (image, column strip, row chunk
   }
 };
 
-template <int kCols, int kNdy, int kIpr>
-__global__ void __launch_bounds__(kStripThreads, 1)
+template <int kCols, int kNdy, int kIpr, bool kTail = false>
+__global__ void __launch_bounds__(kTail ? kStripTailThreads : kStripThreads, 1)
 cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const StripArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [ring: R slots][weights][items][column bias][barriers]
@@ -111,7 +114,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.R; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kTail ? kStripTailEpiWarps : 4); }
     mbar_init(smem_u32(&bars->wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -121,7 +124,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
-  for (int c = threadIdx.x; c < kCols; c += kStripThreads) bias_col[c] = a.bias[c & (a.n_real - 1)];
+  for (int c = threadIdx.x; c < kCols; c += blockDim.x) bias_col[c] = kTail ? 0.f : a.bias[c & (a.n_real - 1)];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -225,6 +228,55 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       un.set(a, u);
       const int x = un.x0 + m;
       const bool valid = x < a.PW;
+      if constexpr (kTail) {
+        // decoder[6] (N = 2) fused with the mask tail: columns = (ph, 8 output pixels of this strip row, re/im), i.e.
+        // each 16-column half is 8 consecutive complex64 values of output row 2j + ph.  raw -> bound_cRM
+        // (c_network.py:225) -> bound_cRM (network_functions.py:394) -> Y (.) mask -> Y - N (396-397) or Y (.) M (434).
+        static_assert(!kTail || kCols == 32, "tail epilogue expects 2 phase rows x 8 pixels x (re, im)");
+        const dcs_strip_tail& tl = a.tail;
+        const bool exact = tl.exact_polar != 0;
+        // 16 epilogue warps: warp (quad, sub) owns phase row ph = sub / 2 and output pixels 4 (sub % 2) .. +3 of each lane
+        const int sub = (warp - 2) >> 2, ph = sub >> 1, half = sub & 1;
+        for (int j = un.j0; j < un.j1; ++j) {
+          mbar_wait(smem_u32(&bars->acc_full[acc]), accp);
+          tc_fence_after();
+          const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)kCols + (uint32_t)(ph * 16 + half * 8);
+          uint32_t rg[8];
+          tc_ld8(taddr, rg);
+          tc_ld_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
+          if (valid) {
+            const int64_t o = ((int64_t)un.b * a.out_h + 2 * j + ph) * a.out_w + (int64_t)x * 8 + 4 * half;   // complex index
+            const float4* yp = reinterpret_cast<const float4*>(tl.noisy_spec) + (o >> 1);
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {      // two output pixels per 16-byte access
+              const float4 y2 = __ldg(yp + e2);
+              float2 raw[2], m1[2], m2[2], cl[2], ns[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const int c = 4 * e2 + 2 * h;
+                raw[h] = make_float2(__uint_as_float(rg[c]) + tl.bias_re, __uint_as_float(rg[c + 1]) + tl.bias_im);
+                m1[h] = bound_crm_dev(raw[h], tl.atan2_eps, exact);
+                m2[h] = bound_crm_dev(m1[h], tl.atan2_eps, exact);
+                const float2 yv = h ? make_float2(y2.z, y2.w) : make_float2(y2.x, y2.y);
+                const float2 pr = cmul(yv, m2[h]);
+                ns[h] = pr;
+                cl[h] = tl.combine == DCS_COMBINE_DCS ? make_float2(yv.x - pr.x, yv.y - pr.y) : pr;
+              }
+              const int64_t q = (o >> 1) + e2;
+              reinterpret_cast<float4*>(tl.clean_spec)[q] = make_float4(cl[0].x, cl[0].y, cl[1].x, cl[1].y);
+              if (tl.noise_spec && tl.combine == DCS_COMBINE_DCS) reinterpret_cast<float4*>(tl.noise_spec)[q] = make_float4(ns[0].x, ns[0].y, ns[1].x, ns[1].y);
+              if (tl.mask) reinterpret_cast<float4*>(tl.mask)[q] = make_float4(m2[0].x, m2[0].y, m2[1].x, m2[1].y);
+              if (tl.net_out) reinterpret_cast<float4*>(tl.net_out)[q] = make_float4(m1[0].x, m1[0].y, m1[1].x, m1[1].y);
+              if (tl.net_raw) reinterpret_cast<float4*>(tl.net_raw)[q] = make_float4(raw[0].x, raw[0].y, raw[1].x, raw[1].y);
+            }
+          }
+          if (++acc == 2) { acc = 0; accp ^= 1; }
+        }
+        continue;
+      }
       // columns are processed in chunks of kChunk = min(kCols, 32); n_real divides kChunk, so column c always maps to
       // channel (c % kChunk) % n_real and the pooling partial sums need only kChunk registers
       constexpr int kChunk = kCols < 32 ? kCols : 32;
@@ -302,7 +354,12 @@ using namespace dcs;
 static int ilog2_exact(int v) { return (v > 0 && (v & (v - 1)) == 0) ? __builtin_ctz(v) : -1; }
 
 extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
-  DCS_REQUIRE(p && p->src0 && p->dst && p->weights && p->items && p->bias, "dcs_cconv2d_strip_fwd: null pointer");
+  DCS_REQUIRE(p && p->src0 && p->weights && p->items, "dcs_cconv2d_strip_fwd: null pointer");
+  const dcs_strip_tail* tail = p->tail;
+  DCS_REQUIRE(tail ? (tail->noisy_spec && tail->clean_spec) : (p->dst && p->bias), "dcs_cconv2d_strip_fwd: null output / bias pointer");
+  DCS_REQUIRE(!tail || (p->cout == 1 && p->up_h == 2 && p->up_w == 8 && p->cols == 32 && p->out_w % 8 == 0 && !p->pool_sums),
+              "dcs_cconv2d_strip_fwd: the tail epilogue is decoder[6] only (cout 1, 2 phase rows x 8 pixels per strip row)");
+  DCS_REQUIRE(!tail || tail->combine == DCS_COMBINE_DCS || tail->combine == DCS_COMBINE_DC, "dcs_cconv2d_strip_fwd: bad combine mode");
   DCS_REQUIRE(p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->cout > 0, "dcs_cconv2d_strip_fwd: bad shape");
   DCS_REQUIRE(p->stride_w == 1 || p->stride_w == 2, "dcs_cconv2d_strip_fwd: stride_w must be 1 or 2");
   DCS_REQUIRE(p->in_w % p->stride_w == 0, "dcs_cconv2d_strip_fwd: in_w must be a multiple of stride_w");
@@ -313,7 +370,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
               "dcs_cconv2d_strip_fwd: strip rows must be 32, 64 or 128 bytes (got %d, %d)", P0, P1);
   DCS_REQUIRE(p->box_units >= kStripM && p->box_units <= 256, "dcs_cconv2d_strip_fwd: box_units must be in [128, 256]");
   const int N = 2 * p->cout;
-  DCS_REQUIRE(ilog2_exact(N) >= 3, "dcs_cconv2d_strip_fwd: 2*cout must be a power of two >= 8");
+  DCS_REQUIRE(ilog2_exact(N) >= (tail ? 1 : 3), "dcs_cconv2d_strip_fwd: 2*cout must be a power of two >= 8");
   DCS_REQUIRE(p->cols == 32 || p->cols == 64 || p->cols == 128, "dcs_cconv2d_strip_fwd: cols must be 32, 64 or 128");
   DCS_REQUIRE(N <= 32, "dcs_cconv2d_strip_fwd: 2*cout must be <= 32 (wider layers use dcs_cconv2d_tc_fwd)");
   DCS_REQUIRE(p->n_mma % 16 == 0 && p->n_mma >= 16 && p->n_mma <= p->cols, "dcs_cconv2d_strip_fwd: bad n_mma");
@@ -321,6 +378,10 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   DCS_REQUIRE(ilog2_exact(run) >= 3 && p->cols % run == 0, "dcs_cconv2d_strip_fwd: cols must be a multiple of up_w*2*cout");
   DCS_REQUIRE(((uintptr_t)p->src0 % 16 == 0) && ((uintptr_t)p->src1 % 16 == 0) && ((uintptr_t)p->weights % 16 == 0) &&
               ((uintptr_t)p->dst % 16 == 0), "dcs_cconv2d_strip_fwd: pointers must be 16-byte aligned");
+  if (tail)
+    DCS_REQUIRE(((uintptr_t)tail->noisy_spec % 16 == 0) && ((uintptr_t)tail->clean_spec % 16 == 0) && ((uintptr_t)tail->noise_spec % 16 == 0) &&
+                ((uintptr_t)tail->mask % 16 == 0) && ((uintptr_t)tail->net_out % 16 == 0) && ((uintptr_t)tail->net_raw % 16 == 0),
+                "dcs_cconv2d_strip_fwd: tail arrays must be 16-byte aligned");
 
   {  // the item table is read on the host (it is copied into the kernel parameters): refuse a device pointer
     cudaPointerAttributes at;
@@ -343,6 +404,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   a.row_bytes0 = (uint32_t)P0; a.row_bytes1 = (uint32_t)P1;
   a.n_mma = p->n_mma; a.act = p->act;
   a.bias = p->bias; a.dst = reinterpret_cast<__nv_bfloat16*>(p->dst); a.pool = p->pool_sums;
+  if (tail) a.tail = *tail;
 
   CUtensorMap tmA0, tmA1;
   const int w_units = p->in_w / p->stride_w;
@@ -388,13 +450,17 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
     a.n_units = p->batch * a.n_strips * a.n_chunks;
     const int grid = std::min(ctas, a.n_units);
 
-#define DCS_STRIP_LAUNCH(COLS, NDY, IPR)                                                                                          \
+#define DCS_STRIP_LAUNCH(...)                                                                                                     \
     do {                                                                                                                          \
-      DCS_CUDA(cudaFuncSetAttribute(cconv_strip_kernel<COLS, NDY, IPR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-      cconv_strip_kernel<COLS, NDY, IPR><<<grid, kStripThreads, smem, st>>>(tmA0, tmA1, a);                                       \
+      DCS_CUDA(cudaFuncSetAttribute(cconv_strip_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+      cconv_strip_kernel<__VA_ARGS__><<<grid, tail ? kStripTailThreads : kStripThreads, smem, st>>>(tmA0, tmA1, a);              \
     } while (0)
     // instantiated shapes (accumulator columns, ring rows per output row, MMA items per ring row)
-    if (p->cols == 32 && s.n_dy == 7 && ipr == 7) DCS_STRIP_LAUNCH(32, 7, 7);          // encoder[1]: k7 s(2,2), 1 source
+    if (tail) {
+      DCS_REQUIRE(s.n_dy == 3 && ipr == 12, "dcs_cconv2d_strip_fwd: no tail kernel instance for n_dy=%d items/row=%d", s.n_dy, ipr);
+      DCS_STRIP_LAUNCH(32, 3, 12, true);                                                // decoder[6] + mask tail, 4-pixel strip rows
+    }
+    else if (p->cols == 32 && s.n_dy == 7 && ipr == 7) DCS_STRIP_LAUNCH(32, 7, 7);     // encoder[1]: k7 s(2,2), 1 source
     else if (p->cols == 64 && s.n_dy == 3 && ipr == 12) DCS_STRIP_LAUNCH(64, 3, 12);   // decoder[5] merged phases
     else if (p->cols == 64 && s.n_dy == 2 && ipr == 32) DCS_STRIP_LAUNCH(64, 2, 32);   // decoder[4], one phase row per launch
     else if (p->cols == 64 && s.n_dy == 2 && ipr == 24) DCS_STRIP_LAUNCH(64, 2, 24);   // decoder[4] merged pw

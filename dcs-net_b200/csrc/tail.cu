@@ -20,36 +20,6 @@ constexpr int kTlRows = 4, kTlCols = 128, kTlThreads = 128;
 constexpr int kTlPitch = kTlCols + 8;  // tile col c lives at index c + 4 (16-byte aligned quads), halo at 3 and 132
 constexpr int kTlCi = 16;
 
-__device__ __forceinline__ float2 bound_crm_dev(float2 m, float eps, bool exact) {
-  if (!exact) {
-    // tanh(|m|) e^{j atan2(im, re+eps)} twice, in the algebraic form (cos(atan2(y,x)) = x/hypot(x,y)) with
-    // short-latency tanh / rsqrt: ~25 instructions instead of ~250 for the literal transcendental sequence
-    const float mag2 = m.x * m.x + m.y * m.y;
-    const float t = fast_tanh(mag2 * rsqrtf(fmaxf(mag2, 1e-37f)));
-    const float x1 = m.x + eps, q1 = x1 * x1 + m.y * m.y;
-    float r1, i1;
-    if (q1 == 0.f) { r1 = t; i1 = 0.f; } else { const float s = t * rsqrtf(q1); r1 = x1 * s; i1 = m.y * s; }
-    const float x2 = r1 + eps, q2 = x2 * x2 + i1 * i1;
-    if (q2 == 0.f) return make_float2(t, 0.f);
-    const float s2 = t * rsqrtf(q2);
-    return make_float2(x2 * s2, i1 * s2);
-  }
-  const float t = tanhf(sqrtf(m.x * m.x + m.y * m.y));
-  if (exact) {
-    const float th1 = atan2f(m.y, m.x + eps);
-    const float r1 = t * cosf(th1), i1 = t * sinf(th1);
-    const float th2 = atan2f(i1, r1 + eps);
-    return make_float2(t * cosf(th2), t * sinf(th2));
-  }
-  float x1 = m.x + eps, h1 = sqrtf(x1 * x1 + m.y * m.y);
-  float r1, i1;
-  if (h1 == 0.f) { r1 = t; i1 = 0.f; } else { const float s = t / h1; r1 = x1 * s; i1 = m.y * s; }
-  float x2 = r1 + eps, h2 = sqrtf(x2 * x2 + i1 * i1);
-  if (h2 == 0.f) return make_float2(t, 0.f);
-  const float s2 = t / h2;
-  return make_float2(x2 * s2, i1 * s2);
-}
-
 // shared-memory element: one complex activation
 template <typename T> struct SmemC;
 template <> struct SmemC<__nv_bfloat16> {

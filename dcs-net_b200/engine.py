@@ -65,6 +65,9 @@ class PackedNet:
             e0 = self.enc[0]
             if (e0.cin, e0.cout, e0.kh, e0.kw, tuple(e0.stride)) == (1, 8, 7, 7, (2, 2)) and os.environ.get("DCS_STRIP_ENC0", "1") != "0":
                 self.strip[("enc", 0)] = packing.StripEnc0(e0, device=device)
+            d6 = self.dec[Lr - 1] if Lr == 7 else None
+            if d6 is not None and (d6.cin, d6.cout, tuple(d6.up)) == (16, 1, (2, 2)) and os.environ.get("DCS_STRIP_DEC6", "1") != "0":
+                self.strip[("dec", 6)] = packing.StripDec6(d6, device=device)
             want = {("enc", 1): (8, 0, True, 1), ("dec", 4): (32, 32, False, 2), ("dec", 5): (16, 16, True, 1)}
             for (kind, i), (c0, c1, merged, groups) in want.items():
                 pc = (self.enc if kind == "enc" else self.dec)[i] if i < Lr else None
@@ -242,7 +245,14 @@ class ForwardPlan:
         d, skip = d_skip
         combine = L.COMBINE_DCS if self.variant == "dcs" else L.COMBINE_DC
         pk6 = self.pk.dec[self.pk.L - 1]
-        if pk6.w_tail is not None:
+        strip6 = self.pk.strip.get(("dec", 6)) if (self.tc and d.dtype == torch.bfloat16 and d.shape[2] % 4 == 0) else None
+        if strip6 is not None:
+            raw = self.dec[-1] if self.keep_taps else None
+            ops.dec6_tail_strip(strip6, d, skip, self.Y, self.clean_spec, net_raw=raw, net_out=self.net_out, mask=self.mask,
+                                noise_spec=self.noise_spec, atan2_eps=self.eps, combine=combine, exact_polar=self.exact)
+            if self.keep_taps:
+                self._tap(f"dec{self.pk.L - 1}", raw)
+        elif pk6.w_tail is not None:
             raw = self.dec[-1] if self.keep_taps else None
             ops.dec6_tail(pk6, d, skip, self.Y, self.clean_spec, net_raw=raw, net_out=self.net_out, mask=self.mask,
                           noise_spec=self.noise_spec, atan2_eps=self.eps, combine=combine, exact_polar=self.exact)

@@ -100,15 +100,20 @@ def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
     return dst
 
 
-def cconv_strip(sp, src0, src1, dst, pool_sums=None):
-    """Row-strip tensor-core convolution (bf16) with operands `sp` (packing.StripConv).  Same tensors as cconv()."""
-    L.require_cuda(src0, dst)
+def cconv_strip(sp, src0, src1, dst, pool_sums=None, tail=None, out_hw=None):
+    """Row-strip tensor-core convolution (bf16) with operands `sp` (packing.StripConv / StripEnc0 / StripDec6).
+    Same tensors as cconv(); with `tail` (a _lib.StripTail, decoder[6] only) dst is None and out_hw = (OH, OW)."""
+    L.require_cuda(src0)
     pk = sp.pk
     B, H, W, c0, _ = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
-    assert (c0, c1) == (sp.c0, sp.c1) and src0.dtype == torch.bfloat16 and dst.dtype == torch.bfloat16
-    _, OH, OW, co, _ = dst.shape
-    assert co == pk.cout
+    assert (c0, c1) == (sp.c0, sp.c1) and src0.dtype == torch.bfloat16
+    if tail is None:
+        assert dst.dtype == torch.bfloat16
+        _, OH, OW, co, _ = dst.shape
+        assert co == pk.cout
+    else:
+        (OH, OW), co = out_hw, pk.cout
     p = L.CstripParams()
     p.src0, p.src1, p.c0, p.c1 = L.ptr(src0), L.ptr(src1), c0, c1
     p.batch, p.in_h, p.in_w = B, H, W
@@ -124,8 +129,22 @@ def cconv_strip(sp, src0, src1, dst, pool_sums=None):
     p.box_units, p.n_mma, p.cols = sp.box_units, sp.n_mma, sp.cols
     p.bias, p.act = L.ptr(pk.bias), pk.act
     p.dst, p.pool_sums = L.ptr(dst), L.ptr(pool_sums)
+    p.tail = C.pointer(tail) if tail is not None else None
     L.check(L.lib().dcs_cconv2d_strip_fwd(C.byref(p), L.stream_ptr()), "dcs_cconv2d_strip_fwd")
     return dst
+
+
+def dec6_tail_strip(sp, d, skip, noisy_spec, clean_spec, net_raw=None, net_out=None, mask=None, noise_spec=None,
+                    atan2_eps=1e-6, combine=L.COMBINE_DCS, exact_polar=False):
+    """decoder[6] + bound_cRM x2 + combine on the tensor cores (row-strip kernel with the tail epilogue).
+    sp = packing.StripDec6; d, skip (B, h, w, 8, 2) bf16; spectrogram arrays (B, 2h, 2w) complex64."""
+    pk = sp.pk
+    B, H, W, Cn, _ = d.shape
+    assert Cn == 8 and skip.shape == d.shape and W % 4 == 0
+    tail = L.StripTail(L.ptr(noisy_spec), L.ptr(net_raw), L.ptr(net_out), L.ptr(mask), L.ptr(noise_spec), L.ptr(clean_spec),
+                       float(pk.bias_host[0]), float(pk.bias_host[1]), float(atan2_eps), combine, int(exact_polar))
+    cconv_strip(sp, sp.view_src(d), sp.view_src(skip), None, tail=tail, out_hw=(2 * H, 2 * W))
+    return clean_spec
 
 
 def conv_out_hw(pk, H, W):

@@ -303,6 +303,55 @@ class StripEnc0:
         return bn0.view(B, F, T // 8, 8, 2)
 
 
+class StripDec6:
+    """decoder[6] (ComplexConvTranspose2d 16 -> 1 after cat + (2,2) up-sampling) for dcs_cconv2d_strip_fwd with the fused
+    mask tail.  N = 2 real outputs per pixel is far below an MMA's minimum, so N is taken from SPACE: a strip row is 4
+    source pixels (128 bytes per source), a K slice is one source pixel (8 complex channels), and the accumulator
+    columns are (phase row ph, source pixel j, phase column pw, re/im) = 2 x 16: every (dy, source, pixel offset q) item
+    multiplies by a Toeplitz block with the pre-summed taps dx = q - j.  6 offsets x 2 sources x 3 rows = 36 MMAs
+    (N = 32) per 512 source pixels.  Kernel geometry: sources viewed as (B, H, W/4, 32 "channels"), up = (2, 8)."""
+
+    def __init__(self, pk, device="cpu"):
+        assert (pk.cin, pk.cout, tuple(pk.up), tuple(pk.stride)) == (16, 1, (2, 2), (1, 1))
+        self.pk, self.c0, self.c1 = pk, 32, 32
+        self.up, self.stride = (2, 8), (1, 1)
+        Wp, T = pk.w_ptnk, pk.ntaps                       # [4 phases][4 taps][n_pad][32]
+        tap = [{(pk.dy[p * T + t], pk.dx[p * T + t]): t for t in range(T)} for p in range(4)]
+        self.x_min, self.box_units, self.cols, self.n_mma = -1, STRIP_M + 2, 32, 32
+        strip_off = [0, (self.box_units * 128 + 1023) // 1024 * 1024]
+        items, blocks = [], []
+        for d_y in (-1, 0, 1):
+            for src in range(2):
+                for q in range(-1, 5):                     # source pixel offset relative to the strip row's first pixel
+                    blk = torch.zeros(32, 16, dtype=torch.float64)
+                    for j in range(4):
+                        d_x = q - j
+                        for ph in range(2):
+                            for pw in range(2):
+                                t = tap[ph * 2 + pw].get((d_y, d_x))
+                                if t is not None:
+                                    c = ph * 16 + j * 4 + pw * 2
+                                    blk[c:c + 2] = Wp[ph * 2 + pw, t, :2, src * 16:(src + 1) * 16]
+                    shift, ks = (0, 3) if q < 0 else ((2, 0) if q > 3 else (1, q))
+                    items.append(dict(a_off16=(strip_off[src] + shift * 128 + ks * 32) // 16, b_off16=len(blocks) * 32 * 32 // 16,
+                                      d_col=0, drow=d_y + 1, src=src, first=not items))
+                    blocks.append(blk)
+        w_bytes = len(blocks) * 32 * 32
+        self.groups = [dict(item0=0, n_items=len(items), dy_min=-1, n_dy=3, ph0=0, n_ph=2, x_min=self.x_min,
+                            w_bytes=w_bytes, w_off=0)]
+        self.items = items
+        self.item_table = _strip_item_table(items)
+        self.w_image = _strip_weight_image(self.groups, [blocks], 32, w_bytes).to(device)
+        self.smem_weight_bytes = w_bytes
+
+    @staticmethod
+    def view_src(x):
+        """(B, H, W, 8, 2) bf16 -> the (B, H, W/4, 32, 2) view the kernel is given (W % 4 == 0)."""
+        B, H, W = x.shape[:3]
+        assert W % 4 == 0
+        return x.view(B, H, W // 4, 32, 2)
+
+
 def pack_lstm(sd, prefix, device, hidden=64, layers=2):
     """ComplexLSTM weights (c_network.py:17-20) -> (w_ih0 [D][1024], w_ih1 [2][128][512], w_hh [2][2][2][256][64],
     bias [1024 + 2*512]) as consumed by dcs_clstm_fwd.  Column order n = lstm*512 + dir*256 + gate."""

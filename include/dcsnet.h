@@ -122,6 +122,13 @@ int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM
 #define DCS_STRIP_MAX_GROUPS 2
 typedef struct { uint32_t a_off16; uint32_t b_off16; uint16_t d_col; uint8_t drow; uint8_t flags; uint32_t reserved; } dcs_strip_item;
 typedef struct { int item0; int n_items; int dy_min; int n_dy; int ph0; int n_ph; int x_min; int w_bytes; int64_t w_off; } dcs_strip_group;
+/* optional fused tail (decoder[6] only, replaces dcs_dec6_tail_fwd on the tensor-core path): the accumulator columns are
+ * (phase row, 8 output pixels, re/im) of decoder[6]'s raw output; the epilogue adds (bias_re, bias_im) and applies
+ * bound_cRM twice, the product with Y and the subtraction exactly as dcs_mask_combine does.  dst / bias are unused. */
+typedef struct {
+  const float* noisy_spec; float* net_raw; float* net_out; float* mask; float* noise_spec; float* clean_spec;
+  float bias_re; float bias_im; float atan2_eps; int combine; int exact_polar;
+} dcs_strip_tail;
 typedef struct {
   const void* src0; const void* src1; int c0; int c1;
   int batch; int in_h; int in_w;
@@ -133,6 +140,7 @@ typedef struct {
   int box_units; int n_mma; int cols;
   const float* bias; int act;
   void* dst; float* pool_sums;
+  const dcs_strip_tail* tail;   /* NULL: bias + activation + bf16 store epilogue */
 } dcs_cstrip_params;
 int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream);
 

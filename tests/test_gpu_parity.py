@@ -223,6 +223,36 @@ def test_strip_enc0_equals_cuda_core_conv(B, F, T):
     assert rel_err(pool, ref.sum(dim=(1, 2))) <= 1.5e-2
 
 
+@pytest.mark.parametrize("B,H,W,variant", [(2, 8, 72, "dcs"), (3, 128, 500, "dcs"), (2, 16, 40, "dc")])
+def test_strip_dec6_tail_equals_cuda_core_tail(B, H, W, variant):
+    """decoder[6] + bound_cRM x2 + combine on the tensor cores (Toeplitz blocks over 4-pixel strip rows, tail epilogue)
+    vs the FFMA dec6_tail kernel on the same bf16 activations; every optional output."""
+    from dcsnet_b200 import packing, _lib as L
+    sd = SW.make_state_dict(1)
+    pk = D.PackedNet(sd, "cuda", "bf16")
+    p = pk.dec[6]
+    g = torch.Generator().manual_seed(13)
+    d = torch.randn(B, H, W, 8, 2, generator=g).cuda().bfloat16()
+    k = torch.randn(B, H, W, 8, 2, generator=g).cuda().bfloat16()
+    Y = torch.complex(torch.randn(B, 2 * H, 2 * W, generator=g), torch.randn(B, 2 * H, 2 * W, generator=g)).cuda()
+    combine = L.COMBINE_DCS if variant == "dcs" else L.COMBINE_DC
+    new = lambda: torch.full((B, 2 * H, 2 * W), float("nan"), dtype=torch.complex64, device="cuda")
+    ref = {n: new() for n in ("clean", "raw", "net", "mask", "noise")}
+    got = {n: new() for n in ("clean", "raw", "net", "mask", "noise")}
+    ops.dec6_tail(p, d, k, Y, ref["clean"], net_raw=ref["raw"], net_out=ref["net"], mask=ref["mask"], noise_spec=ref["noise"],
+                  combine=combine)
+    sp = packing.StripDec6(p, device="cuda")
+    ops.dec6_tail_strip(sp, d, k, Y, got["clean"], net_raw=got["raw"], net_out=got["net"], mask=got["mask"],
+                        noise_spec=got["noise"], combine=combine)
+    torch.cuda.synchronize()
+    for n in ref:
+        if n == "noise" and variant == "dc":
+            continue
+        assert not torch.isnan(torch.view_as_real(got[n])).any(), n
+        # the strip kernel multiplies bf16 weights (the FFMA tail fp32 ones); the phase of near-zero raw values is unstable
+        assert rel_err(got[n], ref[n]) <= (1.5e-2 if n == "raw" else 3e-2), n
+
+
 @pytest.mark.parametrize("C,H,W", [(128, 2, 70), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 75), (8, 128, 130)])
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_fused_attention_equals_separate_kernels(C, H, W, dtype):

@@ -139,3 +139,18 @@ def test_strip_enc0_toeplitz_packing(packed):
     got = strip_geometry(sp, packing.StripEnc0.view_src(x), None, out_hw)
     assert not torch.isnan(got).any()
     assert rel_err(got, ref) <= 1e-2
+
+
+def test_strip_dec6_toeplitz_packing(packed):
+    """decoder[6] on the row-strip kernel: N taken from space (4-pixel strip rows, Toeplitz blocks of pre-summed taps)."""
+    _, pk = packed
+    p = pk.dec[6]
+    g = torch.Generator().manual_seed(4)
+    B, H, W = 2, 3, 136                     # W/4 = 34 strip rows
+    d = torch.randn(B, H, W, 8, 2, generator=g).to(torch.bfloat16).float()
+    k = torch.randn(B, H, W, 8, 2, generator=g).to(torch.bfloat16).float()
+    sp = packing.StripDec6(p)
+    ref = conv_geometry(p, d, k, (2 * H, 2 * W))
+    got = strip_geometry(sp, sp.view_src(d), sp.view_src(k), (2 * H, 2 * W))
+    assert not torch.isnan(got).any()
+    assert rel_err(got, ref) <= 1e-2
