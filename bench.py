@@ -250,6 +250,37 @@ def run_ours(args, rank, local_rank, world):
         dist.destroy_process_group()
 
 
+def ncu_family_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the tensor-core conv family, from the newest committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py); the LSTM input-projection launches (cconv_tc_kernel
+    between lstm_deinterleave and lstm_combine) are not part of the family.  None when no summary is committed."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")))
+    if not files:
+        return None, None
+    rows = list(csv.reader(open(files[-1])))
+    hdr = rows[0]
+    try:
+        ir = next(i for i, h in enumerate(hdr) if h.startswith("dram_read_MB"))
+        iw = next(i for i, h in enumerate(hdr) if h.startswith("dram_write_MB"))
+    except StopIteration:
+        return None, None
+    scale = 1e6 if "Mbyte" in hdr[ir] else (1e9 if "Gbyte" in hdr[ir] else (1e3 if "Kbyte" in hdr[ir] else 1.0))
+    in_lstm, vals = False, []
+    for r in rows[1:]:
+        k = r[1]
+        if "lstm_deinterleave" in k:
+            in_lstm = True
+        elif "lstm_combine" in k:
+            in_lstm = False
+        elif ("cconv_tc_kernel" in k and not in_lstm) or "cconv_strip_kernel" in k:
+            vals.append((float(r[ir]) + float(r[iw])) * scale)
+    if not vals:
+        return None, None
+    return sum(vals) / len(vals), os.path.relpath(files[-1], ROOT)
+
+
 def measure_roofline(plan, args, B, T):
     """Eager (un-graphed) instrumented passes: CUDA events around every kernel family on the launching stream."""
     from dcsnet_b200 import ops
@@ -258,8 +289,10 @@ def measure_roofline(plan, args, B, T):
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
+    from dcsnet_b200 import _lib as L
     acc = {}
     orig = {}
+    nlaunch = {}
 
     def wrap(name, key_fn):
         fn = getattr(ops, name)
@@ -267,10 +300,13 @@ def measure_roofline(plan, args, B, T):
 
         def inner(*a, **k):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = L.launch_count()
             e0.record()
             r = fn(*a, **k)
             e1.record()
-            acc.setdefault(key_fn(*a, **k), []).append((e0, e1))
+            key = key_fn(*a, **k)
+            acc.setdefault(key, []).append((e0, e1))
+            nlaunch[key] = nlaunch.get(key, 0) + L.launch_count() - n0
             return r
         setattr(ops, name, inner)
 
@@ -283,6 +319,7 @@ def measure_roofline(plan, args, B, T):
         plan._enqueue_from_audio()
         torch.cuda.synchronize()
         acc.clear()
+        nlaunch.clear()
         for _ in range(steps):
             plan._enqueue_from_audio()
         torch.cuda.synchronize()
@@ -290,25 +327,38 @@ def measure_roofline(plan, args, B, T):
         for n, fn in orig.items():
             setattr(ops, n, fn)
     stage_ms = {k: sum(a.elapsed_time(b) for a, b in v) / steps for k, v in acc.items()}
+    launches = {k: nlaunch.get(k, 0) // steps for k in acc}   # kernel launches (dcs_launch_count), not op calls
     fl = conv_flops_per_utterance(T)
-    tc_layers = [k for k in fl if k not in ("enc0", "dec6")] if args.mode == "bf16" else []
-    n_tc = (len(acc.get("conv_tc", [])) + len(acc.get("conv_strip", []))) // steps
+    hbm = peaks.get("hbm_gbs")
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (copy bandwidth)"
+    if not hbm:
+        hbm, hbm_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
     roof = None
-    if args.mode == "bf16" and n_tc:
-        flops = B * sum(fl[k] for k in tc_layers)
-        t_ms = stage_ms.get("conv_tc", 0.0) + stage_ms.get("conv_strip", 0.0)
-        t = t_ms / 1e3
+    # ---- tensor-core convolution family (the only dense contractions of the path)
+    tc_keys = [k for k in ("conv_tc", "conv_strip") if k in stage_ms]
+    if args.mode == "bf16" and tc_keys:
+        # every conv layer runs on tcgen05 in this mode when enc0 / dec6 are on the strip kernel; otherwise they are
+        # CUDA-core kernels ("enc0", "dec6_tail" stages) and their FLOPs are excluded
+        layers = [k for k in fl if not ((k == "enc0" and "enc0" in stage_ms) or (k == "dec6" and "dec6_tail" in stage_ms))]
+        flops = B * sum(fl[k] for k in layers)
+        t_ms = sum(stage_ms[k] for k in tc_keys)
+        n_tc = sum(launches[k] for k in tc_keys)
         peak = peaks.get("bf16_tflops_sustained")
-        which = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+        which = "MEASURED_PEAKS.json bf16_tflops_sustained (kernels timed inside a long step)"
         if not peak:
             peak, which = 1590.0, "fallback 1.59 PFLOP/s (B200_PROFILING.md)"
-        ach = flops / t / 1e12
-        roof = {"bound": "tensor", "kernel": "tcgen05 implicit-GEMM complex convs: dcs::cconv_tc_kernel (enc2..enc6, dec0..dec3 bf16, fc tf32) + "
-                                             "dcs::cconv_strip_kernel (enc1, dec4, dec5 bf16)",
-                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
-                "peak_source": which,
-                "algorithmic_flops_per_step": flops, "avg_launch_ms": t_ms / n_tc, "launches_per_step": n_tc,
-                "note": "reference dense formulation FLOPs (SURVEY Appendix C); executed FLOPs are 1.5x/2.25x lower in the decoder (pre-summed sub-pixel taps)"}
+        ach = flops / (t_ms / 1e3) / 1e12
+        traffic, traffic_src = ncu_family_traffic()
+        roof = {"bound": "tensor",
+                "kernel": "tcgen05 implicit-GEMM complex convs: dcs::cconv_tc_kernel (enc2..enc6, dec0..dec3 bf16; fc + LSTM input projections "
+                          "tf32) + dcs::cconv_strip_kernel (enc0, enc1, dec4, dec5, dec6+mask tail bf16)",
+                "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_unit": "bytes per launch (dram read + write, ncu)",
+                "traffic_source": traffic_src, "peak_source": which,
+                "algorithmic_flops_per_step": flops, "layers": layers, "avg_launch_ms": t_ms / n_tc, "launches_per_step": n_tc,
+                "note": "algorithmic FLOPs = the reference's dense formulation (SURVEY Appendix C: 4 real MACs per complex MAC, every tap "
+                        "of the up-sampled input); the kernels execute 1.5x / 2.25x fewer in the decoder (pre-summed sub-pixel taps) and "
+                        "more in enc0 / dec6 (Toeplitz blocks).  The fc and LSTM-projection launches are inside the time but add no FLOPs "
+                        "to the numerator."}
     elif args.mode == "fp32":
         flops = B * sum(fl.values())
         t = stage_ms.get("conv_ffma", 0.0) / 1e3
@@ -316,6 +366,31 @@ def measure_roofline(plan, args, B, T):
         roof = {"bound": "tensor", "kernel": "dcs::cconv_ffma_kernel (fp32 CUDA-core mode; no tensor-core roofline applies)",
                 "achieved": ach, "peak": peaks.get("bf16_tflops_sustained", 1590.0), "unit": "TFLOP/s",
                 "frac": ach / peaks.get("bf16_tflops_sustained", 1590.0), "traffic": None}
+    # ---- bandwidth-bound stages: algorithmic bytes (each tensor moved once) / measured stage time
+    esz = 2 if args.mode == "bf16" else 4
+    att = [t for t in plan.enc] + [t for t in plan.dec[:-1]]
+    att_bytes = sum(t.numel() * t.element_size() for t in att)          # every attended tensor once
+    stage_bytes = {
+        "stft": B * (4 * 32 * (T - 1) + 8 * 256 * T) + (B * 256 * T * 2 * esz if "enc0" not in stage_ms else 0),
+        "istft": B * (8 * 256 * T + 4 * 32 * (T - 1)),
+        "spat_stats": att_bytes + sum(t.shape[0] * t.shape[1] * t.shape[2] * 16 for t in att),
+        "spat_apply": 2 * att_bytes + sum(t.shape[0] * t.shape[1] * t.shape[2] * 16 for t in att),
+        "attention_fused": 2 * att_bytes,
+        "dec6_tail": B * (2 * 128 * (T // 2) * 16 * esz + 2 * 8 * 256 * T),
+        "enc0": B * (8 * 256 * T + 128 * (T // 2) * 16 * esz),
+    }
+    stages = []
+    for k, nbytes in stage_bytes.items():
+        if k in stage_ms and stage_ms[k] > 0:
+            gbs = nbytes / (stage_ms[k] / 1e3) / 1e9
+            stages.append({"stage": k, "bound": "hbm", "ms": stage_ms[k], "launches": launches[k], "algorithmic_bytes": nbytes,
+                           "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm})
+    if "clstm" in stage_ms:
+        stages.append({"stage": "clstm", "bound": "latency (2 x S sequential recurrent steps; reported against neither roof)",
+                       "ms": stage_ms["clstm"], "launches": None, "steps": 2 * 2 * (T // 8)})
+    if roof is not None:
+        roof["stages"] = stages
+        roof["hbm_peak_source"] = hbm_src
     return roof, stage_ms
 
 

@@ -83,7 +83,8 @@ class ChanGateParams(C.Structure):
 
 class SpatStatsParams(C.Structure):
     _fields_ = [("x", _vp), ("chan_gate", _vp), ("stats", _vp), ("batch", _i), ("h", _i), ("w", _i),
-                ("channels", _i), ("dtype", _i)]
+                ("channels", _i), ("dtype", _i),
+                ("sums", _vp), ("reduced", _i), ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp), ("gate_out", _vp)]
 
 
 class SpatApplyParams(C.Structure):

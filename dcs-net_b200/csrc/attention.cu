@@ -9,6 +9,7 @@
 //   2. chan_gate : g_c[b][c]   = sigmoid_c(2 W2 crelu(W1 avg)) (tiny)                  on the tcgen05 path]
 //   3. spat_stats: st[b][h][w] = {mean_c(g_c x), max_c Re, max_c Im}   (read x once, write 16 B / pixel)
 //   4. spat_apply: y = sigmoid_c(conv7x7(st)) * (g_c x)                (read x once, write y once)
+#include <string.h>
 #include "common.cuh"
 
 namespace dcs {
@@ -105,15 +106,55 @@ __global__ void __launch_bounds__(128) chan_gate_kernel(const dcs_chan_gate_para
 }
 
 // ---------------------------------------------------------------- 3. per-pixel channel statistics of u = g_c * x
+struct GateMlp {   // optional fused ComplexChannelAttention MLP (dcs_chan_gate) in the statistics kernel
+  const float* sums; float inv_hw; int reduced;
+  const float *w1_r, *w1_i, *w2_r, *w2_i;
+  float* gate_out;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x, const float* __restrict__ gate,
-                                                         float4* __restrict__ stats, int hw, int C, int G) {
+                                                         float4* __restrict__ stats, int hw, int C, int G, const GateMlp mlp) {
   // G lanes cooperate on one pixel; each lane strides over the channels in 16-byte vectors (G = min(32, C / VEC))
   constexpr int V = Vec16<T>::N;
   __shared__ float2 gs[256];
+  __shared__ float2 avg[256];
+  __shared__ float2 hid[16];
   const int b = blockIdx.y;
-  for (int c = threadIdx.x; c < C; c += blockDim.x)
-    gs[c] = gate ? reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c] : make_float2(1.f, 0.f);
+  if (mlp.sums) {
+    // gate = sigmoid_c(2 W2 crelu(W1 avg)) recomputed by every CTA of the image (C*R complex MACs); CTA 0 publishes it
+    const int R = mlp.reduced;
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      avg[c] = make_float2(mlp.sums[((int64_t)b * C + c) * 2] * mlp.inv_hw, mlp.sums[((int64_t)b * C + c) * 2 + 1] * mlp.inv_hw);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int r = warp; r < R; r += 8) {
+      float re = 0.f, im = 0.f;
+      for (int c = lane; c < C; c += 32) {
+        const float wr = mlp.w1_r[r * C + c], wi = mlp.w1_i[r * C + c];
+        re += wr * avg[c].x - wi * avg[c].y;
+        im += wr * avg[c].y + wi * avg[c].x;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+      if (lane == 0) hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float re = 0.f, im = 0.f;
+      for (int r = 0; r < R; ++r) {
+        const float wr = mlp.w2_r[c * R + r], wi = mlp.w2_i[c * R + r];
+        re += wr * hid[r].x - wi * hid[r].y;
+        im += wr * hid[r].y + wi * hid[r].x;
+      }
+      const float2 gv = make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
+      gs[c] = gv;
+      if (blockIdx.x == 0 && mlp.gate_out) reinterpret_cast<float2*>(mlp.gate_out)[(int64_t)b * C + c] = gv;
+    }
+  } else {
+    for (int c = threadIdx.x; c < C; c += blockDim.x)
+      gs[c] = gate ? reinterpret_cast<const float2*>(gate)[(int64_t)b * C + c] : make_float2(1.f, 0.f);
+  }
   __syncthreads();
   const int sub = threadIdx.x % G, grp = threadIdx.x / G, groups = 256 / G;
   const T* xb = x + (int64_t)b * hw * C * 2;
@@ -474,8 +515,15 @@ extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
   ctas = min(ctas, max(1, 16 * num_sms() / p->batch));
   dim3 grid(ctas, p->batch);
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->dtype == DCS_BF16) spat_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G);
-  else spat_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G);
+  GateMlp mlp;
+  memset(&mlp, 0, sizeof(mlp));
+  if (p->sums) {
+    DCS_REQUIRE(p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->reduced > 0 && p->reduced <= 16, "dcs_spat_stats: incomplete gate MLP operands");
+    mlp.sums = p->sums; mlp.inv_hw = 1.f / (float)hw; mlp.reduced = p->reduced;
+    mlp.w1_r = p->w1_r; mlp.w1_i = p->w1_i; mlp.w2_r = p->w2_r; mlp.w2_i = p->w2_i; mlp.gate_out = p->gate_out;
+  }
+  if (p->dtype == DCS_BF16) spat_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G, mlp);
+  else spat_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G, mlp);
   DCS_LAUNCHED();
   return 0;
 }

@@ -165,8 +165,7 @@ class ForwardPlan:
             ops.chan_pool(x, sums)
         if self.fused_attention and Cn >= 4:
             return ops.attention_fused(x, sums, ca, sa_w7, y)
-        ops.chan_gate(sums, H * W, ca, gate)
-        ops.spat_stats(x, gate, stats)
+        ops.spat_stats(x, None, stats, sums=sums, ca=ca, gate_out=gate)   # channel-gate MLP fused into the statistics pass
         ops.spat_apply(x, gate, stats, sa_w7, y)
         return y
 
@@ -200,6 +199,17 @@ class ForwardPlan:
         if self.fuse_pool:
             self.pool_all.zero_()
         enc_pooled = [False] * Lr
+
+        def skip_attention(i):
+            e = Lr - 1 - i
+            return self._attention(self.enc[e], pk.skip_ca[i], pk.skip_sa[i], self.skip[i],
+                                   sums=self.pool_enc[e] if enc_pooled[e] else None)
+
+        # A skip attention depends only on its encoder output: run it right behind the producing conv while that tensor is
+        # still in the 126 MB L2 (tensors that fit), instead of re-reading it from HBM in the decoder loop.
+        mode = os.environ.get("DCS_EARLY_SKIP", "auto")
+        limit = {"0": -1, "1": 1 << 62}.get(mode, 80 << 20)
+        early = lambda e: (not self.overlap) and self.enc[e].numel() * self.enc[e].element_size() <= limit
         for i in range(Lr):
             if i == 0 and strip0 is not None:
                 x = ops.cconv_strip(strip0, packing.StripEnc0.view_src(self.bn0), None, self.enc[0],
@@ -210,12 +220,9 @@ class ForwardPlan:
             else:
                 x, enc_pooled[i] = self._conv(pk.enc[i], x, None, self.enc[i], self.pool_enc[i], pk.strip.get(("enc", i)))
             self._tap(f"enc{i}", x)
+            if early(i):
+                skip_attention(Lr - 1 - i)
         B, H, W, _, _ = x.shape
-
-        def skip_attention(i):
-            e = Lr - 1 - i
-            return self._attention(self.enc[e], pk.skip_ca[i], pk.skip_sa[i], self.skip[i],
-                                   sums=self.pool_enc[e] if enc_pooled[e] else None)
 
         main = torch.cuda.current_stream()
         if self.overlap:
@@ -232,7 +239,7 @@ class ForwardPlan:
         if self.overlap:
             main.wait_stream(self.side)
         for i in range(Lr):
-            skip = self.skip[i] if self.overlap else skip_attention(i)
+            skip = self.skip[i] if (self.overlap or early(Lr - 1 - i)) else skip_attention(i)
             self._tap(f"skip{i}", skip)
             if i == Lr - 1:
                 return d, skip  # decoder[6] is fused with the mask tail (dcs_dec6_tail_fwd)

@@ -166,9 +166,15 @@ def chan_gate(sums, hw, ca, gate):
     L.check(L.lib().dcs_chan_gate(C.byref(p), L.stream_ptr()), "dcs_chan_gate")
 
 
-def spat_stats(x, gate, stats):
+def spat_stats(x, gate, stats, sums=None, ca=None, gate_out=None):
+    """Per-pixel channel statistics of gate * x.  With sums + ca (pack_channel_attention) the channel-gate MLP runs
+    inside the kernel (no dcs_chan_gate launch) and the gate is written to gate_out for dcs_spat_apply."""
     B, H, W, Cn, _ = x.shape
-    p = L.SpatStatsParams(L.ptr(x), L.ptr(gate), L.ptr(stats), B, H, W, Cn, _code(x))
+    if sums is not None:
+        p = L.SpatStatsParams(L.ptr(x), None, L.ptr(stats), B, H, W, Cn, _code(x), L.ptr(sums), ca["reduced"],
+                              L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(gate_out))
+    else:
+        p = L.SpatStatsParams(L.ptr(x), L.ptr(gate), L.ptr(stats), B, H, W, Cn, _code(x), None, 0, None, None, None, None, None)
     L.check(L.lib().dcs_spat_stats(C.byref(p), L.stream_ptr()), "dcs_spat_stats")
 
 

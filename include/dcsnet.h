@@ -164,6 +164,9 @@ int dcs_chan_gate(const dcs_chan_gate_params* p, void* stream);
  *      w7: fp32 [2 (r,i)][2 (in ch: mean,max)][7][7]  = conv1.conv_r.weight, conv1.conv_i.weight. */
 typedef struct {
   const void* x; const float* chan_gate; float* stats; int batch; int h; int w; int channels; int dtype;
+  /* optional fused dcs_chan_gate: when sums != NULL the kernel computes the channel gate itself from the pooled sums
+   * (sum over H*W of x) and the fc weights, ignores chan_gate, and writes the gate to gate_out (B, C) complex. */
+  const float* sums; int reduced; const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; float* gate_out;
 } dcs_spat_stats_params;
 int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream);
 typedef struct {
