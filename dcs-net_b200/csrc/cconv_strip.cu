@@ -32,9 +32,9 @@ namespace dcs {
 int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_units, int h, int b, int box_units);
 
 constexpr int kStripM = 128;
-constexpr int kStripThreads = 192;        // warp 0 TMA, warp 1 MMA, 4 epilogue warps
-constexpr int kStripTailEpiWarps = 16;    // the tail epilogue is transcendental-heavy: 4 warps per TMEM lane quadrant
-constexpr int kStripTailThreads = 64 + 32 * kStripTailEpiWarps;
+// threads = warp 0 TMA + warp 1 MMA + kEpi epilogue warps (4, 8 or 16: kEpi / 4 warps per TMEM lane quadrant, which split the
+// accumulator's 32-column chunks; the tail epilogue is transcendental-heavy and always uses 16)
+constexpr int strip_threads(int epi_warps) { return 64 + 32 * epi_warps; }
 constexpr int kStripMaxRing = 16;
 constexpr int kStripMaxItems = 64;    // MMA items of one phase group; the table travels in the kernel parameters
 
@@ -98,8 +98,8 @@ struct UnitIter {  // unit u of a phase group -> (image, column strip, row chunk
   }
 };
 
-template <int kCols, int kNdy, int kIpr, bool kTail = false>
-__global__ void __launch_bounds__(kTail ? kStripTailThreads : kStripThreads, 1)
+template <int kCols, int kNdy, int kIpr, int kEpi = 4, bool kTail = false>
+__global__ void __launch_bounds__(strip_threads(kEpi), 1)
 cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const StripArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [ring: R slots][weights][items][column bias][barriers]
@@ -114,7 +114,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.R; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kTail ? kStripTailEpiWarps : 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kEpi); }
     mbar_init(smem_u32(&bars->wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -236,7 +236,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const dcs_strip_tail& tl = a.tail;
         const bool exact = tl.exact_polar != 0;
         // 16 epilogue warps: warp (quad, sub) owns phase row ph = sub / 2 and output pixels 4 (sub % 2) .. +3 of each lane
-        const int sub = (warp - 2) >> 2, ph = sub >> 1, half = sub & 1;
+        const int tsub = (warp - 2) >> 2, ph = tsub >> 1, half = tsub & 1;
         for (int j = un.j0; j < un.j1; ++j) {
           mbar_wait(smem_u32(&bars->acc_full[acc]), accp);
           tc_fence_after();
@@ -280,6 +280,9 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       // columns are processed in chunks of kChunk = min(kCols, 32); n_real divides kChunk, so column c always maps to
       // channel (c % kChunk) % n_real and the pooling partial sums need only kChunk registers
       constexpr int kChunk = kCols < 32 ? kCols : 32;
+      constexpr int kSub = kEpi / 4;                      // warps per quadrant; warp `sub` owns chunks sub, sub + kSub, ...
+      static_assert(kTail || (kCols / kChunk) % kSub == 0, "chunks must divide evenly among the warps of a quadrant");
+      const int sub = (warp - 2) >> 2;
       float pool_acc[kChunk];
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) pool_acc[c] = 0.f;
@@ -289,12 +292,13 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)kCols;
         const int64_t row0 = ((int64_t)un.b * a.out_h + (int64_t)j * a.up_h + G.ph0) * a.out_w + (int64_t)x * a.up_w;
 #pragma unroll
-        for (int ch = 0; ch < kCols / kChunk; ++ch) {
+        for (int cq = 0; cq < kCols / kChunk / kSub; ++cq) {
+          const int ch = sub + cq * kSub;
           uint32_t rg[kChunk / 16][16];
 #pragma unroll
           for (int cb = 0; cb < kChunk / 16; ++cb) tc_ld16(taddr + (uint32_t)(ch * kChunk + 16 * cb), rg[cb]);
           tc_ld_wait();
-          if (ch == kCols / kChunk - 1) {   // the whole accumulator has been read: release it to the MMA warp
+          if (cq == kCols / kChunk / kSub - 1) {   // this warp's share of the accumulator has been read: release it
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
@@ -325,7 +329,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       }
       if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
         if constexpr (kChunk == 32) {
-          const float sum = transpose_reduce32(pool_acc, lane);
+          const float sum = transpose_reduce32(pool_acc, lane);   // pool_acc[c] sums columns c, c + 32 kSub, ... of this warp
           atomicAdd(a.pool + (int64_t)un.b * a.n_real + (lane & (a.n_real - 1)), sum);
         } else {
 #pragma unroll
@@ -450,21 +454,23 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
     a.n_units = p->batch * a.n_strips * a.n_chunks;
     const int grid = std::min(ctas, a.n_units);
 
+    int threads = strip_threads(4);
 #define DCS_STRIP_LAUNCH(...)                                                                                                     \
     do {                                                                                                                          \
       DCS_CUDA(cudaFuncSetAttribute(cconv_strip_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
-      cconv_strip_kernel<__VA_ARGS__><<<grid, tail ? kStripTailThreads : kStripThreads, smem, st>>>(tmA0, tmA1, a);              \
+      cconv_strip_kernel<__VA_ARGS__><<<grid, threads, smem, st>>>(tmA0, tmA1, a);                                                \
     } while (0)
     // instantiated shapes (accumulator columns, ring rows per output row, MMA items per ring row)
     if (tail) {
       DCS_REQUIRE(s.n_dy == 3 && ipr == 12, "dcs_cconv2d_strip_fwd: no tail kernel instance for n_dy=%d items/row=%d", s.n_dy, ipr);
-      DCS_STRIP_LAUNCH(32, 3, 12, true);                                                // decoder[6] + mask tail, 4-pixel strip rows
+      threads = strip_threads(16);
+      DCS_STRIP_LAUNCH(32, 3, 12, 16, true);                                            // decoder[6] + mask tail, 4-pixel strip rows
     }
     else if (p->cols == 32 && s.n_dy == 7 && ipr == 7) DCS_STRIP_LAUNCH(32, 7, 7);     // encoder[1]: k7 s(2,2), 1 source
-    else if (p->cols == 64 && s.n_dy == 3 && ipr == 12) DCS_STRIP_LAUNCH(64, 3, 12);   // decoder[5] merged phases
-    else if (p->cols == 64 && s.n_dy == 2 && ipr == 32) DCS_STRIP_LAUNCH(64, 2, 32);   // decoder[4], one phase row per launch
-    else if (p->cols == 64 && s.n_dy == 2 && ipr == 24) DCS_STRIP_LAUNCH(64, 2, 24);   // decoder[4] merged pw
-    else if (p->cols == 128 && s.n_dy == 7 && ipr == 4) DCS_STRIP_LAUNCH(128, 7, 4);   // encoder[0]: Toeplitz blocks, 16-pixel strip rows
+    else if (p->cols == 64 && s.n_dy == 3 && ipr == 12) { threads = strip_threads(8); DCS_STRIP_LAUNCH(64, 3, 12, 8); }   // decoder[5] merged phases
+    else if (p->cols == 64 && s.n_dy == 2 && ipr == 32) { threads = strip_threads(8); DCS_STRIP_LAUNCH(64, 2, 32, 8); }   // decoder[4], one phase row per launch
+    else if (p->cols == 64 && s.n_dy == 2 && ipr == 24) { threads = strip_threads(8); DCS_STRIP_LAUNCH(64, 2, 24, 8); }   // decoder[4] merged pw
+    else if (p->cols == 128 && s.n_dy == 7 && ipr == 4) { threads = strip_threads(16); DCS_STRIP_LAUNCH(128, 7, 4, 16); } // encoder[0]: Toeplitz blocks
     else DCS_REQUIRE(false, "dcs_cconv2d_strip_fwd: no kernel instance for cols=%d n_dy=%d items/row=%d", p->cols, s.n_dy, ipr);
 #undef DCS_STRIP_LAUNCH
     DCS_LAUNCHED();
