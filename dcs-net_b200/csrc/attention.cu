@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x
 }
 
 // ---------------------------------------------------------------- 4. 7x7 complex conv on the stats, sigmoid, apply
-constexpr int kSaTW = 64, kSaK = 7, kSaR = 3;  // tile = kSaTH x 64 pixels, kSaTH in {4, 16} (template)
+constexpr int kSaK = 7, kSaR = 3;  // tile = kSaTH x kSaTW pixels, kSaTH in {4, 16}, kSaTW in {16, 64} (template)
 
-template <typename TI, typename TO, int kSaTH>
+template <typename TI, typename TO, int kSaTH, int kSaTW>
 __global__ void __launch_bounds__(256) spat_apply_kernel(const TI* __restrict__ x, const float* __restrict__ gate,
                                                          const float4* __restrict__ stats, const float* __restrict__ w7,
                                                          TO* __restrict__ y, float2* __restrict__ gate_out, int H, int W, int C) {
@@ -534,18 +534,26 @@ extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
   DCS_REQUIRE(p->batch <= 65535, "dcs_spat_apply: batch too large for grid.z");
   DCS_REQUIRE(pow2(p->channels) && p->channels >= 4, "dcs_spat_apply: channels must be a power of two >= 4");
   const int th = p->h >= 16 ? 16 : 4;
-  dim3 grid((p->w + kSaTW - 1) / kSaTW, (p->h + th - 1) / th, p->batch);
+  // 64-pixel-wide tiles; wide-channel tensors have few pixels, so narrow 16-pixel tiles keep >= ~4 CTAs per SM busy
+  const int64_t ctas64 = (int64_t)((p->w + 63) / 64) * ((p->h + th - 1) / th) * p->batch;
+  const int tw = ctas64 < 4 * num_sms() ? 16 : 64;
+  dim3 grid((p->w + tw - 1) / tw, (p->h + th - 1) / th, p->batch);
   cudaStream_t s = (cudaStream_t)stream;
   const float4* st = (const float4*)p->stats;
-#define DCS_SA(TI, TO)                                                                                                             \
-  do {                                                                                                                             \
-    if (th == 16) spat_apply_kernel<TI, TO, 16><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels); \
-    else spat_apply_kernel<TI, TO, 4><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels);        \
+#define DCS_SA_T(TI, TO, TH, TW) \
+  spat_apply_kernel<TI, TO, TH, TW><<<grid, 256, 0, s>>>((const TI*)p->x, p->chan_gate, st, p->w7, (TO*)p->y, (float2*)p->gate_out, p->h, p->w, p->channels)
+#define DCS_SA(TI, TO)                                          \
+  do {                                                          \
+    if (th == 16 && tw == 64) DCS_SA_T(TI, TO, 16, 64);         \
+    else if (th == 16) DCS_SA_T(TI, TO, 16, 16);                \
+    else if (tw == 64) DCS_SA_T(TI, TO, 4, 64);                 \
+    else DCS_SA_T(TI, TO, 4, 16);                               \
   } while (0)
   if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_SA(float, float);
   else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_SA(float, __nv_bfloat16);
   else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_SA(__nv_bfloat16, float);
   else DCS_SA(__nv_bfloat16, __nv_bfloat16);
+#undef DCS_SA_T
 #undef DCS_SA
   DCS_LAUNCHED();
   return 0;

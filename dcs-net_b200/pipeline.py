@@ -64,6 +64,7 @@ class Enhancer:
         self.host_out = torch.empty(batch, n_samples, dtype=torch.float32, pin_memory=True)
         self.h2d_bytes = self.host_in.numel() * 4
         self.d2h_bytes = self.host_out.numel() * 4
+        self._stream_state = None
 
     def enhance_device(self, audio_dev=None):
         """Device-resident path: audio (batch, n_samples) on the GPU (or already in plan.audio_in) -> device tensor."""
@@ -75,6 +76,56 @@ class Enhancer:
         self.plan.enhance_audio()
         self.host_out.copy_(self.plan.audio_out, non_blocking=True)
         return self.host_out
+
+    # ------------------------------------------------------------------ streaming (copy / compute overlap)
+    def _streaming(self):
+        if self._stream_state is None:
+            with torch.cuda.device(self.device):
+                st = dict(
+                    h2d=torch.cuda.Stream(), d2h=torch.cuda.Stream(), i=0,
+                    dev_in=[torch.empty_like(self.plan.audio_in) for _ in range(2)],
+                    dev_out=[torch.empty_like(self.plan.audio_out) for _ in range(2)],
+                    in_ready=[torch.cuda.Event() for _ in range(2)], in_free=[torch.cuda.Event() for _ in range(2)],
+                    out_ready=[torch.cuda.Event() for _ in range(2)], out_free=[torch.cuda.Event() for _ in range(2)])
+                cur = torch.cuda.current_stream()
+                for k in range(2):
+                    st["in_free"][k].record(cur)
+                    st["out_free"][k].record(cur)
+            self._stream_state = st
+        return self._stream_state
+
+    def enhance_pinned_stream(self):
+        """Streaming variant of enhance_pinned(): the H2D copy of this call and the D2H copy of the previous one run on
+        their own streams through double-buffered device staging, so in steady state a step costs max(compute, copies).
+        host_in is read asynchronously and host_out holds the result of this call only after drain()."""
+        st = self._streaming()
+        k = st["i"] & 1
+        st["i"] += 1
+        cur = torch.cuda.current_stream()
+        with torch.cuda.stream(st["h2d"]):
+            st["h2d"].wait_event(st["in_free"][k])              # the step that last read this staging buffer has consumed it
+            st["dev_in"][k].copy_(self.host_in, non_blocking=True)
+            st["in_ready"][k].record(st["h2d"])
+        cur.wait_event(st["in_ready"][k])
+        self.plan.audio_in.copy_(st["dev_in"][k], non_blocking=True)
+        st["in_free"][k].record(cur)
+        self.plan.enhance_audio()
+        cur.wait_event(st["out_free"][k])
+        st["dev_out"][k].copy_(self.plan.audio_out, non_blocking=True)
+        st["out_ready"][k].record(cur)
+        with torch.cuda.stream(st["d2h"]):
+            st["d2h"].wait_event(st["out_ready"][k])
+            self.host_out.copy_(st["dev_out"][k], non_blocking=True)
+            st["out_free"][k].record(st["d2h"])
+        return self.host_out
+
+    def drain(self):
+        """Make the current stream wait for every copy issued by enhance_pinned_stream()."""
+        if self._stream_state is not None:
+            cur = torch.cuda.current_stream()
+            for k in range(2):   # waiting on a never-recorded event is a no-op
+                cur.wait_event(self._stream_state["out_free"][k])
+                cur.wait_event(self._stream_state["in_ready"][k])
 
     def __call__(self, noisy_audio):
         """noisy_audio: (n, n_samples) CPU or CUDA float32, n <= batch.  Returns enhanced audio on the same device."""

@@ -364,3 +364,28 @@ def test_enhancer_public_api_and_graph():
     got = enh.enhance_long(long)
     assert got.shape == long.shape
     assert rel_err(got[:16320], ref[:2].reshape(-1)) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_enhancer_streaming_matches_serial():
+    """enhance_pinned_stream (copies on their own streams, double-buffered staging) returns what enhance_pinned returns,
+    step after step, with the input changing every step."""
+    sd = SW.make_state_dict(0)
+    enh = D.Enhancer(sd, batch=2, n_samples=8160, mode="bf16")
+    outs_serial, outs_stream = [], []
+    inputs = [O.synthetic_audio(2, 8160, seed=100 + i)[2] for i in range(4)]
+    for x in inputs:
+        enh.host_in.copy_(x)
+        enh.enhance_pinned()
+        torch.cuda.synchronize()
+        outs_serial.append(enh.host_out.clone())
+    for x in inputs:
+        enh.host_in.copy_(x)
+        enh.enhance_pinned_stream()
+        enh.drain()
+        torch.cuda.synchronize()       # host_in is rewritten next iteration: its H2D copy must have been consumed
+        outs_stream.append(enh.host_out.clone())
+    for a, b in zip(outs_serial, outs_stream):
+        # not bit-equal: the pooling sums are float atomics, so two runs of the same graph differ in the last bf16 digits
+        assert rel_err(a, b) <= 2e-3
+    assert rel_err(outs_stream[0], outs_stream[1]) > 1e-2   # and the inputs did change from step to step
