@@ -19,8 +19,8 @@
 // The host (dcs-net_b200/packing.py: StripConv) flattens the layer into a table of MMA "items"
 // {ring row, A descriptor offset, B block, accumulator column, first}; the issuing warp just walks the table.
 //
-// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-// (TMEM lane quadrant = warp % 4): bias + activation + bf16 + per-(image, channel) pooling sums.
+// Warp roles: warp 0 = TMA producer, warps 1-2 = MMA issuers (warp 1 also allocates TMEM), warps 3.. = 4 / 8 / 16 epilogue
+// warps (TMEM lane quadrant = warp % 4): bias + activation + bf16 + per-(image, channel) pooling sums, or the mask tail.
 #include <cuda.h>
 #include <string.h>
 #include <algorithm>
@@ -32,9 +32,15 @@ namespace dcs {
 int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_units, int h, int b, int box_units);
 
 constexpr int kStripM = 128;
-// threads = warp 0 TMA + warp 1 MMA + kEpi epilogue warps (4, 8 or 16: kEpi / 4 warps per TMEM lane quadrant, which split the
-// accumulator's 32-column chunks; the tail epilogue is transcendental-heavy and always uses 16)
-constexpr int strip_threads(int epi_warps) { return 64 + 32 * epi_warps; }
+// threads = warp 0 TMA + warps 1, 2 MMA issuers + kEpi epilogue warps (4, 8 or 16: kEpi / 4 warps per TMEM lane quadrant,
+// which split the accumulator's 32-column chunks; the tail epilogue is transcendental-heavy and always uses 16).
+// TWO issuing warps: tools/umma_rate_test.cu measures 54.8 cycles per M = 128, N <= 64 MMA from one issuing thread but 39-48
+// from two (the tensor core's own floor, 32 + N/4 cycles: A and B streamed from shared memory at 128 B/clk), so a single
+// issuer — plus its ~15 instructions of descriptor arithmetic per item — was the bound of every small-N layer.
+constexpr int kStripIssuers = 2;
+constexpr int kStripAcc = 4;              // accumulator stages in TMEM: row tile g uses stage g % 4, issuer g % 2
+constexpr int kStripEpi0 = 1 + kStripIssuers;   // first epilogue warp
+constexpr int strip_threads(int epi_warps) { return 32 * (kStripEpi0 + epi_warps); }
 constexpr int kStripMaxRing = 16;
 constexpr int kStripMaxItems = 64;    // MMA items of one phase group; the table travels in the kernel parameters
 
@@ -67,7 +73,7 @@ struct StripArgs {
 };
 
 struct __align__(8) StripBarriers {
-  uint64_t full[kStripMaxRing], empty[kStripMaxRing], acc_full[2], acc_empty[2], wbar;
+  uint64_t full[kStripMaxRing], empty[kStripMaxRing], acc_full[kStripAcc], acc_empty[kStripAcc], wbar;
   uint32_t tmem_base;
 };
 
@@ -98,6 +104,33 @@ struct UnitIter {  // unit u of a phase group -> (image, column strip, row chunk
   }
 };
 
+// Walks this CTA's row tiles in order across its units.  `lo` = index (in the CTA's stream of ring rows) of the tile's first
+// source row, `slot` = lo % R; after the last tile `lo` = total number of rows and valid = false.
+struct TileCursor {
+  UnitIter un;
+  int u, stride, j, n_dy;
+  uint32_t lo, slot;
+  bool valid;
+  __device__ __forceinline__ void init(const StripArgs& a, int first, int step, int ndy) {
+    u = first; stride = step; n_dy = ndy; lo = 0; slot = 0;
+    valid = u < a.n_units;
+    if (valid) { un.set(a, u); j = un.j0; }
+  }
+  __device__ __forceinline__ void advance(const StripArgs& a) {
+    if (!valid) return;
+    uint32_t d;
+    if (++j < un.j1) d = (uint32_t)a.s_h;
+    else {
+      d = (uint32_t)n_dy;
+      u += stride;
+      valid = u < a.n_units;
+      if (valid) { un.set(a, u); j = un.j0; }
+    }
+    lo += d; slot += d;
+    while (slot >= (uint32_t)a.R) slot -= (uint32_t)a.R;
+  }
+};
+
 template <int kCols, int kNdy, int kIpr, int kEpi = 4, bool kTail = false>
 __global__ void __launch_bounds__(strip_threads(kEpi), 1)
 cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1, const StripArgs a) {
@@ -110,11 +143,13 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int cta_in_grp = blockIdx.x, ctas_in_grp = gridDim.x;
   const StripGroup& G = a.grp;
-  constexpr uint32_t tmem_cols = 2 * kCols < 32 ? 32u : (uint32_t)(2 * kCols);  // kCols is a power of two
+  constexpr uint32_t tmem_cols = kStripAcc * kCols < 32 ? 32u : (uint32_t)(kStripAcc * kCols);  // kCols is a power of two
+  static_assert(kStripAcc * kCols <= 512, "accumulator stages exceed TMEM");
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < a.R; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kEpi); }
+    // a ring slot is free again when BOTH issuers have released its row
+    for (int s = 0; s < a.R; ++s) { mbar_init(smem_u32(&bars->full[s]), 1); mbar_init(smem_u32(&bars->empty[s]), kStripIssuers); }
+    for (int i = 0; i < kStripAcc; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), kEpi); }
     mbar_init(smem_u32(&bars->wbar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
@@ -158,71 +193,81 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         if (++slot == (uint32_t)a.R) { slot = 0; par ^= 1; }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (whole warp loops, one lane issues)
+  } else if (warp < kStripEpi0) {
+    // ===================================================================== MMA issuers (2 warps; whole warp loops, one lane issues)
+    // Issuer w owns the row tiles g with g % 2 == w (accumulator stage g % 4).  Both walk the same tile sequence; each waits
+    // for the source rows its tiles need and releases a ring row once ITS last tile that reads it has been issued
+    // (rows below the first row of its next own tile); the slot's empty barrier counts both issuers.
+    const int w_iss = warp - 1;
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_mma >> 3) << 17) | ((uint32_t)(kStripM >> 4) << 24);
     const uint64_t a_desc_c0 = umma_desc(0, a.row_bytes0), a_desc_c1 = umma_desc(0, a.row_bytes1), b_desc_c = umma_desc(0, 32);
     const uint32_t ring16 = (smem_u32(base) & 0x3FFFFu) >> 4, slot16 = a.slot_bytes >> 4, w16 = (smem_u32(w_s) & 0x3FFFFu) >> 4;
     const uint32_t bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
     const uint32_t R = (uint32_t)a.R;
-    uint32_t ws = 0, wp = 0;      // next full barrier to wait on (slot, parity)
-    uint32_t gw = 0, glo = 0;     // rows waited so far / ring row index of the first row of the current output row
-    uint32_t slot_lo = 0, fs = 0; // slot of row glo / next slot to free
-    uint32_t acc = 0, accp = 0;
+    uint32_t ws = 0, wp = 0, gw = 0;   // next full barrier to wait on (slot, parity) / rows waited so far
+    uint32_t fs = 0, rel = 0;          // next slot to release / rows released so far
     mbar_wait(smem_u32(&bars->wbar), 0);
-    UnitIter un;
-    for (int u = cta_in_grp; u < a.n_units; u += ctas_in_grp) {
-      un.set(a, u);
-      for (int j = un.j0; j < un.j1; ++j) {
-        mbar_wait(smem_u32(&bars->acc_empty[acc]), accp ^ 1);
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * (uint32_t)kCols;
-        // items are sorted by ring row (drow): wait for a source row once, then issue its MMAs back to back
+    TileCursor cur, ahead;             // tile g and tile g + 2 (this issuer's next own tile)
+    cur.init(a, cta_in_grp, ctas_in_grp, kNdy);
+    ahead.init(a, cta_in_grp, ctas_in_grp, kNdy);
+    ahead.advance(a); ahead.advance(a);
+    for (uint32_t g = 0; cur.valid; cur.advance(a), ahead.advance(a), ++g) {
+      if ((int)(g & 1u) != w_iss) continue;
+      const uint32_t acc = g & (kStripAcc - 1), accp = (g / kStripAcc) & 1u;
+      mbar_wait(smem_u32(&bars->acc_empty[acc]), accp ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)kCols;
+      // items are sorted by ring row (drow): wait for a source row once, then issue its MMAs back to back
 #pragma unroll
-        for (int dg = 0; dg < kNdy; ++dg) {
-          const uint32_t need = glo + (uint32_t)dg;
-          if (gw <= need) {
-            while (gw <= need) {
-              mbar_wait(bar_full0 + 8u * ws, wp);
-              if (++ws == R) { ws = 0; wp ^= 1; }
-              ++gw;
-            }
-            tc_fence_after();
+      for (int dg = 0; dg < kNdy; ++dg) {
+        const uint32_t need = cur.lo + (uint32_t)dg;
+        if (gw <= need) {
+          while (gw <= need) {
+            mbar_wait(bar_full0 + 8u * ws, wp);
+            if (++ws == R) { ws = 0; wp ^= 1; }
+            ++gw;
           }
-          uint32_t s = slot_lo + (uint32_t)dg;
-          if (s >= R) s -= R;
-          const uint32_t a16 = ring16 + s * slot16;
-          if (elect_one()) {
-#pragma unroll
-            for (int q = 0; q < kIpr; ++q) {
-              const uint4 item = a.items[dg * kIpr + q];
-              const uint32_t flags = item.z >> 24, d_col = item.z & 0xffffu;
-              const uint64_t ad = ((flags & 2u) ? a_desc_c1 : a_desc_c0) + (uint64_t)(a16 + item.x);
-              const uint64_t bd = b_desc_c + (uint64_t)(w16 + item.y);
-              tc_mma_bf16(d_tmem + d_col, ad, bd, idesc, (flags & 1u) ? 0u : 1u);
-            }
-          }
-          __syncwarp();
+          tc_fence_after();
         }
-        const uint32_t nfree = (j == un.j1 - 1) ? (uint32_t)kNdy : (uint32_t)a.s_h;
+        uint32_t sl = cur.slot + (uint32_t)dg;
+        if (sl >= R) sl -= R;
+        const uint32_t a16 = ring16 + sl * slot16;
         if (elect_one()) {
-          tc_commit(smem_u32(&bars->acc_full[acc]));
-          uint32_t f = fs;
-          for (uint32_t i = 0; i < nfree; ++i) { tc_commit(bar_empty0 + 8u * f); if (++f == R) f = 0; }
+#pragma unroll
+          for (int q = 0; q < kIpr; ++q) {
+            const uint4 item = a.items[dg * kIpr + q];
+            const uint32_t flags = item.z >> 24, d_col = item.z & 0xffffu;
+            const uint64_t ad = ((flags & 2u) ? a_desc_c1 : a_desc_c0) + (uint64_t)(a16 + item.x);
+            const uint64_t bd = b_desc_c + (uint64_t)(w16 + item.y);
+            tc_mma_bf16(d_tmem + d_col, ad, bd, idesc, (flags & 1u) ? 0u : 1u);
+          }
         }
         __syncwarp();
-        fs += nfree; while (fs >= R) fs -= R;
-        slot_lo += nfree; while (slot_lo >= R) slot_lo -= R;
-        glo += nfree;
-        if (++acc == 2) { acc = 0; accp ^= 1; }
       }
+      const uint32_t upto = ahead.lo;                 // first row of this issuer's next own tile (or the total row count)
+      // Never release a row this issuer has not waited for: a parity wait on a phase that is two completions old would
+      // spin for ever (rows only the other issuer's tile reads, at unit boundaries).  They are in flight for that tile.
+      while (gw < upto) {
+        mbar_wait(bar_full0 + 8u * ws, wp);
+        if (++ws == R) { ws = 0; wp ^= 1; }
+        ++gw;
+      }
+      const uint32_t nfree = upto - rel;
+      if (elect_one()) {
+        tc_commit(smem_u32(&bars->acc_full[acc]));
+        uint32_t f = fs;
+        for (uint32_t i = 0; i < nfree; ++i) { tc_commit(bar_empty0 + 8u * f); if (++f == R) f = 0; }
+      }
+      __syncwarp();
+      fs += nfree; while (fs >= R) fs -= R;
+      rel = upto;
     }
   } else {
     // ===================================================================== epilogue (4 warps, one TMEM lane quadrant each)
     const int quad = warp & 3;
     const int m = quad * 32 + lane;
     const int run_len = 1 << a.run_log2;                 // columns of one output row run = up_w * n_real
-    uint32_t acc = 0, accp = 0;
+    uint32_t acc = 0, accp = 0;                          // row tile g of this CTA uses stage g % kStripAcc
     UnitIter un;
     for (int u = cta_in_grp; u < a.n_units; u += ctas_in_grp) {
       un.set(a, u);
@@ -236,7 +281,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const dcs_strip_tail& tl = a.tail;
         const bool exact = tl.exact_polar != 0;
         // 16 epilogue warps: warp (quad, sub) owns phase row ph = sub / 2 and output pixels 4 (sub % 2) .. +3 of each lane
-        const int tsub = (warp - 2) >> 2, ph = tsub >> 1, half = tsub & 1;
+        const int tsub = (warp - kStripEpi0) >> 2, ph = tsub >> 1, half = tsub & 1;
         for (int j = un.j0; j < un.j1; ++j) {
           mbar_wait(smem_u32(&bars->acc_full[acc]), accp);
           tc_fence_after();
@@ -273,7 +318,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               if (tl.net_raw) reinterpret_cast<float4*>(tl.net_raw)[q] = make_float4(raw[0].x, raw[0].y, raw[1].x, raw[1].y);
             }
           }
-          if (++acc == 2) { acc = 0; accp ^= 1; }
+          if (++acc == kStripAcc) { acc = 0; accp ^= 1; }
         }
         continue;
       }
@@ -282,7 +327,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       constexpr int kChunk = kCols < 32 ? kCols : 32;
       constexpr int kSub = kEpi / 4;                      // warps per quadrant; warp `sub` owns chunks sub, sub + kSub, ...
       static_assert(kTail || (kCols / kChunk) % kSub == 0, "chunks must divide evenly among the warps of a quadrant");
-      const int sub = (warp - 2) >> 2;
+      const int sub = (warp - kStripEpi0) >> 2;
       float pool_acc[kChunk];
 #pragma unroll
       for (int c = 0; c < kChunk; ++c) pool_acc[c] = 0.f;
@@ -325,7 +370,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
             }
           }
         }
-        if (++acc == 2) { acc = 0; accp ^= 1; }
+        if (++acc == kStripAcc) { acc = 0; accp ^= 1; }
       }
       if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
         if constexpr (kChunk == 32) {

@@ -89,8 +89,13 @@ __device__ __forceinline__ float fast_tanh(float v) {
 }
 // Shortest dependent chains for the serial LSTM cell update: MUFU.EX2 + MUFU.RCP (approximate reciprocal, ~1 ulp) with
 // no Newton fix-up or special-case branch; absolute error <= ~3e-7.
-__device__ __forceinline__ float quick_sigmoid(float v) { return __fdividef(1.f, 1.f + __expf(-v)); }
-__device__ __forceinline__ float quick_tanh(float v) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * v)) - 1.f; }
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));   // bare MUFU.RCP (no range-scaling code as in __fdividef)
+  return r;
+}
+__device__ __forceinline__ float quick_sigmoid(float v) { return rcp_approx(1.f + __expf(-v)); }
+__device__ __forceinline__ float quick_tanh(float v) { return 2.f * rcp_approx(1.f + __expf(-2.f * v)) - 1.f; }
 __device__ __forceinline__ float act_apply(float v, int act) {
   if (act == DCS_ACT_RELU) return fmaxf(v, 0.f);
   if (act == DCS_ACT_LRELU) return v > 0.f ? v : 0.01f * v;

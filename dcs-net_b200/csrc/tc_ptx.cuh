@@ -6,7 +6,7 @@
 
 namespace dcs {
 
-constexpr uint32_t kSpinLimit = 1u << 26;  // mbarrier spin cap: trap instead of hanging the GPU
+constexpr uint32_t kSpinLimit = 1u << 22;  // mbarrier spin cap: trap instead of hanging the GPU
 
 // ------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
