@@ -322,7 +322,7 @@ def measure_roofline(plan, args, B, T):
 
     wrap("cconv", lambda pk, s0, s1, dst, use_tc=False, pool_sums=None: "conv_tc" if use_tc else "conv_ffma")
     wrap("cconv_strip", lambda *a, **k: "conv_strip")
-    for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "attention_fused", "clstm", "mask_combine", "enc0", "dec6_tail"):
+    for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "attention_fused", "attention_stream", "clstm", "mask_combine", "enc0", "dec6_tail"):
         wrap(n, lambda *a, _n=n, **k: _n)
     steps = max(3, min(args.steps, 10))
     try:
@@ -386,6 +386,7 @@ def measure_roofline(plan, args, B, T):
         "spat_stats": att_bytes + sum(t.shape[0] * t.shape[1] * t.shape[2] * 16 for t in att),
         "spat_apply": 2 * att_bytes + sum(t.shape[0] * t.shape[1] * t.shape[2] * 16 for t in att),
         "attention_fused": 2 * att_bytes,
+        "attention_stream": 2 * att_bytes,     # x once in, y once out
         "dec6_tail": B * (2 * 128 * (T // 2) * 16 * esz + 2 * 8 * 256 * T),
         "enc0": B * (8 * 256 * T + 128 * (T // 2) * 16 * esz),
     }

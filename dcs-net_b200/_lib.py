@@ -139,6 +139,7 @@ SYMBOLS = {
     "dcs_spat_stats": (_i, [C.POINTER(SpatStatsParams), _vp]),
     "dcs_spat_apply": (_i, [C.POINTER(SpatApplyParams), _vp]),
     "dcs_attention_fused": (_i, [C.POINTER(AttentionParams), _vp]),
+    "dcs_attention_stream": (_i, [C.POINTER(AttentionParams), _vp]),
     "dcs_clstm_workspace_bytes": (_i64, [_i, _i, _i]),
     "dcs_clstm_fwd": (_i, [C.POINTER(ClstmParams), _vp]),
     "dcs_mask_combine": (_i, [C.POINTER(MaskCombineParams), _vp]),

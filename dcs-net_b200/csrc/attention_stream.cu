@@ -1,0 +1,435 @@
+// attention_stream.cu — ComplexChannelAttention + ComplexSpatialAttention as ONE streaming pass (bf16 / tensor-core mode).
+//
+// Reference: c_network.py:53-84 (modules), 208-211 / 219-220 (y = SA(u) * u, u = CA(x) * x), pools
+// network_functions.py:114-138, ComplexSigmoid 107-112.
+//
+// The three-kernel form (spat_stats -> spat_apply, attention.cu) reads x twice, round-trips 16 B / pixel of statistics
+// through HBM and is issue-bound: at C = 8 the 7x7 gate conv alone is 196 packed FMAs per pixel (r01r profile: 283 us
+// for a 262 MB tensor, 69 % issue-active).  Here a CTA owns a column strip of TW pixels of one image and walks DOWN the
+// rows:
+//   * x rows arrive by 1-D bulk copies (cp.async.bulk, one per row segment + halo: channels-last rows are contiguous)
+//     into a ring of NR rows, NR - 4 rows ahead of their use: x is read from HBM once (halo columns are L2 hits);
+//   * row r: per-pixel statistics (mean_c u, max_c Re u, max_c Im u) -> one shared-memory row, tf32-rounded;
+//   * the 7x7 complex gate conv runs on the tensor cores as mma.sync.m16n8k8 TF32: for ONE statistics row the
+//     A operand is the row itself read as a sliding matrix A[m][kx*4 + ci] = row[(m + kx) * 4 + ci] (16 output pixels
+//     x 7 taps x 4 real inputs, no im2col), B holds the taps with N = (ky, re/im): 8 MMAs per 16 pixels give the 14
+//     row-partials P[ky][re/im].  Partial ky of statistics row r belongs to output row r + 3 - ky: lane t of a quad
+//     owns ky = t and ky = t + 4, so it keeps a 4-deep register ring of pending output rows (the ring slot is the MMA's
+//     C operand 4 rows later); a quad reduction assembles the finished row.  3.1 warp instructions per pixel instead
+//     of ~8 for the packed-FMA form, and no 7-row statistics window in shared memory;
+//   * output row r - 3: gate_s * gate_c * x from the ring -> HBM (16-byte stores).
+// HBM traffic: x once in, y once out.  fp32 mode keeps the exact CUDA-core kernels (TF32 products would break 1e-5).
+#include "tc_ptx.cuh"
+
+namespace dcs {
+
+constexpr int kAsThreads = 256, kAsRing = 8;
+
+struct AttStreamArgs {
+  const __nv_bfloat16* x; __nv_bfloat16* y;
+  const float* sums; float inv_hw;
+  const float *w1_r, *w1_i, *w2_r, *w2_i, *w7;
+  int H, W, R, NR;
+};
+
+// round-to-nearest for a tf32 MMA operand: the tensor core ignores the low 13 mantissa bits, so adding half an ulp of
+// tf32 to the bit pattern is all that is needed (finite inputs)
+__device__ __forceinline__ float tf32_rna(float v) { return __uint_as_float(__float_as_uint(v) + 0x1000u); }
+__device__ __forceinline__ float sigmoid_ex2(float v) {   // MUFU.EX2 + MUFU.RCP, abs. error ~3e-7
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+                 "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+// packed fp32x2 arithmetic (FMUL2 / FADD2 / FFMA2): the kernel is issue-bound, two lanes of work per slot
+__device__ __forceinline__ float2 mul2(const float2 a, const float2 b) {
+  unsigned long long r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 add2(const float2 a, const float2 b) {
+  unsigned long long r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)), "l"(*reinterpret_cast<const unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&r);
+}
+__device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const float2 c) {
+  unsigned long long r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(*reinterpret_cast<const unsigned long long*>(&a)),
+      "l"(*reinterpret_cast<const unsigned long long*>(&b)), "l"(*reinterpret_cast<const unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&r);
+}
+// a 16-byte vector = 4 complex bf16 (e0 e1 e2 e3) as two element PAIRS in split form: re = (e_a.re, e_b.re), im likewise
+struct CPair { float2 re, im; };
+__device__ __forceinline__ void unpack_pairs(const uint4 q, CPair& p01, CPair& p23) {
+  p01.re = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.y << 16));
+  p01.im = make_float2(__uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y & 0xffff0000u));
+  p23.re = make_float2(__uint_as_float(q.z << 16), __uint_as_float(q.w << 16));
+  p23.im = make_float2(__uint_as_float(q.z & 0xffff0000u), __uint_as_float(q.w & 0xffff0000u));
+}
+// per-thread channel gate of an element pair: (g.re, g.im, -g.im) as pairs
+struct GPair { float2 re, im, nim; };
+__device__ __forceinline__ CPair cmul_pair(const GPair& g, const CPair& v) {
+  CPair u;
+  u.re = fma2(g.re, v.re, mul2(g.nim, v.im));
+  u.im = fma2(g.re, v.im, mul2(g.im, v.re));
+  return u;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// shared-memory access by 32-bit address (no generic-address arithmetic in the row loop)
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ float2 lds64f(uint32_t addr) {
+  float2 v;
+  asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128f(uint32_t addr, float a, float b, float c, float d) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+__device__ __forceinline__ void sts64f(uint32_t addr, float a, float b) {
+  asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// C channels (power of two >= 8), strip width TW (multiple of 16, <= 128).
+template <int C, int TW>
+__global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const AttStreamArgs a) {
+  constexpr int PW = TW + 6;                                  // strip + 3-pixel halo each side
+  constexpr int VPP = C / 4;                                  // 16-byte vectors per pixel
+  constexpr int GMAX = kAsThreads / PW;                       // lanes per pixel in the statistics pass: largest power of two
+  constexpr int G = GMAX >= 8 ? (VPP >= 8 ? 8 : VPP) : GMAX >= 4 ? (VPP >= 4 ? 4 : VPP) : GMAX >= 2 ? 2 : 1;
+  constexpr int VPL = VPP / G;                                // vectors per lane (statistics)
+  constexpr int NSEG = TW / 16;                               // 16-pixel MMA segments (one warp each)
+  constexpr bool OWN = NSEG >= 7;                             // a warp applies the 16 pixels whose gate it computed (TW = 112, 128)
+  constexpr int NAPP = OWN ? VPP / 2 : (TW * VPP + kAsThreads - 1) / kAsThreads;   // vectors per thread (product)
+  constexpr uint32_t ROW_BYTES = (uint32_t)PW * C * 4;
+  constexpr int ST_PITCH = (PW + 2) * 4;                      // floats per statistics row (2 zero pixels of padding)
+  static_assert(G >= 1 && VPL >= 1 && VPL * G == VPP && PW * G <= kAsThreads, "statistics mapping");
+  static_assert(OWN || (kAsThreads % VPP == 0), "product mapping");
+
+  extern __shared__ __align__(128) unsigned char as_smem[];
+  const int NR = a.NR, H = a.H, W = a.W;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.y, x0 = blockIdx.x * TW;
+  unsigned char* xs = as_smem;                                       // [NR][PW][C] bf16 complex
+  float* st = reinterpret_cast<float*>(xs + (size_t)NR * ROW_BYTES);  // [4][ST_PITCH]
+  float* sg = st + 4 * ST_PITCH;                                     // [2 rows][2][TW] spatial gates (re plane, im plane) of the step's rows
+  float2* gs = reinterpret_cast<float2*>(sg + 4 * TW);               // [C] channel gate
+  float2* avg = gs + C;                                              // [C]
+  float2* hid = avg + C;                                             // [16]
+  uint64_t* full = reinterpret_cast<uint64_t*>(hid + 16);            // [kAsRing]
+  const uint32_t xs_u32 = smem_u32(xs), full_u32 = smem_u32(full);
+
+  const int xa = max(x0 - 3, 0), xe = min(x0 + TW + 3, W);           // image columns this strip reads
+  const uint32_t seg_bytes = (uint32_t)(xe - xa) * C * 4;
+  const uint32_t seg_off = (uint32_t)(xa - (x0 - 3)) * C * 4;
+  const __nv_bfloat16* xsrc = a.x + ((int64_t)b * H * W + xa) * C * 2;
+  auto issue_row = [&](int r) {                                      // one thread; ring slot r & 7 (r < NR when H < 8)
+    const uint32_t bar = full_u32 + 8 * (r & (kAsRing - 1));
+    mbar_expect_tx(bar, seg_bytes);
+    bulk_g2s(xs_u32 + (r & (kAsRing - 1)) * ROW_BYTES + seg_off, xsrc + (int64_t)r * W * C * 2, seg_bytes, bar);
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kAsRing; ++i) mbar_init(full_u32 + 8 * i, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int i = tid; i < 4 * ST_PITCH; i += kAsThreads) st[i] = 0.f;
+  for (int c = tid; c < C; c += kAsThreads)
+    avg[c] = make_float2(a.sums[((int64_t)b * C + c) * 2] * a.inv_hw, a.sums[((int64_t)b * C + c) * 2 + 1] * a.inv_hw);
+  __syncthreads();
+  if (tid == 0)
+    for (int r = 0; r < min(NR, H); ++r) issue_row(r);
+
+  // ---- channel gate (ComplexChannelAttention): sigmoid_c(2 W2 crelu(W1 avg)), recomputed per CTA (C * R complex MACs)
+  for (int r = warp; r < a.R; r += kAsThreads / 32) {
+    float re = 0.f, im = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wr = a.w1_r[r * C + c], wi = a.w1_i[r * C + c];
+      re += wr * avg[c].x - wi * avg[c].y;
+      im += wr * avg[c].y + wi * avg[c].x;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+    if (lane == 0) hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+  }
+  __syncthreads();
+  for (int c = tid; c < C; c += kAsThreads) {
+    float re = 0.f, im = 0.f;
+    for (int r = 0; r < a.R; ++r) {
+      const float wr = a.w2_r[c * a.R + r], wi = a.w2_i[c * a.R + r];
+      re += wr * hid[r].x - wi * hid[r].y;
+      im += wr * hid[r].y + wi * hid[r].x;
+    }
+    gs[c] = make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
+  }
+
+  // ---- gate conv operands (ComplexConv2d(2, 1, 7, padding=3, bias=False) as a real 4 -> 2 conv).  Per statistics row the
+  //      MMA is  D[m][n] = sum_kk Wm[m][kk] * S[n][kk]:  n = 8 pixels, kk = kx * 4 + ci (28 of 32 used),
+  //      ci = (mean.re, mean.im, max.re, max.im), and m = 16 rows of row-partials: lane group g owns rows g and g + 8 with
+  //      q = g >> 1, output part o = g & 1:   row g: ky = q (q < 3; zero for q = 3),  row g + 8: ky = q + 4 (q < 3), ky = 3 (q = 3).
+  //      The taps are the A operand (constant registers); the statistics row is the B operand, whose fragment
+  //      (k = t, t + 4 of k-step s  <->  kk = 8 t + 2 s, 8 t + 2 s + 1) is 8 consecutive floats of the row: two LDS.128.
+  float afr[4][4];
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int kk = 8 * t + 2 * s + (r >> 1), kx = kk >> 2, ci = kk & 3;
+      const int q = g >> 1, o = g & 1;
+      const int ky = (r & 1) == 0 ? (q < 3 ? q : 7) : (q < 3 ? 4 + q : 3);
+      float v = 0.f;
+      if (kx < 7 && ky < 7) {
+        const int idx = (ci >> 1) * 49 + ky * 7 + kx;
+        const float wr = a.w7[idx], wi = a.w7[98 + idx];
+        v = o == 0 ? ((ci & 1) ? -wi : wr) : ((ci & 1) ? wr : wi);
+      }
+      afr[s][r] = tf32_rna(v);
+    }
+  __syncthreads();
+
+  // ---- per-thread constants of the three phases (the pixel / channels a thread works on never change with the row)
+  const uint32_t st_u32 = smem_u32(st), sg_u32 = smem_u32(sg);
+  // statistics: pixel sp of the padded row, vectors sub + k G
+  const int sp = tid / G, sub = tid % G;
+  const bool s_act = sp < PW;
+  const bool s_in = s_act && (unsigned)(x0 - 3 + sp) < (unsigned)W;
+  const uint32_t s_ld = xs_u32 + (uint32_t)(s_act ? sp : 0) * C * 4 + sub * 16;
+  const uint32_t s_st = st_u32 + (uint32_t)(s_act ? sp : 0) * 16;
+  GPair sgate[VPL][2];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k)
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const float2 ga = gs[(sub + k * G) * 4 + 2 * h2], gb = gs[(sub + k * G) * 4 + 2 * h2 + 1];
+      sgate[k][h2].re = make_float2(ga.x, gb.x); sgate[k][h2].im = make_float2(ga.y, gb.y);
+      sgate[k][h2].nim = make_float2(-ga.y, -gb.y);
+    }
+  // product: vectors i = i0 + k * istep of the strip row -> pixel i / VPP, vector i % VPP (constant per thread)
+  const int i0 = OWN ? warp * 16 * VPP + lane : tid;
+  constexpr int istep = OWN ? 32 : kAsThreads;
+  GPair agate[2];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const float2 ga = gs[(i0 % VPP) * 4 + 2 * h2], gb = gs[(i0 % VPP) * 4 + 2 * h2 + 1];
+    agate[h2].re = make_float2(ga.x, gb.x); agate[h2].im = make_float2(ga.y, gb.y); agate[h2].nim = make_float2(-ga.y, -gb.y);
+  }
+  bool a_ok[NAPP];
+#pragma unroll
+  for (int k = 0; k < NAPP; ++k) a_ok[k] = i0 + k * istep < TW * VPP && x0 + (i0 + k * istep) / VPP < W;
+  const uint32_t a_ld = xs_u32 + 3 * C * 4 + (uint32_t)i0 * 16;          // + ring slot * ROW_BYTES + k * istep * 16
+  const uint32_t a_sg = sg_u32 + (uint32_t)(i0 / VPP) * 4;               // plane re; + TW * 4 plane im; + k * (istep / VPP) * 4
+  __nv_bfloat16* yp = a.y + ((int64_t)b * H * W + x0) * C * 2 + (int64_t)i0 * 8;   // output row 0; + y_pitch per row
+  const int64_t y_pitch = (int64_t)W * C * 2;
+  const float invC = 1.f / (float)C;
+  // conv: this lane's B values in a statistics row (float4 index warp * 16 + g + 2 t; second pixel group + 8), gate
+  // store of the lanes that end up with the row totals (q = 2): plane o, pixels warp * 16 + 2 t (+ 8)
+  const int q = g >> 1;
+  const uint32_t c_ld = st_u32 + (uint32_t)(warp * 16 + g + 2 * t) * 16;
+  const uint32_t c_st = sg_u32 + (uint32_t)((g & 1) * TW + warp * 16 + 2 * t) * 4;
+  const int src_lane = (lane & 7) | (((q + 3) & 3) << 3);
+
+  float slot[4][2][2], run[2][2];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      run[h2][e] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) slot[i][h2][e] = 0.f;
+    }
+  // Two rows per step: the statistics, MMA chains and products of the two rows are independent instruction streams (the
+  // kernel is bound by issue latency at 2 CTAs per SM), one CTA barrier per row pair.
+  auto stats_row = [&](int row, uint32_t sbuf) {
+    const uint32_t ring = (uint32_t)(row & (kAsRing - 1));
+    float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
+    float mr = -INFINITY, mi = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < VPL; ++k) {   // lanes outside the image read (valid) shared memory and are masked at the store
+      CPair p01, p23;
+      unpack_pairs(lds128(s_ld + ring * ROW_BYTES + k * G * 16), p01, p23);
+      const CPair u01 = cmul_pair(sgate[k][0], p01), u23 = cmul_pair(sgate[k][1], p23);
+      sre = add2(sre, add2(u01.re, u23.re));
+      sim = add2(sim, add2(u01.im, u23.im));
+      mr = fmaxf(fmaxf(mr, fmaxf(u01.re.x, u01.re.y)), fmaxf(u23.re.x, u23.re.y));
+      mi = fmaxf(fmaxf(mi, fmaxf(u01.im.x, u01.im.y)), fmaxf(u23.im.x, u23.im.y));
+    }
+    float sr = sre.x + sre.y, si = sim.x + sim.y;
+    if (G > 1) {   // every lane takes part
+#pragma unroll
+      for (int o = G >> 1; o; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o);
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+      }
+    }
+    if (s_act && sub == 0) {
+      if (s_in) sts128f(s_st + sbuf, tf32_rna(sr * invC), tf32_rna(si * invC), tf32_rna(mr), tf32_rna(mi));
+      else sts128f(s_st + sbuf, 0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto apply_row = [&](int yo, uint32_t gbuf) {
+    const uint32_t ring = (uint32_t)(yo & (kAsRing - 1));
+#pragma unroll
+    for (int k = 0; k < NAPP; ++k) {
+      if (a_ok[k]) {
+        CPair p01, p23;
+        unpack_pairs(lds128(a_ld + ring * ROW_BYTES + k * istep * 16), p01, p23);
+        float2 gsp;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gsp.x) : "r"(a_sg + gbuf + k * (istep / VPP) * 4));
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gsp.y) : "r"(a_sg + gbuf + TW * 4 + k * (istep / VPP) * 4));
+        const float2 gre = make_float2(gsp.x, gsp.x), gim = make_float2(gsp.y, gsp.y), gnim = make_float2(-gsp.y, -gsp.y);
+        const CPair u01 = cmul_pair(agate[0], p01), u23 = cmul_pair(agate[1], p23);
+        const float2 r01 = fma2(gre, u01.re, mul2(gnim, u01.im)), i01 = fma2(gre, u01.im, mul2(gim, u01.re));
+        const float2 r23 = fma2(gre, u23.re, mul2(gnim, u23.im)), i23 = fma2(gre, u23.im, mul2(gim, u23.re));
+        *reinterpret_cast<uint4*>(yp + (int64_t)yo * y_pitch + (size_t)k * istep * 8) =
+            make_uint4(pack_bf16x2(r01.x, i01.x), pack_bf16x2(r01.y, i01.y), pack_bf16x2(r23.x, i23.x), pack_bf16x2(r23.y, i23.y));
+      }
+    }
+  };
+  constexpr uint32_t kStBuf = ST_PITCH * 4, kSgBuf = 2 * TW * 4;
+  const int nsteps = H + 3;
+  int next_row = min(NR, H);                       // thread 0: rows below this are issued
+  for (int rr0 = 0; rr0 < nsteps; rr0 += 4) {
+#pragma unroll
+    for (int u = 0; u < 4; u += 2) {
+      const int rr = rr0 + u;                      // this step: statistics rows rr, rr + 1 -> output rows rr - 3, rr - 2
+      if (rr >= nsteps) break;
+      const uint32_t stb = u * kStBuf;             // statistics buffers (u, u + 1): a fast warp's next step must not touch them
+      // ---- 1. statistics (zero rows outside the image = the gate conv's zero padding)
+      if (rr + 1 < H) {
+        mbar_wait(full_u32 + 8 * (rr & (kAsRing - 1)), (uint32_t)((rr >> 3) & 1));
+        mbar_wait(full_u32 + 8 * ((rr + 1) & (kAsRing - 1)), (uint32_t)(((rr + 1) >> 3) & 1));
+        stats_row(rr, stb);
+        stats_row(rr + 1, stb + kStBuf);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (rr + v < H) {
+            mbar_wait(full_u32 + 8 * ((rr + v) & (kAsRing - 1)), (uint32_t)(((rr + v) >> 3) & 1));
+            stats_row(rr + v, stb + v * kStBuf);
+          } else if (tid < PW) {
+            sts128f(st_u32 + stb + v * kStBuf + tid * 16, 0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+      __syncthreads();
+      // rows up to rr - 4 have been multiplied out (previous step): their ring slots take rows up to rr + 4
+      if (tid == 0)
+        while (next_row < H && next_row <= rr + 4) issue_row(next_row++);
+
+      // ---- 2. gate conv: a statistics row's 14 row-partials on the tensor cores.  Partial ky of statistics row r belongs
+      //         to output row r + 3 - ky.  A lane with q < 3 owns ky = q (accumulator rows g: opens a pending output row
+      //         in slot[r & 3]) and ky = q + 4 (rows g + 8, four statistics rows later: the SAME slot, fed back as the C
+      //         operand, closes it); q = 3 owns ky = 3 in rows g + 8.  So after the MMAs every lane holds its finished
+      //         share of output row r - 1 - q (q = 3: row r), and the row total travels q = 3 -> 0 -> 1 -> 2, one hop
+      //         per statistics row: the q = 2 lanes end with the complete output row r - 3.
+      if (warp < NSEG) {
+        float d[2][2][4];
+#pragma unroll
+        for (int v = 0; v < 2; ++v)
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) {
+            const float4 v0 = lds128f(c_ld + stb + v * kStBuf + h2 * 128), v1 = lds128f(c_ld + stb + v * kStBuf + h2 * 128 + 16);
+            d[v][h2][0] = 0.f; d[v][h2][1] = 0.f; d[v][h2][2] = slot[u + v][h2][0]; d[v][h2][3] = slot[u + v][h2][1];
+            mma_tf32_16x8x8(d[v][h2], afr[0], v0.x, v0.y);
+            mma_tf32_16x8x8(d[v][h2], afr[1], v0.z, v0.w);
+            mma_tf32_16x8x8(d[v][h2], afr[2], v1.x, v1.y);
+            mma_tf32_16x8x8(d[v][h2], afr[3], v1.z, v1.w);
+            slot[u + v][h2][0] = d[v][h2][0]; slot[u + v][h2][1] = d[v][h2][1];
+          }
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const float in = __shfl_sync(0xffffffffu, run[h2][e], src_lane);   // the previous lane's total one row earlier
+              run[h2][e] = q == 3 ? d[v][h2][2 + e] : d[v][h2][2 + e] + in;
+            }
+          if (q == 2) {   // gate of pixels 2 t, 2 t + 1 (+ 8) of this warp's segment, part o, output row rr + v - 3
+            sts64f(c_st + v * kSgBuf, sigmoid_ex2(run[0][0]), sigmoid_ex2(run[0][1]));
+            sts64f(c_st + v * kSgBuf + 32, sigmoid_ex2(run[1][0]), sigmoid_ex2(run[1][1]));
+          }
+        }
+      }
+      if (OWN) __syncwarp(); else __syncthreads();
+
+      // ---- 3. y = gate_s * (gate_c * x) for output rows rr - 3, rr - 2
+      if (rr >= 3 && rr - 2 < H) {
+        apply_row(rr - 3, 0);
+        apply_row(rr - 2, kSgBuf);
+      } else {
+        if (rr >= 3 && rr - 3 < H) apply_row(rr - 3, 0);
+        if (rr >= 2 && rr - 2 < H) apply_row(rr - 2, kSgBuf);
+      }
+    }
+  }
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+template <int C, int TW>
+static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s) {
+  const int NR = p->h < kAsRing ? p->h : kAsRing;
+  const size_t pw = TW + 6;
+  const size_t smem = (size_t)NR * pw * C * 4 + 4 * (pw + 2) * 16 + (size_t)TW * 16 + (size_t)(2 * C + 16) * 8 + kAsRing * 8;
+  DCS_REQUIRE(smem <= 227 * 1024, "dcs_attention_stream: strip does not fit shared memory (C=%d)", C);
+  AttStreamArgs a;
+  a.x = (const __nv_bfloat16*)p->x; a.y = (__nv_bfloat16*)p->y; a.sums = p->sums; a.inv_hw = 1.f / ((float)p->h * (float)p->w);
+  a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
+  a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = NR;
+  static size_t smem_set = 0;
+  if (smem > smem_set) {
+    DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<C, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_set = smem;
+  }
+  dim3 grid((p->w + TW - 1) / TW, p->batch);
+  attention_stream_kernel<C, TW><<<grid, kAsThreads, smem, s>>>(a);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_attention_stream(const dcs_attention_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->y && p->sums && p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->w7, "dcs_attention_stream: null pointer");
+  DCS_REQUIRE(p->in_dtype == DCS_BF16 && p->out_dtype == DCS_BF16, "dcs_attention_stream: bf16 storage only (the fp32 mode uses dcs_spat_stats / dcs_spat_apply)");
+  DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0, "dcs_attention_stream: bad shape");
+  DCS_REQUIRE(p->reduced > 0 && p->reduced <= 16, "dcs_attention_stream: reduced must be in [1, 16]");
+  cudaStream_t s = (cudaStream_t)stream;
+  // strip width: 128 pixels (every warp owns 16) for the few-channel tensors; narrow strips where a row of C channels is
+  // long (ring of 8 rows) and the tensor has few pixels (enough CTAs), or where the image itself is narrow
+  const int w = p->w;
+  // 112- or 128-pixel strips for the wide images: whichever fills the 2-CTAs-per-SM waves better (time of a CTA ~ TW + 6)
+  auto cost = [&](int tw) { const int64_t ctas = (int64_t)((w + tw - 1) / tw) * p->batch, slots = 2 * num_sms(); return ((ctas + slots - 1) / slots) * (tw + 6); };
+  const bool wide112 = cost(112) < cost(128);
+  switch (p->channels) {
+    case 8: return w > 64 ? (wide112 ? launch_attention_stream<8, 112>(p, s) : launch_attention_stream<8, 128>(p, s))
+                          : w > 32 ? launch_attention_stream<8, 64>(p, s) : launch_attention_stream<8, 32>(p, s);
+    case 16: return w > 64 ? (wide112 ? launch_attention_stream<16, 112>(p, s) : launch_attention_stream<16, 128>(p, s))
+                           : w > 32 ? launch_attention_stream<16, 64>(p, s) : launch_attention_stream<16, 32>(p, s);
+    case 32: return w > 16 ? launch_attention_stream<32, 32>(p, s) : launch_attention_stream<32, 16>(p, s);
+    case 64: return w > 16 ? launch_attention_stream<64, 32>(p, s) : launch_attention_stream<64, 16>(p, s);
+    case 128: return launch_attention_stream<128, 16>(p, s);
+    default: break;
+  }
+  return set_error(-1, "dcs_attention_stream: channels must be 8, 16, 32, 64 or 128 (got %d)", p->channels);
+}

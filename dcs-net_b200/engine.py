@@ -150,6 +150,8 @@ class ForwardPlan:
         # (opt-in with DCS_FUSED_ATTENTION=1: measured slower than the three separate kernels on B200 — its load / stats / conv /
         # apply phases serialise inside a CTA; kept for the next round's TMA-pipelined version)
         self.fused_attention = os.environ.get("DCS_FUSED_ATTENTION", "0") == "1"
+        # bf16 mode: streaming row-ring attention (x read once, TF32 tensor-core gate conv; csrc/attention_stream.cu)
+        self.stream_attention = self.tc and os.environ.get("DCS_STREAM_ATTENTION", "1") != "0"
         self.side = torch.cuda.Stream(device=dev)
 
     # ------------------------------------------------------------------ building blocks
@@ -163,6 +165,8 @@ class ForwardPlan:
             sums = self.sums.view(-1)[: B * Cn * 2].view(B, Cn, 2)
             sums.zero_()
             ops.chan_pool(x, sums)
+        if self.stream_attention and Cn >= 8 and x.dtype == torch.bfloat16 and y.dtype == torch.bfloat16:
+            return ops.attention_stream(x, sums, ca, sa_w7, y)
         if self.fused_attention and Cn >= 4:
             return ops.attention_fused(x, sums, ca, sa_w7, y)
         ops.spat_stats(x, None, stats, sums=sums, ca=ca, gate_out=gate)   # channel-gate MLP fused into the statistics pass

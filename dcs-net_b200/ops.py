@@ -195,6 +195,16 @@ def attention_fused(x, sums, ca, w7, y):
     return y
 
 
+def attention_stream(x, sums, ca, w7, y):
+    """attention_fused() as the streaming row-ring kernel (bf16 storage; TF32 tensor-core gate conv)."""
+    L.require_cuda(x, sums, y)
+    B, H, W, Cn, _ = x.shape
+    p = L.AttentionParams(L.ptr(x), L.ptr(y), L.ptr(sums), B, H, W, Cn, ca["reduced"], _code(x), _code(y),
+                          L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(w7))
+    L.check(L.lib().dcs_attention_stream(C.byref(p), L.stream_ptr()), "dcs_attention_stream")
+    return y
+
+
 def clstm_workspace_bytes(B, S, hidden=64):
     n = L.lib().dcs_clstm_workspace_bytes(B, S, hidden)
     if n < 0:

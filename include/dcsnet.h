@@ -186,6 +186,10 @@ typedef struct {
   const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; const float* w7;
 } dcs_attention_params;
 int dcs_attention_fused(const dcs_attention_params* p, void* stream);
+/* Same contract, bf16 storage only (tensor-core mode): streaming row-ring form — x read once by bulk copies, the 7x7 gate
+ * conv (c_network.py:74,79-83) as mma.sync TF32 row-partials with a register ring of pending output rows, y written
+ * once.  Replaces dcs_spat_stats + dcs_spat_apply on the bf16 path (csrc/attention_stream.cu). */
+int dcs_attention_stream(const dcs_attention_params* p, void* stream);
 
 /* ---- a7: ComplexLSTM (c_network.py:12-51): real_lstm / imag_lstm = nn.LSTM(128->64, 2 layers, bidirectional),
  *      out = (R(re) - I(im)) + j (R(im) + I(re)).  x (B,S,D) complex channels-last (the latent, sequence index

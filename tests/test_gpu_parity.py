@@ -281,6 +281,36 @@ def test_fused_attention_equals_separate_kernels(C, H, W, dtype):
     assert rel_err(got.float(), ref.float()) <= (2e-6 if dtype == torch.float32 else 8e-3)
 
 
+@pytest.mark.parametrize("C,H,W", [(128, 2, 70), (128, 4, 33), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 75),
+                                   (16, 64, 260), (8, 128, 130), (8, 128, 300), (8, 11, 16)])
+def test_stream_attention_equals_separate_kernels(C, H, W):
+    """dcs_attention_stream (bf16 path: x rows through a bulk-copy ring, 7x7 gate conv as TF32 mma.sync row-partials with
+    a register ring of pending rows) vs the chan_gate -> spat_stats -> spat_apply sequence with an fp32 output: every
+    layer geometry, ragged widths, several column strips, heights that are not a multiple of the 4-row unroll."""
+    from dcsnet_b200 import packing
+    sd = SW.make_state_dict(1)
+    i = {128: 0, 64: 3, 32: 4, 16: 5, 8: 6}[C]
+    ca = packing.pack_channel_attention(sd, f"skip_attention.{2 * i}.", "cuda")
+    w7 = packing.pack_spatial_attention(sd, f"skip_attention.{2 * i + 1}.", "cuda")
+    g = torch.Generator().manual_seed(C + H + W)
+    B = 3
+    x = torch.randn(B, H, W, C, 2, generator=g).cuda().to(torch.bfloat16)
+    sums = torch.zeros(B, C, 2, device="cuda")
+    ops.chan_pool(x, sums)
+    gate = torch.empty(B, C, 2, device="cuda")
+    stats = torch.empty(B, H * W, 4, device="cuda")
+    ref = torch.empty(B, H, W, C, 2, device="cuda")
+    ops.chan_gate(sums, H * W, ca, gate)
+    ops.spat_stats(x, gate, stats)
+    ops.spat_apply(x, gate, stats, w7, ref)
+    got = torch.full_like(x, float("nan"))
+    ops.attention_stream(x, sums, ca, w7, got)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got.float()).any()
+    # bf16 output rounding (half an ulp: up to 2^-8 of the largest element) + TF32 gate conv (~1e-4)
+    assert rel_err(got.float(), ref) <= 5e-3
+
+
 # ------------------------------------------------------------------ properties at BASELINE size (B=64 x 4 s)
 @pytest.mark.parametrize("mode,tol", [("fp32", TOL_FP32), ("bf16", 5e-3)])
 def test_full_size_batch_subset_vs_oracle_and_batch_independence(mode, tol):

@@ -166,6 +166,50 @@ def part_stripunit(B, T):
         print(json.dumps(res), flush=True)
 
 
+def part_attn(B, T):
+    """Streaming attention kernel vs the separate stats/apply kernels on every attended-tensor geometry: parity + time."""
+    sd = SW.make_state_dict(1)
+    F = 256
+    shapes = [(8, F // 2, T // 2), (16, F // 4, T // 4), (32, F // 8, T // 8), (64, F // 16, T // 8), (128, F // 32, T // 8),
+              (128, F // 64, T // 8), (128, F // 128, T // 8)]
+    for C, H, W in shapes:
+        i = {128: 0, 64: 3, 32: 4, 16: 5, 8: 6}[C]
+        ca = packing.pack_channel_attention(sd, f"skip_attention.{2 * i}.", "cuda")
+        w7 = packing.pack_spatial_attention(sd, f"skip_attention.{2 * i + 1}.", "cuda")
+        g = torch.Generator().manual_seed(C + H)
+        x = torch.randn(B, H, W, C, 2, generator=g).to(torch.bfloat16).cuda()
+        sums = torch.zeros(B, C, 2, device="cuda")
+        ops.chan_pool(x, sums)
+        gate = torch.empty(B, C, 2, device="cuda")
+        stats = torch.empty(B, H * W, 4, device="cuda")
+        ref = torch.empty(B, H, W, C, 2, device="cuda")
+        ref16 = torch.empty_like(x)
+        got = torch.full_like(x, float("nan"))
+
+        def sep(out):
+            ops.spat_stats(x, None, stats, sums=sums, ca=ca, gate_out=gate)
+            ops.spat_apply(x, gate, stats, w7, out)
+        sep(ref)
+        ops.attention_stream(x, sums, ca, w7, got)
+        torch.cuda.synchronize()
+        nan = int(torch.isnan(got.float()).sum())
+        r = float((got.float() - ref).abs().max() / ref.abs().max())
+
+        def timeit(fn, n=5):
+            fn(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        ms_s = timeit(lambda: ops.attention_stream(x, sums, ca, w7, got))
+        ms_r = timeit(lambda: sep(ref16))
+        mb = x.numel() * 2 / 1e6
+        print(json.dumps({"part": "attn", "C": C, "H": H, "W": W, "rel": r, "nan": nan, "ms_stream": round(ms_s, 4),
+                          "ms_separate": round(ms_r, 4), "GBps_stream": round(2 * mb / ms_s, 1)}), flush=True)
+
+
 def part_layers(B, T):
     """per-layer timing of the tcgen05 conv (and the FFMA layers) at full size"""
     sd = SW.make_state_dict(0)
@@ -296,6 +340,8 @@ if __name__ == "__main__":
         part_net(part, B, T)
     elif part == "tcunit":
         part_tcunit(B, T)
+    elif part == "attn":
+        part_attn(B, T)
     elif part == "stripunit":
         part_stripunit(B, T)
     elif part == "layers":
