@@ -268,6 +268,20 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_kernel(const float* __
 //   exchange.  Lanes with l%4 >= 2 (padding columns) take over the odd sequence of lane l-2 (4 shuffles): one cell per
 //   thread.  W_hh lives in registers in A-fragment order (w_hh_frag, packed + tf32-rounded by the host); h is kept in
 //   shared memory, tf32-rounded, in a K order that makes a lane's 16 B-fragment values contiguous (4 LDS.128).
+// bare MUFU.EX2 / MUFU.RCP forms (no range fix-up code): sigmoid = 1 / (1 + 2^(-x log2 e)), tanh = 2 sigmoid(2x) - 1;
+// abs. error ~3e-7; 2^(+big) = inf -> rcp = 0, 2^(-big) = 0 -> 1: both limits are exact
+__device__ __forceinline__ float sigmoid_mufu(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+__device__ __forceinline__ float tanh_mufu(float v) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * v));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return 2.f * r - 1.f;
+}
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -326,69 +340,74 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma_kernel(const float
   if (tid < 32)
     for (int blk = 0; blk < min(kStg, n_blocks); ++blk) issue_block(blk);
 
-  for (int step = 0; step < S; ++step) {
-    const int t = dir ? S - 1 - step : step;
-    const int cur = step & 1;
-    const int blk = step / kBlk, stage = blk % kStg;
-    const int s0 = blk * kBlk, nbk = min(kBlk, S - s0);
-    const int t_lo = dir ? S - s0 - nbk : s0;
-    // B fragments: h of sequence nb, this lane's 16 k values (k = 8 ks + l4 + 4 half  <->  position l4*16 + 2 ks + half)
-    uint4 hb[4];
-    if (nb < 4) {
-      const uint4* hp = reinterpret_cast<const uint4*>(&hs[cur][nb][l4 * 16]);
+  // One block of kBlk steps per ring stage; inside a block every address advances by a constant per step (no divisions,
+  // no index arithmetic on the serial path: the recurrence is bound by the length of a warp's own instruction stream).
+  const int hstep = dir ? -2 * kH : 2 * kH, pstep = dir ? -kG : kG;
+  hq += (int64_t)(dir ? S - 1 : 0) * (2 * kH);
+  const uint4* hrd = reinterpret_cast<const uint4*>(&hs[0][nb < 4 ? nb : 0][l4 * 16]);   // + cur * 4 * kH floats
+  uint32_t* hwr = reinterpret_cast<uint32_t*>(&hs[0][seq][0]) + hpos;                     // + (cur ^ 1) * 4 * kH
+  int cur = 0, stage = 0;
+  uint32_t phase = 0;
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const int nbk = min(kBlk, S - blk * kBlk);
+    mbar_wait(smem_u32(&full_bar[stage]), phase);
+    const float* pr = pre_s + (stage * 4 + seq) * kSeqPitch + (dir ? (nbk - 1) * kG : 0) + u;
+    for (int r = 0; r < nbk; ++r) {
+      // B fragments: h of sequence nb, this lane's 16 k values (k = 8 ks + l4 + 4 half  <->  position l4*16 + 2 ks + half)
+      uint4 hb[4];
+      if (nb < 4) {
+        const uint4* hp = hrd + cur * (4 * kH / 4);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) hb[i] = hp[i];
-    } else {
+        for (int i = 0; i < 4; ++i) hb[i] = hp[i];
+      } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) hb[i] = make_uint4(0, 0, 0, 0);
-    }
-    if (step == s0) mbar_wait(smem_u32(&full_bar[stage]), (uint32_t)((blk / kStg) & 1));
-    float pcur[4];
-    {
-      const float* pr = pre_s + (stage * 4 + seq) * kSeqPitch + (t - t_lo) * kG + u;
+        for (int i = 0; i < 4; ++i) hb[i] = make_uint4(0, 0, 0, 0);
+      }
+      float pcur[4];
 #pragma unroll
       for (int g = 0; g < 4; ++g) pcur[g] = pr[g * kH];
+      // two independent accumulation chains per tile (even / odd k steps) to halve the dependent-MMA latency
+      float d[2][2][4];
+#pragma unroll
+      for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[tl][c][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint4 hv = hb[ks >> 1];
+        const uint32_t b0 = (ks & 1) ? hv.z : hv.x, b1 = (ks & 1) ? hv.w : hv.y;
+        mma_tf32(d[0][ks & 1], af[0][ks], b0, b1);
+        mma_tf32(d[1][ks & 1], af[1][ks], b0, b1);
+      }
+      // fragment: [0],[1] = rows 0-7 (gate i resp. g) for sequences 2 l4, 2 l4 + 1; [2],[3] = rows 8-15 (gate f resp. o)
+      float gi[2], gf[2], gg[2], go[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        gi[e] = d[0][0][e] + d[0][1][e];
+        gf[e] = d[0][0][2 + e] + d[0][1][2 + e];
+        gg[e] = d[1][0][e] + d[1][1][e];
+        go[e] = d[1][0][2 + e] + d[1][1][2 + e];
+      }
+      // lanes l4 >= 2 hold padding columns: they take the odd sequence of lane l - 2
+      const int src = lane & ~2;
+      const float oi = __shfl_sync(0xffffffffu, gi[1], src), of = __shfl_sync(0xffffffffu, gf[1], src);
+      const float og_ = __shfl_sync(0xffffffffu, gg[1], src), oo = __shfl_sync(0xffffffffu, go[1], src);
+      const bool odd = l4 >= 2;
+      const float ri = (odd ? oi : gi[0]) + pcur[0], rf = (odd ? of : gf[0]) + pcur[1];
+      const float rg = (odd ? og_ : gg[0]) + pcur[2], ro = (odd ? oo : go[0]) + pcur[3];
+      const float ig = sigmoid_mufu(ri), fg = sigmoid_mufu(rf), gt = tanh_mufu(rg), ot = sigmoid_mufu(ro);
+      c_state = fg * c_state + ig * gt;
+      const float h = ot * tanh_mufu(c_state);
+      // tf32 operand for the next step: the tensor core ignores the low 13 mantissa bits, + half an ulp = round to nearest
+      hwr[(cur ^ 1) * (4 * kH)] = __float_as_uint(h) + 0x1000u;
+      *hq = h;
+      hq += hstep; pr += pstep; cur ^= 1;
+      __syncthreads();
     }
-    // two independent accumulation chains per tile (even / odd k steps) to halve the dependent-MMA latency
-    float d[2][2][4];
-#pragma unroll
-    for (int tl = 0; tl < 2; ++tl)
-#pragma unroll
-      for (int c = 0; c < 2; ++c)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) d[tl][c][j] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint4 hv = hb[ks >> 1];
-      const uint32_t b0 = (ks & 1) ? hv.z : hv.x, b1 = (ks & 1) ? hv.w : hv.y;
-      mma_tf32(d[0][ks & 1], af[0][ks], b0, b1);
-      mma_tf32(d[1][ks & 1], af[1][ks], b0, b1);
-    }
-    // fragment: [0],[1] = rows 0-7 (gate i resp. g) for sequences 2 l4, 2 l4 + 1; [2],[3] = rows 8-15 (gate f resp. o)
-    float gi[2], gf[2], gg[2], go[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      gi[e] = d[0][0][e] + d[0][1][e];
-      gf[e] = d[0][0][2 + e] + d[0][1][2 + e];
-      gg[e] = d[1][0][e] + d[1][1][e];
-      go[e] = d[1][0][2 + e] + d[1][1][2 + e];
-    }
-    // lanes l4 >= 2 hold padding columns: they take the odd sequence of lane l - 2
-    const int src = lane & ~2;
-    const float oi = __shfl_sync(0xffffffffu, gi[1], src), of = __shfl_sync(0xffffffffu, gf[1], src);
-    const float og_ = __shfl_sync(0xffffffffu, gg[1], src), oo = __shfl_sync(0xffffffffu, go[1], src);
-    const bool odd = l4 >= 2;
-    const float ri = (odd ? oi : gi[0]) + pcur[0], rf = (odd ? of : gf[0]) + pcur[1];
-    const float rg = (odd ? og_ : gg[0]) + pcur[2], ro = (odd ? oo : go[0]) + pcur[3];
-    const float ig = quick_sigmoid(ri), fg = quick_sigmoid(rf), gt = quick_tanh(rg), ot = quick_sigmoid(ro);
-    c_state = fg * c_state + ig * gt;
-    const float h = ot * quick_tanh(c_state);
-    uint32_t h_tf32;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h_tf32) : "f"(h));
-    reinterpret_cast<uint32_t*>(&hs[cur ^ 1][seq][0])[hpos] = h_tf32;
-    hq[(int64_t)t * (2 * kH)] = h;
-    __syncthreads();
-    if (tid < 32 && step == s0 + nbk - 1 && blk + kStg < n_blocks) issue_block(blk + kStg);
+    if (tid < 32 && blk + kStg < n_blocks) issue_block(blk + kStg);
+    if (++stage == kStg) { stage = 0; phase ^= 1; }
   }
 }
 

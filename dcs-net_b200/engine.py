@@ -145,7 +145,7 @@ class ForwardPlan:
         # the skip attentions depend only on encoder outputs, so they can run on a side stream concurrently with the
         # ComplexLSTM + fc (fork / join is captured into the CUDA graph as parallel branches).  Measured on B200 at
         # batch 64 x 4 s: no gain (9.73 vs 9.72 ms) — the recurrence is issue-bound on 128 SMs, so it stays off.
-        self.overlap = False
+        self.overlap = os.environ.get("DCS_OVERLAP", "0") == "1"
         # channel gate + spatial statistics + 7x7 gate conv + product in one kernel per attended tensor
         # (opt-in with DCS_FUSED_ATTENTION=1: measured slower than the three separate kernels on B200 — its load / stats / conv /
         # apply phases serialise inside a CTA; kept for the next round's TMA-pipelined version)
@@ -213,7 +213,7 @@ class ForwardPlan:
         # still in the 126 MB L2 (tensors that fit), instead of re-reading it from HBM in the decoder loop.
         mode = os.environ.get("DCS_EARLY_SKIP", "auto")
         limit = {"0": -1, "1": 1 << 62}.get(mode, 80 << 20)
-        early = lambda e: (not self.overlap) and self.enc[e].numel() * self.enc[e].element_size() <= limit
+        early = lambda e: self.enc[e].numel() * self.enc[e].element_size() <= limit
         for i in range(Lr):
             if i == 0 and strip0 is not None:
                 x = ops.cconv_strip(strip0, packing.StripEnc0.view_src(self.bn0), None, self.enc[0],
@@ -229,21 +229,33 @@ class ForwardPlan:
         B, H, W, _, _ = x.shape
 
         main = torch.cuda.current_stream()
-        if self.overlap:
+        # The attentions of the large (not L2-resident) skip tensors depend only on encoder outputs: with `overlap` they
+        # run on a side stream next to the latency-bound ComplexLSTM recurrence (one CTA per SM, ~30 % of the issue
+        # slots) and join before their decoder stage.  Needs the streaming attention (no shared scratch buffers).
+        late = [i for i in range(Lr) if not early(Lr - 1 - i)]
+        side_run = self.overlap and self.stream_attention and bool(late)
+        if side_run:
             self.side.wait_stream(main)
             with torch.cuda.stream(self.side):
-                for i in range(Lr):
+                for i in late:
                     skip_attention(i)
         ops.clstm(x.view(B, H * W, x.shape[3], 2), self.lat.view(B, H * W, 128, 2), pk.lstm, self.lstm_ws, use_tc=self.tc,
-                  seqs_per_cta=4 if self.overlap else 0)
+                  seqs_per_cta=0)
         self._tap("lstm", self.lat)
         self._conv(pk.fc, self.lat.view(B, 1, H * W, 128, 2), None, self.fc.view(B, 1, H * W, 128, 2))
         d = self.fc
         self._tap("fc", d)
-        if self.overlap:
-            main.wait_stream(self.side)
+        joined = False
         for i in range(Lr):
-            skip = self.skip[i] if (self.overlap or early(Lr - 1 - i)) else skip_attention(i)
+            if early(Lr - 1 - i):
+                skip = self.skip[i]
+            elif side_run:
+                if not joined:
+                    main.wait_stream(self.side)
+                    joined = True
+                skip = self.skip[i]
+            else:
+                skip = skip_attention(i)
             self._tap(f"skip{i}", skip)
             if i == Lr - 1:
                 return d, skip  # decoder[6] is fused with the mask tail (dcs_dec6_tail_fwd)
