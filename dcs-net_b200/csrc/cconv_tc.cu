@@ -53,6 +53,7 @@ struct TcArgs {
   unsigned long long* dbg;    // optional per-CTA wait-cycle counters (dcs_tc_set_debug_buffer), 8 words per CTA
 };
 
+constexpr int kEpiStagePayload = 2560, kEpiStageBytes = kEpiStagePayload + 32 * 8;  // per epilogue warp: transpose tile + row table
 constexpr int kMaxAcc = 4;  // accumulator stages in TMEM: 4 when 4*n_pad <= 256 columns, else 2
 
 // Division-free walk over this CTA's tiles: tile = ((phase*tiles_b + bt)*tiles_h + ht)*tiles_w + wt, advanced by a
@@ -76,10 +77,10 @@ struct TileIter {
   }
 };
 
-struct __align__(8) TcBarriers {
+struct __align__(16) TcBarriers {
+  float bias[256];            // first: 16-byte aligned for the epilogue's vector loads
   uint64_t full[kMaxStages], empty[kMaxStages], acc_full[kMaxAcc], acc_empty[kMaxAcc];
   uint32_t tmem_base;
-  float bias[256];
 };
 
 __global__ void __launch_bounds__(kTcThreads, 1)
@@ -284,6 +285,14 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const int ncols = split ? a.n_pad / 2 : a.n_pad;
     const int col0 = split ? set * ncols : 0;
     const bool active = tile_split || split || set == 0;
+    // Coalescing stage of this warp (after the barriers): the TMEM layout gives a lane one tile ROW (= one pixel, whose
+    // channels are contiguous in HBM), so direct stores put the 32 lanes of every store instruction into 32 different
+    // lines, 16 bytes each — 8192 partial-sector requests per 128 x 256 fp32 tile, ~2 cycles each (measured with the
+    // role counters: 17 k cycles of epilogue per tile against 2 k cycles of MMA for the LSTM projections).  Instead a
+    // warp transposes through 2.5 KB of shared memory so that a store instruction writes whole 64 / 128-byte row pieces.
+    unsigned char* est = reinterpret_cast<unsigned char*>(bars + 1) + ew * kEpiStageBytes;
+    const uint32_t est_u32 = smem_u32(est);
+    long long* pixs = reinterpret_cast<long long*>(est + kEpiStagePayload);
     const int m = quad * 32 + lane;                  // tile row = TMEM lane
     const int cc = m & (a.TW - 1), rr = (m >> a.tw_log2) & (a.TH - 1), nb = m >> (a.tw_log2 + a.th_log2);
     const bool warp_uniform_image = ((a.TH * a.TW) % 32) == 0;
@@ -305,6 +314,19 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int ph_h = a.up_w == 2 ? (ph_idx >> 1) : ph_idx, ph_w = a.up_w == 2 ? (ph_idx & 1) : 0;
         const int oy = j * a.up_h + ph_h, ox = i * a.up_w + ph_w;
         const int64_t pix = ((int64_t)b * a.out_h + oy) * a.out_w + ox;
+        // output pixel of every row of this warp's quadrant (-1: outside the tensor), for the lanes that store the row
+        __syncwarp();
+        pixs[lane] = valid ? (long long)pix : -1ll;   // (pix is computed for every lane; `valid` masks rows outside the tensor)
+        __syncwarp();
+        // element offset of the rows this lane STORES: fp32 rows (lane >> 3) + 4 j (two 16-row passes, j < 8),
+        // bf16 rows (lane >> 2) + 8 j (j < 4)
+        long long prow[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = a.out_f32 ? (lane >> 3) + 4 * j : (lane >> 2) + 8 * (j & 3);
+          const long long pv = pixs[r];
+          prow[j] = pv < 0 ? -1ll : pv * a.n_real;
+        }
         mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase, dwe);
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * (uint32_t)a.n_pad + (uint32_t)col0;
@@ -315,17 +337,86 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc_ld16(taddr + (uint32_t)c, rg0);
           if (nblk == 32) tc_ld16(taddr + (uint32_t)c + 16, rg1);
           tc_ld_wait();
+          // bias (vector loads) + activation; the activation is selected once per block (the epilogue is bound by its own
+          // instruction stream: a per-value runtime switch cost ~8 instructions per accumulator element)
           float v[32];
+          {
+            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0);
 #pragma unroll
-          for (int q = 0; q < 16; ++q) v[q] = act_apply(__uint_as_float(rg0[q]) + bias_s[n0 + q], a.act);
-          if (nblk == 32) {
+            for (int q = 0; q < 4; ++q) {
+              const float4 bb = b4[q];
+              v[4 * q] = __uint_as_float(rg0[4 * q]) + bb.x; v[4 * q + 1] = __uint_as_float(rg0[4 * q + 1]) + bb.y;
+              v[4 * q + 2] = __uint_as_float(rg0[4 * q + 2]) + bb.z; v[4 * q + 3] = __uint_as_float(rg0[4 * q + 3]) + bb.w;
+            }
+            if (nblk == 32) {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[16 + q] = act_apply(__uint_as_float(rg1[q]) + bias_s[n0 + 16 + q], a.act);
-          } else {
+              for (int q = 0; q < 4; ++q) {
+                const float4 bb = b4[4 + q];
+                v[16 + 4 * q] = __uint_as_float(rg1[4 * q]) + bb.x; v[16 + 4 * q + 1] = __uint_as_float(rg1[4 * q + 1]) + bb.y;
+                v[16 + 4 * q + 2] = __uint_as_float(rg1[4 * q + 2]) + bb.z; v[16 + 4 * q + 3] = __uint_as_float(rg1[4 * q + 3]) + bb.w;
+              }
+            } else {
 #pragma unroll
-            for (int q = 0; q < 16; ++q) v[16 + q] = 0.f;
+              for (int q = 0; q < 16; ++q) v[16 + q] = 0.f;
+            }
+            if (a.act == DCS_ACT_RELU) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.f);
+            } else if (a.act == DCS_ACT_LRELU) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = fmaxf(v[q], 0.01f * v[q]);     // = v > 0 ? v : 0.01 v
+            } else if (a.act == DCS_ACT_SIGMOID) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) v[q] = sigmoidf_(v[q]);
+            }
           }
-          if (valid) {
+          if (nblk == 32 && n0 + 32 <= a.n_real) {
+            if (a.out_f32) {
+              // two passes of 16 rows x 128 bytes (pitch 144): a store instruction writes 4 rows x one full 128-byte line
+              float* ob = reinterpret_cast<float*>(a.dst) + n0 + (lane & 7) * 4;
+#pragma unroll
+              for (int pass = 0; pass < 2; ++pass) {
+                if ((lane >> 4) == pass) {
+                  const uint32_t wr = est_u32 + (uint32_t)(lane & 15) * 144u;
+#pragma unroll
+                  for (int q = 0; q < 8; ++q)
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(wr + q * 16), "f"(v[4 * q]), "f"(v[4 * q + 1]), "f"(v[4 * q + 2]), "f"(v[4 * q + 3]) : "memory");
+                }
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                  float4 t;
+                  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
+                               : "r"(est_u32 + (uint32_t)((lane >> 3) + 4 * i) * 144u + (uint32_t)(lane & 7) * 16u));
+                  const long long pr = prow[4 * pass + i];
+                  if (pr >= 0) *reinterpret_cast<float4*>(ob + pr) = t;
+                }
+                __syncwarp();
+              }
+            } else {
+              // 32 rows x 64 bytes (pitch 80): a store instruction writes 8 rows x 64 contiguous bytes
+              uint32_t pk[16];
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+                pk[q] = *reinterpret_cast<uint32_t*>(&t);
+              }
+              const uint32_t wr = est_u32 + (uint32_t)lane * 80u;
+#pragma unroll
+              for (int q = 0; q < 4; ++q)
+                asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(wr + q * 16), "r"(pk[4 * q]), "r"(pk[4 * q + 1]), "r"(pk[4 * q + 2]), "r"(pk[4 * q + 3]) : "memory");
+              __syncwarp();
+              __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(a.dst) + n0 + (lane & 3) * 8;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                uint4 t;
+                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
+                             : "r"(est_u32 + (uint32_t)((lane >> 2) + 8 * i) * 80u + (uint32_t)(lane & 3) * 16u));
+                if (prow[i] >= 0) *reinterpret_cast<uint4*>(ob + prow[i]) = t;
+              }
+              __syncwarp();
+            }
+          } else if (valid) {
             if (a.out_f32) {
               float* o = reinterpret_cast<float*>(a.dst) + pix * a.n_real + n0;
               if (n0 + nblk <= a.n_real) {
@@ -529,7 +620,7 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   int n_stages = (int)((200 * 1024) / stage_bytes);
   n_stages = std::max(2, std::min(n_stages, kMaxStages));
   a.n_stages = n_stages;
-  const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers);
+  const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers) + 8 * kEpiStageBytes;
 
   CUtensorMap tmA0, tmA1, tmB;
   if (int e = make_weight_map(&tmB, p->weight, esz, a.ksteps * kstep_elems, a.phases * n_pad, n_pad)) return e;
