@@ -354,8 +354,23 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
               const int cl = 8 * s8 + q;
-              v[q] = act_apply(__uint_as_float(rg[cl / 16][cl % 16]) + bias_col[ch * kChunk + cl], a.act);
-              if (valid) pool_acc[cl] += v[q];
+              v[q] = __uint_as_float(rg[cl / 16][cl % 16]) + bias_col[ch * kChunk + cl];
+            }
+            // activation selected once per group (a per-value runtime switch is ~8 instructions per accumulator element,
+            // and the epilogue is bound by its own instruction stream)
+            if (a.act == DCS_ACT_RELU) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.f);
+            } else if (a.act == DCS_ACT_LRELU) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = fmaxf(v[q], 0.01f * v[q]);
+            } else if (a.act == DCS_ACT_SIGMOID) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) v[q] = sigmoidf_(v[q]);
+            }
+            if (valid) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) pool_acc[8 * s8 + q] += v[q];
             }
             if (valid) {
               const int c0 = ch * kChunk + 8 * s8, run = c0 >> a.run_log2, off = c0 & (run_len - 1);
