@@ -23,6 +23,10 @@ constexpr int kChunk = 16;        // frames per CTA iteration (one per half-warp
 constexpr int kThreads = 256;
 constexpr int kTrStride = 17;     // padded row of the 16x16 transpose tile (float2 units)
 constexpr int kStStride = 17;     // padded row of the [bin][frame] staging tile (float2 units)
+// One buffer per half-warp (= per frame of a chunk) serves, in turn, as the 16 x 17 transpose tile of its FFT and as the
+// frame's 256 spectrum / 512 time samples: 273 float2 (odd multiple of 2 words -> the 16 frames start in different banks).
+// Shared memory per CTA drops from 80 / 112 KB to 45 KB, i.e. from 2 to 4-5 resident CTAs per SM.
+constexpr int kBufPitch = 273;
 
 __device__ __forceinline__ float2 f2add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
 __device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
@@ -114,12 +118,11 @@ __device__ __forceinline__ void init_tables(FftTables* t) {
 struct StftSmem {
   FftTables tab;
   float x[(kChunk - 1) * kHop + kNfft];             // 992 samples feeding 16 frames
-  float2 tr[kChunk][16 * kTrStride];
-  float2 stage[kBins][kStStride];
+  float2 buf[kChunk][kBufPitch];                    // per frame: transpose tile, then Z[0..255]
 };
 
 template <typename TBN>
-__global__ void __launch_bounds__(kThreads) stft_kernel(const float* __restrict__ audio, float2* __restrict__ spec,
+__global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restrict__ audio, float2* __restrict__ spec,
                                                         int L, int T, int chunks_per_cta,
                                                         const float* __restrict__ bn_affine, TBN* __restrict__ bn_out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -158,9 +161,9 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(const float* __restrict_
         const float2 ws = *reinterpret_cast<const float2*>(sm.tab.win + 2 * n);
         v[r] = make_float2(xs.x * ws.x, xs.y * ws.y);
       }
-      fft256_halfwarp<false>(v, l, sm.tr[h], sm.tab.tw256);
+      fft256_halfwarp<false>(v, l, sm.buf[h], sm.tab.tw256);
 #pragma unroll
-      for (int k2 = 0; k2 < 16; ++k2) sm.stage[l + 16 * k2][h] = v[k2];
+      for (int k2 = 0; k2 < 16; ++k2) sm.buf[h][l + 16 * k2] = v[k2];   // (every lane has left the transpose tile: __syncwarp inside)
     }
     __syncthreads();
     // real-FFT post-processing + transposed store: thread (f = tid&15, k rows tid>>4 + 16*i)
@@ -172,13 +175,13 @@ __global__ void __launch_bounds__(kThreads) stft_kernel(const float* __restrict_
           const int k = 1 + (tid >> 4) + 16 * i;  // output bin 1..256
           float2 X;
           if (k < 256) {
-            const float2 zk = sm.stage[k][f], zm = sm.stage[256 - k][f];
+            const float2 zk = sm.buf[f][k], zm = sm.buf[f][256 - k];
             const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
             const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));  // (zk - conj zm)/(2j)
             const float2 w = sm.tab.tw512[k];  // e^{-i th} = (cos, -sin)
             X = make_float2(E.x + O.x * w.x + O.y * w.y, E.y + O.y * w.x - O.x * w.y);
           } else {
-            const float2 z0 = sm.stage[0][f];
+            const float2 z0 = sm.buf[f][0];
             X = make_float2(z0.x - z0.y, 0.f);
           }
           X.x *= scale; X.y *= scale;
@@ -197,10 +200,9 @@ __host__ __device__ inline int istft_chunks(int T) { return (T + 7 + kChunk - 1)
 
 struct IstftSmem {
   FftTables tab;
-  float2 tr[kChunk][16 * kTrStride];
-  float2 stage[kBins][kStStride];
-  float fr[kChunk][kNfft];
+  float2 buf[kChunk][kBufPitch];   // per frame: X[0..255] -> transpose tile -> 512 windowed time samples
   float acc[2 * kNfft];
+  float env32[kHop];               // overlap-add envelope of an interior sample (depends on n mod 32 only)
 };
 
 // polar round trip of network_functions.py:398-401 + 140-142: (|s| cos(th), |s| sin(th)), th = atan2(im, re+eps)
@@ -217,7 +219,7 @@ __device__ __forceinline__ float2 polar_roundtrip(float2 s, float eps, bool exac
   return make_float2(xr * inv, s.y * inv);
 }
 
-__global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restrict__ spec, const float* __restrict__ mag,
+__global__ void __launch_bounds__(kThreads, 3) istft_kernel(const float2* __restrict__ spec, const float* __restrict__ mag,
                                                          const float* __restrict__ phase, float* __restrict__ audio,
                                                          int T, int chunks_per_cta, float eps, int exact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -231,6 +233,11 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
   const int Lout = kHop * (T - 1);
   init_tables(&sm.tab);
   for (int i = tid; i < 2 * kNfft; i += kThreads) sm.acc[i] = 0.f;
+  if (tid < kHop) {   // sum over the 16 frames covering a sample of hann^2 (recomputed: the table is not published yet)
+    float e = 0.f;
+    for (int j = 0; j < kNfft / kHop; ++j) { const float w = 0.5f - 0.5f * cospif((float)(tid + kHop * j) / 256.f); e += w * w; }
+    sm.env32[tid] = e;
+  }
   // unnormalised 256-pt inverse DFT with the 1/2 of the even/odd split already applied: remaining 1/256 of the
   // irfft, times sqrt(512) for normalized=True  ->  sqrt(512)/256
   const float scale = 0.08838834764831845f;
@@ -238,19 +245,7 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
   const float* mg = mag ? mag + (int64_t)b * kBins * T : nullptr;
   const float* phs = phase ? phase + (int64_t)b * kBins * T : nullptr;
 
-  // The spectrogram rows of chunk c+1 are fetched into registers while chunk c is transformed (one HBM round trip
-  // per chunk was fully exposed before: two CTAs per SM cannot hide it).
   const int f_ld = tid & 15, k_ld = tid >> 4;
-  float2 nx[16];
-  auto fetch = [&](int c) {
-    const int t = c * kChunk + f_ld;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      nx[i] = make_float2(0.f, 0.f);
-      if (t < T) nx[i] = __ldg(sp + (int64_t)(k_ld + 16 * i) * T + t);
-    }
-  };
-  if (sp) fetch(max(c_begin - 1, 0));
   for (int c = max(c_begin - 1, 0); c < c_end; ++c) {
     const bool emit = c >= c_begin;
     const int t0 = c * kChunk;
@@ -258,17 +253,21 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
     {  // stage [256 rfft rows][16 frames]; row k of the iSTFT input is spectrogram row k (zero row appended at 256)
       const int f = f_ld, t = t0 + f;
       if (sp) {
+        // 16 independent loads per thread (rows k_ld + 16 i of frame t), then the polar round trip; three resident CTAs
+        // per SM hide the HBM round trip (the register prefetch of the 2-CTA version cost 32 registers)
+        float2 nx[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) nx[i] = t < T ? __ldg(sp + (int64_t)(k_ld + 16 * i) * T + t) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          sm.stage[k_ld + 16 * i][f] = t < T ? polar_roundtrip(nx[i], eps, exact != 0) : make_float2(0.f, 0.f);
-        if (c + 1 < c_end) fetch(c + 1);
+          sm.buf[f][k_ld + 16 * i] = t < T ? polar_roundtrip(nx[i], eps, exact != 0) : make_float2(0.f, 0.f);
       } else {
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {
           const int k = k_ld + 16 * i;
           float2 s = make_float2(0.f, 0.f);
           if (t < T) { const float m_ = __ldg(mg + (int64_t)k * T + t), p_ = __ldg(phs + (int64_t)k * T + t); s = make_float2(m_ * cosf(p_), m_ * sinf(p_)); }
-          sm.stage[k][f] = s;
+          sm.buf[f][k] = s;
         }
       }
     }
@@ -278,18 +277,19 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const int k = 16 * r + l;
-        float2 xk = sm.stage[k][h];
+        float2 xk = sm.buf[h][k];
         float2 xm;
         if (k == 0) { xk.y = 0.f; xm = make_float2(0.f, 0.f); }  // C2R ignores Im X[0]; X[256] is the zero pad row
-        else { xm = sm.stage[256 - k][h]; xm.y = -xm.y; }
+        else { xm = sm.buf[h][256 - k]; xm.y = -xm.y; }
         const float2 E = make_float2(0.5f * (xk.x + xm.x), 0.5f * (xk.y + xm.y));
         const float2 D = make_float2(0.5f * (xk.x - xm.x), 0.5f * (xk.y - xm.y));
         const float2 w = sm.tab.tw512[k];  // e^{+i th}
         const float2 O = make_float2(D.x * w.x - D.y * w.y, D.x * w.y + D.y * w.x);
         v[r] = make_float2(E.x - O.y, E.y + O.x);  // E + j O
       }
-      fft256_halfwarp<true>(v, l, sm.tr[h], sm.tab.tw256);
-      float* fr = sm.fr[h];
+      __syncwarp();   // every lane has read its spectrum values: the buffer becomes the transpose tile
+      fft256_halfwarp<true>(v, l, sm.buf[h], sm.tab.tw256);
+      float* fr = reinterpret_cast<float*>(sm.buf[h]);
 #pragma unroll
       for (int k2 = 0; k2 < 16; ++k2) {
         const int m = l + 16 * k2;
@@ -306,7 +306,7 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
         float s = 0.f;
         const int h_hi = min(off / kHop, kChunk - 1);
         const int h_lo = max(0, (off - kNfft + kHop) / kHop);
-        for (int hh = h_lo; hh <= h_hi; ++hh) s += sm.fr[hh][off - kHop * hh];
+        for (int hh = h_lo; hh <= h_hi; ++hh) s += reinterpret_cast<const float*>(sm.buf[hh])[off - kHop * hh];
         const int ring = (c * kNfft + off) & (2 * kNfft - 1);
         const float a = sm.acc[ring] + s;
         if (q < 2) {
@@ -315,8 +315,13 @@ __global__ void __launch_bounds__(kThreads) istft_kernel(const float2* __restric
           if (emit && n >= 0 && n < Lout) {
             const int t_hi = min(T - 1, np / kHop);
             const int t_lo = max(0, (np - kNfft + kHop) / kHop);
-            float env = 0.f;
-            for (int t = t_lo; t <= t_hi; ++t) { const float w = sm.tab.win[np - kHop * t]; env += w * w; }
+            float env;
+            if (t_hi - t_lo == kNfft / kHop - 1) {
+              env = sm.env32[np & (kHop - 1)];      // interior sample: all 16 covering frames exist
+            } else {
+              env = 0.f;
+              for (int t = t_lo; t <= t_hi; ++t) { const float w = sm.tab.win[np - kHop * t]; env += w * w; }
+            }
             audio[(int64_t)b * Lout + n] = a / env;
           }
           sm.acc[ring] = 0.f;
