@@ -11,6 +11,8 @@
 // The recurrence is latency-bound (S = 2*T/8 sequential steps); it is reported separately from both rooflines.
 #include <string.h>
 #include <algorithm>
+#include <stdlib.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -411,6 +413,147 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma_kernel(const float
   }
 }
 
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// fp16 variant of the tensor-core recurrence: W_hh and h as fp16 (11-bit significands, like tf32; |h| < 1, |W_hh| small:
+// no range issue), m16n8k16 -> 8 instead of 16 MMAs per warp and step (the legacy tensor pipe was ~275 of the ~970
+// cycles of a step), two LDS.128 instead of four for the h fragments, 32 instead of 64 weight registers.
+__global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const float* __restrict__ pre0, int64_t stride_lstm,
+                                                                     int64_t stride_dir, int ld, const float* __restrict__ whh,
+                                                                     float* __restrict__ hout, int B, int S) {
+  __shared__ __align__(16) __half hs[2][4][kH];    // [buffer][sequence][permuted k], fp16
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const int q0 = blockIdx.x * 4;
+  const int lstm = q0 / (2 * B);
+  // A fragments of m16n8k16 (fp16: the same 11-bit significand as tf32, half the MMAs), built from the fp32 W_hh
+  // (4H x H, gate-major rows) of this (lstm, dir): tile tl rows 0-7 / 8-15 = gates (i, f) resp. (g, o) of units 8w..8w+7;
+  // register r of k-step ks holds columns 16 ks + 2 t + 8 (r >> 1) + {0, 1} of row (lane >> 2) + 8 (r & 1).
+  uint32_t af[2][4][4];
+  {
+    const float* wm = whh + (int64_t)(lstm * 2 + dir) * kG * kH;
+    const int t = lane & 3, g8 = lane >> 2;
+#pragma unroll
+    for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int gate = 2 * tl + (r & 1);
+          const float* wr = wm + (int64_t)(gate * kH + 8 * warp + g8) * kH + 16 * ks + 2 * t + 8 * (r >> 1);
+          const __half2 hv = __floats2half2_rn(__ldg(wr), __ldg(wr + 1));
+          af[tl][ks][r] = *reinterpret_cast<const uint32_t*>(&hv);
+        }
+  }
+  const int u = 8 * warp + (lane >> 2);                                   // this thread's hidden unit
+  const int l4 = lane & 3;
+  const int seq = l4 < 2 ? 2 * l4 : 2 * (l4 - 2) + 1;                     // this thread's cell: (u, seq)
+  const int nb = lane >> 2;                                               // B-fragment column = sequence (real if < 4)
+  // logical k = u = 16 ks + kk lives at half position t * 16 + ks * 4 + j with t = (kk & 7) >> 1, j = (kk & 1) + 2 (kk >> 3):
+  // a lane's B values of all four k-steps are 16 consecutive halves (two LDS.128)
+  const int hpos = (((u & 7) >> 1) * 16) + ((u >> 4) * 4) + (u & 1) + 2 * ((u >> 3) & 1);
+  float* hq = hout + (int64_t)(q0 + seq) * S * (2 * kH) + dir * kH + u;
+  float c_state = 0.f;
+  for (int i = tid; i < 2 * 4 * kH; i += 256) (&hs[0][0][0])[i] = __float2half_rn(0.f);
+
+  constexpr int kBlk = 8, kStg = 3, kSeqPitch = kBlk * kG + 8;
+  extern __shared__ __align__(16) float pre_s[];                          // [kStg][4][kSeqPitch]
+  __shared__ uint64_t full_bar[kStg];
+  const int n_blocks = (S + kBlk - 1) / kBlk;
+  const float* pre_cta = pre0 + lstm * stride_lstm + dir * stride_dir;
+  auto issue_block = [&](int blk) {
+    const int s0 = blk * kBlk, n = min(kBlk, S - s0);
+    const int t_lo = dir ? S - s0 - n : s0;
+    const uint32_t bar = smem_u32(&full_bar[blk % kStg]);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * 4 * kG * sizeof(float)));
+    __syncwarp();
+    if (lane < 4 * n) {
+      const int sq = lane / n, r = lane - sq * n;
+      const int pbq = (q0 + sq) % (2 * B);
+      bulk_g2s(smem_u32(pre_s + ((blk % kStg) * 4 + sq) * kSeqPitch + r * kG), pre_cta + ((int64_t)pbq * S + t_lo + r) * ld,
+               (uint32_t)(kG * sizeof(float)), bar);
+    }
+  };
+  if (tid == 0) {
+    for (int i = 0; i < kStg; ++i) mbar_init(smem_u32(&full_bar[i]), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 32)
+    for (int blk = 0; blk < min(kStg, n_blocks); ++blk) issue_block(blk);
+
+  // One block of kBlk steps per ring stage; inside a block every address advances by a constant per step (no divisions,
+  // no index arithmetic on the serial path: the recurrence is bound by the length of a warp's own instruction stream).
+  const int hstep = dir ? -2 * kH : 2 * kH, pstep = dir ? -kG : kG;
+  hq += (int64_t)(dir ? S - 1 : 0) * (2 * kH);
+  const uint4* hrd = reinterpret_cast<const uint4*>(&hs[0][nb < 4 ? nb : 0][l4 * 16]);   // + cur * 4 * kH halves
+  __half* hwr = &hs[0][seq][0] + hpos;                                                    // + (cur ^ 1) * 4 * kH
+  int cur = 0, stage = 0;
+  uint32_t phase = 0;
+  for (int blk = 0; blk < n_blocks; ++blk) {
+    const int nbk = min(kBlk, S - blk * kBlk);
+    mbar_wait(smem_u32(&full_bar[stage]), phase);
+    const float* pr = pre_s + (stage * 4 + seq) * kSeqPitch + (dir ? (nbk - 1) * kG : 0) + u;
+    for (int r = 0; r < nbk; ++r) {
+      // B fragments: h of sequence nb, this lane's 16 k values (k = 8 ks + l4 + 4 half  <->  position l4*16 + 2 ks + half)
+      uint4 hb[2];
+      if (nb < 4) {
+        const uint4* hp = hrd + cur * (4 * kH / 8);
+        hb[0] = hp[0]; hb[1] = hp[1];
+      } else {
+        hb[0] = make_uint4(0, 0, 0, 0); hb[1] = make_uint4(0, 0, 0, 0);
+      }
+      float pcur[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g) pcur[g] = pr[g * kH];
+      // two independent accumulation chains per tile (even / odd k steps)
+      float d[2][2][4];
+#pragma unroll
+      for (int tl = 0; tl < 2; ++tl)
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) d[tl][c][j] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        const uint4 hv = hb[ks >> 1];
+        const uint32_t b0 = (ks & 1) ? hv.z : hv.x, b1 = (ks & 1) ? hv.w : hv.y;
+        mma_f16(d[0][ks & 1], af[0][ks], b0, b1);
+        mma_f16(d[1][ks & 1], af[1][ks], b0, b1);
+      }
+      // fragment: [0],[1] = rows 0-7 (gate i resp. g) for sequences 2 l4, 2 l4 + 1; [2],[3] = rows 8-15 (gate f resp. o)
+      float gi[2], gf[2], gg[2], go[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        gi[e] = d[0][0][e] + d[0][1][e];
+        gf[e] = d[0][0][2 + e] + d[0][1][2 + e];
+        gg[e] = d[1][0][e] + d[1][1][e];
+        go[e] = d[1][0][2 + e] + d[1][1][2 + e];
+      }
+      // lanes l4 >= 2 hold padding columns: they take the odd sequence of lane l - 2
+      const int src = lane & ~2;
+      const float oi = __shfl_sync(0xffffffffu, gi[1], src), of = __shfl_sync(0xffffffffu, gf[1], src);
+      const float og_ = __shfl_sync(0xffffffffu, gg[1], src), oo = __shfl_sync(0xffffffffu, go[1], src);
+      const bool odd = l4 >= 2;
+      const float ri = (odd ? oi : gi[0]) + pcur[0], rf = (odd ? of : gf[0]) + pcur[1];
+      const float rg = (odd ? og_ : gg[0]) + pcur[2], ro = (odd ? oo : go[0]) + pcur[3];
+      const float ig = sigmoid_mufu(ri), fg = sigmoid_mufu(rf), gt = tanh_mufu(rg), ot = sigmoid_mufu(ro);
+      c_state = fg * c_state + ig * gt;
+      const float h = ot * tanh_mufu(c_state);
+      hwr[(cur ^ 1) * (4 * kH)] = __float2half_rn(h);
+      *hq = h;
+      hq += hstep; pr += pstep; cur ^= 1;
+      __syncthreads();
+    }
+    if (tid < 32 && blk + kStg < n_blocks) issue_block(blk + kStg);
+    if (++stage == kStg) { stage = 0; phase ^= 1; }
+  }
+}
+
 __global__ void lstm_combine_kernel(const float* __restrict__ h1, float2* __restrict__ y, int64_t n_per_q4) {
   // h1: [lstm][part][B*S*2H];  out.re = R(re) - I(im), out.im = R(im) + I(re)
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n_per_q4; i += (int64_t)gridDim.x * blockDim.x) {
@@ -448,7 +591,11 @@ static int gemm_rows(const float* a, int64_t rows, int K, const float* w, const 
 static void launch_rec(int nseq, const float* pre, int64_t stride_lstm, int64_t stride_dir, int ld, const float* whh,
                        float* hout, int B, int S, cudaStream_t s, const float* whh_frag = nullptr) {
   dim3 grid(4 * B / nseq, 2);
-  if (nseq == 4 && whh_frag) {
+  static const bool tf32_rec = getenv("DCS_LSTM_TF32") && atoi(getenv("DCS_LSTM_TF32")) != 0;   // A/B switch (default: fp16 MMAs)
+  if (nseq == 4 && whh_frag && !tf32_rec) {
+    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
+    lstm_recurrent4_mma16_kernel<<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+  } else if (nseq == 4 && whh_frag) {
     cudaFuncSetAttribute(lstm_recurrent4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
     lstm_recurrent4_mma_kernel<<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh_frag, hout, B, S);
   } else if (nseq == 4) {
