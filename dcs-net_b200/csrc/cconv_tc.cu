@@ -179,12 +179,10 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       // Descriptors = constant high word + (start address >> 4) in the low word; per-MMA byte offsets inside a stage
       // are precomputed once so the issue loop is a handful of 32-bit adds per MMA (single latency-exposed thread).
       const uint64_t a_desc0 = umma_desc(0, a_row_bytes), b_desc0 = umma_desc(0, 128);
-      uint32_t a_off[kKStepBytes / 32];
-#pragma unroll
-      for (int i = 0; i < kKStepBytes / 32; ++i) {
-        const uint32_t g = (32u * i) / a_row_bytes, j = (32u * i - g * a_row_bytes) / 32u;
-        a_off[i] = (g * (kTileM * a_row_bytes) + j * 32u) >> 4;
-      }
+      // Per-MMA descriptor offsets (16-byte units) inside a stage are COMPILE-TIME constants of the A row length: with
+      // a per-thread offset table every descriptor went through vector registers and 16 R2UR moves per k-step into the
+      // uniform registers UTCHMMA reads — the single issuing thread then needed ~125 cycles per MMA, twice the tensor
+      // core's floor for N <= 128 (tools/umma_rate_test: 55 / 64 cycles at N = 64 / 128).
       const uint32_t smem_base = smem_u32(base), bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
       const uint32_t bar_accf0 = smem_u32(&bars->acc_full[0]), bar_acce0 = smem_u32(&bars->acc_empty[0]);
       uint32_t stage = 0, phase_bit = 0, acc = 0, acc_phase = 0;
@@ -200,14 +198,28 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           tc_fence_after();
           const uint32_t sa16 = ((smem_base + stage * stage_bytes) & 0x3FFFFu) >> 4;  // stage start, 16-byte units
           const uint32_t sb16 = sa16 + (a_bytes >> 4);
+          const uint64_t ad0 = a_desc0 + (uint64_t)sa16, bd0 = b_desc0 + (uint64_t)sb16;
+          const uint32_t acc0 = ks != 0;
           if (elect_one()) {
-#pragma unroll
-            for (int i = 0; i < kKStepBytes / 32; ++i) {  // one MMA per 32 bytes of K (16 bf16 / 8 tf32)
-              const uint64_t ad = a_desc0 + (uint64_t)(sa16 + a_off[i]);
-              const uint64_t bd = b_desc0 + (uint64_t)(sb16 + 2u * i);
-              if (a.esz == 2) tc_mma_bf16(d_tmem, ad, bd, idesc, (ks | i) != 0);
-              else tc_mma_tf32(d_tmem, ad, bd, idesc, (ks | i) != 0);
-            }
+            // one MMA per 32 bytes of K (16 bf16 / 8 tf32); A sub-tile g = 128 rows x a_row_bytes, 32-byte slice j inside it
+#define DCS_TC_ISSUE4(O1, O2, O3)                                                        \
+  do {                                                                                   \
+    if (a.esz == 2) {                                                                    \
+      tc_mma_bf16(d_tmem, ad0, bd0, idesc, acc0);                                        \
+      tc_mma_bf16(d_tmem, ad0 + (O1), bd0 + 2, idesc, 1u);                               \
+      tc_mma_bf16(d_tmem, ad0 + (O2), bd0 + 4, idesc, 1u);                               \
+      tc_mma_bf16(d_tmem, ad0 + (O3), bd0 + 6, idesc, 1u);                               \
+    } else {                                                                             \
+      tc_mma_tf32(d_tmem, ad0, bd0, idesc, acc0);                                        \
+      tc_mma_tf32(d_tmem, ad0 + (O1), bd0 + 2, idesc, 1u);                               \
+      tc_mma_tf32(d_tmem, ad0 + (O2), bd0 + 4, idesc, 1u);                               \
+      tc_mma_tf32(d_tmem, ad0 + (O3), bd0 + 6, idesc, 1u);                               \
+    }                                                                                    \
+  } while (0)
+            if (a_row_bytes == 128u) DCS_TC_ISSUE4(2, 4, 6);
+            else if (a_row_bytes == 64u) DCS_TC_ISSUE4(2, (kTileM * 64) >> 4, ((kTileM * 64) >> 4) + 2);
+            else DCS_TC_ISSUE4((kTileM * 32) >> 4, (2 * kTileM * 32) >> 4, (3 * kTileM * 32) >> 4);
+#undef DCS_TC_ISSUE4
             tc_commit(bar_empty0 + 8u * stage);     // frees the smem stage once these MMAs have read it
             if (ks == a.ksteps - 1) tc_commit(bar_accf0 + 8u * acc);  // accumulator complete -> epilogue
           }
