@@ -303,8 +303,8 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               for (int h = 0; h < 2; ++h) {
                 const int c = 4 * e2 + 2 * h;
                 raw[h] = make_float2(__uint_as_float(rg[c]) + tl.bias_re, __uint_as_float(rg[c + 1]) + tl.bias_im);
-                m1[h] = bound_crm_dev(raw[h], tl.atan2_eps, exact);
-                m2[h] = bound_crm_dev(m1[h], tl.atan2_eps, exact);
+                m1[h] = exact ? bound_crm_dev(raw[h], tl.atan2_eps, true) : bound_crm_mufu(raw[h], tl.atan2_eps);
+                m2[h] = exact ? bound_crm_dev(m1[h], tl.atan2_eps, true) : bound_crm_mufu(m1[h], tl.atan2_eps);
                 const float2 yv = h ? make_float2(y2.z, y2.w) : make_float2(y2.x, y2.y);
                 const float2 pr = cmul(yv, m2[h]);
                 ns[h] = pr;

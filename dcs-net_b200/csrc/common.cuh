@@ -134,4 +134,27 @@ __device__ __forceinline__ float2 bound_crm_dev(float2 m, float eps, bool exact)
   return make_float2(x2 * s2, i1 * s2);
 }
 
+// bound_cRM for the bf16 / tensor-core tail (cconv_strip.cu): the same algebraic form with bare MUFU instructions only
+// (ex2.approx, rcp.approx, rsqrt.approx — no range fix-up, no Newton step, no slow-path call): ~22 instead of ~38
+// instructions per call; abs. error ~3e-7 on a value bounded by 1, against the bf16 inputs' 4e-3.
+__device__ __forceinline__ float2 bound_crm_mufu(float2 m, float eps) {
+  const float mag2 = m.x * m.x + m.y * m.y;
+  float rs, e, r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(fmaxf(mag2, 1e-37f)));
+  const float mag = mag2 * rs;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * mag));      // e^(-2 |m|) in (0, 1]
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  const float t = (1.f - e) * r;                                                        // tanh(|m|) >= 0
+  const float x1 = m.x + eps, q1 = x1 * x1 + m.y * m.y;
+  float s1;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s1) : "f"(q1));
+  const bool z1 = q1 == 0.f;
+  const float r1 = z1 ? t : x1 * (t * s1), i1 = z1 ? 0.f : m.y * (t * s1);
+  const float x2 = r1 + eps, q2 = x2 * x2 + i1 * i1;
+  float s2;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(s2) : "f"(q2));
+  const bool z2 = q2 == 0.f;
+  return make_float2(z2 ? t : x2 * (t * s2), z2 ? 0.f : i1 * (t * s2));
+}
+
 }  // namespace dcs
