@@ -390,7 +390,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
         if constexpr (kChunk == 32) {
           const float sum = transpose_reduce32(pool_acc, lane);   // pool_acc[c] sums columns c, c + 32 kSub, ... of this warp
-          atomicAdd(a.pool + (int64_t)un.b * a.n_real + (lane & (a.n_real - 1)), sum);
+          atomicAdd(a.pool + (int64_t)un.b * a.n_real + ((sub * kChunk + lane) & (a.n_real - 1)), sum);   // chunk sub of the row
         } else {
 #pragma unroll
           for (int c = 0; c < kChunk; ++c) {
@@ -436,7 +436,8 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   const int N = 2 * p->cout;
   DCS_REQUIRE(ilog2_exact(N) >= (tail ? 1 : 3), "dcs_cconv2d_strip_fwd: 2*cout must be a power of two >= 8");
   DCS_REQUIRE(p->cols == 32 || p->cols == 64 || p->cols == 128, "dcs_cconv2d_strip_fwd: cols must be 32, 64 or 128");
-  DCS_REQUIRE(N <= 32, "dcs_cconv2d_strip_fwd: 2*cout must be <= 32 (wider layers use dcs_cconv2d_tc_fwd)");
+  DCS_REQUIRE(N <= 64, "dcs_cconv2d_strip_fwd: 2*cout must be <= 64 (wider layers use dcs_cconv2d_tc_fwd)");
+  DCS_REQUIRE(N <= 32 || p->cols == N, "dcs_cconv2d_strip_fwd: 2*cout = 64 needs a single-phase accumulator (cols = 64)");
   DCS_REQUIRE(p->n_mma % 16 == 0 && p->n_mma >= 16 && p->n_mma <= p->cols, "dcs_cconv2d_strip_fwd: bad n_mma");
   const int run = p->up_w * N;
   DCS_REQUIRE(ilog2_exact(run) >= 3 && p->cols % run == 0, "dcs_cconv2d_strip_fwd: cols must be a multiple of up_w*2*cout");
@@ -531,6 +532,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
     else if (p->cols == 64 && s.n_dy == 2 && ipr == 32) { threads = strip_threads(8); DCS_STRIP_LAUNCH(64, 2, 32, 8); }   // decoder[4], one phase row per launch
     else if (p->cols == 64 && s.n_dy == 2 && ipr == 24) { threads = strip_threads(8); DCS_STRIP_LAUNCH(64, 2, 24, 8); }   // decoder[4] merged pw
     else if (p->cols == 128 && s.n_dy == 7 && ipr == 4) { threads = strip_threads(16); DCS_STRIP_LAUNCH(128, 7, 4, 16); } // encoder[0]: Toeplitz blocks
+    else if (p->cols == 64 && s.n_dy == 5 && ipr == 10) { threads = strip_threads(8); DCS_STRIP_LAUNCH(64, 5, 10, 8); }   // encoder[2]: k5 s(2,2), N = 64
     else DCS_REQUIRE(false, "dcs_cconv2d_strip_fwd: no kernel instance for cols=%d n_dy=%d items/row=%d", p->cols, s.n_dy, ipr);
 #undef DCS_STRIP_LAUNCH
     DCS_LAUNCHED();

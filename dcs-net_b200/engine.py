@@ -69,9 +69,11 @@ class PackedNet:
             if d6 is not None and (d6.cin, d6.cout, tuple(d6.up)) == (16, 1, (2, 2)) and os.environ.get("DCS_STRIP_DEC6", "1") != "0":
                 self.strip[("dec", 6)] = packing.StripDec6(d6, device=device)
             want = {("enc", 1): (8, 0, True, 1), ("dec", 4): (32, 32, False, 2), ("dec", 5): (16, 16, True, 1)}
+            if os.environ.get("DCS_STRIP_ENC2", "1") != "0":
+                want[("enc", 2)] = (16, 0, True, 1)       # k5 s(2,2), N = 64: 50 MMA items, 100 KB of resident weights
             for (kind, i), (c0, c1, merged, groups) in want.items():
                 pc = (self.enc if kind == "enc" else self.dec)[i] if i < Lr else None
-                if pc is not None and pc.cin == c0 + c1 and (2 * pc.cout) in (16, 32):
+                if pc is not None and pc.cin == c0 + c1 and (2 * pc.cout) in ((16, 32, 64) if (kind, i) == ("enc", 2) else (16, 32)):
                     self.strip[(kind, i)] = packing.StripConv(pc, c0, c1, merged=merged, groups=groups, device=device)
         self.lstm = packing.pack_lstm(sd, "lstm.", device)
         w_r, w_i = sd["fc.fc_r.weight"], sd["fc.fc_i.weight"]

@@ -170,7 +170,7 @@ def test_tensor_core_conv_equals_cuda_core_conv_on_same_operands():
         assert rel_err(got, ref) <= tol, (p.cin, p.cout, p.up, p.stride)
 
 
-@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("dec5", True, 1), ("dec4", False, 2), ("dec4", True, 2)])
+@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("enc2", True, 1), ("dec5", True, 1), ("dec4", False, 2), ("dec4", True, 2)])
 @pytest.mark.parametrize("B,H,W", [(2, 8, 66), (3, 20, 300)])
 def test_strip_conv_equals_cuda_core_conv_on_same_operands(layer, merged, groups, B, H, W):
     """Row-strip tcgen05 kernel (ring of source rows, row-shifted descriptors, resident weights) vs the FFMA kernel on
@@ -178,9 +178,9 @@ def test_strip_conv_equals_cuda_core_conv_on_same_operands(layer, merged, groups
     from dcsnet_b200 import packing
     sd = SW.make_state_dict(1)
     pk = D.PackedNet(sd, "cuda", "bf16")
-    p = {"enc1": pk.enc[1], "dec4": pk.dec[4], "dec5": pk.dec[5]}[layer]
+    p = {"enc1": pk.enc[1], "enc2": pk.enc[2], "dec4": pk.dec[4], "dec5": pk.dec[5]}[layer]
     g = torch.Generator().manual_seed(7)
-    if layer == "enc1":
+    if layer in ("enc1", "enc2"):
         c0, c1 = p.cin, 0
         x0, x1 = torch.randn(B, H, 2 * W, c0, 2, generator=g).cuda().bfloat16(), None
     else:
