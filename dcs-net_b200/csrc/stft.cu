@@ -12,6 +12,8 @@
 // (deterministic), so the (B,T,512) frame matrix never exists in HBM.
 //
 // Algorithmic HBM bytes: STFT 4*L + 8*256*T per utterance; iSTFT 8*256*T + 4*32*(T-1).
+#include <algorithm>
+#include <stdint.h>
 #include "common.cuh"
 
 namespace dcs {
@@ -343,9 +345,17 @@ extern "C" int dcs_stft_fwd(const dcs_stft_params* p, void* stream) {
   DCS_REQUIRE(p->n_frames == p->length / kHop + 1, "dcs_stft_fwd: n_frames must be length/32+1 (got %d for L=%d)", p->n_frames, p->length);
   DCS_REQUIRE(!p->bn_out || p->bn_affine, "dcs_stft_fwd: bn_out without bn_affine");
   const int n_chunks = (p->n_frames + kChunk - 1) / kChunk;
-  // aim for >= 2 waves of 148 SMs x 2 resident CTAs
-  int cpc = max(1, (n_chunks * p->batch) / (4 * num_sms()));
-  cpc = min(cpc, 16);
+  // chunks per CTA: the value that minimises (waves of 148 SMs x 4 resident CTAs) x (chunks per CTA)
+  int cpc = 1;
+  {
+    const int64_t slots = 4 * (int64_t)num_sms();
+    int64_t best = INT64_MAX;
+    for (int c = 1; c <= 32; ++c) {
+      const int64_t ctas = (int64_t)((n_chunks + c - 1) / c) * p->batch;
+      const int64_t cost = ((ctas + slots - 1) / slots) * (c + 1);   // + 1: table set-up and pipeline fill of a CTA
+      if (cost < best) { best = cost; cpc = c; }
+    }
+  }
   dim3 grid((n_chunks + cpc - 1) / cpc, p->batch);
   const size_t smem = sizeof(StftSmem);
   cudaStream_t s = (cudaStream_t)stream;
@@ -366,9 +376,18 @@ extern "C" int dcs_istft_fwd(const dcs_istft_params* p, void* stream) {
   DCS_REQUIRE(p && p->audio && (p->spec || (p->mag && p->phase)), "dcs_istft_fwd: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->n_frames >= 2, "dcs_istft_fwd: bad batch/n_frames (%d, %d)", p->batch, p->n_frames);
   const int n_chunks = istft_chunks(p->n_frames);
-  // chunks per CTA: 8 keeps the halo re-compute at 12.5 % while giving many more CTAs than resident slots, so
-  // the last wave is short (a single CTA per utterance for short inputs)
-  int cpc = min(8, n_chunks);
+  // chunks per CTA: every CTA re-computes one halo chunk, so the cost of a choice is (waves of 148 SMs x 3 resident
+  // CTAs) x (chunks per CTA + 1)
+  int cpc = std::min(8, n_chunks);
+  {
+    const int64_t slots = 3 * (int64_t)num_sms();
+    int64_t best = INT64_MAX;
+    for (int c = 1; c <= std::min(32, n_chunks); ++c) {
+      const int64_t ctas = (int64_t)((n_chunks + c - 1) / c) * p->batch;
+      const int64_t cost = ((ctas + slots - 1) / slots) * (c + 1);
+      if (cost < best) { best = cost; cpc = c; }
+    }
+  }
   dim3 grid((n_chunks + cpc - 1) / cpc, p->batch);
   const size_t smem = sizeof(IstftSmem);
   DCS_CUDA(cudaFuncSetAttribute(istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

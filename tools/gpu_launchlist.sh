@@ -1,7 +1,7 @@
 #!/bin/bash
 # quick per-kernel device times of one eager pass (cold-cache, serialised): ncu launch list only
 mkdir -p gpurun_out
-N=${PROF_LAUNCHES:-45}
+N=${PROF_LAUNCHES:-44}
 timeout 300 python tools/prof_pass.py > gpurun_out/plain_prof.log 2>&1 && \
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s $N -c $N --csv --log-file gpurun_out/launches_${TAG:-x}.csv python tools/prof_pass.py > gpurun_out/ncu_launches.log 2>&1
 echo "rc=$?"; cat gpurun_out/plain_prof.log
