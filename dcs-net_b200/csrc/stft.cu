@@ -221,6 +221,21 @@ __device__ __forceinline__ float2 polar_roundtrip(float2 s, float eps, bool exac
   return make_float2(xr * inv, s.y * inv);
 }
 
+// the same round trip with bare MUFU.RSQ instead of IEEE sqrt / division (exact_polar = 2, the tensor-core mode's choice):
+// mag / hypot = mag2 * rsqrt(mag2) * rsqrt(hy2), rel. error ~2e-7; ~12 instead of ~40 instructions per spectrogram value
+__device__ __forceinline__ float2 polar_roundtrip_mufu(float2 s, float eps) {
+  const float mag2 = s.x * s.x + s.y * s.y;
+  const float xr = s.x + eps;
+  const float hy2 = xr * xr + s.y * s.y;
+  float r1, r2;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(fmaxf(mag2, 1e-37f)));
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r2) : "f"(hy2));
+  const float mag = mag2 * r1;
+  const bool z = hy2 == 0.f;
+  const float inv = mag * r2;
+  return make_float2(z ? mag : xr * inv, z ? 0.f : s.y * inv);
+}
+
 __global__ void __launch_bounds__(kThreads, 3) istft_kernel(const float2* __restrict__ spec, const float* __restrict__ mag,
                                                          const float* __restrict__ phase, float* __restrict__ audio,
                                                          int T, int chunks_per_cta, float eps, int exact) {
@@ -262,7 +277,8 @@ __global__ void __launch_bounds__(kThreads, 3) istft_kernel(const float2* __rest
         for (int i = 0; i < 16; ++i) nx[i] = t < T ? __ldg(sp + (int64_t)(k_ld + 16 * i) * T + t) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          sm.buf[f][k_ld + 16 * i] = t < T ? polar_roundtrip(nx[i], eps, exact != 0) : make_float2(0.f, 0.f);
+          sm.buf[f][k_ld + 16 * i] = t < T ? (exact == 2 ? polar_roundtrip_mufu(nx[i], eps) : polar_roundtrip(nx[i], eps, exact != 0))
+                                           : make_float2(0.f, 0.f);
       } else {
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {

@@ -295,9 +295,10 @@ class ForwardPlan:
         else:
             ops.stft(self.audio_in, self.Y)
         self._tail(self._network(bn0_ready=strip0))
-        ops.istft(self.clean_spec, self.audio_out, self.eps, self.exact)
+        polar = 1 if self.exact else (2 if self.tc else 0)   # tensor-core mode: MUFU-only polar round trip (rel. ~2e-7)
+        ops.istft(self.clean_spec, self.audio_out, self.eps, polar)
         if with_noise_audio and self.noise_audio is not None:
-            ops.istft(self.noise_spec, self.noise_audio, self.eps, self.exact)
+            ops.istft(self.noise_spec, self.noise_audio, self.eps, polar)
 
     def _enqueue_from_spec(self):
         self._tail(self._network())

@@ -54,7 +54,8 @@ int dcs_stft_fwd(const dcs_stft_params* p, void* stream);
  *      (network_functions.py:140-150): abs / atan2(im, re+eps) / mag*cos / mag*sin, zero row appended at the END
  *      of the frequency axis, torch.istft(n_fft=512, hop=32, hann, normalized).  spec (B,256,T) complex64 ->
  *      audio (B, 32*(T-1)) fp32.  exact_polar=1 evaluates atan2f/cosf/sinf literally, 0 uses the algebraically
- *      identical (re+eps, im)/hypot form. */
+ *      identical (re+eps, im)/hypot form, 2 the same form with approximate reciprocal square roots (rel. error ~2e-7;
+ *      the bf16 / tensor-core mode's choice). */
 typedef struct {
   const float* spec; float* audio; int batch; int n_frames; float atan2_eps; int exact_polar;
   /* mag_phase_2_wave(mag, phase, config) called directly (network_functions.py:140): if spec == NULL the input is
