@@ -25,6 +25,12 @@ class StftParams(C.Structure):
                 ("bn_affine", _vp), ("bn_out", _vp), ("bn_dtype", _i)]
 
 
+class FrontendParams(C.Structure):
+    _fields_ = [("clean48", _vp), ("noisy48", _vp), ("lengths48", _vp), ("start16", _vp), ("batch", _i), ("stride48", _i64),
+                ("window", _i), ("kernel", _vp), ("n_taps", _i), ("orig", _i), ("width", _i),
+                ("clean16", _vp), ("noisy16", _vp), ("noise16", _vp), ("flags", _vp)]
+
+
 class IstftParams(C.Structure):
     _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
                 ("mag", _vp), ("phase", _vp)]
@@ -128,6 +134,7 @@ SYMBOLS = {
     "dcs_abi_version": (_i, []),
     "dcs_last_error_string": (C.c_char_p, []),
     "dcs_launch_count": (C.c_uint64, []),
+    "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),
     "dcs_cbn_apply": (_i, [C.POINTER(CbnParams), _vp]),

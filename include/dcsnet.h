@@ -50,6 +50,21 @@ typedef struct {
 } dcs_stft_params;
 int dcs_stft_fwd(const dcs_stft_params* p, void* stream);
 
+/* ---- f3: GPU data front-end = VoiceBankDataset.__getitem__ (data.py:68-143) for a batch:
+ *      torchaudio Resample(48000 -> 16000) (config.py:61; 41-tap hann-windowed sinc, stride 3: `kernel` holds the taps,
+ *      built on the host by the restated torchaudio formula), zero padding of short utterances, crop of `window`
+ *      samples at start16[b] (16 kHz samples; NULL = 0), noise = noisy - clean, and the inf / nan checks:
+ *      flags[b] |= 1 / 2 / 4 when clean / noisy / noise holds a non-finite value (flags may be NULL; zero it first).
+ *      clean48 / noisy48: (B, stride48) fp32, valid lengths lengths48[b] (NULL = stride48).  Outputs (B, window) fp32;
+ *      the three STFTs of data.py:115-134 are dcs_stft_fwd on them. */
+typedef struct {
+  const float* clean48; const float* noisy48; const int64_t* lengths48; const int64_t* start16;
+  int batch; int64_t stride48; int window;
+  const float* kernel; int n_taps; int orig; int width;
+  float* clean16; float* noisy16; float* noise16; unsigned int* flags;
+} dcs_frontend_params;
+int dcs_frontend_fwd(const dcs_frontend_params* p, void* stream);
+
 /* ---- a15: iSTFT back-end.  Replaces the polar round trip (network_functions.py:398-401) + mag_phase_2_wave
  *      (network_functions.py:140-150): abs / atan2(im, re+eps) / mag*cos / mag*sin, zero row appended at the END
  *      of the frequency axis, torch.istft(n_fft=512, hop=32, hann, normalized).  spec (B,256,T) complex64 ->

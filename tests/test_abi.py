@@ -38,12 +38,12 @@ def test_exports_are_plain_c():
 
 def test_struct_sizes_match_header():
     """ctypes mirrors of the POD parameter structs must have the C compiler's layout."""
-    src = '#include <stdio.h>\n#include "dcsnet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "dcsnet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(dcs_stft_params),sizeof(dcs_istft_params),sizeof(dcs_cbn_params),sizeof(dcs_cconv_params),' \
           'sizeof(dcs_chan_pool_params),sizeof(dcs_chan_gate_params),sizeof(dcs_spat_stats_params),' \
           'sizeof(dcs_spat_apply_params),sizeof(dcs_clstm_params),sizeof(dcs_mask_combine_params),' \
           'sizeof(dcs_strip_item),sizeof(dcs_strip_group),sizeof(dcs_strip_tail),sizeof(dcs_cstrip_params),' \
-          'sizeof(dcs_attention_params),sizeof(dcs_enc0_params),sizeof(dcs_dec6_tail_params));return 0;}'
+          'sizeof(dcs_attention_params),sizeof(dcs_enc0_params),sizeof(dcs_dec6_tail_params),sizeof(dcs_frontend_params));return 0;}'
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -54,7 +54,8 @@ def test_struct_sizes_match_header():
     mine = [ctypes.sizeof(t) for t in (L.StftParams, L.IstftParams, L.CbnParams, L.CconvParams, L.ChanPoolParams,
                                        L.ChanGateParams, L.SpatStatsParams, L.SpatApplyParams, L.ClstmParams,
                                        L.MaskCombineParams)] + [16] + \
-           [ctypes.sizeof(t) for t in (L.StripGroup, L.StripTail, L.CstripParams, L.AttentionParams, L.Enc0Params, L.Dec6TailParams)]
+           [ctypes.sizeof(t) for t in (L.StripGroup, L.StripTail, L.CstripParams, L.AttentionParams, L.Enc0Params, L.Dec6TailParams,
+                                       L.FrontendParams)]
     assert sizes == mine
 
 
