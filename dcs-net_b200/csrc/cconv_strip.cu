@@ -203,6 +203,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const uint64_t a_desc_c0 = umma_desc(0, a.row_bytes0), a_desc_c1 = umma_desc(0, a.row_bytes1), b_desc_c = umma_desc(0, 32);
     const uint32_t ring16 = (smem_u32(base) & 0x3FFFFu) >> 4, slot16 = a.slot_bytes >> 4, w16 = (smem_u32(w_s) & 0x3FFFFu) >> 4;
     const uint32_t bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
+    const uint64_t b_base = b_desc_c + (uint64_t)w16;   // descriptor bases: ONE vector -> uniform move each, item offsets are constant-bank adds
     const uint32_t R = (uint32_t)a.R;
     uint32_t ws = 0, wp = 0, gw = 0;   // next full barrier to wait on (slot, parity) / rows waited so far
     uint32_t fs = 0, rel = 0;          // next slot to release / rows released so far
@@ -232,13 +233,16 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         uint32_t sl = cur.slot + (uint32_t)dg;
         if (sl >= R) sl -= R;
         const uint32_t a16 = ring16 + sl * slot16;
+        // (per-item `desc + (a16 + item.x)` kept every descriptor in vector registers: ~5 R2UR moves per MMA on the
+        // issuing thread; with per-row bases the item offsets are uniform adds of constant-bank operands)
+        const uint64_t a_base0 = a_desc_c0 + (uint64_t)a16, a_base1 = a_desc_c1 + (uint64_t)a16;
         if (elect_one()) {
 #pragma unroll
           for (int q = 0; q < kIpr; ++q) {
             const uint4 item = a.items[dg * kIpr + q];
             const uint32_t flags = item.z >> 24, d_col = item.z & 0xffffu;
-            const uint64_t ad = ((flags & 2u) ? a_desc_c1 : a_desc_c0) + (uint64_t)(a16 + item.x);
-            const uint64_t bd = b_desc_c + (uint64_t)(w16 + item.y);
+            const uint64_t ad = ((flags & 2u) ? a_base1 : a_base0) + (uint64_t)item.x;
+            const uint64_t bd = b_base + (uint64_t)item.y;
             tc_mma_bf16(d_tmem + d_col, ad, bd, idesc, (flags & 1u) ? 0u : 1u);
           }
         }
