@@ -203,7 +203,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     const uint64_t a_desc_c0 = umma_desc(0, a.row_bytes0), a_desc_c1 = umma_desc(0, a.row_bytes1), b_desc_c = umma_desc(0, 32);
     const uint32_t ring16 = (smem_u32(base) & 0x3FFFFu) >> 4, slot16 = a.slot_bytes >> 4, w16 = (smem_u32(w_s) & 0x3FFFFu) >> 4;
     const uint32_t bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
-    const uint64_t b_base = b_desc_c + (uint64_t)w16;   // descriptor bases: ONE vector -> uniform move each, item offsets are constant-bank adds
+    const uint32_t b_lo = (uint32_t)b_desc_c + w16, b_hi = (uint32_t)(b_desc_c >> 32);
     const uint32_t R = (uint32_t)a.R;
     uint32_t ws = 0, wp = 0, gw = 0;   // next full barrier to wait on (slot, parity) / rows waited so far
     uint32_t fs = 0, rel = 0;          // next slot to release / rows released so far
@@ -235,15 +235,16 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         const uint32_t a16 = ring16 + sl * slot16;
         // (per-item `desc + (a16 + item.x)` kept every descriptor in vector registers: ~5 R2UR moves per MMA on the
         // issuing thread; with per-row bases the item offsets are uniform adds of constant-bank operands)
-        const uint64_t a_base0 = a_desc_c0 + (uint64_t)a16, a_base1 = a_desc_c1 + (uint64_t)a16;
+        // descriptor = {constant high word, low word = LBO | (address >> 4)}: the row's base goes through ONE vector ->
+        // uniform move, every item adds constant-bank operands (offsets, and the A high word pre-computed by the host)
+        const uint32_t a_lo = (uint32_t)a_desc_c0 + a16;
         if (elect_one()) {
 #pragma unroll
           for (int q = 0; q < kIpr; ++q) {
             const uint4 item = a.items[dg * kIpr + q];
-            const uint32_t flags = item.z >> 24, d_col = item.z & 0xffffu;
-            const uint64_t ad = ((flags & 2u) ? a_base1 : a_base0) + (uint64_t)item.x;
-            const uint64_t bd = b_base + (uint64_t)item.y;
-            tc_mma_bf16(d_tmem + d_col, ad, bd, idesc, (flags & 1u) ? 0u : 1u);
+            const uint64_t ad = ((uint64_t)item.w << 32) | (uint64_t)(a_lo + item.x);
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + item.y);
+            tc_mma_bf16(d_tmem + (item.z & 0xffffu), ad, bd, idesc, (item.z & (1u << 24)) ? 0u : 1u);
           }
         }
         __syncwarp();
@@ -496,6 +497,11 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
     a.grp.dy_min = s.dy_min; a.grp.n_dy = s.n_dy; a.grp.ph0 = s.ph0; a.grp.x_min = s.x_min; a.grp.w_bytes = (uint32_t)s.w_bytes;
     a.grp.w_ptr = reinterpret_cast<const unsigned char*>(p->weights) + s.w_off;
     memcpy(a.items, p->items + s.item0, (size_t)s.n_items * sizeof(uint4));
+    for (int i = 0; i < s.n_items; ++i) {   // .w = high word of the item's A descriptor (SBO | version | swizzle of its source's rows)
+      const uint32_t rb = (a.items[i].z >> 24) & 2u ? a.row_bytes1 : a.row_bytes0;
+      const uint32_t layout = rb == 128 ? 2u : (rb == 64 ? 4u : 6u);
+      a.items[i].w = ((8u * rb) >> 4) | (1u << 14) | (layout << 29);
+    }
     a.w_smem_bytes = ((uint32_t)s.w_bytes + 1023u) & ~1023u;
     const size_t fixed = 1024 + a.w_smem_bytes + (size_t)p->cols * sizeof(float) + sizeof(StripBarriers);
     const size_t budget = 227 * 1024;
