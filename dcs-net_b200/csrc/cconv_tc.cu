@@ -39,6 +39,9 @@ struct TcArgs {
   int phases, ntaps, up_h, up_w, stride_h, stride_w;
   int C2, C2_src0, CK, ksteps, n_stages;
   int esz;                    // operand element size: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32)
+  int kb;                     // 128-byte K blocks per pipeline stage: 1, or 2 (TMA mode, n_pad <= 128: one tcgen05.mma issue costs
+                              // ~55 cycles and a stage's wait / fence / descriptor / commit overhead ~300, so 8 MMAs per stage
+                              // instead of 4 lift the issue-bound N <= 128 layers)
   int gather;                 // 1: A tiles are gathered by 4 warps with 16-byte cp.async (rows shorter than 128 B or
                               //    small N, where the per-row cost of TMA boxes dominates); 0: A tiles come from TMA boxes
   int tw_log2, th_log2;       // tile extents are powers of two
@@ -88,7 +91,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
   // layout: [stage][A 16 KB | B n_pad*128 B] (1024-aligned), then barriers
-  const uint32_t a_bytes = kTileM * kKStepBytes, b_bytes = (uint32_t)a.n_pad * kKStepBytes;
+  const uint32_t a_bytes = kTileM * kKStepBytes * (uint32_t)a.kb, b_bytes = (uint32_t)a.n_pad * kKStepBytes * (uint32_t)a.kb;
   const uint32_t stage_bytes = a_bytes + b_bytes;  // multiple of 1024 (n_pad % 16 == 0 -> b_bytes % 2048 == 0)
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(base + (size_t)a.n_stages * stage_bytes);
@@ -119,7 +122,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
-  const int kstep_elems = kKStepBytes / a.esz;
+  const int kstep_elems = kKStepBytes * a.kb / a.esz;
   const int sub_per_step = kstep_elems / a.CK;
 
   if (warp == 0) {
@@ -161,7 +164,10 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               if (tap + 1 < a.ntaps) { ++tap; y = ybase + dyp[tap]; x = xbase + dxp[tap]; }
             }
           }
-          if (leader) tma_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, full, kcol, wrow);
+          if (leader) {
+            tma_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, full, kcol, wrow);
+            if (a.kb == 2) tma_load_2d(smem_base + stage * stage_bytes + a_bytes + (uint32_t)a.n_pad * kKStepBytes, &tmB, full, kcol + kKStepBytes / a.esz, wrow);
+          }
           __syncwarp();
           kcol += kstep_elems;
           if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
@@ -216,7 +222,16 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
       tc_mma_tf32(d_tmem, ad0 + (O3), bd0 + 6, idesc, 1u);                               \
     }                                                                                    \
   } while (0)
-            if (a_row_bytes == 128u) DCS_TC_ISSUE4(2, 4, 6);
+            if (a_row_bytes == 128u) {
+              DCS_TC_ISSUE4(2, 4, 6);
+              if (a.kb == 2) {   // second 128-byte K block of the stage: next A sub-tile (128 rows x 128 B) and B sub-tile
+                const uint64_t ad1 = ad0 + (uint64_t)((kTileM * 128) >> 4), bd1 = bd0 + (uint64_t)(((uint32_t)a.n_pad * 128u) >> 4);
+                tc_mma_bf16(d_tmem, ad1, bd1, idesc, 1u);
+                tc_mma_bf16(d_tmem, ad1 + 2, bd1 + 2, idesc, 1u);
+                tc_mma_bf16(d_tmem, ad1 + 4, bd1 + 4, idesc, 1u);
+                tc_mma_bf16(d_tmem, ad1 + 6, bd1 + 6, idesc, 1u);
+              }
+            }
             else if (a_row_bytes == 64u) DCS_TC_ISSUE4(2, (kTileM * 64) >> 4, ((kTileM * 64) >> 4) + 2);
             else DCS_TC_ISSUE4((kTileM * 32) >> 4, (2 * kTileM * 32) >> 4, (3 * kTileM * 32) >> 4);
 #undef DCS_TC_ISSUE4
@@ -583,9 +598,10 @@ using namespace dcs;
 extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   if (int e = validate_conv(p, "dcs_cconv2d_tc_fwd")) return e;
   const int esz = p->in_dtype == DCS_BF16 ? 2 : 4;  // bf16 operands (kind::f16) or fp32 operands read as tf32
-  const int kstep_elems = kKStepBytes / esz;
+  const int kblk_elems = kKStepBytes / esz;          // elements of one 128-byte K block
+  int kstep_elems = kblk_elems;
   const int C2s0 = 2 * p->c0, C2s1 = 2 * p->c1, C2 = C2s0 + C2s1;
-  const int CK = C2s0 >= kstep_elems ? kstep_elems : C2s0;
+  const int CK = C2s0 >= kblk_elems ? kblk_elems : C2s0;
   const int N_ = 2 * p->cout;
   // A-operand path: TMA boxes cost ~2 cycles per box row regardless of the row length, so short rows (few channels per
   // tap: several boxes per K step) are gathered with 16-byte cp.async instead (measured: enc1 1.09 -> 0.78 ms; layers
@@ -617,6 +633,12 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   a.n_tiles = a.tiles_per_phase * a.phases;
   a.ntaps = p->ntaps; a.up_h = p->up_h; a.up_w = p->up_w; a.stride_h = p->stride_h; a.stride_w = p->stride_w;
   a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK; a.esz = esz; a.gather = gather;
+  {
+    static const bool no_kb2 = getenv("DCS_TC_NO_KB2") && atoi(getenv("DCS_TC_NO_KB2")) != 0;
+    const int n_pad_ = (2 * p->cout + 15) / 16 * 16;
+    a.kb = (!no_kb2 && !gather && esz == 2 && CK * esz == 128 && n_pad_ <= 128 && p->ntaps * C2 >= 4 * kblk_elems) ? 2 : 1;
+    kstep_elems = kblk_elems * a.kb;
+  }
   a.tw_log2 = __builtin_ctz(a.TW); a.th_log2 = __builtin_ctz(a.TH);
   a.in_h = p->in_h; a.in_w = p->in_w; a.src0 = p->src0; a.src1 = p->src1;
   const int K = p->ntaps * C2;
@@ -628,14 +650,15 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   DCS_REQUIRE(p->bias, "dcs_cconv2d_tc_fwd: bias is required (pass zeros)");
   a.bias = p->bias; a.dst = p->dst; a.pool = p->pool_sums; a.dbg = g_tc_dbg;
 
-  const size_t stage_bytes = (size_t)kTileM * kKStepBytes + (size_t)n_pad * kKStepBytes;
+  const size_t stage_bytes = ((size_t)kTileM * kKStepBytes + (size_t)n_pad * kKStepBytes) * a.kb;
   int n_stages = (int)((200 * 1024) / stage_bytes);
   n_stages = std::max(2, std::min(n_stages, kMaxStages));
   a.n_stages = n_stages;
   const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers) + 8 * kEpiStageBytes;
 
   CUtensorMap tmA0, tmA1, tmB;
-  if (int e = make_weight_map(&tmB, p->weight, esz, a.ksteps * kstep_elems, a.phases * n_pad, n_pad)) return e;
+  // (the packed weight matrix is padded to whole 128-byte K blocks; a half-empty last double stage reads zeros out of bounds)
+  if (int e = make_weight_map(&tmB, p->weight, esz, (K + kblk_elems - 1) / kblk_elems * kblk_elems, a.phases * n_pad, n_pad)) return e;
   if (gather) {
     tmA0 = tmB; tmA1 = tmB;  // unused by the kernel in gather mode (kept valid for the descriptor prefetch)
   } else {
