@@ -218,6 +218,46 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       mbar_wait(smem_u32(&bars->acc_empty[acc]), accp ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * (uint32_t)kCols;
+      // Two issue schedules (measured per instance on B200): whole-tile batches win where a tile has many ring rows with
+      // few items each or the ring has slack (enc0, enc1, dec4); per-row issue keeps more overlap with the loads where the
+      // ring is tight (enc2: R = n_dy + stride) and for the 3-row decoders.
+      constexpr bool kBatchIssue = (kNdy == 7 || kNdy == 2);
+      if constexpr (kBatchIssue) {
+      // Wait for ALL source rows of the tile first (in steady state they are already there), then issue the whole tile's
+      // MMAs in ONE elected region: a wait / fence / elect / sync round per ring row cost ~150-300 cycles of the issuing
+      // thread against ~55 per MMA (the same stage overhead that bounded cconv_tc).
+      {
+        const uint32_t need = cur.lo + (uint32_t)(kNdy - 1);
+        if (gw <= need) {
+          while (gw <= need) {
+            mbar_wait(bar_full0 + 8u * ws, wp);
+            if (++ws == R) { ws = 0; wp ^= 1; }
+            ++gw;
+          }
+          tc_fence_after();
+        }
+      }
+      uint32_t a_lo[kNdy];
+#pragma unroll
+      for (int dg = 0; dg < kNdy; ++dg) {
+        uint32_t sl = cur.slot + (uint32_t)dg;
+        if (sl >= R) sl -= R;
+        a_lo[dg] = (uint32_t)a_desc_c0 + ring16 + sl * slot16;   // descriptor low word = LBO | (row base >> 4)
+      }
+      if (elect_one()) {
+#pragma unroll
+        for (int dg = 0; dg < kNdy; ++dg) {
+#pragma unroll
+          for (int q = 0; q < kIpr; ++q) {
+            const uint4 item = a.items[dg * kIpr + q];
+            const uint64_t ad = ((uint64_t)item.w << 32) | (uint64_t)(a_lo[dg] + item.x);
+            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + item.y);
+            tc_mma_bf16(d_tmem + (item.z & 0xffffu), ad, bd, idesc, (item.z & (1u << 24)) ? 0u : 1u);
+          }
+        }
+      }
+      __syncwarp();
+      } else {
       // items are sorted by ring row (drow): wait for a source row once, then issue its MMAs back to back
 #pragma unroll
       for (int dg = 0; dg < kNdy; ++dg) {
@@ -248,6 +288,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           }
         }
         __syncwarp();
+      }
       }
       const uint32_t upto = ahead.lo;                 // first row of this issuer's next own tile (or the total row count)
       // Never release a row this issuer has not waited for: a parity wait on a phase that is two completions old would
