@@ -118,7 +118,7 @@ typedef struct {
 int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream);    /* fp32 CUDA-core path (<=1e-5 mode) */
 int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (bf16 mode)  */
 
-/* ---- a4 / a12 / a11 (few-channel layers: encoder[1], decoder[4], decoder[5]): "row-strip" tensor-core convolution.
+/* ---- a4 / a12 / a11 (few-channel layers: encoder[0..2], decoder[4..6]): "row-strip" tensor-core convolution.
  *      Same math and reference call sites as dcs_cconv2d_tc_fwd (c_network.py:107-112, 135-147, 214-216); different
  *      data movement: one TMA box per SOURCE ROW (a strip of `box_units` strip rows; a strip row = one pixel, or a
  *      pixel pair when stride_w = 2, of 32 / 64 / 128 bytes) is loaded once into a ring of rows in shared memory and
@@ -136,7 +136,7 @@ int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM
  *      Phase groups: group g owns output phase rows ph0 .. ph0+n_ph-1 of every up_h block and is served by its own
  *      CTAs (weights of one group resident per CTA).  bf16 in / bf16 out only. */
 #define DCS_STRIP_MAX_GROUPS 2
-typedef struct { uint32_t a_off16; uint32_t b_off16; uint16_t d_col; uint8_t drow; uint8_t flags; uint32_t reserved; } dcs_strip_item;
+typedef struct { uint32_t a_off16; uint32_t b_off16; uint16_t d_col; uint8_t drow; uint8_t flags; uint32_t reserved; /* caller: 0; the library writes the item's A-descriptor high word into its own copy */ } dcs_strip_item;
 typedef struct { int item0; int n_items; int dy_min; int n_dy; int ph0; int n_ph; int x_min; int w_bytes; int64_t w_off; } dcs_strip_group;
 /* optional fused tail (decoder[6] only, replaces dcs_dec6_tail_fwd on the tensor-core path): the accumulator columns are
  * (phase row, 8 output pixels, re/im) of decoder[6]'s raw output; the epilogue adds (bias_re, bias_im) and applies
