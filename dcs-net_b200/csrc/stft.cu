@@ -236,7 +236,7 @@ __device__ __forceinline__ float2 polar_roundtrip_mufu(float2 s, float eps) {
   return make_float2(z ? mag : xr * inv, z ? 0.f : s.y * inv);
 }
 
-__global__ void __launch_bounds__(kThreads, 3) istft_kernel(const float2* __restrict__ spec, const float* __restrict__ mag,
+__global__ void __launch_bounds__(kThreads, 4) istft_kernel(const float2* __restrict__ spec, const float* __restrict__ mag,
                                                          const float* __restrict__ phase, float* __restrict__ audio,
                                                          int T, int chunks_per_cta, float eps, int exact) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -392,11 +392,11 @@ extern "C" int dcs_istft_fwd(const dcs_istft_params* p, void* stream) {
   DCS_REQUIRE(p && p->audio && (p->spec || (p->mag && p->phase)), "dcs_istft_fwd: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->n_frames >= 2, "dcs_istft_fwd: bad batch/n_frames (%d, %d)", p->batch, p->n_frames);
   const int n_chunks = istft_chunks(p->n_frames);
-  // chunks per CTA: every CTA re-computes one halo chunk, so the cost of a choice is (waves of 148 SMs x 3 resident
+  // chunks per CTA: every CTA re-computes one halo chunk, so the cost of a choice is (waves of 148 SMs x 4 resident
   // CTAs) x (chunks per CTA + 1)
   int cpc = std::min(8, n_chunks);
   {
-    const int64_t slots = 3 * (int64_t)num_sms();
+    const int64_t slots = 4 * (int64_t)num_sms();
     int64_t best = INT64_MAX;
     for (int c = 1; c <= std::min(32, n_chunks); ++c) {
       const int64_t ctas = (int64_t)((n_chunks + c - 1) / c) * p->batch;
