@@ -98,15 +98,15 @@ def test_bias_rule_quirk():
     assert torch.allclose(p.bias[:6].view(3, 2), torch.stack([br - bi, br + bi], 1))
 
 
-@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("dec5", True, 1), ("dec5", False, 1), ("dec4", False, 2),
-                                                 ("dec4", True, 2)])
+@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("enc2", True, 1), ("dec5", True, 1), ("dec5", False, 1),
+                                                 ("dec4", False, 2), ("dec4", True, 2)])
 def test_strip_packing(packed, layer, merged, groups):
     """The row-strip kernel's item table + swizzled weight image (packing.StripConv) describe the same convolution as
     the per-tap operands (conv_geometry), up to the bf16 rounding of the weights."""
     _, pk = packed
-    p = {"enc1": pk.enc[1], "dec4": pk.dec[4], "dec5": pk.dec[5], "dec6": pk.dec[6]}[layer]
+    p = {"enc1": pk.enc[1], "enc2": pk.enc[2], "dec4": pk.dec[4], "dec5": pk.dec[5], "dec6": pk.dec[6]}[layer]
     g = torch.Generator().manual_seed(31)
-    if layer == "enc1":
+    if layer in ("enc1", "enc2"):
         H, W = 6, 260                      # W/2 = 130 output columns: two strips, ragged
         srcs = [torch.randn(2, H, W, p.cin, 2, generator=g), None]
         c0, c1 = p.cin, 0
