@@ -398,11 +398,8 @@ static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s
   a.x = (const __nv_bfloat16*)p->x; a.y = (__nv_bfloat16*)p->y; a.sums = p->sums; a.inv_hw = 1.f / ((float)p->h * (float)p->w);
   a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
   a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = NR;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<C, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_set = smem;
-  }
+  // (set on every call: the attribute is per device, and one process may drive several GPUs)
+  DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<C, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->w + TW - 1) / TW, p->batch);
   attention_stream_kernel<C, TW><<<grid, kAsThreads, smem, s>>>(a);
   DCS_LAUNCHED();
