@@ -65,20 +65,24 @@ class PackedConv:
     """GEMM operands of one complex convolution layer (see include/dcsnet.h: dcs_cconv_params)."""
 
     def __init__(self, w_r, w_i, b_r=None, b_i=None, bn=None, transposed=False, stride=(1, 1), up=(1, 1),
-                 act=0, device="cpu", want_bf16=False, want_tf32=False):
-        w_r, w_i = w_r.detach().double().cpu(), w_i.detach().double().cpu()
-        if transposed:  # (Cin, Cout, k, k) -> equivalent conv weight (Cout, Cin, k, k), spatially flipped
-            w_r = w_r.permute(1, 0, 2, 3).flip(2, 3)
-            w_i = w_i.permute(1, 0, 2, 3).flip(2, 3)
-        cout, cin, kh, kw = w_r.shape
-        # real block weight M[(co,ro), (ci,ri), ky, kx]
-        M = torch.zeros(cout, 2, cin, 2, kh, kw, dtype=torch.float64)
-        M[:, 0, :, 0], M[:, 0, :, 1] = w_r, -w_i
-        M[:, 1, :, 0], M[:, 1, :, 1] = w_i, w_r
-        bias = torch.zeros(cout, 2, dtype=torch.float64)
-        if b_r is not None:
-            b_r, b_i = b_r.detach().double().cpu(), b_i.detach().double().cpu()
-            bias[:, 0], bias[:, 1] = b_r - b_i, b_r + b_i
+                 act=0, device="cpu", want_bf16=False, want_tf32=False, _block=None):
+        if _block is not None:      # PackedConv.from_real: the real block weight / bias are given directly
+            M, bias = _block
+            cout, _, cin, _, kh, kw = M.shape
+        else:
+            w_r, w_i = w_r.detach().double().cpu(), w_i.detach().double().cpu()
+            if transposed:  # (Cin, Cout, k, k) -> equivalent conv weight (Cout, Cin, k, k), spatially flipped
+                w_r = w_r.permute(1, 0, 2, 3).flip(2, 3)
+                w_i = w_i.permute(1, 0, 2, 3).flip(2, 3)
+            cout, cin, kh, kw = w_r.shape
+            # real block weight M[(co,ro), (ci,ri), ky, kx]
+            M = torch.zeros(cout, 2, cin, 2, kh, kw, dtype=torch.float64)
+            M[:, 0, :, 0], M[:, 0, :, 1] = w_r, -w_i
+            M[:, 1, :, 0], M[:, 1, :, 1] = w_i, w_r
+            bias = torch.zeros(cout, 2, dtype=torch.float64)
+            if b_r is not None:
+                b_r, b_i = b_r.detach().double().cpu(), b_i.detach().double().cpu()
+                bias[:, 0], bias[:, 1] = b_r - b_i, b_r + b_i
         if bn is not None:
             A, c = bn
             M = torch.einsum("oab,obcdyx->oacdyx", A, M)
@@ -129,6 +133,38 @@ class PackedConv:
             # dcs_dec6_tail_fwd operand: [phase][tap][ci][(M00 M10 M01 M11)]  (M[n][ri], stored by columns)
             self.w_tail = Wp[:, :, :2].reshape(self.phases, self.ntaps, 2, cin, 2).permute(0, 1, 3, 4, 2) \
                 .contiguous().float().to(device)
+
+
+def real_bn_affine(weight, bias, running_mean, running_var, eps=BN_EPS):
+    """Eval-mode torch.nn.BatchNorm2d over C real channels as the (A (C/2,2,2), c (C/2,2)) affine of C/2 channel PAIRS
+    (diagonal A): the real path (r_network.py) stores real channels 2c, 2c+1 where the complex path stores (re, im) of
+    channel c, so the same kernels and the same BN fold apply.  An odd C is padded with an identity channel."""
+    s = weight.detach().double().cpu() / torch.sqrt(running_var.detach().double().cpu() + eps)
+    t = bias.detach().double().cpu() - running_mean.detach().double().cpu() * s
+    if s.numel() % 2:
+        s, t = torch.cat([s, torch.ones(1, dtype=torch.float64)]), torch.cat([t, torch.zeros(1, dtype=torch.float64)])
+    A = torch.zeros(s.numel() // 2, 2, 2, dtype=torch.float64)
+    A[:, 0, 0], A[:, 1, 1] = s[0::2], s[1::2]
+    return A, torch.stack([t[0::2], t[1::2]], dim=1)
+
+
+def packed_conv_from_real(weight, bias=None, bn=None, transposed=False, **kw):
+    """A REAL Conv2d / ConvTranspose2d (r_network.py:61-66, 89-103) as the operands of the complex-conv kernels: real
+    channels are paired (2c, 2c+1) <-> (re, im) of pseudo-complex channel c, so the real weight W[co][ci] IS the block
+    matrix M[(co/2, co%2), (ci/2, ci%2)] the kernels multiply by; odd channel counts (the 1-channel magnitude input, the
+    1-channel mask output) are zero-padded.  `bn` = real_bn_affine(...) of the BatchNorm2d that follows."""
+    W = weight.detach().double().cpu()
+    if transposed:
+        W = W.permute(1, 0, 2, 3).flip(2, 3)
+    co, ci, kh, kw_ = W.shape
+    cop, cip = co + co % 2, ci + ci % 2
+    Wp = torch.zeros(cop, cip, kh, kw_, dtype=torch.float64)
+    Wp[:co, :ci] = W
+    M = Wp.reshape(cop // 2, 2, cip // 2, 2, kh, kw_)
+    b = torch.zeros(cop, dtype=torch.float64)
+    if bias is not None:
+        b[:co] = bias.detach().double().cpu()
+    return PackedConv(None, None, bn=bn, _block=(M, b.reshape(cop // 2, 2)), **kw)
 
 
 STRIP_M = 128  # pixels (strip rows) per M tile of the row-strip kernel (csrc/cconv_strip.cu)

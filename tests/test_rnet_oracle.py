@@ -68,3 +68,56 @@ def test_product_forward_fails_loudly_without_fallback():
     net = product_net()
     with pytest.raises(NotImplementedError, match="no CPU"):
         net(torch.rand(2, 256, 64))
+
+
+# ------------------------------------------------------------------ real convs on the complex-conv operand layout (CPU emulation)
+def _pairs(t):
+    """(B, C, H, W) real NCHW -> channels-last pseudo-complex (B, H, W, ceil(C/2), 2): channel pairs (2c, 2c+1) = (re, im)."""
+    B, C, H, W = t.shape
+    if C % 2:
+        t = torch.cat([t, torch.zeros(B, 1, H, W)], dim=1)
+    return t.permute(0, 2, 3, 1).reshape(B, H, W, -1, 2).contiguous()
+
+
+@pytest.mark.parametrize("layer", ["enc0", "enc3", "dec0", "dec4", "dec6"])
+def test_real_conv_packing_reproduces_the_reference_layers(layer):
+    """packing.packed_conv_from_real + real_bn_affine: a real Conv2d / (cat + nearest Upsample + ConvTranspose2d) with the
+    BatchNorm2d and activation that follow, evaluated through the SAME operand definitions the complex-conv kernels use
+    (tests/emulate.conv_geometry), equals the torch layer stack of r_network.py."""
+    from dcsnet_b200 import packing, _lib as L
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emulate import conv_geometry
+    import torch.nn.functional as F
+    net = product_net()
+    randomise_bn(net.state_dict(), 7)
+    sd = net.state_dict()
+    g = torch.Generator().manual_seed(5)
+    if layer.startswith("enc"):
+        i = int(layer[3:])
+        conv, bn = net.encoder[i][0], net.encoder[i][1]
+        x = torch.randn(2, conv.in_channels, 12, 10, generator=g)
+        pk = packing.packed_conv_from_real(conv.weight, conv.bias, bn=packing.real_bn_affine(bn.weight, bn.bias, bn.running_mean, bn.running_var),
+                                           stride=conv.stride, act=L.ACT_RELU)
+        ref = F.relu(F.batch_norm(F.conv2d(x, conv.weight, conv.bias, stride=conv.stride, padding=conv.padding), bn.running_mean,
+                                  bn.running_var, bn.weight, bn.bias, False, 0.0, 1e-5))
+        oh, ow = ref.shape[2:]
+        got = conv_geometry(pk, _pairs(x), None, (oh, ow))
+    else:
+        i = int(layer[3:])
+        last = i == 6
+        convt = net.decoder[i] if last else net.decoder[i][0]
+        up = RO.UPSAMPLE[i]
+        c = convt.in_channels // 2
+        d, skip = torch.randn(2, c, 4, 5, generator=g), torch.randn(2, c, 4, 5, generator=g)
+        bn = None if last else net.decoder[i][1]
+        pk = packing.packed_conv_from_real(convt.weight, convt.bias, transposed=True, up=up,
+                                           bn=None if last else packing.real_bn_affine(bn.weight, bn.bias, bn.running_mean, bn.running_var),
+                                           act=L.ACT_NONE if last else L.ACT_LRELU)
+        ref = F.conv_transpose2d(F.interpolate(torch.cat((d, skip), 1), scale_factor=up, mode="nearest"), convt.weight, convt.bias,
+                                 stride=1, padding=1)
+        if not last:
+            ref = F.leaky_relu(F.batch_norm(ref, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, 1e-5))
+        oh, ow = ref.shape[2:]
+        got = conv_geometry(pk, _pairs(d), _pairs(skip), (oh, ow))
+    got = got.reshape(2, oh, ow, -1)[..., :ref.shape[1]].permute(0, 3, 1, 2)
+    assert rel_err(got, ref) <= 2e-6
