@@ -441,3 +441,48 @@ def pack_spatial_attention(sd, prefix, device):
     wr, wi = sd[prefix + "conv1.conv_r.weight"], sd[prefix + "conv1.conv_i.weight"]
     assert tuple(wr.shape) == (1, 2, 7, 7), "only spatial_attention_kernel_size = 7 is built"
     return torch.cat([wr.detach().float().reshape(-1), wi.detach().float().reshape(-1)]).contiguous().to(device)
+
+
+class PackedRNet:
+    """GEMM-ready operands of an R_NETWORK state_dict (r_network.py) in the layout of the complex path:
+    real channels (2c, 2c+1) are the (re, im) of pseudo-complex channel c, so the convs, the fc and the initial BatchNorm
+    run on the existing kernels; the real CBAM / LSTM weights are kept in the reference's own layout for the round-2
+    kernels.  Host-only so far (tests/emulate.rnet_dataflow evaluates the network through these operands on the CPU)."""
+
+    KERNEL_E = [7, 7, 5, 5, 3, 3, 3]
+    STRIDE_E = [(2, 2), (2, 2), (2, 2), (2, 1), (2, 1), (2, 1), (2, 1)]
+    UPSAMPLE = [(2, 1), (2, 1), (2, 1), (2, 1), (2, 2), (2, 2), (2, 2)]
+
+    def __init__(self, model_or_sd, device="cpu", no_of_layers=7, want_bf16=False):
+        sd = model_or_sd.state_dict() if hasattr(model_or_sd, "state_dict") else model_or_sd
+        sd = {k: v.detach() for k, v in sd.items()}
+        Lr = self.L = no_of_layers
+        bn = lambda p: real_bn_affine(sd[p + "weight"], sd[p + "bias"], sd[p + "running_mean"], sd[p + "running_var"])  # noqa: E731
+        self.bn0 = affine6(*bn("initial_batchnorm.")).to(device)          # magnitude in .re, 0 in .im (identity channel)
+        self.enc, self.dec, self.skip_att, self.dec_att = [], [], [], []
+        att = lambda p: dict(w1=sd[p + "fc.0.weight"].float().flatten(1).contiguous().to(device),   # noqa: E731
+                             w2=sd[p + "fc.2.weight"].float().flatten(1).contiguous().to(device))
+        for i in range(Lr):
+            p = f"encoder.{i}."
+            self.enc.append(packed_conv_from_real(sd[p + "0.weight"], sd[p + "0.bias"], bn=bn(p + "1."), stride=self.STRIDE_E[i],
+                                                  act=1, device=device, want_bf16=want_bf16))
+        for i in range(Lr):
+            last = i == Lr - 1
+            p = f"decoder.{i}." if last else f"decoder.{i}.0."
+            self.dec.append(packed_conv_from_real(sd[p + "weight"], sd[p + "bias"], bn=None if last else bn(f"decoder.{i}.1."),
+                                                  transposed=True, up=self.UPSAMPLE[i], act=0 if last else 2, device=device,
+                                                  want_bf16=want_bf16))
+            self.skip_att.append((att(f"skip_attention.{2 * i}."), sd[f"skip_attention.{2 * i + 1}.conv1.weight"].float().reshape(2, 49).contiguous().to(device)))
+            if not last:
+                self.dec_att.append((att(f"decoder_attention.{2 * i}."), sd[f"decoder_attention.{2 * i + 1}.conv1.weight"].float().reshape(2, 49).contiguous().to(device)))
+        self.fc = packed_conv_from_real(sd["fc.weight"][:, :, None, None], sd["fc.bias"], device=device, want_bf16=want_bf16)
+        # nn.LSTM(256 -> 128, 2 layers, bidirectional): [layer][dir] -> (w_ih (4H, in), w_hh (4H, H), b_ih + b_hh)
+        self.lstm = []
+        for layer in range(2):
+            dirs = []
+            for suf in ("", "_reverse"):
+                k = f"lstm.{{}}_l{layer}{suf}"
+                dirs.append(dict(w_ih=sd[k.format("weight_ih")].float().contiguous().to(device),
+                                 w_hh=sd[k.format("weight_hh")].float().contiguous().to(device),
+                                 bias=(sd[k.format("bias_ih")] + sd[k.format("bias_hh")]).float().contiguous().to(device)))
+            self.lstm.append(dirs)

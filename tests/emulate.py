@@ -137,3 +137,65 @@ def strip_geometry(sp, src0, src1, out_hw):
                     oy = j * uh + g["ph0"] + c0 // run
                     out[:, oy, x0 * uw:(x0 + nx) * uw] = acc[:, :nx, c0:c0 + run].reshape(B, nx * uw, N)
     return out.reshape(B, OH, OW, pk.cout, 2)
+
+
+def rnet_dataflow(pk, mag):
+    """R_NETWORK.forward (r_network.py:125-173) evaluated through packing.PackedRNet: every conv / fc / BatchNorm goes
+    through the kernel operand definitions (conv_geometry on channel-pair tensors), the real CBAM and the real LSTM use the
+    packed weights with plain torch arithmetic (the definitions the round-2 kernels will implement).  mag: (B, F, T) fp32."""
+    import torch.nn.functional as F
+    B, Fb, T = mag.shape
+    Lr = pk.L
+
+    def out_hw(p, H, W):
+        if p.up != (1, 1):
+            return H * p.up[0], W * p.up[1]
+        return (H + 2 * (p.kh // 2) - p.kh) // p.stride[0] + 1, (W + 2 * (p.kw // 2) - p.kw) // p.stride[1] + 1
+
+    def real(t):      # (B,H,W,C/2,2) channel pairs -> (B,H,W,C) real channels
+        return t.reshape(t.shape[0], t.shape[1], t.shape[2], -1)
+
+    def attention(x, ca, w7):
+        xr = real(x)                                                  # (B,H,W,C)
+        m = xr.amax(dim=(1, 2))                                       # global max pool (the only branch that counts)
+        gate = torch.sigmoid(F.relu(m @ ca["w1"].double().T) @ ca["w2"].double().T)   # (B,C)
+        u = xr * gate[:, None, None, :]
+        st = torch.stack([u.mean(dim=3), u.amax(dim=3)], dim=1)      # (B,2,H,W)
+        s = torch.sigmoid(F.conv2d(st, w7.double().reshape(1, 2, 7, 7), padding=3))[:, 0]
+        return (u * s[..., None]).reshape(x.shape)
+
+    a6 = pk.bn0.double()[0]
+    x = torch.zeros(B, Fb, T, 1, 2, dtype=torch.float64)
+    x[..., 0, 0] = a6[0] * mag.double() + a6[4]                       # initial BatchNorm2d on the magnitude (pair's .im stays 0)
+    enc = [x]
+    H, W = Fb, T
+    for i in range(Lr):
+        H, W = out_hw(pk.enc[i], H, W)
+        enc.append(conv_geometry(pk.enc[i], enc[i], None, (H, W)))
+    e = real(enc[-1])                                                 # (B,H,W,256)
+    seq = e.reshape(B, H * W, -1)
+    for layer in range(2):
+        outs = []
+        for d, w in enumerate(pk.lstm[layer]):
+            Hd = w["w_hh"].shape[1]
+            h = torch.zeros(B, Hd, dtype=torch.float64)
+            c = torch.zeros(B, Hd, dtype=torch.float64)
+            out = torch.zeros(B, seq.shape[1], Hd, dtype=torch.float64)
+            steps = range(seq.shape[1] - 1, -1, -1) if d else range(seq.shape[1])
+            for t in steps:
+                g = seq[:, t] @ w["w_ih"].double().T + h @ w["w_hh"].double().T + w["bias"].double()
+                i_, f_, g_, o_ = g.chunk(4, dim=1)
+                c = torch.sigmoid(f_) * c + torch.sigmoid(i_) * torch.tanh(g_)
+                h = torch.sigmoid(o_) * torch.tanh(c)
+                out[:, t] = h
+            outs.append(out)
+        seq = torch.cat(outs, dim=2)
+    lat = seq.reshape(B, 1, H * W, -1, 2)                             # sequence index = h * W + w (flatten(2, 3))
+    d = conv_geometry(pk.fc, lat, None, (1, H * W)).reshape(B, H, W, -1, 2)
+    for i in range(Lr):
+        skip = attention(enc[Lr - i], *pk.skip_att[i])
+        H, W = out_hw(pk.dec[i], H, W)
+        d = conv_geometry(pk.dec[i], d, skip, (H, W))
+        if i != Lr - 1:
+            d = attention(d, *pk.dec_att[i])
+    return torch.sigmoid(d[..., 0, 0])                                # 1-channel output in the pair's .re

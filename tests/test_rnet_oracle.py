@@ -121,3 +121,18 @@ def test_real_conv_packing_reproduces_the_reference_layers(layer):
         got = conv_geometry(pk, _pairs(d), _pairs(skip), (oh, ow))
     got = got.reshape(2, oh, ow, -1)[..., :ref.shape[1]].permute(0, 3, 1, 2)
     assert rel_err(got, ref) <= 2e-6
+
+
+def test_whole_rnetwork_through_the_packed_operands_matches_reference_golden():
+    """packing.PackedRNet (BN folds, channel pairing, concat order, sub-pixel phases of the up-sampling, LSTM / CBAM weight
+    layouts) evaluated by tests/emulate.rnet_dataflow reproduces the mask the reference's R_NETWORK produced."""
+    from dcsnet_b200 import packing
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emulate import rnet_dataflow
+    g = torch.load(GOLDEN)
+    net = product_net()
+    randomise_bn(net.state_dict(), g["bn_seed"])
+    pk = packing.PackedRNet(net.state_dict())
+    spec = O.stft(g["noisy_audio"])
+    mask = rnet_dataflow(pk, torch.abs(spec))
+    assert rel_err(mask, g["mask"]) <= 1e-5
