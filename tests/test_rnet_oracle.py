@@ -136,3 +136,47 @@ def test_whole_rnetwork_through_the_packed_operands_matches_reference_golden():
     spec = O.stft(g["noisy_audio"])
     mask = rnet_dataflow(pk, torch.abs(spec))
     assert rel_err(mask, g["mask"]) <= 1e-5
+
+
+@pytest.mark.gpu
+def test_gpu_real_encoder_and_decoder_convs_on_the_existing_kernels():
+    """First GPU piece of the real path: R_NETWORK's BatchNorm'd magnitude, its 7 encoder convs (fp32 CUDA-core kernels) and
+    a decoder stage (cat + up-sampling + ConvTranspose2d + BN + LeakyReLU; fp32 and the tcgen05 bf16 kernel) run on the
+    EXISTING complex-conv kernels from packing.PackedRNet operands and match the oracle's layer taps."""
+    from dcsnet_b200 import packing, ops
+    import torch.nn.functional as F
+    g = torch.load(GOLDEN)
+    net = product_net()
+    randomise_bn(net.state_dict(), g["bn_seed"])
+    sd = net.state_dict()
+    pk = packing.PackedRNet(sd, device="cuda", want_bf16=True)
+    spec = O.stft(g["noisy_audio"])
+    mag = torch.abs(spec)
+    taps = {}
+    RO.r_network_forward(sd, mag, taps=taps)
+    B, Fb, T = mag.shape
+    x = torch.zeros(B, Fb, T, 1, 2, device="cuda")
+    x[..., 0, 0] = mag.cuda()
+    x = ops.cbn_apply(x, pk.bn0)
+    H, W = Fb, T
+    for i in range(7):
+        H, W = ops.conv_out_hw(pk.enc[i], H, W)
+        y = torch.empty(B, H, W, pk.enc[i].cout, 2, device="cuda")
+        ops.cconv(pk.enc[i], x, None, y, use_tc=False)
+        x = y
+        got = y.reshape(B, H, W, -1).permute(0, 3, 1, 2).cpu()
+        assert rel_err(got, taps[f"enc{i}"]) <= 1e-5, i
+    # decoder stage 1 on random inputs: (cat + Upsample(2,1) + ConvTranspose2d + BN + LeakyReLU)
+    gen = torch.Generator().manual_seed(9)
+    convt, bn = net.decoder[1][0], net.decoder[1][1]
+    c = convt.in_channels // 2
+    d, skip = torch.randn(2, c, 4, 8, generator=gen), torch.randn(2, c, 4, 8, generator=gen)
+    ref = F.leaky_relu(F.batch_norm(F.conv_transpose2d(F.interpolate(torch.cat((d, skip), 1), scale_factor=(2, 1), mode="nearest"),
+                                                       convt.weight, convt.bias, stride=1, padding=1),
+                                    bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, 1e-5))
+    cl = lambda t: t.permute(0, 2, 3, 1).reshape(t.shape[0], t.shape[2], t.shape[3], -1, 2).contiguous().cuda()   # noqa: E731
+    for dtype, use_tc, tol in ((torch.float32, False, 1e-5), (torch.bfloat16, True, 1.5e-2)):
+        out = torch.empty(2, 8, 8, pk.dec[1].cout, 2, device="cuda", dtype=dtype)
+        ops.cconv(pk.dec[1], cl(d).to(dtype), cl(skip).to(dtype), out, use_tc=use_tc)
+        got = out.float().reshape(2, 8, 8, -1).permute(0, 3, 1, 2).cpu()
+        assert rel_err(got, ref) <= tol, dtype
