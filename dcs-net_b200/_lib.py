@@ -31,6 +31,11 @@ class FrontendParams(C.Structure):
                 ("clean16", _vp), ("noisy16", _vp), ("noise16", _vp), ("flags", _vp)]
 
 
+class RealAttentionParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("h", _i), ("w", _i), ("channels", _i), ("reduced", _i), ("dtype", _i),
+                ("w1", _vp), ("w2", _vp), ("w7", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 class IstftParams(C.Structure):
     _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
                 ("mag", _vp), ("phase", _vp)]
@@ -134,6 +139,8 @@ SYMBOLS = {
     "dcs_abi_version": (_i, []),
     "dcs_last_error_string": (C.c_char_p, []),
     "dcs_launch_count": (C.c_uint64, []),
+    "dcs_real_attention_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "dcs_real_attention_fwd": (_i, [C.POINTER(RealAttentionParams), _vp]),
     "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),

@@ -205,6 +205,24 @@ def attention_stream(x, sums, ca, w7, y):
     return y
 
 
+def real_attention(x, att, w7, y=None, workspace=None):
+    """RealChannelAttention + RealSpatialAttention (r_network.py:8-40) on a channels-last real tensor (B, H, W, C) — or the
+    same memory viewed as channel pairs (B, H, W, C/2, 2).  att = dict(w1 (R, C), w2 (C, R)), w7 = conv1.weight flattened."""
+    L.require_cuda(x)
+    shp = x.shape
+    xr = x.reshape(shp[0], shp[1], shp[2], -1)
+    B, H, W, Cn = xr.shape
+    if y is None:
+        y = torch.empty_like(x)
+    need = int(L.lib().dcs_real_attention_workspace_bytes(B, H, W, Cn))
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+    p = L.RealAttentionParams(L.ptr(x), L.ptr(y), B, H, W, Cn, att["w1"].shape[0], _code(x), L.ptr(att["w1"]), L.ptr(att["w2"]),
+                              L.ptr(w7), L.ptr(workspace), workspace.numel() * workspace.element_size())
+    L.check(L.lib().dcs_real_attention_fwd(C.byref(p), L.stream_ptr()), "dcs_real_attention_fwd")
+    return y
+
+
 def clstm_workspace_bytes(B, S, hidden=64):
     n = L.lib().dcs_clstm_workspace_bytes(B, S, hidden)
     if n < 0:

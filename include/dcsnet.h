@@ -207,6 +207,19 @@ int dcs_attention_fused(const dcs_attention_params* p, void* stream);
  * once.  Replaces dcs_spat_stats + dcs_spat_apply on the bf16 path (csrc/attention_stream.cu). */
 int dcs_attention_stream(const dcs_attention_params* p, void* stream);
 
+/* ---- f1 (real path): RealChannelAttention + RealSpatialAttention (r_network.py:8-40; applied at
+ *      152-156, 163-165) on a channels-last REAL tensor x (B, H, W, C), fp32 or bf16 (`dtype`), C a power of two <= 256:
+ *      gate_c = sigmoid(W2 relu(W1 maxpool_hw(x))) with w1 (R, C), w2 (C, R) (only the max-pool branch counts, line 24);
+ *      u = gate_c * x; gate_s = sigmoid(conv7x7([mean_c u, max_c u])) with w7 = conv1.weight (1, 2, 7, 7) flattened;
+ *      y = gate_s * u (same dtype as x).  workspace: dcs_real_attention_workspace_bytes(). */
+typedef struct {
+  const void* x; void* y; int batch; int h; int w; int channels; int reduced; int dtype;
+  const float* w1; const float* w2; const float* w7;
+  void* workspace; int64_t workspace_bytes;
+} dcs_real_attention_params;
+int64_t dcs_real_attention_workspace_bytes(int batch, int h, int w, int channels);
+int dcs_real_attention_fwd(const dcs_real_attention_params* p, void* stream);
+
 /* ---- a7: ComplexLSTM (c_network.py:12-51): real_lstm / imag_lstm = nn.LSTM(128->64, 2 layers, bidirectional),
  *      out = (R(re) - I(im)) + j (R(im) + I(re)).  x (B,S,D) complex channels-last (the latent, sequence index
  *      = h*W'+w, c_network.py:200) -> y (B,S,2*hidden) complex fp32.

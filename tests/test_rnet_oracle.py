@@ -180,3 +180,24 @@ def test_gpu_real_encoder_and_decoder_convs_on_the_existing_kernels():
         ops.cconv(pk.dec[1], cl(d).to(dtype), cl(skip).to(dtype), out, use_tc=use_tc)
         got = out.float().reshape(2, 8, 8, -1).permute(0, 3, 1, 2).cpu()
         assert rel_err(got, ref) <= tol, dtype
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("C,H,W", [(16, 12, 9), (64, 7, 20), (256, 2, 5), (32, 33, 70)])
+def test_gpu_real_attention_matches_oracle(C, H, W):
+    """dcs_real_attention_fwd (RealChannelAttention + RealSpatialAttention, r_network.py:8-40) vs the oracle, fp32 and bf16."""
+    from dcsnet_b200 import ops
+    g = torch.Generator().manual_seed(C + H)
+    R = max(C // 16, 1)
+    sd = {"a.fc.0.weight": 0.3 * torch.randn(R, C, 1, 1, generator=g), "a.fc.2.weight": 0.5 * torch.randn(C, R, 1, 1, generator=g),
+          "s.conv1.weight": 0.2 * torch.randn(1, 2, 7, 7, generator=g)}
+    x = torch.randn(3, C, H, W, generator=g)
+    u = RO.channel_attention(x, sd, "a.") * x
+    ref = RO.spatial_attention(u, sd, "s.") * u
+    att = dict(w1=sd["a.fc.0.weight"].flatten(1).contiguous().cuda(), w2=sd["a.fc.2.weight"].flatten(1).contiguous().cuda())
+    w7 = sd["s.conv1.weight"].reshape(2, 49).contiguous().cuda()
+    xcl = x.permute(0, 2, 3, 1).contiguous().cuda()
+    for dtype, tol in ((torch.float32, 1e-5), (torch.bfloat16, 1.5e-2)):
+        got = ops.real_attention(xcl.to(dtype), att, w7)
+        torch.cuda.synchronize()
+        assert rel_err(got.float().permute(0, 3, 1, 2).cpu(), ref) <= tol, dtype
