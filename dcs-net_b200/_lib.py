@@ -36,6 +36,11 @@ class RealAttentionParams(C.Structure):
                 ("w1", _vp), ("w2", _vp), ("w7", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class RlstmParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("in_dtype", _i),
+                ("w_ih0_t", _vp), ("w_ih1_t", _vp), ("w_hh_t", _vp), ("bias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 class IstftParams(C.Structure):
     _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
                 ("mag", _vp), ("phase", _vp)]
@@ -141,6 +146,8 @@ SYMBOLS = {
     "dcs_launch_count": (C.c_uint64, []),
     "dcs_real_attention_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "dcs_real_attention_fwd": (_i, [C.POINTER(RealAttentionParams), _vp]),
+    "dcs_rlstm_workspace_bytes": (_i64, [_i, _i, _i]),
+    "dcs_rlstm_fwd": (_i, [C.POINTER(RlstmParams), _vp]),
     "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),

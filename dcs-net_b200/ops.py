@@ -223,6 +223,23 @@ def real_attention(x, att, w7, y=None, workspace=None):
     return y
 
 
+def rlstm(x, w, y=None, workspace=None):
+    """nn.LSTM(D -> 128, 2 layers, bidirectional) of the real path: x (B, S, D) fp32 -> (B, S, 256) fp32.
+    w = packing.PackedRNet(...).lstm_t."""
+    L.require_cuda(x)
+    B, S, D = x.shape
+    H = w["w_hh_t"].shape[2]
+    if y is None:
+        y = torch.empty(B, S, 2 * H, dtype=torch.float32, device=x.device)
+    need = int(L.lib().dcs_rlstm_workspace_bytes(B, S, H))
+    if workspace is None:
+        workspace = torch.empty(need, dtype=torch.uint8, device=x.device)
+    p = L.RlstmParams(L.ptr(x), L.ptr(y), B, S, D, H, _code(x), L.ptr(w["w_ih0_t"]), L.ptr(w["w_ih1_t"]), L.ptr(w["w_hh_t"]),
+                      L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size())
+    L.check(L.lib().dcs_rlstm_fwd(C.byref(p), L.stream_ptr()), "dcs_rlstm_fwd")
+    return y
+
+
 def clstm_workspace_bytes(B, S, hidden=64):
     n = L.lib().dcs_clstm_workspace_bytes(B, S, hidden)
     if n < 0:

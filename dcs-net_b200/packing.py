@@ -486,3 +486,8 @@ class PackedRNet:
                                  w_hh=sd[k.format("weight_hh")].float().contiguous().to(device),
                                  bias=(sd[k.format("bias_ih")] + sd[k.format("bias_hh")]).float().contiguous().to(device)))
             self.lstm.append(dirs)
+        # the same weights transposed for dcs_rlstm_fwd: w_ih*_t [in][2*4H] (columns dir*4H + gate row), w_hh_t [layer][dir][H][4H]
+        cat_t = lambda layer, k: torch.cat([d[k].t() for d in self.lstm[layer]], dim=1).contiguous()   # noqa: E731
+        self.lstm_t = dict(w_ih0_t=cat_t(0, "w_ih"), w_ih1_t=cat_t(1, "w_ih"),
+                           w_hh_t=torch.stack([torch.stack([d["w_hh"].t().contiguous() for d in self.lstm[layer]]) for layer in range(2)]).contiguous(),
+                           bias=torch.stack([torch.cat([d["bias"] for d in self.lstm[layer]]) for layer in range(2)]).contiguous())

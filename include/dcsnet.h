@@ -220,6 +220,18 @@ typedef struct {
 int64_t dcs_real_attention_workspace_bytes(int batch, int h, int w, int channels);
 int dcs_real_attention_fwd(const dcs_real_attention_params* p, void* stream);
 
+/* ---- f1 (real path): nn.LSTM(D -> 128, 2 layers, bidirectional, batch_first) of r_network.py:70-74 / 137-139.
+ *      x (B, S, D) fp32 (the channels-last latent viewed as a sequence) -> y (B, S, 256) fp32.  Weights transposed for the
+ *      kernels: w_ih0_t [D][2*4H] and w_ih1_t [2H][2*4H] (columns dir*4H + gate row, gate order i f g o),
+ *      w_hh_t [layer][dir][H][4H], bias [layer][2*4H] = b_ih + b_hh (packing.PackedRNet.lstm_t). */
+typedef struct {
+  const void* x; float* y; int batch; int seq; int in_dim; int hidden; int in_dtype;
+  const float* w_ih0_t; const float* w_ih1_t; const float* w_hh_t; const float* bias;
+  void* workspace; int64_t workspace_bytes;
+} dcs_rlstm_params;
+int64_t dcs_rlstm_workspace_bytes(int batch, int seq, int hidden);
+int dcs_rlstm_fwd(const dcs_rlstm_params* p, void* stream);
+
 /* ---- a7: ComplexLSTM (c_network.py:12-51): real_lstm / imag_lstm = nn.LSTM(128->64, 2 layers, bidirectional),
  *      out = (R(re) - I(im)) + j (R(im) + I(re)).  x (B,S,D) complex channels-last (the latent, sequence index
  *      = h*W'+w, c_network.py:200) -> y (B,S,2*hidden) complex fp32.

@@ -201,3 +201,18 @@ def test_gpu_real_attention_matches_oracle(C, H, W):
         got = ops.real_attention(xcl.to(dtype), att, w7)
         torch.cuda.synchronize()
         assert rel_err(got.float().permute(0, 3, 1, 2).cpu(), ref) <= tol, dtype
+
+
+@pytest.mark.gpu
+def test_gpu_real_lstm_matches_torch_lstm():
+    """dcs_rlstm_fwd (nn.LSTM(256 -> 128, 2 layers, bidirectional) of r_network.py:70-74) vs torch.nn.LSTM on the CPU."""
+    from dcsnet_b200 import packing, ops
+    net = product_net()
+    pk = packing.PackedRNet(net.state_dict(), device="cuda")
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 21, 256, generator=g)
+    with torch.no_grad():
+        ref, _ = net.lstm(x)
+    got = ops.rlstm(x.cuda(), pk.lstm_t)
+    torch.cuda.synchronize()
+    assert rel_err(got.cpu(), ref) <= 2e-5
