@@ -470,7 +470,7 @@ class PackedRNet:
             last = i == Lr - 1
             p = f"decoder.{i}." if last else f"decoder.{i}.0."
             self.dec.append(packed_conv_from_real(sd[p + "weight"], sd[p + "bias"], bn=None if last else bn(f"decoder.{i}.1."),
-                                                  transposed=True, up=self.UPSAMPLE[i], act=0 if last else 2, device=device,
+                                                  transposed=True, up=self.UPSAMPLE[i], act=3 if last else 2, device=device,   # last: torch.sigmoid (r_network.py:172)
                                                   want_bf16=want_bf16))
             self.skip_att.append((att(f"skip_attention.{2 * i}."), sd[f"skip_attention.{2 * i + 1}.conv1.weight"].float().reshape(2, 49).contiguous().to(device)))
             if not last:

@@ -3,13 +3,17 @@ RealSpatialAttention and R_NETWORK(config, hparams, seed) — same constructor s
 order, hence the same 158 state_dict keys / shapes and, for a given seed, bit-identical random-init weights (pinned by
 tests/test_rnet_oracle.py against tests/golden/rnet_*.pt, which were produced by the reference's own r_network.py).
 
-ROUND-1 STATUS: the parameter containers, the CPU oracle (oracle/rnet_oracle.py) and its reference-generated golden
-vectors exist; the sm_100a kernels of the real path do not yet (real convs reuse the implicit-GEMM kernels with real
-packing, but the max-pool channel attention, the real spatial attention, the 256 -> 128 real LSTM and the
-sigmoid / magnitude-mask tail need their own kernels).  `forward` therefore raises — there is no ATen / CPU fallback.
+ROUND-1 STATUS: `R_NETWORK.forward` runs in eval mode, fp32, as a sequence of sm_100a kernels (first, un-tuned path):
+the BatchNorm'd magnitude (dcs_cbn_apply), every Conv2d / ConvTranspose2d + BatchNorm2d + activation on the fp32 conv
+kernel through real packing (packing.PackedRNet: real channels 2c, 2c+1 <-> (re, im) of a channel pair; cat + nearest
+up-sampling folded into the decoder GEMMs; the final sigmoid in the last epilogue), the real CBAM (dcs_real_attention_fwd)
+and the real LSTM (dcs_rlstm_fwd).  No ATen / CPU fallback: CPU tensors and train mode raise.  The stand-alone attention
+modules are parameter containers (their forward raises); bf16 / tensor-core mode, CUDA-graph capture and the
+magnitude-mask / iSTFT step are the next steps.
 """
 import torch
 
+from . import ops, packing
 from .c_network import _Base, _seed_everything
 
 
@@ -89,6 +93,34 @@ class R_NETWORK(_Base):
             if isinstance(m, (torch.nn.Conv2d, torch.nn.ConvTranspose2d, torch.nn.Linear)):
                 init(m.weight)
 
+    def _packed(self, device):
+        key = (str(device),) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if getattr(self, "_pk_key", None) != key:
+            self._pk, self._pk_key = packing.PackedRNet(self.state_dict(), device=device, no_of_layers=self.hparams['no_of_layers']), key
+        return self._pk
+
     def forward(self, x):
-        raise NotImplementedError("dcsnet_b200.R_NETWORK: the real (dr / drs) forward has no sm_100a kernels yet "
-                                  "(SURVEY 8f rank 1; oracle: oracle/rnet_oracle.py); there is no CPU / ATen fallback")
+        """r_network.py:125-173: x (B, F, T) fp32 magnitude -> sigmoid mask, squeezed."""
+        if self.training:
+            raise NotImplementedError("dcsnet_b200.R_NETWORK: only the eval-mode forward is built (training step: SURVEY 8f rank 2)")
+        if not x.is_cuda:
+            raise RuntimeError("dcsnet_b200.R_NETWORK.forward needs CUDA tensors (sm_100a); there is no CPU fallback")
+        pk, Lr = self._packed(x.device), self.hparams['no_of_layers']
+        B, Fb, T = x.shape
+        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=x.device)   # noqa: E731
+        t = torch.zeros(B, Fb, T, 1, 2, dtype=torch.float32, device=x.device)
+        t[..., 0, 0].copy_(x)                                     # magnitude in the pair's first slot, 0 in the padding slot
+        enc = [ops.cbn_apply(t, pk.bn0)]                          # initial_batchnorm
+        H, W = Fb, T
+        for i in range(Lr):
+            H, W = ops.conv_out_hw(pk.enc[i], H, W)
+            enc.append(ops.cconv(pk.enc[i], enc[i], None, new(B, H, W, pk.enc[i].cout, 2)))
+        lat = ops.rlstm(enc[-1].view(B, H * W, -1), pk.lstm_t)    # sequence index = h * W + w (flatten(2, 3).permute(0, 2, 1))
+        d = ops.cconv(pk.fc, lat.view(B, 1, H * W, -1, 2), None, new(B, 1, H * W, pk.fc.cout, 2)).view(B, H, W, pk.fc.cout, 2)
+        for i in range(Lr):
+            skip = ops.real_attention(enc[Lr - i], *pk.skip_att[i])
+            H, W = H * pk.dec[i].up[0], W * pk.dec[i].up[1]
+            d = ops.cconv(pk.dec[i], d, skip, new(B, H, W, pk.dec[i].cout, 2))
+            if i != Lr - 1:
+                d = ops.real_attention(d, *pk.dec_att[i])
+        return torch.squeeze(d[..., 0, 0])                        # sigmoid applied by the last conv's epilogue

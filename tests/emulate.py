@@ -33,6 +33,8 @@ def conv_geometry(pk, src0, src1, out_hw, weights="ffma"):
                 acc = acc.clamp_min(0)
             elif pk.act == 2:
                 acc = torch.where(acc > 0, acc, 0.01 * acc)
+            elif pk.act == 3:
+                acc = torch.sigmoid(acc)
             out[:, ph::uh, pw::uw] = acc[..., :2 * pk.cout]
     return out.reshape(B, OH, OW, pk.cout, 2)
 
@@ -198,4 +200,4 @@ def rnet_dataflow(pk, mag):
         d = conv_geometry(pk.dec[i], d, skip, (H, W))
         if i != Lr - 1:
             d = attention(d, *pk.dec_att[i])
-    return torch.sigmoid(d[..., 0, 0])                                # 1-channel output in the pair's .re
+    return d[..., 0, 0]                                               # 1-channel output in the pair's .re (sigmoid = the packed activation)

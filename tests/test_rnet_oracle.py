@@ -66,8 +66,26 @@ def test_channel_attention_uses_only_the_max_pool_branch():
 
 def test_product_forward_fails_loudly_without_fallback():
     net = product_net()
-    with pytest.raises(NotImplementedError, match="no CPU"):
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
         net(torch.rand(2, 256, 64))
+    with pytest.raises(NotImplementedError):
+        net.train()(torch.rand(2, 256, 64))
+
+
+@pytest.mark.gpu
+def test_gpu_rnetwork_forward_matches_reference_golden():
+    """R_NETWORK.forward on the B200 (fp32 kernel sequence) vs the mask the reference's own R_NETWORK produced."""
+    g = torch.load(GOLDEN)
+    net = product_net()
+    randomise_bn(net.state_dict(), g["bn_seed"])
+    net = net.cuda().eval()
+    spec = O.stft(g["noisy_audio"])
+    n0 = D._lib.launch_count()
+    mask = net(torch.abs(spec).cuda())
+    torch.cuda.synchronize()
+    assert D._lib.launch_count() - n0 >= 7 + 7 + 13 * 4 + 6          # convs, attentions, LSTM: all from libdcsnet_sm100a.so
+    assert tuple(mask.shape) == tuple(g["mask"].shape)
+    assert rel_err(mask.cpu(), g["mask"]) <= 1e-5
 
 
 # ------------------------------------------------------------------ real convs on the complex-conv operand layout (CPU emulation)
