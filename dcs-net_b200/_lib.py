@@ -169,6 +169,8 @@ SYMBOLS = {
     "dcs_bound_crm": (_i, [_vp, _vp, _i64, _f, _i, _vp]),
     "dcs_cmul": (_i, [_vp, _vp, _vp, _i64, _vp]),
     "dcs_crm": (_i, [_vp, _vp, _vp, _i64, _f, _vp]),
+    "dcs_mag_phase": (_i, [_vp, _vp, _vp, _i64, _f, _vp]),
+    "dcs_real_mask_combine": (_i, [_vp, _vp, _i64, _vp, _vp, _i64, _i, _vp]),
     "dcs_upsample_nearest": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_tc_set_debug_buffer": (_i, [_vp]),
     "dcs_convert": (_i, [_vp, _vp, _i64, _i, _i, _vp]),

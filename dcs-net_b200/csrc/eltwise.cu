@@ -185,6 +185,39 @@ extern "C" int dcs_cmul(const float* a, const float* b, float* y, int64_t n, voi
   DCS_LAUNCHED();
   return 0;
 }
+// ---- real path (dr / drs) step functions: network_functions.py:286-288 (magnitude, phase = atan2(im, re + eps)) and
+//      296-305 / 338-342 (magnitude-mask combine).  mask may be a strided view: element i of image-major (B, F*T) at
+//      mask[i * mask_stride].
+namespace dcs {
+__global__ void mag_phase_kernel(const float2* __restrict__ s, float* __restrict__ mag, float* __restrict__ phase, int64_t n, float eps) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = s[i];
+    mag[i] = hypotf(v.x, v.y);                  // torch.abs(complex64)
+    if (phase) phase[i] = atan2f(v.y, v.x + eps);
+  }
+}
+__global__ void real_mask_combine_kernel(const float* __restrict__ mag, const float* __restrict__ mask, int64_t mask_stride,
+                                         float* __restrict__ clean, float* __restrict__ noise, int64_t n, int subtract) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float m = mag[i], pm = m * mask[i * mask_stride];
+    if (subtract) { clean[i] = m - pm; if (noise) noise[i] = pm; }   // drs: noise mask, clean = noisy - noise
+    else clean[i] = pm;                                              // dr: the mask applies to the speech directly
+  }
+}
+}  // namespace dcs
+extern "C" int dcs_mag_phase(const float* spec, float* mag, float* phase, int64_t n, float atan2_eps, void* stream) {
+  DCS_REQUIRE(spec && mag && n > 0, "dcs_mag_phase: bad arguments");
+  mag_phase_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)spec, mag, phase, n, atan2_eps);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_real_mask_combine(const float* mag, const float* mask, int64_t mask_stride, float* clean_mag, float* noise_mag,
+                                     int64_t n, int subtract, void* stream) {
+  DCS_REQUIRE(mag && mask && clean_mag && n > 0 && mask_stride > 0, "dcs_real_mask_combine: bad arguments");
+  real_mask_combine_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>(mag, mask, mask_stride, clean_mag, noise_mag, n, subtract);
+  DCS_LAUNCHED();
+  return 0;
+}
 extern "C" int dcs_crm(const float* s, const float* y_noisy, float* m, int64_t n, float eps, void* stream) {
   DCS_REQUIRE(s && y_noisy && m && n > 0, "dcs_crm: bad arguments");
   crm_kernel<<<ew_grid(n, 256), 256, 0, (cudaStream_t)stream>>>((const float2*)s, (const float2*)y_noisy, (float2*)m, n, eps);

@@ -311,6 +311,34 @@ def cmul(a, b):
     return y
 
 
+def mag_phase(spec, atan2_eps=10e-7, want_phase=True):
+    """|spec| and atan2(im, re + eps) of a complex64 tensor (network_functions.py:286-288)."""
+    L.require_cuda(spec)
+    spec = spec.contiguous()
+    mag = torch.empty(spec.shape, dtype=torch.float32, device=spec.device)
+    phase = torch.empty_like(mag) if want_phase else None
+    L.check(L.lib().dcs_mag_phase(L.ptr(spec), L.ptr(mag), L.ptr(phase), spec.numel(), float(atan2_eps), L.stream_ptr()), "dcs_mag_phase")
+    return mag, phase
+
+
+def real_mask_combine(mag, mask, subtract):
+    """dr (subtract=False): clean = mag * mask; drs (True): noise = mag * mask, clean = mag - noise (network_functions.py:296-305,
+    338-342).  `mask` may be the strided (B, F, T) view R_NETWORK.forward returns."""
+    L.require_cuda(mag, mask)
+    assert mag.is_contiguous() and mask.shape == mag.shape and mask.dtype == torch.float32
+    st = mask.stride()
+    exp, acc = [], 1
+    for n_ in reversed(mask.shape):
+        exp.append(acc); acc *= n_
+    unit = st[-1]
+    assert tuple(st) == tuple(unit * e for e in reversed(exp)), "mask must be a contiguous tensor or a uniformly strided view of one"
+    clean = torch.empty_like(mag)
+    noise = torch.empty_like(mag) if subtract else None
+    L.check(L.lib().dcs_real_mask_combine(L.ptr(mag), L.ptr(mask), unit, L.ptr(clean), L.ptr(noise), mag.numel(), int(subtract),
+                                          L.stream_ptr()), "dcs_real_mask_combine")
+    return clean, noise
+
+
 def crm(S, Y, eps=1e-8):
     L.require_cuda(S, Y)
     S, Y = S.contiguous(), Y.contiguous()

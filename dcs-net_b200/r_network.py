@@ -124,3 +124,16 @@ class R_NETWORK(_Base):
             if i != Lr - 1:
                 d = ops.real_attention(d, *pk.dec_att[i])
         return torch.squeeze(d[..., 0, 0])                        # sigmoid applied by the last conv's epilogue
+
+
+def enhance_batch_real(network, noisy_spec, variant="drs", atan2_eps=10e-7):
+    """The inference lines of the reference's real-path step functions (network_functions.py:286-305 drs, 338-342 dr) on the
+    GPU: |Y|, noisy phase, mask = network(|Y|), magnitude combine, mag_phase_2_wave with the NOISY phase (iSTFT kernel)."""
+    assert variant in ("dr", "drs")
+    mag, phase = ops.mag_phase(noisy_spec, atan2_eps)
+    mask = network(mag)
+    if mask.dim() == 2:
+        mask = mask[None]
+    clean_mag, noise_mag = ops.real_mask_combine(mag, mask, subtract=variant == "drs")
+    return dict(predict_noise_mask=mask, predict_clean_mag=clean_mag, predict_noise_mag=noise_mag,
+                predict_clean_audio=ops.istft_mag_phase(clean_mag, phase))

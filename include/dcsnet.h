@@ -292,6 +292,12 @@ int dcs_dec6_tail_fwd(const dcs_dec6_tail_params* p, void* stream);
 int dcs_bound_crm(const float* x, float* y, int64_t n, float atan2_eps, int exact_polar, void* stream);
 int dcs_cmul(const float* a, const float* b, float* y, int64_t n, void* stream);
 int dcs_crm(const float* s, const float* y_noisy, float* m, int64_t n, float eps, void* stream);
+/* real path (dr / drs) step functions: magnitude + phase = atan2(im, re + eps) of a complex64 array (network_functions.py:
+ * 286-288; phase may be NULL) and the magnitude-mask combine (296-305: subtract = 1, clean = mag - mag*mask, noise = mag*mask;
+ * 338-342: subtract = 0, clean = mag*mask).  mask element i is read at mask[i * mask_stride]. */
+int dcs_mag_phase(const float* spec, float* mag, float* phase, int64_t n, float atan2_eps, void* stream);
+int dcs_real_mask_combine(const float* mag, const float* mask, int64_t mask_stride, float* clean_mag, float* noise_mag,
+                          int64_t n, int subtract, void* stream);
 
 /* ---- a11 stand-alone: complex_upsample(mode='nearest') (complexPyTorch; c_network.py:215) on channels-last complex.
  *      (The fused path never materialises this: see dcs_cconv_params.up_h/up_w.) */

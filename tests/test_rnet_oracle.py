@@ -234,3 +234,18 @@ def test_gpu_real_lstm_matches_torch_lstm():
     got = ops.rlstm(x.cuda(), pk.lstm_t)
     torch.cuda.synchronize()
     assert rel_err(got.cpu(), ref) <= 2e-5
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["drs", "dr"])
+def test_gpu_real_step_matches_reference_golden(variant):
+    """|Y| / noisy phase / mask / magnitude combine / mag_phase_2_wave of the dr and drs step functions, all on the GPU."""
+    from dcsnet_b200 import r_network
+    g = torch.load(GOLDEN)
+    net = product_net()
+    randomise_bn(net.state_dict(), g["bn_seed"])
+    net = net.cuda().eval()
+    out = r_network.enhance_batch_real(net, O.stft(g["noisy_audio"]).cuda(), variant)
+    torch.cuda.synchronize()
+    assert rel_err(out["predict_clean_mag"].cpu(), g[f"{variant}_clean_mag"]) <= 1e-5
+    assert rel_err(out["predict_clean_audio"].cpu(), g[f"{variant}_clean_audio"]) <= 2e-5
