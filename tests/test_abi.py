@@ -38,12 +38,13 @@ def test_exports_are_plain_c():
 
 def test_struct_sizes_match_header():
     """ctypes mirrors of the POD parameter structs must have the C compiler's layout."""
-    src = '#include <stdio.h>\n#include "dcsnet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
+    src = '#include <stdio.h>\n#include "dcsnet.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",' \
           'sizeof(dcs_stft_params),sizeof(dcs_istft_params),sizeof(dcs_cbn_params),sizeof(dcs_cconv_params),' \
           'sizeof(dcs_chan_pool_params),sizeof(dcs_chan_gate_params),sizeof(dcs_spat_stats_params),' \
           'sizeof(dcs_spat_apply_params),sizeof(dcs_clstm_params),sizeof(dcs_mask_combine_params),' \
           'sizeof(dcs_strip_item),sizeof(dcs_strip_group),sizeof(dcs_strip_tail),sizeof(dcs_cstrip_params),' \
-          'sizeof(dcs_attention_params),sizeof(dcs_enc0_params),sizeof(dcs_dec6_tail_params),sizeof(dcs_frontend_params));return 0;}'
+          'sizeof(dcs_attention_params),sizeof(dcs_enc0_params),sizeof(dcs_dec6_tail_params),sizeof(dcs_frontend_params),'\
+          'sizeof(dcs_real_attention_params),sizeof(dcs_rlstm_params));return 0;}'
     import tempfile
     with tempfile.TemporaryDirectory() as d:
         c = os.path.join(d, "s.c")
@@ -55,7 +56,7 @@ def test_struct_sizes_match_header():
                                        L.ChanGateParams, L.SpatStatsParams, L.SpatApplyParams, L.ClstmParams,
                                        L.MaskCombineParams)] + [16] + \
            [ctypes.sizeof(t) for t in (L.StripGroup, L.StripTail, L.CstripParams, L.AttentionParams, L.Enc0Params, L.Dec6TailParams,
-                                       L.FrontendParams)]
+                                       L.FrontendParams, L.RealAttentionParams, L.RlstmParams)]
     assert sizes == mine
 
 
@@ -71,3 +72,10 @@ def test_argument_errors_are_reported_not_swallowed():
     assert lib.dcs_cconv2d_strip_fwd(ctypes.byref(r), None) != 0 and b"null pointer" in lib.dcs_last_error_string()
     assert lib.dcs_clstm_workspace_bytes(2, 10, 32) < 0  # only hidden=64 is built
     assert lib.dcs_clstm_workspace_bytes(2, 10, 64) > 0
+    # entries added for the next rows (front-end, real path): same contract
+    for params, fn in ((L.FrontendParams, lib.dcs_frontend_fwd), (L.RealAttentionParams, lib.dcs_real_attention_fwd),
+                       (L.RlstmParams, lib.dcs_rlstm_fwd), (L.AttentionParams, lib.dcs_attention_stream)):
+        assert fn(ctypes.byref(params()), None) != 0 and b"null pointer" in lib.dcs_last_error_string()
+    assert lib.dcs_rlstm_workspace_bytes(2, 10, 128) == 2 * 10 * 10 * 128 * 4 and lib.dcs_rlstm_workspace_bytes(0, 10, 128) < 0
+    assert lib.dcs_real_attention_workspace_bytes(2, 4, 5, 16) > 0 and lib.dcs_real_attention_workspace_bytes(2, 0, 5, 16) < 0
+    assert lib.dcs_mag_phase(None, None, None, 4, 1e-6, None) != 0 and b"bad arguments" in lib.dcs_last_error_string()
