@@ -249,3 +249,28 @@ def test_gpu_real_step_matches_reference_golden(variant):
     torch.cuda.synchronize()
     assert rel_err(out["predict_clean_mag"].cpu(), g[f"{variant}_clean_mag"]) <= 1e-5
     assert rel_err(out["predict_clean_audio"].cpu(), g[f"{variant}_clean_audio"]) <= 2e-5
+
+
+@pytest.mark.parametrize("layer,merged,groups", [("enc1", True, 1), ("enc2", True, 1), ("dec4", False, 2), ("dec5", True, 1)])
+def test_real_layers_pack_for_the_row_strip_kernel(layer, merged, groups):
+    """The bf16 / tensor-core real path will reuse the row-strip kernel: packing.StripConv built from a REAL layer's
+    PackedConv describes the same convolution as its per-tap operands (CPU emulation of the kernel's item table)."""
+    from dcsnet_b200 import packing, ops
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from emulate import conv_geometry, strip_geometry
+    net = product_net()
+    randomise_bn(net.state_dict(), 7)
+    pk = packing.PackedRNet(net.state_dict(), want_bf16=True)
+    p = {"enc1": pk.enc[1], "enc2": pk.enc[2], "dec4": pk.dec[4], "dec5": pk.dec[5]}[layer]
+    g = torch.Generator().manual_seed(13)
+    if layer.startswith("enc"):
+        H, W = 6, 260
+        srcs, c0, c1 = [torch.randn(2, H, W, p.cin, 2, generator=g), None], p.cin, 0
+    else:
+        H, W = 3, 131
+        c = p.cin // 2
+        srcs, c0, c1 = [torch.randn(2, H, W, c, 2, generator=g), torch.randn(2, H, W, c, 2, generator=g)], c, c
+    srcs = [None if t is None else t.to(torch.bfloat16).float() for t in srcs]
+    sp = packing.StripConv(p, c0, c1, merged=merged, groups=groups)
+    out_hw = ops.conv_out_hw(p, H, W)
+    assert rel_err(strip_geometry(sp, srcs[0], srcs[1], out_hw), conv_geometry(p, srcs[0], srcs[1], out_hw, weights="tc")) <= 1e-2
