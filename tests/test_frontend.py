@@ -54,7 +54,6 @@ def test_oracle_resample_matches_torchaudio_when_available():
 def test_start_point_rules_host_logic():
     """data.py:96-104: short utterances start at 0, long ones draw from [0, data_len - window), equal lengths fail as in
     the reference (torch.randint(0, 0))."""
-    spec = __import__("importlib").util.spec_from_file_location("fe_host", os.path.join(ROOT, "dcs-net_b200", "frontend.py"))
     import dcsnet_b200 as D
     sp = D.GpuFrontEnd.draw_start_points([20000, 48000 * 2 + 1], 8160, torch.Generator().manual_seed(0))
     assert sp[0] == 0 and 0 <= sp[1] < 32001 - 8160
