@@ -129,3 +129,116 @@ def enhance_batch(net, noisy_data, variant="dcs"):
     if out["noise_spec"] is not None:
         res["predict_noise_audio"] = ops.istft(out["noise_spec"], atan2_eps=eps, exact_polar=plan.exact)
     return res
+
+
+# ------------------------------------------------------------------ evaluation step (test.py's per-batch function)
+def _variant(self, variant):
+    import sys
+    v = variant or getattr(self, "variant", None) or (sys.argv[1] if len(sys.argv) > 1 else None)
+    if v not in ("dcs", "drs", "dc", "dr"):
+        raise ValueError("dcsnet_b200: variant must be one of dcs / drs / dc / dr (the reference reads sys.argv[1])")
+    return v
+
+
+def calc_loss(self, variant=None, **kwargs):
+    """network_functions.py:168-208, argument names unchanged; `variant` replaces the reference's read of sys.argv[1]
+    (used as the default when not given).  Note the reference's precedence at line 196: 1 - (speech_alpha * loss)."""
+    v = _variant(self, variant)
+    hp, cfg = self.hparams, self.config
+    if v in ("dcs", "drs"):
+        t = hp['noise_loss_type']
+        wsdr = lambda: cfg.wSDR(kwargs['noisy_audio'], kwargs['noise_audio'], kwargs['predict_noise_audio'])
+        l1_mask = lambda: cfg.L1(kwargs['target_noise_mask'], kwargs['predict_noise_mask'])
+        l1_audio = lambda: cfg.L1(kwargs['noise_audio'], kwargs['predict_noise_audio'])
+        if t == 0:
+            orig = l1_mask()
+        elif t == 1:
+            orig = wsdr()
+        elif t == 2:
+            orig = l1_mask() + l1_audio()
+        elif t == 3:
+            orig = wsdr() + l1_audio()
+        elif t == 4:
+            orig = wsdr() + l1_mask()
+        elif t == 5:
+            tm, pm = kwargs['target_noise_mask'], kwargs['predict_noise_mask']
+            if tm.is_complex():
+                orig = wsdr() + cfg.mse(tm.real, pm.real) + cfg.mse(tm.imag, pm.imag)
+            else:
+                orig = wsdr() + cfg.mse(tm, pm)
+        elif t == 6:
+            orig = -cfg.SiSNR(kwargs['noise_audio'], kwargs['predict_noise_audio'])
+        else:
+            raise ValueError("noise_loss_type must be 0..6")
+        noise_loss = 1 - hp['speech_alpha'] * orig
+    if hp['speech_loss_type'] != 0:
+        raise ValueError("speech_loss_type must be 0")
+    speech_loss = hp['speech_alpha'] * (-cfg.SiSNR(kwargs['clean_audio'], kwargs['predict_clean_audio']))
+    if v in ("dcs", "drs"):
+        return noise_loss, speech_loss, noise_loss + speech_loss
+    return speech_loss
+
+
+def calc_metric(clean_audio, predict_audio, config, metric):
+    """network_functions.py:152-166: mean of a per-utterance CPU metric (pesq / stoi are third-party CPU code)."""
+    from math import isnan
+    vals = []
+    for i in range(predict_audio.shape[0]):
+        m = metric(clean_audio[i, :].cpu().numpy(), predict_audio[i, :].cpu().numpy(), config.sr)
+        if not isnan(m):
+            vals.append(m)
+    return float(sum(vals)) / max(len(vals), 1)
+
+
+def test_batch_2_metric_loss(self, test_batch, test_idx, dtype, variant=None, metrics=None):
+    """network_functions.py:363-448 with the tensor work on the GPU kernels: the three reference iSTFTs
+    (`dcs_istft_fwd`), target mask (`dcs_crm` + `dcs_bound_crm`, or sigmoid(|N| / |Y|) for the real path), the network
+    + mask combine + iSTFT (`enhance_batch` / `enhance_batch_real`), then `calc_loss`.  Same return tuple as the reference.
+    `metrics` = {"pesq": fn, "stoi": fn} (pypesq / pystoi signatures); when a metric is not given and its package is not
+    installed its average is NaN — nothing else on this path touches the CPU."""
+    v = _variant(self, variant)
+    noise_data, noisy_data, clean_data, id, start_point = test_batch
+    eps = self.hparams['atan2_eps']
+    noise_audio = ops.istft(noise_data, atan2_eps=eps, exact_polar=True)
+    noisy_audio = ops.istft(noisy_data, atan2_eps=eps, exact_polar=True)
+    clean_audio = ops.istft(clean_data, atan2_eps=eps, exact_polar=True)
+
+    two_mask = v in ("dcs", "drs")             # the reference branches on sys.argv[1] alone; dtype picks the arithmetic
+    if dtype == "complex":
+        out = enhance_batch(self, noisy_data, variant="dcs" if two_mask else "dc")
+        if two_mask:
+            target_noise_mask = bound_cRM(cRM(noise_data, noisy_data), self.hparams)
+    elif dtype == "real":
+        from .r_network import enhance_batch_real
+        out = enhance_batch_real(self, noisy_data, variant="drs" if two_mask else "dr", atan2_eps=eps)
+        if two_mask:
+            noise_mag, _ = ops.mag_phase(noise_data, eps, want_phase=False)
+            target_noise_mask = torch.sigmoid(noise_mag / out["noisy_mag"])
+    else:
+        raise ValueError("dtype must be 'real' or 'complex'")
+    predict_clean_audio = out["predict_clean_audio"]
+
+    def average(name):
+        fn = (metrics or {}).get(name)
+        if fn is None:
+            try:
+                fn = getattr(__import__("pypesq" if name == "pesq" else "pystoi"), name)
+            except ImportError:
+                return float("nan")
+        return calc_metric(clean_audio, predict_clean_audio, self.config, fn)
+    pesq_av, stoi_av = average("pesq"), average("stoi")
+
+    if two_mask:
+        predict_noise_audio = out["predict_noise_audio"]
+        noise_loss, speech_loss, test_loss = calc_loss(self, variant=v, target_noise_mask=target_noise_mask,
+                                                       predict_noise_mask=out["predict_noise_mask"],
+                                                       predict_noise_audio=predict_noise_audio,
+                                                       predict_clean_audio=predict_clean_audio, noise_audio=noise_audio,
+                                                       noisy_audio=noisy_audio, clean_audio=clean_audio)
+        return noise_loss, speech_loss, test_loss, pesq_av, stoi_av, predict_noise_audio, predict_clean_audio, \
+            noise_audio, noisy_audio, clean_audio, id, start_point
+    speech_loss = calc_loss(self, variant=v, predict_clean_audio=predict_clean_audio, clean_audio=clean_audio)
+    return speech_loss, pesq_av, stoi_av, predict_clean_audio, noise_audio, noisy_audio, clean_audio
+
+
+test_batch_2_metric_loss.__test__ = False   # not a pytest test

@@ -135,5 +135,8 @@ def enhance_batch_real(network, noisy_spec, variant="drs", atan2_eps=10e-7):
     if mask.dim() == 2:
         mask = mask[None]
     clean_mag, noise_mag = ops.real_mask_combine(mag, mask, subtract=variant == "drs")
-    return dict(predict_noise_mask=mask, predict_clean_mag=clean_mag, predict_noise_mag=noise_mag,
-                predict_clean_audio=ops.istft_mag_phase(clean_mag, phase))
+    res = dict(predict_noise_mask=mask, predict_clean_mag=clean_mag, predict_noise_mag=noise_mag, noisy_mag=mag, noisy_phase=phase,
+               predict_clean_audio=ops.istft_mag_phase(clean_mag, phase))
+    if noise_mag is not None:                                     # drs: network_functions.py:304 / 390
+        res["predict_noise_audio"] = ops.istft_mag_phase(noise_mag, phase)
+    return res
