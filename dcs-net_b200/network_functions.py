@@ -190,14 +190,11 @@ def calc_metric(clean_audio, predict_audio, config, metric):
     return float(sum(vals)) / max(len(vals), 1)
 
 
-def test_batch_2_metric_loss(self, test_batch, test_idx, dtype, variant=None, metrics=None):
-    """network_functions.py:363-448 with the tensor work on the GPU kernels: the three reference iSTFTs
-    (`dcs_istft_fwd`), target mask (`dcs_crm` + `dcs_bound_crm`, or sigmoid(|N| / |Y|) for the real path), the network
-    + mask combine + iSTFT (`enhance_batch` / `enhance_batch_real`), then `calc_loss`.  Same return tuple as the reference.
-    `metrics` = {"pesq": fn, "stoi": fn} (pypesq / pystoi signatures); when a metric is not given and its package is not
-    installed its average is NaN — nothing else on this path touches the CPU."""
+def _eval_batch(self, noise_data, noisy_data, clean_data, dtype, variant, metrics):
+    """Shared body of val_ / test_batch_2_metric_loss (network_functions.py:282-361, 363-448): the tensor work on the GPU
+    kernels — three iSTFTs (`dcs_istft_fwd`), target mask (`dcs_crm` + `dcs_bound_crm`, or sigmoid(|N| / |Y|) for the real
+    path), network + mask combine + iSTFT (`enhance_batch` / `enhance_batch_real`) — then `calc_loss`."""
     v = _variant(self, variant)
-    noise_data, noisy_data, clean_data, id, start_point = test_batch
     eps = self.hparams['atan2_eps']
     noise_audio = ops.istft(noise_data, atan2_eps=eps, exact_polar=True)
     noisy_audio = ops.istft(noisy_data, atan2_eps=eps, exact_polar=True)
@@ -230,15 +227,30 @@ def test_batch_2_metric_loss(self, test_batch, test_idx, dtype, variant=None, me
 
     if two_mask:
         predict_noise_audio = out["predict_noise_audio"]
-        noise_loss, speech_loss, test_loss = calc_loss(self, variant=v, target_noise_mask=target_noise_mask,
-                                                       predict_noise_mask=out["predict_noise_mask"],
-                                                       predict_noise_audio=predict_noise_audio,
-                                                       predict_clean_audio=predict_clean_audio, noise_audio=noise_audio,
-                                                       noisy_audio=noisy_audio, clean_audio=clean_audio)
-        return noise_loss, speech_loss, test_loss, pesq_av, stoi_av, predict_noise_audio, predict_clean_audio, \
-            noise_audio, noisy_audio, clean_audio, id, start_point
+        noise_loss, speech_loss, total = calc_loss(self, variant=v, target_noise_mask=target_noise_mask,
+                                                   predict_noise_mask=out["predict_noise_mask"],
+                                                   predict_noise_audio=predict_noise_audio,
+                                                   predict_clean_audio=predict_clean_audio, noise_audio=noise_audio,
+                                                   noisy_audio=noisy_audio, clean_audio=clean_audio)
+        return (noise_loss, speech_loss, total, pesq_av, stoi_av, predict_noise_audio, predict_clean_audio,
+                noise_audio, noisy_audio, clean_audio)
     speech_loss = calc_loss(self, variant=v, predict_clean_audio=predict_clean_audio, clean_audio=clean_audio)
     return speech_loss, pesq_av, stoi_av, predict_clean_audio, noise_audio, noisy_audio, clean_audio
+
+
+def val_batch_2_metric_loss(self, val_batch, val_idx, dtype, variant=None, metrics=None):
+    """network_functions.py:282-361, same return tuple.  `variant` replaces the reference's read of sys.argv[1];
+    `metrics` = {"pesq": fn, "stoi": fn} (pypesq / pystoi signatures) — a metric that is neither given nor installed
+    averages to NaN; nothing else on this path touches the CPU."""
+    noise_data, noisy_data, clean_data, id = val_batch
+    return _eval_batch(self, noise_data, noisy_data, clean_data, dtype, variant, metrics)
+
+
+def test_batch_2_metric_loss(self, test_batch, test_idx, dtype, variant=None, metrics=None):
+    """network_functions.py:363-448, same return tuple (dcs / drs append id and start_point; dc / dr do not, line 446)."""
+    noise_data, noisy_data, clean_data, id, start_point = test_batch
+    r = _eval_batch(self, noise_data, noisy_data, clean_data, dtype, variant, metrics)
+    return r + (id, start_point) if len(r) == 10 else r
 
 
 test_batch_2_metric_loss.__test__ = False   # not a pytest test

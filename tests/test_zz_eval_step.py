@@ -82,6 +82,57 @@ def test_evaluation_step_refuses_cpu_tensors():
         NF.test_batch_2_metric_loss(net, (nb, yb, cb, ["a", "b"], torch.zeros(2)), 0, "complex", variant="dcs")
 
 
+@pytest.mark.parametrize("variant", ["dcs", "dc", "drs", "dr"])
+def test_evaluation_step_plumbing_with_oracle_stand_ins(variant, monkeypatch):
+    """Host logic only: with every kernel wrapper the step calls replaced by the oracle's CPU function of the same contract,
+    val_ / test_batch_2_metric_loss must reproduce the reference's losses, audio and return-tuple layout for all variants.
+    (The kernels themselves are checked by the -m gpu tests; this one pins the glue between them.)"""
+    from dcsnet_b200 import network_functions as NF, ops, r_network, config as C
+    from oracle import rnet_oracle as RO
+    g = load_golden("eval_step.pt")
+    want = g[variant]
+    monkeypatch.setattr(ops, "istft", lambda spec, audio=None, atan2_eps=1e-6, exact_polar=False: O.spec_to_wave(spec, atan2_eps))
+    monkeypatch.setattr(ops, "mag_phase", lambda spec, eps=10e-7, want_phase=True: (torch.abs(spec), None))
+    monkeypatch.setattr(NF, "cRM", _crm)
+    monkeypatch.setattr(NF, "bound_cRM", lambda m, hp: O.bound_crm(m, hp["atan2_eps"]))
+
+    def fake_complex(net, noisy, variant="dcs"):
+        r = O.enhance_spec(net.state_dict(), noisy, variant)
+        d = dict(predict_noise_mask=r["mask"], predict_clean_audio=O.spec_to_wave(r["clean_spec"]))
+        if r["noise_spec"] is not None:
+            d["predict_noise_audio"] = O.spec_to_wave(r["noise_spec"])
+        return d
+
+    def fake_real(net, noisy, variant="drs", atan2_eps=10e-7):
+        r = RO.enhance_spec(net.state_dict(), noisy, variant)
+        phase = torch.atan2(noisy.imag, noisy.real + atan2_eps)
+        d = dict(predict_noise_mask=r["mask"], predict_clean_audio=r["clean_audio"], noisy_mag=torch.abs(noisy))
+        if r["noise_mag"] is not None:
+            d["predict_noise_audio"] = RO.mag_phase_2_wave(r["noise_mag"], phase)
+        return d
+    monkeypatch.setattr(NF, "enhance_batch", fake_complex)
+    monkeypatch.setattr(r_network, "enhance_batch_real", fake_real)
+    if variant in ("dcs", "dc"):
+        net, dtype = build_product_net("randbn"), "complex"
+    else:
+        net = r_network.R_NETWORK(C.Config(), dict(C.hparams), 0).eval()
+        randomise_bn(net.state_dict(), g["bn_seed"])
+        dtype = "real"
+    nb, yb, cb = _batch(g)
+    r = NF.test_batch_2_metric_loss(net, (nb, yb, cb, ["id0", "id1"], torch.tensor([0, 0])), 0, dtype, variant=variant,
+                                    metrics=dict(pesq=lambda c, p, sr: 1.0, stoi=lambda c, p, sr: float("nan")))
+    assert len(r) == want["n_returned"]
+    if variant in ("dcs", "drs"):
+        assert abs(float(r[0]) - want["noise_loss"]) <= LOSS_TOL and abs(float(r[2]) - want["test_loss"]) <= LOSS_TOL
+        assert abs(float(r[1]) - want["speech_loss"]) <= LOSS_TOL
+        assert rel_err(r[5], want["predict_noise_audio"]) <= 1e-4 and rel_err(r[6], want["predict_clean_audio"]) <= 1e-4
+        assert (r[3], r[4]) == (1.0, 0.0) and r[10] == ["id0", "id1"]          # NaN metric values are dropped (line 161)
+    else:
+        assert abs(float(r[0]) - want["speech_loss"]) <= LOSS_TOL and rel_err(r[3], want["predict_clean_audio"]) <= 1e-4
+    rv = NF.val_batch_2_metric_loss(net, (nb, yb, cb, ["id0", "id1"]), 0, dtype, variant=variant, metrics=dict(pesq=lambda c, p, sr: 1.0))
+    assert len(rv) == (10 if variant in ("dcs", "drs") else 7) and float(rv[0]) == float(r[0])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("variant", ["dcs", "dc", "drs", "dr"])
 def test_gpu_evaluation_step_matches_reference(variant):
@@ -111,3 +162,6 @@ def test_gpu_evaluation_step_matches_reference(variant):
     assert abs(float(speech_loss) - want["speech_loss"]) <= LOSS_TOL
     assert rel_err(predict_clean_audio, want["predict_clean_audio"]) <= 1e-4
     assert (pesq_av, stoi_av) == (1.0, 0.5)
+    # the validation function is the same step on a 4-tuple batch, without id / start_point (network_functions.py:282-361)
+    rv = NF.val_batch_2_metric_loss(net, (nb, yb, cb, ["id0", "id1"]), 0, dtype, variant=variant)
+    assert len(rv) == (10 if variant in ("dcs", "drs") else 7) and abs(float(rv[0]) - float(r[0])) <= 1e-6
