@@ -165,3 +165,23 @@ def test_gpu_evaluation_step_matches_reference(variant):
     # the validation function is the same step on a 4-tuple batch, without id / start_point (network_functions.py:282-361)
     rv = NF.val_batch_2_metric_loss(net, (nb, yb, cb, ["id0", "id1"]), 0, dtype, variant=variant)
     assert len(rv) == (10 if variant in ("dcs", "drs") else 7) and abs(float(rv[0]) - float(r[0])) <= 1e-6
+
+
+@pytest.mark.parametrize("variant", ["dcs", "drs"])
+def test_training_step_fixture_lines_up_with_the_product_parameters(variant):
+    """tests/golden/train_step.pt (reference `train_batch_2_loss` + backward, oracle/make_golden_train.py) is the pin for the
+    training step that is still to be built.  Until then: the fixture must describe exactly the product
+    containers' parameters (names and shapes), with finite losses and gradients, so the backward kernels have a target."""
+    import math
+    from dcsnet_b200 import r_network, config as C
+    g = load_golden("train_step.pt")[variant]
+    net = build_product_net("default") if variant == "dcs" else r_network.R_NETWORK(C.Config(), dict(C.hparams), 0)
+    params = {k: tuple(torch.view_as_real(p).shape) if p.is_complex() else tuple(p.shape) for k, p in net.named_parameters()}
+    assert set(params) == set(g["grads"]) | set(g["no_grad"])
+    for k, f in g["grads"].items():
+        assert params[k] == f["shape"], k
+        assert math.isfinite(f["norm"]) and bool(torch.isfinite(f["head"]).all()), k
+    assert all(math.isfinite(g[k]) for k in ("noise_loss", "speech_loss", "train_loss", "grad_norm"))
+    assert abs(g["noise_loss"] + g["speech_loss"] - g["train_loss"]) < 1e-4
+    assert abs(math.sqrt(sum(f["norm"] ** 2 for f in g["grads"].values())) - g["grad_norm"]) <= 1e-3 * g["grad_norm"]
+    assert {k for k in net.state_dict() if "running_" in k} == set(g["running_stats"])
