@@ -174,13 +174,17 @@ def bound_crm(m, eps=HPARAMS["atan2_eps"]):
     return torch.complex(t * torch.cos(th2), t * torch.sin(th2))
 
 
-def c_network_forward(sd, x, hp=HPARAMS, taps=None, explicit_lstm=False):
+def c_network_forward(sd, x, hp=HPARAMS, taps=None, explicit_lstm=False, bn=None, drop=None):
     """C_NETWORK.forward in eval mode (c_network.py:187-226).  x: (B,F,T) complex64 -> bounded mask, squeezed.
 
     `taps`, if a dict, receives named intermediate activations (NCHW complex64) for per-layer parity tests.
+    `bn(x, sd, prefix)` / `drop(x, kind)` replace the eval-mode batch norm / the identity dropout for the train-mode
+    restatement in oracle/train_oracle.py (dropout sits at c_network.py:195, 203, 221).
     """
     L = hp["no_of_layers"]
     tap = (lambda k, v: taps.__setitem__(k, v)) if taps is not None else (lambda k, v: None)
+    cbn_eval = bn or globals()["cbn_eval"]
+    drop = drop or (lambda t, kind: t)
     e = cbn_eval(x.view(x.shape[0], -1, x.shape[1], x.shape[2]), sd, "initial_batchnorm.")
     tap("bn0", e)
     enc = [e]
@@ -189,6 +193,7 @@ def c_network_forward(sd, x, hp=HPARAMS, taps=None, explicit_lstm=False):
         e = cconv2d(enc[i], sd, f"encoder.{i}.0.", STRIDE_E[i], k // 2)
         e = crelu(cbn_eval(e, sd, f"encoder.{i}.1."))
         tap(f"enc{i}", e)
+        e = drop(e, "conv")
         enc.append(e)  # dropout is the identity in eval mode (c_network.py:195-196)
     shp = enc[-1].shape
     seq = torch.flatten(e, 2, 3).permute(0, 2, 1)
@@ -196,6 +201,7 @@ def c_network_forward(sd, x, hp=HPARAMS, taps=None, explicit_lstm=False):
     tap("lstm", lo)
     fo = clinear(lo, sd, "fc.")
     tap("fc", fo)
+    fo = drop(fo, "fc")
     d = fo.permute(0, 2, 1).reshape(shp)
     for i in range(L):
         skip = enc[L - i]
@@ -213,6 +219,7 @@ def c_network_forward(sd, x, hp=HPARAMS, taps=None, explicit_lstm=False):
             d = d * channel_attention(d, sd, f"decoder_attention.{2 * i}.")
             d = d * spatial_attention(d, sd, f"decoder_attention.{2 * i + 1}.", hp["spatial_attention_kernel_size"])
         tap(f"dec{i}", d)
+        d = drop(d, "conv")
     out = torch.squeeze(d)  # also drops the batch dim at B=1 (Appendix D6)
     return bound_crm(out, hp["atan2_eps"])
 

@@ -1,0 +1,87 @@
+"""CPU restatement of the reference's TRAINING step for the complex path (TEST INFRASTRUCTURE ONLY).
+
+No product code exists for this row yet; this is its oracle, pinned by tests/golden/train_step.pt (the reference's own
+`train_batch_2_loss` + `backward()`, oracle/make_golden_train.py).  The forward is oracle/dcsnet_oracle.c_network_forward
+with train-mode ComplexBatchNorm2d (batch statistics, running-stat update; complexPyTorch 0.3) and an
+optional dropout hook; gradients come from torch autograd over this restatement.
+
+Reference lines followed:
+  train_batch_2_loss ........ network_functions.py:210-280 (dcs: 236-258, dc: 271-280)
+  calc_loss ................. network_functions.py:168-208 (noise_loss_type 6, speech_loss_type 0 = config.py defaults)
+  ComplexBatchNorm2d.train .. complexPyTorch/complexLayers.py (momentum 0.1, unbiased running covariance)
+  dropout positions ......... c_network.py:195, 203, 221 (on view_as_real, i.e. real and imaginary parts drop independently)
+"""
+import torch
+
+from . import dcsnet_oracle as O
+
+BN_MOMENTUM = 0.1
+
+
+def cbn_train(new_stats):
+    """Returns bn(x, sd, prefix): batch-statistic complex whitening + affine; the updated running statistics go to `new_stats`."""
+    def bn(x, sd, p, eps=O.BN_EPS):
+        b = lambda v: v[None, :, None, None]  # noqa: E731
+        mean = torch.complex(x.real.mean([0, 2, 3]), x.imag.mean([0, 2, 3]))
+        x = x - b(mean)
+        n = x.numel() / x.size(1)
+        Crr = x.real.pow(2).sum(dim=[0, 2, 3]) / n + eps
+        Cii = x.imag.pow(2).sum(dim=[0, 2, 3]) / n + eps
+        Cri = (x.real * x.imag).mean(dim=[0, 2, 3])
+        with torch.no_grad():
+            m = BN_MOMENTUM
+            new_stats[p + "running_mean"] = m * mean + (1 - m) * sd[p + "running_mean"]
+            cov = sd[p + "running_covar"]
+            new_stats[p + "running_covar"] = torch.stack([m * Crr * n / (n - 1) + (1 - m) * cov[:, 0],
+                                                          m * Cii * n / (n - 1) + (1 - m) * cov[:, 1],
+                                                          m * Cri * n / (n - 1) + (1 - m) * cov[:, 2]], dim=1)
+        s = torch.sqrt(Crr * Cii - Cri.pow(2))
+        t = torch.sqrt(Cii + Crr + 2 * s)
+        ist = 1.0 / (s * t)
+        Rrr, Rii, Rri = (Cii + s) * ist, (Crr + s) * ist, -Cri * ist
+        re, im = b(Rrr) * x.real + b(Rri) * x.imag, b(Rii) * x.imag + b(Rri) * x.real
+        w, c = sd[p + "weight"], sd[p + "bias"]
+        return torch.complex(b(w[:, 0]) * re + b(w[:, 2]) * im + b(c[:, 0]), b(w[:, 2]) * re + b(w[:, 1]) * im + b(c[:, 1]))
+    return bn
+
+
+def dropout_from_masks(masks):
+    """drop(x, kind) applying caller-supplied keep masks in call order (scaled 1 / (1 - p) by the caller); None = identity."""
+    it = iter(masks)
+
+    def drop(x, kind):
+        m = next(it)
+        return x if m is None else torch.view_as_complex(torch.view_as_real(x) * m)
+    return drop
+
+
+def _mul(a, b):
+    return torch.complex(a.real * b.real - a.imag * b.imag, a.real * b.imag + a.imag * b.real)
+
+
+def train_step(sd, noise_spec, noisy_spec, clean_spec, param_names, variant="dcs", hp=O.HPARAMS, speech_alpha=0.7, drop=None):
+    """One training step's forward + backward.  `sd`: reference-format state_dict (not modified); `param_names`: the keys
+    that are nn.Parameters (the rest are buffers).  Returns dict(noise_loss, speech_loss, train_loss, grads{name: tensor},
+    running_stats{name: tensor})."""
+    eps = hp["atan2_eps"]
+    live = {k: (v.detach().clone().requires_grad_(True) if k in param_names else v) for k, v in sd.items()}
+    stats = {}
+    mask_out = O.c_network_forward(live, noisy_spec, hp, explicit_lstm=True, bn=cbn_train(stats), drop=drop)
+    if mask_out.dim() == 2:
+        mask_out = mask_out[None]
+    mask = O.bound_crm(mask_out, eps)                                   # second bound, network_functions.py:240 / 273
+    prod = _mul(noisy_spec, mask)
+    wave = lambda s: O.spec_to_wave(s, eps)                             # noqa: E731
+    clean_audio = wave(clean_spec)
+    if variant == "dcs":
+        noise_loss = 1 - speech_alpha * (-O.si_snr(wave(noise_spec), wave(prod)))        # line 195-196 (precedence as written)
+        speech_loss = speech_alpha * (-O.si_snr(clean_audio, wave(noisy_spec - prod)))
+        total = noise_loss + speech_loss
+    else:
+        noise_loss = None
+        speech_loss = speech_alpha * (-O.si_snr(clean_audio, wave(prod)))
+        total = speech_loss
+    total.backward()
+    return dict(noise_loss=None if noise_loss is None else float(noise_loss.detach()), speech_loss=float(speech_loss.detach()),
+                train_loss=float(total.detach()), grads={k: live[k].grad for k in param_names if live[k].grad is not None},
+                running_stats=stats)
