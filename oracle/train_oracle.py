@@ -1,4 +1,5 @@
-"""CPU restatement of the reference's TRAINING step for the complex path (TEST INFRASTRUCTURE ONLY).
+"""CPU restatement of the reference's TRAINING step, complex (dcs / dc) and real (drs / dr) networks (TEST INFRASTRUCTURE ONLY;
+SURVEY 8f rank 2).
 
 No product code exists for this row yet; this is its oracle, pinned by tests/golden/train_step.pt (the reference's own
 `train_batch_2_loss` + `backward()`, oracle/make_golden_train.py).  The forward is oracle/dcsnet_oracle.c_network_forward
@@ -80,6 +81,33 @@ def train_step(sd, noise_spec, noisy_spec, clean_spec, param_names, variant="dcs
     else:
         noise_loss = None
         speech_loss = speech_alpha * (-O.si_snr(clean_audio, wave(prod)))
+        total = speech_loss
+    total.backward()
+    return dict(noise_loss=None if noise_loss is None else float(noise_loss.detach()), speech_loss=float(speech_loss.detach()),
+                train_loss=float(total.detach()), grads={k: live[k].grad for k in param_names if live[k].grad is not None},
+                running_stats=stats)
+
+
+def train_step_real(sd, noise_spec, noisy_spec, clean_spec, param_names, variant="drs", speech_alpha=0.7, atan2_eps=10e-7):
+    """The real path's training step (network_functions.py:223-233 drs, 260-267 dr; r_network.py:125-173 in train mode)."""
+    from . import rnet_oracle as RO
+    live = {k: (v.detach().clone().requires_grad_(True) if k in param_names else v) for k, v in sd.items()}
+    stats = {}
+    mag = lambda s: torch.abs(s)                                          # noqa: E731
+    wave = lambda s: O.spec_to_wave(s, atan2_eps)                         # noqa: E731
+    noisy_mag, noisy_phase = mag(noisy_spec), torch.atan2(noisy_spec.imag, noisy_spec.real + atan2_eps)
+    mask = RO.r_network_forward(live, noisy_mag, train_stats=stats)
+    if mask.dim() == 2:
+        mask = mask[None]
+    clean_audio = wave(clean_spec)
+    if variant == "drs":
+        noise_mag = noisy_mag * mask
+        noise_loss = 1 - speech_alpha * (-O.si_snr(wave(noise_spec), RO.mag_phase_2_wave(noise_mag, noisy_phase)))
+        speech_loss = speech_alpha * (-O.si_snr(clean_audio, RO.mag_phase_2_wave(noisy_mag - noise_mag, noisy_phase)))
+        total = noise_loss + speech_loss
+    else:
+        noise_loss = None
+        speech_loss = speech_alpha * (-O.si_snr(clean_audio, RO.mag_phase_2_wave(noisy_mag * mask, noisy_phase)))
         total = speech_loss
     total.backward()
     return dict(noise_loss=None if noise_loss is None else float(noise_loss.detach()), speech_loss=float(speech_loss.detach()),
