@@ -49,6 +49,35 @@ except Exception:  # pragma: no cover - the image has no pytorch_lightning
         def log_dict(self, *a, **k):
             return None
 
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, map_location=None, hparams_file=None, strict=True, **kwargs):
+            """The LightningModule call test.py:20-26 makes: `C_NETWORK.load_from_checkpoint(config=, seed=, checkpoint_path=,
+            hparams_file=, map_location=)`.  Reads a Lightning `.ckpt` (`state_dict` + `hyper_parameters`, saved under the
+            constructor argument name `hparams` by `save_hyperparameters(self.hparams)`, c_network.py:93) and the optional
+            `hparams.yaml` (which wins, as in Lightning); entries a yaml python-object tag carries (the
+            `initialisation_distribution` function, config.py:33) fall back to `config.hparams`."""
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            if "state_dict" not in ckpt:
+                raise KeyError(f"{checkpoint_path}: not a Lightning checkpoint (no 'state_dict')")
+            from .config import hparams as defaults
+            hp = dict(defaults)
+            hp.update({k: v for k, v in dict(ckpt.get("hyper_parameters") or {}).items() if v is not None})
+            if hparams_file is not None:
+                hp.update({k: v for k, v in _read_hparams_yaml(hparams_file).items() if v is not None})
+            kwargs.setdefault("hparams", hp)
+            net = cls(**kwargs)
+            net.load_state_dict(ckpt["state_dict"], strict=strict)
+            return net
+
+    def _read_hparams_yaml(path):
+        import yaml
+
+        class _Loader(yaml.SafeLoader):
+            pass
+        _Loader.add_multi_constructor("tag:yaml.org,2002:python/", lambda loader, suffix, node: None)
+        with open(path) as f:
+            return dict(yaml.load(f, Loader=_Loader) or {})
+
     def _seed_everything(seed):
         seed = int(seed)
         random.seed(seed)

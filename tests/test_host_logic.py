@@ -105,3 +105,34 @@ def test_two_rank_sharding_with_gloo():
         assert p.exitcode == 0
     assert tmax == 2.0
     assert torch.equal(cat[:, 0], torch.arange(7, dtype=torch.float32))
+
+
+@pytest.mark.parametrize("kind", ["complex", "real"])
+def test_load_from_checkpoint_like_test_py(kind, tmp_path):
+    """test.py:20-26 / 36-42: `X_NETWORK.load_from_checkpoint(config=, seed=, checkpoint_path=, hparams_file=, map_location=None)`
+    on a Lightning-format checkpoint (state_dict + hyper_parameters under the name `hparams`) and an hparams.yaml whose
+    function-valued entry is a python-object tag."""
+    from dcsnet_b200 import c_network, r_network, config as C
+    cls = c_network.C_NETWORK if kind == "complex" else r_network.R_NETWORK
+    src = cls(C.config, dict(C.hparams), 3)
+    with torch.no_grad():
+        for p in src.parameters():
+            p.add_(0.01)
+    hp = {k: v for k, v in C.hparams.items() if k != "initialisation_distribution"}
+    hp["speech_alpha"] = 0.65
+    ckpt = tmp_path / "epoch=0-step=289.ckpt"
+    torch.save({"state_dict": src.state_dict(), "hyper_parameters": hp, "hparams_name": "hparams", "epoch": 0, "global_step": 289}, ckpt)
+    yml = tmp_path / "hparams.yaml"
+    yml.write_text("lr: 0.0001\nspeech_alpha: 0.6\nchannels:\n- 1\n- 16\n- 32\n- 64\n- 128\n- 256\n- 256\n- 256\n"
+                   "initialisation_distribution: !!python/name:torch.nn.init.xavier_uniform_ ''\n")
+    net = cls.load_from_checkpoint(config=C.config, seed=C.config.seed, checkpoint_path=str(ckpt), hparams_file=str(yml), map_location=None)
+    net.eval()
+    for k, v in net.state_dict().items():
+        assert torch.equal(v, src.state_dict()[k]), k
+    assert net.hparams["speech_alpha"] == 0.6 and net.hparams["noise_loss_type"] == C.hparams["noise_loss_type"]
+    assert net.hparams["initialisation_distribution"] is C.hparams["initialisation_distribution"]
+    net2 = cls.load_from_checkpoint(config=C.config, seed=0, checkpoint_path=str(ckpt))
+    assert net2.hparams["speech_alpha"] == 0.65
+    torch.save({"model": 1}, tmp_path / "bad.ckpt")
+    with pytest.raises(KeyError):
+        cls.load_from_checkpoint(config=C.config, seed=0, checkpoint_path=str(tmp_path / "bad.ckpt"))
