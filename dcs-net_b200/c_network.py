@@ -88,6 +88,70 @@ except Exception:  # pragma: no cover - the image has no pytorch_lightning
         return seed
 
 
+class _StepMixin:
+    """validation_step / test_step / configure_optimizers of the reference's LightningModules (c_network.py:228-239, 263-302,
+    337-372; r_network.py likewise) over the GPU evaluation function.  `variant` (dcs | dc | drs | dr) replaces sys.argv[1]
+    and defaults to it; `step_metrics` optionally carries {"pesq": fn, "stoi": fn}.  training_step is SURVEY 8f rank 2."""
+    _step_dtype = "complex"
+    variant = None
+    step_metrics = None
+
+    def _two_mask(self):
+        from .network_functions import _variant
+        return _variant(self, self.variant) in ("dcs", "drs")
+
+    def configure_optimizers(self):
+        optimiser = torch.optim.Adam(self.parameters(), lr=self.hparams['lr'], eps=self.hparams['optim_eps'],
+                                     weight_decay=self.hparams['optim_weight_decay'], amsgrad=self.hparams['optim_amsgrad'])
+        lr_scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimiser, patience=10)
+        return {'optimizer': optimiser, 'lr_scheduler': lr_scheduler, 'monitor': 'val_loss' if self._two_mask() else 'speech_loss'}
+
+    def training_step(self, train_batch, batch_idx):
+        raise NotImplementedError("dcsnet_b200: the training step (backward kernels) is SURVEY 8f rank 2 and not built yet")
+
+    @staticmethod
+    def _audio_dict(clean, predict_clean, noise, noisy, predict_noise=None):
+        out = {"clean": clean.cpu().numpy(), "predict_clean": predict_clean.cpu().numpy(), "noise": noise.cpu().numpy()}
+        if predict_noise is not None:
+            out["predict_noise"] = predict_noise.cpu().numpy()
+        out["noisy"] = noisy.cpu().numpy()
+        return out
+
+    def validation_step(self, val_batch, val_idx):
+        from .network_functions import val_batch_2_metric_loss
+        r = val_batch_2_metric_loss(self, val_batch, val_idx, dtype=self._step_dtype, variant=self.variant, metrics=self.step_metrics)
+        if self._two_mask():
+            noise_loss, speech_loss, val_loss, pesq_av, stoi_av, predict_noise_audio, predict_clean_audio, noise_audio, noisy_audio, clean_audio = r
+            metrics = {'val_loss': val_loss.detach(), 'val_noise_loss': noise_loss.detach(), 'val_speech_loss': speech_loss.detach(),
+                       'val_pesq': torch.tensor(pesq_av), 'val_stoi': torch.tensor(stoi_av)}
+            output = self._audio_dict(clean_audio, predict_clean_audio, noise_audio, noisy_audio, predict_noise_audio)
+            check = val_loss
+        else:
+            speech_loss, pesq_av, stoi_av, predict_clean_audio, noise_audio, noisy_audio, clean_audio = r
+            metrics = {'val_speech_loss': speech_loss.detach(), 'val_pesq': torch.tensor(pesq_av), 'val_stoi': torch.tensor(stoi_av)}
+            output = self._audio_dict(clean_audio, predict_clean_audio, noise_audio, noisy_audio)
+            check = speech_loss
+        if torch.any(torch.isnan(check)):
+            print("found a NaN in val loss!")
+            return None
+        return output, metrics
+
+    def test_step(self, test_batch, test_idx):
+        from .network_functions import test_batch_2_metric_loss
+        r = test_batch_2_metric_loss(self, test_batch, test_idx, dtype=self._step_dtype, variant=self.variant, metrics=self.step_metrics)
+        if self._two_mask():
+            noise_loss, speech_loss, test_loss, pesq_av, stoi_av, predict_noise_audio, predict_clean_audio, \
+                noise_audio, noisy_audio, clean_audio, id, start_point = r
+            metrics = {'test_loss': test_loss, 'test_noise_loss': noise_loss, 'test_speech_loss': speech_loss,
+                       'test_pesq': pesq_av, 'test_stoi': stoi_av}
+            output = self._audio_dict(clean_audio, predict_clean_audio, noise_audio, noisy_audio, predict_noise_audio)
+        else:
+            speech_loss, pesq_av, stoi_av, predict_clean_audio, noise_audio, noisy_audio, clean_audio = r
+            metrics = {'test_speech_loss': speech_loss, 'test_pesq': pesq_av, 'test_stoi': stoi_av}
+            output = self._audio_dict(clean_audio, predict_clean_audio, noise_audio, noisy_audio)
+        return output, metrics
+
+
 class ComplexLSTM(torch.nn.Module):
     def __init__(self, input_size, hidden_size, num_layers, bidirectional, batch_first, projection_dim=None):
         super(ComplexLSTM, self).__init__()
@@ -176,7 +240,7 @@ class ComplexSpatialAttention(torch.nn.Module):
         return gate.view(B, 1, H, W)
 
 
-class C_NETWORK(_Base):
+class C_NETWORK(_StepMixin, _Base):
     """c_network.py:87-226.  Extra (non-reference) attribute: `compute_mode` in {'fp32', 'bf16'} selects the CUDA-core
     fp32 GEMMs (<=1e-5) or the tcgen05 bf16 GEMMs (<=2e-3); default 'fp32' = the reference's precision=32."""
 

@@ -14,7 +14,7 @@ magnitude-mask / iSTFT step are the next steps.
 import torch
 
 from . import ops, packing
-from .c_network import _Base, _seed_everything
+from .c_network import _Base, _StepMixin, _seed_everything
 
 
 class RealChannelAttention(torch.nn.Module):
@@ -45,8 +45,9 @@ class RealSpatialAttention(torch.nn.Module):
         raise NotImplementedError("dcsnet_b200: the real (dr / drs) path has no sm_100a kernels yet (SURVEY 8f rank 1); no CPU fallback")
 
 
-class R_NETWORK(_Base):
+class R_NETWORK(_StepMixin, _Base):
     """r_network.py:43-173."""
+    _step_dtype = "real"
 
     def __init__(self, config, hparams, seed):
         super().__init__()

@@ -82,15 +82,10 @@ def test_evaluation_step_refuses_cpu_tensors():
         NF.test_batch_2_metric_loss(net, (nb, yb, cb, ["a", "b"], torch.zeros(2)), 0, "complex", variant="dcs")
 
 
-@pytest.mark.parametrize("variant", ["dcs", "dc", "drs", "dr"])
-def test_evaluation_step_plumbing_with_oracle_stand_ins(variant, monkeypatch):
-    """Host logic only: with every kernel wrapper the step calls replaced by the oracle's CPU function of the same contract,
-    val_ / test_batch_2_metric_loss must reproduce the reference's losses, audio and return-tuple layout for all variants.
-    (The kernels themselves are checked by the -m gpu tests; this one pins the glue between them.)"""
+def _install_stand_ins(monkeypatch):
+    """Replace every kernel wrapper the evaluation step calls by the oracle's CPU function of the same contract."""
     from dcsnet_b200 import network_functions as NF, ops, r_network, config as C
     from oracle import rnet_oracle as RO
-    g = load_golden("eval_step.pt")
-    want = g[variant]
     monkeypatch.setattr(ops, "istft", lambda spec, audio=None, atan2_eps=1e-6, exact_polar=False: O.spec_to_wave(spec, atan2_eps))
     monkeypatch.setattr(ops, "mag_phase", lambda spec, eps=10e-7, want_phase=True: (torch.abs(spec), None))
     monkeypatch.setattr(NF, "cRM", _crm)
@@ -112,6 +107,17 @@ def test_evaluation_step_plumbing_with_oracle_stand_ins(variant, monkeypatch):
         return d
     monkeypatch.setattr(NF, "enhance_batch", fake_complex)
     monkeypatch.setattr(r_network, "enhance_batch_real", fake_real)
+
+
+@pytest.mark.parametrize("variant", ["dcs", "dc", "drs", "dr"])
+def test_evaluation_step_plumbing_with_oracle_stand_ins(variant, monkeypatch):
+    """Host logic only: with every kernel wrapper the step calls replaced by the oracle's CPU function of the same contract,
+    val_ / test_batch_2_metric_loss must reproduce the reference's losses, audio and return-tuple layout for all variants.
+    (The kernels themselves are checked by the -m gpu tests; this one pins the glue between them.)"""
+    from dcsnet_b200 import network_functions as NF, r_network, config as C
+    g = load_golden("eval_step.pt")
+    want = g[variant]
+    _install_stand_ins(monkeypatch)
     if variant in ("dcs", "dc"):
         net, dtype = build_product_net("randbn"), "complex"
     else:
@@ -223,3 +229,37 @@ def test_training_step_oracle_matches_reference_gradients(variant):
         assert abs(float(t.norm()) - f["norm"]) <= 1e-5 * f["norm"] and float((t.reshape(-1)[:8] - f["head"]).abs().max()) <= 1e-5 * f["max_abs"], k
         n_stats += 1
     assert n_stats == 2 * 14                                   # initial BN + 7 encoder + 6 decoder layers, two statistics each
+
+
+@pytest.mark.parametrize("variant", ["dcs", "dr"])
+def test_lightning_style_steps_with_oracle_stand_ins(variant, monkeypatch):
+    """validation_step / test_step / configure_optimizers of the product networks (c_network.py:228-239, 263-302, 337-372):
+    metric names, audio dictionary and NaN handling as in the reference; kernels replaced by oracle stand-ins (host logic)."""
+    from dcsnet_b200 import r_network, config as C
+    g = load_golden("eval_step.pt")
+    _install_stand_ins(monkeypatch)
+    if variant == "dcs":
+        net = build_product_net("randbn")
+    else:
+        net = r_network.R_NETWORK(C.Config(), dict(C.hparams), 0).eval()
+        randomise_bn(net.state_dict(), g["bn_seed"])
+    net.variant = variant
+    nb, yb, cb = _batch(g)
+    out, metrics = net.test_step((nb, yb, cb, ["id0", "id1"], torch.tensor([0, 0])), 0)
+    vout, vmetrics = net.validation_step((nb, yb, cb, ["id0", "id1"]), 0)
+    if variant == "dcs":
+        assert list(metrics) == ["test_loss", "test_noise_loss", "test_speech_loss", "test_pesq", "test_stoi"]
+        assert list(out) == ["clean", "predict_clean", "noise", "predict_noise", "noisy"]
+        assert abs(float(metrics["test_loss"]) - g["dcs"]["test_loss"]) <= LOSS_TOL
+        assert list(vmetrics) == ["val_loss", "val_noise_loss", "val_speech_loss", "val_pesq", "val_stoi"]
+        assert abs(float(vmetrics["val_loss"]) - g["dcs"]["test_loss"]) <= LOSS_TOL
+    else:
+        assert list(metrics) == ["test_speech_loss", "test_pesq", "test_stoi"] and list(out) == ["clean", "predict_clean", "noise", "noisy"]
+        assert abs(float(metrics["test_speech_loss"]) - g["dr"]["speech_loss"]) <= LOSS_TOL
+        assert list(vmetrics) == ["val_speech_loss", "val_pesq", "val_stoi"]
+    assert out["predict_clean"].shape == (2, 32 * (g["T"] - 1)) and vout["clean"].dtype.name == "float32"
+    opt = net.configure_optimizers()
+    assert opt["monitor"] == ("val_loss" if variant == "dcs" else "speech_loss")
+    assert opt["optimizer"].defaults["amsgrad"] is True and opt["optimizer"].defaults["lr"] == C.hparams["lr"]
+    with pytest.raises(NotImplementedError):
+        net.training_step(None, 0)
