@@ -58,9 +58,21 @@ def main():
             total = float(torch.sqrt(sum((torch.view_as_real(p.grad) if p.grad.is_complex() else p.grad).float().pow(2).sum()
                                          for p in net.parameters() if p.grad is not None)))
             stats = {k: fp(v) for k, v in net.state_dict().items() if "running_" in k}
-            out[variant] = dict(noise_loss=float(noise_loss), speech_loss=float(speech_loss), train_loss=float(train_loss),
+            out[variant] = dict(noise_loss=float(noise_loss.detach()), speech_loss=float(speech_loss.detach()), train_loss=float(train_loss.detach()),
                                 grads=grads, no_grad=missing, grad_norm=total, running_stats=stats)
             print(variant, out[variant]["train_loss"], "grad_norm", total, len(grads), "grads", len(missing), "without grad")
+        # dropout at the reference's own probabilities (config.py:41-42): torch's CPU stream from a fixed seed.  Another
+        # implementation cannot reproduce the stream, but a restatement that draws from the same generator in the same
+        # order can — this pins WHERE dropout sits and that real and imaginary parts drop independently (c_network.py:195).
+        hp2 = dict(mods["config"].hparams)
+        with rh.argv_variant("dcs"):
+            net = mods["c_network"].C_NETWORK(mods["config"].config, hp2, 0)
+            net.train()
+            torch.manual_seed(11)
+            nl, sl, tl = nf.train_batch_2_loss(net, batch, 0, "complex")
+        out["dcs_dropout"] = dict(seed=11, dropout_conv=hp2["dropout_conv"], dropout_fc=hp2["dropout_fc"],
+                                  noise_loss=float(nl.detach()), speech_loss=float(sl.detach()), train_loss=float(tl.detach()))
+        print("dcs with dropout", out["dcs_dropout"])
     finally:
         nf.mag_phase_2_wave = orig
     path = os.path.join(OUT, "train_step.pt")

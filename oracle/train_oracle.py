@@ -56,6 +56,16 @@ def dropout_from_masks(masks):
     return drop
 
 
+def dropout_torch_stream(p_conv, p_fc):
+    """drop(x, kind) drawing from torch's global CPU generator exactly as the reference does (torch.nn.Dropout on
+    view_as_real, c_network.py:195-196 / 203-204 / 221-222): after the same torch.manual_seed the masks are identical."""
+    import torch.nn.functional as F
+
+    def drop(x, kind):
+        return torch.view_as_complex(F.dropout(torch.view_as_real(x), p_fc if kind == "fc" else p_conv, True))
+    return drop
+
+
 def _mul(a, b):
     return torch.complex(a.real * b.real - a.imag * b.imag, a.real * b.imag + a.imag * b.real)
 

@@ -263,3 +263,22 @@ def test_lightning_style_steps_with_oracle_stand_ins(variant, monkeypatch):
     assert opt["optimizer"].defaults["amsgrad"] is True and opt["optimizer"].defaults["lr"] == C.hparams["lr"]
     with pytest.raises(NotImplementedError):
         net.training_step(None, 0)
+
+
+def test_training_step_oracle_dropout_positions_match_reference():
+    """With the reference's dropout probabilities (0.1 conv / 0.2 fc) and torch's CPU generator seeded as in the fixture run,
+    the restatement draws the same masks in the same order (7 encoder outputs, fc output, 7 decoder outputs; real and
+    imaginary parts independently) and must land on the reference's losses."""
+    from oracle import train_oracle as TO
+    g = load_golden("train_step.pt")
+    w = g["dcs_dropout"]
+    net = build_product_net("default")
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    names = {k for k, _ in net.named_parameters()}
+    clean, noise, noisy = O.synthetic_audio(g["B"], 32 * (g["T"] - 1), seed=g["audio_seed"])
+    specs = O.stft(noise), O.stft(noisy), O.stft(clean)
+    torch.manual_seed(w["seed"])
+    r = TO.train_step(sd, *specs, names, "dcs", drop=TO.dropout_torch_stream(w["dropout_conv"], w["dropout_fc"]))
+    for k in ("noise_loss", "speech_loss", "train_loss"):
+        assert abs(r[k] - w[k]) <= 1e-4, (k, r[k], w[k])
+    assert abs(w["train_loss"] - g["dcs"]["train_loss"]) > 0.1          # the dropout case really differs from p = 0
