@@ -136,3 +136,59 @@ def test_load_from_checkpoint_like_test_py(kind, tmp_path):
     torch.save({"model": 1}, tmp_path / "bad.ckpt")
     with pytest.raises(KeyError):
         cls.load_from_checkpoint(config=C.config, seed=0, checkpoint_path=str(tmp_path / "bad.ckpt"))
+
+
+def _grad_sync_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from dcsnet_b200 import c_network, config as C, grad_sync
+    net = c_network.C_NETWORK(C.config, dict(C.hparams), 0)
+    names = sorted(n for n, _ in net.named_parameters())
+    seeds = {n: i for i, n in enumerate(names)}                      # hash() is salted per process: use a stable index
+    for n, p in net.named_parameters():
+        g = torch.Generator().manual_seed(seeds[n] + 7919 * rank)
+        p.grad = torch.randn(p.shape, generator=g) * (1.0 + rank)
+    gb = grad_sync.GradBuckets(net.named_parameters(), bucket_bytes=4 << 20)
+    first, last = next(iter(gb.slices)), list(gb.slices)[-1]         # decoder-first layout
+    gb.launch(0)                                                     # overlapped bucket, the rest reduced in finish()
+    gb.finish()
+    want = {}
+    for n, p in net.named_parameters():
+        acc = torch.zeros_like(p)
+        for r in range(world):
+            g = torch.Generator().manual_seed(seeds[n] + 7919 * r)
+            acc += torch.randn(p.shape, generator=g) * (1.0 + r)
+        want[n] = acc / world
+    err = max(float((p.grad - want[n]).abs().max()) for n, p in net.named_parameters())
+    ref_params = [torch.nn.Parameter(p.detach().clone()) for _, p in net.named_parameters()]
+    for rp, (n, _) in zip(ref_params, net.named_parameters()):
+        rp.grad = want[n].clone()
+    ref_norm = torch.nn.utils.clip_grad_norm_(ref_params, 100.0)
+    norm = gb.clip_by_global_norm(100.0)
+    cerr = max(float((p.grad - rp.grad).abs().max()) for rp, (_, p) in zip(ref_params, net.named_parameters()))
+    views = all(p.grad.data_ptr() == gb.buckets[gb.slices[n][0]][gb.slices[n][1]:].data_ptr() for n, p in net.named_parameters())
+    if rank == 0:
+        q.put(dict(err=err, cerr=cerr, norm=float(norm), ref_norm=float(ref_norm), numel=gb.numel, nb=len(gb.buckets), first=first, last=last, views=views))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_all_reduce_and_clip_with_gloo():
+    """Training-step exchange: flat decoder-first buckets, async all-reduce of the first bucket, mean over ranks,
+    global-norm clip after the reduce == torch's clip_grad_norm_ on the averaged gradients."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_grad_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    r = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert r["numel"] == 2912707 and r["nb"] >= 3 and r["views"]
+    # last decoder stage first (decoder_attention.12 / 13 are constructed but unused by forward, c_network.py:218), input BN last
+    assert r["first"].split(".")[0] in ("decoder", "decoder_attention") and r["last"].startswith("initial_batchnorm.")
+    assert r["err"] <= 1e-6 and r["norm"] > 100.0 and abs(r["norm"] - r["ref_norm"]) <= 1e-3 * r["ref_norm"] and r["cerr"] <= 1e-6
