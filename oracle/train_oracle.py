@@ -123,3 +123,29 @@ def train_step_real(sd, noise_spec, noisy_spec, clean_spec, param_names, variant
     return dict(noise_loss=None if noise_loss is None else float(noise_loss.detach()), speech_loss=float(speech_loss.detach()),
                 train_loss=float(total.detach()), grads={k: live[k].grad for k in param_names if live[k].grad is not None},
                 running_stats=stats)
+
+
+def istft_adjoint(g, n_frames):
+    """Closed form of d<g, mag_phase_2_wave(S)>/dS for the reference's iSTFT (network_functions.py:140-150: zero row appended
+    at the END of the frequency axis, n_fft 512, hop 32, hann, normalized, centre-trimmed) — the backward kernel's contract.
+
+    g: (B, 32 (T-1)) waveform gradient -> (B, 256, T) complex64 gradient in torch's convention (dL/dRe + j dL/dIm):
+    zero-pad g by 256 on both sides, divide by the overlap-add envelope sum_t w^2, then a NON-centred, normalized STFT with the
+    same window; rfft bins 0..255 are kept (the forward put spectrogram row k on rfft bin k), scaled by 2 for bins 1..255
+    (Hermitian halves of the C2R transform) and by 1 with the imaginary part dropped for bin 0 (C2R ignores it).
+    So it is the forward STFT kernel with: no reflect padding, a 1/envelope pre-scale, bin offset 0 instead of 1, and the
+    per-bin factor."""
+    n, hop = O.N_FFT, O.HOP
+    win = torch.hann_window(n)
+    full = hop * (n_frames - 1) + n
+    env = torch.zeros(full)
+    for t in range(n_frames):
+        env[t * hop:t * hop + n] += win ** 2
+    G = torch.nn.functional.pad(g, (n // 2, n // 2)) / env.clamp_min(1e-20)
+    X = torch.stft(G, n_fft=n, hop_length=hop, win_length=n, window=win, center=False, normalized=True, return_complex=True)[:, :256]
+    scale = torch.full((256,), 2.0)
+    scale[0] = 1.0
+    X = X * scale[None, :, None]
+    imag = X.imag.clone()
+    imag[:, 0] = 0.0
+    return torch.complex(X.real, imag)

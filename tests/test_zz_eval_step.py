@@ -282,3 +282,20 @@ def test_training_step_oracle_dropout_positions_match_reference():
     for k in ("noise_loss", "speech_loss", "train_loss"):
         assert abs(r[k] - w[k]) <= 1e-4, (k, r[k], w[k])
     assert abs(w["train_loss"] - g["dcs"]["train_loss"]) > 0.1          # the dropout case really differs from p = 0
+
+
+@pytest.mark.parametrize("B,T", [(2, 40), (1, 17)])
+def test_istft_adjoint_closed_form_equals_autograd(B, T):
+    """oracle/train_oracle.istft_adjoint — the contract of the training step's first backward kernel (the loss is SI-SNR on
+    waveforms, so every gradient enters through the iSTFT) — against torch autograd through the reference's mag_phase_2_wave."""
+    from oracle import train_oracle as TO, rnet_oracle as RO
+    gen = torch.Generator().manual_seed(B * 100 + T)
+    mag = torch.rand(B, 256, T, generator=gen).requires_grad_(True)
+    phase = (6.28 * torch.rand(B, 256, T, generator=gen) - 3.14).requires_grad_(True)
+    y = RO.mag_phase_2_wave(mag, phase)
+    g = torch.randn(y.shape, generator=gen)
+    (y * g).sum().backward()
+    gs = TO.istft_adjoint(g, T)                                         # gradient w.r.t. the complex spectrogram
+    want_mag = gs.real * torch.cos(phase.detach()) + gs.imag * torch.sin(phase.detach())
+    want_phase = mag.detach() * (-gs.real * torch.sin(phase.detach()) + gs.imag * torch.cos(phase.detach()))
+    assert rel_err(want_mag, mag.grad) <= 1e-5 and rel_err(want_phase, phase.grad) <= 1e-5
