@@ -149,3 +149,39 @@ def istft_adjoint(g, n_frames):
     imag = X.imag.clone()
     imag[:, 0] = 0.0
     return torch.complex(X.real, imag)
+
+
+def cbn_train_backward(x, dy, weight, eps=O.BN_EPS):
+    """Closed-form backward of train-mode ComplexBatchNorm2d (the contract of the BN backward kernel): x, dy complex (B,C,H,W)
+    with dy = dL/dRe y + j dL/dIm y; weight (C,3).  Returns (dx complex, dweight (C,3), dbias (C,2)).
+
+    Two reduction passes per channel, like the forward: pass 1 accumulates the eight sums below (dW, db, and <dz, xc> for the
+    whitening matrix), a per-channel 3x3 Jacobian turns dR into dC, pass 2 forms dx = R^T dz + (2/n)(dC applied to xc) and
+    removes its mean."""
+    b = lambda v: v[None, :, None, None]  # noqa: E731
+    red = lambda v: v.sum(dim=[0, 2, 3])  # noqa: E731
+    xr, xi = x.real - b(x.real.mean([0, 2, 3])), x.imag - b(x.imag.mean([0, 2, 3]))
+    n = x.numel() / x.size(1)
+    A, Bc, Cc = red(xr * xr) / n + eps, red(xi * xi) / n + eps, red(xr * xi) / n
+    s = torch.sqrt(A * Bc - Cc * Cc)
+    t = torch.sqrt(A + Bc + 2 * s)
+    u = 1.0 / (s * t)
+    Rrr, Rii, Rri = (Bc + s) * u, (A + s) * u, -Cc * u
+    zr, zi = b(Rrr) * xr + b(Rri) * xi, b(Rii) * xi + b(Rri) * xr
+    w0, w1, w2 = weight[:, 0], weight[:, 1], weight[:, 2]
+    gr, gi = dy.real, dy.imag
+    dweight = torch.stack([red(gr * zr), red(gi * zi), red(gr * zi + gi * zr)], dim=1)
+    dbias = torch.stack([red(gr), red(gi)], dim=1)
+    dzr, dzi = b(w0) * gr + b(w2) * gi, b(w2) * gr + b(w1) * gi
+    dRrr, dRii, dRri = red(dzr * xr), red(dzi * xi), red(dzr * xi + dzi * xr)
+    # Jacobian of (Rrr, Rii, Rri) w.r.t. (A, B, C)
+    s_a, s_b, s_c = Bc / (2 * s), A / (2 * s), -Cc / s
+    t_a, t_b, t_c = (1 + 2 * s_a) / (2 * t), (1 + 2 * s_b) / (2 * t), s_c / t
+    u_a, u_b, u_c = -u * (s_a / s + t_a / t), -u * (s_b / s + t_b / t), -u * (s_c / s + t_c / t)
+    dA = dRrr * (s_a * u + (Bc + s) * u_a) + dRii * ((1 + s_a) * u + (A + s) * u_a) + dRri * (-Cc * u_a)
+    dB = dRrr * ((1 + s_b) * u + (Bc + s) * u_b) + dRii * (s_b * u + (A + s) * u_b) + dRri * (-Cc * u_b)
+    dC = dRrr * (s_c * u + (Bc + s) * u_c) + dRii * (s_c * u + (A + s) * u_c) + dRri * (-u - Cc * u_c)
+    dxr = b(Rrr) * dzr + b(Rri) * dzi + (2 * b(dA) * xr + b(dC) * xi) / n
+    dxi = b(Rii) * dzi + b(Rri) * dzr + (2 * b(dB) * xi + b(dC) * xr) / n
+    dxr, dxi = dxr - b(dxr.mean([0, 2, 3])), dxi - b(dxi.mean([0, 2, 3]))
+    return torch.complex(dxr, dxi), dweight, dbias

@@ -299,3 +299,23 @@ def test_istft_adjoint_closed_form_equals_autograd(B, T):
     want_mag = gs.real * torch.cos(phase.detach()) + gs.imag * torch.sin(phase.detach())
     want_phase = mag.detach() * (-gs.real * torch.sin(phase.detach()) + gs.imag * torch.cos(phase.detach()))
     assert rel_err(want_mag, mag.grad) <= 1e-5 and rel_err(want_phase, phase.grad) <= 1e-5
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 6, 10), (2, 1, 16, 5), (4, 32, 2, 7)])
+def test_complex_batchnorm_train_backward_closed_form_equals_autograd(shape):
+    """oracle/train_oracle.cbn_train_backward (two reduction passes + a per-channel 3x3 Jacobian) against autograd through the
+    train-mode restatement that itself reproduces the reference's gradients."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(sum(shape))
+    Cn = shape[1]
+    x = torch.complex(torch.randn(shape, generator=gen) * 1.5 + 0.3, torch.randn(shape, generator=gen) * 0.7 - 0.2)
+    x = torch.complex(x.real, x.imag + 0.4 * x.real).requires_grad_(True)            # correlated parts: Cri != 0
+    sd = {"p.weight": torch.stack([1 + 0.3 * torch.rand(Cn, generator=gen), 1 + 0.3 * torch.rand(Cn, generator=gen),
+                                   0.3 * torch.rand(Cn, generator=gen) - 0.15], dim=1).requires_grad_(True),
+          "p.bias": (0.1 * torch.randn(Cn, 2, generator=gen)).requires_grad_(True),
+          "p.running_mean": torch.zeros(Cn, dtype=torch.complex64), "p.running_covar": torch.ones(Cn, 3)}
+    y = TO.cbn_train({})(x, sd, "p.")
+    dy = torch.complex(torch.randn(shape, generator=gen), torch.randn(shape, generator=gen))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    dx, dw, db = TO.cbn_train_backward(x.detach(), dy, sd["p.weight"].detach())
+    assert rel_err(dx, x.grad) <= 2e-5 and rel_err(dw, sd["p.weight"].grad) <= 2e-5 and rel_err(db, sd["p.bias"].grad) <= 2e-5
