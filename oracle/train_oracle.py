@@ -185,3 +185,59 @@ def cbn_train_backward(x, dy, weight, eps=O.BN_EPS):
     dxi = b(Rii) * dzi + b(Rri) * dzr + (2 * b(dB) * xi + b(dC) * xr) / n
     dxr, dxi = dxr - b(dxr.mean([0, 2, 3])), dxi - b(dxi.mean([0, 2, 3]))
     return torch.complex(dxr, dxi), dweight, dbias
+
+
+def bound_crm_backward(m, dout, eps=O.HPARAMS["atan2_eps"]):
+    """Closed-form backward of bound_cRM (network_functions.py:77-88; applied twice on the training path, c_network.py:225 and
+    network_functions.py:240): m complex, dout = dL/dRe out + j dL/dIm out -> dL/dm in the same convention.  Element-wise."""
+    mr, mi, gr, gi = m.real, m.imag, dout.real, dout.imag
+    rho = torch.sqrt(mr * mr + mi * mi)
+    t = torch.tanh(rho)
+    a = mr + eps
+    th1 = torch.atan2(mi, a)
+    c1, s1 = torch.cos(th1), torch.sin(th1)
+    r1, i1 = t * c1, t * s1
+    a2 = r1 + eps
+    th2 = torch.atan2(i1, a2)
+    c2, s2 = torch.cos(th2), torch.sin(th2)
+    dt = gr * c2 + gi * s2
+    dth2 = t * (-gr * s2 + gi * c2)
+    q2 = a2 * a2 + i1 * i1
+    dr1, di1 = dth2 * (-i1 / q2), dth2 * (a2 / q2)
+    dt = dt + dr1 * c1 + di1 * s1
+    dth1 = t * (-dr1 * s1 + di1 * c1)
+    q1 = a * a + mi * mi
+    sech2 = 1 - t * t
+    return torch.complex(dt * sech2 * mr / rho + dth1 * (-mi / q1), dt * sech2 * mi / rho + dth1 * (a / q1))
+
+
+def polar_roundtrip_backward(s, dout, eps=O.HPARAMS["atan2_eps"]):
+    """Backward of the polar split + recombination in front of the iSTFT (network_functions.py:398-401 with 141-143):
+    out = |s| (cos phi, sin phi), phi = atan2(Im s, Re s + eps).  Element-wise; identity up to O(eps)."""
+    sr, si, gr, gi = s.real, s.imag, dout.real, dout.imag
+    rho = torch.sqrt(sr * sr + si * si)
+    a = sr + eps
+    phi = torch.atan2(si, a)
+    c, sn = torch.cos(phi), torch.sin(phi)
+    drho = gr * c + gi * sn
+    dphi = rho * (-gr * sn + gi * c)
+    q = a * a + si * si
+    return torch.complex(drho * sr / rho + dphi * (-si / q), drho * si / rho + dphi * (a / q))
+
+
+def mask_tail_backward(raw, noisy_spec, g_clean_wave, g_noise_wave=None, eps=O.HPARAMS["atan2_eps"]):
+    """The training step's first backward stage in one piece (the adjoint of the fused decoder[6] mask tail, variant dcs when
+    `g_noise_wave` is given, dc otherwise): waveform gradients -> gradient w.r.t. the un-bounded decoder output `raw` (B,256,T).
+    iSTFT adjoint -> polar adjoint -> combine adjoint (Ŝ = Y - Y·M, N̂ = Y·M; dM = conj(Y)·dN̂) -> bound_cRM adjoint twice."""
+    T = raw.shape[-1]
+    m1 = O.bound_crm(raw, eps)
+    m2 = O.bound_crm(m1, eps)
+    prod = _mul(noisy_spec, m2)
+    if g_noise_wave is not None:
+        clean = noisy_spec - prod
+        dprod = polar_roundtrip_backward(prod, istft_adjoint(g_noise_wave, T), eps) \
+            - polar_roundtrip_backward(clean, istft_adjoint(g_clean_wave, T), eps)
+    else:
+        dprod = polar_roundtrip_backward(prod, istft_adjoint(g_clean_wave, T), eps)
+    dm2 = _mul(torch.conj(noisy_spec), dprod)
+    return bound_crm_backward(raw, bound_crm_backward(m1, dm2, eps), eps)

@@ -319,3 +319,37 @@ def test_complex_batchnorm_train_backward_closed_form_equals_autograd(shape):
     (y.real * dy.real + y.imag * dy.imag).sum().backward()
     dx, dw, db = TO.cbn_train_backward(x.detach(), dy, sd["p.weight"].detach())
     assert rel_err(dx, x.grad) <= 2e-5 and rel_err(dw, sd["p.weight"].grad) <= 2e-5 and rel_err(db, sd["p.bias"].grad) <= 2e-5
+
+
+def test_bound_crm_backward_closed_form_equals_autograd():
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(21)
+    m = torch.complex(torch.randn(4, 256, 9, generator=gen) * 1.3, torch.randn(4, 256, 9, generator=gen) * 0.8).requires_grad_(True)
+    out = O.bound_crm(O.bound_crm(m))                                   # the training path applies it twice
+    dout = torch.complex(torch.randn(out.shape, generator=gen), torch.randn(out.shape, generator=gen))
+    (out.real * dout.real + out.imag * dout.imag).sum().backward()
+    inner = O.bound_crm(m.detach())
+    got = TO.bound_crm_backward(m.detach(), TO.bound_crm_backward(inner, dout))
+    assert rel_err(got, m.grad) <= 2e-5
+
+
+@pytest.mark.parametrize("variant", ["dcs", "dc"])
+def test_mask_tail_backward_closed_form_equals_autograd(variant):
+    """Waveform gradients -> gradient at the decoder output through iSTFT, polar split, combine and the two bound_cRM, as one
+    closed-form stage (the adjoint of the forward's fused mask tail) vs autograd through the oracle's forward functions."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(5)
+    B, T = 2, 24
+    raw = torch.complex(torch.randn(B, 256, T, generator=gen), torch.randn(B, 256, T, generator=gen)).requires_grad_(True)
+    Y = O.stft(O.synthetic_audio(B, 32 * (T - 1))[2])
+    m2 = O.bound_crm(O.bound_crm(raw))
+    prod = torch.complex(Y.real * m2.real - Y.imag * m2.imag, Y.real * m2.imag + Y.imag * m2.real)
+    gc = torch.randn(B, 32 * (T - 1), generator=gen)
+    gn = torch.randn(B, 32 * (T - 1), generator=gen)
+    if variant == "dcs":
+        loss = (O.spec_to_wave(Y - prod) * gc).sum() + (O.spec_to_wave(prod) * gn).sum()
+    else:
+        loss = (O.spec_to_wave(prod) * gc).sum()
+    loss.backward()
+    got = TO.mask_tail_backward(raw.detach(), Y, gc, gn if variant == "dcs" else None)
+    assert rel_err(got, raw.grad) <= 5e-5
