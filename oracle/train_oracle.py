@@ -12,6 +12,8 @@ Reference lines followed:
   ComplexBatchNorm2d.train .. complexPyTorch/complexLayers.py (momentum 0.1, unbiased running covariance)
   dropout positions ......... c_network.py:195, 203, 221 (on view_as_real, i.e. real and imaginary parts drop independently)
 """
+import math
+
 import torch
 
 from . import dcsnet_oracle as O
@@ -241,3 +243,29 @@ def mask_tail_backward(raw, noisy_spec, g_clean_wave, g_noise_wave=None, eps=O.H
         dprod = polar_roundtrip_backward(prod, istft_adjoint(g_clean_wave, T), eps)
     dm2 = _mul(torch.conj(noisy_spec), dprod)
     return bound_crm_backward(raw, bound_crm_backward(m1, dm2, eps), eps)
+
+
+def si_snr_backward(clean, estimate, eps=1e-8):
+    """d SiSNR(clean, estimate) / d estimate (network_functions.py:30-42; mean over the batch rows), closed form: three
+    row reductions (<e,c>, <c,c>, then |e - s_t|^2) and one element-wise pass — the loss kernel's contract."""
+    rows = estimate.shape[0] if estimate.dim() > 1 else 1
+    dot = torch.sum(estimate * clean, -1, keepdim=True)
+    cc = torch.sum(clean * clean, -1, keepdim=True)
+    k = dot / (cc + eps)
+    s_t = k * clean
+    e = estimate - s_t
+    Tn = torch.sum(s_t * s_t, -1, keepdim=True)
+    Nn = torch.sum(e * e, -1, keepdim=True)
+    ratio = Tn / (Nn + eps) + eps
+    dTn = 2 * k * cc / (cc + eps) * clean                      # d|s_t|^2 / d estimate
+    dNn = 2 * (e - torch.sum(e * clean, -1, keepdim=True) / (cc + eps) * clean)
+    return (10.0 / math.log(10.0)) / rows / ratio * (dTn / (Nn + eps) - Tn * dNn / (Nn + eps) ** 2)
+
+
+def loss_backward(clean_audio, predict_clean_audio, noise_audio=None, predict_noise_audio=None, speech_alpha=0.7):
+    """Waveform gradients of calc_loss with the config.py defaults (noise_loss_type 6, speech_loss_type 0):
+    total = [1 - alpha * (-SiSNR(noise, n_hat))] + alpha * (-SiSNR(clean, s_hat))  (network_functions.py:195-204, precedence as
+    written).  Returns (d total / d s_hat, d total / d n_hat or None)."""
+    g_clean = -speech_alpha * si_snr_backward(clean_audio, predict_clean_audio)
+    g_noise = None if noise_audio is None else speech_alpha * si_snr_backward(noise_audio, predict_noise_audio)
+    return g_clean, g_noise

@@ -353,3 +353,30 @@ def test_mask_tail_backward_closed_form_equals_autograd(variant):
     loss.backward()
     got = TO.mask_tail_backward(raw.detach(), Y, gc, gn if variant == "dcs" else None)
     assert rel_err(got, raw.grad) <= 5e-5
+
+
+def test_loss_backward_closed_form_and_full_tail_chain_equal_autograd():
+    """calc_loss's waveform gradients in closed form (SI-SNR adjoint), then the whole chain loss -> waveforms -> mask tail ->
+    decoder output against autograd through the product's calc_loss and the oracle's forward functions."""
+    import types
+    from oracle import train_oracle as TO
+    from dcsnet_b200 import network_functions as NF, config as C
+    gen = torch.Generator().manual_seed(17)
+    B, T = 2, 24
+    clean, noise, noisy = O.synthetic_audio(B, 32 * (T - 1))
+    est = (clean + 0.3 * torch.randn(clean.shape, generator=gen)).requires_grad_(True)
+    NF.SiSNR()(clean, est).backward()
+    assert rel_err(TO.si_snr_backward(clean, est.detach()), est.grad) <= 1e-5
+    raw = torch.complex(torch.randn(B, 256, T, generator=gen), torch.randn(B, 256, T, generator=gen)).requires_grad_(True)
+    Y, Nn, S = O.stft(noisy), O.stft(noise), O.stft(clean)
+    m2 = O.bound_crm(O.bound_crm(raw))
+    prod = torch.complex(Y.real * m2.real - Y.imag * m2.imag, Y.real * m2.imag + Y.imag * m2.real)
+    s_hat, n_hat = O.spec_to_wave(Y - prod), O.spec_to_wave(prod)
+    clean_audio, noise_audio = O.spec_to_wave(S), O.spec_to_wave(Nn)
+    fake = types.SimpleNamespace(hparams=dict(C.hparams), config=C.config)
+    _, _, total = NF.calc_loss(fake, variant="dcs", predict_noise_audio=n_hat, predict_clean_audio=s_hat, noise_audio=noise_audio,
+                               noisy_audio=O.spec_to_wave(Y), clean_audio=clean_audio, target_noise_mask=None, predict_noise_mask=None)
+    total.backward()
+    gc, gn = TO.loss_backward(clean_audio, s_hat.detach(), noise_audio, n_hat.detach(), C.hparams["speech_alpha"])
+    got = TO.mask_tail_backward(raw.detach(), Y, gc, gn)
+    assert rel_err(got, raw.grad) <= 1e-4
