@@ -269,3 +269,24 @@ def loss_backward(clean_audio, predict_clean_audio, noise_audio=None, predict_no
     g_clean = -speech_alpha * si_snr_backward(clean_audio, predict_clean_audio)
     g_noise = None if noise_audio is None else speech_alpha * si_snr_backward(noise_audio, predict_noise_audio)
     return g_clean, g_noise
+
+
+def cconv2d_backward(x, w_r, w_i, dy, stride, padding):
+    """Backward of ComplexConv2d (`apply_complex`) in the PACKED real formulation the forward kernels
+    use (one real implicit GEMM with N = 2 Cout, K = 2 Cin k^2): X = [x_re ; x_im], Wp = [[w_r, -w_i], [w_i, w_r]].
+      dgrad : dX  = conv_transpose(dY, Wp)                    -> one GEMM, K = 2 Cout k^2
+      wgrad : dWp = correlation(X, dY) (K = pixels)           -> one GEMM; its four blocks fold into
+              dw_r = dWp[re,re] + dWp[im,im],  dw_i = dWp[im,re] - dWp[re,im]   (a 2-add epilogue)
+      bias  : conv_r / conv_i each carry a bias (effective complex bias (b_r - b_i) + j (b_r + b_i)):
+              db_r = sum(dY_re + dY_im), db_i = sum(dY_im - dY_re)
+    Returns (dx complex, dw_r, dw_i, db_r, db_i)."""
+    cout, cin = w_r.shape[0], w_r.shape[1]
+    X = torch.cat([x.real, x.imag], dim=1)
+    dY = torch.cat([dy.real, dy.imag], dim=1)
+    Wp = torch.cat([torch.cat([w_r, -w_i], dim=1), torch.cat([w_i, w_r], dim=1)], dim=0)
+    dX = torch.nn.grad.conv2d_input(X.shape, Wp, dY, stride=stride, padding=padding)
+    dWp = torch.nn.grad.conv2d_weight(X, Wp.shape, dY, stride=stride, padding=padding)
+    dw_r = dWp[:cout, :cin] + dWp[cout:, cin:]
+    dw_i = dWp[cout:, :cin] - dWp[:cout, cin:]
+    s = dY.sum(dim=[0, 2, 3])
+    return torch.complex(dX[:, :cin], dX[:, cin:]), dw_r, dw_i, s[:cout] + s[cout:], s[cout:] - s[:cout]

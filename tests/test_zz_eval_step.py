@@ -380,3 +380,22 @@ def test_loss_backward_closed_form_and_full_tail_chain_equal_autograd():
     gc, gn = TO.loss_backward(clean_audio, s_hat.detach(), noise_audio, n_hat.detach(), C.hparams["speech_alpha"])
     got = TO.mask_tail_backward(raw.detach(), Y, gc, gn)
     assert rel_err(got, raw.grad) <= 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,k,stride", [(1, 8, 7, (2, 2)), (16, 32, 5, (2, 2)), (64, 128, 3, (2, 1))])
+def test_complex_conv_backward_in_packed_formulation_equals_autograd(cin, cout, k, stride):
+    """dgrad / wgrad / bias gradients of ComplexConv2d as ONE packed real GEMM each (the formulation the forward kernels
+    already use) vs autograd through the oracle's four-real-convolution restatement, at encoder layer shapes."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(cin + cout)
+    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
+    sd = {"c.conv_r.weight": (0.2 * rnd(cout, cin, k, k)).requires_grad_(True), "c.conv_i.weight": (0.2 * rnd(cout, cin, k, k)).requires_grad_(True),
+          "c.conv_r.bias": rnd(cout).requires_grad_(True), "c.conv_i.bias": rnd(cout).requires_grad_(True)}
+    x = torch.complex(rnd(2, cin, 16, 12), rnd(2, cin, 16, 12)).requires_grad_(True)
+    y = O.cconv2d(x, sd, "c.", stride, k // 2)
+    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    dx, dwr, dwi, dbr, dbi = TO.cconv2d_backward(x.detach(), sd["c.conv_r.weight"].detach(), sd["c.conv_i.weight"].detach(), dy, stride, k // 2)
+    for got, want in ((dx, x.grad), (dwr, sd["c.conv_r.weight"].grad), (dwi, sd["c.conv_i.weight"].grad),
+                      (dbr, sd["c.conv_r.bias"].grad), (dbi, sd["c.conv_i.bias"].grad)):
+        assert rel_err(got, want) <= 2e-5
