@@ -173,64 +173,6 @@ def test_gpu_evaluation_step_matches_reference(variant):
     assert len(rv) == (10 if variant in ("dcs", "drs") else 7) and abs(float(rv[0]) - float(r[0])) <= 1e-6
 
 
-@pytest.mark.parametrize("variant", ["dcs", "drs"])
-def test_training_step_fixture_lines_up_with_the_product_parameters(variant):
-    """tests/golden/train_step.pt (reference `train_batch_2_loss` + backward, oracle/make_golden_train.py) is the pin for the
-    training step that is still to be built.  Until then: the fixture must describe exactly the product
-    containers' parameters (names and shapes), with finite losses and gradients, so the backward kernels have a target."""
-    import math
-    from dcsnet_b200 import r_network, config as C
-    g = load_golden("train_step.pt")[variant]
-    net = build_product_net("default") if variant == "dcs" else r_network.R_NETWORK(C.Config(), dict(C.hparams), 0)
-    params = {k: tuple(torch.view_as_real(p).shape) if p.is_complex() else tuple(p.shape) for k, p in net.named_parameters()}
-    assert set(params) == set(g["grads"]) | set(g["no_grad"])
-    for k, f in g["grads"].items():
-        assert params[k] == f["shape"], k
-        assert math.isfinite(f["norm"]) and bool(torch.isfinite(f["head"]).all()), k
-    assert all(math.isfinite(g[k]) for k in ("noise_loss", "speech_loss", "train_loss", "grad_norm"))
-    assert abs(g["noise_loss"] + g["speech_loss"] - g["train_loss"]) < 1e-4
-    assert abs(math.sqrt(sum(f["norm"] ** 2 for f in g["grads"].values())) - g["grad_norm"]) <= 1e-3 * g["grad_norm"]
-    assert {k for k in net.state_dict() if "running_" in k} == set(g["running_stats"])
-
-
-@pytest.mark.parametrize("variant", ["dcs", "drs"])
-def test_training_step_oracle_matches_reference_gradients(variant):
-    """oracle/train_oracle.py (train-mode restatement + autograd) against the reference's own `train_batch_2_loss` +
-    `backward()` (tests/golden/train_step.pt): losses, every parameter gradient, BN running statistics after the step, for
-    the complex (dcs) and the real (drs) network.  Conv biases that feed a batch-statistic BN have a mathematically zero
-    gradient (1e-8 rounding noise on both sides): they are compared on an absolute scale."""
-    from oracle import train_oracle as TO
-    from dcsnet_b200 import r_network, config as C
-    g = load_golden("train_step.pt")
-    w = g[variant]
-    net = build_product_net("default") if variant == "dcs" else r_network.R_NETWORK(C.Config(), dict(C.hparams), 0)
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    names = {k for k, _ in net.named_parameters()}
-    clean, noise, noisy = O.synthetic_audio(g["B"], 32 * (g["T"] - 1), seed=g["audio_seed"])
-    step = TO.train_step if variant == "dcs" else TO.train_step_real
-    r = step(sd, O.stft(noise), O.stft(noisy), O.stft(clean), names, variant)
-    for k in ("noise_loss", "speech_loss", "train_loss"):
-        assert abs(r[k] - w[k]) <= 1e-4, k
-    assert set(r["grads"]) == set(w["grads"])
-    floor = 1e-6 * w["grad_norm"]
-    checked = 0
-    for k, f in w["grads"].items():
-        gr = r["grads"][k].float()
-        assert abs(float(gr.norm()) - f["norm"]) <= 1e-3 * f["norm"] + floor, k
-        assert float((gr.reshape(-1)[:8] - f["head"]).abs().max()) <= 1e-3 * f["max_abs"] + floor, k
-        checked += f["norm"] > 100 * floor
-    assert checked > 0.75 * len(w["grads"])                   # the bulk of the gradients is far above the noise floor
-    n_stats = 0
-    for k, f in w["running_stats"].items():
-        if k.endswith("num_batches_tracked"):
-            continue
-        t = r["running_stats"][k]
-        t = (torch.view_as_real(t) if t.is_complex() else t).float()
-        assert abs(float(t.norm()) - f["norm"]) <= 1e-5 * f["norm"] and float((t.reshape(-1)[:8] - f["head"]).abs().max()) <= 1e-5 * f["max_abs"], k
-        n_stats += 1
-    assert n_stats == 2 * 14                                   # initial BN + 7 encoder + 6 decoder layers, two statistics each
-
-
 @pytest.mark.parametrize("variant", ["dcs", "dr"])
 def test_lightning_style_steps_with_oracle_stand_ins(variant, monkeypatch):
     """validation_step / test_step / configure_optimizers of the product networks (c_network.py:228-239, 263-302, 337-372):
@@ -263,139 +205,3 @@ def test_lightning_style_steps_with_oracle_stand_ins(variant, monkeypatch):
     assert opt["optimizer"].defaults["amsgrad"] is True and opt["optimizer"].defaults["lr"] == C.hparams["lr"]
     with pytest.raises(NotImplementedError):
         net.training_step(None, 0)
-
-
-def test_training_step_oracle_dropout_positions_match_reference():
-    """With the reference's dropout probabilities (0.1 conv / 0.2 fc) and torch's CPU generator seeded as in the fixture run,
-    the restatement draws the same masks in the same order (7 encoder outputs, fc output, 7 decoder outputs; real and
-    imaginary parts independently) and must land on the reference's losses."""
-    from oracle import train_oracle as TO
-    g = load_golden("train_step.pt")
-    w = g["dcs_dropout"]
-    net = build_product_net("default")
-    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
-    names = {k for k, _ in net.named_parameters()}
-    clean, noise, noisy = O.synthetic_audio(g["B"], 32 * (g["T"] - 1), seed=g["audio_seed"])
-    specs = O.stft(noise), O.stft(noisy), O.stft(clean)
-    torch.manual_seed(w["seed"])
-    r = TO.train_step(sd, *specs, names, "dcs", drop=TO.dropout_torch_stream(w["dropout_conv"], w["dropout_fc"]))
-    for k in ("noise_loss", "speech_loss", "train_loss"):
-        assert abs(r[k] - w[k]) <= 1e-4, (k, r[k], w[k])
-    assert abs(w["train_loss"] - g["dcs"]["train_loss"]) > 0.1          # the dropout case really differs from p = 0
-
-
-@pytest.mark.parametrize("B,T", [(2, 40), (1, 17)])
-def test_istft_adjoint_closed_form_equals_autograd(B, T):
-    """oracle/train_oracle.istft_adjoint — the contract of the training step's first backward kernel (the loss is SI-SNR on
-    waveforms, so every gradient enters through the iSTFT) — against torch autograd through the reference's mag_phase_2_wave."""
-    from oracle import train_oracle as TO, rnet_oracle as RO
-    gen = torch.Generator().manual_seed(B * 100 + T)
-    mag = torch.rand(B, 256, T, generator=gen).requires_grad_(True)
-    phase = (6.28 * torch.rand(B, 256, T, generator=gen) - 3.14).requires_grad_(True)
-    y = RO.mag_phase_2_wave(mag, phase)
-    g = torch.randn(y.shape, generator=gen)
-    (y * g).sum().backward()
-    gs = TO.istft_adjoint(g, T)                                         # gradient w.r.t. the complex spectrogram
-    want_mag = gs.real * torch.cos(phase.detach()) + gs.imag * torch.sin(phase.detach())
-    want_phase = mag.detach() * (-gs.real * torch.sin(phase.detach()) + gs.imag * torch.cos(phase.detach()))
-    assert rel_err(want_mag, mag.grad) <= 1e-5 and rel_err(want_phase, phase.grad) <= 1e-5
-
-
-@pytest.mark.parametrize("shape", [(3, 8, 6, 10), (2, 1, 16, 5), (4, 32, 2, 7)])
-def test_complex_batchnorm_train_backward_closed_form_equals_autograd(shape):
-    """oracle/train_oracle.cbn_train_backward (two reduction passes + a per-channel 3x3 Jacobian) against autograd through the
-    train-mode restatement that itself reproduces the reference's gradients."""
-    from oracle import train_oracle as TO
-    gen = torch.Generator().manual_seed(sum(shape))
-    Cn = shape[1]
-    x = torch.complex(torch.randn(shape, generator=gen) * 1.5 + 0.3, torch.randn(shape, generator=gen) * 0.7 - 0.2)
-    x = torch.complex(x.real, x.imag + 0.4 * x.real).requires_grad_(True)            # correlated parts: Cri != 0
-    sd = {"p.weight": torch.stack([1 + 0.3 * torch.rand(Cn, generator=gen), 1 + 0.3 * torch.rand(Cn, generator=gen),
-                                   0.3 * torch.rand(Cn, generator=gen) - 0.15], dim=1).requires_grad_(True),
-          "p.bias": (0.1 * torch.randn(Cn, 2, generator=gen)).requires_grad_(True),
-          "p.running_mean": torch.zeros(Cn, dtype=torch.complex64), "p.running_covar": torch.ones(Cn, 3)}
-    y = TO.cbn_train({})(x, sd, "p.")
-    dy = torch.complex(torch.randn(shape, generator=gen), torch.randn(shape, generator=gen))
-    (y.real * dy.real + y.imag * dy.imag).sum().backward()
-    dx, dw, db = TO.cbn_train_backward(x.detach(), dy, sd["p.weight"].detach())
-    assert rel_err(dx, x.grad) <= 2e-5 and rel_err(dw, sd["p.weight"].grad) <= 2e-5 and rel_err(db, sd["p.bias"].grad) <= 2e-5
-
-
-def test_bound_crm_backward_closed_form_equals_autograd():
-    from oracle import train_oracle as TO
-    gen = torch.Generator().manual_seed(21)
-    m = torch.complex(torch.randn(4, 256, 9, generator=gen) * 1.3, torch.randn(4, 256, 9, generator=gen) * 0.8).requires_grad_(True)
-    out = O.bound_crm(O.bound_crm(m))                                   # the training path applies it twice
-    dout = torch.complex(torch.randn(out.shape, generator=gen), torch.randn(out.shape, generator=gen))
-    (out.real * dout.real + out.imag * dout.imag).sum().backward()
-    inner = O.bound_crm(m.detach())
-    got = TO.bound_crm_backward(m.detach(), TO.bound_crm_backward(inner, dout))
-    assert rel_err(got, m.grad) <= 2e-5
-
-
-@pytest.mark.parametrize("variant", ["dcs", "dc"])
-def test_mask_tail_backward_closed_form_equals_autograd(variant):
-    """Waveform gradients -> gradient at the decoder output through iSTFT, polar split, combine and the two bound_cRM, as one
-    closed-form stage (the adjoint of the forward's fused mask tail) vs autograd through the oracle's forward functions."""
-    from oracle import train_oracle as TO
-    gen = torch.Generator().manual_seed(5)
-    B, T = 2, 24
-    raw = torch.complex(torch.randn(B, 256, T, generator=gen), torch.randn(B, 256, T, generator=gen)).requires_grad_(True)
-    Y = O.stft(O.synthetic_audio(B, 32 * (T - 1))[2])
-    m2 = O.bound_crm(O.bound_crm(raw))
-    prod = torch.complex(Y.real * m2.real - Y.imag * m2.imag, Y.real * m2.imag + Y.imag * m2.real)
-    gc = torch.randn(B, 32 * (T - 1), generator=gen)
-    gn = torch.randn(B, 32 * (T - 1), generator=gen)
-    if variant == "dcs":
-        loss = (O.spec_to_wave(Y - prod) * gc).sum() + (O.spec_to_wave(prod) * gn).sum()
-    else:
-        loss = (O.spec_to_wave(prod) * gc).sum()
-    loss.backward()
-    got = TO.mask_tail_backward(raw.detach(), Y, gc, gn if variant == "dcs" else None)
-    assert rel_err(got, raw.grad) <= 5e-5
-
-
-def test_loss_backward_closed_form_and_full_tail_chain_equal_autograd():
-    """calc_loss's waveform gradients in closed form (SI-SNR adjoint), then the whole chain loss -> waveforms -> mask tail ->
-    decoder output against autograd through the product's calc_loss and the oracle's forward functions."""
-    import types
-    from oracle import train_oracle as TO
-    from dcsnet_b200 import network_functions as NF, config as C
-    gen = torch.Generator().manual_seed(17)
-    B, T = 2, 24
-    clean, noise, noisy = O.synthetic_audio(B, 32 * (T - 1))
-    est = (clean + 0.3 * torch.randn(clean.shape, generator=gen)).requires_grad_(True)
-    NF.SiSNR()(clean, est).backward()
-    assert rel_err(TO.si_snr_backward(clean, est.detach()), est.grad) <= 1e-5
-    raw = torch.complex(torch.randn(B, 256, T, generator=gen), torch.randn(B, 256, T, generator=gen)).requires_grad_(True)
-    Y, Nn, S = O.stft(noisy), O.stft(noise), O.stft(clean)
-    m2 = O.bound_crm(O.bound_crm(raw))
-    prod = torch.complex(Y.real * m2.real - Y.imag * m2.imag, Y.real * m2.imag + Y.imag * m2.real)
-    s_hat, n_hat = O.spec_to_wave(Y - prod), O.spec_to_wave(prod)
-    clean_audio, noise_audio = O.spec_to_wave(S), O.spec_to_wave(Nn)
-    fake = types.SimpleNamespace(hparams=dict(C.hparams), config=C.config)
-    _, _, total = NF.calc_loss(fake, variant="dcs", predict_noise_audio=n_hat, predict_clean_audio=s_hat, noise_audio=noise_audio,
-                               noisy_audio=O.spec_to_wave(Y), clean_audio=clean_audio, target_noise_mask=None, predict_noise_mask=None)
-    total.backward()
-    gc, gn = TO.loss_backward(clean_audio, s_hat.detach(), noise_audio, n_hat.detach(), C.hparams["speech_alpha"])
-    got = TO.mask_tail_backward(raw.detach(), Y, gc, gn)
-    assert rel_err(got, raw.grad) <= 1e-4
-
-
-@pytest.mark.parametrize("cin,cout,k,stride", [(1, 8, 7, (2, 2)), (16, 32, 5, (2, 2)), (64, 128, 3, (2, 1))])
-def test_complex_conv_backward_in_packed_formulation_equals_autograd(cin, cout, k, stride):
-    """dgrad / wgrad / bias gradients of ComplexConv2d as ONE packed real GEMM each (the formulation the forward kernels
-    already use) vs autograd through the oracle's four-real-convolution restatement, at encoder layer shapes."""
-    from oracle import train_oracle as TO
-    gen = torch.Generator().manual_seed(cin + cout)
-    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
-    sd = {"c.conv_r.weight": (0.2 * rnd(cout, cin, k, k)).requires_grad_(True), "c.conv_i.weight": (0.2 * rnd(cout, cin, k, k)).requires_grad_(True),
-          "c.conv_r.bias": rnd(cout).requires_grad_(True), "c.conv_i.bias": rnd(cout).requires_grad_(True)}
-    x = torch.complex(rnd(2, cin, 16, 12), rnd(2, cin, 16, 12)).requires_grad_(True)
-    y = O.cconv2d(x, sd, "c.", stride, k // 2)
-    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
-    (y.real * dy.real + y.imag * dy.imag).sum().backward()
-    dx, dwr, dwi, dbr, dbi = TO.cconv2d_backward(x.detach(), sd["c.conv_r.weight"].detach(), sd["c.conv_i.weight"].detach(), dy, stride, k // 2)
-    for got, want in ((dx, x.grad), (dwr, sd["c.conv_r.weight"].grad), (dwi, sd["c.conv_i.weight"].grad),
-                      (dbr, sd["c.conv_r.bias"].grad), (dbi, sd["c.conv_i.bias"].grad)):
-        assert rel_err(got, want) <= 2e-5
