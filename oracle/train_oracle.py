@@ -290,3 +290,42 @@ def cconv2d_backward(x, w_r, w_i, dy, stride, padding):
     dw_i = dWp[cout:, :cin] - dWp[:cout, cin:]
     s = dY.sum(dim=[0, 2, 3])
     return torch.complex(dX[:, :cin], dX[:, cin:]), dw_r, dw_i, s[:cout] + s[cout:], s[cout:] - s[:cout]
+
+
+def lstm_forward_saved(pre, whh):
+    """One direction of one layer, forward in index order (reverse direction = flip the time axis outside): pre (B,S,4H) =
+    x W_ih^T + b_ih + b_hh, gate order i,f,g,o.  Returns h (B,S,H) and what BPTT needs (activated gates, cell states)."""
+    B, S, G = pre.shape
+    H = G // 4
+    h, c = pre.new_zeros(B, H), pre.new_zeros(B, H)
+    hs, cs, gates = [], [], []
+    for t in range(S):
+        a = pre[:, t] + h @ whh.t()
+        i, f, g, o = torch.sigmoid(a[:, :H]), torch.sigmoid(a[:, H:2 * H]), torch.tanh(a[:, 2 * H:3 * H]), torch.sigmoid(a[:, 3 * H:])
+        c = f * c + i * g
+        h = o * torch.tanh(c)
+        hs.append(h), cs.append(c), gates.append(torch.cat([i, f, g, o], dim=1))
+    return torch.stack(hs, 1), torch.stack(cs, 1), torch.stack(gates, 1)
+
+
+def lstm_bptt(whh, hs, cs, gates, dh_out):
+    """Back-propagation through time for lstm_forward_saved — the reverse-time recurrence the BPTT kernel runs (same shape as
+    the forward recurrence: one H x 4H mat-vec per step, here with W_hh instead of W_hh^T).  Returns (dpre (B,S,4H), dW_hh);
+    dW_ih = dpre^T x, db = sum dpre and dx = dpre W_ih are plain GEMMs / reductions outside the recurrence."""
+    B, S, H = hs.shape
+    dh_next, dc_next = hs.new_zeros(B, H), hs.new_zeros(B, H)
+    dpre = hs.new_zeros(B, S, 4 * H)
+    dW = torch.zeros_like(whh)
+    for t in range(S - 1, -1, -1):
+        i, f, g, o = gates[:, t, :H], gates[:, t, H:2 * H], gates[:, t, 2 * H:3 * H], gates[:, t, 3 * H:]
+        tc = torch.tanh(cs[:, t])
+        c_prev = cs[:, t - 1] if t > 0 else torch.zeros_like(tc)
+        h_prev = hs[:, t - 1] if t > 0 else torch.zeros_like(tc)
+        dh = dh_out[:, t] + dh_next
+        dc = dh * o * (1 - tc * tc) + dc_next
+        da = torch.cat([dc * g * i * (1 - i), dc * c_prev * f * (1 - f), dc * i * (1 - g * g), dh * tc * o * (1 - o)], dim=1)
+        dpre[:, t] = da
+        dW += da.t() @ h_prev
+        dh_next = da @ whh
+        dc_next = dc * f
+    return dpre, dW

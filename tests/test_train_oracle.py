@@ -206,3 +206,24 @@ def test_complex_conv_backward_in_packed_formulation_equals_autograd(cin, cout, 
     for got, want in ((dx, x.grad), (dwr, sd["c.conv_r.weight"].grad), (dwi, sd["c.conv_i.weight"].grad),
                       (dbr, sd["c.conv_r.bias"].grad), (dbi, sd["c.conv_i.bias"].grad)):
         assert rel_err(got, want) <= 2e-5
+
+
+@pytest.mark.parametrize("B,S,H", [(3, 8, 64), (2, 5, 128)])
+def test_lstm_bptt_explicit_recurrence_equals_autograd(B, S, H):
+    """The reverse-time recurrence of the BPTT kernel (ComplexLSTM hidden 64, real LSTM hidden 128) vs autograd."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(B + S + H)
+    pre = (0.5 * torch.randn(B, S, 4 * H, generator=gen)).requires_grad_(True)
+    whh = (0.1 * torch.randn(4 * H, H, generator=gen)).requires_grad_(True)
+    hs, cs, gates = TO.lstm_forward_saved(pre, whh)
+    dh = torch.randn(B, S, H, generator=gen)
+    (hs * dh).sum().backward()
+    dpre, dW = TO.lstm_bptt(whh.detach(), hs.detach(), cs.detach(), gates.detach(), dh)
+    assert rel_err(dpre, pre.grad) <= 2e-5 and rel_err(dW, whh.grad) <= 2e-5
+    # and the forward agrees with torch.nn.LSTM (what the reference calls, c_network.py:19-28)
+    m = torch.nn.LSTM(7, H, batch_first=True)
+    x = torch.randn(B, S, 7, generator=gen)
+    with torch.no_grad():
+        ref, _ = m(x)
+        mine, _, _ = TO.lstm_forward_saved(x @ m.weight_ih_l0.t() + m.bias_ih_l0 + m.bias_hh_l0, m.weight_hh_l0)
+    assert rel_err(mine, ref) <= 1e-5
