@@ -329,3 +329,53 @@ def lstm_bptt(whh, hs, cs, gates, dh_out):
         dh_next = da @ whh
         dc_next = dc * f
     return dpre, dW
+
+
+def _cmul_conj(a, g):
+    """dL/db for y = a * b (complex) in torch's gradient convention: conj(a) * g."""
+    return _mul(torch.conj(a), g)
+
+
+def attention_backward(x, sd, p_chan, p_spat, dy, k=7):
+    """Backward of the attended product y = s * (a * x) (c_network.py:208-211 / 219-220): a = ComplexChannelAttention(x) =
+    sigma_c(2 fc(avg x)) (the "max" pool is an average, network_functions.py:135-138), u = a * x,
+    s = ComplexSpatialAttention(u) = sigma_c(conv7x7([mean_c u, max_c Re u + j max_c Im u])).
+    Returns (dx, {parameter name: gradient}).  Structure for the kernels: pass 1 over (u, dy) reduces ds = sum_c conj(u) dy per
+    pixel; a 7x7 transposed conv of the 1-channel gate gradient gives (dmean, dmax) per pixel; pass 2 forms
+    du = conj(s) dy + dmean / C + [c == argmax] dmax, reduces da = sum_hw conj(x) du per channel and writes dx = conj(a) du;
+    the gate MLP's backward adds a per-channel constant to dx."""
+    B, C, H, W = x.shape
+    ones = lambda t: t * (1 - t)  # noqa: E731
+    # ---- forward, keeping what backward needs
+    avg = torch.complex(x.real.mean([2, 3], keepdim=True), x.imag.mean([2, 3], keepdim=True))
+    w1r, w1i = sd[p_chan + "fc.0.conv_r.weight"], sd[p_chan + "fc.0.conv_i.weight"]
+    w2r, w2i = sd[p_chan + "fc.2.conv_r.weight"], sd[p_chan + "fc.2.conv_i.weight"]
+    hid_pre = O.apply_complex(lambda t: torch.nn.functional.conv2d(t, w1r), lambda t: torch.nn.functional.conv2d(t, w1i), avg)
+    hid = O.crelu(hid_pre)
+    fc = O.apply_complex(lambda t: torch.nn.functional.conv2d(t, w2r), lambda t: torch.nn.functional.conv2d(t, w2i), hid)
+    a = O.csigmoid(2 * fc)
+    u = _mul(a, x)
+    mean = torch.mean(u, dim=1, keepdim=True)
+    mre, are = torch.max(u.real, dim=1, keepdim=True)
+    mim, aim = torch.max(u.imag, dim=1, keepdim=True)
+    stats = torch.cat([mean, torch.complex(mre, mim)], dim=1)
+    w7r, w7i = sd[p_spat + "conv1.conv_r.weight"], sd[p_spat + "conv1.conv_i.weight"]
+    s = O.csigmoid(O.apply_complex(lambda t: torch.nn.functional.conv2d(t, w7r, padding=k // 2),
+                                   lambda t: torch.nn.functional.conv2d(t, w7i, padding=k // 2), stats))
+    # ---- backward
+    ds = _cmul_conj(u, dy).sum(dim=1, keepdim=True)
+    dspre = torch.complex(ds.real * ones(s.real), ds.imag * ones(s.imag))
+    dstats, d7r, d7i, _, _ = cconv2d_backward(stats, w7r, w7i, dspre, 1, k // 2)
+    du = _cmul_conj(s, dy) + dstats[:, :1] / C
+    dmax = dstats[:, 1:2]
+    du = torch.complex(du.real + torch.zeros_like(u.real).scatter_(1, are, dmax.real),
+                       du.imag + torch.zeros_like(u.imag).scatter_(1, aim, dmax.imag))
+    da = _cmul_conj(x, du).sum(dim=[2, 3], keepdim=True)
+    dfc = 2 * torch.complex(da.real * ones(a.real), da.imag * ones(a.imag))
+    dhid, d2r, d2i, _, _ = cconv2d_backward(hid, w2r, w2i, dfc, 1, 0)
+    dhid_pre = torch.complex(dhid.real * (hid_pre.real > 0), dhid.imag * (hid_pre.imag > 0))
+    davg, d1r, d1i, _, _ = cconv2d_backward(avg, w1r, w1i, dhid_pre, 1, 0)
+    dx = _cmul_conj(a, du) + davg / (H * W)
+    grads = {p_spat + "conv1.conv_r.weight": d7r, p_spat + "conv1.conv_i.weight": d7i, p_chan + "fc.2.conv_r.weight": d2r,
+             p_chan + "fc.2.conv_i.weight": d2i, p_chan + "fc.0.conv_r.weight": d1r, p_chan + "fc.0.conv_i.weight": d1i}
+    return dx, grads

@@ -227,3 +227,26 @@ def test_lstm_bptt_explicit_recurrence_equals_autograd(B, S, H):
         ref, _ = m(x)
         mine, _, _ = TO.lstm_forward_saved(x @ m.weight_ih_l0.t() + m.bias_ih_l0 + m.bias_hh_l0, m.weight_hh_l0)
     assert rel_err(mine, ref) <= 1e-5
+
+
+@pytest.mark.parametrize("C,H,W", [(16, 12, 9), (128, 2, 11), (8, 32, 20)])
+def test_attention_backward_closed_form_equals_autograd(C, H, W):
+    """Channel + spatial attention and both complex products as one backward stage (two passes over the tensor, like the
+    forward's streaming kernel) vs autograd through the oracle's forward functions."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(C + H + W)
+    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
+    R = max(C // 16, 1)
+    sd = {"a.fc.0.conv_r.weight": 0.3 * rnd(R, C, 1, 1), "a.fc.0.conv_i.weight": 0.3 * rnd(R, C, 1, 1),
+          "a.fc.2.conv_r.weight": 0.5 * rnd(C, R, 1, 1), "a.fc.2.conv_i.weight": 0.5 * rnd(C, R, 1, 1),
+          "s.conv1.conv_r.weight": 0.2 * rnd(1, 2, 7, 7), "s.conv1.conv_i.weight": 0.2 * rnd(1, 2, 7, 7)}
+    sd = {k_: v.requires_grad_(True) for k_, v in sd.items()}
+    x = torch.complex(rnd(2, C, H, W), rnd(2, C, H, W)).requires_grad_(True)
+    u = O.channel_attention(x, sd, "a.") * x
+    y = O.spatial_attention(u, sd, "s.") * u
+    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    dx, grads = TO.attention_backward(x.detach(), {k_: v.detach() for k_, v in sd.items()}, "a.", "s.", dy)
+    assert rel_err(dx, x.grad) <= 5e-5
+    for k_, g_ in grads.items():
+        assert rel_err(g_, sd[k_].grad) <= 5e-5, k_
