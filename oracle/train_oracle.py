@@ -379,3 +379,30 @@ def attention_backward(x, sd, p_chan, p_spat, dy, k=7):
     grads = {p_spat + "conv1.conv_r.weight": d7r, p_spat + "conv1.conv_i.weight": d7i, p_chan + "fc.2.conv_r.weight": d2r,
              p_chan + "fc.2.conv_i.weight": d2i, p_chan + "fc.0.conv_r.weight": d1r, p_chan + "fc.0.conv_i.weight": d1i}
     return dx, grads
+
+
+def decoder_stage_backward(d, skip, w_r, w_i, dy, up):
+    """Backward of one decoder stage's linear part (c_network.py:214-216): z = cat(d, skip) -> nearest up-sampling by `up`
+    -> ComplexConvTranspose2d(k3, s1, p1) with weights (Cin, Cout, 3, 3), in the packed formulation
+    Wp[(in part), (out part)] = [[w_r, w_i], [-w_i, w_r]]:
+      dgrad : dZup = conv2d(dY, Wp, padding 1)  (the adjoint of a stride-1 transposed conv is a plain conv with the same tensor)
+      wgrad : dWp  = correlation(dY, Zup);  dw_r = dWp[re,re] + dWp[im,im],  dw_i = dWp[re,im] - dWp[im,re]
+      up-sampling adjoint: sum over each uh x uw pixel block (an epilogue of the dgrad GEMM); concat adjoint: channel split.
+    Returns (dd, dskip, dw_r, dw_i, db_r, db_i)."""
+    F_ = torch.nn.functional
+    cin, cout = w_r.shape[0], w_r.shape[1]
+    z = torch.cat([d, skip], dim=1)
+    zup = O.cupsample_nearest(z, up)
+    Z = torch.cat([zup.real, zup.imag], dim=1)
+    dY = torch.cat([dy.real, dy.imag], dim=1)
+    Wp = torch.cat([torch.cat([w_r, w_i], dim=1), torch.cat([-w_i, w_r], dim=1)], dim=0)        # (2 Cin, 2 Cout, 3, 3)
+    dZ = F_.conv2d(dY, Wp, padding=1)
+    dWp = torch.nn.grad.conv2d_weight(dY, Wp.shape, Z, padding=1)
+    dw_r = dWp[:cin, :cout] + dWp[cin:, cout:]
+    dw_i = dWp[:cin, cout:] - dWp[cin:, :cout]
+    B, _, Hu, Wu = dZ.shape
+    dz = dZ.reshape(B, 2 * cin, Hu // up[0], up[0], Wu // up[1], up[1]).sum(dim=(3, 5))
+    dz = torch.complex(dz[:, :cin], dz[:, cin:])
+    s = dY.sum(dim=[0, 2, 3])
+    cd = d.shape[1]
+    return dz[:, :cd], dz[:, cd:], dw_r, dw_i, s[:cout] + s[cout:], s[cout:] - s[:cout]

@@ -250,3 +250,24 @@ def test_attention_backward_closed_form_equals_autograd(C, H, W):
     assert rel_err(dx, x.grad) <= 5e-5
     for k_, g_ in grads.items():
         assert rel_err(g_, sd[k_].grad) <= 5e-5, k_
+
+
+@pytest.mark.parametrize("cd,cs,cout,up", [(128, 128, 128, (2, 1)), (16, 16, 8, (2, 2)), (8, 8, 1, (2, 2))])
+def test_decoder_stage_backward_in_packed_formulation_equals_autograd(cd, cs, cout, up):
+    """concat + nearest up-sampling + ComplexConvTranspose2d backward (dgrad as a plain conv with a pixel-block-sum epilogue,
+    wgrad with block folding) vs autograd through the oracle's forward functions, at decoder shapes incl. decoder[6]."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(cd + cout)
+    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
+    cin = cd + cs
+    sd = {"t.conv_tran_r.weight": (0.1 * rnd(cin, cout, 3, 3)).requires_grad_(True), "t.conv_tran_i.weight": (0.1 * rnd(cin, cout, 3, 3)).requires_grad_(True),
+          "t.conv_tran_r.bias": rnd(cout).requires_grad_(True), "t.conv_tran_i.bias": rnd(cout).requires_grad_(True)}
+    d = torch.complex(rnd(2, cd, 4, 6), rnd(2, cd, 4, 6)).requires_grad_(True)
+    skip = torch.complex(rnd(2, cs, 4, 6), rnd(2, cs, 4, 6)).requires_grad_(True)
+    y = O.cconvT2d(O.cupsample_nearest(torch.cat((d, skip), dim=1), up), sd, "t.", 1, 1)
+    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    got = TO.decoder_stage_backward(d.detach(), skip.detach(), sd["t.conv_tran_r.weight"].detach(), sd["t.conv_tran_i.weight"].detach(), dy, up)
+    want = (d.grad, skip.grad, sd["t.conv_tran_r.weight"].grad, sd["t.conv_tran_i.weight"].grad, sd["t.conv_tran_r.bias"].grad, sd["t.conv_tran_i.bias"].grad)
+    for g_, w_ in zip(got, want):
+        assert rel_err(g_, w_) <= 2e-5
