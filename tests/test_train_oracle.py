@@ -271,3 +271,31 @@ def test_decoder_stage_backward_in_packed_formulation_equals_autograd(cd, cs, co
     want = (d.grad, skip.grad, sd["t.conv_tran_r.weight"].grad, sd["t.conv_tran_i.weight"].grad, sd["t.conv_tran_r.bias"].grad, sd["t.conv_tran_i.bias"].grad)
     for g_, w_ in zip(got, want):
         assert rel_err(g_, w_) <= 2e-5
+
+
+def test_encoder_layer_backward_chain_equals_autograd():
+    """The contracts composed as an encoder layer runs them backward: ComplexReLU mask -> cbn_train_backward ->
+    cconv2d_backward, vs autograd through conv + train-mode BN + ReLU.  (Also shows why the reference's conv biases get a
+    zero gradient in train mode: dY into the conv has zero mean per channel after the BN backward.)"""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
+    cin, cout, k, stride = 8, 16, 5, (2, 2)
+    sd = {"e.0.conv_r.weight": (0.2 * rnd(cout, cin, k, k)).requires_grad_(True), "e.0.conv_i.weight": (0.2 * rnd(cout, cin, k, k)).requires_grad_(True),
+          "e.0.conv_r.bias": rnd(cout).requires_grad_(True), "e.0.conv_i.bias": rnd(cout).requires_grad_(True),
+          "e.1.weight": torch.stack([1 + 0.2 * torch.rand(cout, generator=gen), 1 + 0.2 * torch.rand(cout, generator=gen),
+                                     0.2 * torch.rand(cout, generator=gen) - 0.1], dim=1).requires_grad_(True),
+          "e.1.bias": (0.1 * rnd(cout, 2)).requires_grad_(True),
+          "e.1.running_mean": torch.zeros(cout, dtype=torch.complex64), "e.1.running_covar": torch.ones(cout, 3)}
+    x = torch.complex(rnd(3, cin, 16, 12), rnd(3, cin, 16, 12)).requires_grad_(True)
+    conv = O.cconv2d(x, sd, "e.0.", stride, k // 2)
+    bn = TO.cbn_train({})(conv, sd, "e.1.")
+    y = O.crelu(bn)
+    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    dbn = torch.complex(dy.real * (bn.real > 0), dy.imag * (bn.imag > 0)).detach()
+    dconv, dw, db = TO.cbn_train_backward(conv.detach(), dbn, sd["e.1.weight"].detach())
+    dx, dwr, dwi, dbr, dbi = TO.cconv2d_backward(x.detach(), sd["e.0.conv_r.weight"].detach(), sd["e.0.conv_i.weight"].detach(), dconv, stride, k // 2)
+    assert rel_err(dx, x.grad) <= 5e-5 and rel_err(dwr, sd["e.0.conv_r.weight"].grad) <= 5e-5 and rel_err(dwi, sd["e.0.conv_i.weight"].grad) <= 5e-5
+    assert rel_err(dw, sd["e.1.weight"].grad) <= 5e-5 and rel_err(db, sd["e.1.bias"].grad) <= 5e-5
+    assert float(dbr.abs().max()) <= 1e-4 * float(dwr.abs().max()) and float(dbi.abs().max()) <= 1e-4 * float(dwr.abs().max())
