@@ -299,3 +299,48 @@ def test_encoder_layer_backward_chain_equals_autograd():
     assert rel_err(dx, x.grad) <= 5e-5 and rel_err(dwr, sd["e.0.conv_r.weight"].grad) <= 5e-5 and rel_err(dwi, sd["e.0.conv_i.weight"].grad) <= 5e-5
     assert rel_err(dw, sd["e.1.weight"].grad) <= 5e-5 and rel_err(db, sd["e.1.bias"].grad) <= 5e-5
     assert float(dbr.abs().max()) <= 1e-4 * float(dwr.abs().max()) and float(dbi.abs().max()) <= 1e-4 * float(dwr.abs().max())
+
+
+def test_decoder_stage_full_backward_chain_equals_autograd():
+    """A whole decoder stage backward from the contracts: attention_backward (decoder attention) -> LeakyReLU mask ->
+    cbn_train_backward -> decoder_stage_backward (convT, up-sampling, concat), and the skip branch through attention_backward
+    (skip attention), vs autograd through the oracle's forward functions (c_network.py:207-220)."""
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(8)
+    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
+    C, cout, up = 32, 16, (2, 2)
+    R_in, R_out = max(C // 16, 1), max(cout // 16, 1)
+    sd = {"sk.a.fc.0.conv_r.weight": 0.3 * rnd(R_in, C, 1, 1), "sk.a.fc.0.conv_i.weight": 0.3 * rnd(R_in, C, 1, 1),
+          "sk.a.fc.2.conv_r.weight": 0.5 * rnd(C, R_in, 1, 1), "sk.a.fc.2.conv_i.weight": 0.5 * rnd(C, R_in, 1, 1),
+          "sk.s.conv1.conv_r.weight": 0.2 * rnd(1, 2, 7, 7), "sk.s.conv1.conv_i.weight": 0.2 * rnd(1, 2, 7, 7),
+          "da.a.fc.0.conv_r.weight": 0.3 * rnd(R_out, cout, 1, 1), "da.a.fc.0.conv_i.weight": 0.3 * rnd(R_out, cout, 1, 1),
+          "da.a.fc.2.conv_r.weight": 0.5 * rnd(cout, R_out, 1, 1), "da.a.fc.2.conv_i.weight": 0.5 * rnd(cout, R_out, 1, 1),
+          "da.s.conv1.conv_r.weight": 0.2 * rnd(1, 2, 7, 7), "da.s.conv1.conv_i.weight": 0.2 * rnd(1, 2, 7, 7),
+          "t.0.conv_tran_r.weight": 0.1 * rnd(2 * C, cout, 3, 3), "t.0.conv_tran_i.weight": 0.1 * rnd(2 * C, cout, 3, 3),
+          "t.0.conv_tran_r.bias": rnd(cout), "t.0.conv_tran_i.bias": rnd(cout),
+          "t.1.weight": torch.stack([1 + 0.2 * torch.rand(cout, generator=gen), 1 + 0.2 * torch.rand(cout, generator=gen),
+                                     0.2 * torch.rand(cout, generator=gen) - 0.1], dim=1), "t.1.bias": 0.1 * rnd(cout, 2)}
+    sd = {k_: v.requires_grad_(True) for k_, v in sd.items()}
+    sd.update({"t.1.running_mean": torch.zeros(cout, dtype=torch.complex64), "t.1.running_covar": torch.ones(cout, 3)})
+    d = torch.complex(rnd(2, C, 4, 6), rnd(2, C, 4, 6)).requires_grad_(True)
+    skip = torch.complex(rnd(2, C, 4, 6), rnd(2, C, 4, 6)).requires_grad_(True)
+    ca = O.channel_attention(skip, sd, "sk.a.") * skip
+    sa = O.spatial_attention(ca, sd, "sk.s.") * ca
+    lin = O.cconvT2d(O.cupsample_nearest(torch.cat((d, sa), dim=1), up), sd, "t.0.", 1, 1)
+    bn = TO.cbn_train({})(lin, sd, "t.1.")
+    act = O.clrelu(bn)
+    y = act * O.channel_attention(act, sd, "da.a.")
+    y = y * O.spatial_attention(y, sd, "da.s.")
+    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    det = {k_: v.detach() for k_, v in sd.items()}
+    dact, g_da = TO.attention_backward(act.detach(), det, "da.a.", "da.s.", dy)
+    slope = lambda t: torch.where(t > 0, torch.ones_like(t), torch.full_like(t, O.LRELU_SLOPE))   # noqa: E731
+    dbn = torch.complex(dact.real * slope(bn.real.detach()), dact.imag * slope(bn.imag.detach()))
+    dlin, dw_bn, db_bn = TO.cbn_train_backward(lin.detach(), dbn, det["t.1.weight"])
+    dd, dsa, dwr, dwi, _, _ = TO.decoder_stage_backward(d.detach(), sa.detach(), det["t.0.conv_tran_r.weight"], det["t.0.conv_tran_i.weight"], dlin, up)
+    dskip, g_sk = TO.attention_backward(skip.detach(), det, "sk.a.", "sk.s.", dsa)
+    assert rel_err(dd, d.grad) <= 1e-4 and rel_err(dskip, skip.grad) <= 1e-4
+    assert rel_err(dwr, sd["t.0.conv_tran_r.weight"].grad) <= 1e-4 and rel_err(dw_bn, sd["t.1.weight"].grad) <= 1e-4
+    for k_, g_ in list(g_da.items()) + list(g_sk.items()):
+        assert rel_err(g_, sd[k_].grad) <= 1e-4, k_
