@@ -406,3 +406,12 @@ def decoder_stage_backward(d, skip, w_r, w_i, dy, up):
     s = dY.sum(dim=[0, 2, 3])
     cd = d.shape[1]
     return dz[:, :cd], dz[:, cd:], dw_r, dw_i, s[:cout] + s[cout:], s[cout:] - s[:cout]
+
+
+def clinear_backward(x, w_r, w_i, dy):
+    """ComplexLinear (c_network.py:124-126, 202) backward = the 1x1 case of cconv2d_backward on (B*S, in) rows.
+    x, dy: (B, S, features) complex.  Returns (dx, dw_r, dw_i, db_r, db_i)."""
+    B, S, _ = x.shape
+    as_img = lambda t: t.reshape(B * S, -1, 1, 1)                        # noqa: E731
+    dx, dwr, dwi, dbr, dbi = cconv2d_backward(as_img(x), w_r[:, :, None, None], w_i[:, :, None, None], as_img(dy), 1, 0)
+    return dx.reshape(B, S, -1), dwr[:, :, 0, 0], dwi[:, :, 0, 0], dbr, dbi

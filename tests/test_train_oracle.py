@@ -344,3 +344,19 @@ def test_decoder_stage_full_backward_chain_equals_autograd():
     assert rel_err(dwr, sd["t.0.conv_tran_r.weight"].grad) <= 1e-4 and rel_err(dw_bn, sd["t.1.weight"].grad) <= 1e-4
     for k_, g_ in list(g_da.items()) + list(g_sk.items()):
         assert rel_err(g_, sd[k_].grad) <= 1e-4, k_
+
+
+def test_complex_linear_backward_equals_autograd():
+    from oracle import train_oracle as TO
+    gen = torch.Generator().manual_seed(4)
+    rnd = lambda *s: torch.randn(*s, generator=gen)                      # noqa: E731
+    sd = {"fc.fc_r.weight": (0.1 * rnd(128, 128)).requires_grad_(True), "fc.fc_i.weight": (0.1 * rnd(128, 128)).requires_grad_(True),
+          "fc.fc_r.bias": rnd(128).requires_grad_(True), "fc.fc_i.bias": rnd(128).requires_grad_(True)}
+    x = torch.complex(rnd(2, 10, 128), rnd(2, 10, 128)).requires_grad_(True)
+    y = O.clinear(x, sd, "fc.")
+    dy = torch.complex(rnd(*y.shape), rnd(*y.shape))
+    (y.real * dy.real + y.imag * dy.imag).sum().backward()
+    got = TO.clinear_backward(x.detach(), sd["fc.fc_r.weight"].detach(), sd["fc.fc_i.weight"].detach(), dy)
+    want = (x.grad, sd["fc.fc_r.weight"].grad, sd["fc.fc_i.weight"].grad, sd["fc.fc_r.bias"].grad, sd["fc.fc_i.bias"].grad)
+    for g_, w_ in zip(got, want):
+        assert rel_err(g_, w_) <= 2e-5
