@@ -32,7 +32,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--mode", default="fp16", choices=["fp16", "bf16", "fp32"],
+                    help="fp16 = the tensor-core mode (tcgen05 kind::f16 on fp16 storage, fp32 accumulation; parity <= 2e-3)")
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
     ap.add_argument("--frames", type=int, default=2000, help="STFT frames per utterance (2000 = 3.998 s)")
     ap.add_argument("--variant", default="dcs", choices=["dcs", "dc"])
@@ -232,7 +233,7 @@ def run_ours(args, rank, local_rank, world):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "bf16" if args.mode == "bf16" else "f32", "data": "synthetic",
+        "dtype": {"fp16": "f16", "bf16": "bf16", "fp32": "f32"}[args.mode], "data": "synthetic",
         "config": {"workload": f"DCS-Net ({args.variant}) batched inference, batch {B} x {O.audio_seconds(T):.3f} s utterances per GPU "
                                f"(T={T} frames, config.py STFT defaults), random-init weights seed 0 (BASELINE.json configs[1])",
                    "mode": args.mode, "global_batch": B * world, "samples_per_utterance": n_samples,
@@ -346,7 +347,7 @@ def measure_roofline(plan, args, B, T):
     roof = None
     # ---- tensor-core convolution family (the only dense contractions of the path)
     tc_keys = [k for k in ("conv_tc", "conv_strip") if k in stage_ms]
-    if args.mode == "bf16" and tc_keys:
+    if args.mode in ("fp16", "bf16") and tc_keys:
         # every conv layer runs on tcgen05 in this mode when enc0 / dec6 are on the strip kernel; otherwise they are
         # CUDA-core kernels ("enc0", "dec6_tail" stages) and their FLOPs are excluded
         layers = [k for k in fl if not ((k == "enc0" and "enc0" in stage_ms) or (k == "dec6" and "dec6_tail" in stage_ms))]
@@ -377,7 +378,7 @@ def measure_roofline(plan, args, B, T):
                 "achieved": ach, "peak": peaks.get("bf16_tflops_sustained", 1590.0), "unit": "TFLOP/s",
                 "frac": ach / peaks.get("bf16_tflops_sustained", 1590.0), "traffic": None}
     # ---- bandwidth-bound stages: algorithmic bytes (each tensor moved once) / measured stage time
-    esz = 2 if args.mode == "bf16" else 4
+    esz = 2 if args.mode in ("fp16", "bf16") else 4
     att = [t for t in plan.enc] + [t for t in plan.dec[:-1]]
     att_bytes = sum(t.numel() * t.element_size() for t in att)          # every attended tensor once
     stage_bytes = {

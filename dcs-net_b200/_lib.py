@@ -12,7 +12,8 @@ import torch
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcsnet_sm100a.so")
 
-F32, BF16 = 0, 1
+F32, BF16, F16 = 0, 1, 2
+POOL_FRAC_BITS = 28           # pooled sums are int64 fixed point (include/dcsnet.h: DCS_POOL_FRAC_BITS)
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 COMBINE_DCS, COMBINE_DC = 0, 1
 MAX_TAPS = 64
@@ -85,7 +86,7 @@ class CstripParams(C.Structure):
                 ("weights", _vp),
                 ("box_units", _i), ("n_mma", _i), ("cols", _i),
                 ("bias", _vp), ("act", _i),
-                ("dst", _vp), ("pool_sums", _vp), ("tail", C.POINTER(StripTail))]
+                ("dst", _vp), ("pool_sums", _vp), ("tail", C.POINTER(StripTail)), ("dtype", _i)]
 
 
 class ChanPoolParams(C.Structure):
@@ -157,6 +158,7 @@ SYMBOLS = {
     "dcs_cconv2d_strip_fwd": (_i, [C.POINTER(CstripParams), _vp]),
     "dcs_chan_pool": (_i, [C.POINTER(ChanPoolParams), _vp]),
     "dcs_chan_gate": (_i, [C.POINTER(ChanGateParams), _vp]),
+    "dcs_pool_mean": (_i, [_vp, _f, _vp, _i64, _vp]),
     "dcs_spat_stats": (_i, [C.POINTER(SpatStatsParams), _vp]),
     "dcs_spat_apply": (_i, [C.POINTER(SpatApplyParams), _vp]),
     "dcs_attention_fused": (_i, [C.POINTER(AttentionParams), _vp]),
@@ -174,6 +176,7 @@ SYMBOLS = {
     "dcs_upsample_nearest": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_tc_set_debug_buffer": (_i, [_vp]),
     "dcs_convert": (_i, [_vp, _vp, _i64, _i, _i, _vp]),
+    "dcs_zero": (_i, [_vp, _i64, _vp]),
 }
 
 _lib = None
@@ -194,7 +197,7 @@ def lib():
             except AttributeError as e:
                 raise RuntimeError(f"{LIB_PATH} does not export {name}; rebuild it") from e
             fn.restype, fn.argtypes = res, args
-        if l.dcs_abi_version() != 1:
+        if l.dcs_abi_version() != 2:
             raise RuntimeError("libdcsnet_sm100a.so ABI version mismatch; rebuild it")
         _lib = l
     return _lib
@@ -229,4 +232,6 @@ def dtype_code(t):
         return F32
     if t.dtype == torch.bfloat16:
         return BF16
+    if t.dtype == torch.float16:
+        return F16
     raise RuntimeError(f"unsupported activation dtype {t.dtype}")

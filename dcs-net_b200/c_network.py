@@ -29,7 +29,15 @@ except Exception:  # pragma: no cover - the image has no pytorch_lightning
     pl = None
 
     class _HParams(dict):
-        __getattr__ = dict.__getitem__
+        """Attribute-style dict like Lightning's AttributeDict: a missing key is an AttributeError (so copy.deepcopy,
+        hasattr and getattr-with-default work)."""
+
+        def __getattr__(self, name):
+            try:
+                return self[name]
+            except KeyError:
+                raise AttributeError(name) from None
+
         __setattr__ = dict.__setitem__
 
     class _Base(torch.nn.Module):
@@ -211,7 +219,7 @@ class ComplexChannelAttention(torch.nn.Module):
         sd = {"a." + k: v for k, v in self.state_dict().items()}
         ca = self._cache.get(_version_key(*self.parameters()) + (str(x.device),),
                              lambda: packing.pack_channel_attention(sd, "a.", x.device))
-        sums = torch.zeros(B, Cn, 2, dtype=torch.float32, device=x.device)
+        sums = ops.zero_(torch.empty(B, Cn, 2, dtype=torch.int64, device=x.device))
         gate = torch.empty(B, Cn, 2, dtype=torch.float32, device=x.device)
         ops.chan_pool(xr, sums)
         ops.chan_gate(sums, H * W, ca, gate)
@@ -241,8 +249,9 @@ class ComplexSpatialAttention(torch.nn.Module):
 
 
 class C_NETWORK(_StepMixin, _Base):
-    """c_network.py:87-226.  Extra (non-reference) attribute: `compute_mode` in {'fp32', 'bf16'} selects the CUDA-core
-    fp32 GEMMs (<=1e-5) or the tcgen05 bf16 GEMMs (<=2e-3); default 'fp32' = the reference's precision=32."""
+    """c_network.py:87-226.  Extra (non-reference) attribute: `compute_mode` in {'fp32', 'fp16', 'bf16'} (engine.MODES) selects the
+    CUDA-core fp32 GEMMs (<=1e-5) or the tcgen05 GEMMs on fp16 storage (<=2e-3; 'bf16' = the wide-range variant, ~3.6e-3 on
+    the randomised-BN parity state); default 'fp32' = the reference's precision=32."""
 
     def __init__(self, config, hparams, seed):
         super().__init__()

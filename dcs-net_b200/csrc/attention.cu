@@ -10,6 +10,7 @@
 //   3. spat_stats: st[b][h][w] = {mean_c(g_c x), max_c Re, max_c Im}   (read x once, write 16 B / pixel)
 //   4. spat_apply: y = sigmoid_c(conv7x7(st)) * (g_c x)                (read x once, write y once)
 #include <string.h>
+#include <algorithm>
 #include "common.cuh"
 
 namespace dcs {
@@ -26,25 +27,27 @@ template <> struct Vec16<float> {
     *reinterpret_cast<float4*>(p + 2 * cidx) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
   }
 };
-template <> struct Vec16<__nv_bfloat16> {
+template <typename T> struct Vec16H {   // 16-bit storage (fp16 / bf16): 4 complex per 16 bytes
   static constexpr int N = 4;
-  static __device__ __forceinline__ void ld(const __nv_bfloat16* p, int64_t cidx, float2 (&v)[4]) {
+  static __device__ __forceinline__ void ld(const T* p, int64_t cidx, float2 (&v)[4]) {
     const uint4 q = __ldg(reinterpret_cast<const uint4*>(p + 2 * cidx));
     const uint32_t w[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = make_float2(__uint_as_float(w[i] << 16), __uint_as_float(w[i] & 0xffff0000u));
+    for (int i = 0; i < 4; ++i) v[i] = unpack_h2<T>(w[i]);
   }
-  static __device__ __forceinline__ void st(__nv_bfloat16* p, int64_t cidx, const float2 (&v)[4]) {
+  static __device__ __forceinline__ void st(T* p, int64_t cidx, const float2 (&v)[4]) {
     uint32_t w[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) { __nv_bfloat162 t = __float22bfloat162_rn(v[i]); w[i] = *reinterpret_cast<uint32_t*>(&t); }
+    for (int i = 0; i < 4; ++i) w[i] = pack_h2<T>(v[i].x, v[i].y);
     *reinterpret_cast<uint4*>(p + 2 * cidx) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
+template <> struct Vec16<__nv_bfloat16> : Vec16H<__nv_bfloat16> {};
+template <> struct Vec16<__half> : Vec16H<__half> {};
 
 // ---------------------------------------------------------------- 1. global average pool (sums)
 template <typename T>
-__global__ void __launch_bounds__(256) chan_pool_kernel(const T* __restrict__ x, float* __restrict__ sums, int hw, int C,
+__global__ void __launch_bounds__(256) chan_pool_kernel(const T* __restrict__ x, long long* __restrict__ sums, int hw, int C,
                                                         int pix_per_cta) {
   __shared__ float2 red[256];
   const int b = blockIdx.y;
@@ -64,8 +67,8 @@ __global__ void __launch_bounds__(256) chan_pool_kernel(const T* __restrict__ x,
   if (threadIdx.x < C) {
     float2 s = make_float2(0.f, 0.f);
     for (int l = 0; l < lanes; ++l) { const float2 v = red[l * C + threadIdx.x]; s.x += v.x; s.y += v.y; }
-    atomicAdd(sums + ((int64_t)b * C + threadIdx.x) * 2 + 0, s.x);
-    atomicAdd(sums + ((int64_t)b * C + threadIdx.x) * 2 + 1, s.y);
+    pool_add(sums + ((int64_t)b * C + threadIdx.x) * 2 + 0, s.x);
+    pool_add(sums + ((int64_t)b * C + threadIdx.x) * 2 + 1, s.y);
   }
 }
 
@@ -75,7 +78,8 @@ __global__ void __launch_bounds__(128) chan_gate_kernel(const dcs_chan_gate_para
   __shared__ float2 hid[16];
   const int b = blockIdx.x, C = p.channels, R = p.reduced;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    avg[c] = make_float2(p.sums[((int64_t)b * C + c) * 2] * p.inv_hw, p.sums[((int64_t)b * C + c) * 2 + 1] * p.inv_hw);
+    const long long* sm = reinterpret_cast<const long long*>(p.sums);
+    avg[c] = make_float2(pool_mean(sm, ((int64_t)b * C + c) * 2, p.inv_hw), pool_mean(sm, ((int64_t)b * C + c) * 2 + 1, p.inv_hw));
   }
   __syncthreads();
   // hidden r: one warp per r (C <= 256), complex 1x1 conv without bias then ComplexReLU
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(128) chan_gate_kernel(const dcs_chan_gate_para
 
 // ---------------------------------------------------------------- 3. per-pixel channel statistics of u = g_c * x
 struct GateMlp {   // optional fused ComplexChannelAttention MLP (dcs_chan_gate) in the statistics kernel
-  const float* sums; float inv_hw; int reduced;
+  const long long* sums; float inv_hw; int reduced;
   const float *w1_r, *w1_i, *w2_r, *w2_i;
   float* gate_out;
 };
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(256) spat_stats_kernel(const T* __restrict__ x
     // gate = sigmoid_c(2 W2 crelu(W1 avg)) recomputed by every CTA of the image (C*R complex MACs); CTA 0 publishes it
     const int R = mlp.reduced;
     for (int c = threadIdx.x; c < C; c += blockDim.x)
-      avg[c] = make_float2(mlp.sums[((int64_t)b * C + c) * 2] * mlp.inv_hw, mlp.sums[((int64_t)b * C + c) * 2 + 1] * mlp.inv_hw);
+      avg[c] = make_float2(pool_mean(mlp.sums, ((int64_t)b * C + c) * 2, mlp.inv_hw), pool_mean(mlp.sums, ((int64_t)b * C + c) * 2 + 1, mlp.inv_hw));
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int r = warp; r < R; r += 8) {
@@ -296,7 +300,7 @@ constexpr int kFaR = 3, kFaThreads = 256;
 
 struct FusedAttArgs {
   const void* x; void* y;
-  const float* sums; float inv_hw;
+  const long long* sums; float inv_hw;
   const float *w1_r, *w1_i, *w2_r, *w2_i, *w7;
   int H, W, C, clog2, R, TH, TW;
 };
@@ -334,7 +338,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attention_fused_kernel(const Fu
   // ---- 0. channel gate (ComplexChannelAttention: sigmoid_c(2 W2 crelu(W1 avg)))
   for (int i = tid; i < 49; i += kFaThreads) wq[i] = make_float4(a.w7[i], a.w7[49 + i], a.w7[98 + i], a.w7[147 + i]);
   for (int c = tid; c < C; c += kFaThreads)
-    avg[c] = make_float2(a.sums[((int64_t)b * C + c) * 2] * a.inv_hw, a.sums[((int64_t)b * C + c) * 2 + 1] * a.inv_hw);
+    avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
   __syncthreads();
   for (int r = warp; r < a.R; r += kFaThreads / 32) {
     float re = 0.f, im = 0.f;
@@ -373,7 +377,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attention_fused_kernel(const Fu
           if constexpr (VI == 4) {
             const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = make_float2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u));
+            for (int e = 0; e < 4; ++e) v[e] = unpack_h2<TI>(w4[e]);
           } else {
             v[0] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
             v[1] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
@@ -452,7 +456,7 @@ __global__ void __launch_bounds__(kFaThreads, 2) attention_fused_kernel(const Fu
       if constexpr (VI == 4) {
         const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = make_float2(__uint_as_float(w4[e] << 16), __uint_as_float(w4[e] & 0xffff0000u));
+        for (int e = 0; e < 4; ++e) v[e] = unpack_h2<TI>(w4[e]);
       } else {
         v[0] = make_float2(__uint_as_float(q.x), __uint_as_float(q.y));
         v[1] = make_float2(__uint_as_float(q.z), __uint_as_float(q.w));
@@ -463,9 +467,8 @@ __global__ void __launch_bounds__(kFaThreads, 2) attention_fused_kernel(const Fu
       const int64_t o = ((int64_t)yy * a.W + xx) * C + cv * VI;
       if constexpr (sizeof(TO) == sizeof(TI)) {
         Vec16<TO>::st(yb, o, v);
-      } else if constexpr (sizeof(TO) == 2) {          // fp32 in, bf16 out: 2 complex = 8 bytes
-        __nv_bfloat162 t0 = __float22bfloat162_rn(v[0]), t1 = __float22bfloat162_rn(v[1]);
-        *reinterpret_cast<uint2*>(yb + 2 * o) = make_uint2(*reinterpret_cast<uint32_t*>(&t0), *reinterpret_cast<uint32_t*>(&t1));
+      } else if constexpr (sizeof(TO) == 2) {          // fp32 in, 16-bit out: 2 complex = 8 bytes
+        *reinterpret_cast<uint2*>(yb + 2 * o) = make_uint2(pack_h2<TO>(v[0].x, v[0].y), pack_h2<TO>(v[1].x, v[1].y));
       } else {                                         // bf16 in, fp32 out: 4 complex = 32 bytes
         *reinterpret_cast<float4*>(yb + 2 * o) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
         *reinterpret_cast<float4*>(yb + 2 * o + 4) = make_float4(v[2].x, v[2].y, v[3].x, v[3].y);
@@ -490,8 +493,25 @@ extern "C" int dcs_chan_pool(const dcs_chan_pool_params* p, void* stream) {
   const int ppc = (p->hw + ctas - 1) / ctas;
   dim3 grid((p->hw + ppc - 1) / ppc, p->batch);
   cudaStream_t s = (cudaStream_t)stream;
-  if (p->dtype == DCS_BF16) chan_pool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, p->sums, p->hw, p->channels, ppc);
-  else chan_pool_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, p->sums, p->hw, p->channels, ppc);
+  DCS_REQUIRE(is_dtype(p->dtype), "dcs_chan_pool: bad dtype");
+  long long* sums = reinterpret_cast<long long*>(p->sums);
+  if (p->dtype == DCS_BF16) chan_pool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, sums, p->hw, p->channels, ppc);
+  else if (p->dtype == DCS_F16) chan_pool_kernel<__half><<<grid, 256, 0, s>>>((const __half*)p->x, sums, p->hw, p->channels, ppc);
+  else chan_pool_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, sums, p->hw, p->channels, ppc);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+namespace dcs {
+__global__ void pool_mean_kernel(const long long* __restrict__ sums, float inv_hw, float* __restrict__ mean, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    mean[i] = pool_mean(sums, i, inv_hw);
+}
+}  // namespace dcs
+
+extern "C" int dcs_pool_mean(const int64_t* sums, float inv_hw, float* mean, int64_t n, void* stream) {
+  DCS_REQUIRE(sums && mean && n > 0, "dcs_pool_mean: bad arguments");
+  pool_mean_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 1024), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const long long*>(sums), inv_hw, mean, n);
   DCS_LAUNCHED();
   return 0;
 }
@@ -508,7 +528,8 @@ extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
   DCS_REQUIRE(p && p->x && p->stats, "dcs_spat_stats: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->h > 0 && p->w > 0 && pow2(p->channels) && p->channels <= 256, "dcs_spat_stats: bad shape");
   const int hw = p->h * p->w;
-  const int vec = p->dtype == DCS_BF16 ? 4 : 2;
+  DCS_REQUIRE(is_dtype(p->dtype), "dcs_spat_stats: bad dtype");
+  const int vec = is_h16(p->dtype) ? 4 : 2;
   DCS_REQUIRE(p->channels % vec == 0, "dcs_spat_stats: channels must be a multiple of %d", vec);
   const int G = min(32, p->channels / vec), groups = 256 / G;
   int ctas = (hw + groups - 1) / groups;
@@ -519,10 +540,11 @@ extern "C" int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream) {
   memset(&mlp, 0, sizeof(mlp));
   if (p->sums) {
     DCS_REQUIRE(p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->reduced > 0 && p->reduced <= 16, "dcs_spat_stats: incomplete gate MLP operands");
-    mlp.sums = p->sums; mlp.inv_hw = 1.f / (float)hw; mlp.reduced = p->reduced;
+    mlp.sums = reinterpret_cast<const long long*>(p->sums); mlp.inv_hw = 1.f / (float)hw; mlp.reduced = p->reduced;
     mlp.w1_r = p->w1_r; mlp.w1_i = p->w1_i; mlp.w2_r = p->w2_r; mlp.w2_i = p->w2_i; mlp.gate_out = p->gate_out;
   }
   if (p->dtype == DCS_BF16) spat_stats_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G, mlp);
+  else if (p->dtype == DCS_F16) spat_stats_kernel<__half><<<grid, 256, 0, s>>>((const __half*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G, mlp);
   else spat_stats_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, p->chan_gate, (float4*)p->stats, hw, p->channels, G, mlp);
   DCS_LAUNCHED();
   return 0;
@@ -549,9 +571,14 @@ extern "C" int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream) {
     else if (tw == 64) DCS_SA_T(TI, TO, 4, 64);                 \
     else DCS_SA_T(TI, TO, 4, 16);                               \
   } while (0)
+  DCS_REQUIRE(is_dtype(p->in_dtype) && is_dtype(p->out_dtype), "dcs_spat_apply: bad dtype");
+  DCS_REQUIRE(!is_h16(p->in_dtype) || !is_h16(p->out_dtype) || p->in_dtype == p->out_dtype, "dcs_spat_apply: mixed 16-bit types");
   if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_SA(float, float);
   else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_SA(float, __nv_bfloat16);
+  else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F16) DCS_SA(float, __half);
   else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_SA(__nv_bfloat16, float);
+  else if (p->in_dtype == DCS_F16 && p->out_dtype == DCS_F32) DCS_SA(__half, float);
+  else if (p->in_dtype == DCS_F16) DCS_SA(__half, __half);
   else DCS_SA(__nv_bfloat16, __nv_bfloat16);
 #undef DCS_SA_T
 #undef DCS_SA
@@ -565,7 +592,9 @@ extern "C" int dcs_attention_fused(const dcs_attention_params* p, void* stream) 
   DCS_REQUIRE(pow2(p->channels) && p->channels >= 4 && p->channels <= 256 && p->reduced > 0 && p->reduced <= 16,
               "dcs_attention_fused: channels must be a power of two in [4, 256], reduced <= 16");
   const int C = p->channels;
-  const size_t esz = p->in_dtype == DCS_BF16 ? 2 : 4;
+  DCS_REQUIRE(is_dtype(p->in_dtype) && is_dtype(p->out_dtype), "dcs_attention_fused: bad dtype");
+  DCS_REQUIRE(!is_h16(p->in_dtype) || !is_h16(p->out_dtype) || p->in_dtype == p->out_dtype, "dcs_attention_fused: mixed 16-bit types");
+  const size_t esz = is_h16(p->in_dtype) ? 2 : 4;
   // tile: full image height when it is short (no vertical halo), else 16 rows; the widest power-of-two TW whose
   // x tile + halo stays under ~92 KB (two CTAs per SM)
   const int TH = p->h <= 32 ? p->h : 16;
@@ -579,7 +608,7 @@ extern "C" int dcs_attention_fused(const dcs_attention_params* p, void* stream) 
   const size_t smem = bytes(TW);
   DCS_REQUIRE(smem <= 227 * 1024, "dcs_attention_fused: tile does not fit shared memory (C=%d H=%d)", C, p->h);
   FusedAttArgs a;
-  a.x = p->x; a.y = p->y; a.sums = p->sums; a.inv_hw = 1.f / ((float)p->h * (float)p->w);
+  a.x = p->x; a.y = p->y; a.sums = reinterpret_cast<const long long*>(p->sums); a.inv_hw = 1.f / ((float)p->h * (float)p->w);
   a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
   a.H = p->h; a.W = p->w; a.C = C; a.clog2 = __builtin_ctz(C); a.R = p->reduced; a.TH = TH; a.TW = TW;
   dim3 grid((p->w + TW - 1) / TW, (p->h + TH - 1) / TH, p->batch);
@@ -591,7 +620,10 @@ extern "C" int dcs_attention_fused(const dcs_attention_params* p, void* stream) 
   } while (0)
   if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32) DCS_FA(float, float);
   else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16) DCS_FA(float, __nv_bfloat16);
+  else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F16) DCS_FA(float, __half);
   else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32) DCS_FA(__nv_bfloat16, float);
+  else if (p->in_dtype == DCS_F16 && p->out_dtype == DCS_F32) DCS_FA(__half, float);
+  else if (p->in_dtype == DCS_F16) DCS_FA(__half, __half);
   else DCS_FA(__nv_bfloat16, __nv_bfloat16);
 #undef DCS_FA
   DCS_LAUNCHED();

@@ -26,8 +26,8 @@ namespace dcs {
 constexpr int kAsThreads = 256, kAsRing = 8;
 
 struct AttStreamArgs {
-  const __nv_bfloat16* x; __nv_bfloat16* y;
-  const float* sums; float inv_hw;
+  const void* x; void* y;           // 16-bit storage (fp16 or bf16: the kernel's template parameter)
+  const long long* sums; float inv_hw;
   const float *w1_r, *w1_i, *w2_r, *w2_i, *w7;
   int H, W, R, NR;
 };
@@ -64,13 +64,14 @@ __device__ __forceinline__ float2 fma2(const float2 a, const float2 b, const flo
       "l"(*reinterpret_cast<const unsigned long long*>(&b)), "l"(*reinterpret_cast<const unsigned long long*>(&c)));
   return *reinterpret_cast<float2*>(&r);
 }
-// a 16-byte vector = 4 complex bf16 (e0 e1 e2 e3) as two element PAIRS in split form: re = (e_a.re, e_b.re), im likewise
+// a 16-byte vector = 4 complex 16-bit values (e0 e1 e2 e3) as two element PAIRS in split form: re = (e_a.re, e_b.re), im
+// likewise.  Eight single-result conversions either way (bf16: shift / mask, fp16: the two halves of HADD2.F32).
 struct CPair { float2 re, im; };
+template <typename T>
 __device__ __forceinline__ void unpack_pairs(const uint4 q, CPair& p01, CPair& p23) {
-  p01.re = make_float2(__uint_as_float(q.x << 16), __uint_as_float(q.y << 16));
-  p01.im = make_float2(__uint_as_float(q.x & 0xffff0000u), __uint_as_float(q.y & 0xffff0000u));
-  p23.re = make_float2(__uint_as_float(q.z << 16), __uint_as_float(q.w << 16));
-  p23.im = make_float2(__uint_as_float(q.z & 0xffff0000u), __uint_as_float(q.w & 0xffff0000u));
+  const float2 e0 = unpack_h2<T>(q.x), e1 = unpack_h2<T>(q.y), e2 = unpack_h2<T>(q.z), e3 = unpack_h2<T>(q.w);
+  p01.re = make_float2(e0.x, e1.x); p01.im = make_float2(e0.y, e1.y);
+  p23.re = make_float2(e2.x, e3.x); p23.im = make_float2(e2.y, e3.y);
 }
 // per-thread channel gate of an element pair: (g.re, g.im, -g.im) as pairs
 struct GPair { float2 re, im, nim; };
@@ -79,11 +80,6 @@ __device__ __forceinline__ CPair cmul_pair(const GPair& g, const CPair& v) {
   u.re = fma2(g.re, v.re, mul2(g.nim, v.im));
   u.im = fma2(g.re, v.im, mul2(g.im, v.re));
   return u;
-}
-__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
 }
 
 // shared-memory access by 32-bit address (no generic-address arithmetic in the row loop)
@@ -110,7 +106,7 @@ __device__ __forceinline__ void sts64f(uint32_t addr, float a, float b) {
 }
 
 // C channels (power of two >= 8), strip width TW (multiple of 16, <= 128).
-template <int C, int TW>
+template <typename T, int C, int TW>
 __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const AttStreamArgs a) {
   constexpr int PW = TW + 6;                                  // strip + 3-pixel halo each side
   constexpr int VPP = C / 4;                                  // 16-byte vectors per pixel
@@ -142,7 +138,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
   const int xa = max(x0 - 3, 0), xe = min(x0 + TW + 3, W);           // image columns this strip reads
   const uint32_t seg_bytes = (uint32_t)(xe - xa) * C * 4;
   const uint32_t seg_off = (uint32_t)(xa - (x0 - 3)) * C * 4;
-  const __nv_bfloat16* xsrc = a.x + ((int64_t)b * H * W + xa) * C * 2;
+  const T* xsrc = reinterpret_cast<const T*>(a.x) + ((int64_t)b * H * W + xa) * C * 2;
   auto issue_row = [&](int r) {                                      // one thread; ring slot r & 7 (r < NR when H < 8)
     const uint32_t bar = full_u32 + 8 * (r & (kAsRing - 1));
     mbar_expect_tx(bar, seg_bytes);
@@ -154,7 +150,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
   }
   for (int i = tid; i < 4 * ST_PITCH; i += kAsThreads) st[i] = 0.f;
   for (int c = tid; c < C; c += kAsThreads)
-    avg[c] = make_float2(a.sums[((int64_t)b * C + c) * 2] * a.inv_hw, a.sums[((int64_t)b * C + c) * 2 + 1] * a.inv_hw);
+    avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
   __syncthreads();
   if (tid == 0)
     for (int r = 0; r < min(NR, H); ++r) issue_row(r);
@@ -237,7 +233,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
   for (int k = 0; k < NAPP; ++k) a_ok[k] = i0 + k * istep < TW * VPP && x0 + (i0 + k * istep) / VPP < W;
   const uint32_t a_ld = xs_u32 + 3 * C * 4 + (uint32_t)i0 * 16;          // + ring slot * ROW_BYTES + k * istep * 16
   const uint32_t a_sg = sg_u32 + (uint32_t)(i0 / VPP) * 4;               // plane re; + TW * 4 plane im; + k * (istep / VPP) * 4
-  __nv_bfloat16* yp = a.y + ((int64_t)b * H * W + x0) * C * 2 + (int64_t)i0 * 8;   // output row 0; + y_pitch per row
+  T* yp = reinterpret_cast<T*>(a.y) + ((int64_t)b * H * W + x0) * C * 2 + (int64_t)i0 * 8;   // output row 0; + y_pitch per row
   const int64_t y_pitch = (int64_t)W * C * 2;
   const float invC = 1.f / (float)C;
   // conv: this lane's B values in a statistics row (float4 index warp * 16 + g + 2 t; second pixel group + 8), gate
@@ -265,7 +261,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
 #pragma unroll
     for (int k = 0; k < VPL; ++k) {   // lanes outside the image read (valid) shared memory and are masked at the store
       CPair p01, p23;
-      unpack_pairs(lds128(s_ld + ring * ROW_BYTES + k * G * 16), p01, p23);
+      unpack_pairs<T>(lds128(s_ld + ring * ROW_BYTES + k * G * 16), p01, p23);
       const CPair u01 = cmul_pair(sgate[k][0], p01), u23 = cmul_pair(sgate[k][1], p23);
       sre = add2(sre, add2(u01.re, u23.re));
       sim = add2(sim, add2(u01.im, u23.im));
@@ -291,7 +287,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
     for (int k = 0; k < NAPP; ++k) {
       if (a_ok[k]) {
         CPair p01, p23;
-        unpack_pairs(lds128(a_ld + ring * ROW_BYTES + k * istep * 16), p01, p23);
+        unpack_pairs<T>(lds128(a_ld + ring * ROW_BYTES + k * istep * 16), p01, p23);
         float2 gsp;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gsp.x) : "r"(a_sg + gbuf + k * (istep / VPP) * 4));
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gsp.y) : "r"(a_sg + gbuf + TW * 4 + k * (istep / VPP) * 4));
@@ -300,7 +296,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
         const float2 r01 = fma2(gre, u01.re, mul2(gnim, u01.im)), i01 = fma2(gre, u01.im, mul2(gim, u01.re));
         const float2 r23 = fma2(gre, u23.re, mul2(gnim, u23.im)), i23 = fma2(gre, u23.im, mul2(gim, u23.re));
         *reinterpret_cast<uint4*>(yp + (int64_t)yo * y_pitch + (size_t)k * istep * 8) =
-            make_uint4(pack_bf16x2(r01.x, i01.x), pack_bf16x2(r01.y, i01.y), pack_bf16x2(r23.x, i23.x), pack_bf16x2(r23.y, i23.y));
+            make_uint4(pack_h2<T>(r01.x, i01.x), pack_h2<T>(r01.y, i01.y), pack_h2<T>(r23.x, i23.x), pack_h2<T>(r23.y, i23.y));
       }
     }
   };
@@ -388,30 +384,26 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
 
 using namespace dcs;
 
-template <int C, int TW>
+template <typename T, int C, int TW>
 static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s) {
   const int NR = p->h < kAsRing ? p->h : kAsRing;
   const size_t pw = TW + 6;
   const size_t smem = (size_t)NR * pw * C * 4 + 4 * (pw + 2) * 16 + (size_t)TW * 16 + (size_t)(2 * C + 16) * 8 + kAsRing * 8;
   DCS_REQUIRE(smem <= 227 * 1024, "dcs_attention_stream: strip does not fit shared memory (C=%d)", C);
   AttStreamArgs a;
-  a.x = (const __nv_bfloat16*)p->x; a.y = (__nv_bfloat16*)p->y; a.sums = p->sums; a.inv_hw = 1.f / ((float)p->h * (float)p->w);
+  a.x = p->x; a.y = p->y; a.sums = reinterpret_cast<const long long*>(p->sums); a.inv_hw = 1.f / ((float)p->h * (float)p->w);
   a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
   a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = NR;
   // (set on every call: the attribute is per device, and one process may drive several GPUs)
-  DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<C, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<T, C, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->w + TW - 1) / TW, p->batch);
-  attention_stream_kernel<C, TW><<<grid, kAsThreads, smem, s>>>(a);
+  attention_stream_kernel<T, C, TW><<<grid, kAsThreads, smem, s>>>(a);
   DCS_LAUNCHED();
   return 0;
 }
 
-extern "C" int dcs_attention_stream(const dcs_attention_params* p, void* stream) {
-  DCS_REQUIRE(p && p->x && p->y && p->sums && p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->w7, "dcs_attention_stream: null pointer");
-  DCS_REQUIRE(p->in_dtype == DCS_BF16 && p->out_dtype == DCS_BF16, "dcs_attention_stream: bf16 storage only (the fp32 mode uses dcs_spat_stats / dcs_spat_apply)");
-  DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0, "dcs_attention_stream: bad shape");
-  DCS_REQUIRE(p->reduced > 0 && p->reduced <= 16, "dcs_attention_stream: reduced must be in [1, 16]");
-  cudaStream_t s = (cudaStream_t)stream;
+template <typename T>
+static int dispatch_attention_stream(const dcs_attention_params* p, cudaStream_t s) {
   // strip width: 128 pixels (every warp owns 16) for the few-channel tensors; narrow strips where a row of C channels is
   // long (ring of 8 rows) and the tensor has few pixels (enough CTAs), or where the image itself is narrow
   const int w = p->w;
@@ -419,14 +411,24 @@ extern "C" int dcs_attention_stream(const dcs_attention_params* p, void* stream)
   auto cost = [&](int tw) { const int64_t ctas = (int64_t)((w + tw - 1) / tw) * p->batch, slots = 2 * num_sms(); return ((ctas + slots - 1) / slots) * (tw + 6); };
   const bool wide112 = cost(112) < cost(128);
   switch (p->channels) {
-    case 8: return w > 64 ? (wide112 ? launch_attention_stream<8, 112>(p, s) : launch_attention_stream<8, 128>(p, s))
-                          : w > 32 ? launch_attention_stream<8, 64>(p, s) : launch_attention_stream<8, 32>(p, s);
-    case 16: return w > 64 ? (wide112 ? launch_attention_stream<16, 112>(p, s) : launch_attention_stream<16, 128>(p, s))
-                           : w > 32 ? launch_attention_stream<16, 64>(p, s) : launch_attention_stream<16, 32>(p, s);
-    case 32: return w > 16 ? launch_attention_stream<32, 32>(p, s) : launch_attention_stream<32, 16>(p, s);
-    case 64: return w > 16 ? launch_attention_stream<64, 32>(p, s) : launch_attention_stream<64, 16>(p, s);
-    case 128: return launch_attention_stream<128, 16>(p, s);
+    case 8: return w > 64 ? (wide112 ? launch_attention_stream<T, 8, 112>(p, s) : launch_attention_stream<T, 8, 128>(p, s))
+                          : w > 32 ? launch_attention_stream<T, 8, 64>(p, s) : launch_attention_stream<T, 8, 32>(p, s);
+    case 16: return w > 64 ? (wide112 ? launch_attention_stream<T, 16, 112>(p, s) : launch_attention_stream<T, 16, 128>(p, s))
+                           : w > 32 ? launch_attention_stream<T, 16, 64>(p, s) : launch_attention_stream<T, 16, 32>(p, s);
+    case 32: return w > 16 ? launch_attention_stream<T, 32, 32>(p, s) : launch_attention_stream<T, 32, 16>(p, s);
+    case 64: return w > 16 ? launch_attention_stream<T, 64, 32>(p, s) : launch_attention_stream<T, 64, 16>(p, s);
+    case 128: return launch_attention_stream<T, 128, 16>(p, s);
     default: break;
   }
   return set_error(-1, "dcs_attention_stream: channels must be 8, 16, 32, 64 or 128 (got %d)", p->channels);
+}
+
+extern "C" int dcs_attention_stream(const dcs_attention_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->y && p->sums && p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->w7, "dcs_attention_stream: null pointer");
+  DCS_REQUIRE(is_h16(p->in_dtype) && p->out_dtype == p->in_dtype,
+              "dcs_attention_stream: 16-bit storage only, same type in and out (the fp32 mode uses dcs_spat_stats / dcs_spat_apply)");
+  DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0, "dcs_attention_stream: bad shape");
+  DCS_REQUIRE(p->reduced > 0 && p->reduced <= 16, "dcs_attention_stream: reduced must be in [1, 16]");
+  cudaStream_t s = (cudaStream_t)stream;
+  return p->in_dtype == DCS_F16 ? dispatch_attention_stream<__half>(p, s) : dispatch_attention_stream<__nv_bfloat16>(p, s);
 }

@@ -7,6 +7,7 @@
 //
 // Tile: 64 pixels x BN outputs per CTA (256 threads, 4 x BN/16 register micro-tile), K-step 16 = one 16-float
 // slice of one tap (channels-last => 64 contiguous bytes per pixel), register-prefetched double buffering.
+#include <type_traits>
 #include "common.cuh"
 
 namespace dcs {
@@ -25,8 +26,13 @@ __device__ __forceinline__ float4 load4<float>(const float* p) { return __ldg(re
 template <>
 __device__ __forceinline__ float4 load4<__nv_bfloat16>(const __nv_bfloat16* p) {
   const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
-  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.x));
-  const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r.y));
+  const float2 a = unpack_h2<__nv_bfloat16>(r.x), b = unpack_h2<__nv_bfloat16>(r.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+template <>
+__device__ __forceinline__ float4 load4<__half>(const __half* p) {
+  const uint2 r = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 a = unpack_h2<__half>(r.x), b = unpack_h2<__half>(r.y);
   return make_float4(a.x, a.y, b.x, b.y);
 }
 template <typename TIN>
@@ -35,23 +41,27 @@ template <>
 __device__ __forceinline__ float load1<float>(const float* p) { return __ldg(p); }
 template <>
 __device__ __forceinline__ float load1<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
-
-template <typename TOUT>
-__device__ __forceinline__ void store_n(TOUT* p, const float* v, int n);
 template <>
-__device__ __forceinline__ void store_n<float>(float* p, const float* v, int n) {
-  if (n == 4) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+__device__ __forceinline__ float load1<__half>(const __half* p) { return __half2float(*p); }
+
+// `vec_ok`: the destination is 4-element aligned (2*cout % 4 == 0); otherwise (odd cout) every other pixel's 4 outputs
+// straddle an alignment boundary and a vector store would fault
+template <typename TOUT>
+__device__ __forceinline__ void store_n(TOUT* p, const float* v, int n, bool vec_ok);
+template <>
+__device__ __forceinline__ void store_n<float>(float* p, const float* v, int n, bool vec_ok) {
+  if (n == 4 && vec_ok) *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
   else for (int i = 0; i < n; ++i) p[i] = v[i];
 }
-template <>
-__device__ __forceinline__ void store_n<__nv_bfloat16>(__nv_bfloat16* p, const float* v, int n) {
-  if (n == 4) {
-    uint2 r;
-    *reinterpret_cast<__nv_bfloat162*>(&r.x) = __floats2bfloat162_rn(v[0], v[1]);
-    *reinterpret_cast<__nv_bfloat162*>(&r.y) = __floats2bfloat162_rn(v[2], v[3]);
-    *reinterpret_cast<uint2*>(p) = r;
-  } else for (int i = 0; i < n; ++i) p[i] = __float2bfloat16_rn(v[i]);
+template <typename T>
+__device__ __forceinline__ void store_n_h16(T* p, const float* v, int n, bool vec_ok) {
+  if (n == 4 && vec_ok) *reinterpret_cast<uint2*>(p) = make_uint2(pack_h2<T>(v[0], v[1]), pack_h2<T>(v[2], v[3]));
+  else for (int i = 0; i < n; ++i) p[i] = from_float<T>(v[i]);
 }
+template <>
+__device__ __forceinline__ void store_n<__nv_bfloat16>(__nv_bfloat16* p, const float* v, int n, bool vec_ok) { store_n_h16(p, v, n, vec_ok); }
+template <>
+__device__ __forceinline__ void store_n<__half>(__half* p, const float* v, int n, bool vec_ok) { store_n_h16(p, v, n, vec_ok); }
 
 // VEC: 2*(c0+c1) and 2*c0 are multiples of 16 -> one K-step lies inside one tap and one source.
 template <int BN, bool VEC, typename TIN, typename TOUT>
@@ -173,19 +183,26 @@ __global__ void __launch_bounds__(kConvThreads) cconv_ffma_kernel(const dcs_ccon
       const int n = nb + jn;
       if (n < N) { v[jn] = act_apply(acc[i][jn] + (p.bias ? __ldg(p.bias + n) : 0.f), p.act); ++nvalid; }
     }
-    if (nvalid) store_n<TOUT>(dst + (((int64_t)b * p.out_h + oy) * p.out_w + ox) * N + nb, v, nvalid);
+    if (nvalid) store_n<TOUT>(dst + (((int64_t)b * p.out_h + oy) * p.out_w + ox) * N + nb, v, nvalid, (N & 3) == 0);
   }
 }
 
 template <int BN, bool VEC, typename TIN>
 static int launch_out(const dcs_cconv_params& p, const ConvGeom& g, int n_pad, dim3 grid, cudaStream_t s) {
-  if (p.out_dtype == DCS_BF16) cconv_ffma_kernel<BN, VEC, TIN, __nv_bfloat16><<<grid, kConvThreads, 0, s>>>(p, g, n_pad);
-  else cconv_ffma_kernel<BN, VEC, TIN, float><<<grid, kConvThreads, 0, s>>>(p, g, n_pad);
+  // a 16-bit input only pairs with fp32 or the same 16-bit type on the output side
+  if constexpr (!std::is_same<TIN, __half>::value) {
+    if (p.out_dtype == DCS_BF16) { cconv_ffma_kernel<BN, VEC, TIN, __nv_bfloat16><<<grid, kConvThreads, 0, s>>>(p, g, n_pad); return 0; }
+  }
+  if constexpr (!std::is_same<TIN, __nv_bfloat16>::value) {
+    if (p.out_dtype == DCS_F16) { cconv_ffma_kernel<BN, VEC, TIN, __half><<<grid, kConvThreads, 0, s>>>(p, g, n_pad); return 0; }
+  }
+  cconv_ffma_kernel<BN, VEC, TIN, float><<<grid, kConvThreads, 0, s>>>(p, g, n_pad);
   return 0;
 }
 template <int BN, bool VEC>
 static int launch_in(const dcs_cconv_params& p, const ConvGeom& g, int n_pad, dim3 grid, cudaStream_t s) {
   if (p.in_dtype == DCS_BF16) return launch_out<BN, VEC, __nv_bfloat16>(p, g, n_pad, grid, s);
+  if (p.in_dtype == DCS_F16) return launch_out<BN, VEC, __half>(p, g, n_pad, grid, s);
   return launch_out<BN, VEC, float>(p, g, n_pad, grid, s);
 }
 
@@ -198,8 +215,9 @@ int validate_conv(const dcs_cconv_params* p, const char* who) {
   DCS_REQUIRE(p->out_h % p->up_h == 0 && p->out_w % p->up_w == 0, "%s: out dims not divisible by up factors", who);
   DCS_REQUIRE(p->ntaps >= 1 && p->ntaps * p->up_h * p->up_w <= DCS_MAX_TAPS, "%s: too many taps (%d x %d phases)", who,
               p->ntaps, p->up_h * p->up_w);
-  DCS_REQUIRE(p->in_dtype == DCS_F32 || p->in_dtype == DCS_BF16, "%s: bad in_dtype", who);
-  DCS_REQUIRE(p->out_dtype == DCS_F32 || p->out_dtype == DCS_BF16, "%s: bad out_dtype", who);
+  DCS_REQUIRE(is_dtype(p->in_dtype), "%s: bad in_dtype", who);
+  DCS_REQUIRE(is_dtype(p->out_dtype), "%s: bad out_dtype", who);
+  DCS_REQUIRE(!is_h16(p->in_dtype) || !is_h16(p->out_dtype) || p->in_dtype == p->out_dtype, "%s: mixed 16-bit storage types", who);
   return 0;
 }
 

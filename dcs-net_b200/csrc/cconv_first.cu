@@ -100,7 +100,7 @@ __global__ void __launch_bounds__(kF_Threads, 2) enc0_kernel(const dcs_enc0_para
     if constexpr (sizeof(TOUT) == 2) {
       uint32_t pk[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]); pk[j] = *reinterpret_cast<uint32_t*>(&t); }
+      for (int j = 0; j < 8; ++j) pk[j] = pack_h2<TOUT>(v[2 * j], v[2 * j + 1]);
       *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
       *reinterpret_cast<uint4*>(o + 8) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
     } else {
@@ -117,13 +117,16 @@ using namespace dcs;
 extern "C" int dcs_enc0_fwd(const dcs_enc0_params* p, void* stream) {
   DCS_REQUIRE(p && p->spec && p->weight && p->bias && p->dst, "dcs_enc0_fwd: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0 && p->h % 2 == 0 && p->w % 2 == 0, "dcs_enc0_fwd: bad shape");
-  DCS_REQUIRE(p->out_dtype == DCS_F32 || p->out_dtype == DCS_BF16, "dcs_enc0_fwd: bad out_dtype");
+  DCS_REQUIRE(is_dtype(p->out_dtype), "dcs_enc0_fwd: bad out_dtype");
   dim3 grid((p->w / 2 + kF_TW - 1) / kF_TW, (p->h / 2 + kF_TH - 1) / kF_TH, p->batch);
   const size_t smem = sizeof(FirstSmem);
   cudaStream_t s = (cudaStream_t)stream;
   if (p->out_dtype == DCS_BF16) {
     DCS_CUDA(cudaFuncSetAttribute(enc0_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     enc0_kernel<__nv_bfloat16><<<grid, kF_Threads, smem, s>>>(*p);
+  } else if (p->out_dtype == DCS_F16) {
+    DCS_CUDA(cudaFuncSetAttribute(enc0_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    enc0_kernel<__half><<<grid, kF_Threads, smem, s>>>(*p);
   } else {
     DCS_CUDA(cudaFuncSetAttribute(enc0_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     enc0_kernel<float><<<grid, kF_Threads, smem, s>>>(*p);

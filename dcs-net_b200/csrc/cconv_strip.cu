@@ -29,7 +29,7 @@
 
 namespace dcs {
 
-int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_units, int h, int b, int box_units);
+int make_act_map_generic(CUtensorMap* m, const void* ptr, int f16, int row_elems, int w_units, int h, int b, int box_units);
 
 constexpr int kStripM = 128;
 // threads = warp 0 TMA + warps 1, 2 MMA issuers + kEpi epilogue warps (4, 8 or 16: kEpi / 4 warps per TMEM lane quadrant,
@@ -61,9 +61,10 @@ struct StripArgs {
   int has_src1;
   uint32_t row_bytes0, row_bytes1;
   int n_mma, act;
+  int f16;                 // operands / output are IEEE half (1) or bf16 (0)
   const float* bias;
-  __nv_bfloat16* dst;
-  float* pool;
+  __nv_bfloat16* dst;      // 16-bit storage (either type)
+  long long* pool;         // fixed-point pooled sums (common.cuh: pool_add)
   dcs_strip_tail tail;  // kTail instances only: decoder[6] + bound_cRM x2 + mask combine epilogue
   // The item table lives in the constant bank (kernel parameters) and the issue loop is fully unrolled (kNdy ring
   // rows x kIpr items per row are template parameters), so every item field is a constant-bank operand of a uniform
@@ -199,7 +200,8 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
     // for the source rows its tiles need and releases a ring row once ITS last tile that reads it has been issued
     // (rows below the first row of its next own tile); the slot's empty barrier counts both issuers.
     const int w_iss = warp - 1;
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.n_mma >> 3) << 17) | ((uint32_t)(kStripM >> 4) << 24);
+    const uint32_t fmt = a.f16 ? 0u : 1u;   // A / B format: F16 (0) or BF16 (1)
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.n_mma >> 3) << 17) | ((uint32_t)(kStripM >> 4) << 24);
     const uint64_t a_desc_c0 = umma_desc(0, a.row_bytes0), a_desc_c1 = umma_desc(0, a.row_bytes1), b_desc_c = umma_desc(0, 32);
     const uint32_t ring16 = (smem_u32(base) & 0x3FFFFu) >> 4, slot16 = a.slot_bytes >> 4, w16 = (smem_u32(w_s) & 0x3FFFFu) >> 4;
     const uint32_t bar_full0 = smem_u32(&bars->full[0]), bar_empty0 = smem_u32(&bars->empty[0]);
@@ -422,10 +424,12 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               const int c0 = ch * kChunk + 8 * s8, run = c0 >> a.run_log2, off = c0 & (run_len - 1);
               __nv_bfloat16* o = a.dst + (row0 + (int64_t)run * a.out_w) * a.n_real + off;
               uint32_t pk[4];
+              if (a.f16) {
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                pk[q] = *reinterpret_cast<uint32_t*>(&t);
+                for (int q = 0; q < 4; ++q) pk[q] = pack_f16x2(v[2 * q], v[2 * q + 1]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
               }
               *reinterpret_cast<uint4*>(o) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
             }
@@ -436,14 +440,14 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
         if constexpr (kChunk == 32) {
           const float sum = transpose_reduce32(pool_acc, lane);   // pool_acc[c] sums columns c, c + 32 kSub, ... of this warp
-          atomicAdd(a.pool + (int64_t)un.b * a.n_real + ((sub * kChunk + lane) & (a.n_real - 1)), sum);   // chunk sub of the row
+          pool_add(a.pool + (int64_t)un.b * a.n_real + ((sub * kChunk + lane) & (a.n_real - 1)), sum);   // chunk sub of the row
         } else {
 #pragma unroll
           for (int c = 0; c < kChunk; ++c) {
             float sum = pool_acc[c];
 #pragma unroll
             for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-            if (lane == 0) atomicAdd(a.pool + (int64_t)un.b * a.n_real + (c & (a.n_real - 1)), sum);
+            if (lane == 0) pool_add(a.pool + (int64_t)un.b * a.n_real + (c & (a.n_real - 1)), sum);
           }
         }
       }
@@ -471,6 +475,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
               "dcs_cconv2d_strip_fwd: the tail epilogue is decoder[6] only (cout 1, 2 phase rows x 8 pixels per strip row)");
   DCS_REQUIRE(!tail || tail->combine == DCS_COMBINE_DCS || tail->combine == DCS_COMBINE_DC, "dcs_cconv2d_strip_fwd: bad combine mode");
   DCS_REQUIRE(p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->cout > 0, "dcs_cconv2d_strip_fwd: bad shape");
+  DCS_REQUIRE(is_h16(p->dtype), "dcs_cconv2d_strip_fwd: dtype must be DCS_F16 or DCS_BF16");
   DCS_REQUIRE(p->stride_w == 1 || p->stride_w == 2, "dcs_cconv2d_strip_fwd: stride_w must be 1 or 2");
   DCS_REQUIRE(p->in_w % p->stride_w == 0, "dcs_cconv2d_strip_fwd: in_w must be a multiple of stride_w");
   DCS_REQUIRE(p->n_groups >= 1 && p->n_groups <= DCS_STRIP_MAX_GROUPS, "dcs_cconv2d_strip_fwd: bad n_groups");
@@ -514,13 +519,14 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   a.tx_bytes = (uint32_t)(p->box_units * P0 + (p->c1 ? p->box_units * P1 : 0));
   a.row_bytes0 = (uint32_t)P0; a.row_bytes1 = (uint32_t)P1;
   a.n_mma = p->n_mma; a.act = p->act;
-  a.bias = p->bias; a.dst = reinterpret_cast<__nv_bfloat16*>(p->dst); a.pool = p->pool_sums;
+  a.f16 = p->dtype == DCS_F16 ? 1 : 0;
+  a.bias = p->bias; a.dst = reinterpret_cast<__nv_bfloat16*>(p->dst); a.pool = reinterpret_cast<long long*>(p->pool_sums);
   if (tail) a.tail = *tail;
 
   CUtensorMap tmA0, tmA1;
   const int w_units = p->in_w / p->stride_w;
-  if (int e = make_act_map_generic(&tmA0, p->src0, P0 / 2, w_units, p->in_h, p->batch, p->box_units)) return e;
-  if (p->c1) { if (int e = make_act_map_generic(&tmA1, p->src1, P1 / 2, w_units, p->in_h, p->batch, p->box_units)) return e; }
+  if (int e = make_act_map_generic(&tmA0, p->src0, a.f16, P0 / 2, w_units, p->in_h, p->batch, p->box_units)) return e;
+  if (p->c1) { if (int e = make_act_map_generic(&tmA1, p->src1, a.f16, P1 / 2, w_units, p->in_h, p->batch, p->box_units)) return e; }
   else tmA1 = tmA0;
   cudaStream_t st = (cudaStream_t)stream;
 

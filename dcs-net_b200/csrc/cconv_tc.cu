@@ -38,7 +38,8 @@ struct TcArgs {
   int tiles_w, tiles_h, tiles_b, tiles_per_phase, n_tiles;
   int phases, ntaps, up_h, up_w, stride_h, stride_w;
   int C2, C2_src0, CK, ksteps, n_stages;
-  int esz;                    // operand element size: 2 = bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32)
+  int esz;                    // operand element size: 2 = fp16 / bf16 (kind::f16), 4 = fp32 read as tf32 (kind::tf32)
+  int f16;                    // 16-bit operands / outputs are IEEE half (1) or bf16 (0)
   int kb;                     // 128-byte K blocks per pipeline stage: 1, or 2 (TMA mode, n_pad <= 128: one tcgen05.mma issue costs
                               // ~55 cycles and a stage's wait / fence / descriptor / commit overhead ~300, so 8 MMAs per stage
                               // instead of 4 lift the issue-bound N <= 128 layers)
@@ -52,7 +53,7 @@ struct TcArgs {
   int8_t dy[DCS_MAX_TAPS], dx[DCS_MAX_TAPS];
   const float* bias;
   void* dst;
-  float* pool;
+  long long* pool;            // fixed-point pooled sums (common.cuh: pool_add)
   unsigned long long* dbg;    // optional per-CTA wait-cycle counters (dcs_tc_set_debug_buffer), 8 words per CTA
 };
 
@@ -178,8 +179,8 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (whole warp loops, one lane issues)
     {
-      // instruction descriptor: D=F32, A=B=BF16 (1) or TF32 (2), both K-major, N>>3 @17, M>>4 @24
-      const uint32_t fmt = a.esz == 2 ? 1u : 2u;
+      // instruction descriptor: D=F32, A=B=F16 (0) / BF16 (1) or TF32 (2), both K-major, N>>3 @17, M>>4 @24
+      const uint32_t fmt = a.esz == 2 ? (a.f16 ? 0u : 1u) : 2u;
       const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
       const uint32_t a_row_bytes = a.gather ? 128u : (uint32_t)(a.CK * a.esz);  // gathered tiles are always 128 x 128 B, SWIZZLE_128B
       // Descriptors = constant high word + (start address >> 4) in the low word; per-MMA byte offsets inside a stage
@@ -424,9 +425,12 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               // 32 rows x 64 bytes (pitch 80): a store instruction writes 8 rows x 64 contiguous bytes
               uint32_t pk[16];
 #pragma unroll
-              for (int q = 0; q < 16; ++q) {
-                __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                pk[q] = *reinterpret_cast<uint32_t*>(&t);
+              if (a.f16) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pk[q] = pack_f16x2(v[2 * q], v[2 * q + 1]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) pk[q] = pack_bf16x2(v[2 * q], v[2 * q + 1]);
               }
               const uint32_t wr = est_u32 + (uint32_t)lane * 80u;
 #pragma unroll
@@ -459,16 +463,14 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               if (n0 + nblk <= a.n_real) {
                 uint32_t pk[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                  __nv_bfloat162 t = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
-                  pk[q] = *reinterpret_cast<uint32_t*>(&t);
-                }
+                for (int q = 0; q < 16; ++q) pk[q] = pack_h2_rt(v[2 * q], v[2 * q + 1], a.f16 != 0);
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                   if (8 * q < nblk) *reinterpret_cast<uint4*>(o + 8 * q) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
               } else {
 #pragma unroll
-                for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) o[q] = __float2bfloat16_rn(v[q]);
+                for (int q = 0; q < 32; ++q)
+                  if (q < nblk && n0 + q < a.n_real) reinterpret_cast<unsigned short*>(o)[q] = (unsigned short)(pack_h2_rt(v[q], 0.f, a.f16 != 0) & 0xffffu);
               }
             }
           }
@@ -490,10 +492,10 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 }
               }
               const int bw = __shfl_sync(0xffffffffu, b, 0);
-              if (lane < nblk && bw < a.batch && n0 + lane < a.n_real) atomicAdd(a.pool + (int64_t)bw * a.n_real + n0 + lane, v[0]);
+              if (lane < nblk && bw < a.batch && n0 + lane < a.n_real) pool_add(a.pool + (int64_t)bw * a.n_real + n0 + lane, v[0]);
             } else if (valid) {
 #pragma unroll
-              for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) atomicAdd(a.pool + (int64_t)b * a.n_real + n0 + q, v[q]);
+              for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) pool_add(a.pool + (int64_t)b * a.n_real + n0 + q, v[q]);
             }
           }
         }
@@ -534,7 +536,11 @@ static CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 // activations: channels-last complex bf16 (B, H, W, C2) -> 4-D map, box (CK, TW*sx, TH*sy, NB), element strides (1,sx,sy,1)
-static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy) {
+static CUtensorMapDataType map_dtype(int esz, int f16) {
+  return esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
+}
+
+static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int f16, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -542,7 +548,7 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int C2, int W,
   cuuint32_t box[4] = {(cuuint32_t)CK, (cuuint32_t)(TW * sx), (cuuint32_t)(TH * sy), (cuuint32_t)NB};
   cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
   DCS_REQUIRE(box[1] <= 256 && box[2] <= 256, "TMA box too large (%u x %u)", box[1], box[2]);
-  CUresult r = fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = fn(m, map_dtype(esz, f16), 4, const_cast<void*>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(CK * esz), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(activations) failed with CUresult %d (C2=%d W=%d H=%d B=%d box=%d,%d,%d,%d)",
@@ -550,14 +556,14 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int C2, int W,
   return 0;
 }
 
-static int make_weight_map(CUtensorMap* m, const void* ptr, int esz, int Kpad, int rows, int n_pad) {
+static int make_weight_map(CUtensorMap* m, const void* ptr, int esz, int f16, int Kpad, int rows, int n_pad) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)Kpad * esz};
   cuuint32_t box[2] = {(cuuint32_t)(kKStepBytes / esz), (cuuint32_t)n_pad};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = fn(m, esz == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+  CUresult r = fn(m, map_dtype(esz, f16), 2, const_cast<void*>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(weights) failed with CUresult %d", (int)r);
@@ -565,7 +571,7 @@ static int make_weight_map(CUtensorMap* m, const void* ptr, int esz, int Kpad, i
 }
 
 // strips of the row-strip kernel (cconv_strip.cu): (B, H, W_units, row_elems) bf16 -> box (row_elems, box_units, 1, 1)
-int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_units, int h, int b, int box_units) {
+int make_act_map_generic(CUtensorMap* m, const void* ptr, int f16, int row_elems, int w_units, int h, int b, int box_units) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   const cuuint64_t rb = (cuuint64_t)row_elems * 2;
@@ -573,7 +579,7 @@ int make_act_map_generic(CUtensorMap* m, const void* ptr, int row_elems, int w_u
   cuuint64_t strides[3] = {rb, (cuuint64_t)w_units * rb, (cuuint64_t)h * w_units * rb};
   cuuint32_t box[4] = {(cuuint32_t)row_elems, (cuuint32_t)box_units, 1, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  CUresult r = fn(m, map_dtype(2, f16), 4, const_cast<void*>(ptr), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   swizzle_for((int)rb), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DCS_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled(strip) failed with CUresult %d (row=%d w=%d h=%d b=%d box=%d)", (int)r, row_elems,
               w_units, h, b, box_units);
@@ -597,7 +603,10 @@ using namespace dcs;
 
 extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   if (int e = validate_conv(p, "dcs_cconv2d_tc_fwd")) return e;
-  const int esz = p->in_dtype == DCS_BF16 ? 2 : 4;  // bf16 operands (kind::f16) or fp32 operands read as tf32
+  const int esz = is_h16(p->in_dtype) ? 2 : 4;  // fp16 / bf16 operands (kind::f16) or fp32 operands read as tf32
+  const int f16 = p->in_dtype == DCS_F16 ? 1 : 0;
+  DCS_REQUIRE(!is_h16(p->out_dtype) || !is_h16(p->in_dtype) || p->out_dtype == p->in_dtype,
+              "dcs_cconv2d_tc_fwd: 16-bit input and output must be the same type");
   const int kblk_elems = kKStepBytes / esz;          // elements of one 128-byte K block
   int kstep_elems = kblk_elems;
   const int C2s0 = 2 * p->c0, C2s1 = 2 * p->c1, C2 = C2s0 + C2s1;
@@ -633,6 +642,7 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   a.n_tiles = a.tiles_per_phase * a.phases;
   a.ntaps = p->ntaps; a.up_h = p->up_h; a.up_w = p->up_w; a.stride_h = p->stride_h; a.stride_w = p->stride_w;
   a.C2 = C2; a.C2_src0 = C2s0; a.CK = CK; a.esz = esz; a.gather = gather;
+  a.f16 = is_h16(p->in_dtype) ? f16 : (p->out_dtype == DCS_F16 ? 1 : 0);   // tf32 operands: the flag selects the output packing
   {
     static const bool no_kb2 = getenv("DCS_TC_NO_KB2") && atoi(getenv("DCS_TC_NO_KB2")) != 0;
     const int n_pad_ = (2 * p->cout + 15) / 16 * 16;
@@ -648,7 +658,7 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   memcpy(a.dy, p->dy, sizeof(a.dy));
   memcpy(a.dx, p->dx, sizeof(a.dx));
   DCS_REQUIRE(p->bias, "dcs_cconv2d_tc_fwd: bias is required (pass zeros)");
-  a.bias = p->bias; a.dst = p->dst; a.pool = p->pool_sums; a.dbg = g_tc_dbg;
+  a.bias = p->bias; a.dst = p->dst; a.pool = reinterpret_cast<long long*>(p->pool_sums); a.dbg = g_tc_dbg;
 
   const size_t stage_bytes = ((size_t)kTileM * kKStepBytes + (size_t)n_pad * kKStepBytes) * a.kb;
   int n_stages = (int)((200 * 1024) / stage_bytes);
@@ -658,13 +668,13 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
 
   CUtensorMap tmA0, tmA1, tmB;
   // (the packed weight matrix is padded to whole 128-byte K blocks; a half-empty last double stage reads zeros out of bounds)
-  if (int e = make_weight_map(&tmB, p->weight, esz, (K + kblk_elems - 1) / kblk_elems * kblk_elems, a.phases * n_pad, n_pad)) return e;
+  if (int e = make_weight_map(&tmB, p->weight, esz, f16, (K + kblk_elems - 1) / kblk_elems * kblk_elems, a.phases * n_pad, n_pad)) return e;
   if (gather) {
     tmA0 = tmB; tmA1 = tmB;  // unused by the kernel in gather mode (kept valid for the descriptor prefetch)
   } else {
-    if (int e = make_act_map(&tmA0, p->src0, esz, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+    if (int e = make_act_map(&tmA0, p->src0, esz, f16, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
     if (p->c1) {
-      if (int e = make_act_map(&tmA1, p->src1, esz, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+      if (int e = make_act_map(&tmA1, p->src1, esz, f16, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
     } else {
       tmA1 = tmA0;
     }

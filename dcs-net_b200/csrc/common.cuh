@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <atomic>
@@ -36,15 +37,17 @@ extern std::atomic<uint64_t> g_launches;
       return ::dcs::set_error((int)e__, "kernel launch failed: %s", cudaGetErrorString(e__)); \
   } while (0)
 
-static inline int num_sms() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+static inline int num_sms() {   // of the CURRENT device (cached per device: one process may drive several GPUs)
+  static int n[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (!n[dev]) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 // ---- element access for the two activation storage types (complex element = 2 scalars)
@@ -63,6 +66,71 @@ template <> struct Elem<__nv_bfloat16> {
     reinterpret_cast<__nv_bfloat162*>(p)[i] = __float22bfloat162_rn(v);
   }
 };
+template <> struct Elem<__half> {
+  using pair_t = __half2;
+  static __device__ __forceinline__ float2 ldc(const __half* p, int64_t i) {
+    return __half22float2(reinterpret_cast<const __half2*>(p)[i]);
+  }
+  static __device__ __forceinline__ void stc(__half* p, int64_t i, float2 v);
+};
+
+// ---- 16-bit activation storage (the tensor-core modes): DCS_F16 = IEEE half (11-bit significand, the default: every
+// stored activation is rounded once per layer, and bf16's 8 bits put the enhanced spectrogram at 3.6e-3 of its maximum on
+// the randomised-BN parity state against the 2e-3 budget; fp16 gives 4e-4) or DCS_BF16 (wide range, for checkpoints whose
+// activations exceed fp16's 65504).  fp16 stores SATURATE to +-65504 instead of producing inf.
+// pack (lo, hi) -> one 32-bit word of two 16-bit values, lo in the low half
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+template <typename T> __device__ __forceinline__ uint32_t pack_h2(float lo, float hi);
+template <> __device__ __forceinline__ uint32_t pack_h2<__nv_bfloat16>(float lo, float hi) { return pack_bf16x2(lo, hi); }
+template <> __device__ __forceinline__ uint32_t pack_h2<__half>(float lo, float hi) { return pack_f16x2(lo, hi); }
+// runtime-selected form for kernels that are not templated on the storage type (uniform branch)
+__device__ __forceinline__ uint32_t pack_h2_rt(float lo, float hi, bool f16) { return f16 ? pack_f16x2(lo, hi) : pack_bf16x2(lo, hi); }
+// unpack one 32-bit word of two 16-bit values -> (lo, hi) fp32
+template <typename T> __device__ __forceinline__ float2 unpack_h2(uint32_t w);
+template <> __device__ __forceinline__ float2 unpack_h2<__nv_bfloat16>(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+template <> __device__ __forceinline__ float2 unpack_h2<__half>(uint32_t w) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&w));
+}
+template <typename T> __device__ __forceinline__ T from_float(float v);
+template <> __device__ __forceinline__ float from_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_float<__nv_bfloat16>(float v) { return __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ __half from_float<__half>(float v) {
+  const uint32_t w = pack_f16x2(v, 0.f);
+  return __ushort_as_half((unsigned short)(w & 0xffffu));
+}
+template <typename T> __device__ __forceinline__ float to_float(T v);
+template <> __device__ __forceinline__ float to_float<float>(float v) { return v; }
+template <> __device__ __forceinline__ float to_float<__nv_bfloat16>(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <> __device__ __forceinline__ float to_float<__half>(__half v) { return __half2float(v); }
+__device__ __forceinline__ void Elem<__half>::stc(__half* p, int64_t i, float2 v) {
+  reinterpret_cast<uint32_t*>(p)[i] = pack_f16x2(v.x, v.y);
+}
+static inline bool is_h16(int dtype) { return dtype == DCS_BF16 || dtype == DCS_F16; }
+static inline bool is_dtype(int dtype) { return dtype == DCS_F32 || dtype == DCS_BF16 || dtype == DCS_F16; }
+
+// ---- pooled sums (numerators of ComplexAdaptiveAvgPool2d(1)): accumulated with 64-bit INTEGER atomics in fixed point
+// (Q35.28), so the result does not depend on the order in which CTAs / warps arrive: two runs on the same input are
+// bit-identical (float atomics made the channel gates, and through them every later layer, differ from run to run by
+// ~1e-3 of the bf16 mode's tolerance budget).  Each partial (a warp's / CTA's fp32 sum of >= 32 values, computed in a
+// fixed order) is rounded once to 2^-28 = 3.7e-9; range +-3.4e10.
+constexpr float kPoolScale = 268435456.f, kPoolInvScale = 1.f / 268435456.f;
+__device__ __forceinline__ void pool_add(long long* acc, float partial) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(acc), (unsigned long long)__float2ll_rn(partial * kPoolScale));
+}
+__device__ __forceinline__ float pool_mean(const long long* acc, int64_t i, float inv_hw) {
+  return __ll2float_rn(acc[i]) * (kPoolInvScale * inv_hw);
+}
 
 // Packed fp32x2 FMA (sm_100: FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, two IEEE fma.rn in ONE issue slot.
 // The CUDA-core kernels here are issue-bound (FFMA + LDS share the schedulers), so halving the FMA instruction count is

@@ -125,7 +125,29 @@ static inline int ew_grid(int64_t n, int threads) {
 
 using namespace dcs;
 
+// every (input, output) storage pair of the element-wise kernels
+#define DCS_DISPATCH_IO(IN, OUT, F)                                             \
+  do {                                                                          \
+    const int io__ = (IN) * 3 + (OUT);                                          \
+    switch (io__) {                                                             \
+      case DCS_F32 * 3 + DCS_F32: F(float, float); break;                       \
+      case DCS_F32 * 3 + DCS_BF16: F(float, __nv_bfloat16); break;              \
+      case DCS_F32 * 3 + DCS_F16: F(float, __half); break;                      \
+      case DCS_BF16 * 3 + DCS_F32: F(__nv_bfloat16, float); break;              \
+      case DCS_BF16 * 3 + DCS_BF16: F(__nv_bfloat16, __nv_bfloat16); break;     \
+      case DCS_BF16 * 3 + DCS_F16: F(__nv_bfloat16, __half); break;             \
+      case DCS_F16 * 3 + DCS_F32: F(__half, float); break;                      \
+      case DCS_F16 * 3 + DCS_BF16: F(__half, __nv_bfloat16); break;             \
+      default: F(__half, __half); break;                                        \
+    }                                                                           \
+  } while (0)
+
 extern "C" int dcs_abi_version(void) { return DCS_ABI_VERSION; }
+extern "C" int dcs_zero(void* dst, int64_t bytes, void* stream) {
+  DCS_REQUIRE(dst && bytes > 0, "dcs_zero: bad arguments");
+  DCS_CUDA(cudaMemsetAsync(dst, 0, (size_t)bytes, (cudaStream_t)stream));
+  return 0;
+}
 extern "C" const char* dcs_last_error_string(void) { return err_buf(); }
 extern "C" uint64_t dcs_launch_count(void) { return g_launches.load(); }
 
@@ -135,14 +157,10 @@ extern "C" int dcs_cbn_apply(const dcs_cbn_params* p, void* stream) {
   const int64_t n = p->n_pix * p->channels;
   cudaStream_t s = (cudaStream_t)stream;
   const int g = ew_grid(n, 256);
-  if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_F32)
-    cbn_kernel<float, float><<<g, 256, 0, s>>>((const float*)p->x, (float*)p->y, p->affine, n, p->channels, p->act);
-  else if (p->in_dtype == DCS_F32 && p->out_dtype == DCS_BF16)
-    cbn_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)p->x, (__nv_bfloat16*)p->y, p->affine, n, p->channels, p->act);
-  else if (p->in_dtype == DCS_BF16 && p->out_dtype == DCS_F32)
-    cbn_kernel<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)p->x, (float*)p->y, p->affine, n, p->channels, p->act);
-  else
-    cbn_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)p->x, (__nv_bfloat16*)p->y, p->affine, n, p->channels, p->act);
+  DCS_REQUIRE(is_dtype(p->in_dtype) && is_dtype(p->out_dtype), "dcs_cbn_apply: bad dtype");
+#define DCS_CBN(TI, TO) cbn_kernel<TI, TO><<<g, 256, 0, s>>>((const TI*)p->x, (TO*)p->y, p->affine, n, p->channels, p->act)
+  DCS_DISPATCH_IO(p->in_dtype, p->out_dtype, DCS_CBN);
+#undef DCS_CBN
   DCS_LAUNCHED();
   return 0;
 }
@@ -161,14 +179,10 @@ extern "C" int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_
   const int64_t n2 = n_floats / 2;
   cudaStream_t s = (cudaStream_t)stream;
   const int g = ew_grid(n2, 256);
-  if (in_dtype == DCS_F32 && out_dtype == DCS_BF16)
-    convert_kernel<float, __nv_bfloat16><<<g, 256, 0, s>>>((const float*)src, (__nv_bfloat16*)dst, n2);
-  else if (in_dtype == DCS_BF16 && out_dtype == DCS_F32)
-    convert_kernel<__nv_bfloat16, float><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (float*)dst, n2);
-  else if (in_dtype == DCS_F32 && out_dtype == DCS_F32)
-    convert_kernel<float, float><<<g, 256, 0, s>>>((const float*)src, (float*)dst, n2);
-  else
-    convert_kernel<__nv_bfloat16, __nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)src, (__nv_bfloat16*)dst, n2);
+  DCS_REQUIRE(is_dtype(in_dtype) && is_dtype(out_dtype), "dcs_convert: bad dtype");
+#define DCS_CVT(TI, TO) convert_kernel<TI, TO><<<g, 256, 0, s>>>((const TI*)src, (TO*)dst, n2)
+  DCS_DISPATCH_IO(in_dtype, out_dtype, DCS_CVT);
+#undef DCS_CVT
   DCS_LAUNCHED();
   return 0;
 }
@@ -229,7 +243,9 @@ extern "C" int dcs_upsample_nearest(const void* x, void* y, int batch, int h, in
   DCS_REQUIRE(x && y && batch > 0 && h > 0 && w > 0 && channels > 0 && up_h >= 1 && up_w >= 1, "dcs_upsample_nearest: bad arguments");
   const int64_t n = (int64_t)batch * h * up_h * w * up_w * channels;
   cudaStream_t s = (cudaStream_t)stream;
+  DCS_REQUIRE(is_dtype(dtype), "dcs_upsample_nearest: bad dtype");
   if (dtype == DCS_BF16) upsample_kernel<__nv_bfloat16><<<ew_grid(n, 256), 256, 0, s>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, batch, h, w, channels, up_h, up_w);
+  else if (dtype == DCS_F16) upsample_kernel<__half><<<ew_grid(n, 256), 256, 0, s>>>((const __half*)x, (__half*)y, batch, h, w, channels, up_h, up_w);
   else upsample_kernel<float><<<ew_grid(n, 256), 256, 0, s>>>((const float*)x, (float*)y, batch, h, w, channels, up_h, up_w);
   DCS_LAUNCHED();
   return 0;

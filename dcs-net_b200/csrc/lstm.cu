@@ -638,7 +638,9 @@ extern "C" int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream) {
   {
     const int64_t n = rows * D;
     const int g = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
+    DCS_REQUIRE(is_dtype(p->in_dtype), "dcs_clstm_fwd: bad in_dtype");
     if (p->in_dtype == DCS_BF16) lstm_deinterleave_kernel<__nv_bfloat16><<<g, 256, 0, s>>>((const __nv_bfloat16*)p->x, w.xp, rows, D);
+    else if (p->in_dtype == DCS_F16) lstm_deinterleave_kernel<__half><<<g, 256, 0, s>>>((const __half*)p->x, w.xp, rows, D);
     else lstm_deinterleave_kernel<float><<<g, 256, 0, s>>>((const float*)p->x, w.xp, rows, D);
     DCS_LAUNCHED();
   }

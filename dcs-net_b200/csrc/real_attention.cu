@@ -14,9 +14,11 @@ namespace dcs {
 template <typename T> __device__ __forceinline__ float ldr(const T* p, int64_t i);
 template <> __device__ __forceinline__ float ldr<float>(const float* p, int64_t i) { return p[i]; }
 template <> __device__ __forceinline__ float ldr<__nv_bfloat16>(const __nv_bfloat16* p, int64_t i) { return __bfloat162float(p[i]); }
+template <> __device__ __forceinline__ float ldr<__half>(const __half* p, int64_t i) { return __half2float(p[i]); }
 template <typename T> __device__ __forceinline__ void str(T* p, int64_t i, float v);
 template <> __device__ __forceinline__ void str<float>(float* p, int64_t i, float v) { p[i] = v; }
 template <> __device__ __forceinline__ void str<__nv_bfloat16>(__nv_bfloat16* p, int64_t i, float v) { p[i] = __float2bfloat16_rn(v); }
+template <> __device__ __forceinline__ void str<__half>(__half* p, int64_t i, float v) { p[i] = from_float<__half>(v); }
 
 // 1. per-(image, chunk, channel) maximum over a chunk of pixels -> scratch[b][chunk][c]
 template <typename T>
@@ -144,8 +146,10 @@ extern "C" int dcs_real_attention_fwd(const dcs_real_attention_params* p, void* 
   int n_chunks = std::min(64, std::max(1, hw / (lanes * 8)));
   const int ppc = (hw + n_chunks - 1) / n_chunks;
   n_chunks = (hw + ppc - 1) / ppc;
-  const bool bf = p->dtype == DCS_BF16;
+  DCS_REQUIRE(is_dtype(p->dtype), "dcs_real_attention_fwd: bad dtype");
+  const bool bf = p->dtype == DCS_BF16, hf = p->dtype == DCS_F16;
   if (bf) real_chan_max_kernel<__nv_bfloat16><<<dim3(n_chunks, p->batch), 256, 0, s>>>((const __nv_bfloat16*)p->x, scratch, hw, C, ppc);
+  else if (hf) real_chan_max_kernel<__half><<<dim3(n_chunks, p->batch), 256, 0, s>>>((const __half*)p->x, scratch, hw, C, ppc);
   else real_chan_max_kernel<float><<<dim3(n_chunks, p->batch), 256, 0, s>>>((const float*)p->x, scratch, hw, C, ppc);
   DCS_LAUNCHED();
   real_gate_kernel<<<p->batch, 256, 0, s>>>(scratch, p->w1, p->w2, gate, n_chunks, C, R);
@@ -153,10 +157,12 @@ extern "C" int dcs_real_attention_fwd(const dcs_real_attention_params* p, void* 
   const int G = std::min(32, C), groups = 256 / G;
   const int ctas = std::max(1, std::min((hw + groups - 1) / groups, 16 * num_sms() / p->batch + 1));
   if (bf) real_spat_stats_kernel<__nv_bfloat16><<<dim3(ctas, p->batch), 256, 0, s>>>((const __nv_bfloat16*)p->x, gate, stats, hw, C, G);
+  else if (hf) real_spat_stats_kernel<__half><<<dim3(ctas, p->batch), 256, 0, s>>>((const __half*)p->x, gate, stats, hw, C, G);
   else real_spat_stats_kernel<float><<<dim3(ctas, p->batch), 256, 0, s>>>((const float*)p->x, gate, stats, hw, C, G);
   DCS_LAUNCHED();
   const int actas = std::max(1, std::min((hw + 7) / 8, 32 * num_sms() / p->batch + 1));
   if (bf) real_spat_apply_kernel<__nv_bfloat16, __nv_bfloat16><<<dim3(actas, p->batch), 256, 0, s>>>((const __nv_bfloat16*)p->x, gate, stats, p->w7, (__nv_bfloat16*)p->y, p->h, p->w, C);
+  else if (hf) real_spat_apply_kernel<__half, __half><<<dim3(actas, p->batch), 256, 0, s>>>((const __half*)p->x, gate, stats, p->w7, (__half*)p->y, p->h, p->w, C);
   else real_spat_apply_kernel<float, float><<<dim3(actas, p->batch), 256, 0, s>>>((const float*)p->x, gate, stats, p->w7, (float*)p->y, p->h, p->w, C);
   DCS_LAUNCHED();
   return 0;

@@ -379,6 +379,10 @@ extern "C" int dcs_stft_fwd(const dcs_stft_params* p, void* stream) {
     DCS_CUDA(cudaFuncSetAttribute(stft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,
                                                             p->bn_affine, (__nv_bfloat16*)p->bn_out);
+  } else if (p->bn_out && p->bn_dtype == DCS_F16) {
+    DCS_CUDA(cudaFuncSetAttribute(stft_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    stft_kernel<__half><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,
+                                                     p->bn_affine, (__half*)p->bn_out);
   } else {
     DCS_CUDA(cudaFuncSetAttribute(stft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_kernel<float><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,

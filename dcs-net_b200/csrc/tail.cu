@@ -24,7 +24,11 @@ constexpr int kTlCi = 16;
 template <typename T> struct SmemC;
 template <> struct SmemC<__nv_bfloat16> {
   using type = uint32_t;
-  static __device__ __forceinline__ float2 get(uint32_t v) { return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u)); }
+  static __device__ __forceinline__ float2 get(uint32_t v) { return unpack_h2<__nv_bfloat16>(v); }
+};
+template <> struct SmemC<__half> {
+  using type = uint32_t;
+  static __device__ __forceinline__ float2 get(uint32_t v) { return unpack_h2<__half>(v); }
 };
 template <> struct SmemC<float> {
   using type = float2;
@@ -171,14 +175,17 @@ extern "C" int dcs_dec6_tail_fwd(const dcs_dec6_tail_params* p, void* stream) {
   DCS_REQUIRE(p && p->d && p->skip && p->weight && p->noisy_spec && p->clean_spec, "dcs_dec6_tail_fwd: null pointer");
   DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0, "dcs_dec6_tail_fwd: bad shape");
   DCS_REQUIRE(p->combine == DCS_COMBINE_DCS || p->combine == DCS_COMBINE_DC, "dcs_dec6_tail_fwd: bad combine mode");
-  DCS_REQUIRE(p->in_dtype == DCS_F32 || p->in_dtype == DCS_BF16, "dcs_dec6_tail_fwd: bad dtype");
+  DCS_REQUIRE(is_dtype(p->in_dtype), "dcs_dec6_tail_fwd: bad dtype");
   dim3 grid((p->w + kTlCols - 1) / kTlCols, (p->h + kTlRows - 1) / kTlRows, p->batch);
-  const size_t elem = p->in_dtype == DCS_BF16 ? 4 : 8;
+  const size_t elem = is_h16(p->in_dtype) ? 4 : 8;
   const size_t smem = kTlCi * 16 * sizeof(float4) + (size_t)kTlCi * (kTlRows + 2) * kTlPitch * elem;
   cudaStream_t s = (cudaStream_t)stream;
   if (p->in_dtype == DCS_BF16) {
     DCS_CUDA(cudaFuncSetAttribute(dec6_tail_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dec6_tail_kernel<__nv_bfloat16><<<grid, kTlThreads, smem, s>>>(*p);
+  } else if (p->in_dtype == DCS_F16) {
+    DCS_CUDA(cudaFuncSetAttribute(dec6_tail_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dec6_tail_kernel<__half><<<grid, kTlThreads, smem, s>>>(*p);
   } else {
     DCS_CUDA(cudaFuncSetAttribute(dec6_tail_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dec6_tail_kernel<float><<<grid, kTlThreads, smem, s>>>(*p);

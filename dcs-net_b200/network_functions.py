@@ -59,11 +59,9 @@ def _global_avg(input, output_size):
     L.require_cuda(input)
     x = to_cl(input)
     B, H, W, Cn, _ = x.shape
-    sums = torch.zeros(B, Cn, 2, dtype=torch.float32, device=x.device)
+    sums = ops.zero_(torch.empty(B, Cn, 2, dtype=torch.int64, device=x.device))
     ops.chan_pool(x, sums)
-    aff = torch.tensor([1.0 / (H * W), 0.0, 0.0, 1.0 / (H * W), 0.0, 0.0], device=x.device).repeat(Cn, 1).contiguous()
-    y = ops.cbn_apply(sums.view(B, 1, 1, Cn, 2), aff)
-    return from_cl(y)
+    return from_cl(ops.pool_mean(sums, H * W).view(B, 1, 1, Cn, 2))
 
 
 class ComplexAdaptiveAvgPool2d(torch.nn.Module):

@@ -1,14 +1,20 @@
 """Thin tensor-level wrappers over the C ABI (include/dcsnet.h).  Every function enqueues sm_100a kernels on the
 current CUDA stream and returns immediately; nothing here computes on the host or falls back to PyTorch ops.
 
-Activation tensors are channels-last complex: a float32 / bfloat16 tensor of shape (B, H, W, C, 2).
+Activation tensors are channels-last complex: a float32 / float16 / bfloat16 tensor of shape (B, H, W, C, 2).
+
+Every wrapper runs on the device of its tensor arguments (`_on_tensor_device`): the kernels are launched on that
+device's current stream whatever `torch.cuda.current_device()` is.
 """
 import ctypes as C
+import functools
 
 import torch
 
 from . import _lib as L
-from ._lib import F32, BF16, ACT_NONE, ACT_RELU, ACT_LRELU  # noqa: F401
+from ._lib import F32, BF16, F16, ACT_NONE, ACT_RELU, ACT_LRELU  # noqa: F401
+
+H16 = (torch.float16, torch.bfloat16)      # 16-bit activation storage types of the tensor-core modes
 
 N_FFT, HOP, BINS = 512, 32, 256
 
@@ -86,8 +92,9 @@ def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
     for i, (a, b) in enumerate(zip(pk.dy, pk.dx)):
         p.dy[i], p.dx[i] = a, b
     if use_tc:
-        w = pk.w_tc if src0.dtype == torch.bfloat16 else pk.w_tc32
+        w = pk.w_tc if src0.dtype in H16 else pk.w_tc32
         assert w is not None, "PackedConv was not packed for this tensor-core operand type"
+        assert src0.dtype not in H16 or w.dtype == src0.dtype, (w.dtype, src0.dtype)
     else:
         w = pk.w_ffma
     p.weight = L.ptr(w)
@@ -101,15 +108,15 @@ def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
 
 
 def cconv_strip(sp, src0, src1, dst, pool_sums=None, tail=None, out_hw=None):
-    """Row-strip tensor-core convolution (bf16) with operands `sp` (packing.StripConv / StripEnc0 / StripDec6).
+    """Row-strip tensor-core convolution (fp16 / bf16) with operands `sp` (packing.StripConv / StripEnc0 / StripDec6).
     Same tensors as cconv(); with `tail` (a _lib.StripTail, decoder[6] only) dst is None and out_hw = (OH, OW)."""
     L.require_cuda(src0)
     pk = sp.pk
     B, H, W, c0, _ = src0.shape
     c1 = 0 if src1 is None else src1.shape[3]
-    assert (c0, c1) == (sp.c0, sp.c1) and src0.dtype == torch.bfloat16
+    assert (c0, c1) == (sp.c0, sp.c1) and src0.dtype == sp.w_image.dtype and src0.dtype in H16
     if tail is None:
-        assert dst.dtype == torch.bfloat16
+        assert dst.dtype == src0.dtype
         _, OH, OW, co, _ = dst.shape
         assert co == pk.cout
     else:
@@ -130,6 +137,7 @@ def cconv_strip(sp, src0, src1, dst, pool_sums=None, tail=None, out_hw=None):
     p.bias, p.act = L.ptr(pk.bias), pk.act
     p.dst, p.pool_sums = L.ptr(dst), L.ptr(pool_sums)
     p.tail = C.pointer(tail) if tail is not None else None
+    p.dtype = _code(src0)
     L.check(L.lib().dcs_cconv2d_strip_fwd(C.byref(p), L.stream_ptr()), "dcs_cconv2d_strip_fwd")
     return dst
 
@@ -153,10 +161,35 @@ def conv_out_hw(pk, H, W):
     return (H + 2 * (pk.kh // 2) - pk.kh) // pk.stride[0] + 1, (W + 2 * (pk.kw // 2) - pk.kw) // pk.stride[1] + 1
 
 
+def zero_(t):
+    """Clear a device buffer with cudaMemsetAsync on the current stream (a memset node under graph capture)."""
+    L.require_cuda(t)
+    assert t.is_contiguous()
+    L.check(L.lib().dcs_zero(L.ptr(t), t.numel() * t.element_size(), L.stream_ptr()), "dcs_zero")
+    return t
+
+
+def pool_sums_to_float(sums):
+    """int64 fixed-point pooled sums (include/dcsnet.h: DCS_POOL_FRAC_BITS) -> float64 tensor (host-side inspection)."""
+    return sums.double() / float(1 << L.POOL_FRAC_BITS)
+
+
 def chan_pool(x, sums):
+    """sums (B, C, 2) int64 fixed point, pre-zeroed (zero_())."""
+    assert sums.dtype == torch.int64
     B, H, W, Cn, _ = x.shape
     p = L.ChanPoolParams(L.ptr(x), L.ptr(sums), B, H * W, Cn, _code(x))
     L.check(L.lib().dcs_chan_pool(C.byref(p), L.stream_ptr()), "dcs_chan_pool")
+
+
+def pool_mean(sums, hw, mean=None):
+    """int64 fixed-point pooled sums (B, C, 2) -> fp32 means (B, C, 2) = sums / hw."""
+    L.require_cuda(sums)
+    assert sums.dtype == torch.int64 and sums.is_contiguous()
+    if mean is None:
+        mean = torch.empty(sums.shape, dtype=torch.float32, device=sums.device)
+    L.check(L.lib().dcs_pool_mean(L.ptr(sums), 1.0 / hw, L.ptr(mean), sums.numel(), L.stream_ptr()), "dcs_pool_mean")
+    return mean
 
 
 def chan_gate(sums, hw, ca, gate):
@@ -196,7 +229,7 @@ def attention_fused(x, sums, ca, w7, y):
 
 
 def attention_stream(x, sums, ca, w7, y):
-    """attention_fused() as the streaming row-ring kernel (bf16 storage; TF32 tensor-core gate conv)."""
+    """attention_fused() as the streaming row-ring kernel (fp16 / bf16 storage; TF32 tensor-core gate conv)."""
     L.require_cuda(x, sums, y)
     B, H, W, Cn, _ = x.shape
     p = L.AttentionParams(L.ptr(x), L.ptr(y), L.ptr(sums), B, H, W, Cn, ca["reduced"], _code(x), _code(y),
@@ -352,3 +385,26 @@ def upsample_nearest(x, up):
     y = torch.empty(B, H * up[0], W * up[1], Cn, 2, dtype=x.dtype, device=x.device)
     L.check(L.lib().dcs_upsample_nearest(L.ptr(x), L.ptr(y), B, H, W, Cn, up[0], up[1], _code(x), L.stream_ptr()), "dcs_upsample_nearest")
     return y
+
+
+# ---------------------------------------------------------------- device guard
+def _on_tensor_device(fn):
+    """Run `fn` with the CUDA device of its first CUDA-tensor argument current: `L.stream_ptr()` and the library's
+    launches then target the tensors' device even when the caller's current device is another GPU."""
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        for a in list(args) + list(kwargs.values()):
+            if isinstance(a, torch.Tensor) and a.is_cuda:
+                if a.device.index != torch.cuda.current_device():
+                    with torch.cuda.device(a.device):
+                        return fn(*args, **kwargs)
+                break
+        return fn(*args, **kwargs)
+    return wrapper
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
+            and _name not in ("conv_out_hw", "clstm_workspace_bytes", "pool_sums_to_float"):
+        globals()[_name] = _on_tensor_device(_fn)
+del _name, _fn

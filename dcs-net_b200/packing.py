@@ -61,11 +61,24 @@ def _phase_taps(k, up):
     return out
 
 
+def _to_h16(t, dtype):
+    """float64 -> fp16 / bf16 (round to nearest even); fp16 saturates at +-65504 like the kernels' stores."""
+    if dtype == torch.float16:
+        t = t.clamp(-65504.0, 65504.0)
+    return t.to(dtype)
+
+
 class PackedConv:
     """GEMM operands of one complex convolution layer (see include/dcsnet.h: dcs_cconv_params)."""
 
     def __init__(self, w_r, w_i, b_r=None, b_i=None, bn=None, transposed=False, stride=(1, 1), up=(1, 1),
-                 act=0, device="cpu", want_bf16=False, want_tf32=False, _block=None):
+                 act=0, device="cpu", tc_dtype=None, want_tf32=False, _block=None, want_bf16=False):
+        # tc_dtype: torch.float16 / torch.bfloat16 = also pack the tcgen05 kind::f16 operand in that type (the type of the
+        # activations it multiplies); want_bf16=True is the older spelling of tc_dtype=torch.bfloat16
+        if want_bf16 and tc_dtype is None:
+            tc_dtype = torch.bfloat16
+        assert tc_dtype in (None, torch.float16, torch.bfloat16)
+        self.tc_dtype = tc_dtype
         if _block is not None:      # PackedConv.from_real: the real block weight / bias are given directly
             M, bias = _block
             cout, _, cin, _, kh, kw = M.shape
@@ -108,15 +121,15 @@ class PackedConv:
         Wp = torch.zeros(self.phases, self.ntaps, self.n_pad, C2, dtype=torch.float64)
         Wp[:, :, :N] = Wt
         self.w_ptnk = Wp                                          # [p][t][n_pad][C2] float64, CPU
-        # FFMA operand: [p][t][k][n_pad] fp32 ;  tcgen05 operand: [p][n_pad][t*C2 + k] bf16 (K contiguous)
+        # FFMA operand: [p][t][k][n_pad] fp32 ;  tcgen05 operand: [p][n_pad][t*C2 + k] fp16 / bf16 (K contiguous)
         self.w_ffma = Wp.permute(0, 1, 3, 2).contiguous().float().to(device)
         self.w_tc = None
-        if want_bf16:
+        if tc_dtype is not None:
             K = self.ntaps * C2
-            self.k_pad = (K + 63) // 64 * 64  # one pipeline stage of the tcgen05 kernel = 64 bf16 of K
+            self.k_pad = (K + 63) // 64 * 64  # one pipeline stage of the tcgen05 kernel = 64 16-bit values of K
             wt = torch.zeros(self.phases, self.n_pad, self.k_pad, dtype=torch.float64)
             wt[:, :, :K] = Wp.permute(0, 2, 1, 3).reshape(self.phases, self.n_pad, K)
-            self.w_tc = wt.to(torch.bfloat16).contiguous().to(device)
+            self.w_tc = _to_h16(wt, tc_dtype).contiguous().to(device)
         self.w_tc32 = None
         if want_tf32:
             K = self.ntaps * C2
@@ -181,8 +194,9 @@ class StripConv:
     groups      : 1, or 2 = one phase row (ph) per CTA group (halves the resident weights and the ring depth).
     """
 
-    def __init__(self, pk, c0, c1, merged=True, groups=1, device="cpu"):
+    def __init__(self, pk, c0, c1, merged=True, groups=1, device="cpu", dtype=None):
         assert c0 + c1 == pk.cin
+        dtype = dtype or pk.tc_dtype or torch.bfloat16
         uh, uw = pk.up
         sh, sw = pk.stride
         N = 2 * pk.cout
@@ -264,7 +278,7 @@ class StripConv:
             blocks.append(g_blocks)
         self.items = items
         self.item_table = _strip_item_table(items)
-        self.w_image = _strip_weight_image(self.groups, blocks, self.n_mma, w_off).to(device)
+        self.w_image = _strip_weight_image(self.groups, blocks, self.n_mma, w_off, dtype).to(device)
         self.smem_weight_bytes = max(g["w_bytes"] for g in self.groups)
 
 
@@ -278,17 +292,17 @@ def _strip_item_table(items):
     return tab.to(torch.int32).contiguous()
 
 
-def _strip_weight_image(groups, blocks, n_mma, total_bytes):
-    """Per group, blocks of [n_mma][16] bf16 as rows of 32 bytes with the SWIZZLE_32B pattern (the 16-byte halves of a row
+def _strip_weight_image(groups, blocks, n_mma, total_bytes, dtype=torch.bfloat16):
+    """Per group, blocks of [n_mma][16] fp16 / bf16 as rows of 32 bytes with the SWIZZLE_32B pattern (the 16-byte halves of a row
     swap when bit 7 of the byte offset is set): the exact shared-memory image, bulk-copied by the kernel."""
-    img = torch.zeros(total_bytes // 2, dtype=torch.bfloat16)
+    img = torch.zeros(total_bytes // 2, dtype=dtype)
     n = torch.arange(n_mma)[:, None]
     k = torch.arange(16)[None, :]
     off = n * 32 + k * 2
     off = off ^ (((off >> 7) & 1) << 4)
     for g, g_blocks in zip(groups, blocks):
         for bi, blk in enumerate(g_blocks):
-            img[(g["w_off"] + bi * n_mma * 32 + off) // 2] = blk.to(torch.bfloat16)
+            img[(g["w_off"] + bi * n_mma * 32 + off) // 2] = _to_h16(blk, dtype)
     return img.contiguous()
 
 
@@ -302,8 +316,9 @@ class StripEnc0:
     1024 output pixels.  The kernel is told a reinterpreted geometry: source (B, F, T/8, 8 "channels"), stride_w 2
     (a strip row = 2 such pixels), up_w = 8 (8 output pixels per strip row), cout 8."""
 
-    def __init__(self, pk, device="cpu"):
+    def __init__(self, pk, device="cpu", dtype=None):
         assert (pk.cin, pk.cout, pk.kh, pk.kw, tuple(pk.stride), tuple(pk.up)) == (1, 8, 7, 7, (2, 2), (1, 1))
+        dtype = dtype or pk.tc_dtype or torch.bfloat16
         self.pk, self.c0, self.c1 = pk, 8, 0
         self.up, self.stride = (1, 8), (2, 2)
         N = 16
@@ -328,7 +343,7 @@ class StripEnc0:
                             w_bytes=w_bytes, w_off=0)]
         self.items = items
         self.item_table = _strip_item_table(items)
-        self.w_image = _strip_weight_image(self.groups, [blocks], self.n_mma, w_bytes).to(device)
+        self.w_image = _strip_weight_image(self.groups, [blocks], self.n_mma, w_bytes, dtype).to(device)
         self.smem_weight_bytes = w_bytes
 
     @staticmethod
@@ -347,8 +362,9 @@ class StripDec6:
     multiplies by a Toeplitz block with the pre-summed taps dx = q - j.  6 offsets x 2 sources x 3 rows = 36 MMAs
     (N = 32) per 512 source pixels.  Kernel geometry: sources viewed as (B, H, W/4, 32 "channels"), up = (2, 8)."""
 
-    def __init__(self, pk, device="cpu"):
+    def __init__(self, pk, device="cpu", dtype=None):
         assert (pk.cin, pk.cout, tuple(pk.up), tuple(pk.stride)) == (16, 1, (2, 2), (1, 1))
+        dtype = dtype or pk.tc_dtype or torch.bfloat16
         self.pk, self.c0, self.c1 = pk, 32, 32
         self.up, self.stride = (2, 8), (1, 1)
         Wp, T = pk.w_ptnk, pk.ntaps                       # [4 phases][4 taps][n_pad][32]
@@ -377,7 +393,7 @@ class StripDec6:
                             w_bytes=w_bytes, w_off=0)]
         self.items = items
         self.item_table = _strip_item_table(items)
-        self.w_image = _strip_weight_image(self.groups, [blocks], 32, w_bytes).to(device)
+        self.w_image = _strip_weight_image(self.groups, [blocks], 32, w_bytes, dtype).to(device)
         self.smem_weight_bytes = w_bytes
 
     @staticmethod
@@ -453,7 +469,10 @@ class PackedRNet:
     STRIDE_E = [(2, 2), (2, 2), (2, 2), (2, 1), (2, 1), (2, 1), (2, 1)]
     UPSAMPLE = [(2, 1), (2, 1), (2, 1), (2, 1), (2, 2), (2, 2), (2, 2)]
 
-    def __init__(self, model_or_sd, device="cpu", no_of_layers=7, want_bf16=False):
+    def __init__(self, model_or_sd, device="cpu", no_of_layers=7, want_bf16=False, tc_dtype=None):
+        if want_bf16 and tc_dtype is None:
+            tc_dtype = torch.bfloat16
+        self.tc_dtype = tc_dtype
         sd = model_or_sd.state_dict() if hasattr(model_or_sd, "state_dict") else model_or_sd
         sd = {k: v.detach() for k, v in sd.items()}
         Lr = self.L = no_of_layers
@@ -465,17 +484,17 @@ class PackedRNet:
         for i in range(Lr):
             p = f"encoder.{i}."
             self.enc.append(packed_conv_from_real(sd[p + "0.weight"], sd[p + "0.bias"], bn=bn(p + "1."), stride=self.STRIDE_E[i],
-                                                  act=1, device=device, want_bf16=want_bf16))
+                                                  act=1, device=device, tc_dtype=tc_dtype))
         for i in range(Lr):
             last = i == Lr - 1
             p = f"decoder.{i}." if last else f"decoder.{i}.0."
             self.dec.append(packed_conv_from_real(sd[p + "weight"], sd[p + "bias"], bn=None if last else bn(f"decoder.{i}.1."),
                                                   transposed=True, up=self.UPSAMPLE[i], act=3 if last else 2, device=device,   # last: torch.sigmoid (r_network.py:172)
-                                                  want_bf16=want_bf16))
+                                                  tc_dtype=tc_dtype))
             self.skip_att.append((att(f"skip_attention.{2 * i}."), sd[f"skip_attention.{2 * i + 1}.conv1.weight"].float().reshape(2, 49).contiguous().to(device)))
             if not last:
                 self.dec_att.append((att(f"decoder_attention.{2 * i}."), sd[f"decoder_attention.{2 * i + 1}.conv1.weight"].float().reshape(2, 49).contiguous().to(device)))
-        self.fc = packed_conv_from_real(sd["fc.weight"][:, :, None, None], sd["fc.bias"], device=device, want_bf16=want_bf16)
+        self.fc = packed_conv_from_real(sd["fc.weight"][:, :, None, None], sd["fc.bias"], device=device, tc_dtype=tc_dtype)
         # nn.LSTM(256 -> 128, 2 layers, bidirectional): [layer][dir] -> (w_ih (4H, in), w_hh (4H, H), b_ih + b_hh)
         self.lstm = []
         for layer in range(2):

@@ -47,7 +47,7 @@ def split_windows(audio_1d, window):
 class Enhancer:
     """Fixed-shape enhancer: `batch` windows of `n_samples` samples per call."""
 
-    def __init__(self, model_or_sd, batch, n_samples=WINDOW_4S, mode="bf16", variant="dcs", device=None, graph=True,
+    def __init__(self, model_or_sd, batch, n_samples=WINDOW_4S, mode="fp16", variant="dcs", device=None, graph=True,
                  atan2_eps=10e-7, exact_polar=False):
         if not torch.cuda.is_available():
             raise RuntimeError("dcsnet_b200.Enhancer needs a CUDA device (sm_100a); there is no CPU fallback")
@@ -71,10 +71,12 @@ class Enhancer:
         return self.plan.enhance_audio(audio_dev)
 
     def enhance_pinned(self):
-        """host_in (pinned) -> H2D -> graph -> D2H -> host_out (pinned).  Asynchronous on the current stream."""
-        self.plan.audio_in.copy_(self.host_in, non_blocking=True)
-        self.plan.enhance_audio()
-        self.host_out.copy_(self.plan.audio_out, non_blocking=True)
+        """host_in (pinned) -> H2D -> graph -> D2H -> host_out (pinned).  Asynchronous on the current stream of the
+        enhancer's device."""
+        with torch.cuda.device(self.device):
+            self.plan.audio_in.copy_(self.host_in, non_blocking=True)
+            self.plan.enhance_audio()
+            self.host_out.copy_(self.plan.audio_out, non_blocking=True)
         return self.host_out
 
     # ------------------------------------------------------------------ streaming (copy / compute overlap)
@@ -98,6 +100,10 @@ class Enhancer:
         """Streaming variant of enhance_pinned(): the H2D copy of this call and the D2H copy of the previous one run on
         their own streams through double-buffered device staging, so in steady state a step costs max(compute, copies).
         host_in is read asynchronously and host_out holds the result of this call only after drain()."""
+        with torch.cuda.device(self.device):
+            return self._enhance_pinned_stream()
+
+    def _enhance_pinned_stream(self):
         st = self._streaming()
         k = st["i"] & 1
         st["i"] += 1
@@ -122,7 +128,7 @@ class Enhancer:
     def drain(self):
         """Make the current stream wait for every copy issued by enhance_pinned_stream()."""
         if self._stream_state is not None:
-            cur = torch.cuda.current_stream()
+            cur = torch.cuda.current_stream(self.device)
             for k in range(2):   # waiting on a never-recorded event is a no-op
                 cur.wait_event(self._stream_state["out_free"][k])
                 cur.wait_event(self._stream_state["in_ready"][k])

@@ -15,7 +15,7 @@
  *     message via dcs_last_error_string() (thread-local).  There is no CPU fallback.
  *   - activation tensors are "channels-last complex": (B, H, W, C, 2) with the (re, im) pair innermost, which
  *     is the memory of a torch complex64 NCHW tensor in torch.channels_last format (dtype DCS_F32) or its
- *     bf16 twin (dtype DCS_BF16, used by the tcgen05 tensor-core mode).
+ *     16-bit twin (dtype DCS_F16 or DCS_BF16, used by the tcgen05 tensor-core modes).
  *   - spectrograms at the boundary use the reference layout (B, F=256, T) complex64, T contiguous.
  */
 #ifndef DCSNET_H_
@@ -27,9 +27,14 @@
 extern "C" {
 #endif
 
-#define DCS_ABI_VERSION 1
+#define DCS_ABI_VERSION 2
 
-enum { DCS_F32 = 0, DCS_BF16 = 1 };
+/* activation storage types.  The tensor-core modes store activations in 16 bits: DCS_F16 (IEEE half, 11-bit significand;
+ * the default — stores saturate at +-65504) or DCS_BF16 (8-bit significand, fp32 range).  kind::f16 MMAs take either. */
+enum { DCS_F32 = 0, DCS_BF16 = 1, DCS_F16 = 2 };
+/* Pooled sums (numerators of ComplexAdaptiveAvgPool2d(1): `pool_sums`, `sums`) are 64-bit fixed point, value * 2^28,
+ * accumulated with integer atomics so that results are bit-identical from run to run. */
+#define DCS_POOL_FRAC_BITS 28
 enum { DCS_ACT_NONE = 0, DCS_ACT_RELU = 1, DCS_ACT_LRELU = 2, DCS_ACT_SIGMOID = 3 }; /* ComplexReLU / ComplexLReLU(0.01) / ComplexSigmoid */
 enum { DCS_COMBINE_DCS = 0, DCS_COMBINE_DC = 1 };                /* S = Y - Y*M   |   S = Y*M */
 
@@ -100,10 +105,11 @@ int dcs_cbn_apply(const dcs_cbn_params* p, void* stream);
  *      (j, i) in [0,out_h/up_h) x [0,out_w/up_w); tap t of phase p reads source pixel
  *      (j*stride_h + dy[p*ntaps+t], i*stride_w + dx[p*ntaps+t]), zero outside [0,in_h) x [0,in_w).
  *      weight: FFMA path  fp32 [phases][ntaps][2*(c0+c1)][2*cout]   (N contiguous)
- *              tcgen05    bf16 (in_dtype BF16, kind::f16) or fp32 pre-rounded to tf32 (in_dtype F32, kind::tf32)
+ *              tcgen05    fp16 / bf16 (in_dtype F16 / BF16, kind::f16; same type as the activations) or fp32 pre-rounded
+ *                         to tf32 (in_dtype F32, kind::tf32)
  *                         [phases][n_pad][K padded to 128 bytes]     (K contiguous), n_pad = max(16, 2*cout)
  *      bias:   fp32 [2*cout] added before `act`.
- *      pool_sums (optional, fp32 [B][2*cout], pre-zeroed): per-(b, channel) sums of the epilogue output, i.e. the
+ *      pool_sums (optional, int64 fixed point [B][2*cout], pre-zeroed): per-(b, channel) sums of the epilogue output, i.e. the
  *      numerator of ComplexAdaptiveAvgPool2d(1) for the channel attention that follows (c_network.py:219). */
 typedef struct {
   const void* src0; const void* src1; int c0; int c1;
@@ -113,10 +119,10 @@ typedef struct {
   int ntaps; int8_t dy[DCS_MAX_TAPS]; int8_t dx[DCS_MAX_TAPS];
   const void* weight; const float* bias; int act;
   void* dst; int in_dtype; int out_dtype;
-  float* pool_sums;
+  int64_t* pool_sums;
 } dcs_cconv_params;
 int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream);    /* fp32 CUDA-core path (<=1e-5 mode) */
-int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (bf16 mode)  */
+int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (fp16 / bf16 / tf32) */
 
 /* ---- a4 / a12 / a11 (few-channel layers: encoder[0..2], decoder[4..6]): "row-strip" tensor-core convolution.
  *      Same math and reference call sites as dcs_cconv2d_tc_fwd (c_network.py:107-112, 135-147, 214-216); different
@@ -134,7 +140,8 @@ int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM
  *        drow     ring row relative to the first source row of the output row: source row = j*stride_h + dy_min + drow
  *        flags    bit 0: first MMA into its accumulator columns (overwrite), bit 1: reads src1
  *      Phase groups: group g owns output phase rows ph0 .. ph0+n_ph-1 of every up_h block and is served by its own
- *      CTAs (weights of one group resident per CTA).  bf16 in / bf16 out only. */
+ *      CTAs (weights of one group resident per CTA).  16-bit storage only: `dtype` (DCS_F16 / DCS_BF16) is the type of
+ *      src0 / src1 / weights / dst. */
 #define DCS_STRIP_MAX_GROUPS 2
 typedef struct { uint32_t a_off16; uint32_t b_off16; uint16_t d_col; uint8_t drow; uint8_t flags; uint32_t reserved; /* caller: 0; the library writes the item's A-descriptor high word into its own copy */ } dcs_strip_item;
 typedef struct { int item0; int n_items; int dy_min; int n_dy; int ph0; int n_ph; int x_min; int w_bytes; int64_t w_off; } dcs_strip_group;
@@ -155,8 +162,9 @@ typedef struct {
   const void* weights;
   int box_units; int n_mma; int cols;
   const float* bias; int act;
-  void* dst; float* pool_sums;
-  const dcs_strip_tail* tail;   /* NULL: bias + activation + bf16 store epilogue */
+  void* dst; int64_t* pool_sums;
+  const dcs_strip_tail* tail;   /* NULL: bias + activation + 16-bit store epilogue */
+  int dtype;                    /* DCS_F16 or DCS_BF16 */
 } dcs_cstrip_params;
 int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream);
 
@@ -165,10 +173,13 @@ int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream);
  *      dcs_chan_pool: sums[b][c] (complex) = sum over H*W of x (channels-last).  sums must be pre-zeroed.
  *      dcs_chan_gate: gate[b][c] = sigmoid_c( 2 * W2 * crelu( W1 * (sums/hw) ) ), W1: (Cr,C) W2: (C,Cr) complex,
  *      given as separate real/imag fp32 matrices (the conv_r / conv_i 1x1 weights, no bias). */
-typedef struct { const void* x; float* sums; int batch; int hw; int channels; int dtype; } dcs_chan_pool_params;
+typedef struct { const void* x; int64_t* sums; int batch; int hw; int channels; int dtype; } dcs_chan_pool_params;
 int dcs_chan_pool(const dcs_chan_pool_params* p, void* stream);
+/* mean[i] = sums[i] * 2^-DCS_POOL_FRAC_BITS * inv_hw  (n scalars): the pooled means themselves, i.e. ComplexAdaptiveAvgPool2d(1)
+ * / ComplexAdaptiveMaxPool2d(1) called on their own (network_functions.py:114-138) */
+int dcs_pool_mean(const int64_t* sums, float inv_hw, float* mean, int64_t n, void* stream);
 typedef struct {
-  const float* sums; float inv_hw; float* gate; int batch; int channels; int reduced;
+  const int64_t* sums; float inv_hw; float* gate; int batch; int channels; int reduced;
   const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i;
 } dcs_chan_gate_params;
 int dcs_chan_gate(const dcs_chan_gate_params* p, void* stream);
@@ -182,7 +193,7 @@ typedef struct {
   const void* x; const float* chan_gate; float* stats; int batch; int h; int w; int channels; int dtype;
   /* optional fused dcs_chan_gate: when sums != NULL the kernel computes the channel gate itself from the pooled sums
    * (sum over H*W of x) and the fc weights, ignores chan_gate, and writes the gate to gate_out (B, C) complex. */
-  const float* sums; int reduced; const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; float* gate_out;
+  const int64_t* sums; int reduced; const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; float* gate_out;
 } dcs_spat_stats_params;
 int dcs_spat_stats(const dcs_spat_stats_params* p, void* stream);
 typedef struct {
@@ -197,14 +208,14 @@ int dcs_spat_apply(const dcs_spat_apply_params* p, void* stream);
  *      epilogue's pool_sums), then per pixel tile: x tile + halo -> shared memory, statistics of dcs_spat_stats, the 7x7
  *      gate conv of dcs_spat_apply, and the product.  x is read once, y written once. */
 typedef struct {
-  const void* x; void* y; const float* sums;
+  const void* x; void* y; const int64_t* sums;
   int batch; int h; int w; int channels; int reduced; int in_dtype; int out_dtype;
   const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; const float* w7;
 } dcs_attention_params;
 int dcs_attention_fused(const dcs_attention_params* p, void* stream);
-/* Same contract, bf16 storage only (tensor-core mode): streaming row-ring form — x read once by bulk copies, the 7x7 gate
+/* Same contract, 16-bit storage only (tensor-core modes; in_dtype == out_dtype): streaming row-ring form — x read once by bulk copies, the 7x7 gate
  * conv (c_network.py:74,79-83) as mma.sync TF32 row-partials with a register ring of pending output rows, y written
- * once.  Replaces dcs_spat_stats + dcs_spat_apply on the bf16 path (csrc/attention_stream.cu). */
+ * once.  Replaces dcs_spat_stats + dcs_spat_apply on the tensor-core path (csrc/attention_stream.cu). */
 int dcs_attention_stream(const dcs_attention_params* p, void* stream);
 
 /* ---- f1 (real path): RealChannelAttention + RealSpatialAttention (r_network.py:8-40; applied at
@@ -307,8 +318,11 @@ int dcs_upsample_nearest(const void* x, void* y, int batch, int h, int w, int ch
 /* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */
 int dcs_tc_set_debug_buffer(void* dev_ptr);
 
-/* ---- layout helpers for the layer-wise drop-in modules: fp32 <-> bf16 copies of channels-last activations */
+/* ---- layout helpers for the layer-wise drop-in modules: fp32 <-> fp16 / bf16 copies of channels-last activations */
 int dcs_convert(const void* src, void* dst, int64_t n_floats, int in_dtype, int out_dtype, void* stream);
+/* zero `bytes` bytes of device memory on `stream` (cudaMemsetAsync: a memset node when captured, not a kernel): the
+ * per-step clear of the pooled-sum accumulators */
+int dcs_zero(void* dst, int64_t bytes, void* stream);
 
 #ifdef __cplusplus
 }

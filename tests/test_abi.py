@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.lib()  # raises if the .so is missing or a symbol is absent: no fallback
     for name in header_symbols():
         assert hasattr(lib, name), name
-    assert lib.dcs_abi_version() == 1
+    assert lib.dcs_abi_version() == 2
 
 
 def test_exports_are_plain_c():

@@ -6,7 +6,7 @@ import dcsnet_b200 as D
 import bench
 B, T = int(os.environ.get("PROF_B", 64)), int(os.environ.get("PROF_T", 2000))
 sd = bench.make_weights()
-plan = D.ForwardPlan(D.PackedNet(sd, "cuda", os.environ.get("PROF_MODE", "bf16")), B, T, want_aux=False)
+plan = D.ForwardPlan(D.PackedNet(sd, "cuda", os.environ.get("PROF_MODE", "fp16")), B, T, want_aux=False)
 g = torch.Generator().manual_seed(0)
 plan.audio_in.copy_(0.1 * torch.randn(B, 32 * (T - 1), generator=g))
 for _ in range(2):
