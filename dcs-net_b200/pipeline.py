@@ -96,21 +96,23 @@ class Enhancer:
             self._stream_state = st
         return self._stream_state
 
-    def enhance_pinned_stream(self):
+    def enhance_pinned_stream(self, src=None, dst=None):
         """Streaming variant of enhance_pinned(): the H2D copy of this call and the D2H copy of the previous one run on
         their own streams through double-buffered device staging, so in steady state a step costs max(compute, copies).
-        host_in is read asynchronously and host_out holds the result of this call only after drain()."""
+        `src` / `dst`: pinned host tensors of n <= batch windows (default host_in / host_out).  The host buffers are read /
+        written asynchronously: `dst` holds the result of this call only after drain()."""
         with torch.cuda.device(self.device):
-            return self._enhance_pinned_stream()
+            return self._enhance_pinned_stream(self.host_in if src is None else src, self.host_out if dst is None else dst)
 
-    def _enhance_pinned_stream(self):
+    def _enhance_pinned_stream(self, src, dst):
         st = self._streaming()
         k = st["i"] & 1
         st["i"] += 1
+        n = src.shape[0]
         cur = torch.cuda.current_stream()
         with torch.cuda.stream(st["h2d"]):
             st["h2d"].wait_event(st["in_free"][k])              # the step that last read this staging buffer has consumed it
-            st["dev_in"][k].copy_(self.host_in, non_blocking=True)
+            st["dev_in"][k][:n].copy_(src, non_blocking=True)
             st["in_ready"][k].record(st["h2d"])
         cur.wait_event(st["in_ready"][k])
         self.plan.audio_in.copy_(st["dev_in"][k], non_blocking=True)
@@ -121,9 +123,9 @@ class Enhancer:
         st["out_ready"][k].record(cur)
         with torch.cuda.stream(st["d2h"]):
             st["d2h"].wait_event(st["out_ready"][k])
-            self.host_out.copy_(st["dev_out"][k], non_blocking=True)
+            dst.copy_(st["dev_out"][k][:dst.shape[0]], non_blocking=True)
             st["out_free"][k].record(st["d2h"])
-        return self.host_out
+        return dst
 
     def drain(self):
         """Make the current stream wait for every copy issued by enhance_pinned_stream()."""
@@ -151,8 +153,28 @@ class Enhancer:
             torch.cuda.current_stream().synchronize()
             return self.host_out[:n].clone()
 
+    def enhance_windows_stream(self, windows_host, out_host=None):
+        """Long-form path: (n_windows, n_samples) PINNED host windows -> enhanced windows in `out_host` (pinned; allocated if
+        None), `batch` windows per step through enhance_pinned_stream(): every step's H2D and D2H copies overlap the
+        neighbouring steps' compute, nothing synchronises between steps.  Asynchronous: call drain() + a stream sync before
+        reading `out_host`.  A short last step reuses the stale tail rows of the staging buffer (windows are independent
+        and those outputs are not copied back)."""
+        n = windows_host.shape[0]
+        assert windows_host.shape[1] == self.n_samples and windows_host.dtype == torch.float32
+        if out_host is None:
+            out_host = torch.empty(n, self.n_samples, dtype=torch.float32, pin_memory=True)
+        with torch.cuda.device(self.device):
+            for i in range(0, n, self.batch):
+                self._enhance_pinned_stream(windows_host[i:i + self.batch], out_host[i:i + self.batch])
+        return out_host
+
     def enhance_long(self, audio_1d):
-        """Arbitrary-length 1-D waveform -> enhanced waveform of the same length (independent windows, in order)."""
+        """Arbitrary-length 1-D waveform -> enhanced waveform of the same length (independent windows, in order), streamed
+        through enhance_windows_stream()."""
         wins, n = split_windows(audio_1d.detach().float().cpu(), self.n_samples)
-        outs = [self(wins[i:i + self.batch]) for i in range(0, wins.shape[0], self.batch)]
-        return torch.cat(outs, 0).reshape(-1)[:n]
+        wins = wins.pin_memory()
+        with torch.cuda.device(self.device):
+            out = self.enhance_windows_stream(wins)
+            self.drain()
+            torch.cuda.current_stream().synchronize()
+        return out.reshape(-1)[:n].clone()

@@ -192,3 +192,66 @@ def test_two_rank_gradient_all_reduce_and_clip_with_gloo():
     # last decoder stage first (decoder_attention.12 / 13 are constructed but unused by forward, c_network.py:218), input BN last
     assert r["first"].split(".")[0] in ("decoder", "decoder_attention") and r["last"].startswith("initial_batchnorm.")
     assert r["err"] <= 1e-6 and r["norm"] > 100.0 and abs(r["norm"] - r["ref_norm"]) <= 1e-3 * r["ref_norm"] and r["cerr"] <= 1e-6
+
+
+def test_hparams_shim_behaves_like_attribute_dict():
+    """Lightning's AttributeDict contract the reference relies on: attribute access, AttributeError (not KeyError) for a
+    missing name — so hasattr, getattr-with-default, copy.deepcopy and torch.save(model) work."""
+    import copy
+    import io
+    net = build_product_net()
+    hp = net.hparams
+    assert hp.no_of_layers == hp["no_of_layers"] == 7
+    assert not hasattr(hp, "no_such_key") and getattr(hp, "no_such_key", 5) == 5
+    twin = copy.deepcopy(net)
+    assert twin.hparams == net.hparams and twin.hparams is not net.hparams
+    for (k, a), (_, b) in zip(net.state_dict().items(), twin.state_dict().items()):
+        assert torch.equal(a, b), k
+    buf = io.BytesIO()
+    torch.save(net, buf)
+
+
+def test_non_default_geometry_is_refused():
+    """A model whose config / BN eps differ from the geometry the kernel plan is built for must not be computed
+    silently with the default tables."""
+    import copy
+    net = build_product_net()
+    bad = copy.deepcopy(net)
+    bad.config = copy.copy(net.config)
+    bad.config.strideE = [(2, 2)] * 7
+    with pytest.raises(NotImplementedError, match="strideE"):
+        D.PackedNet(bad, "cpu", "fp32")
+    bad2 = copy.deepcopy(net)
+    bad2.encoder[0][1].eps = 1e-3
+    with pytest.raises(NotImplementedError, match="eps"):
+        D.PackedNet(bad2, "cpu", "fp32")
+
+
+@pytest.mark.parametrize("mode,dtype", [("fp16", torch.float16), ("bf16", torch.bfloat16), ("tc", torch.float16)])
+def test_tensor_core_modes_pack_in_their_storage_type(mode, dtype):
+    pk = D.PackedNet(build_product_net(), "cpu", mode)
+    assert pk.tc and pk.act_dtype == dtype
+    assert all(p.w_tc.dtype == dtype for p in pk.enc + pk.dec)
+    assert all(s.w_image.dtype == dtype for s in pk.strip.values())
+    assert pk.fc.w_tc32 is not None and pk.fc.w_tc32.dtype == torch.float32
+
+
+@pytest.mark.gpu
+def test_ops_run_on_the_tensors_device_not_the_current_one():
+    """a plan / tensors on cuda:1 while the current device is cuda:0 must launch on cuda:1's stream."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from dcsnet_b200 import ops
+    from oracle import dcsnet_oracle as O, synthetic_weights as SW
+    torch.cuda.set_device(0)
+    _, _, noisy = O.synthetic_audio(2, 32 * 63)
+    want = O.stft(noisy)
+    got = ops.stft(noisy.to("cuda:1"))
+    assert got.device.index == 1 and float((got.cpu() - want).abs().max()) < 1e-5
+    sd = SW.make_state_dict(0)
+    enh = D.Enhancer(sd, batch=2, n_samples=32 * 63, mode="fp16", device="cuda:1")
+    assert torch.cuda.current_device() == 0
+    out = enh(noisy)
+    ref = O.enhance_audio(sd, noisy)["clean_audio"]
+    assert float((out - ref).abs().max() / ref.abs().max()) <= 2e-3
+    assert torch.cuda.current_device() == 0
