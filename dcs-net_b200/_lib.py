@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(HERE, "libdcsnet_sm100a.so")
 F32, BF16, F16 = 0, 1, 2
 POOL_FRAC_BITS = 28           # pooled sums are int64 fixed point (include/dcsnet.h: DCS_POOL_FRAC_BITS)
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
-COMBINE_DCS, COMBINE_DC = 0, 1
+COMBINE_DCS, COMBINE_DC, COMBINE_DR, COMBINE_DRS = 0, 1, 2, 3
 MAX_TAPS = 64
 
 _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
@@ -23,7 +23,7 @@ _vp, _i, _f, _i64 = C.c_void_p, C.c_int, C.c_float, C.c_int64
 
 class StftParams(C.Structure):
     _fields_ = [("audio", _vp), ("spec", _vp), ("batch", _i), ("length", _i), ("n_frames", _i),
-                ("bn_affine", _vp), ("bn_out", _vp), ("bn_dtype", _i)]
+                ("bn_affine", _vp), ("bn_out", _vp), ("bn_dtype", _i), ("bn_real", _i)]
 
 
 class FrontendParams(C.Structure):
@@ -40,6 +40,11 @@ class RealAttentionParams(C.Structure):
 class RlstmParams(C.Structure):
     _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("in_dtype", _i),
                 ("w_ih0_t", _vp), ("w_ih1_t", _vp), ("w_hh_t", _vp), ("bias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
+class RlstmTcParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("batch", _i), ("seq", _i), ("in_dim", _i), ("hidden", _i), ("dtype", _i),
+                ("w_ih0", _vp), ("w_ih1", _vp), ("w_hh", _vp), ("bias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
 class IstftParams(C.Structure):
@@ -149,6 +154,8 @@ SYMBOLS = {
     "dcs_real_attention_fwd": (_i, [C.POINTER(RealAttentionParams), _vp]),
     "dcs_rlstm_workspace_bytes": (_i64, [_i, _i, _i]),
     "dcs_rlstm_fwd": (_i, [C.POINTER(RlstmParams), _vp]),
+    "dcs_rlstm_tc_workspace_bytes": (_i64, [_i, _i, _i]),
+    "dcs_rlstm_tc_fwd": (_i, [C.POINTER(RlstmTcParams), _vp]),
     "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),

@@ -340,7 +340,40 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
-          if (valid) {
+          if (valid && tl.combine >= DCS_COMBINE_DR) {
+            // real path (r_network.py:172, network_functions.py:286-305 / 338-342): m = sigmoid(logit); |S| = |Y| m (dr) or
+            // |Y| - |Y| m (drs); the waveform takes the NOISY phase atan2(Im Y, Re Y + eps), so S = |S| e^{j phase} is formed
+            // here and the iSTFT reads it without a polar round trip
+            const int64_t o = ((int64_t)un.b * a.out_h + 2 * j + ph) * a.out_w + (int64_t)x * 8 + 4 * half;   // element index
+            const float4* yp = reinterpret_cast<const float4*>(tl.noisy_spec) + (o >> 1);
+#pragma unroll
+            for (int e2 = 0; e2 < 2; ++e2) {
+              const float4 y2 = __ldg(yp + e2);
+              float mk[2];
+              float2 cl[2], ns[2];
+#pragma unroll
+              for (int h = 0; h < 2; ++h) {
+                const float logit = __uint_as_float(rg[4 * e2 + 2 * h]) + tl.bias_re;
+                const float2 yv = h ? make_float2(y2.z, y2.w) : make_float2(y2.x, y2.y);
+                const float m = exact ? sigmoidf_(logit) : fast_sigmoid(logit);
+                const float mag = hypotf(yv.x, yv.y);                       // torch.abs(complex64)
+                float cs, sn;
+                if (exact) { const float th = atan2f(yv.y, yv.x + tl.atan2_eps); cs = cosf(th); sn = sinf(th); }
+                else {
+                  const float xr = yv.x + tl.atan2_eps, hy = hypotf(xr, yv.y);
+                  const float inv = hy > 0.f ? 1.f / hy : 0.f;
+                  cs = hy > 0.f ? xr * inv : 1.f; sn = yv.y * inv;
+                }
+                const float nm = mag * m;                                    // masked magnitude
+                const float cm = tl.combine == DCS_COMBINE_DRS ? mag - nm : nm;
+                mk[h] = m; cl[h] = make_float2(cm * cs, cm * sn); ns[h] = make_float2(nm * cs, nm * sn);
+              }
+              const int64_t q = (o >> 1) + e2;
+              reinterpret_cast<float4*>(tl.clean_spec)[q] = make_float4(cl[0].x, cl[0].y, cl[1].x, cl[1].y);
+              if (tl.noise_spec && tl.combine == DCS_COMBINE_DRS) reinterpret_cast<float4*>(tl.noise_spec)[q] = make_float4(ns[0].x, ns[0].y, ns[1].x, ns[1].y);
+              if (tl.mask) reinterpret_cast<float2*>(tl.mask)[q] = make_float2(mk[0], mk[1]);
+            }
+          } else if (valid) {
             const int64_t o = ((int64_t)un.b * a.out_h + 2 * j + ph) * a.out_w + (int64_t)x * 8 + 4 * half;   // complex index
             const float4* yp = reinterpret_cast<const float4*>(tl.noisy_spec) + (o >> 1);
 #pragma unroll
@@ -473,7 +506,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   DCS_REQUIRE(tail ? (tail->noisy_spec && tail->clean_spec) : (p->dst && p->bias), "dcs_cconv2d_strip_fwd: null output / bias pointer");
   DCS_REQUIRE(!tail || (p->cout == 1 && p->up_h == 2 && p->up_w == 8 && p->cols == 32 && p->out_w % 8 == 0 && !p->pool_sums),
               "dcs_cconv2d_strip_fwd: the tail epilogue is decoder[6] only (cout 1, 2 phase rows x 8 pixels per strip row)");
-  DCS_REQUIRE(!tail || tail->combine == DCS_COMBINE_DCS || tail->combine == DCS_COMBINE_DC, "dcs_cconv2d_strip_fwd: bad combine mode");
+  DCS_REQUIRE(!tail || (tail->combine >= DCS_COMBINE_DCS && tail->combine <= DCS_COMBINE_DRS), "dcs_cconv2d_strip_fwd: bad combine mode");
   DCS_REQUIRE(p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->cout > 0, "dcs_cconv2d_strip_fwd: bad shape");
   DCS_REQUIRE(is_h16(p->dtype), "dcs_cconv2d_strip_fwd: dtype must be DCS_F16 or DCS_BF16");
   DCS_REQUIRE(p->stride_w == 1 || p->stride_w == 2, "dcs_cconv2d_strip_fwd: stride_w must be 1 or 2");

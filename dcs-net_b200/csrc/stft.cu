@@ -126,7 +126,7 @@ struct StftSmem {
 template <typename TBN>
 __global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restrict__ audio, float2* __restrict__ spec,
                                                         int L, int T, int chunks_per_cta,
-                                                        const float* __restrict__ bn_affine, TBN* __restrict__ bn_out) {
+                                                        const float* __restrict__ bn_affine, TBN* __restrict__ bn_out, int bn_real) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   StftSmem& sm = *reinterpret_cast<StftSmem*>(smem_raw);
   const int b = blockIdx.y;
@@ -189,7 +189,10 @@ __global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restri
           X.x *= scale; X.y *= scale;
           const int64_t o = ((int64_t)b * kBins + (k - 1)) * T + t;
           spec[o] = X;
-          if (bn_out) Elem<TBN>::stc(bn_out, o, make_float2(A00 * X.x + A01 * X.y + o0, A10 * X.x + A11 * X.y + o1));
+          if (bn_out) {
+            const float2 Xb = bn_real ? make_float2(hypotf(X.x, X.y), 0.f) : X;   // real path: BatchNorm2d of |Y| (torch.abs = hypot)
+            Elem<TBN>::stc(bn_out, o, make_float2(A00 * Xb.x + A01 * Xb.y + o0, A10 * Xb.x + A11 * Xb.y + o1));
+          }
         }
       }
     }
@@ -277,8 +280,9 @@ __global__ void __launch_bounds__(kThreads, 4) istft_kernel(const float2* __rest
         for (int i = 0; i < 16; ++i) nx[i] = t < T ? __ldg(sp + (int64_t)(k_ld + 16 * i) * T + t) : make_float2(0.f, 0.f);
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          sm.buf[f][k_ld + 16 * i] = t < T ? (exact == 2 ? polar_roundtrip_mufu(nx[i], eps) : polar_roundtrip(nx[i], eps, exact != 0))
-                                           : make_float2(0.f, 0.f);
+          sm.buf[f][k_ld + 16 * i] = t >= T ? make_float2(0.f, 0.f)
+                                     : exact == 3 ? nx[i]                              // already mag * e^{j phase} (real-path tail)
+                                     : exact == 2 ? polar_roundtrip_mufu(nx[i], eps) : polar_roundtrip(nx[i], eps, exact != 0);
       } else {
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {
@@ -378,15 +382,15 @@ extern "C" int dcs_stft_fwd(const dcs_stft_params* p, void* stream) {
   if (p->bn_out && p->bn_dtype == DCS_BF16) {
     DCS_CUDA(cudaFuncSetAttribute(stft_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_kernel<__nv_bfloat16><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,
-                                                            p->bn_affine, (__nv_bfloat16*)p->bn_out);
+                                                            p->bn_affine, (__nv_bfloat16*)p->bn_out, p->bn_real);
   } else if (p->bn_out && p->bn_dtype == DCS_F16) {
     DCS_CUDA(cudaFuncSetAttribute(stft_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_kernel<__half><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,
-                                                     p->bn_affine, (__half*)p->bn_out);
+                                                     p->bn_affine, (__half*)p->bn_out, p->bn_real);
   } else {
     DCS_CUDA(cudaFuncSetAttribute(stft_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     stft_kernel<float><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,
-                                                    p->bn_affine, (float*)p->bn_out);
+                                                    p->bn_affine, (float*)p->bn_out, p->bn_real);
   }
   DCS_LAUNCHED();
   return 0;

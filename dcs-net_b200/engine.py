@@ -59,6 +59,28 @@ def _sd_tensor_dict(model_or_sd):
     return {k: v.detach() for k, v in sd.items()}
 
 
+def build_strips(enc, dec, Lr, device):
+    """Row-strip operands (packing.StripConv / StripEnc0 / StripDec6) for the few-channel layers of a packed encoder /
+    decoder stack — complex net or the real net in pair packing (same geometry): {(kind, layer): strip}."""
+    strip = {}
+    if os.environ.get("DCS_STRIP", "1") == "0":
+        return strip
+    e0 = enc[0]
+    if (e0.cin, e0.cout, e0.kh, e0.kw, tuple(e0.stride)) == (1, 8, 7, 7, (2, 2)) and os.environ.get("DCS_STRIP_ENC0", "1") != "0":
+        strip[("enc", 0)] = packing.StripEnc0(e0, device=device)
+    d6 = dec[Lr - 1] if Lr == 7 else None
+    if d6 is not None and (d6.cin, d6.cout, tuple(d6.up)) == (16, 1, (2, 2)) and os.environ.get("DCS_STRIP_DEC6", "1") != "0":
+        strip[("dec", 6)] = packing.StripDec6(d6, device=device)
+    want = {("enc", 1): (8, 0, True, 1), ("dec", 4): (32, 32, False, 2), ("dec", 5): (16, 16, True, 1)}
+    if os.environ.get("DCS_STRIP_ENC2", "1") != "0":
+        want[("enc", 2)] = (16, 0, True, 1)       # k5 s(2,2), N = 64: 50 MMA items, 100 KB of resident weights
+    for (kind, i), (c0, c1, merged, groups) in want.items():
+        pc = (enc if kind == "enc" else dec)[i] if i < Lr else None
+        if pc is not None and pc.cin == c0 + c1 and (2 * pc.cout) in ((16, 32, 64) if (kind, i) == ("enc", 2) else (16, 32)):
+            strip[(kind, i)] = packing.StripConv(pc, c0, c1, merged=merged, groups=groups, device=device)
+    return strip
+
+
 class PackedNet:
     """All GEMM-ready operands of a C_NETWORK state_dict for one device and mode."""
 
@@ -93,22 +115,8 @@ class PackedNet:
             if not last:  # decoder_attention[12], [13] never run (c_network.py:218)
                 self.dec_ca.append(packing.pack_channel_attention(sd, f"decoder_attention.{2 * i}.", device))
                 self.dec_sa.append(packing.pack_spatial_attention(sd, f"decoder_attention.{2 * i + 1}.", device))
-        # few-channel layers: row-strip tensor-core kernel (csrc/cconv_strip.cu); {layer: (c0, c1, merged, groups)}
-        self.strip = {}
-        if bf and os.environ.get("DCS_STRIP", "1") != "0":
-            e0 = self.enc[0]
-            if (e0.cin, e0.cout, e0.kh, e0.kw, tuple(e0.stride)) == (1, 8, 7, 7, (2, 2)) and os.environ.get("DCS_STRIP_ENC0", "1") != "0":
-                self.strip[("enc", 0)] = packing.StripEnc0(e0, device=device)
-            d6 = self.dec[Lr - 1] if Lr == 7 else None
-            if d6 is not None and (d6.cin, d6.cout, tuple(d6.up)) == (16, 1, (2, 2)) and os.environ.get("DCS_STRIP_DEC6", "1") != "0":
-                self.strip[("dec", 6)] = packing.StripDec6(d6, device=device)
-            want = {("enc", 1): (8, 0, True, 1), ("dec", 4): (32, 32, False, 2), ("dec", 5): (16, 16, True, 1)}
-            if os.environ.get("DCS_STRIP_ENC2", "1") != "0":
-                want[("enc", 2)] = (16, 0, True, 1)       # k5 s(2,2), N = 64: 50 MMA items, 100 KB of resident weights
-            for (kind, i), (c0, c1, merged, groups) in want.items():
-                pc = (self.enc if kind == "enc" else self.dec)[i] if i < Lr else None
-                if pc is not None and pc.cin == c0 + c1 and (2 * pc.cout) in ((16, 32, 64) if (kind, i) == ("enc", 2) else (16, 32)):
-                    self.strip[(kind, i)] = packing.StripConv(pc, c0, c1, merged=merged, groups=groups, device=device)
+        # few-channel layers: row-strip tensor-core kernel (csrc/cconv_strip.cu)
+        self.strip = build_strips(self.enc, self.dec, Lr, device) if bf else {}
         self.lstm = packing.pack_lstm(sd, "lstm.", device)
         w_r, w_i = sd["fc.fc_r.weight"], sd["fc.fc_i.weight"]
         self.fc = packing.PackedConv(w_r[:, :, None, None], w_i[:, :, None, None], sd["fc.fc_r.bias"], sd["fc.fc_i.bias"],

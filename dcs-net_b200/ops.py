@@ -23,8 +23,9 @@ def _code(t):
     return L.dtype_code(t)
 
 
-def stft(audio, spec=None, bn_affine=None, bn_out=None):
-    """(B, L) fp32 -> (B, 256, T) complex64 [data.py:112-134]; optionally also the folded initial BN output."""
+def stft(audio, spec=None, bn_affine=None, bn_out=None, bn_real=False):
+    """(B, L) fp32 -> (B, 256, T) complex64 [data.py:112-134]; optionally also the folded initial BN output (bn_real: of
+    the magnitude, for the real path)."""
     L.require_cuda(audio)
     assert audio.dtype == torch.float32 and audio.dim() == 2 and audio.is_contiguous()
     B, n = audio.shape
@@ -32,7 +33,7 @@ def stft(audio, spec=None, bn_affine=None, bn_out=None):
     if spec is None:
         spec = torch.empty(B, BINS, T, dtype=torch.complex64, device=audio.device)
     p = L.StftParams(L.ptr(audio), L.ptr(spec), B, n, T, L.ptr(bn_affine), L.ptr(bn_out),
-                     _code(bn_out) if bn_out is not None else F32)
+                     _code(bn_out) if bn_out is not None else F32, int(bn_real))
     L.check(L.lib().dcs_stft_fwd(C.byref(p), L.stream_ptr()), "dcs_stft_fwd")
     return spec
 
@@ -273,6 +274,24 @@ def rlstm(x, w, y=None, workspace=None):
     return y
 
 
+def rlstm_tc_workspace_bytes(B, S, hidden=128):
+    n = L.lib().dcs_rlstm_tc_workspace_bytes(B, S, hidden)
+    if n < 0:
+        raise RuntimeError("dcs_rlstm_tc_workspace_bytes: unsupported shape")
+    return int(n)
+
+
+def rlstm_tc(x, w, y, workspace):
+    """Tensor-core form of rlstm(): x (B, S, D) and y (B, S, 256) in the same 16-bit type; w = PackedRNet(...).lstm_tc."""
+    L.require_cuda(x, y)
+    B, S, D = x.shape
+    assert x.dtype in H16 and y.dtype == x.dtype and w["w_ih0"].dtype == x.dtype and x.is_contiguous() and y.is_contiguous()
+    p = L.RlstmTcParams(L.ptr(x), L.ptr(y), B, S, D, y.shape[2] // 2, _code(x), L.ptr(w["w_ih0"]), L.ptr(w["w_ih1"]), L.ptr(w["w_hh"]),
+                        L.ptr(w["bias"]), L.ptr(workspace), workspace.numel() * workspace.element_size())
+    L.check(L.lib().dcs_rlstm_tc_fwd(C.byref(p), L.stream_ptr()), "dcs_rlstm_tc_fwd")
+    return y
+
+
 def clstm_workspace_bytes(B, S, hidden=64):
     n = L.lib().dcs_clstm_workspace_bytes(B, S, hidden)
     if n < 0:
@@ -405,6 +424,6 @@ def _on_tensor_device(fn):
 
 for _name, _fn in list(globals().items()):
     if callable(_fn) and getattr(_fn, "__module__", None) == __name__ and not _name.startswith("_") \
-            and _name not in ("conv_out_hw", "clstm_workspace_bytes", "pool_sums_to_float"):
+            and _name not in ("conv_out_hw", "clstm_workspace_bytes", "rlstm_tc_workspace_bytes", "pool_sums_to_float"):
         globals()[_name] = _on_tensor_device(_fn)
 del _name, _fn

@@ -505,6 +505,14 @@ class PackedRNet:
                                  w_hh=sd[k.format("weight_hh")].float().contiguous().to(device),
                                  bias=(sd[k.format("bias_ih")] + sd[k.format("bias_hh")]).float().contiguous().to(device)))
             self.lstm.append(dirs)
+        # tensor-core operands (dcs_rlstm_tc_fwd): input projections [dir][half][256 gate rows][in] in the 16-bit storage type,
+        # W_hh fp32 [layer][dir][4H][H] (the kernel builds its fp16 register fragments itself), bias fp32 [layer][dir][4H]
+        self.lstm_tc = None
+        if tc_dtype is not None:
+            ih = lambda layer: torch.stack([d["w_ih"].reshape(2, 256, -1) for d in self.lstm[layer]]).to(tc_dtype).contiguous()   # noqa: E731
+            self.lstm_tc = dict(w_ih0=ih(0), w_ih1=ih(1),
+                                w_hh=torch.stack([torch.stack([d["w_hh"] for d in self.lstm[layer]]) for layer in range(2)]).contiguous(),
+                                bias=torch.stack([torch.stack([d["bias"] for d in self.lstm[layer]]) for layer in range(2)]).contiguous())
         # the same weights transposed for dcs_rlstm_fwd: w_ih*_t [in][2*4H] (columns dir*4H + gate row), w_hh_t [layer][dir][H][4H]
         cat_t = lambda layer, k: torch.cat([d[k].t() for d in self.lstm[layer]], dim=1).contiguous()   # noqa: E731
         self.lstm_t = dict(w_ih0_t=cat_t(0, "w_ih"), w_ih1_t=cat_t(1, "w_ih"),

@@ -12,6 +12,7 @@ import torch
 
 from . import _lib as L
 from .engine import ForwardPlan, PackedNet
+from .rengine import RealForwardPlan, PackedRealNet
 
 HOP = 32
 WINDOW_4S = 63968   # 32 * (2000 - 1): "4 s" utterance with T = 2000 frames (T % 8 == 0)
@@ -46,6 +47,7 @@ def split_windows(audio_1d, window):
 
 class Enhancer:
     """Fixed-shape enhancer: `batch` windows of `n_samples` samples per call."""
+    _packed_cls, _plan_cls, _variants = PackedNet, ForwardPlan, ("dcs", "dc")
 
     def __init__(self, model_or_sd, batch, n_samples=WINDOW_4S, mode="fp16", variant="dcs", device=None, graph=True,
                  atan2_eps=10e-7, exact_polar=False):
@@ -54,10 +56,12 @@ class Enhancer:
         L.lib()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.batch, self.n_samples, self.T = batch, n_samples, frames_for(n_samples)
+        if variant not in self._variants:
+            raise ValueError(f"{type(self).__name__} serves variants {self._variants}, got {variant!r}")
         with torch.cuda.device(self.device):
-            self.packed = model_or_sd if isinstance(model_or_sd, PackedNet) else PackedNet(model_or_sd, self.device, mode)
-            self.plan = ForwardPlan(self.packed, batch, self.T, variant=variant, atan2_eps=atan2_eps,
-                                    exact_polar=exact_polar, want_aux=False)
+            self.packed = model_or_sd if isinstance(model_or_sd, self._packed_cls) else self._packed_cls(model_or_sd, self.device, mode)
+            self.plan = self._plan_cls(self.packed, batch, self.T, variant=variant, atan2_eps=atan2_eps,
+                                       exact_polar=exact_polar, want_aux=False)
             if graph:
                 self.plan.capture()
         self.host_in = torch.empty(batch, n_samples, dtype=torch.float32, pin_memory=True)
@@ -178,3 +182,11 @@ class Enhancer:
             self.drain()
             torch.cuda.current_stream().synchronize()
         return out.reshape(-1)[:n].clone()
+
+
+class RealEnhancer(Enhancer):
+    """Enhancer for the real-valued DR-Net / DRS-Net (R_NETWORK weights; rengine.RealForwardPlan): same host API."""
+    _packed_cls, _plan_cls, _variants = PackedRealNet, RealForwardPlan, ("dr", "drs")
+
+    def __init__(self, model_or_sd, batch, n_samples=WINDOW_4S, mode="fp16", variant="drs", **kw):
+        super().__init__(model_or_sd, batch, n_samples=n_samples, mode=mode, variant=variant, **kw)

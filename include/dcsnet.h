@@ -36,7 +36,8 @@ enum { DCS_F32 = 0, DCS_BF16 = 1, DCS_F16 = 2 };
  * accumulated with integer atomics so that results are bit-identical from run to run. */
 #define DCS_POOL_FRAC_BITS 28
 enum { DCS_ACT_NONE = 0, DCS_ACT_RELU = 1, DCS_ACT_LRELU = 2, DCS_ACT_SIGMOID = 3 }; /* ComplexReLU / ComplexLReLU(0.01) / ComplexSigmoid */
-enum { DCS_COMBINE_DCS = 0, DCS_COMBINE_DC = 1 };                /* S = Y - Y*M   |   S = Y*M */
+enum { DCS_COMBINE_DCS = 0, DCS_COMBINE_DC = 1,                  /* S = Y - Y*M   |   S = Y*M                (complex masks) */
+       DCS_COMBINE_DR = 2, DCS_COMBINE_DRS = 3 };                 /* |S| = |Y| m   |   |S| = |Y| - |Y| m, noisy phase (real masks) */
 
 #define DCS_MAX_TAPS 64
 
@@ -48,10 +49,12 @@ uint64_t dcs_launch_count(void);
 /* ---- a1: STFT front-end.  Replaces torch.stft(n_fft=512, hop=32, win=512, hann, normalized, center) [1:257]
  *      at data.py:112-134 (config.py:72-77).  audio (B, L) fp32 -> spec (B, 256, T) complex64, T = L/32 + 1.
  *      If bn_affine != NULL (6 floats A00 A01 A10 A11 c0 c1: the folded eval-mode `initial_batchnorm`,
- *      c_network.py:190) a second tensor bn_out (B,256,T,1) of dtype bn_dtype receives A*[re;im]+c. */
+ *      c_network.py:190) a second tensor bn_out (B,256,T,1) of dtype bn_dtype receives A*[re;im]+c; with bn_real != 0 the
+ *      affine is applied to (|spec|, 0) instead — the real path's initial BatchNorm2d of the magnitude (r_network.py:128,
+ *      network_functions.py:286), stored as the channel pair (bn(|Y|), padding). */
 typedef struct {
   const float* audio; float* spec; int batch; int length; int n_frames;
-  const float* bn_affine; void* bn_out; int bn_dtype;
+  const float* bn_affine; void* bn_out; int bn_dtype; int bn_real;
 } dcs_stft_params;
 int dcs_stft_fwd(const dcs_stft_params* p, void* stream);
 
@@ -75,7 +78,8 @@ int dcs_frontend_fwd(const dcs_frontend_params* p, void* stream);
  *      of the frequency axis, torch.istft(n_fft=512, hop=32, hann, normalized).  spec (B,256,T) complex64 ->
  *      audio (B, 32*(T-1)) fp32.  exact_polar=1 evaluates atan2f/cosf/sinf literally, 0 uses the algebraically
  *      identical (re+eps, im)/hypot form, 2 the same form with approximate reciprocal square roots (rel. error ~2e-7;
- *      the bf16 / tensor-core mode's choice). */
+ *      the tensor-core mode's choice), 3 skips the round trip (spec is already mag * e^{j phase}: the real path's fused
+ *      tail, which applies the NOISY phase itself, network_functions.py:300-304). */
 typedef struct {
   const float* spec; float* audio; int batch; int n_frames; float atan2_eps; int exact_polar;
   /* mag_phase_2_wave(mag, phase, config) called directly (network_functions.py:140): if spec == NULL the input is
@@ -147,7 +151,11 @@ typedef struct { uint32_t a_off16; uint32_t b_off16; uint16_t d_col; uint8_t dro
 typedef struct { int item0; int n_items; int dy_min; int n_dy; int ph0; int n_ph; int x_min; int w_bytes; int64_t w_off; } dcs_strip_group;
 /* optional fused tail (decoder[6] only, replaces dcs_dec6_tail_fwd on the tensor-core path): the accumulator columns are
  * (phase row, 8 output pixels, re/im) of decoder[6]'s raw output; the epilogue adds (bias_re, bias_im) and applies
- * bound_cRM twice, the product with Y and the subtraction exactly as dcs_mask_combine does.  dst / bias are unused. */
+ * bound_cRM twice, the product with Y and the subtraction exactly as dcs_mask_combine does.  dst / bias are unused.
+ * Real path (combine = DCS_COMBINE_DR / DRS; r_network.py:172 + network_functions.py:286-305, 338-342): the logit is the
+ * .re column, m = sigmoid(logit) is written to `mask` as an fp32 REAL (B, 2h, 2w) array, and clean_spec / noise_spec
+ * receive |Y| m (or |Y| - |Y| m) times e^{j atan2(Im Y, Re Y + eps)} as complex64, ready for dcs_istft_fwd with
+ * exact_polar = 3; net_raw / net_out are ignored. */
 typedef struct {
   const float* noisy_spec; float* net_raw; float* net_out; float* mask; float* noise_spec; float* clean_spec;
   float bias_re; float bias_im; float atan2_eps; int combine; int exact_polar;
@@ -242,6 +250,19 @@ typedef struct {
 } dcs_rlstm_params;
 int64_t dcs_rlstm_workspace_bytes(int batch, int seq, int hidden);
 int dcs_rlstm_fwd(const dcs_rlstm_params* p, void* stream);
+
+/* Tensor-core form of the same LSTM (fp16 / bf16 modes): x (B, S, D) and y (B, S, 256) in the 16-bit storage type `dtype`;
+ *      input projections as tcgen05 kind::f16 GEMMs, recurrence as fp16 mma.sync with W_hh resident in registers.
+ *      w_ih0: [dir 2][half 2][256][D] and w_ih1: [dir][half][256][2H] in `dtype`, K contiguous (gate rows half*256.. of the
+ *      direction); w_hh: fp32 [layer][dir][4H][H] (the reference layout); bias: fp32 [layer][dir][4H] = b_ih + b_hh
+ *      (packing.PackedRNet.lstm_tc). */
+typedef struct {
+  const void* x; void* y; int batch; int seq; int in_dim; int hidden; int dtype;
+  const void* w_ih0; const void* w_ih1; const float* w_hh; const float* bias;
+  void* workspace; int64_t workspace_bytes;
+} dcs_rlstm_tc_params;
+int64_t dcs_rlstm_tc_workspace_bytes(int batch, int seq, int hidden);
+int dcs_rlstm_tc_fwd(const dcs_rlstm_tc_params* p, void* stream);
 
 /* ---- a7: ComplexLSTM (c_network.py:12-51): real_lstm / imag_lstm = nn.LSTM(128->64, 2 layers, bidirectional),
  *      out = (R(re) - I(im)) + j (R(im) + I(re)).  x (B,S,D) complex channels-last (the latent, sequence index

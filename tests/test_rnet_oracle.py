@@ -274,3 +274,81 @@ def test_real_layers_pack_for_the_row_strip_kernel(layer, merged, groups):
     sp = packing.StripConv(p, c0, c1, merged=merged, groups=groups)
     out_hw = ops.conv_out_hw(p, H, W)
     assert rel_err(strip_geometry(sp, srcs[0], srcs[1], out_hw), conv_geometry(p, srcs[0], srcs[1], out_hw, weights="tc")) <= 1e-2
+
+
+# ------------------------------------------------------------------ the real path on the tensor cores (rengine.RealForwardPlan)
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode,B,S", [("fp16", 3, 37), ("fp16", 8, 500), ("bf16", 5, 21)])
+def test_gpu_real_lstm_tensor_core_matches_torch_lstm(mode, B, S):
+    """dcs_rlstm_tc_fwd (kind::f16 projections + fp16 mma.sync recurrence, W_hh in registers) vs torch.nn.LSTM on the same
+    16-bit-rounded input; batch sizes that are not a multiple of the 4 sequences a CTA owns; the full sequence length."""
+    from dcsnet_b200 import ops
+    net = product_net()
+    dt = torch.float16 if mode == "fp16" else torch.bfloat16
+    pk = D.PackedRealNet(net.state_dict(), "cuda", mode)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(B, S, 256, generator=g).to(dt)
+    with torch.no_grad():
+        ref, _ = net.lstm(x.float())
+    y = torch.full((B, S, 256), float("nan"), dtype=dt, device="cuda")
+    ws = torch.empty(ops.rlstm_tc_workspace_bytes(B, S), dtype=torch.uint8, device="cuda")
+    ops.rlstm_tc(x.cuda(), pk.lstm_tc, y, ws)
+    torch.cuda.synchronize()
+    assert not torch.isnan(y.float()).any()
+    # 16-bit weights / hidden state / output (|h| < 1): a few ulps of the storage type
+    assert rel_err(y.float().cpu(), ref) <= (3e-3 if mode == "fp16" else 2.5e-2)
+    y2 = torch.empty_like(y)
+    ops.rlstm_tc(x.cuda(), pk.lstm_tc, y2, ws)
+    torch.cuda.synchronize()
+    assert torch.equal(y.view(torch.int16), y2.view(torch.int16))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["drs", "dr"])
+def test_gpu_real_tensor_core_plan_matches_reference_golden(variant):
+    """RealForwardPlan (fp16 storage, tcgen05 convs, fused sigmoid / magnitude / noisy-phase tail) from the AUDIO against
+    what the reference's own r_network.py + step functions produced: mask, clean magnitude, waveform <= 2e-3, |dSI-SDR|."""
+    g = torch.load(GOLDEN)
+    net = product_net()
+    randomise_bn(net.state_dict(), g["bn_seed"])
+    B, n = g["noisy_audio"].shape
+    T = n // 32 + 1
+    plan = D.RealForwardPlan(D.PackedRealNet(net.state_dict(), "cuda", "fp16"), B, T, variant=variant)
+    n0 = D._lib.launch_count()
+    audio = plan.enhance_audio(g["noisy_audio"].cuda()).clone()
+    torch.cuda.synchronize()
+    assert D._lib.launch_count() - n0 >= 30
+    assert rel_err(plan.mask.cpu(), g["mask"]) <= 2e-3
+    assert rel_err(plan.clean_spec.abs().cpu(), g[f"{variant}_clean_mag"]) <= 2e-3
+    assert rel_err(audio.cpu(), g[f"{variant}_clean_audio"]) <= 2e-3
+    clean = O.synthetic_audio(B, n)[0]
+    assert abs(float(O.si_snr(clean, audio.cpu()) - O.si_snr(clean, g[f"{variant}_clean_audio"]))) <= 0.01
+    again = plan.enhance_audio(g["noisy_audio"].cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(again, audio)           # bit-reproducible
+
+
+@pytest.mark.gpu
+def test_gpu_real_tensor_core_plan_full_size_vs_oracle():
+    """BASELINE configs[2] size (batch 64 x 3.998 s) through RealEnhancer (CUDA graph): utterances of the full batch against
+    the oracle, replays bit-identical, samples independent."""
+    net = product_net()
+    randomise_bn(net.state_dict(), 7)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    B, T = 64, 2000
+    clean, _, noisy = O.synthetic_audio(B, 32 * (T - 1))
+    enh = D.RealEnhancer(sd, batch=B, n_samples=32 * (T - 1), mode="fp16", variant="drs")
+    full = enh.enhance_device(noisy.cuda()).clone()
+    torch.cuda.synchronize()
+    assert torch.isfinite(full).all()
+    idx = [0, 63]
+    ref = RO.enhance_spec(sd, O.stft(noisy[idx]), "drs")["clean_audio"]
+    assert rel_err(full[idx].cpu(), ref) <= 2e-3
+    assert abs(float(O.si_snr(clean[idx], full[idx].cpu()) - O.si_snr(clean[idx], ref))) <= 0.01
+    again = enh.enhance_device().clone()
+    torch.cuda.synchronize()
+    assert torch.equal(again, full)
+    perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+    out_p = enh.enhance_device(noisy[perm].cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(out_p, full[perm.cuda()])
