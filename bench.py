@@ -445,10 +445,11 @@ def measure_roofline(plan, args, B, T, clocks=None):
             return r
         setattr(ops, name, inner)
 
-    wrap("cconv", lambda pk, s0, s1, dst, use_tc=False, pool_sums=None: "conv_tc" if use_tc else "conv_ffma")
+    wrap("cconv", lambda pk, s0, s1, dst, use_tc=False, **k: "conv_tc" if use_tc else "conv_ffma")
     wrap("cconv_strip", lambda *a, **k: "conv_strip")
     for n in ("stft", "istft", "chan_pool", "chan_gate", "spat_stats", "spat_apply", "attention_fused", "attention_stream", "clstm",
-              "mask_combine", "enc0", "dec6_tail", "real_attention", "rlstm", "mag_phase", "real_mask_combine"):
+              "mask_combine", "enc0", "dec6_tail", "real_attention", "real_attention_stream", "chan_max", "rlstm", "rlstm_tc", "mag_phase",
+              "real_mask_combine"):
         if hasattr(ops, n):
             wrap(n, lambda *a, _n=n, **k: _n)
     steps = max(3, min(args.steps, 10))
@@ -530,6 +531,7 @@ def measure_roofline(plan, args, B, T, clocks=None):
         "attention_fused": 2 * att_bytes,
         "attention_stream": 2 * att_bytes,     # x once in, y once out
         "real_attention": 2 * att_bytes,       # the algorithmic minimum (a multi-pass kernel set reads x more than once)
+        "real_attention_stream": 2 * att_bytes,
         "dec6_tail": B * (2 * 128 * (T // 2) * 16 * esz + 2 * 8 * 256 * T),
         "enc0": B * (8 * 256 * T + 128 * (T // 2) * 16 * esz),
     }
@@ -539,7 +541,7 @@ def measure_roofline(plan, args, B, T, clocks=None):
             gbs = nbytes / (stage_ms[k] / 1e3) / 1e9
             stages.append({"stage": k, "bound": "hbm", "ms": stage_ms[k], "launches": launches[k], "algorithmic_bytes": nbytes,
                            "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm, "frac_vs_8tbs": gbs / HBM_SPEC_GBS})
-    for k in ("clstm", "rlstm"):
+    for k in ("clstm", "rlstm", "rlstm_tc"):
         if k in stage_ms:
             stages.append({"stage": k, "bound": "latency (2 x S sequential recurrent steps; reported against neither roof)",
                            "ms": stage_ms[k], "launches": launches.get(k), "steps": 2 * 2 * (T // 8)})

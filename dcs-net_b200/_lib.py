@@ -13,6 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdcsnet_sm100a.so")
 
 F32, BF16, F16 = 0, 1, 2
+POOL_SUM, POOL_MAX = 0, 1
 POOL_FRAC_BITS = 28           # pooled sums are int64 fixed point (include/dcsnet.h: DCS_POOL_FRAC_BITS)
 ACT_NONE, ACT_RELU, ACT_LRELU, ACT_SIGMOID = 0, 1, 2, 3
 COMBINE_DCS, COMBINE_DC, COMBINE_DR, COMBINE_DRS = 0, 1, 2, 3
@@ -65,7 +66,7 @@ class CconvParams(C.Structure):
                 ("ntaps", _i), ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS),
                 ("weight", _vp), ("bias", _vp), ("act", _i),
                 ("dst", _vp), ("in_dtype", _i), ("out_dtype", _i),
-                ("pool_sums", _vp)]
+                ("pool_sums", _vp), ("pool_mode", _i)]
 
 
 STRIP_MAX_GROUPS = 2
@@ -91,7 +92,7 @@ class CstripParams(C.Structure):
                 ("weights", _vp),
                 ("box_units", _i), ("n_mma", _i), ("cols", _i),
                 ("bias", _vp), ("act", _i),
-                ("dst", _vp), ("pool_sums", _vp), ("tail", C.POINTER(StripTail)), ("dtype", _i)]
+                ("dst", _vp), ("pool_sums", _vp), ("tail", C.POINTER(StripTail)), ("dtype", _i), ("pool_mode", _i)]
 
 
 class ChanPoolParams(C.Structure):
@@ -118,7 +119,7 @@ class SpatApplyParams(C.Structure):
 class AttentionParams(C.Structure):
     _fields_ = [("x", _vp), ("y", _vp), ("sums", _vp), ("batch", _i), ("h", _i), ("w", _i), ("channels", _i),
                 ("reduced", _i), ("in_dtype", _i), ("out_dtype", _i),
-                ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp), ("w7", _vp)]
+                ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp), ("w7", _vp), ("real", _i)]
 
 
 class ClstmParams(C.Structure):
@@ -164,6 +165,7 @@ SYMBOLS = {
     "dcs_cconv2d_tc_fwd": (_i, [C.POINTER(CconvParams), _vp]),
     "dcs_cconv2d_strip_fwd": (_i, [C.POINTER(CstripParams), _vp]),
     "dcs_chan_pool": (_i, [C.POINTER(ChanPoolParams), _vp]),
+    "dcs_chan_max": (_i, [C.POINTER(ChanPoolParams), _vp]),
     "dcs_chan_gate": (_i, [C.POINTER(ChanGateParams), _vp]),
     "dcs_pool_mean": (_i, [_vp, _f, _vp, _i64, _vp]),
     "dcs_spat_stats": (_i, [C.POINTER(SpatStatsParams), _vp]),

@@ -72,6 +72,33 @@ __global__ void __launch_bounds__(256) chan_pool_kernel(const T* __restrict__ x,
   }
 }
 
+// per-(image, pair, slot) maxima in the DCS_POOL_MAX encoding (the real path's AdaptiveMaxPool2d(1))
+template <typename T>
+__global__ void __launch_bounds__(256) chan_max_kernel(const T* __restrict__ x, long long* __restrict__ maxima, int hw, int C,
+                                                       int pix_per_cta) {
+  __shared__ float2 red[256];
+  const int b = blockIdx.y;
+  const int lanes = 256 / C;
+  const int c = threadIdx.x % C, pl = threadIdx.x / C;
+  const int p0 = blockIdx.x * pix_per_cta, p1 = min(p0 + pix_per_cta, hw);
+  float2 acc = make_float2(-INFINITY, -INFINITY);
+  if (pl < lanes) {
+    const T* xb = x + (int64_t)b * hw * C * 2;
+    for (int p = p0 + pl; p < p1; p += lanes) {
+      const float2 v = Elem<T>::ldc(xb, (int64_t)p * C + c);
+      acc.x = fmaxf(acc.x, v.x); acc.y = fmaxf(acc.y, v.y);
+    }
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    float2 s = make_float2(-INFINITY, -INFINITY);
+    for (int l = 0; l < lanes; ++l) { const float2 v = red[l * C + threadIdx.x]; s.x = fmaxf(s.x, v.x); s.y = fmaxf(s.y, v.y); }
+    pool_max(maxima + ((int64_t)b * C + threadIdx.x) * 2 + 0, s.x);
+    pool_max(maxima + ((int64_t)b * C + threadIdx.x) * 2 + 1, s.y);
+  }
+}
+
 // ---------------------------------------------------------------- 2. the squeeze/excite MLP on (B, C) complex
 __global__ void __launch_bounds__(128) chan_gate_kernel(const dcs_chan_gate_params p) {
   __shared__ float2 avg[256];
@@ -498,6 +525,24 @@ extern "C" int dcs_chan_pool(const dcs_chan_pool_params* p, void* stream) {
   if (p->dtype == DCS_BF16) chan_pool_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, sums, p->hw, p->channels, ppc);
   else if (p->dtype == DCS_F16) chan_pool_kernel<__half><<<grid, 256, 0, s>>>((const __half*)p->x, sums, p->hw, p->channels, ppc);
   else chan_pool_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, sums, p->hw, p->channels, ppc);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_chan_max(const dcs_chan_pool_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->sums, "dcs_chan_max: null pointer");
+  DCS_REQUIRE(p->batch > 0 && p->hw > 0 && pow2(p->channels) && p->channels <= 256, "dcs_chan_max: channels must be a power of two <= 256");
+  DCS_REQUIRE(is_dtype(p->dtype), "dcs_chan_max: bad dtype");
+  const int lanes = 256 / p->channels;
+  int ctas = (p->hw + lanes * 8 - 1) / (lanes * 8);
+  ctas = min(ctas, max(1, 8 * num_sms() / p->batch));
+  const int ppc = (p->hw + ctas - 1) / ctas;
+  dim3 grid((p->hw + ppc - 1) / ppc, p->batch);
+  cudaStream_t s = (cudaStream_t)stream;
+  long long* mx = reinterpret_cast<long long*>(p->sums);
+  if (p->dtype == DCS_BF16) chan_max_kernel<__nv_bfloat16><<<grid, 256, 0, s>>>((const __nv_bfloat16*)p->x, mx, p->hw, p->channels, ppc);
+  else if (p->dtype == DCS_F16) chan_max_kernel<__half><<<grid, 256, 0, s>>>((const __half*)p->x, mx, p->hw, p->channels, ppc);
+  else chan_max_kernel<float><<<grid, 256, 0, s>>>((const float*)p->x, mx, p->hw, p->channels, ppc);
   DCS_LAUNCHED();
   return 0;
 }

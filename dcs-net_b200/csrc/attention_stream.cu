@@ -106,7 +106,10 @@ __device__ __forceinline__ void sts64f(uint32_t addr, float a, float b) {
 }
 
 // C channels (power of two >= 8), strip width TW (multiple of 16, <= 128).
-template <typename T, int C, int TW>
+// REAL: the real network's CBAM (r_network.py:8-40) on a pair tensor — C pairs = 2C real channels, element-wise gates,
+// max-pool channel gate, 2 statistics per pixel, one real spatial gate (same data movement, same MMA structure with the
+// imaginary rows / inputs zero).
+template <typename T, int C, int TW, bool REAL = false>
 __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const AttStreamArgs a) {
   constexpr int PW = TW + 6;                                  // strip + 3-pixel halo each side
   constexpr int VPP = C / 4;                                  // 16-byte vectors per pixel
@@ -149,19 +152,26 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int i = tid; i < 4 * ST_PITCH; i += kAsThreads) st[i] = 0.f;
-  for (int c = tid; c < C; c += kAsThreads)
-    avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
+  for (int c = tid; c < C; c += kAsThreads) {
+    if constexpr (REAL) avg[c] = make_float2(pool_max_value(a.sums, ((int64_t)b * C + c) * 2), pool_max_value(a.sums, ((int64_t)b * C + c) * 2 + 1));
+    else avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
+  }
   __syncthreads();
   if (tid == 0)
     for (int r = 0; r < min(NR, H); ++r) issue_row(r);
 
   // ---- channel gate (ComplexChannelAttention): sigmoid_c(2 W2 crelu(W1 avg)), recomputed per CTA (C * R complex MACs)
+  //      REAL (RealChannelAttention, r_network.py:20-25): sigmoid(W2 relu(W1 max)) over the 2C real channels; w1 (R, 2C), w2 (2C, R)
   for (int r = warp; r < a.R; r += kAsThreads / 32) {
     float re = 0.f, im = 0.f;
     for (int c = lane; c < C; c += 32) {
-      const float wr = a.w1_r[r * C + c], wi = a.w1_i[r * C + c];
-      re += wr * avg[c].x - wi * avg[c].y;
-      im += wr * avg[c].y + wi * avg[c].x;
+      if constexpr (REAL) {
+        re += a.w1_r[r * 2 * C + 2 * c] * avg[c].x + a.w1_r[r * 2 * C + 2 * c + 1] * avg[c].y;
+      } else {
+        const float wr = a.w1_r[r * C + c], wi = a.w1_i[r * C + c];
+        re += wr * avg[c].x - wi * avg[c].y;
+        im += wr * avg[c].y + wi * avg[c].x;
+      }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
@@ -171,11 +181,16 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
   for (int c = tid; c < C; c += kAsThreads) {
     float re = 0.f, im = 0.f;
     for (int r = 0; r < a.R; ++r) {
-      const float wr = a.w2_r[c * a.R + r], wi = a.w2_i[c * a.R + r];
-      re += wr * hid[r].x - wi * hid[r].y;
-      im += wr * hid[r].y + wi * hid[r].x;
+      if constexpr (REAL) {
+        re += a.w2_r[(2 * c) * a.R + r] * hid[r].x;
+        im += a.w2_r[(2 * c + 1) * a.R + r] * hid[r].x;
+      } else {
+        const float wr = a.w2_r[c * a.R + r], wi = a.w2_i[c * a.R + r];
+        re += wr * hid[r].x - wi * hid[r].y;
+        im += wr * hid[r].y + wi * hid[r].x;
+      }
     }
-    gs[c] = make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
+    gs[c] = REAL ? make_float2(sigmoidf_(re), sigmoidf_(im)) : make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
   }
 
   // ---- gate conv operands (ComplexConv2d(2, 1, 7, padding=3, bias=False) as a real 4 -> 2 conv).  Per statistics row the
@@ -194,9 +209,13 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
       const int ky = (r & 1) == 0 ? (q < 3 ? q : 7) : (q < 3 ? 4 + q : 3);
       float v = 0.f;
       if (kx < 7 && ky < 7) {
-        const int idx = (ci >> 1) * 49 + ky * 7 + kx;
-        const float wr = a.w7[idx], wi = a.w7[98 + idx];
-        v = o == 0 ? ((ci & 1) ? -wi : wr) : ((ci & 1) ? wr : wi);
+        if constexpr (REAL) {   // Conv2d(2, 1, 7): inputs ci = (mean, max, -, -), one real output (the o = 0 rows)
+          if (o == 0 && ci < 2) v = a.w7[ci * 49 + ky * 7 + kx];
+        } else {
+          const int idx = (ci >> 1) * 49 + ky * 7 + kx;
+          const float wr = a.w7[idx], wi = a.w7[98 + idx];
+          v = o == 0 ? ((ci & 1) ? -wi : wr) : ((ci & 1) ? wr : wi);
+        }
       }
       afr[s][r] = tf32_rna(v);
     }
@@ -262,13 +281,20 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
     for (int k = 0; k < VPL; ++k) {   // lanes outside the image read (valid) shared memory and are masked at the store
       CPair p01, p23;
       unpack_pairs<T>(lds128(s_ld + ring * ROW_BYTES + k * G * 16), p01, p23);
-      const CPair u01 = cmul_pair(sgate[k][0], p01), u23 = cmul_pair(sgate[k][1], p23);
+      CPair u01, u23;
+      if constexpr (REAL) {   // element-wise gates: the (re, im) slots are independent real channels
+        u01.re = mul2(sgate[k][0].re, p01.re); u01.im = mul2(sgate[k][0].im, p01.im);
+        u23.re = mul2(sgate[k][1].re, p23.re); u23.im = mul2(sgate[k][1].im, p23.im);
+      } else {
+        u01 = cmul_pair(sgate[k][0], p01); u23 = cmul_pair(sgate[k][1], p23);
+      }
       sre = add2(sre, add2(u01.re, u23.re));
       sim = add2(sim, add2(u01.im, u23.im));
       mr = fmaxf(fmaxf(mr, fmaxf(u01.re.x, u01.re.y)), fmaxf(u23.re.x, u23.re.y));
       mi = fmaxf(fmaxf(mi, fmaxf(u01.im.x, u01.im.y)), fmaxf(u23.im.x, u23.im.y));
     }
     float sr = sre.x + sre.y, si = sim.x + sim.y;
+    if constexpr (REAL) { sr = 0.5f * (sr + si); si = 0.f; mr = fmaxf(mr, mi); mi = 0.f; }   // mean / max over all 2C real channels
     if (G > 1) {   // every lane takes part
 #pragma unroll
       for (int o = G >> 1; o; o >>= 1) {
@@ -277,7 +303,10 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
       }
     }
     if (s_act && sub == 0) {
-      if (s_in) sts128f(s_st + sbuf, tf32_rna(sr * invC), tf32_rna(si * invC), tf32_rna(mr), tf32_rna(mi));
+      if (s_in) {
+        if constexpr (REAL) sts128f(s_st + sbuf, tf32_rna(sr * invC), tf32_rna(mr), 0.f, 0.f);   // ci = (mean, max, -, -)
+        else sts128f(s_st + sbuf, tf32_rna(sr * invC), tf32_rna(si * invC), tf32_rna(mr), tf32_rna(mi));
+      }
       else sts128f(s_st + sbuf, 0.f, 0.f, 0.f, 0.f);
     }
   };
@@ -292,9 +321,15 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gsp.x) : "r"(a_sg + gbuf + k * (istep / VPP) * 4));
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(gsp.y) : "r"(a_sg + gbuf + TW * 4 + k * (istep / VPP) * 4));
         const float2 gre = make_float2(gsp.x, gsp.x), gim = make_float2(gsp.y, gsp.y), gnim = make_float2(-gsp.y, -gsp.y);
-        const CPair u01 = cmul_pair(agate[0], p01), u23 = cmul_pair(agate[1], p23);
-        const float2 r01 = fma2(gre, u01.re, mul2(gnim, u01.im)), i01 = fma2(gre, u01.im, mul2(gim, u01.re));
-        const float2 r23 = fma2(gre, u23.re, mul2(gnim, u23.im)), i23 = fma2(gre, u23.im, mul2(gim, u23.re));
+        float2 r01, i01, r23, i23;
+        if constexpr (REAL) {   // y = gate_s * gate_c * x, everything real
+          r01 = mul2(gre, mul2(agate[0].re, p01.re)); i01 = mul2(gre, mul2(agate[0].im, p01.im));
+          r23 = mul2(gre, mul2(agate[1].re, p23.re)); i23 = mul2(gre, mul2(agate[1].im, p23.im));
+        } else {
+          const CPair u01 = cmul_pair(agate[0], p01), u23 = cmul_pair(agate[1], p23);
+          r01 = fma2(gre, u01.re, mul2(gnim, u01.im)); i01 = fma2(gre, u01.im, mul2(gim, u01.re));
+          r23 = fma2(gre, u23.re, mul2(gnim, u23.im)); i23 = fma2(gre, u23.im, mul2(gim, u23.re));
+        }
         *reinterpret_cast<uint4*>(yp + (int64_t)yo * y_pitch + (size_t)k * istep * 8) =
             make_uint4(pack_h2<T>(r01.x, i01.x), pack_h2<T>(r01.y, i01.y), pack_h2<T>(r23.x, i23.x), pack_h2<T>(r23.y, i23.y));
       }
@@ -384,7 +419,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
 
 using namespace dcs;
 
-template <typename T, int C, int TW>
+template <typename T, int C, int TW, bool REAL = false>
 static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s) {
   const int NR = p->h < kAsRing ? p->h : kAsRing;
   const size_t pw = TW + 6;
@@ -395,14 +430,14 @@ static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s
   a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
   a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = NR;
   // (set on every call: the attribute is per device, and one process may drive several GPUs)
-  DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<T, C, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DCS_CUDA(cudaFuncSetAttribute(attention_stream_kernel<T, C, TW, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->w + TW - 1) / TW, p->batch);
-  attention_stream_kernel<T, C, TW><<<grid, kAsThreads, smem, s>>>(a);
+  attention_stream_kernel<T, C, TW, REAL><<<grid, kAsThreads, smem, s>>>(a);
   DCS_LAUNCHED();
   return 0;
 }
 
-template <typename T>
+template <typename T, bool REAL = false>
 static int dispatch_attention_stream(const dcs_attention_params* p, cudaStream_t s) {
   // strip width: 128 pixels (every warp owns 16) for the few-channel tensors; narrow strips where a row of C channels is
   // long (ring of 8 rows) and the tensor has few pixels (enough CTAs), or where the image itself is narrow
@@ -411,24 +446,28 @@ static int dispatch_attention_stream(const dcs_attention_params* p, cudaStream_t
   auto cost = [&](int tw) { const int64_t ctas = (int64_t)((w + tw - 1) / tw) * p->batch, slots = 2 * num_sms(); return ((ctas + slots - 1) / slots) * (tw + 6); };
   const bool wide112 = cost(112) < cost(128);
   switch (p->channels) {
-    case 8: return w > 64 ? (wide112 ? launch_attention_stream<T, 8, 112>(p, s) : launch_attention_stream<T, 8, 128>(p, s))
-                          : w > 32 ? launch_attention_stream<T, 8, 64>(p, s) : launch_attention_stream<T, 8, 32>(p, s);
-    case 16: return w > 64 ? (wide112 ? launch_attention_stream<T, 16, 112>(p, s) : launch_attention_stream<T, 16, 128>(p, s))
-                           : w > 32 ? launch_attention_stream<T, 16, 64>(p, s) : launch_attention_stream<T, 16, 32>(p, s);
-    case 32: return w > 16 ? launch_attention_stream<T, 32, 32>(p, s) : launch_attention_stream<T, 32, 16>(p, s);
-    case 64: return w > 16 ? launch_attention_stream<T, 64, 32>(p, s) : launch_attention_stream<T, 64, 16>(p, s);
-    case 128: return launch_attention_stream<T, 128, 16>(p, s);
+    case 8: return w > 64 ? (wide112 ? launch_attention_stream<T, 8, 112, REAL>(p, s) : launch_attention_stream<T, 8, 128, REAL>(p, s))
+                          : w > 32 ? launch_attention_stream<T, 8, 64, REAL>(p, s) : launch_attention_stream<T, 8, 32, REAL>(p, s);
+    case 16: return w > 64 ? (wide112 ? launch_attention_stream<T, 16, 112, REAL>(p, s) : launch_attention_stream<T, 16, 128, REAL>(p, s))
+                           : w > 32 ? launch_attention_stream<T, 16, 64, REAL>(p, s) : launch_attention_stream<T, 16, 32, REAL>(p, s);
+    case 32: return w > 16 ? launch_attention_stream<T, 32, 32, REAL>(p, s) : launch_attention_stream<T, 32, 16, REAL>(p, s);
+    case 64: return w > 16 ? launch_attention_stream<T, 64, 32, REAL>(p, s) : launch_attention_stream<T, 64, 16, REAL>(p, s);
+    case 128: return launch_attention_stream<T, 128, 16, REAL>(p, s);
     default: break;
   }
   return set_error(-1, "dcs_attention_stream: channels must be 8, 16, 32, 64 or 128 (got %d)", p->channels);
 }
 
 extern "C" int dcs_attention_stream(const dcs_attention_params* p, void* stream) {
-  DCS_REQUIRE(p && p->x && p->y && p->sums && p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->w7, "dcs_attention_stream: null pointer");
+  DCS_REQUIRE(p && p->x && p->y && p->sums && p->w1_r && p->w2_r && p->w7 && (p->real || (p->w1_i && p->w2_i)), "dcs_attention_stream: null pointer");
   DCS_REQUIRE(is_h16(p->in_dtype) && p->out_dtype == p->in_dtype,
               "dcs_attention_stream: 16-bit storage only, same type in and out (the fp32 mode uses dcs_spat_stats / dcs_spat_apply)");
   DCS_REQUIRE(p->batch > 0 && p->batch <= 65535 && p->h > 0 && p->w > 0, "dcs_attention_stream: bad shape");
   DCS_REQUIRE(p->reduced > 0 && p->reduced <= 16, "dcs_attention_stream: reduced must be in [1, 16]");
   cudaStream_t s = (cudaStream_t)stream;
+  if (p->real) {
+    DCS_REQUIRE(p->in_dtype == DCS_F16, "dcs_attention_stream: the real variant is built for fp16 storage (bf16: dcs_real_attention_fwd)");
+    return dispatch_attention_stream<__half, true>(p, s);
+  }
   return p->in_dtype == DCS_F16 ? dispatch_attention_stream<__half>(p, s) : dispatch_attention_stream<__nv_bfloat16>(p, s);
 }

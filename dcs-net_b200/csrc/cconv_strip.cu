@@ -64,7 +64,8 @@ struct StripArgs {
   int f16;                 // operands / output are IEEE half (1) or bf16 (0)
   const float* bias;
   __nv_bfloat16* dst;      // 16-bit storage (either type)
-  long long* pool;         // fixed-point pooled sums (common.cuh: pool_add)
+  long long* pool;         // fixed-point pooled sums (common.cuh: pool_add) or encoded maxima (pool_max)
+  int pool_max;
   dcs_strip_tail tail;  // kTail instances only: decoder[6] + bound_cRM x2 + mask combine epilogue
   // The item table lives in the constant bank (kernel parameters) and the issue loop is fully unrolled (kNdy ring
   // rows x kIpr items per row are template parameters), so every item field is a constant-bank operand of a uniform
@@ -411,7 +412,7 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
       const int sub = (warp - kStripEpi0) >> 2;
       float pool_acc[kChunk];
 #pragma unroll
-      for (int c = 0; c < kChunk; ++c) pool_acc[c] = 0.f;
+      for (int c = 0; c < kChunk; ++c) pool_acc[c] = a.pool_max ? -INFINITY : 0.f;
       for (int j = un.j0; j < un.j1; ++j) {
         mbar_wait(smem_u32(&bars->acc_full[acc]), accp);
         tc_fence_after();
@@ -450,8 +451,13 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
               for (int q = 0; q < 8; ++q) v[q] = sigmoidf_(v[q]);
             }
             if (valid) {
+              if (a.pool_max) {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) pool_acc[8 * s8 + q] += v[q];
+                for (int q = 0; q < 8; ++q) pool_acc[8 * s8 + q] = fmaxf(pool_acc[8 * s8 + q], v[q]);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) pool_acc[8 * s8 + q] += v[q];
+              }
             }
             if (valid) {
               const int c0 = ch * kChunk + 8 * s8, run = c0 >> a.run_log2, off = c0 & (run_len - 1);
@@ -470,7 +476,15 @@ cconv_strip_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_consta
         }
         if (++acc == kStripAcc) { acc = 0; accp ^= 1; }
       }
-      if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
+      if (a.pool && a.pool_max) {   // per-(image, channel) maxima (the real path's AdaptiveMaxPool2d(1))
+#pragma unroll
+        for (int c = 0; c < kChunk; ++c) {
+          float mx = pool_acc[c];
+#pragma unroll
+          for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+          if (lane == 0) pool_max(a.pool + (int64_t)un.b * a.n_real + ((sub * kChunk + c) & (a.n_real - 1)), mx);
+        }
+      } else if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:208, 219)
         if constexpr (kChunk == 32) {
           const float sum = transpose_reduce32(pool_acc, lane);   // pool_acc[c] sums columns c, c + 32 kSub, ... of this warp
           pool_add(a.pool + (int64_t)un.b * a.n_real + ((sub * kChunk + lane) & (a.n_real - 1)), sum);   // chunk sub of the row
@@ -553,6 +567,7 @@ extern "C" int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream) {
   a.row_bytes0 = (uint32_t)P0; a.row_bytes1 = (uint32_t)P1;
   a.n_mma = p->n_mma; a.act = p->act;
   a.f16 = p->dtype == DCS_F16 ? 1 : 0;
+  a.pool_max = p->pool_mode == DCS_POOL_MAX ? 1 : 0;
   a.bias = p->bias; a.dst = reinterpret_cast<__nv_bfloat16*>(p->dst); a.pool = reinterpret_cast<long long*>(p->pool_sums);
   if (tail) a.tail = *tail;
 

@@ -53,7 +53,8 @@ struct TcArgs {
   int8_t dy[DCS_MAX_TAPS], dx[DCS_MAX_TAPS];
   const float* bias;
   void* dst;
-  long long* pool;            // fixed-point pooled sums (common.cuh: pool_add)
+  long long* pool;            // fixed-point pooled sums (common.cuh: pool_add) or encoded maxima (pool_max)
+  int pool_max;
   unsigned long long* dbg;    // optional per-CTA wait-cycle counters (dcs_tc_set_debug_buffer), 8 words per CTA
 };
 
@@ -474,7 +475,29 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
               }
             }
           }
-          if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:219)
+          if (a.pool && a.pool_max) {   // per-(image, channel) maxima: the real path's AdaptiveMaxPool2d(1) (r_network.py:11, 23)
+            if (warp_uniform_image) {
+              if (!valid) {
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = -INFINITY;
+              }
+#pragma unroll
+              for (int off = 16; off >= 1; off >>= 1) {
+                const bool up = (lane & off) != 0;
+#pragma unroll
+                for (int q = 0; q < off; ++q) {
+                  const float send = up ? v[q] : v[q + off];
+                  const float keep = up ? v[q + off] : v[q];
+                  v[q] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, off));
+                }
+              }
+              const int bw = __shfl_sync(0xffffffffu, b, 0);
+              if (lane < nblk && bw < a.batch && n0 + lane < a.n_real) pool_max(a.pool + (int64_t)bw * a.n_real + n0 + lane, v[0]);
+            } else if (valid) {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) if (q < nblk && n0 + q < a.n_real) pool_max(a.pool + (int64_t)b * a.n_real + n0 + q, v[q]);
+            }
+          } else if (a.pool) {  // numerator of the ComplexAdaptiveAvgPool2d(1) that follows (c_network.py:219)
             if (warp_uniform_image) {
               // recursive-halving transpose-reduce: 31 shuffles turn 32 columns x 32 lanes into one column sum per lane
               if (!valid) {
@@ -659,6 +682,7 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   memcpy(a.dx, p->dx, sizeof(a.dx));
   DCS_REQUIRE(p->bias, "dcs_cconv2d_tc_fwd: bias is required (pass zeros)");
   a.bias = p->bias; a.dst = p->dst; a.pool = reinterpret_cast<long long*>(p->pool_sums); a.dbg = g_tc_dbg;
+  a.pool_max = p->pool_mode == DCS_POOL_MAX ? 1 : 0;
 
   const size_t stage_bytes = ((size_t)kTileM * kKStepBytes + (size_t)n_pad * kKStepBytes) * a.kb;
   int n_stages = (int)((200 * 1024) / stage_bytes);

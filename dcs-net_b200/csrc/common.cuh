@@ -131,6 +131,22 @@ __device__ __forceinline__ void pool_add(long long* acc, float partial) {
 __device__ __forceinline__ float pool_mean(const long long* acc, int64_t i, float inv_hw) {
   return __ll2float_rn(acc[i]) * (kPoolInvScale * inv_hw);
 }
+// The same accumulators in MAX mode (the real path's AdaptiveMaxPool2d(1), r_network.py:11,23): a value is stored as its
+// order-preserving unsigned image + 1, so that the memset-zero state means "empty" and atomicMax is exact and
+// order-independent.
+__device__ __forceinline__ unsigned long long pool_max_encode(float v) {
+  const uint32_t b = __float_as_uint(v);
+  return (unsigned long long)((b & 0x80000000u) ? ~b : (b | 0x80000000u)) + 1ull;
+}
+__device__ __forceinline__ void pool_max(long long* acc, float partial) {
+  atomicMax(reinterpret_cast<unsigned long long*>(acc), pool_max_encode(partial));
+}
+__device__ __forceinline__ float pool_max_value(const long long* acc, int64_t i) {
+  const unsigned long long e = (unsigned long long)acc[i];
+  if (e == 0ull) return -INFINITY;
+  const uint32_t o = (uint32_t)(e - 1ull);
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
 
 // Packed fp32x2 FMA (sm_100: FFMA2): acc.{x,y} = a.{x,y} * b.{x,y} + acc.{x,y}, two IEEE fma.rn in ONE issue slot.
 // The CUDA-core kernels here are issue-bound (FFMA + LDS share the schedulers), so halving the FMA instruction count is

@@ -75,7 +75,7 @@ def cbn_apply(x, affine, y=None, act=ACT_NONE, out_dtype=None):
     return y
 
 
-def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
+def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None, pool_max=False):
     """Complex convolution with packed operands `pk` (packing.PackedConv).  src*: (B,H,W,C,2), dst: (B,OH,OW,Cout,2)."""
     L.require_cuda(src0, dst)
     B, H, W, c0, _ = src0.shape
@@ -102,13 +102,13 @@ def cconv(pk, src0, src1, dst, use_tc=False, pool_sums=None):
     p.bias = L.ptr(pk.bias)
     p.act = pk.act
     p.dst, p.in_dtype, p.out_dtype = L.ptr(dst), _code(src0), _code(dst)
-    p.pool_sums = L.ptr(pool_sums)
+    p.pool_sums, p.pool_mode = L.ptr(pool_sums), (L.POOL_MAX if pool_max else L.POOL_SUM)
     fn = L.lib().dcs_cconv2d_tc_fwd if use_tc else L.lib().dcs_cconv2d_fwd
     L.check(fn(C.byref(p), L.stream_ptr()), "dcs_cconv2d_tc_fwd" if use_tc else "dcs_cconv2d_fwd")
     return dst
 
 
-def cconv_strip(sp, src0, src1, dst, pool_sums=None, tail=None, out_hw=None):
+def cconv_strip(sp, src0, src1, dst, pool_sums=None, tail=None, out_hw=None, pool_max=False):
     """Row-strip tensor-core convolution (fp16 / bf16) with operands `sp` (packing.StripConv / StripEnc0 / StripDec6).
     Same tensors as cconv(); with `tail` (a _lib.StripTail, decoder[6] only) dst is None and out_hw = (OH, OW)."""
     L.require_cuda(src0)
@@ -138,7 +138,7 @@ def cconv_strip(sp, src0, src1, dst, pool_sums=None, tail=None, out_hw=None):
     p.bias, p.act = L.ptr(pk.bias), pk.act
     p.dst, p.pool_sums = L.ptr(dst), L.ptr(pool_sums)
     p.tail = C.pointer(tail) if tail is not None else None
-    p.dtype = _code(src0)
+    p.dtype, p.pool_mode = _code(src0), (L.POOL_MAX if pool_max else L.POOL_SUM)
     L.check(L.lib().dcs_cconv2d_strip_fwd(C.byref(p), L.stream_ptr()), "dcs_cconv2d_strip_fwd")
     return dst
 
@@ -224,7 +224,7 @@ def attention_fused(x, sums, ca, w7, y):
     L.require_cuda(x, sums, y)
     B, H, W, Cn, _ = x.shape
     p = L.AttentionParams(L.ptr(x), L.ptr(y), L.ptr(sums), B, H, W, Cn, ca["reduced"], _code(x), _code(y),
-                          L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(w7))
+                          L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(w7), 0)
     L.check(L.lib().dcs_attention_fused(C.byref(p), L.stream_ptr()), "dcs_attention_fused")
     return y
 
@@ -234,9 +234,31 @@ def attention_stream(x, sums, ca, w7, y):
     L.require_cuda(x, sums, y)
     B, H, W, Cn, _ = x.shape
     p = L.AttentionParams(L.ptr(x), L.ptr(y), L.ptr(sums), B, H, W, Cn, ca["reduced"], _code(x), _code(y),
-                          L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(w7))
+                          L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(w7), 0)
     L.check(L.lib().dcs_attention_stream(C.byref(p), L.stream_ptr()), "dcs_attention_stream")
     return y
+
+
+def real_attention_stream(x, maxima, att, w7, y):
+    """Real CBAM (r_network.py:8-40) as the streaming row-ring kernel on a PAIR tensor x (B, H, W, C/2, 2) of 2 * (C/2) real
+    channels, fp16 storage.  maxima (B, C/2, 2) int64: the per-(image, channel) maxima in the conv epilogues' DCS_POOL_MAX
+    encoding; att = dict(w1 (R, C), w2 (C, R)); w7 = conv1.weight flattened (2, 49)."""
+    L.require_cuda(x, maxima, y)
+    B, H, W, Cp, _ = x.shape
+    assert maxima.dtype == torch.int64 and att["w1"].shape[1] == 2 * Cp
+    p = L.AttentionParams(L.ptr(x), L.ptr(y), L.ptr(maxima), B, H, W, Cp, att["w1"].shape[0], _code(x), _code(y),
+                          L.ptr(att["w1"]), None, L.ptr(att["w2"]), None, L.ptr(w7), 1)
+    L.check(L.lib().dcs_attention_stream(C.byref(p), L.stream_ptr()), "dcs_attention_stream")
+    return y
+
+
+def chan_max(x, maxima):
+    """Per-(image, real channel) maxima of a pair tensor into pre-zeroed int64 `maxima` (B, C/2, 2), DCS_POOL_MAX encoding
+    (stand-alone form of the conv epilogues' pool_max; used when the producing kernel could not fuse it)."""
+    L.require_cuda(x, maxima)
+    B, H, W, Cp, _ = x.shape
+    p = L.ChanPoolParams(L.ptr(x), L.ptr(maxima), B, H * W, Cp, _code(x))
+    L.check(L.lib().dcs_chan_max(C.byref(p), L.stream_ptr()), "dcs_chan_max")
 
 
 def real_attention(x, att, w7, y=None, workspace=None):

@@ -15,6 +15,8 @@ channel counts (16, 32, 64, 128, 256, 256, 256 real = 8 ... 128 pairs) give exac
 Modes: 'fp16' (default) / 'bf16' as in engine.py.  (The fp32 <= 1e-5 mode of the real path is R_NETWORK.forward's CUDA-core
 kernel sequence in r_network.py.)
 """
+import os
+
 import torch
 
 from . import _lib as L
@@ -77,6 +79,16 @@ class RealForwardPlan:
                 if t is not None:
                     att_bytes = max(att_bytes, int(L.lib().dcs_real_attention_workspace_bytes(B, t.shape[1], t.shape[2], 2 * t.shape[3])))
         self.att_ws = torch.empty(att_bytes, dtype=torch.uint8, device=dev)
+        # fp16: streaming single-pass attention (attention_stream.cu, REAL variant) fed by per-(image, channel) maxima that
+        # the producing conv's epilogue accumulates (DCS_POOL_MAX); one int64 buffer for all tensors, cleared once per step
+        self.stream_attention = adt == torch.float16 and os.environ.get("DCS_STREAM_ATTENTION", "1") != "0"
+        chans = [t.shape[3] for t in self.enc] + [t.shape[3] for t in self.dec[:-1]]
+        self.pool_all = new(B * 2 * sum(chans), dtype=torch.int64)
+        views, off = [], 0
+        for c in chans:
+            views.append(self.pool_all[off:off + B * c * 2].view(B, c, 2))
+            off += B * c * 2
+        self.pool_enc, self.pool_dec = views[:len(self.enc)], views[len(self.enc):]
         self.clean_spec = new(B, F, T, dtype=torch.complex64)
         self.noise_spec = new(B, F, T, dtype=torch.complex64) if (want_aux and variant == "drs") else None
         self.mask = new(B, F, T, dtype=torch.float32) if want_aux else None
@@ -87,16 +99,25 @@ class RealForwardPlan:
         self.taps = {}
 
     # ------------------------------------------------------------------ building blocks
-    def _attention(self, x, att, y):
-        """y = gate_s * gate_c * x (r_network.py:152-156 / 163-165) on the pair tensor viewed as 2C real channels."""
+    def _attention(self, x, att, y, maxima=None):
+        """y = gate_s * gate_c * x (r_network.py:152-156 / 163-165) on the pair tensor viewed as 2C real channels.
+        `maxima`: the per-channel maxima accumulated by the kernel that produced x (None: the three-pass kernels)."""
         w12, w7 = att
+        if maxima is not None:
+            return ops.real_attention_stream(x, maxima, w12, w7, y)
         return ops.real_attention(x, w12, w7, y=y, workspace=self.att_ws)
 
-    def _conv(self, pk, src0, src1, dst, strip=None):
+    def _conv(self, pk, src0, src1, dst, strip=None, pool=None):
+        """Returns True when the kernel accumulated the channel maxima of dst into `pool`."""
+        pool = pool if self.stream_attention else None
         if strip is not None and src0.shape[2] % pk.stride[1] == 0:
-            return ops.cconv_strip(strip, src0, src1, dst)
+            ops.cconv_strip(strip, src0, src1, dst, pool_sums=pool, pool_max=True)
+            return pool is not None
         use_tc = (2 * pk.cin) % 16 == 0 and pk.w_tc is not None
-        return ops.cconv(pk, src0, src1, dst, use_tc=use_tc)
+        ops.cconv(pk, src0, src1, dst, use_tc=use_tc, pool_sums=pool if use_tc else None, pool_max=True)
+        if pool is not None and not use_tc:
+            ops.chan_max(dst, pool)
+        return pool is not None
 
     def _tap(self, name, t):
         if self.keep_taps:
@@ -107,12 +128,18 @@ class RealForwardPlan:
         """bn0 -> ... -> (d, skip) in front of decoder[6] (r_network.py:128-165)."""
         pk, Lr = self.pk, self.pk.L
         strip0 = pk.strip.get(("enc", 0)) if self.T % 16 == 0 else None
+        if self.stream_attention:
+            ops.zero_(self.pool_all)
         x = self.bn0
+        pooled_e = [False] * Lr
         for i in range(Lr):
             if i == 0 and strip0 is not None:
-                x = ops.cconv_strip(strip0, packing.StripEnc0.view_src(self.bn0), None, self.enc[0])
+                pool = self.pool_enc[0] if self.stream_attention else None
+                ops.cconv_strip(strip0, packing.StripEnc0.view_src(self.bn0), None, self.enc[0], pool_sums=pool, pool_max=True)
+                pooled_e[0] = pool is not None
             else:
-                x = self._conv(pk.enc[i], x, None, self.enc[i], pk.strip.get(("enc", i)) if i else None)
+                pooled_e[i] = self._conv(pk.enc[i], x, None, self.enc[i], pk.strip.get(("enc", i)) if i else None, self.pool_enc[i])
+            x = self.enc[i]
             self._tap(f"enc{i}", x)
         B, H, W, Cp, _ = x.shape
         ops.rlstm_tc(x.view(B, H * W, 2 * Cp), pk.lstm_tc, self.lat.view(B, H * W, -1), self.lstm_ws)   # sequence index = h * W + w
@@ -121,12 +148,13 @@ class RealForwardPlan:
         d = self.fc
         self._tap("fc", d)
         for i in range(Lr):
-            skip = self._attention(self.enc[Lr - 1 - i], pk.skip_att[i], self.skip[i])
+            e = Lr - 1 - i
+            skip = self._attention(self.enc[e], pk.skip_att[i], self.skip[i], self.pool_enc[e] if pooled_e[e] else None)
             self._tap(f"skip{i}", skip)
             if i == Lr - 1:
                 return d, skip      # decoder[6] is fused with the mask tail
-            d = self._conv(pk.dec[i], d, skip, self.dec[i], pk.strip.get(("dec", i)))
-            d = self._attention(d, pk.dec_att[i], self.datt[i])
+            pooled = self._conv(pk.dec[i], d, skip, self.dec[i], pk.strip.get(("dec", i)), self.pool_dec[i])
+            d = self._attention(self.dec[i], pk.dec_att[i], self.datt[i], self.pool_dec[i] if pooled else None)
             self._tap(f"dec{i}", d)
 
     def _tail(self, d_skip):

@@ -35,6 +35,9 @@ enum { DCS_F32 = 0, DCS_BF16 = 1, DCS_F16 = 2 };
 /* Pooled sums (numerators of ComplexAdaptiveAvgPool2d(1): `pool_sums`, `sums`) are 64-bit fixed point, value * 2^28,
  * accumulated with integer atomics so that results are bit-identical from run to run. */
 #define DCS_POOL_FRAC_BITS 28
+/* pool_mode of the conv epilogues: sums (above) or per-(b, channel) MAXIMA (the real path's AdaptiveMaxPool2d(1)), stored as
+ * the order-preserving unsigned image of the float + 1 (0 = empty, so the same memset-zero clear applies). */
+enum { DCS_POOL_SUM = 0, DCS_POOL_MAX = 1 };
 enum { DCS_ACT_NONE = 0, DCS_ACT_RELU = 1, DCS_ACT_LRELU = 2, DCS_ACT_SIGMOID = 3 }; /* ComplexReLU / ComplexLReLU(0.01) / ComplexSigmoid */
 enum { DCS_COMBINE_DCS = 0, DCS_COMBINE_DC = 1,                  /* S = Y - Y*M   |   S = Y*M                (complex masks) */
        DCS_COMBINE_DR = 2, DCS_COMBINE_DRS = 3 };                 /* |S| = |Y| m   |   |S| = |Y| - |Y| m, noisy phase (real masks) */
@@ -124,6 +127,7 @@ typedef struct {
   const void* weight; const float* bias; int act;
   void* dst; int in_dtype; int out_dtype;
   int64_t* pool_sums;
+  int pool_mode;   /* DCS_POOL_SUM / DCS_POOL_MAX (tcgen05 path) */
 } dcs_cconv_params;
 int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream);    /* fp32 CUDA-core path (<=1e-5 mode) */
 int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (fp16 / bf16 / tf32) */
@@ -173,6 +177,7 @@ typedef struct {
   void* dst; int64_t* pool_sums;
   const dcs_strip_tail* tail;   /* NULL: bias + activation + 16-bit store epilogue */
   int dtype;                    /* DCS_F16 or DCS_BF16 */
+  int pool_mode;                /* DCS_POOL_SUM / DCS_POOL_MAX */
 } dcs_cstrip_params;
 int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream);
 
@@ -183,6 +188,8 @@ int dcs_cconv2d_strip_fwd(const dcs_cstrip_params* p, void* stream);
  *      given as separate real/imag fp32 matrices (the conv_r / conv_i 1x1 weights, no bias). */
 typedef struct { const void* x; int64_t* sums; int batch; int hw; int channels; int dtype; } dcs_chan_pool_params;
 int dcs_chan_pool(const dcs_chan_pool_params* p, void* stream);
+/* same arguments; sums[b][c][re/im slot] = maximum over H*W in the DCS_POOL_MAX encoding (pre-zeroed) */
+int dcs_chan_max(const dcs_chan_pool_params* p, void* stream);
 /* mean[i] = sums[i] * 2^-DCS_POOL_FRAC_BITS * inv_hw  (n scalars): the pooled means themselves, i.e. ComplexAdaptiveAvgPool2d(1)
  * / ComplexAdaptiveMaxPool2d(1) called on their own (network_functions.py:114-138) */
 int dcs_pool_mean(const int64_t* sums, float inv_hw, float* mean, int64_t n, void* stream);
@@ -219,6 +226,11 @@ typedef struct {
   const void* x; void* y; const int64_t* sums;
   int batch; int h; int w; int channels; int reduced; int in_dtype; int out_dtype;
   const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i; const float* w7;
+  /* dcs_attention_stream only: real != 0 = the REAL CBAM of r_network.py:8-40 on a pair tensor (channels = C/2 pairs of
+   * real channels): `sums` holds per-channel MAXIMA (DCS_POOL_MAX encoding), w1_r = fc.0.weight (R, C), w2_r = fc.2.weight
+   * (C, R) (w1_i / w2_i unused), w7 = conv1.weight (2, 49); gate_c = sigmoid(W2 relu(W1 max)), statistics (mean_c u, max_c u),
+   * gate_s = sigmoid(conv7x7), y = gate_s * gate_c * x element-wise.  fp16 storage. */
+  int real;
 } dcs_attention_params;
 int dcs_attention_fused(const dcs_attention_params* p, void* stream);
 /* Same contract, 16-bit storage only (tensor-core modes; in_dtype == out_dtype): streaming row-ring form — x read once by bulk copies, the 7x7 gate

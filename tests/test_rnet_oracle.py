@@ -352,3 +352,33 @@ def test_gpu_real_tensor_core_plan_full_size_vs_oracle():
     out_p = enh.enhance_device(noisy[perm].cuda())
     torch.cuda.synchronize()
     assert torch.equal(out_p, full[perm.cuda()])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("Cp,H,W", [(128, 2, 70), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 260), (8, 128, 300), (8, 11, 16)])
+def test_gpu_real_stream_attention_equals_three_pass_kernels(Cp, H, W):
+    """The REAL variant of dcs_attention_stream (max-pool channel gate from DCS_POOL_MAX-encoded maxima, (mean, max)
+    statistics, TF32 mma.sync gate conv, element-wise products) vs dcs_real_attention_fwd (fp32 output) and the oracle's
+    torch functions; every layer geometry, ragged widths; stand-alone dcs_chan_max."""
+    from dcsnet_b200 import ops, packing
+    net = product_net()
+    pk = packing.PackedRNet(net.state_dict(), device="cuda")
+    i = {128: 0, 64: 3, 32: 4, 16: 5, 8: 6}[Cp]
+    att, w7 = pk.skip_att[i]
+    g = torch.Generator().manual_seed(Cp + H + W)
+    B = 3
+    x = torch.randn(B, H, W, Cp, 2, generator=g).to(torch.float16)
+    maxima = torch.zeros(B, Cp, 2, dtype=torch.int64, device="cuda")
+    ops.chan_max(x.cuda(), maxima)
+    ref = ops.real_attention(x.float().cuda(), att, w7)
+    got = torch.full((B, H, W, Cp, 2), float("nan"), dtype=torch.float16, device="cuda")
+    ops.real_attention_stream(x.cuda(), maxima, att, w7, got)
+    torch.cuda.synchronize()
+    assert not torch.isnan(got.float()).any()
+    assert rel_err(got.float().cpu(), ref.cpu()) <= 8e-4          # fp16 output rounding (2^-11) + TF32 gate conv (~1e-4)
+    # and against the oracle's own functions on the same input (NCHW real view of the pair tensor)
+    sd = {k: v.detach() for k, v in net.state_dict().items()}
+    xr = x.float().reshape(B, H, W, 2 * Cp).permute(0, 3, 1, 2)
+    u = xr * RO.channel_attention(xr, sd, f"skip_attention.{2 * i}.")
+    want = (u * RO.spatial_attention(u, sd, f"skip_attention.{2 * i + 1}.")).permute(0, 2, 3, 1).reshape(B, H, W, Cp, 2)
+    assert rel_err(got.float().cpu(), want) <= 8e-4
