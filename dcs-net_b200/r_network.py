@@ -3,13 +3,15 @@ RealSpatialAttention and R_NETWORK(config, hparams, seed) — same constructor s
 order, hence the same 158 state_dict keys / shapes and, for a given seed, bit-identical random-init weights (pinned by
 tests/test_rnet_oracle.py against tests/golden/rnet_*.pt, which were produced by the reference's own r_network.py).
 
-ROUND-1 STATUS: `R_NETWORK.forward` runs in eval mode, fp32, as a sequence of sm_100a kernels (first, un-tuned path):
-the BatchNorm'd magnitude (dcs_cbn_apply), every Conv2d / ConvTranspose2d + BatchNorm2d + activation on the fp32 conv
-kernel through real packing (packing.PackedRNet: real channels 2c, 2c+1 <-> (re, im) of a channel pair; cat + nearest
-up-sampling folded into the decoder GEMMs; the final sigmoid in the last epilogue), the real CBAM (dcs_real_attention_fwd)
-and the real LSTM (dcs_rlstm_fwd).  No ATen / CPU fallback: CPU tensors and train mode raise.  The stand-alone attention
-modules are parameter containers (their forward raises); bf16 / tensor-core mode, CUDA-graph capture and the
-magnitude-mask / iSTFT step are the next steps.
+`R_NETWORK.forward` runs in eval mode in two precisions, selected by the (non-reference) attribute `compute_mode`:
+  'fp32' (default, <= 1e-5): a sequence of sm_100a CUDA-core kernels — the BatchNorm'd magnitude (dcs_cbn_apply), every
+      Conv2d / ConvTranspose2d + BatchNorm2d + activation on the fp32 conv kernel through real packing (packing.PackedRNet:
+      real channels 2c, 2c+1 <-> (re, im) of a channel pair; cat + nearest up-sampling folded into the decoder GEMMs; the
+      final sigmoid in the last epilogue), the real CBAM (dcs_real_attention_fwd) and the real LSTM (dcs_rlstm_fwd);
+  'fp16' / 'bf16' (<= 2e-3): the tensor-core plan of rengine.RealForwardPlan (tcgen05 convs, fp16 mma.sync LSTM, streaming
+      CBAM, fused sigmoid tail).  The audio -> audio hot path with CUDA-graph replay is dcsnet_b200.RealEnhancer.
+No ATen / CPU fallback: CPU tensors and train mode raise.  The stand-alone attention modules are parameter containers (their
+forward raises).
 """
 import torch
 
@@ -87,6 +89,19 @@ class R_NETWORK(_StepMixin, _Base):
             self.decoder_attention.append(RealChannelAttention(out_channels, hp['channel_attention_reduction_ratio']))
             self.decoder_attention.append(RealSpatialAttention(hp['spatial_attention_kernel_size']))
         self.weights_init()
+        self.compute_mode = "fp32"
+        self._plans = {}
+
+    def _tc_plan(self, device, B, Fb, T):
+        from .rengine import PackedRealNet, RealForwardPlan
+        pkey = (str(device), self.compute_mode) + tuple((t.data_ptr(), t._version) for t in list(self.parameters()) + list(self.buffers()))
+        if getattr(self, "_tc_pk_key", None) != pkey:
+            self._tc_pk, self._tc_pk_key = PackedRealNet(self.state_dict(), device, self.compute_mode, self.hparams['no_of_layers']), pkey
+            self._plans = {}
+        key = (B, Fb, T)
+        if key not in self._plans:
+            self._plans[key] = RealForwardPlan(self._tc_pk, B, T, n_bins=Fb, variant="drs")
+        return self._plans[key]
 
     def weights_init(self):
         init = self.hparams['initialisation_distribution']
@@ -106,8 +121,14 @@ class R_NETWORK(_StepMixin, _Base):
             raise NotImplementedError("dcsnet_b200.R_NETWORK: only the eval-mode forward is built (training step: SURVEY 8f rank 2)")
         if not x.is_cuda:
             raise RuntimeError("dcsnet_b200.R_NETWORK.forward needs CUDA tensors (sm_100a); there is no CPU fallback")
-        pk, Lr = self._packed(x.device), self.hparams['no_of_layers']
         B, Fb, T = x.shape
+        if self.compute_mode != "fp32":      # tensor-core plan; the mask does not depend on the phase, so Y = |Y| + 0j serves
+            plan = self._tc_plan(x.device, B, Fb, T)
+            with torch.cuda.device(x.device):
+                plan.Y.copy_(torch.complex(x.float(), torch.zeros_like(x, dtype=torch.float32)))
+                plan._enqueue_from_spec()
+            return torch.squeeze(plan.mask.clone())
+        pk, Lr = self._packed(x.device), self.hparams['no_of_layers']
         new = lambda *s: torch.empty(*s, dtype=torch.float32, device=x.device)   # noqa: E731
         t = torch.zeros(B, Fb, T, 1, 2, dtype=torch.float32, device=x.device)
         t[..., 0, 0].copy_(x)                                     # magnitude in the pair's first slot, 0 in the padding slot

@@ -382,3 +382,17 @@ def test_gpu_real_stream_attention_equals_three_pass_kernels(Cp, H, W):
     u = xr * RO.channel_attention(xr, sd, f"skip_attention.{2 * i}.")
     want = (u * RO.spatial_attention(u, sd, f"skip_attention.{2 * i + 1}.")).permute(0, 2, 3, 1).reshape(B, H, W, Cp, 2)
     assert rel_err(got.float().cpu(), want) <= 8e-4
+
+
+@pytest.mark.gpu
+def test_gpu_rnetwork_forward_tensor_core_mode_matches_reference_golden():
+    """R_NETWORK.forward with compute_mode = 'fp16' (the module-level drop-in call on the tensor-core plan) vs the reference."""
+    g = torch.load(GOLDEN)
+    net = product_net()
+    randomise_bn(net.state_dict(), g["bn_seed"])
+    net = net.cuda().eval()
+    net.compute_mode = "fp16"
+    mask = net(torch.abs(O.stft(g["noisy_audio"])).cuda())
+    torch.cuda.synchronize()
+    assert tuple(mask.shape) == tuple(g["mask"].shape)
+    assert rel_err(mask.cpu(), g["mask"]) <= 2e-3
