@@ -48,6 +48,18 @@ class RlstmTcParams(C.Structure):
                 ("w_ih0", _vp), ("w_ih1", _vp), ("w_hh", _vp), ("bias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class CbnTrainParams(C.Structure):
+    _fields_ = [("x", _vp), ("y", _vp), ("n_pix", _i64), ("channels", _i), ("act", _i), ("in_dtype", _i), ("out_dtype", _i),
+                ("weight", _vp), ("bias", _vp), ("eps", _f), ("momentum", _f),
+                ("running_mean", _vp), ("running_covar", _vp), ("num_batches_tracked", _vp),
+                ("affine", _vp), ("saved", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
+class CbnTrainBwdParams(C.Structure):
+    _fields_ = [("x", _vp), ("dy", _vp), ("dx", _vp), ("n_pix", _i64), ("channels", _i),
+                ("saved", _vp), ("weight", _vp), ("dweight", _vp), ("dbias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 class IstftParams(C.Structure):
     _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
                 ("mag", _vp), ("phase", _vp)]
@@ -157,6 +169,13 @@ SYMBOLS = {
     "dcs_rlstm_fwd": (_i, [C.POINTER(RlstmParams), _vp]),
     "dcs_rlstm_tc_workspace_bytes": (_i64, [_i, _i, _i]),
     "dcs_rlstm_tc_fwd": (_i, [C.POINTER(RlstmTcParams), _vp]),
+    "dcs_cbn_train_workspace_bytes": (_i64, [_i64, _i]),
+    "dcs_cbn_train_fwd": (_i, [C.POINTER(CbnTrainParams), _vp]),
+    "dcs_cbn_train_bwd": (_i, [C.POINTER(CbnTrainBwdParams), _vp]),
+    "dcs_si_snr": (_i, [_vp, _vp, _i, _i, _f, _f, _vp, _vp, _vp]),
+    "dcs_istft_adjoint": (_i, [_vp, _vp, _i, _i, _vp]),
+    "dcs_mask_tail_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _vp]),
+    "dcs_upcat_adjoint": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),

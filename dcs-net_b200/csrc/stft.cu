@@ -123,7 +123,12 @@ struct StftSmem {
   float2 buf[kChunk][kBufPitch];                    // per frame: transpose tile, then Z[0..255]
 };
 
-template <typename TBN>
+// ADJ = true: the ADJOINT of the reference's iSTFT (mag_phase_2_wave's torch.istft, network_functions.py:140-150), i.e. the
+// first backward kernel of the training step (the loss is SI-SNR on waveforms, so every gradient enters through the iSTFT):
+// `audio` is the waveform gradient g (B, 32 (T-1)); it is zero-padded by 256 instead of reflected, divided by the
+// overlap-add envelope sum_t w^2, and the rfft bins 0..255 are kept (the forward put spectrogram row k on rfft bin k), scaled
+// by 2 for bins 1..255 and by 1 with the imaginary part dropped for bin 0 (oracle/train_oracle.istft_adjoint).
+template <typename TBN, bool ADJ = false>
 __global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restrict__ audio, float2* __restrict__ spec,
                                                         int L, int T, int chunks_per_cta,
                                                         const float* __restrict__ bn_affine, TBN* __restrict__ bn_out, int bn_real) {
@@ -147,6 +152,18 @@ __global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restri
     // centre=True reflect padding: sample index s = 32*t + n - 256
     for (int i = tid; i < (kChunk - 1) * kHop + kNfft; i += kThreads) {
       int s = t0 * kHop + i - kNfft / 2;
+      if constexpr (ADJ) {
+        float v = 0.f;
+        if (s >= 0 && s < L) {
+          const int np = s + kNfft / 2;                      // index in the zero-padded signal
+          const int t_hi = min(T - 1, np / kHop), t_lo = max(0, (np - kNfft + kHop) / kHop);
+          float env = 0.f;
+          for (int t = t_lo; t <= t_hi; ++t) { const float w = 0.5f - 0.5f * cospif((float)(np - kHop * t) / 256.f); env += w * w; }
+          v = a[s] / env;
+        }
+        sm.x[i] = v;
+        continue;
+      }
       if (s < 0) s = -s;
       if (s >= L) s = 2 * (L - 1) - s;
       s = max(0, min(s, L - 1));  // frames past T are computed on clamped garbage and never stored
@@ -174,9 +191,12 @@ __global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restri
       if (t < T) {
 #pragma unroll 4
         for (int i = 0; i < 16; ++i) {
-          const int k = 1 + (tid >> 4) + 16 * i;  // output bin 1..256
+          const int k = (ADJ ? 0 : 1) + (tid >> 4) + 16 * i;  // output bin 1..256 (adjoint: 0..255)
           float2 X;
-          if (k < 256) {
+          if (ADJ && k == 0) {
+            const float2 z0 = sm.buf[f][0];
+            X = make_float2(z0.x + z0.y, 0.f);               // DC bin; its imaginary part does not reach the C2R transform
+          } else if (k < 256) {
             const float2 zk = sm.buf[f][k], zm = sm.buf[f][256 - k];
             const float2 E = make_float2(0.5f * (zk.x + zm.x), 0.5f * (zk.y - zm.y));
             const float2 O = make_float2(0.5f * (zk.y + zm.y), -0.5f * (zk.x - zm.x));  // (zk - conj zm)/(2j)
@@ -187,7 +207,8 @@ __global__ void __launch_bounds__(kThreads, 4) stft_kernel(const float* __restri
             X = make_float2(z0.x - z0.y, 0.f);
           }
           X.x *= scale; X.y *= scale;
-          const int64_t o = ((int64_t)b * kBins + (k - 1)) * T + t;
+          if (ADJ && k > 0) { X.x *= 2.f; X.y *= 2.f; }      // both Hermitian halves of bin k
+          const int64_t o = ((int64_t)b * kBins + (ADJ ? k : k - 1)) * T + t;
           spec[o] = X;
           if (bn_out) {
             const float2 Xb = bn_real ? make_float2(hypotf(X.x, X.y), 0.f) : X;   // real path: BatchNorm2d of |Y| (torch.abs = hypot)
@@ -392,6 +413,28 @@ extern "C" int dcs_stft_fwd(const dcs_stft_params* p, void* stream) {
     stft_kernel<float><<<grid, kThreads, smem, s>>>(p->audio, (float2*)p->spec, p->length, p->n_frames, cpc,
                                                     p->bn_affine, (float*)p->bn_out, p->bn_real);
   }
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_istft_adjoint(const float* grad_audio, float* grad_spec, int batch, int n_frames, void* stream) {
+  DCS_REQUIRE(grad_audio && grad_spec && batch > 0 && n_frames >= 2, "dcs_istft_adjoint: bad arguments");
+  const int n_chunks = (n_frames + kChunk - 1) / kChunk;
+  int cpc = 1;
+  {
+    const int64_t slots = 4 * (int64_t)num_sms();
+    int64_t best = INT64_MAX;
+    for (int c = 1; c <= std::min(32, n_chunks); ++c) {
+      const int64_t ctas = (int64_t)((n_chunks + c - 1) / c) * batch;
+      const int64_t cost = ((ctas + slots - 1) / slots) * (c + 1);
+      if (cost < best) { best = cost; cpc = c; }
+    }
+  }
+  dim3 grid((n_chunks + cpc - 1) / cpc, batch);
+  const size_t smem = sizeof(StftSmem);
+  DCS_CUDA(cudaFuncSetAttribute(stft_kernel<float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  stft_kernel<float, true><<<grid, kThreads, smem, (cudaStream_t)stream>>>(grad_audio, (float2*)grad_spec, kHop * (n_frames - 1), n_frames, cpc,
+                                                                           nullptr, nullptr, 0);
   DCS_LAUNCHED();
   return 0;
 }

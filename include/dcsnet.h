@@ -348,6 +348,51 @@ int dcs_real_mask_combine(const float* mag, const float* mask, int64_t mask_stri
 int dcs_upsample_nearest(const void* x, void* y, int batch, int h, int w, int channels, int up_h, int up_w, int dtype,
                          void* stream);
 
+/* ==== f2: first kernels of the TRAINING step (network_functions.py:210-280 train_batch_2_loss,
+ *      168-208 calc_loss; c_network.py:243-261 training_step).  Contracts in closed form: oracle/train_oracle.py. ==== */
+
+/* ---- train-mode ComplexBatchNorm2d forward (complexPyTorch 0.3): batch statistics over n_pix pixels
+ *      per channel (two-stage deterministic double-precision reduction), 2x2 inverse-square-root whitening, affine, optional
+ *      activation; y = A x + c with the per-channel affine written to `affine` (C x 6, the dcs_cbn_apply operand).
+ *      running_mean (C x 2: the complex64 buffer viewed as floats) / running_covar (C x 3) are updated in place with
+ *      `momentum` (unbiased covariance, eps-inclusive diagonal, as the reference accumulates them); num_batches_tracked
+ *      (int64, optional) += 1; saved (C x 8, optional): mean.re, mean.im, Rrr, Rii, Rri, Crr, Cii, Cri for the backward. */
+typedef struct {
+  const void* x; void* y; int64_t n_pix; int channels; int act; int in_dtype; int out_dtype;
+  const float* weight; const float* bias; float eps; float momentum;
+  float* running_mean; float* running_covar; int64_t* num_batches_tracked;
+  float* affine; float* saved; void* workspace; int64_t workspace_bytes;
+} dcs_cbn_train_params;
+int64_t dcs_cbn_train_workspace_bytes(int64_t n_pix, int channels);
+int dcs_cbn_train_fwd(const dcs_cbn_train_params* p, void* stream);
+/* ---- its backward (no activation): x, dy fp32 channels-last complex, `saved` from the forward ->
+ *      dx, dweight (C x 3), dbias (C x 2).  Pass 1 reduces eight per-channel sums, a per-channel 3x3 Jacobian of the whitening
+ *      matrix gives the coefficients of pass 2, dx = P dy + Q x + k. */
+typedef struct {
+  const float* x; const float* dy; float* dx; int64_t n_pix; int channels;
+  const float* saved; const float* weight; float* dweight; float* dbias; void* workspace; int64_t workspace_bytes;
+} dcs_cbn_train_bwd_params;
+int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream);
+
+/* ---- SiSNR (network_functions.py:30-42) per batch row: value[row] = 10 log10(|s_t|^2 / (|e - s_t|^2 + eps) + eps) and
+ *      grad = grad_scale / rows * d value / d estimate (the loss is the batch mean; calc_loss's signs and alpha go into
+ *      grad_scale).  value or grad may be NULL. */
+int dcs_si_snr(const float* clean, const float* estimate, int rows, int length, float eps, float grad_scale, float* value,
+               float* grad, void* stream);
+/* ---- adjoint of mag_phase_2_wave's iSTFT (network_functions.py:140-150): waveform gradient (B, 32 (T-1)) -> spectrogram
+ *      gradient (B, 256, T) complex64 in the dL/dRe + j dL/dIm convention (the STFT kernel in adjoint mode). */
+int dcs_istft_adjoint(const float* grad_audio, float* grad_spec, int batch, int n_frames, void* stream);
+/* ---- adjoint of the fused mask tail (dcs_mask_combine / the dec6 tail): iSTFT-adjoint gradients of the clean (and, dcs,
+ *      noise: g_noise != NULL) waveforms -> gradient w.r.t. decoder[6]'s raw output: polar^T, combine^T (dM = conj(Y) dN),
+ *      bound_cRM^T twice.  n complex elements. */
+int dcs_mask_tail_bwd(const float* net_raw, const float* noisy_spec, const float* g_clean, const float* g_noise, float* d_raw,
+                      int64_t n, float atan2_eps, void* stream);
+/* ---- adjoint of torch.cat((d, skip), 1) + complex_upsample (c_network.py:214-215): g (B, h*up_h, w*up_w, c0 + c1) = the
+ *      conv dgrad of the up-sampled concatenation -> gd (B, h, w, c0), gskip (B, h, w, c1), fp32 channels-last complex.
+ *      (The dgrad itself is dcs_cconv2d_tc_fwd / dcs_cconv2d_fwd with the role-swapped weights of packing.dgrad_conv.) */
+int dcs_upcat_adjoint(const float* g, float* gd, float* gskip, int batch, int h, int w, int c0, int c1, int up_h, int up_w,
+                      void* stream);
+
 /* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */
 int dcs_tc_set_debug_buffer(void* dev_ptr);
 

@@ -1,0 +1,178 @@
+"""GPU (B200): the training-step kernels built so far (include/dcsnet.h section f2, csrc/train.cu, the ADJ
+mode of csrc/stft.cu, dcsnet_b200/train_engine.py) against
+  (i)  tests/golden/train_step.pt — the reference's own `train_batch_2_loss` executed in train mode (losses, BN running
+       statistics after the step), and
+  (ii) the closed-form contracts of oracle/train_oracle.py, each of which is itself checked against autograd on the CPU
+       (tests/test_train_oracle.py).
+Tolerances: fp32 kernels against fp32 / fp64 CPU references, 'rel' = max|a-b| / max|b|.
+"""
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import dcsnet_oracle as O, train_oracle as TO  # noqa: E402
+from conftest import load_golden, rel_err, build_product_net  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def cl(t):       # NCHW complex -> channels-last (B, H, W, C, 2) fp32
+    return torch.view_as_real(t.permute(0, 2, 3, 1).contiguous())
+
+
+def nchw(t):     # channels-last (B, H, W, C, 2) -> NCHW complex
+    return torch.view_as_complex(t.detach().float().cpu().contiguous()).permute(0, 3, 1, 2)
+
+
+def rc(g, *s):
+    return torch.complex(torch.randn(*s, generator=g), torch.randn(*s, generator=g))
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 16, 24), (3, 64, 4, 10), (2, 1, 32, 16)])
+def test_train_mode_complex_batchnorm_forward_and_backward(shape):
+    """dcs_cbn_train_fwd / dcs_cbn_train_bwd vs the oracle's train-mode BN (complexPyTorch semantics) and its closed-form
+    backward: output, running statistics (momentum, unbiased covariance, eps-inclusive diagonal), dx, dweight, dbias."""
+    from dcsnet_b200 import train_ops as T
+    g = torch.Generator().manual_seed(sum(shape))
+    B, C, H, W = shape
+    x = rc(g, *shape) * 0.7 + torch.complex(torch.tensor(0.3), torch.tensor(-0.2))
+    x = torch.complex(x.real + 0.5 * x.imag, x.imag)                     # correlated parts: a non-trivial whitening matrix
+    sd = {"p.weight": torch.rand(C, 3, generator=g) + torch.tensor([0.5, 0.5, -0.5]), "p.bias": torch.randn(C, 2, generator=g),
+          "p.running_mean": rc(g, C) * 0.1, "p.running_covar": torch.rand(C, 3, generator=g) + torch.tensor([1.0, 1.0, -0.5])}
+    stats = {}
+    want = TO.cbn_train(stats)(x, sd, "p.")
+    rm, rcov = sd["p.running_mean"].clone().cuda(), sd["p.running_covar"].clone().cuda()
+    nbt = torch.zeros((), dtype=torch.int64, device="cuda")
+    y, saved, _ = T.cbn_train_fwd(cl(x).cuda(), sd["p.weight"].cuda(), sd["p.bias"].cuda(), rm, rcov, nbt)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(y), want) <= 2e-5
+    assert rel_err(rm, stats["p.running_mean"]) <= 2e-6 and rel_err(rcov, stats["p.running_covar"]) <= 2e-6
+    assert int(nbt) == 1
+    dy = rc(g, *shape)
+    dx_w, dw_w, db_w = TO.cbn_train_backward(x, dy, sd["p.weight"])
+    dx, dw, db = T.cbn_train_bwd(cl(x).cuda(), cl(dy).cuda(), saved, sd["p.weight"].cuda())
+    torch.cuda.synchronize()
+    assert rel_err(nchw(dx), dx_w) <= 5e-5
+    assert rel_err(dw, dw_w) <= 2e-5 and rel_err(db, db_w) <= 2e-5
+    # and with a fused activation the forward equals activation(BN(x))
+    y2, _, _ = T.cbn_train_fwd(cl(x).cuda(), sd["p.weight"].cuda(), sd["p.bias"].cuda(), act=1)
+    assert rel_err(nchw(y2), O.crelu(want)) <= 2e-5
+
+
+@pytest.mark.parametrize("B,T", [(2, 64), (3, 40), (1, 2000)])
+def test_istft_adjoint_kernel(B, T):
+    from dcsnet_b200 import train_ops as T_
+    g = torch.Generator().manual_seed(T)
+    gw = torch.randn(B, 32 * (T - 1), generator=g)
+    want = TO.istft_adjoint(gw, T)
+    got = T_.istft_adjoint(gw.cuda(), T)
+    torch.cuda.synchronize()
+    assert rel_err(got, want) <= 5e-6
+    # adjointness itself, at full size: <g, istft(S)> == Re <adjoint(g), S> for a random S (bin-0 imaginary part is ignored by both)
+    from dcsnet_b200 import ops
+    S = rc(g, B, 256, T)
+    lhs = float((gw.double() * ops.istft(S.cuda(), atan2_eps=0.0, exact_polar=3).cpu().double()).sum())
+    rhs = float((torch.view_as_real(got.cpu()).double() * torch.view_as_real(S).double()).sum())
+    assert abs(lhs - rhs) <= 2e-5 * max(abs(lhs), 1.0)
+
+
+def test_si_snr_value_and_gradient_kernel():
+    from dcsnet_b200 import train_ops as T
+    g = torch.Generator().manual_seed(3)
+    clean = 0.1 * torch.randn(4, 8160, generator=g)
+    est = clean + 0.05 * torch.randn(4, 8160, generator=g)
+    val, grad = T.si_snr(clean.cuda(), est.cuda(), grad_scale=-0.7)
+    torch.cuda.synchronize()
+    assert abs(float(val.mean()) - float(O.si_snr(clean, est))) <= 1e-4
+    assert rel_err(grad, -0.7 * TO.si_snr_backward(clean, est)) <= 2e-5
+
+
+@pytest.mark.parametrize("variant", ["dcs", "dc"])
+def test_mask_tail_backward_kernel(variant):
+    from dcsnet_b200 import train_ops as T
+    g = torch.Generator().manual_seed(5)
+    B, T_ = 2, 40
+    raw, Y = rc(g, B, 256, T_) * 0.8, rc(g, B, 256, T_)
+    gc, gn = torch.randn(B, 32 * (T_ - 1), generator=g), torch.randn(B, 32 * (T_ - 1), generator=g)
+    want = TO.mask_tail_backward(raw, Y, gc, gn if variant == "dcs" else None)
+    gS = T.istft_adjoint(gc.cuda(), T_)
+    gN = T.istft_adjoint(gn.cuda(), T_) if variant == "dcs" else None
+    got = T.mask_tail_bwd(raw.cuda(), Y.cuda(), gS, gN)
+    torch.cuda.synchronize()
+    assert rel_err(got, want) <= 5e-5
+
+
+@pytest.mark.parametrize("cd,cs,cout,up,mode", [(8, 8, 1, (2, 2), "fp32"), (16, 16, 8, (2, 2), "fp32"), (64, 64, 32, (2, 1), "fp32"),
+                                                (64, 64, 32, (2, 1), "fp16"), (128, 128, 64, (2, 1), "fp16")])
+def test_decoder_stage_dgrad_on_the_forward_conv_kernels(cd, cs, cout, up, mode):
+    """The data gradient of cat + nearest up-sampling + ComplexConvTranspose2d(k3 s1 p1): the forward conv kernel (FFMA, or
+    tcgen05 kind::f16 in the tensor-core mode) with role-swapped weights (train_ops.dgrad_conv), then dcs_upcat_adjoint —
+    against oracle/train_oracle.decoder_stage_backward (itself equal to autograd)."""
+    from dcsnet_b200 import ops, train_ops as T
+    g = torch.Generator().manual_seed(cd + cout)
+    B, H, W = 2, 6, 20
+    d, skip = rc(g, B, cd, H, W), rc(g, B, cs, H, W)
+    w_r, w_i = 0.1 * torch.randn(cd + cs, cout, 3, 3, generator=g), 0.1 * torch.randn(cd + cs, cout, 3, 3, generator=g)
+    dy = rc(g, B, cout, H * up[0], W * up[1])
+    gd_w, gs_w = TO.decoder_stage_backward(d, skip, w_r, w_i, dy, up)[:2]
+    dt = {"fp32": None, "fp16": torch.float16}[mode]
+    pk = T.dgrad_conv(w_r, w_i, transposed=True, device="cuda", tc_dtype=dt)
+    dyc = cl(dy).cuda()
+    if dt is not None:
+        dyc = dyc.to(dt)
+    g_up = torch.empty(B, H * up[0], W * up[1], cd + cs, 2, dtype=torch.float32, device="cuda")
+    ops.cconv(pk, dyc, None, g_up, use_tc=dt is not None)
+    gd, gs = T.upcat_adjoint(g_up, cd, cs, up)
+    torch.cuda.synchronize()
+    tol = 2e-5 if dt is None else 2e-3
+    assert rel_err(nchw(gd), gd_w) <= tol and rel_err(nchw(gs), gs_w) <= tol
+
+
+def test_train_mode_forward_reproduces_reference_losses_and_running_stats():
+    """TrainStep.forward (train-mode C_NETWORK.forward with batch-statistic BN at all 15 BatchNorms + calc_loss, all on the GPU)
+    against what the REFERENCE's own train_batch_2_loss produced (tests/golden/train_step.pt): the three losses and the
+    running statistics of every BatchNorm after the step; then the first backward stage against the oracle's closed forms
+    evaluated on the saved forward tensors."""
+    import dcsnet_b200 as D
+    from dcsnet_b200 import config as cfg, c_network, train_engine
+    g = load_golden("train_step.pt")
+    w = g["dcs"]
+    hp = dict(cfg.hparams)
+    hp["dropout_conv"], hp["dropout_fc"] = 0.0, 0.0
+    net = c_network.C_NETWORK(cfg.config, hp, 0).cuda()
+    clean, noise, noisy = O.synthetic_audio(g["B"], 32 * (g["T"] - 1), seed=g["audio_seed"])
+    step = train_engine.TrainStep(net, "dcs")
+    n0 = D._lib.launch_count()
+    out = step.forward(O.stft(noise).cuda(), O.stft(noisy).cuda(), O.stft(clean).cuda())
+    torch.cuda.synchronize()
+    assert D._lib.launch_count() - n0 > 100
+    for k in ("noise_loss", "speech_loss", "train_loss"):
+        assert abs(float(out[k]) - w[k]) <= 2e-4, (k, float(out[k]), w[k])
+    sd = net.state_dict()
+    for k, f in w["running_stats"].items():
+        t = sd[k]
+        t = torch.view_as_real(t) if t.is_complex() else t
+        t = t.float().cpu()
+        assert tuple(t.shape) == f["shape"], k
+        assert abs(float(t.norm()) - f["norm"]) <= 2e-4 * f["norm"] + 1e-7, k
+        assert float((t.reshape(-1)[:8] - f["head"]).abs().max()) <= 2e-4 * f["max_abs"] + 1e-7, k
+    assert all(int(v) == 1 for k, v in sd.items() if k.endswith("num_batches_tracked"))
+    # ---- first backward stage vs the closed forms on the saved tensors
+    b = step.backward_first_stage()
+    torch.cuda.synchronize()
+    sv = step.saved
+    gc_w, gn_w = TO.loss_backward(sv["clean_audio"].cpu(), sv["est_clean_audio"].cpu(), sv["noise_audio"].cpu(), sv["est_noise_audio"].cpu())
+    assert rel_err(b["g_clean_wave"], gc_w) <= 5e-5 and rel_err(b["g_noise_wave"], gn_w) <= 5e-5
+    d_raw_w = TO.mask_tail_backward(sv["raw"].cpu(), sv["Y"].cpu(), gc_w, gn_w)
+    assert rel_err(b["d_raw"], d_raw_w) <= 1e-4
+    d5, skip6 = nchw(sv["d5"]), nchw(sv["skip6"])
+    sdc = {k: v.detach().cpu() for k, v in sd.items()}
+    gd_w, gs_w = TO.decoder_stage_backward(d5, skip6, sdc["decoder.6.conv_tran_r.weight"], sdc["decoder.6.conv_tran_i.weight"],
+                                           d_raw_w[:, None], (2, 2))[:2]
+    assert rel_err(nchw(b["g_d5"]), gd_w) <= 1e-4 and rel_err(nchw(b["g_skip6"]), gs_w) <= 1e-4
+    assert math.isfinite(float(b["g_d5"].abs().sum()))
