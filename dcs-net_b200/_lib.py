@@ -60,6 +60,13 @@ class CbnTrainBwdParams(C.Structure):
                 ("saved", _vp), ("weight", _vp), ("dweight", _vp), ("dbias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class CwgradParams(C.Structure):
+    _fields_ = [("x", _vp), ("dy", _vp), ("dtype", _i),
+                ("batch", _i), ("in_h", _i), ("in_w", _i), ("out_h", _i), ("out_w", _i), ("cin", _i), ("cout", _i),
+                ("stride_h", _i), ("stride_w", _i), ("ntaps", _i), ("dy_off", C.c_int8 * MAX_TAPS), ("dx_off", C.c_int8 * MAX_TAPS),
+                ("dw_r", _vp), ("dw_i", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 class IstftParams(C.Structure):
     _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
                 ("mag", _vp), ("phase", _vp)]
@@ -176,6 +183,8 @@ SYMBOLS = {
     "dcs_istft_adjoint": (_i, [_vp, _vp, _i, _i, _vp]),
     "dcs_mask_tail_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _vp]),
     "dcs_upcat_adjoint": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_cwgrad_workspace_bytes": (_i64, [C.POINTER(CwgradParams)]),
+    "dcs_cwgrad_tc": (_i, [C.POINTER(CwgradParams), _vp]),
     "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),

@@ -133,3 +133,29 @@ def dgrad_conv(w_r, w_i, transposed, device, tc_dtype=None, want_tf32=False):
         # forward: y = conv(x, W) with W (Cout, Cin, k, k); adjoint: dx = convT(dy, W) = conv(dy, flip(W^T))
         wr, wi = w_r.permute(1, 0, 2, 3).flip(2, 3), -w_i.permute(1, 0, 2, 3).flip(2, 3)
     return packing.PackedConv(wr, wi, None, None, device=device, tc_dtype=tc_dtype, want_tf32=want_tf32)
+
+
+@ops._on_tensor_device
+def cwgrad(x, dy, kernel, stride):
+    """Weight gradient of ComplexConv2d(cin -> cout, kernel, stride, padding = kernel // 2) on the tensor cores: x (B, H, W, cin, 2),
+    dy (B, OH, OW, cout, 2) in the same 16-bit storage type -> (dw_r, dw_i) fp32 (cout, cin, kh, kw) = conv_r / conv_i .weight.grad."""
+    L.require_cuda(x, dy)
+    kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
+    B, H, W, cin, _ = x.shape
+    _, OH, OW, cout, _ = dy.shape
+    assert x.dtype in ops.H16 and dy.dtype == x.dtype and x.is_contiguous() and dy.is_contiguous()
+    p = L.CwgradParams()
+    p.x, p.dy, p.dtype = L.ptr(x), L.ptr(dy), L.dtype_code(x)
+    p.batch, p.in_h, p.in_w, p.out_h, p.out_w, p.cin, p.cout = B, H, W, OH, OW, cin, cout
+    p.stride_h, p.stride_w = stride
+    p.ntaps = kh * kw
+    for ky in range(kh):
+        for kx in range(kw):
+            p.dy_off[ky * kw + kx], p.dx_off[ky * kw + kx] = ky - kh // 2, kx - kw // 2
+    dw_r = torch.empty(cout, cin, kh, kw, dtype=torch.float32, device=x.device)
+    dw_i = torch.empty_like(dw_r)
+    n = int(L.lib().dcs_cwgrad_workspace_bytes(C.byref(p)))
+    ws = torch.empty(max(n, 16), dtype=torch.uint8, device=x.device)
+    p.dw_r, p.dw_i, p.workspace, p.workspace_bytes = L.ptr(dw_r), L.ptr(dw_i), L.ptr(ws), ws.numel()
+    L.check(L.lib().dcs_cwgrad_tc(C.byref(p), L.stream_ptr()), "dcs_cwgrad_tc")
+    return dw_r, dw_i

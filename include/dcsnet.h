@@ -393,6 +393,21 @@ int dcs_mask_tail_bwd(const float* net_raw, const float* noisy_spec, const float
 int dcs_upcat_adjoint(const float* g, float* gd, float* gskip, int batch, int h, int w, int c0, int c1, int up_h, int up_w,
                       void* stream);
 
+/* ---- weight gradient of ComplexConv2d on the tensor cores (csrc/wgrad_tc.cu; oracle/train_oracle.cconv2d_backward):
+ *      x (B, in_h, in_w, cin) and dy (B, out_h, out_w, cout) channels-last complex in 16-bit storage `dtype`;
+ *      dWp[n][tap][k] = sum_pixels dy[pix][n] x[pix * stride + off(tap)][k] as ONE tcgen05 GEMM with K = pixels (both operands
+ *      MN-major straight from the activations' layout, TMA-staged, zero padding by out-of-bounds fill), split over K and folded:
+ *      dw_r, dw_i fp32 (cout, cin, ntaps) = the reference's conv_r.weight.grad / conv_i.weight.grad with tap = ky*kw + kx,
+ *      offsets dy_off[tap] = ky - pad_h, dx_off[tap] = kx - pad_w.  Needs 2*cout % 128 == 0, 2*cin in {64, 128, 192, 256}. */
+typedef struct {
+  const void* x; const void* dy; int dtype;
+  int batch; int in_h; int in_w; int out_h; int out_w; int cin; int cout; int stride_h; int stride_w;
+  int ntaps; int8_t dy_off[DCS_MAX_TAPS]; int8_t dx_off[DCS_MAX_TAPS];
+  float* dw_r; float* dw_i; void* workspace; int64_t workspace_bytes;
+} dcs_cwgrad_params;
+int64_t dcs_cwgrad_workspace_bytes(const dcs_cwgrad_params* p);
+int dcs_cwgrad_tc(const dcs_cwgrad_params* p, void* stream);
+
 /* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */
 int dcs_tc_set_debug_buffer(void* dev_ptr);
 

@@ -176,3 +176,22 @@ def test_train_mode_forward_reproduces_reference_losses_and_running_stats():
                                            d_raw_w[:, None], (2, 2))[:2]
     assert rel_err(nchw(b["g_d5"]), gd_w) <= 1e-4 and rel_err(nchw(b["g_skip6"]), gs_w) <= 1e-4
     assert math.isfinite(float(b["g_d5"].abs().sum()))
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,B,H,W", [(64, 128, 3, (2, 1), 2, 16, 70), (32, 64, 5, (2, 1), 3, 8, 130), (128, 128, 3, (2, 1), 2, 8, 64),
+                                                     (64, 64, 3, (1, 1), 2, 6, 33)])
+def test_conv_wgrad_on_tcgen05(cin, cout, k, stride, B, H, W):
+    """dcs_cwgrad_tc (one tcgen05 GEMM with K = pixels, MN-major operands straight from the channels-last activations, split-K +
+    fold) vs oracle/train_oracle.cconv2d_backward (= autograd) on the same fp16-rounded activations: encoder[3..6]-like shapes,
+    strides, ragged rows."""
+    from dcsnet_b200 import train_ops as T
+    g = torch.Generator().manual_seed(cin + cout + k)
+    h16 = lambda t: torch.complex(t.real.half().float(), t.imag.half().float())   # noqa: E731
+    x = h16(rc(g, B, cin, H, W))
+    OH, OW = (H + 2 * (k // 2) - k) // stride[0] + 1, (W + 2 * (k // 2) - k) // stride[1] + 1
+    dy = h16(rc(g, B, cout, OH, OW) * 0.1)
+    w_r, w_i = torch.zeros(cout, cin, k, k), torch.zeros(cout, cin, k, k)
+    _, dwr_w, dwi_w, _, _ = TO.cconv2d_backward(x, w_r, w_i, dy, stride, k // 2)
+    dwr, dwi = T.cwgrad(cl(x).cuda().half(), cl(dy).cuda().half(), k, stride)
+    torch.cuda.synchronize()
+    assert rel_err(dwr, dwr_w) <= 2e-5 and rel_err(dwi, dwi_w) <= 2e-5
