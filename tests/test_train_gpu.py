@@ -195,3 +195,19 @@ def test_conv_wgrad_on_tcgen05(cin, cout, k, stride, B, H, W):
     dwr, dwi = T.cwgrad(cl(x).cuda().half(), cl(dy).cuda().half(), k, stride)
     torch.cuda.synchronize()
     assert rel_err(dwr, dwr_w) <= 2e-5 and rel_err(dwi, dwi_w) <= 2e-5
+
+
+def test_two_gpu_nccl_gradient_all_reduce():
+    """SURVEY 8e (training-step row): GradBuckets over NCCL on two GPUs — one process per GPU (torchrun), each running the GPU
+    train-mode forward + first backward stage on its own shard, then the flat-bucket all-reduce (first bucket asynchronous), the
+    mean and the global-norm clip, checked against the closed form (tools/nccl_grad_sync.py)."""
+    import json
+    import subprocess
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run with gpurun --gpus 2)")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(ROOT, "tools", "nccl_grad_sync.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["backend"] == "nccl" and line["world"] == 2 and line["numel"] == 2912707 and line["ok"], line
+    assert abs(line["train_loss_per_rank"][0] - line["train_loss_per_rank"][1]) > 1e-3      # the ranks did work on different shards
