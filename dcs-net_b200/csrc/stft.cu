@@ -82,13 +82,16 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
 }
 
 // 256-point complex DFT by one half-warp.  In: lane l holds v[r] = z[16*r + l].  Out: v[k2] = Z[l + 16*k2].
-// tr: this half-warp's private 16 x kTrStride float2 tile.  tw256[i] = (cos, sin)(2*pi*i/256).
+// tr: this half-warp's private 16 x kTrStride float2 tile.  tw256[k1 * 16 + l] = (cos, sin)(2*pi*l*k1/256): the inter-stage
+// twiddles stored in the order the lanes read them (consecutive lanes -> consecutive words; the natural table indexed by
+// (l * k1) & 255 put the 16 lanes 2 / 4 / 8 words apart for even k1: 2- to 8-way bank conflicts, 3.7 M per launch in the
+// r03a profile).
 template <bool INV>
 __device__ __forceinline__ void fft256_halfwarp(float2 (&v)[16], int l, float2* tr, const float2* tw256) {
   fft16<INV>(v);
 #pragma unroll
   for (int k1 = 0; k1 < 16; ++k1) {
-    const float2 w = tw256[(l * k1) & 255];
+    const float2 w = tw256[k1 * 16 + l];
     const float c = w.x, s = INV ? w.y : -w.y;
     float2 t = v[k1];
     tr[k1 * kTrStride + l] = make_float2(t.x * c - t.y * s, t.x * s + t.y * c);
@@ -109,7 +112,7 @@ struct FftTables {
 __device__ __forceinline__ void init_tables(FftTables* t) {
   for (int i = threadIdx.x; i < 256; i += blockDim.x) {
     float s, c;
-    sincospif((float)i / 128.f, &s, &c);
+    sincospif((float)(((i & 15) * (i >> 4)) & 255) / 128.f, &s, &c);   // entry [k1 = i >> 4][l = i & 15] = w256^(l k1)
     t->tw256[i] = make_float2(c, s);
     sincospif((float)i / 256.f, &s, &c);
     t->tw512[i] = make_float2(c, s);
