@@ -115,7 +115,32 @@ class _StepMixin:
         return {'optimizer': optimiser, 'lr_scheduler': lr_scheduler, 'monitor': 'val_loss' if self._two_mask() else 'speech_loss'}
 
     def training_step(self, train_batch, batch_idx):
-        raise NotImplementedError("dcsnet_b200: the training step (backward kernels) is SURVEY 8f rank 2 and not built yet")
+        """c_network.py:243-261: `train_batch_2_loss` in TRAIN mode (batch-statistic BatchNorm with the running-stat update) and
+        the metrics dict, on the GPU through train_engine.TrainStep (complex variants; dropout probabilities must be 0).  Returns
+        the loss as a device scalar WITHOUT a grad_fn: the backward pass is `self.train_step.backward_first_stage()` so far
+        (the remaining backward kernels and the optimizer step are not built), so a Lightning-style
+        `loss.backward()` on it is not possible."""
+        from .network_functions import _variant
+        variant = _variant(self, self.variant)
+        if self._step_dtype != "complex":
+            raise NotImplementedError("dcsnet_b200: the real path's training step is not built (SURVEY 8f rank 2)")
+        from .train_engine import TrainStep
+        if getattr(self, "train_step", None) is None or self.train_step.variant != variant:
+            object.__setattr__(self, "train_step", TrainStep(self, variant, speech_alpha=self.hparams["speech_alpha"],
+                                                             atan2_eps=self.hparams["atan2_eps"]))
+        noise_data, noisy_data, clean_data = train_batch[0], train_batch[1], train_batch[2]
+        out = self.train_step.forward(noise_data, noisy_data, clean_data)
+        if variant == "dcs":
+            metrics = {'train_loss': out["train_loss"].detach(), 'noise_loss': out["noise_loss"].detach(), 'speech_loss': out["speech_loss"].detach()}
+            loss = out["train_loss"]
+        else:
+            metrics = {'speech_loss': out["speech_loss"].detach()}
+            loss = out["speech_loss"]
+        self.log_dict(metrics, on_epoch=True)
+        if torch.any(torch.isnan(loss)):
+            print("found NaN in C train loss!")
+            return None
+        return loss
 
     @staticmethod
     def _audio_dict(clean, predict_clean, noise, noisy, predict_noise=None):

@@ -211,3 +211,21 @@ def test_two_gpu_nccl_gradient_all_reduce():
     line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
     assert line["backend"] == "nccl" and line["world"] == 2 and line["numel"] == 2912707 and line["ok"], line
     assert abs(line["train_loss_per_rank"][0] - line["train_loss_per_rank"][1]) > 1e-3      # the ranks did work on different shards
+
+
+@pytest.mark.parametrize("script,args", [("test.py", ["dcs", "0", "--batches", "2", "--frames", "64"]),
+                                         ("test.py", ["drs", "0", "--batches", "2", "--frames", "64", "--mode", "fp16"]),
+                                         ("train.py", ["dcs", "0", "--steps", "2", "--batch", "2", "--frames", "64"])])
+def test_entry_point_shims_honour_the_reference_command_line(script, args):
+    """`python test.py|train.py [dcs|drs|dc|dr] <gpu>` (the reference's entry points, test.py:17-91, train.py:108-152)."""
+    import json
+    import subprocess
+    r = subprocess.run([sys.executable, os.path.join(ROOT, script)] + args, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    assert line["variant"] == args[0] and line["gpu"] == 0
+    if script == "test.py":
+        assert line["batches"] == 2 and all(math.isfinite(v) or v != v for v in line["metrics"].values())
+        assert any(k.endswith("speech_loss") for k in line["metrics"])
+    else:
+        assert len(line["steps"]) == 2 and all(math.isfinite(s["loss"]) and s["g_d5_norm"] > 0 for s in line["steps"]) and line["optimizer_step"] is False
