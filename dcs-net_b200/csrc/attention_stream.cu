@@ -20,6 +20,8 @@
 //   * output row r - 3: gate_s * gate_c * x from the ring -> HBM (16-byte stores).
 // HBM traffic: x once in, y once out.  fp32 mode keeps the exact CUDA-core kernels (TF32 products would break 1e-5).
 #include "tc_ptx.cuh"
+#include <stdlib.h>
+#include <type_traits>
 
 namespace dcs {
 
@@ -415,6 +417,271 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Whole-strip ("tile") kernel for the SHORT, WIDE-CHANNEL tensors (C >= 32 pairs: H * C <= 1024, i.e. encoder[2..6] outputs
+// and decoder[0..3] outputs: 32 x 250 x 32 ... 2 x 250 x 128 per image).  The row-streaming kernel above walks down the rows
+// with three CTA barriers per row pair and ONE warp on the gate conv of a 16-pixel strip; on these tensors (2 ... 32 rows)
+// it is bound by the fill / drain latency of that pipeline (58-70 us for a 65 MB tensor = 1 TB/s).  Here a full-height column
+// strip of 16 pixels (+3 halo each side) is ONE shared-memory tile (H * 22 * C * 4 B <= 88 KB, 2 CTAs per SM), every row
+// arrives by its own bulk copy, and the CTA runs three flat phases separated by two barriers:
+//   1. statistics of all H x 22 pixels (threads own a fixed vector subset of a pixel; conflict-free rotated reads),
+//      written as fp16 (mean.re, mean.im, max.re, max.im) — the same 11-bit significand as the streaming kernel's tf32;
+//   2. the 7x7 gate conv of FOUR output rows x 16 pixels per warp as 20 mma.sync.m16n8k16 (fp16, fp32 accumulate):
+//      M = 16 pixels, N = (output row j = 0..3, re / im), K = (statistics row y' = 0..9, kx = 0..7, ci = 0..3); the A
+//      fragment is the statistics tile itself read as a sliding window (A[m][(y', kx, ci)] = st[r0 + y'][m + kx][ci], four
+//      conflict-free LDS.32 per MMA, no im2col), B = the taps shifted by the output row, W[y' - j][kx][ci][o];
+//   3. y = gate_s * (gate_c * x) for the H x 16 strip pixels, 16-byte loads / stores, consecutive lanes on consecutive
+//      addresses.
+constexpr int kAtTW = 16, kAtPW = kAtTW + 6, kAtStPitch = 24, kAtThreads = 256;
+
+__device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <int C, bool REAL>
+__global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const AttStreamArgs a) {
+  using T = __half;
+  constexpr int PW = kAtPW, TW = kAtTW;
+  constexpr int VPP = C / 4;                  // 16-byte vectors per pixel
+  constexpr int G = C / 16;                   // lanes per pixel in the statistics phase (4 vectors per lane)
+  constexpr int PPI = kAtThreads / G;         // pixels per statistics iteration (a multiple of 4: the read rotation is per thread)
+  constexpr int QS = kAtThreads / VPP;        // output pixels per product iteration
+  constexpr int NW7 = REAL ? 98 : 196;
+  static_assert(G >= 2 && G <= 8 && VPP * 4 == C, "tile attention: C = 32, 64 or 128");
+
+  extern __shared__ __align__(128) unsigned char as_smem[];
+  const int H = a.H, W = a.W;
+  const int HP = (H + 3) & ~3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.y, x0 = blockIdx.x * TW;
+  unsigned char* xs = as_smem;                                                         // [H][PW][C] complex fp16
+  uint2* st = reinterpret_cast<uint2*>(xs + (size_t)H * PW * C * 4);                    // [HP + 6][24] 4 x fp16 statistics
+  float2* sg = reinterpret_cast<float2*>(st + (size_t)(HP + 6) * kAtStPitch);            // [HP][16] spatial gate
+  float2* gs = sg + HP * TW;                                                           // [C] channel gate
+  float2* avg = gs + C;                                                                // [C]
+  float2* hid = avg + C;                                                               // [16]
+  float* w7s = reinterpret_cast<float*>(hid + 16);                                     // [196]
+  uint2* bt = reinterpret_cast<uint2*>(w7s + 196);                                     // [20][32] B fragments of the gate conv
+  uint64_t* full = reinterpret_cast<uint64_t*>(bt + 20 * 32);                          // [4] one per group of RG rows
+  const uint32_t xs_u32 = smem_u32(xs), st_u32 = smem_u32(st), full_u32 = smem_u32(full);
+  const int RG = (H + 3) >> 2;                                                         // rows per arrival group (<= 4 groups)
+
+  // ---- rows -> shared memory (one bulk copy per row: the strip's columns are contiguous in the channels-last layout)
+  const int xa = max(x0 - 3, 0), xe = min(x0 + TW + 3, W);
+  const uint32_t seg_bytes = (uint32_t)(xe - xa) * C * 4;
+  const uint32_t seg_off = (uint32_t)(xa - (x0 - 3)) * C * 4;
+  if (tid < 4) {
+    mbar_init(full_u32 + 8 * tid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < H) {
+    const int grp = tid / RG;
+    const uint32_t bar = full_u32 + 8 * grp;
+    if (tid == grp * RG) mbar_expect_tx(bar, (uint32_t)(min(RG, H - grp * RG)) * seg_bytes);   // one arrival per group; the copies may land in any order
+    bulk_g2s(xs_u32 + (uint32_t)tid * (PW * C * 4) + seg_off,
+             reinterpret_cast<const T*>(a.x) + (((int64_t)b * H + tid) * W + xa) * C * 2, seg_bytes, bar);
+  }
+  for (int i = tid; i < (HP + 6) * kAtStPitch; i += kAtThreads) st[i] = make_uint2(0u, 0u);
+  for (int i = tid; i < NW7; i += kAtThreads) w7s[i] = a.w7[i];
+  for (int c = tid; c < C; c += kAtThreads) {
+    if constexpr (REAL) avg[c] = make_float2(pool_max_value(a.sums, ((int64_t)b * C + c) * 2), pool_max_value(a.sums, ((int64_t)b * C + c) * 2 + 1));
+    else avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
+  }
+  __syncthreads();
+
+  // ---- B fragments of the gate conv (phase 2), one (b0, b1) pair per (k-step, lane): k-step ks = (statistics row y' = ks / 2,
+  //      kx half s = ks % 2); lane (g, t): column n = g = (output row j = g / 2, part o = g % 2), k pair (2 t, 2 t + 1) [+ 8]
+  //      -> kx = 4 s + t / 2 [+ 2], ci = 2 (t % 2), 2 (t % 2) + 1 = (re, im) of statistics input t % 2; tap row ky = y' - j.
+  for (int e = tid; e < 20 * 32; e += kAtThreads) {
+    const int ks = e >> 5, ln = e & 31, gg = ln >> 2, tt = ln & 3;
+    const int ky = (ks >> 1) - (gg >> 1), o = gg & 1, cp = tt & 1;
+    uint32_t bfr[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int kx = 4 * (ks & 1) + 2 * h2 + (tt >> 1);
+      float v0 = 0.f, v1 = 0.f;
+      if (ky >= 0 && ky < 7 && kx < 7) {
+        if constexpr (REAL) {                 // Conv2d(2, 1, 7): ci = (mean, max, -, -), one real output (o = 0)
+          if (o == 0 && cp == 0) { v0 = w7s[ky * 7 + kx]; v1 = w7s[49 + ky * 7 + kx]; }
+        } else {
+          const float wr = w7s[cp * 49 + ky * 7 + kx], wi = w7s[98 + cp * 49 + ky * 7 + kx];
+          v0 = o == 0 ? wr : wi; v1 = o == 0 ? -wi : wr;
+        }
+      }
+      bfr[h2] = pack_f16x2(v0, v1);
+    }
+    bt[e] = make_uint2(bfr[0], bfr[1]);
+  }
+
+  // ---- channel gate (same arithmetic as the streaming kernel; all loads of a pass in flight together)
+  for (int r = warp; r < a.R; r += kAtThreads / 32) {
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int c = lane; c < C; c += 32) {
+      if constexpr (REAL) {
+        re += a.w1_r[r * 2 * C + 2 * c] * avg[c].x + a.w1_r[r * 2 * C + 2 * c + 1] * avg[c].y;
+      } else {
+        const float wr = a.w1_r[r * C + c], wi = a.w1_i[r * C + c];
+        re += wr * avg[c].x - wi * avg[c].y;
+        im += wr * avg[c].y + wi * avg[c].x;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+    if (lane == 0) hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+  }
+  __syncthreads();
+  if (tid < C) {
+    const int c = tid;
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r < a.R) {
+        if constexpr (REAL) {
+          re += a.w2_r[(2 * c) * a.R + r] * hid[r].x;
+          im += a.w2_r[(2 * c + 1) * a.R + r] * hid[r].x;
+        } else {
+          const float wr = a.w2_r[c * a.R + r], wi = a.w2_i[c * a.R + r];
+          re += wr * hid[r].x - wi * hid[r].y;
+          im += wr * hid[r].y + wi * hid[r].x;
+        }
+      }
+    }
+    gs[c] = REAL ? make_float2(sigmoidf_(re), sigmoidf_(im)) : make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
+  }
+  __syncthreads();
+
+  // ---- 1. statistics: thread = (pixel f0 + j PPI, vectors sub + G ((k + rot) & 3)); the rotation spreads the lanes of a
+  //         quarter warp over all 32 banks (pixels are 128 / 256 / 512 bytes apart)
+  {
+    const int sub = tid % G, f0 = tid / G, rot = f0 & 3;
+    GPair sgate[4][2];
+    uint32_t voff[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int vi = sub + G * ((k + rot) & 3);
+      voff[k] = (uint32_t)vi * 16;
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        const float2 ga = gs[vi * 4 + 2 * h2], gb = gs[vi * 4 + 2 * h2 + 1];
+        sgate[k][h2].re = make_float2(ga.x, gb.x); sgate[k][h2].im = make_float2(ga.y, gb.y);
+        sgate[k][h2].nim = make_float2(-ga.y, -gb.y);
+      }
+    }
+    const int npix = H * PW;
+    const float invC = 1.f / (float)C;
+    int waited = -1;
+    for (int fb = 0; fb < npix; fb += PPI) {
+      const bool valid = fb + f0 < npix;
+      const int f = valid ? fb + f0 : npix - 1;
+      const int r = f / PW, p = f - r * PW;
+      const int grp = r / RG;
+      if (grp > waited) { for (int q = waited + 1; q <= grp; ++q) mbar_wait(full_u32 + 8 * q, 0); waited = grp; }
+      const uint32_t base = xs_u32 + (uint32_t)f * (C * 4);
+      float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
+      float mr = -INFINITY, mi = -INFINITY;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        CPair p01, p23, u01, u23;
+        unpack_pairs<T>(lds128(base + voff[k]), p01, p23);
+        if constexpr (REAL) {
+          u01.re = mul2(sgate[k][0].re, p01.re); u01.im = mul2(sgate[k][0].im, p01.im);
+          u23.re = mul2(sgate[k][1].re, p23.re); u23.im = mul2(sgate[k][1].im, p23.im);
+        } else {
+          u01 = cmul_pair(sgate[k][0], p01); u23 = cmul_pair(sgate[k][1], p23);
+        }
+        sre = add2(sre, add2(u01.re, u23.re));
+        sim = add2(sim, add2(u01.im, u23.im));
+        mr = fmaxf(fmaxf(mr, fmaxf(u01.re.x, u01.re.y)), fmaxf(u23.re.x, u23.re.y));
+        mi = fmaxf(fmaxf(mi, fmaxf(u01.im.x, u01.im.y)), fmaxf(u23.im.x, u23.im.y));
+      }
+      float sr = sre.x + sre.y, si = sim.x + sim.y;
+      if constexpr (REAL) { sr = 0.5f * (sr + si); si = 0.f; mr = fmaxf(mr, mi); mi = 0.f; }
+#pragma unroll
+      for (int o = G >> 1; o; o >>= 1) {
+        sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o);
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+      }
+      if (valid && sub == 0 && (unsigned)(x0 - 3 + p) < (unsigned)W)      // columns outside the image keep their zeros
+        st[(r + 3) * kAtStPitch + p] = REAL ? make_uint2(pack_f16x2(sr * invC, mr), 0u)       // ci = (mean, max, -, -)
+                                            : make_uint2(pack_f16x2(sr * invC, si * invC), pack_f16x2(mr, mi));
+    }
+  }
+  __syncthreads();
+
+  // ---- 2. gate conv: warp w -> output rows 4 w .. 4 w + 3 (two accumulators: half the dependent MMA chain)
+  if (4 * warp < H) {
+    const int r0 = 4 * warp;
+    float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t a_base = st_u32 + (uint32_t)((r0 * kAtStPitch + g + (t >> 1)) * 8 + (t & 1) * 4);
+    const uint32_t b_base = smem_u32(bt) + (uint32_t)lane * 8;
+#pragma unroll
+    for (int ks = 0; ks < 20; ++ks) {
+      const uint32_t aa = a_base + (uint32_t)(((ks >> 1) * kAtStPitch + 4 * (ks & 1)) * 8);
+      uint2 bb;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bb.x), "=r"(bb.y) : "r"(b_base + ks * 256));
+      if (ks & 1) mma_f16_16x8x16(d2, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
+      else mma_f16_16x8x16(d, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] += d2[i];
+    const int r = r0 + t;                     // accumulator columns 2 t, 2 t + 1 = (re, im) of output row r0 + t
+    if (r < H) {
+      if constexpr (REAL) {
+        sg[r * TW + g] = make_float2(sigmoid_ex2(d[0]), 0.f);
+        sg[r * TW + g + 8] = make_float2(sigmoid_ex2(d[2]), 0.f);
+      } else {
+        sg[r * TW + g] = make_float2(sigmoid_ex2(d[0]), sigmoid_ex2(d[1]));
+        sg[r * TW + g + 8] = make_float2(sigmoid_ex2(d[2]), sigmoid_ex2(d[3]));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- 3. y = gate_s * (gate_c * x)
+  {
+    const int vi = tid % VPP, q0 = tid / VPP;
+    GPair agate[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const float2 ga = gs[vi * 4 + 2 * h2], gb = gs[vi * 4 + 2 * h2 + 1];
+      agate[h2].re = make_float2(ga.x, gb.x); agate[h2].im = make_float2(ga.y, gb.y); agate[h2].nim = make_float2(-ga.y, -gb.y);
+    }
+    const int nq = H * TW;
+    T* ybase = reinterpret_cast<T*>(a.y) + (((int64_t)b * H * W + x0) * C + vi * 4) * 2;
+#pragma unroll 4
+    for (int q = q0; q < nq; q += QS) {
+      const int r = q >> 4, px = q & 15;
+      if (x0 + px < W) {
+        CPair p01, p23;
+        unpack_pairs<T>(lds128(xs_u32 + (uint32_t)(((r * PW + 3 + px) * VPP + vi) * 16)), p01, p23);
+        const float2 gsp = sg[q];
+        const float2 gre = make_float2(gsp.x, gsp.x), gim = make_float2(gsp.y, gsp.y), gnim = make_float2(-gsp.y, -gsp.y);
+        float2 r01, i01, r23, i23;
+        if constexpr (REAL) {
+          r01 = mul2(gre, mul2(agate[0].re, p01.re)); i01 = mul2(gre, mul2(agate[0].im, p01.im));
+          r23 = mul2(gre, mul2(agate[1].re, p23.re)); i23 = mul2(gre, mul2(agate[1].im, p23.im));
+        } else {
+          const CPair u01 = cmul_pair(agate[0], p01), u23 = cmul_pair(agate[1], p23);
+          r01 = fma2(gre, u01.re, mul2(gnim, u01.im)); i01 = fma2(gre, u01.im, mul2(gim, u01.re));
+          r23 = fma2(gre, u23.re, mul2(gnim, u23.im)); i23 = fma2(gre, u23.im, mul2(gim, u23.re));
+        }
+        *reinterpret_cast<uint4*>(ybase + ((int64_t)r * W + px) * C * 2) =
+            make_uint4(pack_h2<T>(r01.x, i01.x), pack_h2<T>(r01.y, i01.y), pack_h2<T>(r23.x, i23.x), pack_h2<T>(r23.y, i23.y));
+      }
+    }
+  }
+}
+
 }  // namespace dcs
 
 using namespace dcs;
@@ -437,8 +704,41 @@ static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s
   return 0;
 }
 
+template <int C, bool REAL>
+static int launch_attention_tile(const dcs_attention_params* p, cudaStream_t s) {
+  const int H = p->h, HP = (H + 3) & ~3;
+  const size_t smem = (size_t)H * kAtPW * C * 4 + (size_t)(HP + 6) * kAtStPitch * 8 + (size_t)HP * kAtTW * 8 + (size_t)(2 * C + 16) * 8 + 196 * 4 + 20 * 32 * 8 + 4 * 8;
+  DCS_REQUIRE(smem <= 113 * 1024, "dcs_attention_stream: tile does not fit shared memory (C=%d, H=%d)", C, H);
+  AttStreamArgs a;
+  a.x = p->x; a.y = p->y; a.sums = reinterpret_cast<const long long*>(p->sums); a.inv_hw = 1.f / ((float)p->h * (float)p->w);
+  a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
+  a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = 0;
+  DCS_CUDA(cudaFuncSetAttribute(attention_tile_kernel<C, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p->w + kAtTW - 1) / kAtTW, p->batch);
+  attention_tile_kernel<C, REAL><<<grid, kAtThreads, smem, s>>>(a);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+// DCS_ATT_TILE=0 keeps the row-streaming kernel for every tensor (A/B runs)
+static bool att_tile_enabled() {
+  static const bool on = [] { const char* e = getenv("DCS_ATT_TILE"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 template <typename T, bool REAL = false>
 static int dispatch_attention_stream(const dcs_attention_params* p, cudaStream_t s) {
+  if constexpr (std::is_same<T, __half>::value) {
+    // short wide-channel tensors: the whole column strip is one shared-memory tile (attention_tile_kernel)
+    if (att_tile_enabled() && p->channels >= 32 && p->h <= 32 && p->h * p->channels <= 1024) {
+      switch (p->channels) {
+        case 32: return launch_attention_tile<32, REAL>(p, s);
+        case 64: return launch_attention_tile<64, REAL>(p, s);
+        case 128: return launch_attention_tile<128, REAL>(p, s);
+        default: break;
+      }
+    }
+  }
   // strip width: 128 pixels (every warp owns 16) for the few-channel tensors; narrow strips where a row of C channels is
   // long (ring of 8 rows) and the tensor has few pixels (enough CTAs), or where the image itself is narrow
   const int w = p->w;
