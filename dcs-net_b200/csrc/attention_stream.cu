@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
 //      conflict-free LDS.32 per MMA, no im2col), B = the taps shifted by the output row, W[y' - j][kx][ci][o];
 //   3. y = gate_s * (gate_c * x) for the H x 16 strip pixels, 16-byte loads / stores, consecutive lanes on consecutive
 //      addresses.
-constexpr int kAtTW = 16, kAtPW = kAtTW + 6, kAtStPitch = 24, kAtThreads = 256;
+constexpr int kAtTW = 16, kAtPW = kAtTW + 6, kAtStPitch = 24;
 
 __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
@@ -445,16 +445,17 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   return v;
 }
 
-template <int C, bool REAL>
+template <int C, bool REAL, int kAtThreads>
 __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const AttStreamArgs a) {
   using T = __half;
   constexpr int PW = kAtPW, TW = kAtTW;
   constexpr int VPP = C / 4;                  // 16-byte vectors per pixel
-  constexpr int G = C / 16;                   // lanes per pixel in the statistics phase (4 vectors per lane)
+  constexpr int VPL = 1024 / kAtThreads;      // vectors per lane in the statistics phase (4 at 256 threads, 2 at 512)
+  constexpr int G = VPP / VPL;                // lanes per pixel in the statistics phase
   constexpr int PPI = kAtThreads / G;         // pixels per statistics iteration (a multiple of 4: the read rotation is per thread)
   constexpr int QS = kAtThreads / VPP;        // output pixels per product iteration
   constexpr int NW7 = REAL ? 98 : 196;
-  static_assert(G >= 2 && G <= 8 && VPP * 4 == C, "tile attention: C = 32, 64 or 128");
+  static_assert(G >= 2 && G <= 16 && VPP * 4 == C && (VPL == 2 || VPL == 4), "tile attention: C = 32, 64 or 128");
 
   extern __shared__ __align__(128) unsigned char as_smem[];
   const int H = a.H, W = a.W;
@@ -563,12 +564,12 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
   // ---- 1. statistics: thread = (pixel f0 + j PPI, vectors sub + G ((k + rot) & 3)); the rotation spreads the lanes of a
   //         quarter warp over all 32 banks (pixels are 128 / 256 / 512 bytes apart)
   {
-    const int sub = tid % G, f0 = tid / G, rot = f0 & 3;
-    GPair sgate[4][2];
-    uint32_t voff[4];
+    const int sub = tid % G, f0 = tid / G, rot = f0 & (VPL - 1);
+    GPair sgate[VPL][2];
+    uint32_t voff[VPL];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int vi = sub + G * ((k + rot) & 3);
+    for (int k = 0; k < VPL; ++k) {
+      const int vi = sub + G * ((k + rot) & (VPL - 1));
       voff[k] = (uint32_t)vi * 16;
 #pragma unroll
       for (int h2 = 0; h2 < 2; ++h2) {
@@ -584,13 +585,13 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
       const bool valid = fb + f0 < npix;
       const int f = valid ? fb + f0 : npix - 1;
       const int r = f / PW, p = f - r * PW;
-      const int grp = r / RG;
+      const int grp = (r >= RG) + (r >= 2 * RG) + (r >= 3 * RG);       // r / RG without the runtime division
       if (grp > waited) { for (int q = waited + 1; q <= grp; ++q) mbar_wait(full_u32 + 8 * q, 0); waited = grp; }
       const uint32_t base = xs_u32 + (uint32_t)f * (C * 4);
       float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
       float mr = -INFINITY, mi = -INFINITY;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
+      for (int k = 0; k < VPL; ++k) {
         CPair p01, p23, u01, u23;
         unpack_pairs<T>(lds128(base + voff[k]), p01, p23);
         if constexpr (REAL) {
@@ -704,8 +705,8 @@ static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s
   return 0;
 }
 
-template <int C, bool REAL>
-static int launch_attention_tile(const dcs_attention_params* p, cudaStream_t s) {
+template <int C, bool REAL, int NT>
+static int launch_attention_tile_nt(const dcs_attention_params* p, cudaStream_t s) {
   const int H = p->h, HP = (H + 3) & ~3;
   const size_t smem = (size_t)H * kAtPW * C * 4 + (size_t)(HP + 6) * kAtStPitch * 8 + (size_t)HP * kAtTW * 8 + (size_t)(2 * C + 16) * 8 + 196 * 4 + 20 * 32 * 8 + 4 * 8;
   DCS_REQUIRE(smem <= 113 * 1024, "dcs_attention_stream: tile does not fit shared memory (C=%d, H=%d)", C, H);
@@ -713,11 +714,18 @@ static int launch_attention_tile(const dcs_attention_params* p, cudaStream_t s) 
   a.x = p->x; a.y = p->y; a.sums = reinterpret_cast<const long long*>(p->sums); a.inv_hw = 1.f / ((float)p->h * (float)p->w);
   a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
   a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = 0;
-  DCS_CUDA(cudaFuncSetAttribute(attention_tile_kernel<C, REAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  DCS_CUDA(cudaFuncSetAttribute(attention_tile_kernel<C, REAL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((p->w + kAtTW - 1) / kAtTW, p->batch);
-  attention_tile_kernel<C, REAL><<<grid, kAtThreads, smem, s>>>(a);
+  attention_tile_kernel<C, REAL, NT><<<grid, NT, smem, s>>>(a);
   DCS_LAUNCHED();
   return 0;
+}
+// 8 warps (4 vectors per lane in the statistics phase, ~100 registers) by default; DCS_ATT_TILE_NT=512 selects the 16-warp
+// instance (2 vectors per lane, 64 registers), measured 10 % slower on B200 (more shuffles, longer barriers)
+template <int C, bool REAL>
+static int launch_attention_tile(const dcs_attention_params* p, cudaStream_t s) {
+  static const bool nt512 = [] { const char* e = getenv("DCS_ATT_TILE_NT"); return e && atoi(e) == 512; }();
+  return nt512 ? launch_attention_tile_nt<C, REAL, 512>(p, s) : launch_attention_tile_nt<C, REAL, 256>(p, s);
 }
 
 // DCS_ATT_TILE=0 keeps the row-streaming kernel for every tensor (A/B runs)
