@@ -31,6 +31,8 @@ constexpr int kKStepBytes = 128;         // bytes of K per pipeline stage (= one
 constexpr int kTcThreads = 448;    // warp 0 TMA, warp 1 MMA, warps 2..5 A-gather (cp.async), warps 6..13 epilogue
 constexpr int kGatherThreads = 128;
 constexpr int kMaxStages = 8;
+constexpr int kDxMaxTaps = 5;            // dx-reuse staging: up to 5 horizontal taps (k5)
+constexpr uint32_t kDxABytes = 17 * 1024; // (128 + 4) rows x 128 B, rounded to the 1024-byte swizzle atom
 
 struct TcArgs {
   int PH, PW;                 // phase grid
@@ -43,6 +45,13 @@ struct TcArgs {
   int kb;                     // 128-byte K blocks per pipeline stage: 1, or 2 (TMA mode, n_pad <= 128: one tcgen05.mma issue costs
                               // ~55 cycles and a stage's wait / fence / descriptor / commit overhead ~300, so 8 MMAs per stage
                               // instead of 4 lift the issue-bound N <= 128 layers)
+  int dxm;                    // > 0: "dx-reuse" staging (TMA mode, tile = 128 consecutive pixels of ONE image row, stride_w = 1): a stage holds
+                              //      ONE A box of 128 + dxm - 1 pixels x 128 bytes of K per (tap row dy, 64-channel block) and the dxm
+                              //      horizontal taps read it through UMMA descriptors whose start is shifted by whole 128-byte rows (the
+                              //      swizzle is a function of the absolute shared-memory address: tools/umma_shift_test), plus dxm weight
+                              //      tiles.  The im2col form re-stages the A tile once per tap — dxm x the TMA rows, and the TMA row rate
+                              //      (~2 cycles per 128-byte row) is what bounds these layers.
+  int nrows;                  // dx-reuse: tap rows (dy values) per phase; ntaps = nrows * dxm
   int gather;                 // 1: A tiles are gathered by 4 warps with 16-byte cp.async (rows shorter than 128 B or
                               //    small N, where the per-row cost of TMA boxes dominates); 0: A tiles come from TMA boxes
   int tw_log2, th_log2;       // tile extents are powers of two
@@ -88,12 +97,20 @@ struct __align__(16) TcBarriers {
   uint32_t tmem_base;
 };
 
+// CTA2: the CTAs of a 2-CTA cluster work on two neighbouring M tiles of the same phase with ONE tcgen05.mma.cta_group::2
+// (M = 256) per k-slice: each CTA stages its own A tile and only HALF of the weight rows, so the L2 -> shared-memory
+// operand traffic per tile drops from A + B to A + B / 2 (what bounds these layers: ~45 B / clk / SM).
+template <bool CTA2>
 __global__ void __launch_bounds__(kTcThreads, 1)
 cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                 const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
   extern __shared__ __align__(1024) unsigned char smem[];
-  // layout: [stage][A 16 KB | B n_pad*128 B] (1024-aligned), then barriers
-  const uint32_t a_bytes = kTileM * kKStepBytes * (uint32_t)a.kb, b_bytes = (uint32_t)a.n_pad * kKStepBytes * (uint32_t)a.kb;
+  // layout: [stage][A 16 KB | B b_rows*128 B] (1024-aligned), then barriers
+  const uint32_t cta_rank = CTA2 ? cluster_ctarank() : 0u;
+  const uint32_t b_rows = CTA2 ? (uint32_t)a.n_pad / 2u : (uint32_t)a.n_pad;   // weight rows staged by this CTA
+  const uint32_t b_tile = b_rows * kKStepBytes;                                  // one weight tile (b_rows x 128 bytes of K)
+  const uint32_t a_bytes = a.dxm ? kDxABytes : kTileM * kKStepBytes * (uint32_t)a.kb;
+  const uint32_t b_bytes = a.dxm ? b_tile * (uint32_t)a.dxm : b_tile * (uint32_t)a.kb;
   const uint32_t stage_bytes = a_bytes + b_bytes;  // multiple of 1024 (n_pad % 16 == 0 -> b_bytes % 2048 == 0)
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem + 1023) & ~(uintptr_t)1023);
   TcBarriers* bars = reinterpret_cast<TcBarriers*>(base + (size_t)a.n_stages * stage_bytes);
@@ -108,20 +125,26 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     const uint32_t full_count = a.gather ? 1u + kGatherThreads : 1u;  // B-TMA expect_tx arrive (+ one per gather thread)
     for (int s = 0; s < a.n_stages; ++s) { mbar_init(smem_u32(&bars->full[s]), full_count); mbar_init(smem_u32(&bars->empty[s]), 1); }
     const uint32_t n_epi_warps = tile_split ? 4u : ((a.n_pad % 32) == 0 ? 8u : 4u);
-    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), n_epi_warps); }
+    // CTA2: the leader's acc_empty collects the epilogue warps of BOTH CTAs (its MMAs write both accumulators)
+    for (int i = 0; i < kMaxAcc; ++i) { mbar_init(smem_u32(&bars->acc_full[i]), 1); mbar_init(smem_u32(&bars->acc_empty[i]), CTA2 ? 2u * n_epi_warps : n_epi_warps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA1) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; the same warp frees it
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CTA2) {   // the same warp of both CTAs, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&bars->tmem_base)), "r"(tmem_cols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   for (int i = threadIdx.x; i < a.n_pad; i += kTcThreads) bars->bias[i] = a.bias[i];
   const float* bias_s = bars->bias;
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // the peer's barriers must exist before any remote arrive / commit
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
   const int kstep_elems = kKStepBytes * a.kb / a.esz;
@@ -146,18 +169,55 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int8_t* dxp = a.dx + ph_idx * a.ntaps;
         const int ybase = j0 * a.stride_h, xbase = i0 * a.stride_w;
         const int wrow = ph_idx * a.n_pad;
+        if (a.dxm) {
+          // dx-reuse: stage = (tap row r, 64-channel block): one A box of 128 + dxm - 1 pixels starting at the leftmost tap, dxm weight tiles
+          const uint32_t tx_bytes = (uint32_t)((kTileM + a.dxm - 1) * 128) + b_bytes;   // (TMA counts the whole box, zero fill included)
+          const int xl = xbase + dxp[0];
+          for (int r = 0; r < a.nrows; ++r) {
+            const int yy = ybase + dyp[r * a.dxm];
+            for (int cb = 0; cb < a.C2; cb += 64) {
+              mbar_wait(bar_empty0 + 8u * stage, phase_bit ^ 1, dw);
+              const uint32_t full = bar_full0 + 8u * stage;
+              if (elect_one()) {
+                const uint32_t dst = smem_base + stage * stage_bytes;
+                const int kc0 = r * a.dxm * a.C2 + cb;           // weight column of tap (r, 0), channel block cb
+                if constexpr (CTA2) {
+                  if (cta_rank == 0) mbar_expect_tx(full, 2u * tx_bytes);
+                  if (cb < a.C2_src0) tma_load_4d_2cta(dst, &tmA0, full, cb, xl, yy, b0);
+                  else tma_load_4d_2cta(dst, &tmA1, full, cb - a.C2_src0, xl, yy, b0);
+                  const int wr2 = wrow + (int)(cta_rank * b_rows);
+                  for (int j = 0; j < a.dxm; ++j) tma_load_2d_2cta(dst + a_bytes + (uint32_t)j * b_tile, &tmB, full, kc0 + j * a.C2, wr2);
+                } else {
+                  mbar_expect_tx(full, tx_bytes);
+                  if (cb < a.C2_src0) tma_load_4d(dst, &tmA0, full, cb, xl, yy, b0);
+                  else tma_load_4d(dst, &tmA1, full, cb - a.C2_src0, xl, yy, b0);
+                  for (int j = 0; j < a.dxm; ++j) tma_load_2d(dst + a_bytes + (uint32_t)j * b_tile, &tmB, full, kc0 + j * a.C2, wrow);
+                }
+              }
+              __syncwarp();
+              if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
+            }
+          }
+          continue;
+        }
         int tap = 0, c = 0, kcol = 0;                       // running (tap, channel) position and weight column
         int y = ybase + dyp[0], x = xbase + dxp[0];
         for (int ks = 0; ks < a.ksteps; ++ks) {
           mbar_wait(bar_empty0 + 8u * stage, phase_bit ^ 1, dw);
           const uint32_t full = bar_full0 + 8u * stage;
           const bool leader = elect_one();
-          if (leader) mbar_expect_tx(full, a.gather ? b_bytes : stage_bytes);
+          if constexpr (CTA2) { if (leader && cta_rank == 0) mbar_expect_tx(full, 2u * stage_bytes); }   // both CTAs' bytes land on the leader's barrier
+          else if (leader) mbar_expect_tx(full, a.gather ? b_bytes : stage_bytes);
           uint32_t dst = smem_base + stage * stage_bytes;
           for (int g = 0; g < (a.gather ? 0 : sub_per_step); ++g) {
             if (leader) {
-              if (c < a.C2_src0) tma_load_4d(dst, &tmA0, full, c, x, y, b0);
-              else tma_load_4d(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
+              if constexpr (CTA2) {
+                if (c < a.C2_src0) tma_load_4d_2cta(dst, &tmA0, full, c, x, y, b0);
+                else tma_load_4d_2cta(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
+              } else {
+                if (c < a.C2_src0) tma_load_4d(dst, &tmA0, full, c, x, y, b0);
+                else tma_load_4d(dst, &tmA1, full, c - a.C2_src0, x, y, b0);
+              }
             }
             dst += sub_bytes;
             c += a.CK;
@@ -167,8 +227,14 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             }
           }
           if (leader) {
-            tma_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, full, kcol, wrow);
-            if (a.kb == 2) tma_load_2d(smem_base + stage * stage_bytes + a_bytes + (uint32_t)a.n_pad * kKStepBytes, &tmB, full, kcol + kKStepBytes / a.esz, wrow);
+            if constexpr (CTA2) {   // this CTA's half of the weight rows
+              const int wr2 = wrow + (int)(cta_rank * b_rows);
+              tma_load_2d_2cta(smem_base + stage * stage_bytes + a_bytes, &tmB, full, kcol, wr2);
+              if (a.kb == 2) tma_load_2d_2cta(smem_base + stage * stage_bytes + a_bytes + b_rows * kKStepBytes, &tmB, full, kcol + kKStepBytes / a.esz, wr2);
+            } else {
+              tma_load_2d(smem_base + stage * stage_bytes + a_bytes, &tmB, full, kcol, wrow);
+              if (a.kb == 2) tma_load_2d(smem_base + stage * stage_bytes + a_bytes + b_rows * kKStepBytes, &tmB, full, kcol + kKStepBytes / a.esz, wrow);
+            }
           }
           __syncwarp();
           kcol += kstep_elems;
@@ -179,10 +245,10 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (whole warp loops, one lane issues)
-    {
+    if (!CTA2 || cta_rank == 0) {
       // instruction descriptor: D=F32, A=B=F16 (0) / BF16 (1) or TF32 (2), both K-major, N>>3 @17, M>>4 @24
       const uint32_t fmt = a.esz == 2 ? (a.f16 ? 0u : 1u) : 2u;
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(a.n_pad >> 3) << 17) | ((uint32_t)((CTA2 ? 2 * kTileM : kTileM) >> 4) << 24);
       const uint32_t a_row_bytes = a.gather ? 128u : (uint32_t)(a.CK * a.esz);  // gathered tiles are always 128 x 128 B, SWIZZLE_128B
       // Descriptors = constant high word + (start address >> 4) in the low word; per-MMA byte offsets inside a stage
       // are precomputed once so the issue loop is a handful of 32-bit adds per MMA (single latency-exposed thread).
@@ -208,11 +274,44 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           const uint32_t sb16 = sa16 + (a_bytes >> 4);
           const uint64_t ad0 = a_desc0 + (uint64_t)sa16, bd0 = b_desc0 + (uint64_t)sb16;
           const uint32_t acc0 = ks != 0;
-          if (elect_one()) {
+          if (a.dxm) {
+            if (elect_one()) {
+              // horizontal tap j: the A box read from row j on (descriptor start + j x 128 B), weight tile j
+#pragma unroll
+              for (int j = 0; j < kDxMaxTaps; ++j) {
+                if (j < a.dxm) {
+                  const uint64_t aj = ad0 + (uint64_t)(j * 8), bj = bd0 + (uint64_t)((uint32_t)j * (b_tile >> 4));
+                  if constexpr (CTA2) {
+                    tc_mma_f16_2cta(d_tmem, aj, bj, idesc, (j == 0) ? acc0 : 1u);
+                    tc_mma_f16_2cta(d_tmem, aj + 2, bj + 2, idesc, 1u);
+                    tc_mma_f16_2cta(d_tmem, aj + 4, bj + 4, idesc, 1u);
+                    tc_mma_f16_2cta(d_tmem, aj + 6, bj + 6, idesc, 1u);
+                  } else {
+                    tc_mma_bf16(d_tmem, aj, bj, idesc, (j == 0) ? acc0 : 1u);
+                    tc_mma_bf16(d_tmem, aj + 2, bj + 2, idesc, 1u);
+                    tc_mma_bf16(d_tmem, aj + 4, bj + 4, idesc, 1u);
+                    tc_mma_bf16(d_tmem, aj + 6, bj + 6, idesc, 1u);
+                  }
+                }
+              }
+              if constexpr (CTA2) {
+                tc_commit_2cta(bar_empty0 + 8u * stage);
+                if (ks == a.ksteps - 1) tc_commit_2cta(bar_accf0 + 8u * acc);
+              } else {
+                tc_commit(bar_empty0 + 8u * stage);
+                if (ks == a.ksteps - 1) tc_commit(bar_accf0 + 8u * acc);
+              }
+            }
+          } else if (elect_one()) {
             // one MMA per 32 bytes of K (16 bf16 / 8 tf32); A sub-tile g = 128 rows x a_row_bytes, 32-byte slice j inside it
 #define DCS_TC_ISSUE4(O1, O2, O3)                                                        \
   do {                                                                                   \
-    if (a.esz == 2) {                                                                    \
+    if (CTA2) {                                                                          \
+      tc_mma_f16_2cta(d_tmem, ad0, bd0, idesc, acc0);                                    \
+      tc_mma_f16_2cta(d_tmem, ad0 + (O1), bd0 + 2, idesc, 1u);                           \
+      tc_mma_f16_2cta(d_tmem, ad0 + (O2), bd0 + 4, idesc, 1u);                           \
+      tc_mma_f16_2cta(d_tmem, ad0 + (O3), bd0 + 6, idesc, 1u);                           \
+    } else if (a.esz == 2) {                                                             \
       tc_mma_bf16(d_tmem, ad0, bd0, idesc, acc0);                                        \
       tc_mma_bf16(d_tmem, ad0 + (O1), bd0 + 2, idesc, 1u);                               \
       tc_mma_bf16(d_tmem, ad0 + (O2), bd0 + 4, idesc, 1u);                               \
@@ -227,18 +326,30 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
             if (a_row_bytes == 128u) {
               DCS_TC_ISSUE4(2, 4, 6);
               if (a.kb == 2) {   // second 128-byte K block of the stage: next A sub-tile (128 rows x 128 B) and B sub-tile
-                const uint64_t ad1 = ad0 + (uint64_t)((kTileM * 128) >> 4), bd1 = bd0 + (uint64_t)(((uint32_t)a.n_pad * 128u) >> 4);
-                tc_mma_bf16(d_tmem, ad1, bd1, idesc, 1u);
-                tc_mma_bf16(d_tmem, ad1 + 2, bd1 + 2, idesc, 1u);
-                tc_mma_bf16(d_tmem, ad1 + 4, bd1 + 4, idesc, 1u);
-                tc_mma_bf16(d_tmem, ad1 + 6, bd1 + 6, idesc, 1u);
+                const uint64_t ad1 = ad0 + (uint64_t)((kTileM * 128) >> 4), bd1 = bd0 + (uint64_t)((b_rows * 128u) >> 4);
+                if constexpr (CTA2) {
+                  tc_mma_f16_2cta(d_tmem, ad1, bd1, idesc, 1u);
+                  tc_mma_f16_2cta(d_tmem, ad1 + 2, bd1 + 2, idesc, 1u);
+                  tc_mma_f16_2cta(d_tmem, ad1 + 4, bd1 + 4, idesc, 1u);
+                  tc_mma_f16_2cta(d_tmem, ad1 + 6, bd1 + 6, idesc, 1u);
+                } else {
+                  tc_mma_bf16(d_tmem, ad1, bd1, idesc, 1u);
+                  tc_mma_bf16(d_tmem, ad1 + 2, bd1 + 2, idesc, 1u);
+                  tc_mma_bf16(d_tmem, ad1 + 4, bd1 + 4, idesc, 1u);
+                  tc_mma_bf16(d_tmem, ad1 + 6, bd1 + 6, idesc, 1u);
+                }
               }
             }
             else if (a_row_bytes == 64u) DCS_TC_ISSUE4(2, (kTileM * 64) >> 4, ((kTileM * 64) >> 4) + 2);
             else DCS_TC_ISSUE4((kTileM * 32) >> 4, (2 * kTileM * 32) >> 4, (3 * kTileM * 32) >> 4);
 #undef DCS_TC_ISSUE4
-            tc_commit(bar_empty0 + 8u * stage);     // frees the smem stage once these MMAs have read it
-            if (ks == a.ksteps - 1) tc_commit(bar_accf0 + 8u * acc);  // accumulator complete -> epilogue
+            if constexpr (CTA2) {                   // the same barriers of BOTH CTAs (multicast commit)
+              tc_commit_2cta(bar_empty0 + 8u * stage);
+              if (ks == a.ksteps - 1) tc_commit_2cta(bar_accf0 + 8u * acc);
+            } else {
+              tc_commit(bar_empty0 + 8u * stage);     // frees the smem stage once these MMAs have read it
+              if (ks == a.ksteps - 1) tc_commit(bar_accf0 + 8u * acc);  // accumulator complete -> epilogue
+            }
           }
           __syncwarp();
           if (++stage == (uint32_t)a.n_stages) { stage = 0; phase_bit ^= 1; }
@@ -524,7 +635,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(smem_u32(&bars->acc_empty[acc]));
+        if (lane == 0) { if constexpr (CTA2) mbar_arrive_leader(smem_u32(&bars->acc_empty[acc])); else mbar_arrive(smem_u32(&bars->acc_empty[acc])); }
       }
       acc += (uint32_t)t_step;
       if (acc >= n_acc) { acc -= n_acc; acc_phase ^= 1; }
@@ -532,10 +643,11 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
     if (dwe) { a.dbg[blockIdx.x * 8 + 5] = w_epi; a.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start); a.dbg[blockIdx.x * 8 + 7] = (unsigned long long)n_my_tiles; }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // (pair: the leader's MMAs read the peer's shared memory and TMEM)
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    if constexpr (CTA2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
@@ -563,12 +675,12 @@ static CUtensorMapDataType map_dtype(int esz, int f16) {
   return esz == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : (f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16);
 }
 
-static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int f16, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy) {
+static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int f16, int C2, int W, int H, int B, int CK, int TW, int TH, int NB, int sx, int sy, int box_w = 0) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[4] = {(cuuint64_t)C2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C2 * esz, (cuuint64_t)W * C2 * esz, (cuuint64_t)H * W * C2 * esz};
-  cuuint32_t box[4] = {(cuuint32_t)CK, (cuuint32_t)(TW * sx), (cuuint32_t)(TH * sy), (cuuint32_t)NB};
+  cuuint32_t box[4] = {(cuuint32_t)CK, (cuuint32_t)(box_w ? box_w : TW * sx), (cuuint32_t)(TH * sy), (cuuint32_t)NB};
   cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
   DCS_REQUIRE(box[1] <= 256 && box[2] <= 256, "TMA box too large (%u x %u)", box[1], box[2]);
   CUresult r = fn(m, map_dtype(esz, f16), 4, const_cast<void*>(ptr), dims, strides, box, es,
@@ -579,12 +691,12 @@ static int make_act_map(CUtensorMap* m, const void* ptr, int esz, int f16, int C
   return 0;
 }
 
-static int make_weight_map(CUtensorMap* m, const void* ptr, int esz, int f16, int Kpad, int rows, int n_pad) {
+static int make_weight_map(CUtensorMap* m, const void* ptr, int esz, int f16, int Kpad, int rows, int box_rows) {
   EncodeTiledFn fn = encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
   cuuint64_t dims[2] = {(cuuint64_t)Kpad, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)Kpad * esz};
-  cuuint32_t box[2] = {(cuuint32_t)(kKStepBytes / esz), (cuuint32_t)n_pad};
+  cuuint32_t box[2] = {(cuuint32_t)(kKStepBytes / esz), (cuuint32_t)box_rows};
   cuuint32_t es[2] = {1, 1};
   CUresult r = fn(m, map_dtype(esz, f16), 2, const_cast<void*>(ptr), dims, strides, box, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -660,6 +772,12 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   a.tiles_w = (a.PW + a.TW - 1) / a.TW;
   a.tiles_h = (a.PH + a.TH - 1) / a.TH;
   a.tiles_b = (p->batch + a.NB - 1) / a.NB;
+  // CTA pairs (cta_group::2): 16-bit TMA-mode layers.  DCS_TC_2CTA=0 keeps single-CTA MMAs (A/B runs).
+  static const bool no_2cta = getenv("DCS_TC_2CTA") && atoi(getenv("DCS_TC_2CTA")) == 0;
+  const bool cta2 = !no_2cta && !gather && esz == 2 && n_pad % 16 == 0 && n_pad >= 32 && num_sms() >= 2;
+  // a pair works on tiles (2q, 2q + 1) of one phase (same weights): make the tile count of a phase even (the extra tile
+  // lies beyond the batch: its loads are zero-filled out of bounds, its rows are masked in the epilogue)
+  if (cta2 && ((a.tiles_w * a.tiles_h * a.tiles_b) & 1)) ++a.tiles_b;
   a.tiles_per_phase = a.tiles_w * a.tiles_h * a.tiles_b;
   a.phases = p->up_h * p->up_w;
   a.n_tiles = a.tiles_per_phase * a.phases;
@@ -684,7 +802,32 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   a.bias = p->bias; a.dst = p->dst; a.pool = reinterpret_cast<long long*>(p->pool_sums); a.dbg = g_tc_dbg;
   a.pool_max = p->pool_mode == DCS_POOL_MAX ? 1 : 0;
 
-  const size_t stage_bytes = ((size_t)kTileM * kKStepBytes + (size_t)n_pad * kKStepBytes) * a.kb;
+  const int b_rows = cta2 ? n_pad / 2 : n_pad;
+  size_t stage_bytes = ((size_t)kTileM * kKStepBytes + (size_t)b_rows * kKStepBytes) * a.kb;
+  // dx-reuse staging (see TcArgs::dxm): tile = 128 consecutive pixels of one image row, taps = nrows x kw with consecutive dx
+  {
+    static const bool no_dxm = getenv("DCS_TC_DXM") && atoi(getenv("DCS_TC_DXM")) == 0;
+    int kw = 0, nrows = 0;
+    if (!no_dxm && !gather && esz == 2 && CK * esz == 128 && C2s0 % 64 == 0 && C2s1 % 64 == 0 && p->stride_w == 1 &&
+        a.TW == kTileM && a.TH == 1 && a.NB == 1) {
+      kw = 1;
+      while (kw < p->ntaps && p->dy[kw] == p->dy[0] && p->dx[kw] == p->dx[0] + kw) ++kw;
+      bool ok = kw >= 2 && kw <= kDxMaxTaps && p->ntaps % kw == 0;
+      nrows = ok ? p->ntaps / kw : 0;
+      for (int ph = 0; ok && ph < a.phases; ++ph)
+        for (int r = 0; ok && r < nrows; ++r)
+          for (int j = 0; ok && j < kw; ++j) {
+            const int t = ph * p->ntaps + r * kw + j;
+            ok = p->dy[t] == p->dy[ph * p->ntaps + r * kw] && p->dx[t] == p->dx[ph * p->ntaps] + j;
+          }
+      const size_t sb = (size_t)kDxABytes + (size_t)kw * b_rows * kKStepBytes;
+      if (ok && (200 * 1024) / sb >= 2) {
+        a.dxm = kw; a.nrows = nrows; a.kb = 1;
+        a.ksteps = nrows * (C2 / 64);
+        stage_bytes = sb;
+      }
+    }
+  }
   int n_stages = (int)((200 * 1024) / stage_bytes);
   n_stages = std::max(2, std::min(n_stages, kMaxStages));
   a.n_stages = n_stages;
@@ -692,21 +835,38 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
 
   CUtensorMap tmA0, tmA1, tmB;
   // (the packed weight matrix is padded to whole 128-byte K blocks; a half-empty last double stage reads zeros out of bounds)
-  if (int e = make_weight_map(&tmB, p->weight, esz, f16, (K + kblk_elems - 1) / kblk_elems * kblk_elems, a.phases * n_pad, n_pad)) return e;
+  if (int e = make_weight_map(&tmB, p->weight, esz, f16, (K + kblk_elems - 1) / kblk_elems * kblk_elems, a.phases * n_pad, b_rows)) return e;
   if (gather) {
     tmA0 = tmB; tmA1 = tmB;  // unused by the kernel in gather mode (kept valid for the descriptor prefetch)
   } else {
-    if (int e = make_act_map(&tmA0, p->src0, esz, f16, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+    const int box_w = a.dxm ? a.TW + a.dxm - 1 : 0;
+    if (int e = make_act_map(&tmA0, p->src0, esz, f16, C2s0, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h, box_w)) return e;
     if (p->c1) {
-      if (int e = make_act_map(&tmA1, p->src1, esz, f16, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h)) return e;
+      if (int e = make_act_map(&tmA1, p->src1, esz, f16, C2s1, p->in_w, p->in_h, p->batch, CK, a.TW, a.TH, a.NB, p->stride_w, p->stride_h, box_w)) return e;
     } else {
       tmA1 = tmA0;
     }
   }
 
-  DCS_CUDA(cudaFuncSetAttribute(cconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (cta2) {
+    DCS_CUDA(cudaFuncSetAttribute(cconv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(std::min(a.n_tiles, num_sms()) & ~1), 1, 1);   // n_tiles is even
+    cfg.blockDim = dim3(kTcThreads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    DCS_CUDA(cudaLaunchKernelEx(&cfg, cconv_tc_kernel<true>, tmA0, tmA1, tmB, a));
+    DCS_LAUNCHED();
+    return 0;
+  }
+  DCS_CUDA(cudaFuncSetAttribute(cconv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int grid = std::min(a.n_tiles, num_sms());
-  cconv_tc_kernel<<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, a);
+  cconv_tc_kernel<false><<<grid, kTcThreads, smem, (cudaStream_t)stream>>>(tmA0, tmA1, tmB, a);
   DCS_LAUNCHED();
   return 0;
 }

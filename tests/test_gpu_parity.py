@@ -188,6 +188,37 @@ def test_tensor_core_conv_equals_cuda_core_conv_on_same_operands(mode):
         assert rel_err(got, ref) <= tol, (p.cin, p.cout, p.up, p.stride)
 
 
+@pytest.mark.parametrize("W", [250, 131])
+@pytest.mark.parametrize("mode", ["fp16", "bf16"])
+def test_tensor_core_conv_wide_rows_pairs_and_dx_reuse(mode, W):
+    """The general tcgen05 kernel at the geometry of the full-size step (image rows >= 128 pixels): tiles of 128 consecutive
+    pixels of one row, CTA pairs (tcgen05.mma.cta_group::2, each CTA stages half of the weight rows; an odd tile count adds a
+    masked tile) and dx-reuse staging (one A box per tap row, horizontal taps through row-shifted descriptors) vs the FFMA
+    kernel on the SAME 16-bit activations and 16-bit-rounded weights; ragged width, odd batch, pooled sums."""
+    sd = SW.make_state_dict(1)
+    dt = H16[mode]
+    pk = D.PackedNet(sd, "cuda", mode)
+    g = torch.Generator().manual_seed(11)
+    B = 3
+    cases = [(pk.enc[i], (B, 8, W, pk.enc[i].cin), False) for i in range(3, 7)]
+    cases += [(pk.dec[i], (B, 2 + i, W, pk.dec[i].cin // 2), True) for i in range(4)]
+    for p, s0, two in cases:
+        x0 = torch.randn(*s0, 2, generator=g).cuda().to(dt)
+        x1 = torch.randn(*s0, 2, generator=g).cuda().to(dt) if two else None
+        oh, ow = ops.conv_out_hw(p, s0[1], s0[2])
+        ref = torch.empty(B, oh, ow, p.cout, 2, device="cuda")
+        with rounded_ffma_weights(p):
+            ops.cconv(p, x0, x1, ref, use_tc=False)
+        gb = torch.full((B, oh, ow, p.cout, 2), float("nan"), device="cuda", dtype=dt)
+        sums = torch.zeros(B, p.cout, 2, device="cuda", dtype=torch.int64)
+        ops.cconv(p, x0, x1, gb, use_tc=True, pool_sums=sums)
+        torch.cuda.synchronize()
+        assert not torch.isnan(gb.float()).any(), (p.cin, p.cout)
+        assert rel_err(gb.float(), ref.to(dt).float()) <= ULP[dt], (p.cin, p.cout, p.up, p.stride)
+        want = ref.double().sum(dim=(1, 2))            # the epilogue sums its fp32 values (before the 16-bit rounding)
+        assert rel_err(ops.pool_sums_to_float(sums), want) <= 1e-4, (p.cin, p.cout)
+
+
 class rounded_ffma_weights:
     """Give the CUDA-core reference kernel the SAME 16-bit-rounded weights the tensor-core kernel multiplies (the packed
     tcgen05 operand, re-laid-out), so that a comparison isolates the data movement: a wrong small tap cannot hide inside a

@@ -213,7 +213,7 @@ def part_attn(B, T):
 def part_layers(B, T):
     """per-layer timing of the tcgen05 conv (and the FFMA layers) at full size"""
     sd = SW.make_state_dict(0)
-    pk = D.PackedNet(sd, "cuda", "bf16")
+    pk = D.PackedNet(sd, "cuda", "fp16")
     plan = D.ForwardPlan(pk, B, T, want_aux=False)
     _, _, noisy = O.synthetic_audio(B, 32 * (T - 1))
     plan.enhance_audio(noisy.cuda())
@@ -292,7 +292,7 @@ def part_layers(B, T):
         ms = e0.elapsed_time(e1) / n
         in_bytes = s0.numel() * s0.element_size() + (s1.numel() * s1.element_size() if s1 is not None else 0)
         out_bytes = dst.numel() * dst.element_size()
-        print(json.dumps({"layer": name, "tc": use_tc, "ms": round(ms, 4), "tflops_ref": round(B * fl[name] / ms / 1e9, 1),
+        print(json.dumps({"layer": name, "tc": use_tc, "ms": round(ms, 4), "tflops_ref": round(B * fl[name][0] / ms / 1e9, 1), "tflops_exec": round(B * fl[name][1] / ms / 1e9, 1),
                           "N": 2 * p.cout, "K": p.ntaps * 2 * p.cin * p.phases, "in_MB": round(in_bytes / 1e6, 1), "out_MB": round(out_bytes / 1e6, 1),
                           "GBps_min": round((in_bytes + out_bytes) / ms / 1e6, 1)}))
 
