@@ -85,7 +85,7 @@ class CconvParams(C.Structure):
                 ("ntaps", _i), ("dy", C.c_int8 * MAX_TAPS), ("dx", C.c_int8 * MAX_TAPS),
                 ("weight", _vp), ("bias", _vp), ("act", _i),
                 ("dst", _vp), ("in_dtype", _i), ("out_dtype", _i),
-                ("pool_sums", _vp), ("pool_mode", _i)]
+                ("pool_sums", _vp), ("pool_mode", _i), ("bias_phase_stride", _i)]
 
 
 STRIP_MAX_GROUPS = 2

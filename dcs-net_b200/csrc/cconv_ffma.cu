@@ -210,7 +210,7 @@ int validate_conv(const dcs_cconv_params* p, const char* who) {
   DCS_REQUIRE(p && p->src0 && p->weight && p->dst, "%s: null pointer", who);
   DCS_REQUIRE(p->c0 > 0 && p->c1 >= 0 && (p->c1 == 0 || p->src1), "%s: bad source channels (%d,%d)", who, p->c0, p->c1);
   DCS_REQUIRE(p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->cout > 0, "%s: bad shape", who);
-  DCS_REQUIRE(p->up_h >= 1 && p->up_w >= 1 && p->up_h <= 2 && p->up_w <= 2, "%s: up factors must be 1 or 2", who);
+  DCS_REQUIRE(p->up_h >= 1 && p->up_w >= 1 && p->up_h <= 8 && p->up_w <= 8, "%s: up factors must be in [1, 8]", who);
   DCS_REQUIRE(p->stride_h >= 1 && p->stride_w >= 1, "%s: bad stride", who);
   DCS_REQUIRE(p->out_h % p->up_h == 0 && p->out_w % p->up_w == 0, "%s: out dims not divisible by up factors", who);
   DCS_REQUIRE(p->ntaps >= 1 && p->ntaps * p->up_h * p->up_w <= DCS_MAX_TAPS, "%s: too many taps (%d x %d phases)", who,
@@ -227,6 +227,7 @@ using namespace dcs;
 
 extern "C" int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream) {
   if (int e = validate_conv(p, "dcs_cconv2d_fwd")) return e;
+  DCS_REQUIRE(p->up_h <= 2 && p->up_w <= 2, "dcs_cconv2d_fwd: up factors must be 1 or 2");
   DCS_REQUIRE(!p->pool_sums, "dcs_cconv2d_fwd: fused pooling is only provided by the tcgen05 path; use dcs_chan_pool");
   ConvGeom g;
   g.PH = p->out_h / p->up_h;

@@ -61,6 +61,7 @@ struct TcArgs {
   int batch, out_h, out_w;
   int8_t dy[DCS_MAX_TAPS], dx[DCS_MAX_TAPS];
   const float* bias;
+  int bias_stride;            // floats between the bias vectors of consecutive phases (0: one vector for all phases, staged in shared memory)
   void* dst;
   long long* pool;            // fixed-point pooled sums (common.cuh: pool_add) or encoded maxima (pool_max)
   int pool_max;
@@ -451,7 +452,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         const int ph_idx = it.ph;
         const int b = it.bt * a.NB + nb, j = it.ht * a.TH + rr, i = it.wt * a.TW + cc;
         const bool valid = b < a.batch && j < a.PH && i < a.PW;
-        const int ph_h = a.up_w == 2 ? (ph_idx >> 1) : ph_idx, ph_w = a.up_w == 2 ? (ph_idx & 1) : 0;
+        const int ph_h = ph_idx / a.up_w, ph_w = ph_idx - ph_h * a.up_w;
         const int oy = j * a.up_h + ph_h, ox = i * a.up_w + ph_w;
         const int64_t pix = ((int64_t)b * a.out_h + oy) * a.out_w + ox;
         // output pixel of every row of this warp's quadrant (-1: outside the tensor), for the lanes that store the row
@@ -481,7 +482,9 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           // instruction stream: a per-value runtime switch cost ~8 instructions per accumulator element)
           float v[32];
           {
-            const float4* b4 = reinterpret_cast<const float4*>(bias_s + n0);
+            // (per-phase bias vectors — the merged LSTM input projections — are read from global memory: warp-uniform, L1 hits)
+            const float4* b4 = a.bias_stride ? reinterpret_cast<const float4*>(a.bias + (int64_t)ph_idx * a.bias_stride + n0)
+                                             : reinterpret_cast<const float4*>(bias_s + n0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bb = b4[q];
@@ -799,7 +802,7 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   memcpy(a.dy, p->dy, sizeof(a.dy));
   memcpy(a.dx, p->dx, sizeof(a.dx));
   DCS_REQUIRE(p->bias, "dcs_cconv2d_tc_fwd: bias is required (pass zeros)");
-  a.bias = p->bias; a.dst = p->dst; a.pool = reinterpret_cast<long long*>(p->pool_sums); a.dbg = g_tc_dbg;
+  a.bias = p->bias; a.bias_stride = p->bias_phase_stride; a.dst = p->dst; a.pool = reinterpret_cast<long long*>(p->pool_sums); a.dbg = g_tc_dbg;
   a.pool_max = p->pool_mode == DCS_POOL_MAX ? 1 : 0;
 
   const int b_rows = cta2 ? n_pad / 2 : n_pad;

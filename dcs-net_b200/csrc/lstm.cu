@@ -422,7 +422,11 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], c
 // fp16 variant of the tensor-core recurrence: W_hh and h as fp16 (11-bit significands, like tf32; |h| < 1, |W_hh| small:
 // no range issue), m16n8k16 -> 8 instead of 16 MMAs per warp and step (the legacy tensor pipe was ~275 of the ~970
 // cycles of a step), two LDS.128 instead of four for the h fragments, 32 instead of 64 weight registers.
-__global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const float* __restrict__ pre0, int64_t stride_lstm,
+// PT = storage type of the pre-activations: float, or __half (the tensor-core mode: the projection GEMMs then write and this
+// kernel reads half the bytes — the projections are bound by their 262 MB fp32 output per layer; fp16 pre-activations carry
+// the same 11-bit significand as the fp16 h / W_hh products they are added to).
+template <typename PT>
+__global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const PT* __restrict__ pre0, int64_t stride_lstm,
                                                                      int64_t stride_dir, int ld, const float* __restrict__ whh,
                                                                      float* __restrict__ hout, int B, int S) {
   __shared__ __align__(16) __half hs[2][4][kH];    // [buffer][sequence][permuted k], fp16
@@ -461,21 +465,22 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const flo
   for (int i = tid; i < 2 * 4 * kH; i += 256) (&hs[0][0][0])[i] = __float2half_rn(0.f);
 
   constexpr int kBlk = 8, kStg = 3, kSeqPitch = kBlk * kG + 8;
-  extern __shared__ __align__(16) float pre_s[];                          // [kStg][4][kSeqPitch]
+  extern __shared__ __align__(16) unsigned char pre_raw[];
+  PT* pre_s = reinterpret_cast<PT*>(pre_raw);                             // [kStg][4][kSeqPitch]
   __shared__ uint64_t full_bar[kStg];
   const int n_blocks = (S + kBlk - 1) / kBlk;
-  const float* pre_cta = pre0 + lstm * stride_lstm + dir * stride_dir;
+  const PT* pre_cta = pre0 + lstm * stride_lstm + dir * stride_dir;
   auto issue_block = [&](int blk) {
     const int s0 = blk * kBlk, n = min(kBlk, S - s0);
     const int t_lo = dir ? S - s0 - n : s0;
     const uint32_t bar = smem_u32(&full_bar[blk % kStg]);
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * 4 * kG * sizeof(float)));
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(n * 4 * kG * sizeof(PT)));
     __syncwarp();
     if (lane < 4 * n) {
       const int sq = lane / n, r = lane - sq * n;
       const int pbq = (q0 + sq) % (2 * B);
       bulk_g2s(smem_u32(pre_s + ((blk % kStg) * 4 + sq) * kSeqPitch + r * kG), pre_cta + ((int64_t)pbq * S + t_lo + r) * ld,
-               (uint32_t)(kG * sizeof(float)), bar);
+               (uint32_t)(kG * sizeof(PT)), bar);
     }
   };
   if (tid == 0) {
@@ -497,7 +502,7 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const flo
   for (int blk = 0; blk < n_blocks; ++blk) {
     const int nbk = min(kBlk, S - blk * kBlk);
     mbar_wait(smem_u32(&full_bar[stage]), phase);
-    const float* pr = pre_s + (stage * 4 + seq) * kSeqPitch + (dir ? (nbk - 1) * kG : 0) + u;
+    const PT* pr = pre_s + (stage * 4 + seq) * kSeqPitch + (dir ? (nbk - 1) * kG : 0) + u;
     for (int r = 0; r < nbk; ++r) {
       // B fragments: h of sequence nb, this lane's 16 k values (k = 8 ks + l4 + 4 half  <->  position l4*16 + 2 ks + half)
       uint4 hb[2];
@@ -509,7 +514,7 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const flo
       }
       float pcur[4];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) pcur[g] = pr[g * kH];
+      for (int g = 0; g < 4; ++g) pcur[g] = to_float<PT>(pr[g * kH]);
       // two independent accumulation chains per tile (even / odd k steps)
       float d[2][2][4];
 #pragma unroll
@@ -589,12 +594,17 @@ static int gemm_rows(const float* a, int64_t rows, int K, const float* w, const 
 }
 
 static void launch_rec(int nseq, const float* pre, int64_t stride_lstm, int64_t stride_dir, int ld, const float* whh,
-                       float* hout, int B, int S, cudaStream_t s, const float* whh_frag = nullptr) {
+                       float* hout, int B, int S, cudaStream_t s, const float* whh_frag = nullptr, bool pre16 = false) {
   dim3 grid(4 * B / nseq, 2);
+  if (pre16) {   // (only requested with nseq == 4 and the fp16 recurrence)
+    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem / 2);
+    lstm_recurrent4_mma16_kernel<__half><<<grid, 256, kRec4Smem / 2, s>>>(reinterpret_cast<const __half*>(pre), stride_lstm, stride_dir, ld, whh, hout, B, S);
+    return;
+  }
   static const bool tf32_rec = getenv("DCS_LSTM_TF32") && atoi(getenv("DCS_LSTM_TF32")) != 0;   // A/B switch (default: fp16 MMAs)
   if (nseq == 4 && whh_frag && !tf32_rec) {
-    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
-    lstm_recurrent4_mma16_kernel<<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
+    lstm_recurrent4_mma16_kernel<float><<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
   } else if (nseq == 4 && whh_frag) {
     cudaFuncSetAttribute(lstm_recurrent4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
     lstm_recurrent4_mma_kernel<<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh_frag, hout, B, S);
@@ -605,14 +615,17 @@ static void launch_rec(int nseq, const float* pre, int64_t stride_lstm, int64_t 
   else lstm_recurrent_kernel<2><<<grid, 256, 0, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
 }
 
-// tensor-core input projection (tf32 operands read from fp32 memory): out[rows][256] = a[rows][K] * w[256][K]^T + bias
-static int gemm_rows_tc(const float* a, int64_t rows, int K, const float* w_t, const float* bias, float* out, void* stream) {
+// tensor-core input projections (tf32 operands read from fp32 memory), `nsl` weight slices in ONE launch:
+// out[row][sl][256] = a[row][K] * w[sl][256][K]^T + bias[sl][256].  The slices are the "phases" of the conv kernel with
+// up_w = nsl (output pixel row * nsl + sl reads source pixel row; every phase has the single tap (0, 0)), so the A tile of a
+// row block is re-read from L2, not HBM, and the launch count drops from 8 to 3 per ComplexLSTM.
+static int gemm_rows_tc(const float* a, int64_t rows, int K, const float* w_t, const float* bias, void* out, int nsl, void* stream, bool out16 = false) {
   dcs_cconv_params c;
   memset(&c, 0, sizeof(c));
   c.src0 = a; c.c0 = K / 2; c.c1 = 0;
-  c.batch = 1; c.in_h = 1; c.in_w = (int)rows; c.out_h = 1; c.out_w = (int)rows; c.cout = kG / 2;
-  c.up_h = c.up_w = 1; c.stride_h = c.stride_w = 1; c.ntaps = 1;
-  c.weight = w_t; c.bias = bias; c.act = DCS_ACT_NONE; c.dst = out; c.in_dtype = DCS_F32; c.out_dtype = DCS_F32;
+  c.batch = 1; c.in_h = 1; c.in_w = (int)rows; c.out_h = 1; c.out_w = (int)rows * nsl; c.cout = kG / 2;
+  c.up_h = 1; c.up_w = nsl; c.stride_h = c.stride_w = 1; c.ntaps = 1;
+  c.weight = w_t; c.bias = bias; c.bias_phase_stride = kG; c.act = DCS_ACT_NONE; c.dst = out; c.in_dtype = DCS_F32; c.out_dtype = out16 ? DCS_F16 : DCS_F32;
   return dcs_cconv2d_tc_fwd(&c, stream);
 }
 
@@ -651,16 +664,22 @@ extern "C" int dcs_clstm_fwd(const dcs_clstm_params* p, void* stream) {
   const float* whh1 = p->w_hh + (int64_t)4 * kG * kH;
   const int64_t rows2 = 2 * rows;
   if (p->w_ih0_t && p->w_ih1_t) {
-    // ---- tensor-core (tf32) input projections: pre[(lstm,dir)][(part,b,s)][4H], eight N=256 GEMMs
-    for (int sl = 0; sl < 4; ++sl)
-      if (int e = gemm_rows_tc(w.xp, rows2, D, p->w_ih0_t + (int64_t)sl * kG * D, p->bias + sl * kG, w.pre + sl * rows2 * kG, stream)) return e;
-    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, p->w_hh, w.h0, B, S, s, p->w_hh_frag);
+    // ---- tensor-core (tf32) input projections.  layer 0: pre[(part,b,s)][lstm][dir][4H], ONE launch (4 weight slices)
+    // fp16 pre-activations with the fp16 recurrence (DCS_LSTM_PRE32=1 keeps fp32 pre-activations: A/B runs)
+    static const bool pre32 = getenv("DCS_LSTM_PRE32") && atoi(getenv("DCS_LSTM_PRE32")) != 0;
+    static const bool tf32_rec_ = getenv("DCS_LSTM_TF32") && atoi(getenv("DCS_LSTM_TF32")) != 0;
+    const bool pre16 = !pre32 && !tf32_rec_ && nseq == 4 && p->w_hh_frag;
+    __half* pre_h = reinterpret_cast<__half*>(w.pre);
+    if (int e = gemm_rows_tc(w.xp, rows2, D, p->w_ih0_t, p->bias, w.pre, 4, stream, pre16)) return e;
+    launch_rec(nseq, w.pre, 2 * kG, kG, 4 * kG, p->w_hh, w.h0, B, S, s, p->w_hh_frag, pre16);
     DCS_LAUNCHED();
-    for (int sl = 0; sl < 4; ++sl)
-      if (int e = gemm_rows_tc(w.h0 + (int64_t)(sl / 2) * rows2 * 2 * kH, rows2, 2 * kH, p->w_ih1_t + (int64_t)sl * kG * 2 * kH,
-                               p->bias + 4 * kG + sl * kG, w.pre + sl * rows2 * kG, stream)) return e;
-    launch_rec(nseq, w.pre, 2 * rows2 * kG, rows2 * kG, kG, whh1, w.h1, B, S, s,
-               p->w_hh_frag ? p->w_hh_frag + (int64_t)4 * kG * kH : nullptr);
+    // layer 1: per lstm, rows (part,b,s) of h0[lstm] -> pre1[lstm][(part,b,s)][dir][4H], one launch per lstm (2 slices)
+    for (int l = 0; l < 2; ++l)
+      if (int e = gemm_rows_tc(w.h0 + (int64_t)l * rows2 * 2 * kH, rows2, 2 * kH, p->w_ih1_t + (int64_t)l * 2 * kG * 2 * kH,
+                               p->bias + 4 * kG + l * 2 * kG, pre16 ? (void*)(pre_h + (int64_t)l * rows2 * 2 * kG) : (void*)(w.pre + (int64_t)l * rows2 * 2 * kG),
+                               2, stream, pre16)) return e;
+    launch_rec(nseq, w.pre, rows2 * 2 * kG, kG, 2 * kG, whh1, w.h1, B, S, s,
+               p->w_hh_frag ? p->w_hh_frag + (int64_t)4 * kG * kH : nullptr, pre16);
     DCS_LAUNCHED();
   } else {
     // ---- fp32 CUDA-core projections.  layer 0: pre[(part,b,s)][lstm][dir][4H]

@@ -128,6 +128,7 @@ typedef struct {
   void* dst; int in_dtype; int out_dtype;
   int64_t* pool_sums;
   int pool_mode;   /* DCS_POOL_SUM / DCS_POOL_MAX (tcgen05 path) */
+  int bias_phase_stride; /* tcgen05 path: floats between the bias vectors of consecutive phases; 0 = one bias vector for all phases */
 } dcs_cconv_params;
 int dcs_cconv2d_fwd(const dcs_cconv_params* p, void* stream);    /* fp32 CUDA-core path (<=1e-5 mode) */
 int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream); /* tcgen05/TMEM/TMA path (fp16 / bf16 / tf32) */

@@ -7,7 +7,7 @@ from dcsnet_b200 import ops
 import bench
 B, T = 64, 2000
 sd = bench.make_weights()
-plan = D.ForwardPlan(D.PackedNet(sd, "cuda", "bf16"), B, T, want_aux=False)
+plan = D.ForwardPlan(D.PackedNet(sd, "cuda", "fp16"), B, T, want_aux=False)
 g = torch.Generator().manual_seed(0)
 plan.audio_in.copy_(0.1 * torch.randn(B, 32 * (T - 1), generator=g))
 plan._enqueue_from_audio(); torch.cuda.synchronize()
