@@ -387,7 +387,7 @@ def ncu_family_summary():
     summary is committed."""
     import csv
     import glob
-    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")))
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")) if "_real_" not in os.path.basename(f))
     if not files:
         return None, None, None
     rows = list(csv.reader(open(files[-1])))

@@ -22,6 +22,7 @@
 #include "tc_ptx.cuh"
 #include <stdlib.h>
 #include <type_traits>
+#include <algorithm>
 
 namespace dcs {
 
@@ -433,8 +434,6 @@ __global__ void __launch_bounds__(kAsThreads, 2) attention_stream_kernel(const A
 //      conflict-free LDS.32 per MMA, no im2col), B = the taps shifted by the output row, W[y' - j][kx][ci][o];
 //   3. y = gate_s * (gate_c * x) for the H x 16 strip pixels, 16-byte loads / stores, consecutive lanes on consecutive
 //      addresses.
-constexpr int kAtTW = 16, kAtPW = kAtTW + 6, kAtStPitch = 24;
-
 __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -445,35 +444,47 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   return v;
 }
 
-template <int C, bool REAL, int kAtThreads>
-__global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const AttStreamArgs a) {
+
+// Generalised to row BANDS for the tall few-channel tensors (C = 8: 128 x 1000 pixels per image): a tile is RH output rows x
+// TW output columns plus a 3-pixel halo on every side that lies inside the image (statistics of the halo pixels are
+// recomputed: 1.34 x the pixels at RH = 32, TW = 48), grid = (column strips, images, bands).  The row-streaming kernel needs
+// ~14 warp instructions per pixel at C = 8 (register ring of pending conv rows, three CTA barriers per row pair); the flat
+// phases need ~8.
+template <int C, bool REAL, int NT, int TW>
+__global__ void __launch_bounds__(NT, 2) attention_tile_kernel(const AttStreamArgs a) {
   using T = __half;
-  constexpr int PW = kAtPW, TW = kAtTW;
+  constexpr int PW = TW + 6;                  // x-tile row: strip + 3-pixel halo each side
+  constexpr int SP = TW + 8;                  // statistics row pitch in pixels (the MMA's sliding window reads up to pixel TW + 6)
+  constexpr int NSEG = TW / 16;               // 16-pixel MMA segments per row
   constexpr int VPP = C / 4;                  // 16-byte vectors per pixel
-  constexpr int VPL = 1024 / kAtThreads;      // vectors per lane in the statistics phase (4 at 256 threads, 2 at 512)
+  constexpr int VPL = VPP < 1024 / NT ? VPP : 1024 / NT;   // vectors per lane in the statistics phase (<= 4 at 256 threads)
   constexpr int G = VPP / VPL;                // lanes per pixel in the statistics phase
-  constexpr int PPI = kAtThreads / G;         // pixels per statistics iteration (a multiple of 4: the read rotation is per thread)
-  constexpr int QS = kAtThreads / VPP;        // output pixels per product iteration
+  constexpr int PPI = NT / G;                 // pixels per statistics iteration (a multiple of 8: the read rotation is per thread)
+  constexpr int RSH = VPP >= 8 ? 0 : (VPP == 4 ? 1 : 2);   // rotation = (pixel >> RSH) & (VPL - 1): conflict-free quarter warps
+  constexpr int QS = NT / VPP;                // output pixels per product iteration
   constexpr int NW7 = REAL ? 98 : 196;
-  static_assert(G >= 2 && G <= 16 && VPP * 4 == C && (VPL == 2 || VPL == 4), "tile attention: C = 32, 64 or 128");
+  static_assert(TW % 16 == 0 && VPP * 4 == C && VPL * G == VPP && (VPL == 2 || VPL == 4) && G <= 16, "tile attention geometry");
 
   extern __shared__ __align__(128) unsigned char as_smem[];
-  const int H = a.H, W = a.W;
-  const int HP = (H + 3) & ~3;
+  const int H = a.H, W = a.W, RH = a.NR;      // RH = band height (= H for the whole-strip launches)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.y, x0 = blockIdx.x * TW;
-  unsigned char* xs = as_smem;                                                         // [H][PW][C] complex fp16
-  uint2* st = reinterpret_cast<uint2*>(xs + (size_t)H * PW * C * 4);                    // [HP + 6][24] 4 x fp16 statistics
-  float2* sg = reinterpret_cast<float2*>(st + (size_t)(HP + 6) * kAtStPitch);            // [HP][16] spatial gate
-  float2* gs = sg + HP * TW;                                                           // [C] channel gate
+  const int b = blockIdx.y, x0 = blockIdx.x * TW, r0 = blockIdx.z * RH;
+  const int rh = min(RH, H - r0);                                  // output rows of this band
+  const int lo = max(r0 - 3, 0), hi = min(r0 + rh + 3, H);         // image rows held in the x tile
+  const int nxr = hi - lo, soff = lo - r0 + 3;                     // statistics slot of x-tile row i = i + soff (slot s <-> image row r0 - 3 + s)
+  const int NXR = min(RH + 6, H), RHP = (RH + 3) & ~3;             // allocation sizes (same for every band)
+  unsigned char* xs = as_smem;                                                         // [NXR][PW][C] complex fp16
+  uint2* st = reinterpret_cast<uint2*>(xs + (size_t)NXR * PW * C * 4);                  // [RHP + 6][SP] 4 x fp16 statistics
+  float2* sg = reinterpret_cast<float2*>(st + (size_t)(RHP + 6) * SP);                  // [RHP][TW] spatial gate
+  float2* gs = sg + RHP * TW;                                                          // [C] channel gate
   float2* avg = gs + C;                                                                // [C]
   float2* hid = avg + C;                                                               // [16]
   float* w7s = reinterpret_cast<float*>(hid + 16);                                     // [196]
   uint2* bt = reinterpret_cast<uint2*>(w7s + 196);                                     // [20][32] B fragments of the gate conv
   uint64_t* full = reinterpret_cast<uint64_t*>(bt + 20 * 32);                          // [4] one per group of RG rows
   const uint32_t xs_u32 = smem_u32(xs), st_u32 = smem_u32(st), full_u32 = smem_u32(full);
-  const int RG = (H + 3) >> 2;                                                         // rows per arrival group (<= 4 groups)
+  const int RG = (nxr + 3) >> 2;                                                       // rows per arrival group (<= 4 groups)
 
   // ---- rows -> shared memory (one bulk copy per row: the strip's columns are contiguous in the channels-last layout)
   const int xa = max(x0 - 3, 0), xe = min(x0 + TW + 3, W);
@@ -484,16 +495,16 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid < H) {
+  if (tid < nxr) {
     const int grp = tid / RG;
     const uint32_t bar = full_u32 + 8 * grp;
-    if (tid == grp * RG) mbar_expect_tx(bar, (uint32_t)(min(RG, H - grp * RG)) * seg_bytes);   // one arrival per group; the copies may land in any order
+    if (tid == grp * RG) mbar_expect_tx(bar, (uint32_t)(min(RG, nxr - grp * RG)) * seg_bytes);   // one arrival per group; the copies may land in any order
     bulk_g2s(xs_u32 + (uint32_t)tid * (PW * C * 4) + seg_off,
-             reinterpret_cast<const T*>(a.x) + (((int64_t)b * H + tid) * W + xa) * C * 2, seg_bytes, bar);
+             reinterpret_cast<const T*>(a.x) + (((int64_t)b * H + lo + tid) * W + xa) * C * 2, seg_bytes, bar);
   }
-  for (int i = tid; i < (HP + 6) * kAtStPitch; i += kAtThreads) st[i] = make_uint2(0u, 0u);
-  for (int i = tid; i < NW7; i += kAtThreads) w7s[i] = a.w7[i];
-  for (int c = tid; c < C; c += kAtThreads) {
+  for (int i = tid; i < (RHP + 6) * SP; i += NT) st[i] = make_uint2(0u, 0u);
+  for (int i = tid; i < NW7; i += NT) w7s[i] = a.w7[i];
+  for (int c = tid; c < C; c += NT) {
     if constexpr (REAL) avg[c] = make_float2(pool_max_value(a.sums, ((int64_t)b * C + c) * 2), pool_max_value(a.sums, ((int64_t)b * C + c) * 2 + 1));
     else avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
   }
@@ -502,7 +513,7 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
   // ---- B fragments of the gate conv (phase 2), one (b0, b1) pair per (k-step, lane): k-step ks = (statistics row y' = ks / 2,
   //      kx half s = ks % 2); lane (g, t): column n = g = (output row j = g / 2, part o = g % 2), k pair (2 t, 2 t + 1) [+ 8]
   //      -> kx = 4 s + t / 2 [+ 2], ci = 2 (t % 2), 2 (t % 2) + 1 = (re, im) of statistics input t % 2; tap row ky = y' - j.
-  for (int e = tid; e < 20 * 32; e += kAtThreads) {
+  for (int e = tid; e < 20 * 32; e += NT) {
     const int ks = e >> 5, ln = e & 31, gg = ln >> 2, tt = ln & 3;
     const int ky = (ks >> 1) - (gg >> 1), o = gg & 1, cp = tt & 1;
     uint32_t bfr[2];
@@ -524,7 +535,7 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
   }
 
   // ---- channel gate (same arithmetic as the streaming kernel; all loads of a pass in flight together)
-  for (int r = warp; r < a.R; r += kAtThreads / 32) {
+  for (int r = warp; r < a.R; r += NT / 32) {
     float re = 0.f, im = 0.f;
 #pragma unroll
     for (int c = lane; c < C; c += 32) {
@@ -561,10 +572,10 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
   }
   __syncthreads();
 
-  // ---- 1. statistics: thread = (pixel f0 + j PPI, vectors sub + G ((k + rot) & 3)); the rotation spreads the lanes of a
-  //         quarter warp over all 32 banks (pixels are 128 / 256 / 512 bytes apart)
+  // ---- 1. statistics: thread = (pixel f0 + j PPI, vectors sub + G ((k + rot) & (VPL - 1))); the rotation spreads the lanes of
+  //         a quarter warp over all 32 banks (pixels are 32 ... 512 bytes apart)
   {
-    const int sub = tid % G, f0 = tid / G, rot = f0 & (VPL - 1);
+    const int sub = tid % G, f0 = tid / G, rot = (f0 >> RSH) & (VPL - 1);
     GPair sgate[VPL][2];
     uint32_t voff[VPL];
 #pragma unroll
@@ -578,13 +589,13 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
         sgate[k][h2].nim = make_float2(-ga.y, -gb.y);
       }
     }
-    const int npix = H * PW;
+    const int npix = nxr * PW;
     const float invC = 1.f / (float)C;
     int waited = -1;
     for (int fb = 0; fb < npix; fb += PPI) {
       const bool valid = fb + f0 < npix;
       const int f = valid ? fb + f0 : npix - 1;
-      const int r = f / PW, p = f - r * PW;
+      const int r = f / PW, p = f - r * PW;                              // x-tile row, padded column
       const int grp = (r >= RG) + (r >= 2 * RG) + (r >= 3 * RG);       // r / RG without the runtime division
       if (grp > waited) { for (int q = waited + 1; q <= grp; ++q) mbar_wait(full_u32 + 8 * q, 0); waited = grp; }
       const uint32_t base = xs_u32 + (uint32_t)f * (C * 4);
@@ -613,36 +624,41 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
         mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
       }
       if (valid && sub == 0 && (unsigned)(x0 - 3 + p) < (unsigned)W)      // columns outside the image keep their zeros
-        st[(r + 3) * kAtStPitch + p] = REAL ? make_uint2(pack_f16x2(sr * invC, mr), 0u)       // ci = (mean, max, -, -)
-                                            : make_uint2(pack_f16x2(sr * invC, si * invC), pack_f16x2(mr, mi));
+        st[(r + soff) * SP + p] = REAL ? make_uint2(pack_f16x2(sr * invC, mr), 0u)       // ci = (mean, max, -, -)
+                                       : make_uint2(pack_f16x2(sr * invC, si * invC), pack_f16x2(mr, mi));
     }
   }
   __syncthreads();
 
-  // ---- 2. gate conv: warp w -> output rows 4 w .. 4 w + 3 (two accumulators: half the dependent MMA chain)
-  if (4 * warp < H) {
-    const int r0 = 4 * warp;
-    float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t a_base = st_u32 + (uint32_t)((r0 * kAtStPitch + g + (t >> 1)) * 8 + (t & 1) * 4);
+  // ---- 2. gate conv: unit = (group of 4 output rows, 16-pixel segment), two accumulators (half the dependent MMA chain)
+  {
+    const int nunits = ((rh + 3) >> 2) * NSEG;
     const uint32_t b_base = smem_u32(bt) + (uint32_t)lane * 8;
+    for (int u = warp; u < nunits; u += NT / 32) {
+      const int rg = u / NSEG, sgm = u - rg * NSEG;
+      const int rr0 = 4 * rg;
+      float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint32_t a_base = st_u32 + (uint32_t)((rr0 * SP + sgm * 16 + g + (t >> 1)) * 8 + (t & 1) * 4);
 #pragma unroll
-    for (int ks = 0; ks < 20; ++ks) {
-      const uint32_t aa = a_base + (uint32_t)(((ks >> 1) * kAtStPitch + 4 * (ks & 1)) * 8);
-      uint2 bb;
-      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bb.x), "=r"(bb.y) : "r"(b_base + ks * 256));
-      if (ks & 1) mma_f16_16x8x16(d2, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
-      else mma_f16_16x8x16(d, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
-    }
+      for (int ks = 0; ks < 20; ++ks) {
+        const uint32_t aa = a_base + (uint32_t)(((ks >> 1) * SP + 4 * (ks & 1)) * 8);
+        uint2 bb;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bb.x), "=r"(bb.y) : "r"(b_base + ks * 256));
+        if (ks & 1) mma_f16_16x8x16(d2, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
+        else mma_f16_16x8x16(d, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
+      }
 #pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] += d2[i];
-    const int r = r0 + t;                     // accumulator columns 2 t, 2 t + 1 = (re, im) of output row r0 + t
-    if (r < H) {
-      if constexpr (REAL) {
-        sg[r * TW + g] = make_float2(sigmoid_ex2(d[0]), 0.f);
-        sg[r * TW + g + 8] = make_float2(sigmoid_ex2(d[2]), 0.f);
-      } else {
-        sg[r * TW + g] = make_float2(sigmoid_ex2(d[0]), sigmoid_ex2(d[1]));
-        sg[r * TW + g + 8] = make_float2(sigmoid_ex2(d[2]), sigmoid_ex2(d[3]));
+      for (int i = 0; i < 4; ++i) d[i] += d2[i];
+      const int rl = rr0 + t;                   // accumulator columns 2 t, 2 t + 1 = (re, im) of output row rr0 + t
+      if (rl < rh) {
+        float2* o = sg + rl * TW + sgm * 16 + g;
+        if constexpr (REAL) {
+          o[0] = make_float2(sigmoid_ex2(d[0]), 0.f);
+          o[8] = make_float2(sigmoid_ex2(d[2]), 0.f);
+        } else {
+          o[0] = make_float2(sigmoid_ex2(d[0]), sigmoid_ex2(d[1]));
+          o[8] = make_float2(sigmoid_ex2(d[2]), sigmoid_ex2(d[3]));
+        }
       }
     }
   }
@@ -657,14 +673,15 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
       const float2 ga = gs[vi * 4 + 2 * h2], gb = gs[vi * 4 + 2 * h2 + 1];
       agate[h2].re = make_float2(ga.x, gb.x); agate[h2].im = make_float2(ga.y, gb.y); agate[h2].nim = make_float2(-ga.y, -gb.y);
     }
-    const int nq = H * TW;
-    T* ybase = reinterpret_cast<T*>(a.y) + (((int64_t)b * H * W + x0) * C + vi * 4) * 2;
+    const int nq = rh * TW;
+    const int xrow0 = r0 - lo;                  // x-tile row of output row 0 of the band
+    T* ybase = reinterpret_cast<T*>(a.y) + ((((int64_t)b * H + r0) * W + x0) * C + vi * 4) * 2;
 #pragma unroll 4
     for (int q = q0; q < nq; q += QS) {
-      const int r = q >> 4, px = q & 15;
+      const int rl = q / TW, px = q - rl * TW;
       if (x0 + px < W) {
         CPair p01, p23;
-        unpack_pairs<T>(lds128(xs_u32 + (uint32_t)(((r * PW + 3 + px) * VPP + vi) * 16)), p01, p23);
+        unpack_pairs<T>(lds128(xs_u32 + (uint32_t)((((xrow0 + rl) * PW + 3 + px) * VPP + vi) * 16)), p01, p23);
         const float2 gsp = sg[q];
         const float2 gre = make_float2(gsp.x, gsp.x), gim = make_float2(gsp.y, gsp.y), gnim = make_float2(-gsp.y, -gsp.y);
         float2 r01, i01, r23, i23;
@@ -676,7 +693,7 @@ __global__ void __launch_bounds__(kAtThreads, 2) attention_tile_kernel(const Att
           r01 = fma2(gre, u01.re, mul2(gnim, u01.im)); i01 = fma2(gre, u01.im, mul2(gim, u01.re));
           r23 = fma2(gre, u23.re, mul2(gnim, u23.im)); i23 = fma2(gre, u23.im, mul2(gim, u23.re));
         }
-        *reinterpret_cast<uint4*>(ybase + ((int64_t)r * W + px) * C * 2) =
+        *reinterpret_cast<uint4*>(ybase + ((int64_t)rl * W + px) * C * 2) =
             make_uint4(pack_h2<T>(r01.x, i01.x), pack_h2<T>(r01.y, i01.y), pack_h2<T>(r23.x, i23.x), pack_h2<T>(r23.y, i23.y));
       }
     }
@@ -705,18 +722,20 @@ static int launch_attention_stream(const dcs_attention_params* p, cudaStream_t s
   return 0;
 }
 
-template <int C, bool REAL, int NT>
-static int launch_attention_tile_nt(const dcs_attention_params* p, cudaStream_t s) {
-  const int H = p->h, HP = (H + 3) & ~3;
-  const size_t smem = (size_t)H * kAtPW * C * 4 + (size_t)(HP + 6) * kAtStPitch * 8 + (size_t)HP * kAtTW * 8 + (size_t)(2 * C + 16) * 8 + 196 * 4 + 20 * 32 * 8 + 4 * 8;
-  DCS_REQUIRE(smem <= 113 * 1024, "dcs_attention_stream: tile does not fit shared memory (C=%d, H=%d)", C, H);
+template <int C, bool REAL, int NT, int TW>
+static int launch_attention_tile_nt(const dcs_attention_params* p, cudaStream_t s, int RH) {
+  const int H = p->h;
+  if (RH <= 0 || RH > H) RH = H;
+  const int NXR = std::min(RH + 6, H), RHP = (RH + 3) & ~3;
+  const size_t smem = (size_t)NXR * (TW + 6) * C * 4 + (size_t)(RHP + 6) * (TW + 8) * 8 + (size_t)RHP * TW * 8 + (size_t)(2 * C + 16) * 8 + 196 * 4 + 20 * 32 * 8 + 4 * 8;
+  DCS_REQUIRE(smem <= 113 * 1024 && NXR <= NT, "dcs_attention_stream: tile does not fit shared memory (C=%d, H=%d, band %d)", C, H, RH);
   AttStreamArgs a;
   a.x = p->x; a.y = p->y; a.sums = reinterpret_cast<const long long*>(p->sums); a.inv_hw = 1.f / ((float)p->h * (float)p->w);
   a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
-  a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = 0;
-  DCS_CUDA(cudaFuncSetAttribute(attention_tile_kernel<C, REAL, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((p->w + kAtTW - 1) / kAtTW, p->batch);
-  attention_tile_kernel<C, REAL, NT><<<grid, NT, smem, s>>>(a);
+  a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = RH;
+  DCS_CUDA(cudaFuncSetAttribute(attention_tile_kernel<C, REAL, NT, TW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p->w + TW - 1) / TW, p->batch, (H + RH - 1) / RH);
+  attention_tile_kernel<C, REAL, NT, TW><<<grid, NT, smem, s>>>(a);
   DCS_LAUNCHED();
   return 0;
 }
@@ -725,13 +744,24 @@ static int launch_attention_tile_nt(const dcs_attention_params* p, cudaStream_t 
 template <int C, bool REAL>
 static int launch_attention_tile(const dcs_attention_params* p, cudaStream_t s) {
   static const bool nt512 = [] { const char* e = getenv("DCS_ATT_TILE_NT"); return e && atoi(e) == 512; }();
-  return nt512 ? launch_attention_tile_nt<C, REAL, 512>(p, s) : launch_attention_tile_nt<C, REAL, 256>(p, s);
+  return nt512 ? launch_attention_tile_nt<C, REAL, 512, 16>(p, s, 0) : launch_attention_tile_nt<C, REAL, 256, 16>(p, s, 0);
 }
 
-// DCS_ATT_TILE=0 keeps the row-streaming kernel for every tensor (A/B runs)
+// DCS_ATT_TILE=0 keeps the row-streaming kernel for every tensor, DCS_ATT_BAND=0 for the tall few-channel tensors (A/B runs)
 static bool att_tile_enabled() {
   static const bool on = [] { const char* e = getenv("DCS_ATT_TILE"); return !(e && e[0] == '0'); }();
   return on;
+}
+static int att_band_rh() {     // band height at C = 8 (DCS_ATT_BAND_RH: 16 = three resident CTAs, 32 = two, less halo)
+  static const int m = [] { const char* e = getenv("DCS_ATT_BAND_RH"); const int v = e ? atoi(e) : 32; return v >= 8 && v <= 32 ? v : 32; }();
+  return m;
+}
+// Row bands for C = 8 / 16 are OFF by default: measured on B200 (batch 64 x 4 s) the band kernel needs 102 M warp instructions
+// for a C = 8 tensor against the streaming kernel's 110 M at the same issue rate (225 vs 212 us) — the halo statistics (1.34 x),
+// the per-CTA prologue (5376 CTAs) and the gate conv's fragment loads eat what the missing barriers save.
+static int att_band_mask() {   // DCS_ATT_BAND: bit 0: C = 8, bit 1: C = 16
+  static const int m = [] { const char* e = getenv("DCS_ATT_BAND"); return e ? atoi(e) : 0; }();
+  return m;
 }
 
 template <typename T, bool REAL = false>
@@ -746,6 +776,11 @@ static int dispatch_attention_stream(const dcs_attention_params* p, cudaStream_t
         default: break;
       }
     }
+    // tall few-channel tensors: row bands of the same kernel (32 x 48 pixels at C = 8, 24 x 32 at C = 16, + halo)
+    if (att_tile_enabled() && p->channels == 8 && (att_band_mask() & 1) && p->h >= 32 && p->w >= 48)
+      return launch_attention_tile_nt<8, REAL, 256, 48>(p, s, att_band_rh());
+    if (att_tile_enabled() && p->channels == 16 && (att_band_mask() & 2) && p->h >= 24 && p->w >= 32)
+      return launch_attention_tile_nt<16, REAL, 256, 32>(p, s, 24);
   }
   // strip width: 128 pixels (every warp owns 16) for the few-channel tensors; narrow strips where a row of C channels is
   // long (ring of 8 rows) and the tensor has few pixels (enough CTAs), or where the image itself is narrow

@@ -144,6 +144,10 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
   }
   for (int i = threadIdx.x; i < a.n_pad; i += kTcThreads) bars->bias[i] = a.bias[i];
   const float* bias_s = bars->bias;
+  // per-phase bias vectors (the merged LSTM input projections): all of them, behind the epilogue staging tiles
+  float* bias_ph = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(bars + 1) + 8 * kEpiStageBytes);
+  if (a.bias_stride)
+    for (int i = threadIdx.x; i < a.phases * a.n_pad; i += kTcThreads) bias_ph[i] = a.bias[(i / a.n_pad) * a.bias_stride + (i % a.n_pad)];
   tc_fence_before();
   if constexpr (CTA2) cluster_sync_all(); else __syncthreads();   // the peer's barriers must exist before any remote arrive / commit
   tc_fence_after();
@@ -461,12 +465,12 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
         __syncwarp();
         // element offset of the rows this lane STORES: fp32 rows (lane >> 3) + 4 j (two 16-row passes, j < 8),
         // bf16 rows (lane >> 2) + 8 j (j < 4)
-        long long prow[8];
+        int prow[8];                                   // output PIXEL index (< 2^31) of the stored rows, -1 outside the tensor
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const int r = a.out_f32 ? (lane >> 3) + 4 * j : (lane >> 2) + 8 * (j & 3);
           const long long pv = pixs[r];
-          prow[j] = pv < 0 ? -1ll : pv * a.n_real;
+          prow[j] = pv < 0 ? -1 : (int)pv;
         }
         mbar_wait(smem_u32(&bars->acc_full[acc]), acc_phase, dwe);
         tc_fence_after();
@@ -482,9 +486,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
           // instruction stream: a per-value runtime switch cost ~8 instructions per accumulator element)
           float v[32];
           {
-            // (per-phase bias vectors — the merged LSTM input projections — are read from global memory: warp-uniform, L1 hits)
-            const float4* b4 = a.bias_stride ? reinterpret_cast<const float4*>(a.bias + (int64_t)ph_idx * a.bias_stride + n0)
-                                             : reinterpret_cast<const float4*>(bias_s + n0);
+            const float4* b4 = reinterpret_cast<const float4*>((a.bias_stride ? bias_ph + ph_idx * a.n_pad : bias_s) + n0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 bb = b4[q];
@@ -531,8 +533,8 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                   float4 t;
                   asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w)
                                : "r"(est_u32 + (uint32_t)((lane >> 3) + 4 * i) * 144u + (uint32_t)(lane & 7) * 16u));
-                  const long long pr = prow[4 * pass + i];
-                  if (pr >= 0) *reinterpret_cast<float4*>(ob + pr) = t;
+                  const int pr = prow[4 * pass + i];
+                  if (pr >= 0) *reinterpret_cast<float4*>(ob + (int64_t)pr * a.n_real) = t;
                 }
                 __syncwarp();
               }
@@ -558,7 +560,7 @@ cconv_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant_
                 uint4 t;
                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w)
                              : "r"(est_u32 + (uint32_t)((lane >> 2) + 8 * i) * 80u + (uint32_t)(lane & 3) * 16u));
-                if (prow[i] >= 0) *reinterpret_cast<uint4*>(ob + prow[i]) = t;
+                if (prow[i] >= 0) *reinterpret_cast<uint4*>(ob + (int64_t)prow[i] * a.n_real) = t;
               }
               __syncwarp();
             }
@@ -834,7 +836,8 @@ extern "C" int dcs_cconv2d_tc_fwd(const dcs_cconv_params* p, void* stream) {
   int n_stages = (int)((200 * 1024) / stage_bytes);
   n_stages = std::max(2, std::min(n_stages, kMaxStages));
   a.n_stages = n_stages;
-  const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers) + 8 * kEpiStageBytes;
+  const size_t smem = 1024 + n_stages * stage_bytes + sizeof(TcBarriers) + 8 * kEpiStageBytes + (a.bias_stride ? (size_t)a.phases * n_pad * 4 : 0);
+  DCS_REQUIRE(smem <= 227 * 1024, "dcs_cconv2d_tc_fwd: per-phase bias vectors do not fit shared memory (%d phases)", a.phases);
 
   CUtensorMap tmA0, tmA1, tmB;
   // (the packed weight matrix is padded to whole 128-byte K blocks; a half-empty last double stage reads zeros out of bounds)
