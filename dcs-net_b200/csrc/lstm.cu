@@ -284,6 +284,14 @@ __device__ __forceinline__ float tanh_mufu(float v) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
   return 2.f * r - 1.f;
 }
+// single-MUFU forms (MUFU.TANH: tanh.approx.f32, max. relative error 2^-11 — the precision of the fp16 h it produces):
+// sigmoid(x) = 0.5 + 0.5 tanh(x / 2).  Two dependent MUFUs less per step on the serial path.
+__device__ __forceinline__ float tanh_hw(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_hw(float v) { return fmaf(0.5f, tanh_hw(0.5f * v), 0.5f); }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint4 a, const uint32_t b0, const uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
@@ -425,7 +433,7 @@ __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], c
 // PT = storage type of the pre-activations: float, or __half (the tensor-core mode: the projection GEMMs then write and this
 // kernel reads half the bytes — the projections are bound by their 262 MB fp32 output per layer; fp16 pre-activations carry
 // the same 11-bit significand as the fp16 h / W_hh products they are added to).
-template <typename PT>
+template <typename PT, bool HWTANH>
 __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const PT* __restrict__ pre0, int64_t stride_lstm,
                                                                      int64_t stride_dir, int ld, const float* __restrict__ whh,
                                                                      float* __restrict__ hout, int B, int S) {
@@ -546,9 +554,16 @@ __global__ void __launch_bounds__(256, 1) lstm_recurrent4_mma16_kernel(const PT*
       const bool odd = l4 >= 2;
       const float ri = (odd ? oi : gi[0]) + pcur[0], rf = (odd ? of : gf[0]) + pcur[1];
       const float rg = (odd ? og_ : gg[0]) + pcur[2], ro = (odd ? oo : go[0]) + pcur[3];
-      const float ig = sigmoid_mufu(ri), fg = sigmoid_mufu(rf), gt = tanh_mufu(rg), ot = sigmoid_mufu(ro);
-      c_state = fg * c_state + ig * gt;
-      const float h = ot * tanh_mufu(c_state);
+      float ig, fg, gt, ot, h;
+      if constexpr (HWTANH) {
+        ig = sigmoid_hw(ri); fg = sigmoid_hw(rf); gt = tanh_hw(rg); ot = sigmoid_hw(ro);
+        c_state = fg * c_state + ig * gt;
+        h = ot * tanh_hw(c_state);
+      } else {
+        ig = sigmoid_mufu(ri); fg = sigmoid_mufu(rf); gt = tanh_mufu(rg); ot = sigmoid_mufu(ro);
+        c_state = fg * c_state + ig * gt;
+        h = ot * tanh_mufu(c_state);
+      }
       hwr[(cur ^ 1) * (4 * kH)] = __float2half_rn(h);
       *hq = h;
       hq += hstep; pr += pstep; cur ^= 1;
@@ -597,14 +612,20 @@ static void launch_rec(int nseq, const float* pre, int64_t stride_lstm, int64_t 
                        float* hout, int B, int S, cudaStream_t s, const float* whh_frag = nullptr, bool pre16 = false) {
   dim3 grid(4 * B / nseq, 2);
   if (pre16) {   // (only requested with nseq == 4 and the fp16 recurrence)
-    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem / 2);
-    lstm_recurrent4_mma16_kernel<__half><<<grid, 256, kRec4Smem / 2, s>>>(reinterpret_cast<const __half*>(pre), stride_lstm, stride_dir, ld, whh, hout, B, S);
+    static const bool hwtanh = getenv("DCS_LSTM_HWTANH") && atoi(getenv("DCS_LSTM_HWTANH")) != 0;
+    if (hwtanh) {
+      cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<__half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem / 2);
+      lstm_recurrent4_mma16_kernel<__half, true><<<grid, 256, kRec4Smem / 2, s>>>(reinterpret_cast<const __half*>(pre), stride_lstm, stride_dir, ld, whh, hout, B, S);
+    } else {
+      cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<__half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem / 2);
+      lstm_recurrent4_mma16_kernel<__half, false><<<grid, 256, kRec4Smem / 2, s>>>(reinterpret_cast<const __half*>(pre), stride_lstm, stride_dir, ld, whh, hout, B, S);
+    }
     return;
   }
   static const bool tf32_rec = getenv("DCS_LSTM_TF32") && atoi(getenv("DCS_LSTM_TF32")) != 0;   // A/B switch (default: fp16 MMAs)
   if (nseq == 4 && whh_frag && !tf32_rec) {
-    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
-    lstm_recurrent4_mma16_kernel<float><<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
+    cudaFuncSetAttribute(lstm_recurrent4_mma16_kernel<float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
+    lstm_recurrent4_mma16_kernel<float, false><<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh, hout, B, S);
   } else if (nseq == 4 && whh_frag) {
     cudaFuncSetAttribute(lstm_recurrent4_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kRec4Smem);
     lstm_recurrent4_mma_kernel<<<grid, 256, kRec4Smem, s>>>(pre, stride_lstm, stride_dir, ld, whh_frag, hout, B, S);
