@@ -58,18 +58,14 @@ __global__ void __launch_bounds__(512) rlstm_recurrent_kernel(const float* __res
 constexpr int kRH = 128, kRG = 4 * kRH;
 constexpr int kRBlk = 4, kRStg = 3, kRPitch = kRBlk * kRG + 8;   // steps per ring stage, stages, floats per sequence per stage
 
-__device__ __forceinline__ float rl_sigmoid(float v) {   // MUFU.EX2 + MUFU.RCP, abs. error ~3e-7; both limits exact
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * v));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+// single-MUFU activations (MUFU.TANH: tanh.approx.f32, max. relative error 2^-11 — the precision of the fp16 h they produce;
+// the ex2 / rcp forms they replace put two more dependent MUFUs per gate on the serial path of every step)
+__device__ __forceinline__ float rl_tanh(float v) {
+  float r;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(v));
   return r;
 }
-__device__ __forceinline__ float rl_tanh(float v) {
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-2.8853900817779268f * v));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
-  return 2.f * r - 1.f;
-}
+__device__ __forceinline__ float rl_sigmoid(float v) { return fmaf(0.5f, rl_tanh(0.5f * v), 0.5f); }
 __device__ __forceinline__ void rl_mma_f16(float (&d)[4], const uint32_t (&a)[4], const uint32_t b0, const uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
