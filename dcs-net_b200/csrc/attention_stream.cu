@@ -438,6 +438,11 @@ __device__ __forceinline__ void mma_f16_16x8x16(float (&d)[4], uint32_t a0, uint
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
+__device__ __forceinline__ uint2 lds64u(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
@@ -511,15 +516,16 @@ __global__ void __launch_bounds__(NT, 2) attention_tile_kernel(const AttStreamAr
   __syncthreads();
 
   // ---- B fragments of the gate conv (phase 2), one (b0, b1) pair per (k-step, lane): k-step ks = (statistics row y' = ks / 2,
-  //      kx half s = ks % 2); lane (g, t): column n = g = (output row j = g / 2, part o = g % 2), k pair (2 t, 2 t + 1) [+ 8]
-  //      -> kx = 4 s + t / 2 [+ 2], ci = 2 (t % 2), 2 (t % 2) + 1 = (re, im) of statistics input t % 2; tap row ky = y' - j.
+  //      kx half s = ks % 2); lane (g, t): column n = g = (output row j = g / 2, part o = g % 2); the k order inside a k-step is
+  //      chosen so that a lane's A registers are the two WORDS of one statistics pixel (one LDS.64): k pair (2 t, 2 t + 1) =
+  //      (re, im) of the mean at kx = 4 s + t, pair (2 t + 8, 2 t + 9) = (re, im) of the max at the same kx; tap row ky = y' - j.
   for (int e = tid; e < 20 * 32; e += NT) {
     const int ks = e >> 5, ln = e & 31, gg = ln >> 2, tt = ln & 3;
-    const int ky = (ks >> 1) - (gg >> 1), o = gg & 1, cp = tt & 1;
+    const int ky = (ks >> 1) - (gg >> 1), o = gg & 1;
     uint32_t bfr[2];
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
-      const int kx = 4 * (ks & 1) + 2 * h2 + (tt >> 1);
+      const int kx = 4 * (ks & 1) + tt, cp = h2;      // k pair (2 t, 2 t + 1) = (re, im) of the mean at kx, pair (2 t + 8, 2 t + 9) = of the max
       float v0 = 0.f, v1 = 0.f;
       if (ky >= 0 && ky < 7 && kx < 7) {
         if constexpr (REAL) {                 // Conv2d(2, 1, 7): ci = (mean, max, -, -), one real output (o = 0)
@@ -638,14 +644,13 @@ __global__ void __launch_bounds__(NT, 2) attention_tile_kernel(const AttStreamAr
       const int rg = u / NSEG, sgm = u - rg * NSEG;
       const int rr0 = 4 * rg;
       float d[4] = {0.f, 0.f, 0.f, 0.f}, d2[4] = {0.f, 0.f, 0.f, 0.f};
-      const uint32_t a_base = st_u32 + (uint32_t)((rr0 * SP + sgm * 16 + g + (t >> 1)) * 8 + (t & 1) * 4);
+      const uint32_t a_base = st_u32 + (uint32_t)((rr0 * SP + sgm * 16 + g + t) * 8);
 #pragma unroll
       for (int ks = 0; ks < 20; ++ks) {
         const uint32_t aa = a_base + (uint32_t)(((ks >> 1) * SP + 4 * (ks & 1)) * 8);
-        uint2 bb;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(bb.x), "=r"(bb.y) : "r"(b_base + ks * 256));
-        if (ks & 1) mma_f16_16x8x16(d2, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
-        else mma_f16_16x8x16(d, lds32(aa), lds32(aa + 64), lds32(aa + 16), lds32(aa + 80), bb.x, bb.y);
+        const uint2 bb = lds64u(b_base + ks * 256), alo = lds64u(aa), ahi = lds64u(aa + 64);   // (a0, a2) of pixel g + kx, (a1, a3) of pixel g + 8 + kx
+        if (ks & 1) mma_f16_16x8x16(d2, alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+        else mma_f16_16x8x16(d, alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
       }
 #pragma unroll
       for (int i = 0; i < 4; ++i) d[i] += d2[i];
@@ -700,6 +705,267 @@ __global__ void __launch_bounds__(NT, 2) attention_tile_kernel(const AttStreamAr
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Row-group streaming kernel for the TALL few-channel tensors (C = 8, 16): the flat phases of the tile kernel above, but a CTA
+// walks DOWN a column strip in groups of FOUR rows — x rows in a ring of NG groups (bulk copies, one barrier per group, two
+// groups ahead), statistics rows in a 16-row ring — so nothing is recomputed vertically (halo: 6 columns per strip) and the
+// gate prologue is paid once per strip.  Step s: statistics of rows 4 s .. 4 s + 3; barrier; gate conv of output rows
+// 4 s - 4 .. 4 s - 1 (one 16-pixel segment per warp, 20 fp16 MMAs from statistics rows 4 s - 7 .. 4 s + 2); barrier; product of
+// those rows.  Two CTA barriers per four rows (the older streaming kernel: three per two rows, plus a register ring of pending
+// conv rows and one shuffle hop per row).
+template <int C, bool REAL, int TW, int NG, int MINB = 2>
+__global__ void __launch_bounds__(256, MINB) attention_rows_kernel(const AttStreamArgs a) {
+  using T = __half;
+  constexpr int NT = 256;
+  constexpr int PW = TW + 6, SP = TW + 8, NSEG = TW / 16;
+  constexpr int VPP = C / 4;
+  constexpr int VPL = VPP < 4 ? VPP : 4;
+  constexpr int G = VPP / VPL;
+  constexpr int PPI = NT / G;
+  constexpr int RSH = VPP >= 8 ? 0 : (VPP == 4 ? 1 : 2);
+  constexpr int QS = NT / VPP;
+  constexpr int NW7 = REAL ? 98 : 196;
+  constexpr int NXR = 4 * NG;                 // x ring rows
+  constexpr uint32_t ROWB = (uint32_t)PW * C * 4;
+  static_assert(TW % 16 == 0 && NSEG <= 8 && NG == 4 && VPL * G == VPP, "row-group attention geometry");
+
+  extern __shared__ __align__(128) unsigned char as_smem[];
+  const int H = a.H, W = a.W;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.y, x0 = blockIdx.x * TW;
+  unsigned char* xs = as_smem;                                                         // [NXR][PW][C] complex fp16
+  uint2* st = reinterpret_cast<uint2*>(xs + (size_t)NXR * ROWB);                        // [16][SP] 4 x fp16 statistics (row & 15)
+  float2* sg = reinterpret_cast<float2*>(st + (size_t)16 * SP);                         // [2][4][TW] spatial gates of two row groups
+  float2* gs = sg + 8 * TW;                                                            // [C] channel gate
+  float2* avg = gs + C;
+  float2* hid = avg + C;
+  float* w7s = reinterpret_cast<float*>(hid + 16);
+  uint2* bt = reinterpret_cast<uint2*>(w7s + 196);                                     // [20][32] B fragments
+  uint64_t* full = reinterpret_cast<uint64_t*>(bt + 20 * 32);                          // [NG]
+  const uint32_t xs_u32 = smem_u32(xs), st_u32 = smem_u32(st), full_u32 = smem_u32(full);
+
+  const int xa = max(x0 - 3, 0), xe = min(x0 + TW + 3, W);
+  const uint32_t seg_bytes = (uint32_t)(xe - xa) * C * 4;
+  const uint32_t seg_off = (uint32_t)(xa - (x0 - 3)) * C * 4;
+  const T* xsrc = reinterpret_cast<const T*>(a.x) + ((int64_t)b * H * W + xa) * C * 2;
+  // rows 4 grp .. 4 grp + 3 -> ring group grp % NG (threads 0..3, one row each; thread 0 arms the barrier)
+  auto issue_group = [&](int grp) {
+    const int r = 4 * grp + tid;
+    const int n = min(4, H - 4 * grp);
+    const uint32_t bar = full_u32 + 8 * (grp % NG);
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)n * seg_bytes);
+    if (tid < n) bulk_g2s(xs_u32 + (uint32_t)((grp % NG) * 4 + tid) * ROWB + seg_off, xsrc + (int64_t)r * W * C * 2, seg_bytes, bar);
+  };
+  if (tid < NG) {
+    mbar_init(full_u32 + 8 * tid, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid < 4) issue_group(0);                          // (group s + 1 is issued after step s's barrier)
+  for (int i = tid; i < 16 * SP; i += NT) st[i] = make_uint2(0u, 0u);
+  for (int i = tid; i < NW7; i += NT) w7s[i] = a.w7[i];
+  for (int c = tid; c < C; c += NT) {
+    if constexpr (REAL) avg[c] = make_float2(pool_max_value(a.sums, ((int64_t)b * C + c) * 2), pool_max_value(a.sums, ((int64_t)b * C + c) * 2 + 1));
+    else avg[c] = make_float2(pool_mean(a.sums, ((int64_t)b * C + c) * 2, a.inv_hw), pool_mean(a.sums, ((int64_t)b * C + c) * 2 + 1, a.inv_hw));
+  }
+  __syncthreads();
+  for (int e = tid; e < 20 * 32; e += NT) {            // B fragments of the gate conv (see attention_tile_kernel)
+    const int ks = e >> 5, ln = e & 31, gg = ln >> 2, tt = ln & 3;
+    const int ky = (ks >> 1) - (gg >> 1), o = gg & 1;
+    uint32_t bfr[2];
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const int kx = 4 * (ks & 1) + tt, cp = h2;      // k pair (2 t, 2 t + 1) = (re, im) of the mean at kx, pair (2 t + 8, 2 t + 9) = of the max
+      float v0 = 0.f, v1 = 0.f;
+      if (ky >= 0 && ky < 7 && kx < 7) {
+        if constexpr (REAL) {
+          if (o == 0 && cp == 0) { v0 = w7s[ky * 7 + kx]; v1 = w7s[49 + ky * 7 + kx]; }
+        } else {
+          const float wr = w7s[cp * 49 + ky * 7 + kx], wi = w7s[98 + cp * 49 + ky * 7 + kx];
+          v0 = o == 0 ? wr : wi; v1 = o == 0 ? -wi : wr;
+        }
+      }
+      bfr[h2] = pack_f16x2(v0, v1);
+    }
+    bt[e] = make_uint2(bfr[0], bfr[1]);
+  }
+  for (int r = warp; r < a.R; r += NT / 32) {           // channel gate (as in the other kernels)
+    float re = 0.f, im = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      if constexpr (REAL) {
+        re += a.w1_r[r * 2 * C + 2 * c] * avg[c].x + a.w1_r[r * 2 * C + 2 * c + 1] * avg[c].y;
+      } else {
+        const float wr = a.w1_r[r * C + c], wi = a.w1_i[r * C + c];
+        re += wr * avg[c].x - wi * avg[c].y;
+        im += wr * avg[c].y + wi * avg[c].x;
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) { re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o); }
+    if (lane == 0) hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+  }
+  __syncthreads();
+  if (tid < C) {
+    const int c = tid;
+    float re = 0.f, im = 0.f;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if (r < a.R) {
+        if constexpr (REAL) {
+          re += a.w2_r[(2 * c) * a.R + r] * hid[r].x;
+          im += a.w2_r[(2 * c + 1) * a.R + r] * hid[r].x;
+        } else {
+          const float wr = a.w2_r[c * a.R + r], wi = a.w2_i[c * a.R + r];
+          re += wr * hid[r].x - wi * hid[r].y;
+          im += wr * hid[r].y + wi * hid[r].x;
+        }
+      }
+    }
+    gs[c] = REAL ? make_float2(sigmoidf_(re), sigmoidf_(im)) : make_float2(sigmoidf_(2.f * re), sigmoidf_(2.f * im));
+  }
+  __syncthreads();
+
+  // ---- per-thread constants of the phases
+  const int sub = tid % G, f0 = tid / G, rot = (f0 >> RSH) & (VPL - 1);
+  GPair sgate[VPL][2];
+  uint32_t voff[VPL];
+#pragma unroll
+  for (int k = 0; k < VPL; ++k) {
+    const int vi = sub + G * ((k + rot) & (VPL - 1));
+    voff[k] = (uint32_t)vi * 16;
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      const float2 ga = gs[vi * 4 + 2 * h2], gb = gs[vi * 4 + 2 * h2 + 1];
+      sgate[k][h2].re = make_float2(ga.x, gb.x); sgate[k][h2].im = make_float2(ga.y, gb.y);
+      sgate[k][h2].nim = make_float2(-ga.y, -gb.y);
+    }
+  }
+  const int avi = tid % VPP, q0 = tid / VPP;
+  GPair agate[2];
+#pragma unroll
+  for (int h2 = 0; h2 < 2; ++h2) {
+    const float2 ga = gs[avi * 4 + 2 * h2], gb = gs[avi * 4 + 2 * h2 + 1];
+    agate[h2].re = make_float2(ga.x, gb.x); agate[h2].im = make_float2(ga.y, gb.y); agate[h2].nim = make_float2(-ga.y, -gb.y);
+  }
+  const float invC = 1.f / (float)C;
+  const uint32_t b_base = smem_u32(bt) + (uint32_t)lane * 8;
+  T* ybase = reinterpret_cast<T*>(a.y) + (((int64_t)b * H * W + x0) * C + avi * 4) * 2;
+
+  // Step s: statistics of group s; ONE CTA barrier; gate conv of group s - 1 (-> sg[(s - 1) & 1]) and the product of group
+  // s - 2 (gates from sg[s & 1], written one step earlier) as one instruction stream per warp: the product's independent work
+  // fills the MMA chain's latency, and no second barrier is needed (the hazards — statistics rows, x groups, gate buffers — are
+  // all separated by the next step's barrier).
+  const int ngroups = (H + 3) / 4;
+  for (int s = 0; s < ngroups + 2; ++s) {
+    // ---- 1. statistics of rows 4 s .. 4 s + 3 (zero rows below the image: the conv's zero padding, and the ring holds old rows)
+    if (s <= ngroups) {
+      const int rbase = 4 * s;
+      if (rbase < H) mbar_wait(full_u32 + 8 * (s % NG), (uint32_t)((s / NG) & 1));
+      for (int fb = 0; fb < 4 * PW; fb += PPI) {
+        const bool valid = fb + f0 < 4 * PW;
+        const int f = valid ? fb + f0 : 4 * PW - 1;
+        const int r4 = f / PW, p = f - r4 * PW;
+        const int row = rbase + r4;
+        const uint32_t base = xs_u32 + (uint32_t)(((s % NG) * 4 + r4) * PW + p) * (C * 4);
+        float2 sre = make_float2(0.f, 0.f), sim = make_float2(0.f, 0.f);
+        float mr = -INFINITY, mi = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < VPL; ++k) {
+          CPair p01, p23, u01, u23;
+          unpack_pairs<T>(lds128(base + voff[k]), p01, p23);
+          if constexpr (REAL) {
+            u01.re = mul2(sgate[k][0].re, p01.re); u01.im = mul2(sgate[k][0].im, p01.im);
+            u23.re = mul2(sgate[k][1].re, p23.re); u23.im = mul2(sgate[k][1].im, p23.im);
+          } else {
+            u01 = cmul_pair(sgate[k][0], p01); u23 = cmul_pair(sgate[k][1], p23);
+          }
+          sre = add2(sre, add2(u01.re, u23.re));
+          sim = add2(sim, add2(u01.im, u23.im));
+          mr = fmaxf(fmaxf(mr, fmaxf(u01.re.x, u01.re.y)), fmaxf(u23.re.x, u23.re.y));
+          mi = fmaxf(fmaxf(mi, fmaxf(u01.im.x, u01.im.y)), fmaxf(u23.im.x, u23.im.y));
+        }
+        float sr = sre.x + sre.y, si = sim.x + sim.y;
+        if constexpr (REAL) { sr = 0.5f * (sr + si); si = 0.f; mr = fmaxf(mr, mi); mi = 0.f; }
+#pragma unroll
+        for (int o = G >> 1; o; o >>= 1) {
+          sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o);
+          mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o)); mi = fmaxf(mi, __shfl_xor_sync(0xffffffffu, mi, o));
+        }
+        if (valid && sub == 0) {
+          const bool in = row < H && (unsigned)(x0 - 3 + p) < (unsigned)W;
+          uint2 v = make_uint2(0u, 0u);
+          if (in) v = REAL ? make_uint2(pack_f16x2(sr * invC, mr), 0u) : make_uint2(pack_f16x2(sr * invC, si * invC), pack_f16x2(mr, mi));
+          st[(row & 15) * SP + p] = v;
+        }
+      }
+    }
+    __syncthreads();
+    // every thread has finished the product of group s - 3 (previous step): its ring group takes the rows of group s + 1
+    if (tid < 4 && 4 * (s + 1) < H) issue_group(s + 1);
+    // ---- 2. gate conv of output rows 4 (s - 1) .. + 3 from statistics rows 4 s - 7 .. 4 s + 2: issue the MMAs (four chains) ...
+    const bool do_conv = s >= 1 && s <= ngroups && warp < NSEG;
+    float d[4][4];
+    if (do_conv) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) d[c][i] = 0.f;
+      const uint32_t a_col = (uint32_t)((warp * 16 + g + t) * 8);
+      const int rb = 4 * s - 7;
+#pragma unroll
+      for (int ks = 0; ks < 20; ++ks) {
+        const uint32_t aa = st_u32 + (uint32_t)(((rb + (ks >> 1)) & 15) * SP + 4 * (ks & 1)) * 8 + a_col;
+        const uint2 bb = lds64u(b_base + ks * 256), alo = lds64u(aa), ahi = lds64u(aa + 64);
+        mma_f16_16x8x16(d[ks & 3], alo.x, ahi.x, alo.y, ahi.y, bb.x, bb.y);
+      }
+    }
+    // ---- 3. ... y = gate_s * (gate_c * x) for rows 4 (s - 2) .. + 3 while they complete ...
+    if (s >= 2) {
+      const int ob = 4 * (s - 2);
+      const int nq = min(4, H - ob) * TW;
+      const uint32_t xg = xs_u32 + (uint32_t)(((s - 2) % NG) * 4) * ROWB + 3 * C * 4 + (uint32_t)avi * 16;
+      const float2* sgr = sg + (s & 1) * 4 * TW;
+      T* yrow = ybase + (int64_t)ob * W * C * 2;
+#pragma unroll 4
+      for (int q = q0; q < nq; q += QS) {
+        const int rl = q / TW, px = q - rl * TW;
+        if (x0 + px < W) {
+          CPair p01, p23;
+          unpack_pairs<T>(lds128(xg + (uint32_t)(rl * PW + px) * (C * 4)), p01, p23);
+          const float2 gsp = sgr[q];
+          const float2 gre = make_float2(gsp.x, gsp.x), gim = make_float2(gsp.y, gsp.y), gnim = make_float2(-gsp.y, -gsp.y);
+          float2 r01, i01, r23, i23;
+          if constexpr (REAL) {
+            r01 = mul2(gre, mul2(agate[0].re, p01.re)); i01 = mul2(gre, mul2(agate[0].im, p01.im));
+            r23 = mul2(gre, mul2(agate[1].re, p23.re)); i23 = mul2(gre, mul2(agate[1].im, p23.im));
+          } else {
+            const CPair u01 = cmul_pair(agate[0], p01), u23 = cmul_pair(agate[1], p23);
+            r01 = fma2(gre, u01.re, mul2(gnim, u01.im)); i01 = fma2(gre, u01.im, mul2(gim, u01.re));
+            r23 = fma2(gre, u23.re, mul2(gnim, u23.im)); i23 = fma2(gre, u23.im, mul2(gim, u23.re));
+          }
+          *reinterpret_cast<uint4*>(yrow + ((int64_t)rl * W + px) * C * 2) =
+              make_uint4(pack_h2<T>(r01.x, i01.x), pack_h2<T>(r01.y, i01.y), pack_h2<T>(r23.x, i23.x), pack_h2<T>(r23.y, i23.y));
+        }
+      }
+    }
+    // ---- ... and store the finished gates of group s - 1 for the next step's product
+    if (do_conv) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) d[0][i] = (d[0][i] + d[1][i]) + (d[2][i] + d[3][i]);
+      float2* o = sg + ((s - 1) & 1) * 4 * TW + t * TW + warp * 16 + g;         // accumulator columns 2 t, 2 t + 1 = (re, im) of row 4 (s - 1) + t
+      if constexpr (REAL) {
+        o[0] = make_float2(sigmoid_ex2(d[0][0]), 0.f);
+        o[8] = make_float2(sigmoid_ex2(d[0][2]), 0.f);
+      } else {
+        o[0] = make_float2(sigmoid_ex2(d[0][0]), sigmoid_ex2(d[0][1]));
+        o[8] = make_float2(sigmoid_ex2(d[0][2]), sigmoid_ex2(d[0][3]));
+      }
+    }
+  }
+}
+
 }  // namespace dcs
 
 using namespace dcs;
@@ -747,6 +1013,28 @@ static int launch_attention_tile(const dcs_attention_params* p, cudaStream_t s) 
   return nt512 ? launch_attention_tile_nt<C, REAL, 512, 16>(p, s, 0) : launch_attention_tile_nt<C, REAL, 256, 16>(p, s, 0);
 }
 
+template <int C, bool REAL, int TW, int NG, int MINB = 2>
+static int launch_attention_rows(const dcs_attention_params* p, cudaStream_t s) {
+  const size_t smem = (size_t)4 * NG * (TW + 6) * C * 4 + (size_t)16 * (TW + 8) * 8 + (size_t)8 * TW * 8 + (size_t)(2 * C + 16) * 8 + 196 * 4 + 20 * 32 * 8 + 4 * 8;
+  DCS_REQUIRE(smem <= 113 * 1024, "dcs_attention_stream: row-group ring does not fit shared memory (C=%d, TW=%d)", C, TW);
+  AttStreamArgs a;
+  a.x = p->x; a.y = p->y; a.sums = reinterpret_cast<const long long*>(p->sums); a.inv_hw = 1.f / ((float)p->h * (float)p->w);
+  a.w1_r = p->w1_r; a.w1_i = p->w1_i; a.w2_r = p->w2_r; a.w2_i = p->w2_i; a.w7 = p->w7;
+  a.H = p->h; a.W = p->w; a.R = p->reduced; a.NR = 0;
+  DCS_CUDA(cudaFuncSetAttribute(attention_rows_kernel<C, REAL, TW, NG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((p->w + TW - 1) / TW, p->batch);
+  attention_rows_kernel<C, REAL, TW, NG, MINB><<<grid, 256, smem, s>>>(a);
+  DCS_LAUNCHED();
+  return 0;
+}
+// Default: C = 8 only.  Measured on B200 (batch 64 x 4 s): C = 8 tensors 207 -> 156 us (110 M -> 77 M warp instructions); at C = 16
+// (64- / 80-pixel strips: the ring of 16 rows x 64 B pixels limits the strip width) 87 -> 91 us, so those keep the older kernel.
+// Also tried: 80-pixel strips at three CTAs per SM (<= 80 registers): 0.95 vs 0.88 ms for the attention stage.
+static int att_rows_mask() {   // DCS_ATT_ROWS: bit 0: C = 8, bit 1: C = 16 through attention_rows_kernel (0: the older streaming kernel)
+  static const int m = [] { const char* e = getenv("DCS_ATT_ROWS"); return e ? atoi(e) : 1; }();
+  return m;
+}
+
 // DCS_ATT_TILE=0 keeps the row-streaming kernel for every tensor, DCS_ATT_BAND=0 for the tall few-channel tensors (A/B runs)
 static bool att_tile_enabled() {
   static const bool on = [] { const char* e = getenv("DCS_ATT_TILE"); return !(e && e[0] == '0'); }();
@@ -781,6 +1069,14 @@ static int dispatch_attention_stream(const dcs_attention_params* p, cudaStream_t
       return launch_attention_tile_nt<8, REAL, 256, 48>(p, s, att_band_rh());
     if (att_tile_enabled() && p->channels == 16 && (att_band_mask() & 2) && p->h >= 24 && p->w >= 32)
       return launch_attention_tile_nt<16, REAL, 256, 32>(p, s, 24);
+  }
+  if constexpr (std::is_same<T, __half>::value) {
+    // tall few-channel tensors: row groups of four (attention_rows_kernel); strip width by wave fill like the older kernel
+    auto fill = [&](int tw) { const int64_t ctas = (int64_t)((p->w + tw - 1) / tw) * p->batch, slots = 2 * num_sms(); return ((ctas + slots - 1) / slots) * (tw + 6); };
+    if (p->channels == 8 && (att_rows_mask() & 1) && p->h >= 8 && p->w > 64)
+      return fill(112) < fill(128) ? launch_attention_rows<8, REAL, 112, 4>(p, s) : launch_attention_rows<8, REAL, 128, 4>(p, s);
+    if (p->channels == 16 && (att_rows_mask() & 2) && p->h >= 8 && p->w > 48)
+      return fill(64) <= fill(80) ? launch_attention_rows<16, REAL, 64, 4>(p, s) : launch_attention_rows<16, REAL, 80, 4>(p, s);
   }
   // strip width: 128 pixels (every warp owns 16) for the few-channel tensors; narrow strips where a row of C channels is
   // long (ring of 8 rows) and the tensor has few pixels (enough CTAs), or where the image itself is narrow

@@ -369,7 +369,7 @@ def test_fused_attention_equals_separate_kernels(C, H, W, dtype):
 
 
 @pytest.mark.parametrize("C,H,W", [(128, 2, 70), (128, 4, 33), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 75),
-                                   (16, 64, 260), (8, 128, 130), (8, 128, 300), (8, 11, 16)])
+                                   (16, 64, 260), (8, 128, 130), (8, 128, 300), (8, 11, 16), (8, 30, 70), (16, 18, 50), (8, 9, 250)])
 @pytest.mark.parametrize("dtype", [torch.float16, torch.bfloat16])
 def test_stream_attention_equals_separate_kernels(C, H, W, dtype):
     """dcs_attention_stream (16-bit storage: x rows through a bulk-copy ring, 7x7 gate conv as TF32 mma.sync row-partials with

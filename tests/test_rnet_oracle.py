@@ -355,7 +355,7 @@ def test_gpu_real_tensor_core_plan_full_size_vs_oracle():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("Cp,H,W", [(128, 2, 70), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 260), (8, 128, 300), (8, 11, 16)])
+@pytest.mark.parametrize("Cp,H,W", [(128, 2, 70), (128, 8, 37), (64, 16, 50), (32, 32, 33), (16, 64, 260), (8, 128, 300), (8, 11, 16), (8, 30, 70), (16, 18, 50)])
 def test_gpu_real_stream_attention_equals_three_pass_kernels(Cp, H, W):
     """The REAL variant of dcs_attention_stream (max-pool channel gate from DCS_POOL_MAX-encoded maxima, (mean, max)
     statistics, TF32 mma.sync gate conv, element-wise products) vs dcs_real_attention_fwd (fp32 output) and the oracle's
