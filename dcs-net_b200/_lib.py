@@ -67,6 +67,22 @@ class CwgradParams(C.Structure):
                 ("dw_r", _vp), ("dw_i", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class WgradParams(C.Structure):
+    _fields_ = [("x", _vp), ("dy", _vp),
+                ("batch", _i), ("in_h", _i), ("in_w", _i), ("out_h", _i), ("out_w", _i), ("k2", _i), ("n2", _i), ("x_pitch", _i),
+                ("dy_pitch", _i), ("stride_h", _i), ("stride_w", _i), ("ntaps", _i), ("dy_off", C.c_int8 * MAX_TAPS),
+                ("dx_off", C.c_int8 * MAX_TAPS), ("dwp", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
+class AttentionBwdParams(C.Structure):
+    _fields_ = [("x", _vp), ("dy", _vp), ("gate_c", _vp), ("stats", _vp), ("gate_s", _vp), ("w7", _vp), ("sums", _vp),
+                ("batch", _i), ("h", _i), ("w", _i), ("channels", _i), ("reduced", _i),
+                ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp),
+                ("dspre", _vp), ("dx", _vp), ("chan_const", _vp),
+                ("dw1_r", _vp), ("dw1_i", _vp), ("dw2_r", _vp), ("dw2_i", _vp), ("dw7_r", _vp), ("dw7_i", _vp),
+                ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 class IstftParams(C.Structure):
     _fields_ = [("spec", _vp), ("audio", _vp), ("batch", _i), ("n_frames", _i), ("atan2_eps", _f), ("exact_polar", _i),
                 ("mag", _vp), ("phase", _vp)]
@@ -185,6 +201,28 @@ SYMBOLS = {
     "dcs_upcat_adjoint": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_cwgrad_workspace_bytes": (_i64, [C.POINTER(CwgradParams)]),
     "dcs_cwgrad_tc": (_i, [C.POINTER(CwgradParams), _vp]),
+    "dcs_wgrad_workspace_bytes": (_i64, [C.POINTER(WgradParams)]),
+    "dcs_wgrad": (_i, [C.POINTER(WgradParams), _vp]),
+    "dcs_wgrad_fold_complex": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "dcs_transpose": (_i, [_vp, _vp, _i, _i, _i, _vp]),
+    "dcs_sgemm": (_i, [_vp, _i, _vp, _i, _i, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "dcs_colsum_workspace_bytes": (_i64, [_i64, _i]),
+    "dcs_colsum": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
+    "dcs_dilate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_upcat_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
+    "dcs_dropout": (_i, [_vp, _vp, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
+    "dcs_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
+    "dcs_attention_bwd": (_i, [C.POINTER(AttentionBwdParams), _vp]),
+    "dcs_lstm_train_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "dcs_lstm_train_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
+    "dcs_cplx_split": (_i, [_vp, _vp, _i64, _vp]),
+    "dcs_cplx_merge": (_i, [_vp, _vp, _i64, _vp]),
+    "dcs_clstm_combine": (_i, [_vp, _vp, _i64, _vp]),
+    "dcs_clstm_combine_bwd": (_i, [_vp, _vp, _i64, _vp]),
+    "dcs_sumsq": (_i, [_vp, _i64, _vp, _i, _vp, _i64, _vp]),
+    "dcs_adam_amsgrad": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _vp, _f, _f, _vp]),
+    "dcs_gather_pack": (_i, [_vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "dcs_frontend_fwd": (_i, [C.POINTER(FrontendParams), _vp]),
     "dcs_stft_fwd": (_i, [C.POINTER(StftParams), _vp]),
     "dcs_istft_fwd": (_i, [C.POINTER(IstftParams), _vp]),

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcsnet_sm100a.so")
-SOURCES = ["eltwise.cu", "stft.cu", "cconv_ffma.cu", "cconv_tc.cu", "cconv_strip.cu", "attention.cu", "attention_stream.cu", "frontend.cu", "real_attention.cu", "rlstm.cu", "lstm.cu", "tail.cu", "cconv_first.cu", "train.cu", "wgrad_tc.cu"]
+SOURCES = ["eltwise.cu", "stft.cu", "cconv_ffma.cu", "cconv_tc.cu", "cconv_strip.cu", "attention.cu", "attention_stream.cu", "frontend.cu", "real_attention.cu", "rlstm.cu", "lstm.cu", "tail.cu", "cconv_first.cu", "train.cu", "wgrad_tc.cu", "train_bwd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

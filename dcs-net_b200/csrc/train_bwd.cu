@@ -1,0 +1,1013 @@
+// train_bwd.cu — second slice of the TRAINING step (BASELINE configs[4]): the backward kernels that the
+// first slice (train.cu, wgrad_tc.cu, the ADJ mode of stft.cu) left open, all fp32, all reductions two-stage and
+// deterministic (per-CTA partials to a workspace, combined in a fixed order).  Contracts: oracle/train_oracle.py.
+//   generic weight gradient (implicit GEMM, K = pixels) ... cconv2d_backward / decoder_stage_backward / clinear_backward,
+//                                                            and the LSTM's dW_ih / dW_hh (h shifted by one step = a 1-D tap)
+//   strided-conv dgrad ..................................... zero insertion (dcs_dilate) + the forward conv kernels with
+//                                                            role-swapped weights (train_ops.dgrad_conv)
+//   activation / dropout adjoints .......................... c_network.py:113 (ComplexReLU), 148 (ComplexLReLU), 195/203/221
+//   attention backward ..................................... attention_backward (c_network.py:53-84, 208-211, 219-220)
+//   LSTM forward with saved gates + BPTT ................... lstm_forward_saved / lstm_bptt (c_network.py:12-51)
+//   Adam-amsgrad with the global-norm clip ................. c_network.py:229-235, config.py:48-49
+#include <algorithm>
+#include "common.cuh"
+
+namespace dcs {
+
+// =============================================================================================== generic wgrad GEMM
+// dWp[tap][k][n] = sum over output pixels (b, oh, ow) of x[b, oh*sh + dyo(tap), ow*sw + dxo(tap)][k] * dy[b, oh, ow][n]
+// as a tiled fp32 GEMM: M' = ntaps*k2 rows (im2col columns of the forward), N = n2, reduction over pixels, split over CTAs
+// (gridDim.z) with partial tiles to a workspace.  256 threads, thread tile RM x RN, CTA tile (16 RM) x (16 RN), 16 pixels
+// (one segment of an output row) per stage.
+constexpr int kWgKC = 16;
+
+struct WgArgs {
+  const float* x; const float* dy; float* ws;
+  int batch, in_h, in_w, out_h, out_w, k2, n2, x_pitch, dy_pitch, sh, sw, ntaps, mtot, segs_per_row;
+  int64_t n_items, items_per_split;
+  int8_t dyo[DCS_MAX_TAPS], dxo[DCS_MAX_TAPS];
+};
+
+template <int RM, int RN>
+__global__ void __launch_bounds__(256) wgrad_generic_kernel(const WgArgs a) {
+  constexpr int TM = 16 * RM, TN = 16 * RN;
+  __shared__ __align__(16) float As[kWgKC][TM + 4];
+  __shared__ __align__(16) float Bs[kWgKC][TN + 4];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  // A loader: this thread always loads row m' = m0 + tid % TM (fixed tap / channel), pixels kk = tid / TM + (256 / TM) j
+  const int am = tid % TM, ak0 = tid / TM;
+  const int mrow = m0 + am;
+  const bool a_ok = mrow < a.mtot;
+  const int tap = a_ok ? mrow / a.k2 : 0, kch = a_ok ? mrow % a.k2 : 0;
+  const int dyo = a.dyo[tap], dxo = a.dxo[tap];
+  const int bn = tid % TN, bk0 = tid / TN;
+  const bool b_ok = n0 + bn < a.n2;
+  float acc[RM][RN];
+#pragma unroll
+  for (int i = 0; i < RM; ++i)
+#pragma unroll
+    for (int j = 0; j < RN; ++j) acc[i][j] = 0.f;
+  const int64_t it0 = blockIdx.z * a.items_per_split, it1 = min(it0 + a.items_per_split, a.n_items);
+  for (int64_t it = it0; it < it1; ++it) {
+    const int seg = (int)(it % a.segs_per_row);
+    const int64_t row = it / a.segs_per_row;
+    const int oh = (int)(row % a.out_h), b = (int)(row / a.out_h);
+    const int ow0 = seg * kWgKC;
+    const int ih = oh * a.sh + dyo;
+    const bool row_ok = a_ok && (unsigned)ih < (unsigned)a.in_h;
+    const float* xrow = a.x + ((int64_t)b * a.in_h + (row_ok ? ih : 0)) * a.in_w * a.x_pitch + kch;
+#pragma unroll
+    for (int j = 0; j < (kWgKC * TM) / 256; ++j) {
+      const int kk = ak0 + (256 / TM) * j;
+      const int ow = ow0 + kk, iw = ow * a.sw + dxo;
+      float v = 0.f;
+      if (row_ok && ow < a.out_w && (unsigned)iw < (unsigned)a.in_w) v = xrow[(int64_t)iw * a.x_pitch];
+      As[kk][am] = v;
+    }
+    const float* dyrow = a.dy + (((int64_t)b * a.out_h + oh) * a.out_w) * a.dy_pitch + n0 + bn;
+#pragma unroll
+    for (int j = 0; j < (kWgKC * TN) / 256; ++j) {
+      const int kk = bk0 + (256 / TN) * j;
+      const int ow = ow0 + kk;
+      Bs[kk][bn] = (b_ok && ow < a.out_w) ? dyrow[(int64_t)ow * a.dy_pitch] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kWgKC; ++kk) {
+      float av[RM], bv[RN];
+#pragma unroll
+      for (int i = 0; i < RM; ++i) av[i] = As[kk][ty * RM + i];
+#pragma unroll
+      for (int j = 0; j < RN; ++j) bv[j] = Bs[kk][tx * RN + j];
+#pragma unroll
+      for (int i = 0; i < RM; ++i)
+#pragma unroll
+        for (int j = 0; j < RN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* out = a.ws + (int64_t)blockIdx.z * a.mtot * a.n2;
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    const int m = m0 + ty * RM + i;
+    if (m >= a.mtot) continue;
+#pragma unroll
+    for (int j = 0; j < RN; ++j) {
+      const int n = n0 + tx * RN + j;
+      if (n < a.n2) out[(int64_t)m * a.n2 + n] = acc[i][j];
+    }
+  }
+}
+
+// dst[i] = sum over splits (fixed order) of ws[z][i]
+__global__ void split_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dst, int64_t n, int splits) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += ws[(int64_t)z * n + i];
+    dst[i] = s;
+  }
+}
+
+// fold the four real blocks of dWp[tap][2 cin][2 cout] into conv_r / conv_i .weight.grad (oracle cconv2d_backward):
+//   dw_r = dWp[re,re] + dWp[im,im], dw_i = dWp[re -> im] - dWp[im -> re];  ComplexConv2d: (cout, cin, taps);
+//   ComplexConvTranspose2d (weights (cin_t, cout_t, k, k), run as the flipped, in/out-swapped conv): the gradient of the
+//   equivalent conv weight lands at [ci][co][taps - 1 - t].
+__global__ void wgrad_fold_complex_kernel(const float* __restrict__ dwp, int ntaps, int cin, int cout, int transposed,
+                                          float* __restrict__ dw_r, float* __restrict__ dw_i) {
+  const int n = ntaps * cin * cout, N2 = 2 * cout, K2 = 2 * cin;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const int t = i % ntaps, ci = (i / ntaps) % cin, co = i / (ntaps * cin);
+    const float* w = dwp + ((int64_t)t * K2 + 2 * ci) * N2 + 2 * co;
+    const float rr = w[0], ri = w[1], ir = w[N2], ii = w[N2 + 1];     // [k part][n part]
+    const int64_t d = transposed ? ((int64_t)ci * cout + co) * ntaps + (ntaps - 1 - t) : ((int64_t)co * cin + ci) * ntaps + t;
+    dw_r[d] = rr + ii;
+    dw_i[d] = ri - ir;
+  }
+}
+
+// dst[c][r] = src[r * pitch + c]  (rows x cols -> cols x rows): real GEMM weight gradients, dWp[k][n] -> W.grad[n][k]
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols, int pitch) {
+  __shared__ float t[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int r = r0 + i, c = c0 + threadIdx.x;
+    t[i][threadIdx.x] = (r < rows && c < cols) ? src[(int64_t)r * pitch + c] : 0.f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += 8) {
+    const int c = c0 + i, r = r0 + threadIdx.x;
+    if (r < rows && c < cols) dst[(int64_t)c * rows + r] = t[threadIdx.x][i];
+  }
+}
+
+// =============================================================================================== plain fp32 GEMM
+// C[m][n] = sum_k A[m * lda + k] * B[n * ldb_n + k * ldb_k] (+ bias[n]) (+ C[m][n]): the LSTM projections and their data
+// gradients (NT and NN forms through the two B strides).  64 x 64 x 16 tiles, 256 threads, 4 x 4 per thread.
+__global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb_n, int ldb_k,
+                                                    const float* __restrict__ bias, float* __restrict__ C, int ldc, int M, int N, int K,
+                                                    int accumulate) {
+  __shared__ __align__(16) float As[16][68];
+  __shared__ __align__(16) float Bs[16][68];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int m0 = blockIdx.y * 64, n0 = blockIdx.x * 64;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  // loaders: A tile 64 rows x 16 k: thread -> (row = tid / 4, k = (tid % 4) * 4 .. + 3) (k contiguous in memory)
+  const int ar = tid >> 2, ak = (tid & 3) * 4;
+  for (int k0 = 0; k0 < K; k0 += 16) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k0 + ak + e, m = m0 + ar;
+      As[ak + e][ar] = (m < M && k < K) ? A[(int64_t)m * lda + k] : 0.f;
+    }
+    if (ldb_k == 1) {           // B rows are k-contiguous (NT): same loader as A
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + ak + e, n = n0 + ar;
+        Bs[ak + e][ar] = (n < N && k < K) ? B[(int64_t)n * ldb_n + k] : 0.f;
+      }
+    } else {                    // n-contiguous (NN): thread -> (k = tid / 16, n = (tid % 16) * 4 .. + 3)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = k0 + ty, n = n0 + tx * 4 + e;
+        Bs[ty][tx * 4 + e] = (n < N && k < K) ? B[(int64_t)n * ldb_n + (int64_t)k * ldb_k] : 0.f;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      const float4 av = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      const float4 bv = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+      const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a4[i], b4[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= N) continue;
+      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (accumulate) v += C[(int64_t)m * ldc + n];
+      C[(int64_t)m * ldc + n] = v;
+    }
+  }
+}
+
+// =============================================================================================== column sums (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x, int64_t rows, int cols, int pitch, int64_t rows_per_cta,
+                                                     double* __restrict__ partial) {
+  // thread -> column c = threadIdx.x % cw (cw = min(cols, 256) rounded), row lanes = 256 / cw; columns beyond 256 loop
+  __shared__ double red[256];
+  const int64_t r0 = blockIdx.x * rows_per_cta, r1 = min(r0 + rows_per_cta, rows);
+  for (int cb = 0; cb < cols; cb += 256) {
+    const int cw = min(256, cols - cb);
+    int lanes = 256 / cw;
+    if (lanes < 1) lanes = 1;
+    const int c = threadIdx.x % cw, rl = threadIdx.x / cw;
+    double s = 0.0;
+    if (rl < lanes)
+      for (int64_t r = r0 + rl; r < r1; r += lanes) s += x[r * pitch + cb + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      double t = 0.0;
+      for (int l = 0; l < lanes; ++l) t += red[l * cw + threadIdx.x];
+      partial[(int64_t)blockIdx.x * cols + cb + threadIdx.x] = t;
+    }
+    __syncthreads();
+  }
+}
+// mode 0: out0[c] = S[c] (and out1[c] = S[c] when out1 != NULL);  mode 1 (complex conv bias, columns (co, re/im)):
+// out0[co] = S[2co] + S[2co+1] (conv_r.bias.grad), out1[co] = S[2co+1] - S[2co] (conv_i.bias.grad)
+__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int n_chunks, int cols, int mode, float* __restrict__ out0,
+                                       float* __restrict__ out1) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (mode == 0) {
+    if (i >= cols) return;
+    double s = 0.0;
+    for (int k = 0; k < n_chunks; ++k) s += partial[(int64_t)k * cols + i];
+    out0[i] = (float)s;
+    if (out1) out1[i] = (float)s;
+  } else {
+    if (i >= cols / 2) return;
+    double sr = 0.0, si = 0.0;
+    for (int k = 0; k < n_chunks; ++k) { sr += partial[(int64_t)k * cols + 2 * i]; si += partial[(int64_t)k * cols + 2 * i + 1]; }
+    out0[i] = (float)(sr + si);
+    out1[i] = (float)(si - sr);
+  }
+}
+
+// =============================================================================================== element-wise adjoints
+// zero insertion: out (B, in_h, in_w, c) <- dy (B, out_h, out_w, c) at (oh*sh, ow*sw), zero elsewhere (float2 units)
+__global__ void dilate_kernel(const float2* __restrict__ dy, float2* __restrict__ out, int B, int out_h, int out_w, int in_h, int in_w,
+                              int C, int sh, int sw) {
+  const int64_t n = (int64_t)B * in_h * in_w * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int w = (int)(r % in_w); r /= in_w;
+    const int h = (int)(r % in_h);
+    const int b = (int)(r / in_h);
+    float2 v = make_float2(0.f, 0.f);
+    if (h % sh == 0 && w % sw == 0 && h / sh < out_h && w / sw < out_w)
+      v = dy[(((int64_t)b * out_h + h / sh) * out_w + w / sw) * C + c];
+    out[i] = v;
+  }
+}
+
+// z (B, h*uh, w*uw, c0 + c1) = nearest up-sampling of cat(d, skip) (the decoder convs' input, materialised for the wgrad)
+__global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, float2* __restrict__ z, int B, int H, int W,
+                                 int c0, int c1, int uh, int uw) {
+  const int C = c0 + c1, HH = H * uh, WW = W * uw;
+  const int64_t n = (int64_t)B * HH * WW * C;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    int64_t r = i / C;
+    const int x = (int)(r % WW); r /= WW;
+    const int y = (int)(r % HH);
+    const int b = (int)(r / HH);
+    const int64_t pix = ((int64_t)b * H + y / uh) * W + x / uw;
+    z[i] = c < c0 ? d[pix * c0 + c] : skip[pix * c1 + (c - c0)];
+  }
+}
+
+// dz = act'(y) * (g0 + g1 + chan_const[b][c]) per real component; y = the activation's OUTPUT (ReLU / LeakyReLU keep the sign)
+__global__ void act_bwd_kernel(const float2* __restrict__ y, const float2* __restrict__ g0, const float2* __restrict__ g1,
+                               const float2* __restrict__ cc, float2* __restrict__ dz, int64_t hw_c, int C, int64_t n, int act) {
+  const float slope = act == DCS_ACT_RELU ? 0.f : (act == DCS_ACT_LRELU ? 0.01f : 1.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float2 g = g0[i];
+    if (g1) { const float2 t = g1[i]; g.x += t.x; g.y += t.y; }
+    if (cc) { const float2 t = cc[(i / hw_c) * C + i % C]; g.x += t.x; g.y += t.y; }
+    if (act != DCS_ACT_NONE) {
+      const float2 v = y[i];
+      g.x *= v.x > 0.f ? 1.f : slope;
+      g.y *= v.y > 0.f ? 1.f : slope;
+    }
+    dz[i] = g;
+  }
+}
+
+// ---- dropout (torch.nn.Dropout on view_as_real: real and imaginary parts drop independently, c_network.py:195-196).
+// Philox4x32-10 counter-based generator: element group i (4 floats) draws from counter (i + offset), key = seed, so the
+// backward regenerates the forward's mask from (seed, offset) instead of storing it.
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u; key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t n, float p, float scale, uint64_t seed,
+                               uint64_t offset) {
+  const int64_t n4 = (n + 3) / 4;
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = (uint64_t)i + offset;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = 4 * i + e;
+      if (j < n) y[j] = rr[e] >= thr ? x[j] * scale : 0.f;
+    }
+  }
+}
+
+// =============================================================================================== attention backward
+// y = s * u, u = a * x (a: channel gate (B,C), s: spatial gate (B,HW)); oracle/train_oracle.attention_backward.
+// G = min(C, 32) lanes cooperate on one pixel, 32 / G pixels per warp.
+
+// pass 1: ds = sum_c conj(u_c) dy_c; dspre = ds (.) s (1 - s) per component
+__global__ void __launch_bounds__(256) att_bwd_ds_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
+                                                         const float2* __restrict__ gate_s, float2* __restrict__ dspre, int hw, int C, int G) {
+  __shared__ float2 gs[256];
+  const int b = blockIdx.y;
+  for (int c = threadIdx.x; c < C; c += 256) gs[c] = gate_c[(int64_t)b * C + c];
+  __syncthreads();
+  const int sub = threadIdx.x % G, grp = threadIdx.x / G, groups = 256 / G;
+  const int64_t base = (int64_t)b * hw;
+  for (int pbase = blockIdx.x * groups; pbase < hw; pbase += gridDim.x * groups) {
+    const int p = pbase + grp;
+    float dr = 0.f, di = 0.f;
+    if (p < hw)
+      for (int c = sub; c < C; c += G) {
+        const float2 u = cmul(gs[c], x[(base + p) * C + c]), g = dy[(base + p) * C + c];
+        dr += u.x * g.x + u.y * g.y;          // conj(u) * g
+        di += u.x * g.y - u.y * g.x;
+      }
+    for (int o = G >> 1; o; o >>= 1) { dr += __shfl_xor_sync(0xffffffffu, dr, o); di += __shfl_xor_sync(0xffffffffu, di, o); }
+    if (sub == 0 && p < hw) {
+      const float2 s = gate_s[base + p];
+      dspre[base + p] = make_float2(dr * s.x * (1.f - s.x), di * s.y * (1.f - s.y));
+    }
+  }
+}
+
+// gradient of the 7x7 gate conv's weights: 49 taps x 4 statistics components x 2 gradient components per tile, then folded:
+//   dw7_r[ch][tap] = sum_p dsp.re st.re + dsp.im st.im ; dw7_i[ch][tap] = sum_p dsp.im st.re - dsp.re st.im
+constexpr int kW7TH = 8, kW7TW = 32;
+__global__ void __launch_bounds__(256) att_bwd_w7_kernel(const float4* __restrict__ stats, const float2* __restrict__ dspre, int H, int W,
+                                                         int tiles_x, int tiles_y, double* __restrict__ partial) {
+  __shared__ float4 st[kW7TH + 6][kW7TW + 6];
+  __shared__ float2 dsp[kW7TH][kW7TW];
+  const int tile = blockIdx.x;
+  const int b = tile / (tiles_x * tiles_y), ty = (tile / tiles_x) % tiles_y, tx = tile % tiles_x;
+  const int y0 = ty * kW7TH, x0 = tx * kW7TW;
+  for (int i = threadIdx.x; i < (kW7TH + 6) * (kW7TW + 6); i += 256) {
+    const int r = i / (kW7TW + 6), c = i % (kW7TW + 6);
+    const int yy = y0 + r - 3, xx = x0 + c - 3;
+    st[r][c] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? stats[((int64_t)b * H + yy) * W + xx] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for (int i = threadIdx.x; i < kW7TH * kW7TW; i += 256) {
+    const int r = i / kW7TW, c = i % kW7TW;
+    dsp[r][c] = (y0 + r < H && x0 + c < W) ? dspre[((int64_t)b * H + y0 + r) * W + x0 + c] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  // thread -> (tap, channel ch in {mean, max}, which in {r, i}) : 196 outputs
+  if (threadIdx.x < 196) {
+    const int tap = threadIdx.x % 49, ch = (threadIdx.x / 49) & 1, which = threadIdx.x / 98;
+    const int ky = tap / 7, kx = tap % 7;
+    float s = 0.f;
+    for (int r = 0; r < kW7TH; ++r)
+      for (int c = 0; c < kW7TW; ++c) {
+        const float4 q = st[r + ky][c + kx];
+        const float sr = ch ? q.z : q.x, si = ch ? q.w : q.y;
+        const float2 g = dsp[r][c];
+        s += which ? (g.y * sr - g.x * si) : (g.x * sr + g.y * si);
+      }
+    partial[(int64_t)tile * 196 + threadIdx.x] = (double)s;
+  }
+}
+// out layout = the reference's (1,2,7,7) tensors: dw7_r[ch*49 + tap], dw7_i[ch*49 + tap]
+__global__ void att_bwd_w7_finalize_kernel(const double* __restrict__ partial, int n_tiles, float* __restrict__ dw7_r, float* __restrict__ dw7_i) {
+  const int i = threadIdx.x;
+  if (i >= 196) return;
+  double s = 0.0;
+  for (int t = 0; t < n_tiles; ++t) s += partial[(int64_t)t * 196 + i];
+  const int tap = i % 49, ch = (i / 49) & 1, which = i / 98;
+  (which ? dw7_i : dw7_r)[ch * 49 + tap] = (float)s;
+}
+
+// pass 2: dstats = conv7^T(dspre); du = conj(s) dy + dmean / C + [argmax] dmax; dx = conj(a) du; da partial sums per CTA
+__global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
+                                                         const float2* __restrict__ gate_s, const float2* __restrict__ dspre,
+                                                         const float* __restrict__ w7, float2* __restrict__ dx, double* __restrict__ da_partial,
+                                                         int H, int W, int C, int G) {
+  __shared__ float2 gs[256];
+  __shared__ float4 wq[49];
+  __shared__ float red[256][2];
+  const int b = blockIdx.y, hw = H * W;
+  for (int c = threadIdx.x; c < C; c += 256) gs[c] = gate_c[(int64_t)b * C + c];
+  for (int i = threadIdx.x; i < 49; i += 256) wq[i] = make_float4(w7[i], w7[49 + i], w7[98 + i], w7[147 + i]);   // Wr mean, Wr max, Wi mean, Wi max
+  __syncthreads();
+  const int sub = threadIdx.x % G, grp = threadIdx.x / G, groups = 256 / G;
+  const int64_t base = (int64_t)b * hw;
+  const int nch = (C + G - 1) / G;      // channels per lane (<= 8 for C <= 256)
+  float2 da[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) da[k] = make_float2(0.f, 0.f);
+  const float invC = 1.f / (float)C;
+  for (int pbase = blockIdx.x * groups; pbase < hw; pbase += gridDim.x * groups) {
+    const int p = pbase + grp;
+    const bool ok = p < hw;
+    // transposed 7x7 conv: dstats[ch](q) = sum_tap (conj-transposed block) dspre(q - off_tap); taps split over the G lanes
+    float mr = 0.f, mi = 0.f, xr = 0.f, xi = 0.f;     // d mean (re, im), d max (re, im)
+    if (ok) {
+      const int py = p / W, px = p % W;
+      for (int t = sub; t < 49; t += G) {
+        const int qy = py - (t / 7 - 3), qx = px - (t % 7 - 3);
+        if ((unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W) {
+          const float2 g = dspre[base + (int64_t)qy * W + qx];
+          const float4 wv = wq[t];
+          mr += wv.x * g.x + wv.z * g.y;  mi += -wv.z * g.x + wv.x * g.y;
+          xr += wv.y * g.x + wv.w * g.y;  xi += -wv.w * g.x + wv.y * g.y;
+        }
+      }
+    }
+    // u, and the arg max of Re u / Im u over the channels (first index on ties, like torch.max)
+    float2 uv[8], gv[8];
+    float bre = -INFINITY, bim = -INFINITY;
+    int are = 0x7fffffff, aim = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = sub + k * G;
+      if (k < nch && ok && c < C) {
+        uv[k] = cmul(gs[c], x[(base + p) * C + c]);
+        gv[k] = dy[(base + p) * C + c];
+        if (uv[k].x > bre) { bre = uv[k].x; are = c; }
+        if (uv[k].y > bim) { bim = uv[k].y; aim = c; }
+      }
+    }
+    for (int o = G >> 1; o; o >>= 1) {
+      mr += __shfl_xor_sync(0xffffffffu, mr, o); mi += __shfl_xor_sync(0xffffffffu, mi, o);
+      xr += __shfl_xor_sync(0xffffffffu, xr, o); xi += __shfl_xor_sync(0xffffffffu, xi, o);
+      const float ore = __shfl_xor_sync(0xffffffffu, bre, o), oim = __shfl_xor_sync(0xffffffffu, bim, o);
+      const int oare = __shfl_xor_sync(0xffffffffu, are, o), oaim = __shfl_xor_sync(0xffffffffu, aim, o);
+      if (ore > bre || (ore == bre && oare < are)) { bre = ore; are = oare; }
+      if (oim > bim || (oim == bim && oaim < aim)) { bim = oim; aim = oaim; }
+    }
+    if (ok) {
+      const float2 s = gate_s[base + p];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = sub + k * G;
+        if (k < nch && c < C) {
+          const float2 g = gv[k];
+          float2 du = make_float2(s.x * g.x + s.y * g.y + mr * invC, s.x * g.y - s.y * g.x + mi * invC);   // conj(s) g + dmean / C
+          if (c == are) du.x += xr;
+          if (c == aim) du.y += xi;
+          const float2 xv = x[(base + p) * C + c], a = gs[c];
+          da[k].x += xv.x * du.x + xv.y * du.y;        // conj(x) du
+          da[k].y += xv.x * du.y - xv.y * du.x;
+          dx[(base + p) * C + c] = make_float2(a.x * du.x + a.y * du.y, a.x * du.y - a.y * du.x);   // conj(a) du
+        }
+      }
+    }
+  }
+  // CTA reduction of da over the pixel groups (fixed order), one partial row per CTA
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k >= nch) break;
+    __syncthreads();
+    red[threadIdx.x][0] = da[k].x; red[threadIdx.x][1] = da[k].y;
+    __syncthreads();
+    const int c = threadIdx.x + k * G;
+    if (threadIdx.x < G && c < C) {
+      double sr = 0.0, si = 0.0;
+      for (int g = 0; g < groups; ++g) { sr += red[g * G + threadIdx.x][0]; si += red[g * G + threadIdx.x][1]; }
+      double* o = da_partial + (((int64_t)b * gridDim.x + blockIdx.x) * C + c) * 2;
+      o[0] = sr; o[1] = si;
+    }
+  }
+}
+
+// the gate MLP's backward, one CTA per image: da -> dfc = 2 da (.) a (1 - a) -> W2^T, crelu mask, W1^T -> davg;
+// chan_const[b][c] = davg / (H W); per-image weight gradients to `wpart` (B, 4 R C): [dw1_r (R,C) | dw1_i | dw2_r (C,R) | dw2_i]
+__global__ void __launch_bounds__(256) att_bwd_gate_kernel(const double* __restrict__ da_partial, int n_chunks, const float2* __restrict__ gate_c,
+                                                           const long long* __restrict__ sums, float inv_hw, int C, int R,
+                                                           const float* __restrict__ w1_r, const float* __restrict__ w1_i,
+                                                           const float* __restrict__ w2_r, const float* __restrict__ w2_i,
+                                                           float2* __restrict__ chan_const, float* __restrict__ wpart) {
+  __shared__ float2 avg[256], dfc[256], hid_pre[16], hid[16], dhp[16];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int c = tid; c < C; c += 256) {
+    double sr = 0.0, si = 0.0;
+    for (int k = 0; k < n_chunks; ++k) {
+      const double* o = da_partial + (((int64_t)b * n_chunks + k) * C + c) * 2;
+      sr += o[0]; si += o[1];
+    }
+    const float2 a = gate_c[(int64_t)b * C + c];
+    dfc[c] = make_float2(2.f * (float)sr * a.x * (1.f - a.x), 2.f * (float)si * a.y * (1.f - a.y));
+    avg[c] = make_float2(pool_mean(sums, ((int64_t)b * C + c) * 2, inv_hw), pool_mean(sums, ((int64_t)b * C + c) * 2 + 1, inv_hw));
+  }
+  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = warp; r < R; r += 8) {           // hidden pre-activation (as the forward computes it) and dhid
+    float re = 0.f, im = 0.f, dr = 0.f, di = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      const float wr = w1_r[r * C + c], wi = w1_i[r * C + c];
+      re += wr * avg[c].x - wi * avg[c].y;
+      im += wr * avg[c].y + wi * avg[c].x;
+      const float vr = w2_r[c * R + r], vi = w2_i[c * R + r];
+      dr += vr * dfc[c].x + vi * dfc[c].y;
+      di += -vi * dfc[c].x + vr * dfc[c].y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      re += __shfl_xor_sync(0xffffffffu, re, o); im += __shfl_xor_sync(0xffffffffu, im, o);
+      dr += __shfl_xor_sync(0xffffffffu, dr, o); di += __shfl_xor_sync(0xffffffffu, di, o);
+    }
+    if (lane == 0) {
+      hid_pre[r] = make_float2(re, im);
+      hid[r] = make_float2(fmaxf(re, 0.f), fmaxf(im, 0.f));
+      dhp[r] = make_float2(re > 0.f ? dr : 0.f, im > 0.f ? di : 0.f);
+    }
+  }
+  __syncthreads();
+  float* wp = wpart + (int64_t)b * 4 * R * C;
+  for (int i = tid; i < R * C; i += 256) {
+    {   // dw1 (R, C): dY = dhp[r], X = avg[c]
+      const int r = i / C, c = i % C;
+      wp[i] = dhp[r].x * avg[c].x + dhp[r].y * avg[c].y;
+      wp[R * C + i] = dhp[r].y * avg[c].x - dhp[r].x * avg[c].y;
+    }
+    {   // dw2 (C, R): dY = dfc[c], X = hid[r]
+      const int c = i / R, r = i % R;
+      wp[2 * R * C + i] = dfc[c].x * hid[r].x + dfc[c].y * hid[r].y;
+      wp[3 * R * C + i] = dfc[c].y * hid[r].x - dfc[c].x * hid[r].y;
+    }
+  }
+  const float k = inv_hw;
+  for (int c = tid; c < C; c += 256) {
+    float re = 0.f, im = 0.f;
+    for (int r = 0; r < R; ++r) {
+      const float wr = w1_r[r * C + c], wi = w1_i[r * C + c];
+      re += wr * dhp[r].x + wi * dhp[r].y;
+      im += -wi * dhp[r].x + wr * dhp[r].y;
+    }
+    chan_const[(int64_t)b * C + c] = make_float2(re * k, im * k);
+  }
+}
+// dst[i] = sum_b src[b][i] in a fixed order
+__global__ void batch_reduce_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int b = 0; b < B; ++b) s += src[(int64_t)b * n + i];
+    dst[i] = s;
+  }
+}
+
+// =============================================================================================== LSTM (training form)
+// One CTA per (sequence q, direction d); 4H = 256 threads, thread r owns gate row r (gate r / H of unit r % H) with its W_hh
+// row in registers; q uses the weights of group q / (n_seq / n_groups).  pre / gates: (Q, S, 2, 4H); h / cells: (Q, S, 2, H).
+template <int H>
+__global__ void __launch_bounds__(4 * H) lstm_train_fwd_kernel(const float* __restrict__ pre, const float* __restrict__ w_hh, int n_seq, int n_groups,
+                                                               int S, float* __restrict__ h_out, float* __restrict__ gates, float* __restrict__ cells) {
+  constexpr int G4 = 4 * H;
+  __shared__ float hs[H];
+  __shared__ float act[G4];
+  const int q = blockIdx.x, d = blockIdx.y, r = threadIdx.x;
+  const int grp = q / (n_seq / n_groups);
+  float w[H];
+  const float* wrow = w_hh + (((int64_t)grp * 2 + d) * G4 + r) * H;
+#pragma unroll
+  for (int k = 0; k < H; ++k) w[k] = wrow[k];
+  if (r < H) hs[r] = 0.f;
+  float c = 0.f;
+  __syncthreads();
+  float a_next = pre[(((int64_t)q * S + (d ? S - 1 : 0)) * 2 + d) * G4 + r];
+  for (int step = 0; step < S; ++step) {
+    const int t = d ? S - 1 - step : step;
+    const int64_t row = ((int64_t)q * S + t) * 2 + d;
+    float a = a_next;
+    if (step + 1 < S) a_next = pre[(((int64_t)q * S + (d ? t - 1 : t + 1)) * 2 + d) * G4 + r];   // prefetch: off the serial chain
+#pragma unroll
+    for (int k = 0; k < H; ++k) a = fmaf(w[k], hs[k], a);
+    const float v = (r / H == 2) ? tanhf(a) : sigmoidf_(a);
+    act[r] = v;
+    gates[row * G4 + r] = v;
+    __syncthreads();
+    if (r < H) {
+      c = act[H + r] * c + act[r] * act[2 * H + r];
+      const float hv = act[3 * H + r] * tanhf(c);
+      hs[r] = hv;
+      h_out[row * H + r] = hv;
+      cells[row * H + r] = c;
+    }
+    __syncthreads();
+  }
+}
+
+// BPTT (oracle/train_oracle.lstm_bptt): reverse of the forward's time order; thread r computes da of its gate row, then the
+// CTA forms dh_next = da W_hh (thread (k, part) sums 64 rows of column k held in registers).  dpre (Q, S, 2, 4H).
+template <int H>
+__global__ void __launch_bounds__(4 * H) lstm_train_bwd_kernel(const float* __restrict__ w_hh, const float* __restrict__ gates,
+                                                               const float* __restrict__ cells, const float* __restrict__ dh_out, int n_seq,
+                                                               int n_groups, int S, float* __restrict__ dpre) {
+  constexpr int G4 = 4 * H;
+  __shared__ float da_s[G4];
+  __shared__ float part[4][H];
+  const int q = blockIdx.x, d = blockIdx.y, r = threadIdx.x;
+  const int grp = q / (n_seq / n_groups);
+  const int gate = r / H, u = r % H;
+  const int kcol = r % H, prt = r / H;     // dh_next role: column kcol, rows prt*H .. prt*H + H - 1
+  float wt[H];
+  const float* wbase = w_hh + ((int64_t)grp * 2 + d) * G4 * H;
+#pragma unroll
+  for (int k = 0; k < H; ++k) wt[k] = wbase[(int64_t)(prt * H + k) * H + kcol];
+  float dc_next = 0.f, dh_next = 0.f;
+  // operands of the step being processed are loaded one step ahead (they do not depend on the recurrence)
+  auto row_of = [&](int t) { return ((int64_t)q * S + t) * 2 + d; };
+  int t = d ? 0 : S - 1;
+  float gi, gf, gg, go, cv, dho;
+  {
+    const float* g = gates + row_of(t) * G4;
+    gi = g[u]; gf = g[H + u]; gg = g[2 * H + u]; go = g[3 * H + u];
+    cv = cells[row_of(t) * H + u];
+    dho = dh_out[row_of(t) * H + u];
+  }
+  for (int step = 0; step < S; ++step) {
+    const int tp = d ? t + 1 : t - 1;                       // the step processed before t in the forward = the next one here
+    const bool more = step + 1 < S;
+    float ngi = 0.f, ngf = 0.f, ngg = 0.f, ngo = 0.f, ncv = 0.f, ndho = 0.f;
+    if (more) {
+      const float* g = gates + row_of(tp) * G4;
+      ngi = g[u]; ngf = g[H + u]; ngg = g[2 * H + u]; ngo = g[3 * H + u];
+      ncv = cells[row_of(tp) * H + u];
+      ndho = dh_out[row_of(tp) * H + u];
+    }
+    const float c_prev = ncv;                               // zero at the first forward step
+    const float tc = tanhf(cv);
+    const float dh = dho + dh_next;
+    const float dc = dh * go * (1.f - tc * tc) + dc_next;
+    float da;
+    if (gate == 0) da = dc * gg * gi * (1.f - gi);
+    else if (gate == 1) da = dc * c_prev * gf * (1.f - gf);
+    else if (gate == 2) da = dc * gi * (1.f - gg * gg);
+    else da = dh * tc * go * (1.f - go);
+    dc_next = dc * gf;
+    dpre[row_of(t) * G4 + r] = da;
+    da_s[r] = da;
+    __syncthreads();
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < H; ++k) s = fmaf(da_s[prt * H + k], wt[k], s);
+    part[prt][kcol] = s;
+    __syncthreads();
+    dh_next = part[0][u] + part[1][u] + part[2][u] + part[3][u];
+    gi = ngi; gf = ngf; gg = ngg; go = ngo; cv = ncv; dho = ndho; t = tp;
+  }
+}
+
+// (rows, D, 2) interleaved complex <-> (2, rows, D) planes
+__global__ void cplx_split_kernel(const float2* __restrict__ x, float* __restrict__ planes, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 v = x[i];
+    planes[i] = v.x; planes[n + i] = v.y;
+  }
+}
+__global__ void cplx_merge_kernel(const float* __restrict__ planes, float2* __restrict__ x, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    x[i] = make_float2(planes[i], planes[n + i]);
+}
+// ComplexLSTM combine (c_network.py:39-47): h (2 lstm, 2 part, n): out.re = R(re) - I(im), out.im = R(im) + I(re); and its adjoint
+__global__ void clstm_combine_kernel(const float* __restrict__ h, float2* __restrict__ out, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = make_float2(h[i] - h[3 * n + i], h[n + i] + h[2 * n + i]);
+}
+__global__ void clstm_combine_bwd_kernel(const float2* __restrict__ dout, float* __restrict__ dh, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float2 g = dout[i];
+    dh[i] = g.x; dh[n + i] = g.y; dh[2 * n + i] = g.y; dh[3 * n + i] = -g.x;
+  }
+}
+
+// =============================================================================================== optimizer
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ x, int64_t n, double* __restrict__ partial) {
+  __shared__ double red[8];
+  double s = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s += (double)x[i] * x[i];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) { double t = 0.0; for (int w = 0; w < 8; ++w) t += red[w]; partial[blockIdx.x] = t; }
+}
+__global__ void sumsq_finalize_kernel(const double* __restrict__ partial, int n, double* __restrict__ out, int accumulate) {
+  double t = accumulate ? *out : 0.0;
+  for (int i = 0; i < n; ++i) t += partial[i];
+  *out = t;
+}
+// torch.optim.Adam(amsgrad=True, weight_decay = L2 added to the gradient) on flat buffers; the gradient is first scaled by
+// grad_scale (1 / world size) and by the global-norm clip coefficient min(1, max_norm / (norm + 1e-6)) with norm =
+// grad_scale * sqrt(*grad_sumsq) (torch.nn.utils.clip_grad_norm_, what Lightning's gradient_clip_algorithm "norm" calls).
+__global__ void adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                    float* __restrict__ vmax, int64_t n, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt,
+                                    const double* __restrict__ grad_sumsq, float max_norm, float grad_scale) {
+  float coef = grad_scale;
+  if (grad_sumsq && max_norm > 0.f) {
+    const float norm = grad_scale * (float)sqrt(*grad_sumsq);
+    coef *= fminf(1.f, max_norm / (norm + 1e-6f));
+  }
+  const float step = lr / bc1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float pv = p[i];
+    const float gr = g[i] * coef + wd * pv;
+    const float mv = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    const float vm = fmaxf(vmax[i], vv);
+    m[i] = mv; v[i] = vv; vmax[i] = vm;
+    p[i] = pv - step * mv / (sqrtf(vm) / bc2_sqrt + eps);
+  }
+}
+
+// packed operand = signed sum of up to 4 source elements (the linear map raw weights -> kernel operand layouts, built once on
+// the host as an index table): dst[i] = sum_j sign_j src[idx_j]; idx < 0 = no term
+__global__ void gather_pack_kernel(const float* __restrict__ src, const int4* __restrict__ idx, const char4* __restrict__ sgn, void* __restrict__ dst,
+                                   int64_t n, int out_dtype) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int4 id = idx[i];
+    const char4 sg = sgn[i];
+    float s = 0.f;
+    if (id.x >= 0) s += (float)sg.x * src[id.x];
+    if (id.y >= 0) s += (float)sg.y * src[id.y];
+    if (id.z >= 0) s += (float)sg.z * src[id.z];
+    if (id.w >= 0) s += (float)sg.w * src[id.w];
+    if (out_dtype == DCS_F32) reinterpret_cast<float*>(dst)[i] = s;
+    else if (out_dtype == DCS_F16) reinterpret_cast<__half*>(dst)[i] = from_float<__half>(s);
+    else reinterpret_cast<__nv_bfloat16*>(dst)[i] = from_float<__nv_bfloat16>(s);
+  }
+}
+
+static int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16)); }
+
+struct WgPlan { int rm, rn, mt, nt, splits; int64_t n_items, items_per_split; int segs; };
+static WgPlan wg_plan(const dcs_wgrad_params* p) {
+  WgPlan w;
+  const int mtot = p->ntaps * p->k2;
+  w.rn = p->n2 >= 48 ? 4 : 1;
+  w.rm = 4;
+  const int TM = 16 * w.rm, TN = 16 * w.rn;
+  w.mt = (mtot + TM - 1) / TM;
+  w.nt = (p->n2 + TN - 1) / TN;
+  w.segs = (p->out_w + kWgKC - 1) / kWgKC;
+  w.n_items = (int64_t)p->batch * p->out_h * w.segs;
+  const int64_t tiles = (int64_t)w.mt * w.nt;
+  int64_t splits = std::max<int64_t>(1, (4LL * num_sms() + tiles - 1) / tiles);
+  splits = std::min<int64_t>(splits, std::max<int64_t>(1, w.n_items / 4));
+  splits = std::min<int64_t>(splits, 1024);
+  w.items_per_split = (w.n_items + splits - 1) / splits;
+  w.splits = (int)((w.n_items + w.items_per_split - 1) / w.items_per_split);
+  return w;
+}
+
+}  // namespace dcs
+
+using namespace dcs;
+
+extern "C" int64_t dcs_wgrad_workspace_bytes(const dcs_wgrad_params* p) {
+  if (!p || p->ntaps <= 0 || p->ntaps > DCS_MAX_TAPS || p->k2 <= 0 || p->n2 <= 0 || p->batch <= 0 || p->out_h <= 0 || p->out_w <= 0) return -1;
+  const WgPlan w = wg_plan(p);
+  return (int64_t)w.splits * p->ntaps * p->k2 * p->n2 * sizeof(float);
+}
+
+extern "C" int dcs_wgrad(const dcs_wgrad_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->dy && p->dwp && p->workspace, "dcs_wgrad: null pointer");
+  DCS_REQUIRE(p->ntaps > 0 && p->ntaps <= DCS_MAX_TAPS && p->k2 > 0 && p->n2 > 0 && p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->out_h > 0 &&
+              p->out_w > 0 && p->stride_h > 0 && p->stride_w > 0 && p->x_pitch >= p->k2 && p->dy_pitch >= p->n2, "dcs_wgrad: bad shape");
+  DCS_REQUIRE(p->workspace_bytes >= dcs_wgrad_workspace_bytes(p), "dcs_wgrad: workspace too small");
+  const WgPlan w = wg_plan(p);
+  WgArgs a;
+  a.x = p->x; a.dy = p->dy; a.ws = reinterpret_cast<float*>(p->workspace);
+  a.batch = p->batch; a.in_h = p->in_h; a.in_w = p->in_w; a.out_h = p->out_h; a.out_w = p->out_w; a.k2 = p->k2; a.n2 = p->n2;
+  a.x_pitch = p->x_pitch; a.dy_pitch = p->dy_pitch; a.sh = p->stride_h; a.sw = p->stride_w; a.ntaps = p->ntaps; a.mtot = p->ntaps * p->k2;
+  a.segs_per_row = w.segs; a.n_items = w.n_items; a.items_per_split = w.items_per_split;
+  for (int t = 0; t < p->ntaps; ++t) { a.dyo[t] = p->dy_off[t]; a.dxo[t] = p->dx_off[t]; }
+  cudaStream_t s = (cudaStream_t)stream;
+  dim3 grid(w.mt, w.nt, w.splits);
+  if (w.rn == 4) wgrad_generic_kernel<4, 4><<<grid, 256, 0, s>>>(a);
+  else wgrad_generic_kernel<4, 1><<<grid, 256, 0, s>>>(a);
+  DCS_LAUNCHED();
+  const int64_t n = (int64_t)a.mtot * p->n2;
+  split_reduce_kernel<<<ew_grid(n), 256, 0, s>>>(a.ws, p->dwp, n, w.splits);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_wgrad_fold_complex(const float* dwp, int ntaps, int cin, int cout, int transposed, float* dw_r, float* dw_i, void* stream) {
+  DCS_REQUIRE(dwp && dw_r && dw_i && ntaps > 0 && cin > 0 && cout > 0, "dcs_wgrad_fold_complex: bad arguments");
+  wgrad_fold_complex_kernel<<<ew_grid((int64_t)ntaps * cin * cout), 256, 0, (cudaStream_t)stream>>>(dwp, ntaps, cin, cout, transposed, dw_r, dw_i);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_transpose(const float* src, float* dst, int rows, int cols, int src_pitch, void* stream) {
+  DCS_REQUIRE(src && dst && rows > 0 && cols > 0 && src_pitch >= cols, "dcs_transpose: bad arguments");
+  transpose_kernel<<<dim3((cols + 31) / 32, (rows + 31) / 32), dim3(32, 8), 0, (cudaStream_t)stream>>>(src, dst, rows, cols, src_pitch);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_sgemm(const float* A, int lda, const float* B, int ldb_n, int ldb_k, const float* bias, float* C, int ldc, int M, int N, int K,
+                         int accumulate, void* stream) {
+  DCS_REQUIRE(A && B && C && M > 0 && N > 0 && K > 0 && lda >= K && ldc >= N, "dcs_sgemm: bad arguments");
+  sgemm_kernel<<<dim3((N + 63) / 64, (M + 63) / 64), 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb_n, ldb_k, bias, C, ldc, M, N, K, accumulate);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+static void colsum_chunking(int64_t rows, int* n_chunks, int64_t* rpc) {
+  int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((rows + 63) / 64, 2 * (int64_t)num_sms()));
+  *rpc = (rows + ctas - 1) / ctas;
+  *n_chunks = (int)((rows + *rpc - 1) / *rpc);
+}
+extern "C" int64_t dcs_colsum_workspace_bytes(int64_t rows, int cols) {
+  if (rows <= 0 || cols <= 0) return -1;
+  int nc; int64_t rpc;
+  colsum_chunking(rows, &nc, &rpc);
+  return (int64_t)nc * cols * sizeof(double);
+}
+extern "C" int dcs_colsum(const float* x, int64_t rows, int cols, int pitch, int mode, float* out0, float* out1, void* workspace,
+                          int64_t workspace_bytes, void* stream) {
+  DCS_REQUIRE(x && out0 && workspace && rows > 0 && cols > 0 && pitch >= cols && (mode == 0 || (mode == 1 && out1 && cols % 2 == 0)),
+              "dcs_colsum: bad arguments");
+  DCS_REQUIRE(workspace_bytes >= dcs_colsum_workspace_bytes(rows, cols), "dcs_colsum: workspace too small");
+  int nc; int64_t rpc;
+  colsum_chunking(rows, &nc, &rpc);
+  cudaStream_t s = (cudaStream_t)stream;
+  colsum_kernel<<<nc, 256, 0, s>>>(x, rows, cols, pitch, rpc, reinterpret_cast<double*>(workspace));
+  DCS_LAUNCHED();
+  colsum_finalize_kernel<<<(cols + 127) / 128, 128, 0, s>>>(reinterpret_cast<const double*>(workspace), nc, cols, mode, out0, out1);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_dilate(const float* dy, float* out, int batch, int out_h, int out_w, int in_h, int in_w, int channels, int stride_h,
+                          int stride_w, void* stream) {
+  DCS_REQUIRE(dy && out && batch > 0 && out_h > 0 && out_w > 0 && in_h > 0 && in_w > 0 && channels > 0 && stride_h > 0 && stride_w > 0 &&
+              (out_h - 1) * stride_h < in_h && (out_w - 1) * stride_w < in_w, "dcs_dilate: bad arguments");
+  const int64_t n = (int64_t)batch * in_h * in_w * channels;
+  dilate_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)dy, (float2*)out, batch, out_h, out_w, in_h, in_w, channels, stride_h, stride_w);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_upcat_fwd(const float* d, const float* skip, float* z, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream) {
+  DCS_REQUIRE(d && z && (skip || c1 == 0) && batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 >= 0 && up_h >= 1 && up_w >= 1, "dcs_upcat_fwd: bad arguments");
+  const int64_t n = (int64_t)batch * h * up_h * w * up_w * (c0 + c1);
+  upcat_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)d, (const float2*)skip, (float2*)z, batch, h, w, c0, c1, up_h, up_w);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_act_bwd(const float* y, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,
+                           int act, void* stream) {
+  DCS_REQUIRE(g0 && dz && (y || act == DCS_ACT_NONE) && batch > 0 && hw > 0 && channels > 0 && act >= DCS_ACT_NONE && act <= DCS_ACT_LRELU,
+              "dcs_act_bwd: bad arguments");
+  const int64_t n = (int64_t)batch * hw * channels;
+  act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)y, (const float2*)g0, (const float2*)g1, (const float2*)chan_const,
+                                                               (float2*)dz, hw * channels, channels, n, act);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
+  DCS_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dcs_dropout: bad arguments");
+  dropout_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, 1.f / (1.f - p), seed, offset);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+static int att_G(int C) { return C >= 32 ? 32 : C; }
+static int att_chunks(int hw, int G) { return (int)std::max<int64_t>(1, std::min<int64_t>(((int64_t)hw + (256 / G) * 8 - 1) / ((256 / G) * 8), 64)); }
+
+extern "C" int64_t dcs_attention_bwd_workspace_bytes(int batch, int h, int w, int channels, int reduced) {
+  if (batch <= 0 || h <= 0 || w <= 0 || channels <= 0 || channels > 256 || (channels & (channels - 1)) || reduced <= 0 || reduced > 16) return -1;
+  const int G = att_G(channels), chunks = att_chunks(h * w, G);
+  const int64_t tiles = (int64_t)batch * ((h + kW7TH - 1) / kW7TH) * ((w + kW7TW - 1) / kW7TW);
+  return (int64_t)batch * chunks * channels * 2 * sizeof(double) + tiles * 196 * sizeof(double) + (int64_t)(batch + 1) * 4 * reduced * channels * sizeof(float);
+}
+
+extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->dy && p->gate_c && p->stats && p->gate_s && p->w7 && p->sums && p->w1_r && p->w1_i && p->w2_r && p->w2_i && p->dspre &&
+              p->dx && p->chan_const && p->dw1_r && p->dw1_i && p->dw2_r && p->dw2_i && p->dw7_r && p->dw7_i && p->workspace,
+              "dcs_attention_bwd: null pointer");
+  const int64_t need = dcs_attention_bwd_workspace_bytes(p->batch, p->h, p->w, p->channels, p->reduced);
+  DCS_REQUIRE(need > 0, "dcs_attention_bwd: channels must be a power of two <= 256, reduced <= 16");
+  DCS_REQUIRE(p->workspace_bytes >= need, "dcs_attention_bwd: workspace too small");
+  const int C = p->channels, R = p->reduced, hw = p->h * p->w, G = att_G(C), chunks = att_chunks(hw, G);
+  const int tiles_y = (p->h + kW7TH - 1) / kW7TH, tiles_x = (p->w + kW7TW - 1) / kW7TW;
+  const int n_tiles = p->batch * tiles_y * tiles_x;
+  double* da_partial = reinterpret_cast<double*>(p->workspace);
+  double* w7_partial = da_partial + (int64_t)p->batch * chunks * C * 2;
+  float* wpart = reinterpret_cast<float*>(w7_partial + (int64_t)n_tiles * 196);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float2 *x = (const float2*)p->x, *dy = (const float2*)p->dy, *gc = (const float2*)p->gate_c, *gsp = (const float2*)p->gate_s;
+  att_bwd_ds_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (float2*)p->dspre, hw, C, G);
+  DCS_LAUNCHED();
+  att_bwd_w7_kernel<<<n_tiles, 256, 0, s>>>((const float4*)p->stats, (const float2*)p->dspre, p->h, p->w, tiles_x, tiles_y, w7_partial);
+  DCS_LAUNCHED();
+  att_bwd_w7_finalize_kernel<<<1, 256, 0, s>>>(w7_partial, n_tiles, p->dw7_r, p->dw7_i);
+  DCS_LAUNCHED();
+  att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (const float2*)p->dspre, p->w7, (float2*)p->dx, da_partial, p->h, p->w, C, G);
+  DCS_LAUNCHED();
+  att_bwd_gate_kernel<<<p->batch, 256, 0, s>>>(da_partial, chunks, gc, (const long long*)p->sums, 1.f / (float)hw, C, R, p->w1_r, p->w1_i, p->w2_r,
+                                               p->w2_i, (float2*)p->chan_const, wpart);
+  DCS_LAUNCHED();
+  const int rc = R * C;
+  float* red = wpart + (int64_t)p->batch * 4 * rc;
+  batch_reduce_kernel<<<(4 * rc + 255) / 256, 256, 0, s>>>(wpart, red, p->batch, 4 * rc);
+  DCS_LAUNCHED();
+  DCS_CUDA(cudaMemcpyAsync(p->dw1_r, red, rc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  DCS_CUDA(cudaMemcpyAsync(p->dw1_i, red + rc, rc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  DCS_CUDA(cudaMemcpyAsync(p->dw2_r, red + 2 * rc, rc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  DCS_CUDA(cudaMemcpyAsync(p->dw2_i, red + 3 * rc, rc * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+extern "C" int dcs_lstm_train_fwd(const float* pre, const float* w_hh, int n_seq, int n_groups, int steps, int hidden, float* h, float* gates,
+                                  float* cells, void* stream) {
+  DCS_REQUIRE(pre && w_hh && h && gates && cells && n_seq > 0 && n_groups > 0 && n_seq % n_groups == 0 && steps > 0, "dcs_lstm_train_fwd: bad arguments");
+  DCS_REQUIRE(hidden == 64, "dcs_lstm_train_fwd: only hidden = 64 is built");
+  lstm_train_fwd_kernel<64><<<dim3(n_seq, 2), 256, 0, (cudaStream_t)stream>>>(pre, w_hh, n_seq, n_groups, steps, h, gates, cells);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_lstm_train_bwd(const float* w_hh, const float* gates, const float* cells, const float* dh, int n_seq, int n_groups, int steps,
+                                  int hidden, float* dpre, void* stream) {
+  DCS_REQUIRE(w_hh && gates && cells && dh && dpre && n_seq > 0 && n_groups > 0 && n_seq % n_groups == 0 && steps > 0, "dcs_lstm_train_bwd: bad arguments");
+  DCS_REQUIRE(hidden == 64, "dcs_lstm_train_bwd: only hidden = 64 is built");
+  lstm_train_bwd_kernel<64><<<dim3(n_seq, 2), 256, 0, (cudaStream_t)stream>>>(w_hh, gates, cells, dh, n_seq, n_groups, steps, dpre);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_cplx_split(const float* x, float* planes, int64_t n, void* stream) {
+  DCS_REQUIRE(x && planes && n > 0, "dcs_cplx_split: bad arguments");
+  cplx_split_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)x, planes, n);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_cplx_merge(const float* planes, float* x, int64_t n, void* stream) {
+  DCS_REQUIRE(x && planes && n > 0, "dcs_cplx_merge: bad arguments");
+  cplx_merge_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(planes, (float2*)x, n);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_clstm_combine(const float* h, float* out, int64_t n, void* stream) {
+  DCS_REQUIRE(h && out && n > 0, "dcs_clstm_combine: bad arguments");
+  clstm_combine_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(h, (float2*)out, n);
+  DCS_LAUNCHED();
+  return 0;
+}
+extern "C" int dcs_clstm_combine_bwd(const float* dout, float* dh, int64_t n, void* stream) {
+  DCS_REQUIRE(dh && dout && n > 0, "dcs_clstm_combine_bwd: bad arguments");
+  clstm_combine_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)dout, dh, n);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_sumsq(const float* x, int64_t n, double* out, int accumulate, void* workspace, int64_t workspace_bytes, void* stream) {
+  const int grid = 2 * num_sms();
+  DCS_REQUIRE(x && out && workspace && n > 0 && workspace_bytes >= (int64_t)grid * (int64_t)sizeof(double), "dcs_sumsq: bad arguments (workspace >= 8 * 2 * SMs bytes)");
+  sumsq_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, n, reinterpret_cast<double*>(workspace));
+  DCS_LAUNCHED();
+  sumsq_finalize_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(reinterpret_cast<const double*>(workspace), grid, out, accumulate);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, float lr,
+                                float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq, float max_norm,
+                                float grad_scale, void* stream) {
+  DCS_REQUIRE(param && grad && exp_avg && exp_avg_sq && max_exp_avg_sq && n > 0 && step >= 1, "dcs_adam_amsgrad: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step), bc2s = sqrtf(1.f - powf(beta2, (float)step));
+  adam_amsgrad_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, max_exp_avg_sq, n, lr, beta1, beta2, eps,
+                                                                    weight_decay, bc1, bc2s, grad_sumsq, max_norm, grad_scale);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_gather_pack(const float* src, const int32_t* idx4, const int8_t* sign4, void* dst, int64_t n, int out_dtype, void* stream) {
+  DCS_REQUIRE(src && idx4 && sign4 && dst && n > 0 && is_dtype(out_dtype), "dcs_gather_pack: bad arguments");
+  gather_pack_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, (const int4*)idx4, (const char4*)sign4, dst, n, out_dtype);
+  DCS_LAUNCHED();
+  return 0;
+}

@@ -159,3 +159,239 @@ def cwgrad(x, dy, kernel, stride):
     p.dw_r, p.dw_i, p.workspace, p.workspace_bytes = L.ptr(dw_r), L.ptr(dw_i), L.ptr(ws), ws.numel()
     L.check(L.lib().dcs_cwgrad_tc(C.byref(p), L.stream_ptr()), "dcs_cwgrad_tc")
     return dw_r, dw_i
+
+
+# ================================================================================================ second slice (csrc/train_bwd.cu)
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+
+
+@ops._on_tensor_device
+def wgrad(x, dy, taps, stride=(1, 1), k2=None, n2=None, out=None):
+    """Generic weight-gradient implicit GEMM (dcs_wgrad): x (B, in_h, in_w, x_pitch) fp32 REAL channels (may be a channel slice
+    of a wider tensor: last-dim stride 1, pixel pitch = x.stride(2)), dy (B, out_h, out_w, dy_pitch) likewise; taps = [(dy_off,
+    dx_off)].  Returns dwp (ntaps, k2, n2) fp32."""
+    L.require_cuda(x, dy)
+    assert x.dtype == torch.float32 and dy.dtype == torch.float32 and x.dim() == 4 and dy.dim() == 4
+    assert x.stride(3) == 1 and dy.stride(3) == 1
+    B, in_h, in_w, _ = x.shape
+    _, out_h, out_w, _ = dy.shape
+    xp, dp = x.stride(2), dy.stride(2)
+    assert x.stride(1) == in_w * xp and x.stride(0) == in_h * in_w * xp and dy.stride(1) == out_w * dp and dy.stride(0) == out_h * out_w * dp
+    k2 = k2 or x.shape[3]
+    n2 = n2 or dy.shape[3]
+    p = L.WgradParams()
+    p.x, p.dy = L.ptr(x), L.ptr(dy)
+    p.batch, p.in_h, p.in_w, p.out_h, p.out_w, p.k2, p.n2, p.x_pitch, p.dy_pitch = B, in_h, in_w, out_h, out_w, k2, n2, xp, dp
+    p.stride_h, p.stride_w = stride
+    p.ntaps = len(taps)
+    for t, (a, b) in enumerate(taps):
+        p.dy_off[t], p.dx_off[t] = a, b
+    dwp = out if out is not None else torch.empty(len(taps), k2, n2, dtype=torch.float32, device=x.device)
+    ws = _ws(L.lib().dcs_wgrad_workspace_bytes(C.byref(p)), x.device)
+    p.dwp, p.workspace, p.workspace_bytes = L.ptr(dwp), L.ptr(ws), ws.numel()
+    L.check(L.lib().dcs_wgrad(C.byref(p), L.stream_ptr()), "dcs_wgrad")
+    return dwp
+
+
+def conv_taps(kh, kw):
+    return [(ky - kh // 2, kx - kw // 2) for ky in range(kh) for kx in range(kw)]
+
+
+@ops._on_tensor_device
+def cwgrad_generic(x, dy, kernel, stride=(1, 1), transposed=False, dw_r=None, dw_i=None):
+    """Weight gradient of ComplexConv2d(cin -> cout, kernel, stride, padding k // 2) from fp32 channels-last x (B, H, W, cin, 2),
+    dy (B, OH, OW, cout, 2) -> (dw_r, dw_i) (cout, cin, kh, kw).  transposed=True: the layer is a ComplexConvTranspose2d(k, s1,
+    p k // 2) whose forward runs as the flipped, in / out-swapped conv on x (its own, already up-sampled, input): returns the
+    gradients in the module's (in_channels = cin, out_channels = cout, kh, kw) layout."""
+    kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
+    B, H, W, cin, _ = x.shape
+    cout = dy.shape[3]
+    dwp = wgrad(x.view(B, H, W, 2 * cin), dy.view(B, dy.shape[1], dy.shape[2], 2 * cout), conv_taps(kh, kw), stride)
+    shape = (cin, cout, kh, kw) if transposed else (cout, cin, kh, kw)
+    dw_r = dw_r if dw_r is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
+    dw_i = dw_i if dw_i is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
+    assert tuple(dw_r.shape) == shape and dw_r.is_contiguous() and dw_i.is_contiguous()
+    L.check(L.lib().dcs_wgrad_fold_complex(L.ptr(dwp), kh * kw, cin, cout, int(transposed), L.ptr(dw_r), L.ptr(dw_i), L.stream_ptr()),
+            "dcs_wgrad_fold_complex")
+    return dw_r, dw_i
+
+
+@ops._on_tensor_device
+def transpose_into(src2d, dst):
+    """dst (cols, rows) contiguous <- src2d (rows, cols) with row pitch src2d.stride(0)."""
+    rows, cols = src2d.shape
+    assert src2d.stride(1) == 1 and dst.is_contiguous() and dst.numel() == rows * cols
+    L.check(L.lib().dcs_transpose(L.ptr(src2d), L.ptr(dst), rows, cols, src2d.stride(0), L.stream_ptr()), "dcs_transpose")
+    return dst
+
+
+@ops._on_tensor_device
+def sgemm(A, Bm, bias=None, out=None, b_is_nk=True, accumulate=False):
+    """out (M, N) = A (M, K) @ (Bm^T if b_is_nk [Bm is (N, K)] else Bm [(K, N)]) (+ bias) (+ out).  fp32, row-major with pitches."""
+    L.require_cuda(A, Bm)
+    M, K = A.shape
+    N = Bm.shape[0] if b_is_nk else Bm.shape[1]
+    assert A.stride(1) == 1 and A.dtype == torch.float32 and Bm.dtype == torch.float32
+    if b_is_nk:
+        assert Bm.stride(1) == 1 and Bm.shape[1] == K
+        ldn, ldk = Bm.stride(0), 1
+    else:
+        assert Bm.stride(1) == 1 and Bm.shape[0] == K
+        ldn, ldk = 1, Bm.stride(0)
+    if out is None:
+        assert not accumulate
+        out = torch.empty(M, N, dtype=torch.float32, device=A.device)
+    assert out.stride(1) == 1
+    L.check(L.lib().dcs_sgemm(L.ptr(A), A.stride(0), L.ptr(Bm), ldn, ldk, L.ptr(bias), L.ptr(out), out.stride(0), M, N, K, int(accumulate),
+                              L.stream_ptr()), "dcs_sgemm")
+    return out
+
+
+@ops._on_tensor_device
+def colsum(x2d, mode=0, out0=None, out1=None):
+    """Column sums of x2d (rows, cols) (row pitch x2d.stride(0)).  mode 1 = complex conv / linear bias gradients (db_r, db_i)."""
+    rows, cols = x2d.shape
+    assert x2d.stride(1) == 1 and x2d.dtype == torch.float32
+    n = cols // 2 if mode == 1 else cols
+    out0 = out0 if out0 is not None else torch.empty(n, dtype=torch.float32, device=x2d.device)
+    if mode == 1 and out1 is None:
+        out1 = torch.empty(n, dtype=torch.float32, device=x2d.device)
+    ws = _ws(L.lib().dcs_colsum_workspace_bytes(rows, cols), x2d.device)
+    L.check(L.lib().dcs_colsum(L.ptr(x2d), rows, cols, x2d.stride(0), mode, L.ptr(out0), L.ptr(out1), L.ptr(ws), ws.numel(), L.stream_ptr()),
+            "dcs_colsum")
+    return out0, out1
+
+
+@ops._on_tensor_device
+def dilate(dy, in_h, in_w, stride):
+    """Zero insertion: dy (B, OH, OW, C, 2) -> (B, in_h, in_w, C, 2) with dy at (oh * sh, ow * sw)."""
+    B, OH, OW, Cn, _ = dy.shape
+    assert dy.dtype == torch.float32 and dy.is_contiguous()
+    out = torch.empty(B, in_h, in_w, Cn, 2, dtype=torch.float32, device=dy.device)
+    L.check(L.lib().dcs_dilate(L.ptr(dy), L.ptr(out), B, OH, OW, in_h, in_w, Cn, stride[0], stride[1], L.stream_ptr()), "dcs_dilate")
+    return out
+
+
+@ops._on_tensor_device
+def upcat_fwd(d, skip, up):
+    B, H, W, c0, _ = d.shape
+    c1 = skip.shape[3] if skip is not None else 0
+    assert d.dtype == torch.float32 and d.is_contiguous() and (skip is None or (skip.is_contiguous() and skip.dtype == torch.float32))
+    z = torch.empty(B, H * up[0], W * up[1], c0 + c1, 2, dtype=torch.float32, device=d.device)
+    L.check(L.lib().dcs_upcat_fwd(L.ptr(d), L.ptr(skip), L.ptr(z), B, H, W, c0, c1, up[0], up[1], L.stream_ptr()), "dcs_upcat_fwd")
+    return z
+
+
+@ops._on_tensor_device
+def act_bwd(y, g0, act, g1=None, chan_const=None, out=None):
+    """dz = act'(y) * (g0 + g1 + chan_const[b, c]) on (B, ..., C, 2) fp32 tensors."""
+    B, Cn = g0.shape[0], g0.shape[-2]
+    hw = g0.numel() // (2 * B * Cn)
+    for t in (y, g0, g1):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape == g0.shape)
+    out = out if out is not None else torch.empty_like(g0)
+    L.check(L.lib().dcs_act_bwd(L.ptr(y), L.ptr(g0), L.ptr(g1), L.ptr(chan_const), L.ptr(out), B, hw, Cn, act, L.stream_ptr()), "dcs_act_bwd")
+    return out
+
+
+@ops._on_tensor_device
+def dropout(x, p, seed, offset, out=None):
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    out = out if out is not None else torch.empty_like(x)
+    L.check(L.lib().dcs_dropout(L.ptr(x), L.ptr(out), x.numel(), float(p), int(seed), int(offset), L.stream_ptr()), "dcs_dropout")
+    return out
+
+
+@ops._on_tensor_device
+def attention_bwd(x, dy, gate_c, stats, gate_s, sums, ca, w7, grads=None):
+    """Backward of y = s * (a * x) (dcs_attention_bwd).  ca = packing.pack_channel_attention(...), w7 = pack_spatial_attention(...).
+    Returns (dx_without_const, chan_const (B, C, 2), dict(dw1_r, dw1_i, dw2_r, dw2_i, dw7_r, dw7_i))."""
+    L.require_cuda(x, dy)
+    B, H, W, Cn, _ = x.shape
+    R = ca["reduced"]
+    dev = x.device
+    f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)   # noqa: E731
+    g = grads or dict(dw1_r=f(R, Cn), dw1_i=f(R, Cn), dw2_r=f(Cn, R), dw2_i=f(Cn, R), dw7_r=f(1, 2, 7, 7), dw7_i=f(1, 2, 7, 7))
+    dspre, dx, cc = f(B, H * W, 2), torch.empty_like(x), f(B, Cn, 2)
+    n = int(L.lib().dcs_attention_bwd_workspace_bytes(B, H, W, Cn, R))
+    if n < 0:
+        raise RuntimeError("dcs_attention_bwd: unsupported shape")
+    ws = _ws(n, dev)
+    p = L.AttentionBwdParams(L.ptr(x), L.ptr(dy), L.ptr(gate_c), L.ptr(stats), L.ptr(gate_s), L.ptr(w7), L.ptr(sums), B, H, W, Cn, R,
+                             L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(dspre), L.ptr(dx), L.ptr(cc),
+                             L.ptr(g["dw1_r"]), L.ptr(g["dw1_i"]), L.ptr(g["dw2_r"]), L.ptr(g["dw2_i"]), L.ptr(g["dw7_r"]), L.ptr(g["dw7_i"]),
+                             L.ptr(ws), ws.numel())
+    L.check(L.lib().dcs_attention_bwd(C.byref(p), L.stream_ptr()), "dcs_attention_bwd")
+    return dx, cc, g
+
+
+@ops._on_tensor_device
+def lstm_train_fwd(pre, w_hh, n_groups):
+    """pre (Q, S, 2, 4H) fp32, w_hh (n_groups, 2, 4H, H) -> h (Q, S, 2, H), gates (Q, S, 2, 4H), cells (Q, S, 2, H)."""
+    Q, S, _, G4 = pre.shape
+    H = G4 // 4
+    assert pre.is_contiguous() and w_hh.is_contiguous() and tuple(w_hh.shape) == (n_groups, 2, G4, H)
+    h = torch.empty(Q, S, 2, H, dtype=torch.float32, device=pre.device)
+    gates, cells = torch.empty_like(pre), torch.empty_like(h)
+    L.check(L.lib().dcs_lstm_train_fwd(L.ptr(pre), L.ptr(w_hh), Q, n_groups, S, H, L.ptr(h), L.ptr(gates), L.ptr(cells), L.stream_ptr()),
+            "dcs_lstm_train_fwd")
+    return h, gates, cells
+
+
+@ops._on_tensor_device
+def lstm_train_bwd(w_hh, gates, cells, dh, n_groups):
+    Q, S, _, G4 = gates.shape
+    assert dh.is_contiguous() and tuple(dh.shape) == (Q, S, 2, G4 // 4)
+    dpre = torch.empty_like(gates)
+    L.check(L.lib().dcs_lstm_train_bwd(L.ptr(w_hh), L.ptr(gates), L.ptr(cells), L.ptr(dh), Q, n_groups, S, G4 // 4, L.ptr(dpre), L.stream_ptr()),
+            "dcs_lstm_train_bwd")
+    return dpre
+
+
+def _ew(fn_name, src, dst, n):
+    L.check(getattr(L.lib(), fn_name)(L.ptr(src), L.ptr(dst), n, L.stream_ptr()), fn_name)
+    return dst
+
+
+@ops._on_tensor_device
+def cplx_split(x):
+    """(..., 2) interleaved -> (2, ...) planes."""
+    assert x.is_contiguous() and x.shape[-1] == 2 and x.dtype == torch.float32
+    return _ew("dcs_cplx_split", x, torch.empty((2,) + tuple(x.shape[:-1]), dtype=torch.float32, device=x.device), x.numel() // 2)
+
+
+@ops._on_tensor_device
+def cplx_merge(planes):
+    assert planes.is_contiguous() and planes.shape[0] == 2
+    return _ew("dcs_cplx_merge", planes, torch.empty(tuple(planes.shape[1:]) + (2,), dtype=torch.float32, device=planes.device), planes.numel() // 2)
+
+
+@ops._on_tensor_device
+def clstm_combine(h):
+    """h (2 lstm, 2 part, ...) -> (..., 2) complex: (R(re) - I(im)) + j (R(im) + I(re))."""
+    assert h.is_contiguous() and h.shape[0] == 2 and h.shape[1] == 2
+    return _ew("dcs_clstm_combine", h, torch.empty(tuple(h.shape[2:]) + (2,), dtype=torch.float32, device=h.device), h.numel() // 4)
+
+
+@ops._on_tensor_device
+def clstm_combine_bwd(dout):
+    assert dout.is_contiguous() and dout.shape[-1] == 2
+    return _ew("dcs_clstm_combine_bwd", dout, torch.empty((2, 2) + tuple(dout.shape[:-1]), dtype=torch.float32, device=dout.device), dout.numel() // 2)
+
+
+@ops._on_tensor_device
+def attention_fwd_saved(x, ca, w7):
+    """The attended product y = s * (a * x) (c_network.py:208-211 / 219-220) on fp32 x (B, H, W, C, 2), keeping what
+    dcs_attention_bwd needs: the pooled sums, the channel gate a (B, C, 2), the per-pixel statistics and the spatial gate s."""
+    B, H, W, Cn, _ = x.shape
+    dev = x.device
+    sums = ops.zero_(torch.empty(B, Cn, 2, dtype=torch.int64, device=dev))
+    ops.chan_pool(x, sums)
+    gate = torch.empty(B, Cn, 2, dtype=torch.float32, device=dev)
+    stats = torch.empty(B, H * W, 4, dtype=torch.float32, device=dev)
+    gate_s = torch.empty(B, H * W, 2, dtype=torch.float32, device=dev)
+    y = torch.empty_like(x)
+    ops.spat_stats(x, None, stats, sums=sums, ca=ca, gate_out=gate)
+    ops.spat_apply(x, gate, stats, w7, y, gate_out=gate_s)
+    return y, dict(x=x, sums=sums, gate_c=gate, stats=stats, gate_s=gate_s)

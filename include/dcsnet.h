@@ -409,6 +409,97 @@ typedef struct {
 int64_t dcs_cwgrad_workspace_bytes(const dcs_cwgrad_params* p);
 int dcs_cwgrad_tc(const dcs_cwgrad_params* p, void* stream);
 
+/* ==== f2, second slice (csrc/train_bwd.cu): the rest of the backward pass, fp32, deterministic two-stage reductions.
+ *      Contracts: oracle/train_oracle.py (cconv2d_backward, decoder_stage_backward, clinear_backward, attention_backward,
+ *      lstm_forward_saved / lstm_bptt); reference: c_network.py:12-51, 53-84, 187-240; network_functions.py:210-280. ==== */
+
+/* ---- generic weight-gradient implicit GEMM: dwp[tap][k][n] = sum over output pixels (b, oh, ow) of
+ *      x[(b, oh*stride_h + dy_off[tap], ow*stride_w + dx_off[tap]) * x_pitch + k] * dy[(b, oh, ow) * dy_pitch + n]
+ *      (zero outside the input), k < k2, n < n2 REAL channels.  Covers every ComplexConv2d / ComplexConvTranspose2d /
+ *      ComplexLinear weight gradient (x = the layer's real-block input, k2 = 2 cin, n2 = 2 cout; fold with
+ *      dcs_wgrad_fold_complex) and the LSTM's dW_ih / dW_hh (one tap; h shifted by one step = dx_off -1 / +1 with in_w = S). */
+typedef struct {
+  const float* x; const float* dy;
+  int batch; int in_h; int in_w; int out_h; int out_w; int k2; int n2; int x_pitch; int dy_pitch; int stride_h; int stride_w;
+  int ntaps; int8_t dy_off[DCS_MAX_TAPS]; int8_t dx_off[DCS_MAX_TAPS];
+  float* dwp; void* workspace; int64_t workspace_bytes;
+} dcs_wgrad_params;
+int64_t dcs_wgrad_workspace_bytes(const dcs_wgrad_params* p);
+int dcs_wgrad(const dcs_wgrad_params* p, void* stream);
+/* dwp [ntaps][2 cin][2 cout] -> conv_r.weight.grad / conv_i.weight.grad: dw_r = dWp[re,re] + dWp[im,im], dw_i = dWp[re->im] -
+ * dWp[im->re]; layout (cout, cin, ntaps), or for ComplexConvTranspose2d (transposed = 1; cin / cout = those of the EQUIVALENT
+ * conv the forward runs) the module's (cout_conv = its in_channels ... ) tensor (cin, cout, ntaps) with the taps reversed. */
+int dcs_wgrad_fold_complex(const float* dwp, int ntaps, int cin, int cout, int transposed, float* dw_r, float* dw_i, void* stream);
+/* dst[c * rows + r] = src[r * src_pitch + c]: dwp[k][n] -> a real weight's .grad (n, k) */
+int dcs_transpose(const float* src, float* dst, int rows, int cols, int src_pitch, void* stream);
+/* C[m][n] = sum_k A[m * lda + k] * B[n * ldb_n + k * ldb_k] (+ bias[n]) (+ C[m][n] when accumulate): the LSTM projections
+ * (NT: ldb_k = 1) and their data gradients (NN: ldb_n = 1) in the training step */
+int dcs_sgemm(const float* A, int lda, const float* B, int ldb_n, int ldb_k, const float* bias, float* C, int ldc, int M, int N, int K,
+              int accumulate, void* stream);
+/* column sums of x (rows x cols, row pitch `pitch`): mode 0: out0[c] = S[c] (out1, optional, receives a copy: bias_ih / bias_hh);
+ * mode 1 (complex conv / linear bias, columns (co, re / im)): out0[co] = S[2co] + S[2co+1] = conv_r.bias.grad,
+ * out1[co] = S[2co+1] - S[2co] = conv_i.bias.grad */
+int64_t dcs_colsum_workspace_bytes(int64_t rows, int cols);
+int dcs_colsum(const float* x, int64_t rows, int cols, int pitch, int mode, float* out0, float* out1, void* workspace,
+               int64_t workspace_bytes, void* stream);
+/* zero insertion for the data gradient of a STRIDED conv: out (B, in_h, in_w, channels) complex = dy (B, out_h, out_w, channels)
+ * placed at (oh * stride_h, ow * stride_w), zero elsewhere; the dgrad is then the stride-1 forward conv kernel with the flipped,
+ * in / out-swapped weights (train_ops.dgrad_conv) */
+int dcs_dilate(const float* dy, float* out, int batch, int out_h, int out_w, int in_h, int in_w, int channels, int stride_h,
+               int stride_w, void* stream);
+/* z (B, h*up_h, w*up_w, c0 + c1) = complex_upsample(cat(d, skip)) (c_network.py:214-215), materialised as the wgrad's x operand */
+int dcs_upcat_fwd(const float* d, const float* skip, float* z, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream);
+/* dz = act'(y) (.) (g0 + g1 + chan_const[b][c]) per real component (ComplexReLU / ComplexLReLU act on the parts); y = the
+ * activation's OUTPUT (B, hw, channels) complex; g1 (same shape) and chan_const (B, channels) complex are optional */
+int dcs_act_bwd(const float* y, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,
+                int act, void* stream);
+/* torch.nn.Dropout(p) on n floats (c_network.py:195-196 / 203-204 / 221-222: applied on view_as_real): y = x * keep / (1 - p),
+ * keep drawn from Philox4x32-10 with key `seed` and counter offset + i / 4: the same (seed, offset) regenerates the mask for the
+ * backward.  (The reference draws from torch's generator; the streams differ, the distribution does not.) */
+int dcs_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---- backward of the attended product y = s (.) (a (.) x) (ComplexChannelAttention + ComplexSpatialAttention applied with
+ *      complex products, c_network.py:208-211 / 219-220).  Inputs saved by the forward: x, the channel gate a (B, C), the
+ *      per-pixel statistics (B, hw, 4), the spatial gate s (B, hw) (dcs_spat_apply's gate_out), the pooled sums.
+ *      dx = conj(a) du WITHOUT the per-channel constant davg / hw, which is returned in chan_const (B, C) and added by the
+ *      consumer (dcs_act_bwd).  Weight gradients in the reference's layouts: fc.0 (R, C), fc.2 (C, R), conv1 (1, 2, 7, 7). */
+typedef struct {
+  const float* x; const float* dy; const float* gate_c; const float* stats; const float* gate_s; const float* w7; const void* sums;
+  int batch; int h; int w; int channels; int reduced;
+  const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i;
+  float* dspre; float* dx; float* chan_const;
+  float* dw1_r; float* dw1_i; float* dw2_r; float* dw2_i; float* dw7_r; float* dw7_i;
+  void* workspace; int64_t workspace_bytes;
+} dcs_attention_bwd_params;
+int64_t dcs_attention_bwd_workspace_bytes(int batch, int h, int w, int channels, int reduced);
+int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream);
+
+/* ---- LSTM in training form (one direction pair of one layer; hidden = 64): pre (Q, S, 2 dirs, 4H) = x W_ih^T + b_ih + b_hh,
+ *      w_hh (n_groups, 2, 4H, H) with sequence q using group q / (Q / n_groups); outputs h (Q, S, 2, H) and, for BPTT, the
+ *      activated gates (Q, S, 2, 4H) and cell states (Q, S, 2, H).  dcs_lstm_train_bwd runs the reverse-time recurrence:
+ *      dh (Q, S, 2, H) -> dpre (Q, S, 2, 4H); dW_ih, dW_hh, db, dx are GEMMs / reductions outside it. */
+int dcs_lstm_train_fwd(const float* pre, const float* w_hh, int n_seq, int n_groups, int steps, int hidden, float* h, float* gates,
+                       float* cells, void* stream);
+int dcs_lstm_train_bwd(const float* w_hh, const float* gates, const float* cells, const float* dh, int n_seq, int n_groups, int steps,
+                       int hidden, float* dpre, void* stream);
+/* (n) interleaved complex <-> two planes (2, n); ComplexLSTM's combine (c_network.py:39-47) on h (2 lstm, 2 part, n):
+ * out = (R(re) - I(im)) + j (R(im) + I(re)), and its adjoint */
+int dcs_cplx_split(const float* x, float* planes, int64_t n, void* stream);
+int dcs_cplx_merge(const float* planes, float* x, int64_t n, void* stream);
+int dcs_clstm_combine(const float* h, float* out, int64_t n, void* stream);
+int dcs_clstm_combine_bwd(const float* dout, float* dh, int64_t n, void* stream);
+
+/* ---- optimizer (c_network.py:229-235: torch.optim.Adam(lr, eps, weight_decay, amsgrad=True); config.py:48-49 clip by global
+ *      norm 100): sum of squares of a flat fp32 buffer into a device double (accumulate = add to *out), then one fused update:
+ *      g = grad * grad_scale * min(1, max_norm / (grad_scale * sqrt(*grad_sumsq) + 1e-6)) + weight_decay * p, m / v / vmax / p. */
+int dcs_sumsq(const float* x, int64_t n, double* out, int accumulate, void* workspace, int64_t workspace_bytes, void* stream);
+int dcs_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, float* max_exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq, float max_norm,
+                     float grad_scale, void* stream);
+/* dst[i] = sum_j sign4[4i + j] * src[idx4[4i + j]] (idx < 0 = no term), stored as out_dtype: raw parameters -> kernel operand
+ * layouts (block matrices, phase pre-sums, role swaps) by an index table built once on the host, one launch per step */
+int dcs_gather_pack(const float* src, const int32_t* idx4, const int8_t* sign4, void* dst, int64_t n, int out_dtype, void* stream);
+
 /* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */
 int dcs_tc_set_debug_buffer(void* dev_ptr);
 
