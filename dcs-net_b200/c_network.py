@@ -116,10 +116,10 @@ class _StepMixin:
 
     def training_step(self, train_batch, batch_idx):
         """c_network.py:243-261: `train_batch_2_loss` in TRAIN mode (batch-statistic BatchNorm with the running-stat update) and
-        the metrics dict, on the GPU through train_engine.TrainStep (complex variants; dropout probabilities must be 0).  Returns
-        the loss as a device scalar WITHOUT a grad_fn: the backward pass is `self.train_step.backward_first_stage()` so far
-        (the remaining backward kernels and the optimizer step are not built), so a Lightning-style
-        `loss.backward()` on it is not possible."""
+        the metrics dict, on the GPU through train_engine.TrainStep (complex variants; dropout by dcs_dropout).  Returns the loss as
+        a device scalar WITHOUT a grad_fn: there is no autograd graph — the backward pass is `self.train_step.backward()` (hand-written
+        kernels filling every parameter's .grad) and the update `self.train_step.optimizer_step()` (global-norm clip + Adam-amsgrad),
+        which the train.py shim calls where Lightning would call `loss.backward()` / `optimizer.step()`."""
         from .network_functions import _variant
         variant = _variant(self, self.variant)
         if self._step_dtype != "complex":

@@ -38,7 +38,7 @@ def forward_stage(name):
 
 
 class GradBuckets:
-    def __init__(self, params, bucket_bytes=4 << 20, device=None, stage_of=forward_stage):
+    def __init__(self, params, bucket_bytes=4 << 20, device=None, stage_of=forward_stage, flat=False):
         """params: iterable of (name, Parameter), e.g. `net.named_parameters()`; buckets are laid out last-stage-first (the
         order backward produces gradients).  Complex parameters are not expected (the reference's parameters are all real)."""
         named = [(n, p) for n, p in params if p.requires_grad]
@@ -57,8 +57,13 @@ class GradBuckets:
         if cur:
             plan.append(cur)
         self.buckets, self.slices = [], {}
+        # flat=True: ONE buffer holds every bucket back to back (self.flat), so the optimizer kernels see a single array
+        self.flat = torch.zeros(sum(p.numel() for _, p in self.order), dtype=torch.float32, device=device) if flat else None
+        base = 0
         for b, members in enumerate(plan):
-            flat = torch.zeros(sum(p.numel() for _, p in members), dtype=torch.float32, device=device)
+            size = sum(p.numel() for _, p in members)
+            flat = self.flat[base:base + size] if self.flat is not None else torch.zeros(size, dtype=torch.float32, device=device)
+            base += size
             off = 0
             for n, p in members:
                 view = flat[off:off + p.numel()].view_as(p)
@@ -82,6 +87,20 @@ class GradBuckets:
         """Start the all-reduce of one bucket (call as soon as backward has finished writing it)."""
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
             self._pending.append((index, dist.all_reduce(self.buckets[index], op=dist.ReduceOp.SUM, group=group, async_op=True)))
+
+    def wait(self, group=None):
+        """Wait for the launched buckets and reduce any that were not launched; the SUM stays in the buckets (the fused optimizer
+        kernel applies 1 / world itself)."""
+        world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+        launched = {i for i, _ in self._pending}
+        for _, w in self._pending:
+            w.wait()
+        self._pending = []
+        if world > 1:
+            for i, b in enumerate(self.buckets):
+                if i not in launched:
+                    dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group)
+        return self
 
     def finish(self, group=None):
         """Wait for the launched buckets, reduce any that were not launched, divide by the world size."""

@@ -211,7 +211,8 @@ def cwgrad_generic(x, dy, kernel, stride=(1, 1), transposed=False, dw_r=None, dw
     shape = (cin, cout, kh, kw) if transposed else (cout, cin, kh, kw)
     dw_r = dw_r if dw_r is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
     dw_i = dw_i if dw_i is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
-    assert tuple(dw_r.shape) == shape and dw_r.is_contiguous() and dw_i.is_contiguous()
+    n = cin * cout * kh * kw
+    assert dw_r.numel() == n and dw_i.numel() == n and dw_r.is_contiguous() and dw_i.is_contiguous()
     L.check(L.lib().dcs_wgrad_fold_complex(L.ptr(dwp), kh * kw, cin, cout, int(transposed), L.ptr(dw_r), L.ptr(dw_i), L.stream_ptr()),
             "dcs_wgrad_fold_complex")
     return dw_r, dw_i

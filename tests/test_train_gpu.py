@@ -178,6 +178,97 @@ def test_train_mode_forward_reproduces_reference_losses_and_running_stats():
     assert math.isfinite(float(b["g_d5"].abs().sum()))
 
 
+def _golden_step(variant="dcs", dropout=(0.0, 0.0)):
+    import dcsnet_b200 as D  # noqa: F401
+    from dcsnet_b200 import config as cfg, c_network, train_engine
+    g = load_golden("train_step.pt")
+    hp = dict(cfg.hparams)
+    hp["dropout_conv"], hp["dropout_fc"] = dropout
+    net = c_network.C_NETWORK(cfg.config, hp, 0).cuda()
+    clean, noise, noisy = O.synthetic_audio(g["B"], 32 * (g["T"] - 1), seed=g["audio_seed"])
+    specs = (O.stft(noise).cuda(), O.stft(noisy).cuda(), O.stft(clean).cuda())
+    return g, net, train_engine.TrainStep(net, variant), specs
+
+
+def test_whole_backward_reproduces_the_reference_gradients():
+    """TrainStep.forward + TrainStep.backward (every backward kernel of the training step, no autograd) against the REFERENCE's own
+    train_batch_2_loss + backward() (tests/golden/train_step.pt): every one of the 198 parameter gradients (L2 norm, |max|, first
+    8 values) and the global gradient norm that gradient_clip_val acts on."""
+    g, net, step, specs = _golden_step()
+    w = g["dcs"]
+    step.forward(*specs)
+    step.backward()
+    torch.cuda.synchronize()
+    params = dict(net.named_parameters())
+    assert set(w["grads"]) | set(w["no_grad"]) == set(params)
+    worst = {}
+    total = 0.0
+    for k, f in w["grads"].items():
+        gr = params[k].grad
+        assert gr is not None, k
+        gr = gr.detach().float().cpu()
+        assert tuple(gr.shape) == f["shape"], k
+        total += float(gr.double().pow(2).sum())
+        # relative to the gradient's own size; tensors whose reference gradient is round-off noise (the 26 conv biases in front of
+        # a train-mode BatchNorm: exactly zero in exact arithmetic, 1e-9 .. 2e-7 in the fixture against a global norm of 25) are
+        # compared on an absolute floor of 1e-5 of the global norm
+        floor = 1e-5 * w["grad_norm"]
+        scale = max(f["max_abs"], floor)
+        worst[k] = max(abs(float(gr.norm()) - f["norm"]) / max(f["norm"], floor),
+                       float((gr.reshape(-1)[:8] - f["head"]).abs().max()) / scale)
+    bad = {k: v for k, v in worst.items() if v > 2e-3}
+    assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
+    assert abs(total ** 0.5 - w["grad_norm"]) <= 1e-3 * w["grad_norm"]
+
+
+def test_optimizer_step_matches_torch_adam_amsgrad_with_clip():
+    """TrainStep.optimizer_step (dcs_sumsq + dcs_adam_amsgrad on the flat buffers: global-norm clip, L2 weight decay, amsgrad) against
+    torch.nn.utils.clip_grad_norm_ + torch.optim.Adam(amsgrad=True) applied to the same gradients, two steps; gradient_clip_val is
+    lowered so that the clip is active."""
+    g, net, step, specs = _golden_step()
+    step.hp = dict(step.hp)
+    step.hp["gradient_clip_val"] = 0.5 * g["dcs"]["grad_norm"]
+    step.init_optimizer()
+    import copy
+    ref = copy.deepcopy(net)
+    opt = torch.optim.Adam(ref.parameters(), lr=step.hp["lr"], eps=step.hp["optim_eps"], weight_decay=step.hp["optim_weight_decay"], amsgrad=True)
+    for it in range(2):
+        step.forward(*specs)
+        step.backward()
+        for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            q.grad = p.grad.detach().clone()
+        torch.nn.utils.clip_grad_norm_(ref.parameters(), step.hp["gradient_clip_val"])
+        opt.step()
+        step.optimizer_step()
+        torch.cuda.synchronize()
+        for (k, p), (_, q) in zip(net.named_parameters(), ref.named_parameters()):
+            assert float((p.detach() - q.detach()).abs().max()) <= 2e-6 * max(float(q.detach().abs().max()), 1e-3) + 1e-9, (it, k)
+    # the second forward ran on the UPDATED parameters (operands re-packed), so its loss moved
+    assert step.opt["step"] == 2
+
+
+def test_training_step_with_dropout_runs_and_is_reproducible():
+    """Dropout at the reference's probabilities (config.py:41-42): Philox masks regenerated in the backward from (seed, offset); the
+    same seed gives the same step, another seed another one; expectation-level agreement with the reference's dropout loss."""
+    g, net, step, specs = _golden_step(dropout=(0.1, 0.2))
+    out1 = step.forward(*specs)
+    step.backward()
+    torch.cuda.synchronize()
+    g1 = {k: p.grad.detach().clone() for k, p in net.named_parameters() if p.grad is not None}
+    assert len(g1) == len(g["dcs"]["grads"])
+    assert all(torch.isfinite(v).all() for v in g1.values())
+    l1 = float(out1["train_loss"])
+    _, net2, step2, _ = _golden_step(dropout=(0.1, 0.2))
+    out2 = step2.forward(*specs)
+    step2.backward()
+    assert float(out2["train_loss"]) == l1
+    assert all(torch.equal(p.grad, g1[k]) for k, p in net2.named_parameters() if p.grad is not None)
+    step2.seed = 7
+    assert float(step2.forward(*specs)["train_loss"]) != l1
+    ref = g["dcs_dropout"]["train_loss"]                       # another random stream: same distribution, not the same number
+    assert abs(l1 - ref) < 3.0
+
+
 @pytest.mark.parametrize("cin,cout,k,stride,B,H,W", [(64, 128, 3, (2, 1), 2, 16, 70), (32, 64, 5, (2, 1), 3, 8, 130), (128, 128, 3, (2, 1), 2, 8, 64),
                                                      (64, 64, 3, (1, 1), 2, 6, 33)])
 def test_conv_wgrad_on_tcgen05(cin, cout, k, stride, B, H, W):
@@ -228,4 +319,4 @@ def test_entry_point_shims_honour_the_reference_command_line(script, args):
         assert line["batches"] == 2 and all(math.isfinite(v) or v != v for v in line["metrics"].values())
         assert any(k.endswith("speech_loss") for k in line["metrics"])
     else:
-        assert len(line["steps"]) == 2 and all(math.isfinite(s["loss"]) and s["g_d5_norm"] > 0 for s in line["steps"]) and line["optimizer_step"] is False
+        assert len(line["steps"]) == 2 and all(math.isfinite(s["loss"]) and s["grad_norm"] > 0 for s in line["steps"]) and line["optimizer_step"] is True

@@ -3,12 +3,11 @@
 
 The reference builds the VoiceBank loaders, the network of the variant and a Lightning Trainer (gradient clip 100 by norm, SWA,
 ReduceLROnPlateau) and calls `trainer.fit`.  What this shim runs ON THE GPU per step, for the complex variants (dcs / dc):
-`network.training_step(batch, idx)` = train-mode `C_NETWORK.forward` (batch-statistic BatchNorm, running-stat update) + `calc_loss`,
-then the first backward stage (loss -> iSTFT adjoint -> mask-tail adjoint -> decoder[6] dgrad), `dcsnet_b200.train_engine.TrainStep`.
-The rest of the backward pass and the Adam-amsgrad update are NOT built yet, so parameters are not updated:
-the script reports the per-step losses and says so (`"optimizer_step": false`) instead of pretending to train.  The real variants
-(dr / drs) exit with a clear message.  Data: seeded synthetic batches (no VoiceBank data in the image); dropout is set to 0
-(train-mode dropout kernels are not built).
+`network.training_step(batch, idx)` = train-mode `C_NETWORK.forward` (batch-statistic BatchNorm, running-stat update, dropout) +
+`calc_loss`, then `network.train_step.backward()` (the whole backward pass as hand-written kernels) and
+`network.train_step.optimizer_step()` (NCCL all-reduce of the flat gradient buckets when launched under torchrun, global-norm clip,
+Adam-amsgrad) — `dcsnet_b200.train_engine.TrainStep`.  The real variants (dr / drs) exit with a clear message.  Data: seeded synthetic
+batches (no VoiceBank data in the image).  SWA / ReduceLROnPlateau / checkpointing are Lightning's (out of scope).
 """
 import argparse
 import json
@@ -37,21 +36,19 @@ def main():
         raise SystemExit("train.py needs a CUDA device (sm_100a); dcsnet_b200 has no CPU fallback")
     torch.cuda.set_device(a.gpu)
     hp = dict(cfg.hparams)
-    hp["dropout_conv"], hp["dropout_fc"] = 0.0, 0.0
     network = c_network.C_NETWORK(cfg.config, hp, cfg.config.seed).cuda().train()
     network.variant = a.variant
-    network.configure_optimizers()          # the reference's Adam-amsgrad + ReduceLROnPlateau objects (not stepped, see above)
     log = []
     for idx in range(a.steps):
         clean, noise, noisy = O.synthetic_audio(a.batch, 32 * (a.frames - 1), seed=2000 + idx)
         batch = (ops.stft(noise.cuda()), ops.stft(noisy.cuda()), ops.stft(clean.cuda()), [f"synthetic_{idx}"] * a.batch)
         loss = network.training_step(batch, idx)
-        grads = network.train_step.backward_first_stage()
-        log.append({"step": idx, "loss": float(loss), "d_raw_norm": float(torch.view_as_real(grads["d_raw"]).norm()),
-                    "g_d5_norm": float(grads["g_d5"].norm())})
+        network.train_step.backward()
+        sumsq = network.train_step.optimizer_step()
+        log.append({"step": idx, "loss": float(loss), "grad_norm": float(sumsq.sqrt())})
     torch.cuda.synchronize()
-    print(json.dumps({"variant": a.variant, "gpu": a.gpu, "steps": log, "optimizer_step": False,
-                      "note": "train-mode forward + losses + first backward stage on the GPU; remaining backward kernels and the optimizer are not built"}))
+    print(json.dumps({"variant": a.variant, "gpu": a.gpu, "steps": log, "optimizer_step": True,
+                      "note": "train-mode forward + losses + whole backward pass + clip + Adam-amsgrad, all hand-written sm_100a kernels"}))
 
 
 if __name__ == "__main__":
