@@ -10,6 +10,8 @@
 //   LSTM forward with saved gates + BPTT ................... lstm_forward_saved / lstm_bptt (c_network.py:12-51)
 //   Adam-amsgrad with the global-norm clip ................. c_network.py:229-235, config.py:48-49
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include "common.cuh"
 
 namespace dcs {
@@ -97,6 +99,95 @@ __global__ void __launch_bounds__(256) wgrad_generic_kernel(const WgArgs a) {
       const int n = n0 + tx * RN + j;
       if (n < a.n2) out[(int64_t)m * a.n2 + n] = acc[i][j];
     }
+  }
+}
+
+// Few-channel layers (n2 <= 32: encoder[0..1], decoder[4..6]; millions of pixels, a few thousand gradient elements): the GEMM
+// tiling above wastes its N tile and re-reads x once per tap.  Here a persistent CTA walks 4 x 16-pixel output tiles: the x tile with
+// its halo and the dy tile are staged in shared memory once, thread t owns gradient row (tap, k) = blockIdx.y * 256 + t with all
+// N2 columns in registers and streams the 64 pixels (one LDS of x + N2 / 4 broadcast LDS.128 of dy per N2 FMAs).  One partial
+// [rows][n2] block per CTA, combined by split_reduce_kernel in a fixed order.
+constexpr int kWsTH = 4, kWsTW = 16;
+struct WsArgs {
+  const float* x; const float* dy; float* ws;
+  int batch, in_h, in_w, out_h, out_w, k2, n2, x_pitch, dy_pitch, sh, sw, ntaps, rows;
+  int min_dy, min_dx, XH, XW, tiles_h, tiles_w, n_tiles;
+  int8_t dyo[DCS_MAX_TAPS], dxo[DCS_MAX_TAPS];
+};
+template <int N2>
+__global__ void __launch_bounds__(256) wgrad_small_kernel(const WsArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  float* xs = smem;                                    // [XH][XW][k2]
+  float* dys = smem + (((size_t)a.XH * a.XW * a.k2 + 3) & ~(size_t)3);      // [TH * TW][N2], 16-byte aligned
+  const int tid = threadIdx.x;
+  const int row = blockIdx.y * 256 + tid;
+  const bool ok = row < a.rows;
+  const int tap = ok ? row / a.k2 : 0, kch = ok ? row % a.k2 : 0;
+  const int xoff = ((a.dyo[tap] - a.min_dy) * a.XW + (a.dxo[tap] - a.min_dx)) * a.k2 + kch;
+  float acc[N2];
+#pragma unroll
+  for (int j = 0; j < N2; ++j) acc[j] = 0.f;
+  const int xt = a.XH * a.XW * a.k2;
+  for (int t = blockIdx.x; t < a.n_tiles; t += gridDim.x) {
+    const int tw = t % a.tiles_w, th = (t / a.tiles_w) % a.tiles_h, b = t / (a.tiles_w * a.tiles_h);
+    const int oh0 = th * kWsTH, ow0 = tw * kWsTW;
+    const int iy0 = oh0 * a.sh + a.min_dy, ix0 = ow0 * a.sw + a.min_dx;
+    __syncthreads();                                   // the previous tile's readers are done
+    if ((a.k2 & 3) == 0 && (a.x_pitch & 3) == 0 && ((uintptr_t)a.x & 15) == 0) {
+      const int k4 = a.k2 >> 2;
+      for (int i = tid; i < xt >> 2; i += 256) {
+        const int k = i % k4, px = i / k4;
+        const int xx = px % a.XW, yy = px / a.XW;
+        const int iy = iy0 + yy, ix = ix0 + xx;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if ((unsigned)iy < (unsigned)a.in_h && (unsigned)ix < (unsigned)a.in_w)
+          v = *reinterpret_cast<const float4*>(a.x + (((int64_t)b * a.in_h + iy) * a.in_w + ix) * a.x_pitch + 4 * k);
+        reinterpret_cast<float4*>(xs)[i] = v;
+      }
+    } else {
+      for (int i = tid; i < xt; i += 256) {
+        const int k = i % a.k2, px = i / a.k2;
+        const int xx = px % a.XW, yy = px / a.XW;
+        const int iy = iy0 + yy, ix = ix0 + xx;
+        xs[i] = ((unsigned)iy < (unsigned)a.in_h && (unsigned)ix < (unsigned)a.in_w)
+                    ? a.x[(((int64_t)b * a.in_h + iy) * a.in_w + ix) * a.x_pitch + k] : 0.f;
+      }
+    }
+    for (int i = tid; i < kWsTH * kWsTW * N2; i += 256) {
+      const int n = i % N2, px = i / N2;
+      const int oh = oh0 + px / kWsTW, ow = ow0 + px % kWsTW;
+      dys[i] = (n < a.n2 && oh < a.out_h && ow < a.out_w) ? a.dy[(((int64_t)b * a.out_h + oh) * a.out_w + ow) * a.dy_pitch + n] : 0.f;
+    }
+    __syncthreads();
+    if (ok) {
+#pragma unroll
+      for (int r = 0; r < kWsTH; ++r) {
+        const float* xr = xs + xoff + (r * a.sh * a.XW) * a.k2;
+        const int cstep = a.sw * a.k2;
+#pragma unroll 4
+        for (int c = 0; c < kWsTW; ++c) {
+          const float xv = xr[c * cstep];
+          const float* dp = dys + (r * kWsTW + c) * N2;
+          if constexpr (N2 >= 4) {
+#pragma unroll
+            for (int j = 0; j < N2; j += 4) {
+              const float4 d4 = *reinterpret_cast<const float4*>(dp + j);
+              acc[j] = fmaf(xv, d4.x, acc[j]); acc[j + 1] = fmaf(xv, d4.y, acc[j + 1]);
+              acc[j + 2] = fmaf(xv, d4.z, acc[j + 2]); acc[j + 3] = fmaf(xv, d4.w, acc[j + 3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < N2; ++j) acc[j] = fmaf(xv, dp[j], acc[j]);
+          }
+        }
+      }
+    }
+  }
+  if (ok) {
+    float* out = a.ws + ((int64_t)blockIdx.x * a.rows + row) * a.n2;
+#pragma unroll
+    for (int j = 0; j < N2; ++j)
+      if (j < a.n2) out[j] = acc[j];
   }
 }
 
@@ -750,16 +841,45 @@ __global__ void gather_pack_kernel(const float* __restrict__ src, const int4* __
     if (id.z >= 0) s += (float)sg.z * src[id.z];
     if (id.w >= 0) s += (float)sg.w * src[id.w];
     if (out_dtype == DCS_F32) reinterpret_cast<float*>(dst)[i] = s;
-    else if (out_dtype == DCS_F16) reinterpret_cast<__half*>(dst)[i] = from_float<__half>(s);
+    else if (out_dtype == 3) {        // fp32 rounded to tf32 (nearest even): the tensor core would otherwise truncate the low 13 bits
+      uint32_t u = __float_as_uint(s);
+      u = (u + 0xFFFu + ((u >> 13) & 1u)) & ~0x1FFFu;
+      reinterpret_cast<float*>(dst)[i] = __uint_as_float(u);
+    } else if (out_dtype == DCS_F16) reinterpret_cast<__half*>(dst)[i] = from_float<__half>(s);
     else reinterpret_cast<__nv_bfloat16*>(dst)[i] = from_float<__nv_bfloat16>(s);
   }
 }
 
 static int ew_grid(int64_t n) { return (int)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16)); }
 
-struct WgPlan { int rm, rn, mt, nt, splits; int64_t n_items, items_per_split; int segs; };
+struct WgPlan { int rm, rn, mt, nt, splits; int64_t n_items, items_per_split; int segs; int small, N2, workers, row_groups; size_t smem; WsArgs sa; };
 static WgPlan wg_plan(const dcs_wgrad_params* p) {
   WgPlan w;
+  memset(&w, 0, sizeof(w));
+  // few-channel path
+  if (p->n2 <= 32 && p->ntaps * p->k2 >= 64 && !getenv("DCS_WGRAD_NO_SMALL")) {
+    WsArgs& a = w.sa;
+    int mn_y = 127, mx_y = -127, mn_x = 127, mx_x = -127;
+    for (int t = 0; t < p->ntaps; ++t) {
+      mn_y = std::min<int>(mn_y, p->dy_off[t]); mx_y = std::max<int>(mx_y, p->dy_off[t]);
+      mn_x = std::min<int>(mn_x, p->dx_off[t]); mx_x = std::max<int>(mx_x, p->dx_off[t]);
+    }
+    a.min_dy = mn_y; a.min_dx = mn_x;
+    a.XH = (kWsTH - 1) * p->stride_h + (mx_y - mn_y) + 1;
+    a.XW = (kWsTW - 1) * p->stride_w + (mx_x - mn_x) + 1;
+    w.N2 = p->n2 <= 2 ? 2 : (p->n2 <= 16 ? 16 : 32);
+    w.smem = ((((size_t)a.XH * a.XW * p->k2 + 3) & ~(size_t)3) + (size_t)kWsTH * kWsTW * w.N2) * sizeof(float);
+    if (w.smem <= 96 * 1024) {
+      w.small = 1;
+      a.rows = p->ntaps * p->k2;
+      w.row_groups = (a.rows + 255) / 256;
+      a.tiles_h = (p->out_h + kWsTH - 1) / kWsTH; a.tiles_w = (p->out_w + kWsTW - 1) / kWsTW;
+      a.n_tiles = p->batch * a.tiles_h * a.tiles_w;
+      w.workers = std::max(1, std::min(a.n_tiles, (3 * num_sms() + w.row_groups - 1) / w.row_groups));
+      w.splits = w.workers;
+      return w;
+    }
+  }
   const int mtot = p->ntaps * p->k2;
   w.rn = p->n2 >= 48 ? 4 : 1;
   w.rm = 4;
@@ -793,6 +913,30 @@ extern "C" int dcs_wgrad(const dcs_wgrad_params* p, void* stream) {
               p->out_w > 0 && p->stride_h > 0 && p->stride_w > 0 && p->x_pitch >= p->k2 && p->dy_pitch >= p->n2, "dcs_wgrad: bad shape");
   DCS_REQUIRE(p->workspace_bytes >= dcs_wgrad_workspace_bytes(p), "dcs_wgrad: workspace too small");
   const WgPlan w = wg_plan(p);
+  if (w.small) {
+    WsArgs sa = w.sa;
+    sa.x = p->x; sa.dy = p->dy; sa.ws = reinterpret_cast<float*>(p->workspace);
+    sa.batch = p->batch; sa.in_h = p->in_h; sa.in_w = p->in_w; sa.out_h = p->out_h; sa.out_w = p->out_w; sa.k2 = p->k2; sa.n2 = p->n2;
+    sa.x_pitch = p->x_pitch; sa.dy_pitch = p->dy_pitch; sa.sh = p->stride_h; sa.sw = p->stride_w; sa.ntaps = p->ntaps;
+    for (int t = 0; t < p->ntaps; ++t) { sa.dyo[t] = p->dy_off[t]; sa.dxo[t] = p->dx_off[t]; }
+    cudaStream_t s = (cudaStream_t)stream;
+    dim3 grid(w.workers, w.row_groups);
+    if (w.N2 == 2) {
+      DCS_CUDA(cudaFuncSetAttribute(wgrad_small_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+      wgrad_small_kernel<2><<<grid, 256, w.smem, s>>>(sa);
+    } else if (w.N2 == 16) {
+      DCS_CUDA(cudaFuncSetAttribute(wgrad_small_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+      wgrad_small_kernel<16><<<grid, 256, w.smem, s>>>(sa);
+    } else {
+      DCS_CUDA(cudaFuncSetAttribute(wgrad_small_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w.smem));
+      wgrad_small_kernel<32><<<grid, 256, w.smem, s>>>(sa);
+    }
+    DCS_LAUNCHED();
+    const int64_t n = (int64_t)sa.rows * p->n2;
+    split_reduce_kernel<<<ew_grid(n), 256, 0, s>>>(sa.ws, p->dwp, n, w.workers);
+    DCS_LAUNCHED();
+    return 0;
+  }
   WgArgs a;
   a.x = p->x; a.dy = p->dy; a.ws = reinterpret_cast<float*>(p->workspace);
   a.batch = p->batch; a.in_h = p->in_h; a.in_w = p->in_w; a.out_h = p->out_h; a.out_w = p->out_w; a.k2 = p->k2; a.n2 = p->n2;
@@ -1006,7 +1150,7 @@ extern "C" int dcs_adam_amsgrad(float* param, const float* grad, float* exp_avg,
 }
 
 extern "C" int dcs_gather_pack(const float* src, const int32_t* idx4, const int8_t* sign4, void* dst, int64_t n, int out_dtype, void* stream) {
-  DCS_REQUIRE(src && idx4 && sign4 && dst && n > 0 && is_dtype(out_dtype), "dcs_gather_pack: bad arguments");
+  DCS_REQUIRE(src && idx4 && sign4 && dst && n > 0 && (is_dtype(out_dtype) || out_dtype == 3), "dcs_gather_pack: bad arguments");
   gather_pack_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(src, (const int4*)idx4, (const char4*)sign4, dst, n, out_dtype);
   DCS_LAUNCHED();
   return 0;

@@ -26,8 +26,11 @@ ADAM_BETAS = (0.9, 0.999)        # torch.optim.Adam defaults (c_network.py:229-2
 
 
 class TrainStep:
-    def __init__(self, model, variant="dcs", speech_alpha=None, atan2_eps=None, seed=0):
-        assert variant in ("dcs", "dc")
+    def __init__(self, model, variant="dcs", speech_alpha=None, atan2_eps=None, seed=0, mode="fp32"):
+        """mode: "fp32" = CUDA-core FFMA convolutions (the parity mode); "tf32" = the forward and data-gradient convolutions on the
+        tensor cores (tcgen05 kind::tf32 through dcs_cconv2d_tc_fwd, fp32 storage, fp32 accumulation)."""
+        assert variant in ("dcs", "dc") and mode in ("fp32", "tf32")
+        self.mode = mode
         hp = getattr(model, "hparams", {})
         self.model, self.variant, self.hp = model, variant, hp
         self.alpha = float(speech_alpha if speech_alpha is not None else hp.get("speech_alpha", 0.7))
@@ -37,6 +40,8 @@ class TrainStep:
         self.seed, self.steps_done = int(seed), 0
         self.L = int(hp.get("no_of_layers", 7))
         self._packed_key = None
+        self._stale = False
+        self.gather = None
         self.opt = None
         self.saved = None
 
@@ -44,20 +49,29 @@ class TrainStep:
     def _pack(self, device):
         sd = _sd_tensor_dict(self.model)
         key = (str(device),) + tuple((v.data_ptr(), v._version) for v in sd.values())
-        if key == self._packed_key:
+        if key == self._packed_key and not self._stale:
+            return
+        if self.gather is not None and self._packed_key is not None and key[0] == self._packed_key[0]:
+            self.gather.run()                 # one launch: every operand rebuilt from the flat parameter buffer
+            self._packed_key, self._stale = key, False
             return
         Lr = self.L
+        tf = self.mode == "tf32"
         self.enc, self.dec, self.enc_dgrad, self.dec_dgrad = [], [], [], []
         for i in range(Lr):
             p = f"encoder.{i}.0."
             self.enc.append(packing.PackedConv(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], sd[p + "conv_r.bias"], sd[p + "conv_i.bias"],
-                                               stride=STRIDE_E[i], act=L.ACT_NONE, device=device))
-            self.enc_dgrad.append(T.dgrad_conv(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], transposed=False, device=device))
+                                               stride=STRIDE_E[i], act=L.ACT_NONE, device=device, want_tf32=tf))
+            self.enc_dgrad.append(T.dgrad_conv(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], transposed=False, device=device, want_tf32=tf))
         for i in range(Lr):
             p = f"decoder.{i}." if i == Lr - 1 else f"decoder.{i}.0."
             self.dec.append(packing.PackedConv(sd[p + "conv_tran_r.weight"], sd[p + "conv_tran_i.weight"], sd[p + "conv_tran_r.bias"],
-                                               sd[p + "conv_tran_i.bias"], transposed=True, up=UPSAMPLE[i], act=L.ACT_NONE, device=device))
-            self.dec_dgrad.append(T.dgrad_conv(sd[p + "conv_tran_r.weight"], sd[p + "conv_tran_i.weight"], transposed=True, device=device))
+                                               sd[p + "conv_tran_i.bias"], transposed=True, up=UPSAMPLE[i], act=L.ACT_NONE, device=device, want_tf32=tf))
+            # data gradient per source (decoder path d: the first half of the input channels, skip: the second), so that each GEMM's
+            # N = 2 * channels stays within the tensor-core kernel's 256 columns
+            c0 = sd[p + "conv_tran_r.weight"].shape[0] // 2
+            self.dec_dgrad.append(tuple(T.dgrad_conv(sd[p + "conv_tran_r.weight"][sl], sd[p + "conv_tran_i.weight"][sl], transposed=True, device=device,
+                                                     want_tf32=tf) for sl in (slice(0, c0), slice(c0, None))))
         self.skip_ca = [packing.pack_channel_attention(sd, f"skip_attention.{2 * i}.", device) for i in range(Lr)]
         self.skip_sa = [packing.pack_spatial_attention(sd, f"skip_attention.{2 * i + 1}.", device) for i in range(Lr)]
         self.dec_ca = [packing.pack_channel_attention(sd, f"decoder_attention.{2 * i}.", device) for i in range(Lr - 1)]
@@ -70,10 +84,17 @@ class TrainStep:
         self.lstm_b = [[torch.cat([f(f"{n}.bias_ih_l{l}{s}") + f(f"{n}.bias_hh_l{l}{s}") for s in sfx], 0).contiguous() for n in names] for l in range(2)]
         self.lstm_whh = [torch.stack([torch.stack([f(f"{n}.weight_hh_l{l}{s}") for s in sfx], 0) for n in names], 0).contiguous() for l in range(2)]
         self.fc = packing.PackedConv(sd["fc.fc_r.weight"][:, :, None, None], sd["fc.fc_i.weight"][:, :, None, None], sd["fc.fc_r.bias"],
-                                     sd["fc.fc_i.bias"], device=device)
-        self.fc_dgrad = T.dgrad_conv(sd["fc.fc_r.weight"][:, :, None, None], sd["fc.fc_i.weight"][:, :, None, None], transposed=False, device=device)
-        self.dec6_dgrad = self.dec_dgrad[Lr - 1]
-        self._packed_key = key
+                                     sd["fc.fc_i.bias"], device=device, want_tf32=tf)
+        self.fc_dgrad = T.dgrad_conv(sd["fc.fc_r.weight"][:, :, None, None], sd["fc.fc_i.weight"][:, :, None, None], transposed=False, device=device,
+                                     want_tf32=tf)
+        self._packed_key, self._stale = key, False
+
+    def _conv(self, pk, src0, src1, dst):
+        """One complex convolution: tcgen05 kind::tf32 when the mode and the layer allow it (>= 4 complex channels per source = 32-byte
+        rows for the operand loader, 2 cout <= 256), CUDA-core FFMA otherwise."""
+        c1 = 0 if src1 is None else src1.shape[3]
+        tc = self.mode == "tf32" and pk.w_tc32 is not None and src0.shape[3] % 4 == 0 and c1 % 4 == 0 and 2 * pk.cout <= 256
+        return ops.cconv(pk, src0, src1, dst, use_tc=tc)
 
     def _bn(self, x, prefix, act):
         """Train-mode ComplexBatchNorm2d on the module's own parameters / buffers (running statistics updated in place)."""
@@ -135,7 +156,7 @@ class TrainStep:
         H, W = F, Tn
         for i in range(Lr):
             H, W = ops.conv_out_hw(self.enc[i], H, W)
-            pre = ops.cconv(self.enc[i], x, None, new(B, H, W, self.enc[i].cout, 2))
+            pre = self._conv(self.enc[i], x, None, new(B, H, W, self.enc[i].cout, 2))
             x, sv[f"enc{i}"] = self._bn(pre, f"encoder.{i}.1", L.ACT_RELU)
             sv[f"enc{i}_pre"] = pre
             x = self._drop(x, self.p_conv, f"enc{i}")
@@ -144,14 +165,14 @@ class TrainStep:
         S = H * W
         lat = self._lstm_forward(x.view(B, S, x.shape[3], 2), sv)
         sv["lat"] = lat
-        d = ops.cconv(self.fc, lat.view(B, 1, S, 128, 2), None, new(B, 1, S, self.fc.cout, 2)).view(B, H, W, self.fc.cout, 2)
+        d = self._conv(self.fc, lat.view(B, 1, S, 128, 2), None, new(B, 1, S, self.fc.cout, 2)).view(B, H, W, self.fc.cout, 2)
         d = self._drop(d, self.p_fc, "fc")
         sv["dec_in"], sv["skip"], sv["skip_att"], sv["dec_att"], sv["dec_act"] = [], [], [], [], []
         for i in range(Lr):
             skip, att = T.attention_fwd_saved(enc[Lr - i], self.skip_ca[i], self.skip_sa[i])
             sv["dec_in"].append(d), sv["skip"].append(skip), sv["skip_att"].append(att)
             H, W = H * UPSAMPLE[i][0], W * UPSAMPLE[i][1]
-            pre = ops.cconv(self.dec[i], d, skip, new(B, H, W, self.dec[i].cout, 2))
+            pre = self._conv(self.dec[i], d, skip, new(B, H, W, self.dec[i].cout, 2))
             if i == Lr - 1:
                 pre = self._drop(pre, self.p_conv, f"dec{i}")
                 sv["d5"], sv["skip6"] = d, skip
@@ -206,10 +227,18 @@ class TrainStep:
             g_clean, g_noise, d_raw = self._tail_backward()
             B, F, Tn = d_raw.shape
             dy = self._drop_bwd(torch.view_as_real(d_raw).view(B, F, Tn, 1, 2), f"dec{self.L - 1}")
-            c0, c1 = sv["d5"].shape[3], sv["skip6"].shape[3]
-            g_up = ops.cconv(self.dec6_dgrad, dy, None, torch.empty(B, F, Tn, c0 + c1, 2, dtype=torch.float32, device=dev))
-            g_d5, g_skip6 = T.upcat_adjoint(g_up, c0, c1, UPSAMPLE[self.L - 1])
+            g_d5, g_skip6 = self._dec_dgrad(self.L - 1, dy.contiguous(), sv["d5"].shape[3], sv["skip6"].shape[3])
         return dict(g_clean_wave=g_clean, g_noise_wave=g_noise, d_raw=d_raw, g_d5=g_d5, g_skip6=g_skip6)
+
+    def _dec_dgrad(self, i, dpre, c0, c1):
+        """Data gradient of decoder stage i's cat + up-sampling + ComplexConvTranspose2d: per source, the forward conv kernel with the
+        role-swapped weights, then the up-sampling adjoint (sum over each up_h x up_w block)."""
+        B, HH, WW = dpre.shape[0], dpre.shape[1], dpre.shape[2]
+        out = []
+        for pk, c in zip(self.dec_dgrad[i], (c0, c1)):
+            g_up = self._conv(pk, dpre, None, torch.empty(B, HH, WW, c, 2, dtype=torch.float32, device=dpre.device))
+            out.append(T.upcat_adjoint(g_up, c, 0, UPSAMPLE[i])[0])
+        return out
 
     def _grad(self, name):
         """The parameter's .grad tensor (allocated on first use; GradBuckets / FlatAdam make it a view into a flat buffer)."""
@@ -304,9 +333,7 @@ class TrainStep:
             z = T.upcat_fwd(d_in, skip, UPSAMPLE[i])
             self._conv_param_grads(z, dpre, prefix, ("conv_tran_r", "conv_tran_i"), 3, (1, 1), True)
             del z
-            c0, c1 = d_in.shape[3], skip.shape[3]
-            g_up = ops.cconv(self.dec_dgrad[i], dpre, None, new(B, dpre.shape[1], dpre.shape[2], c0 + c1, 2))
-            g, g_skip = T.upcat_adjoint(g_up, c0, c1, UPSAMPLE[i])
+            g, g_skip = self._dec_dgrad(i, dpre, d_in.shape[3], skip.shape[3])
             if i == Lr - 1:
                 info["g_d5"], info["g_skip6"] = g, g_skip
             att = sv["skip_att"][i]
@@ -319,7 +346,7 @@ class TrainStep:
         g = self._drop_bwd(g, "fc").contiguous().view(B, 1, S, 128, 2)
         lat = sv["lat"].view(B, 1, S, 128, 2)
         self._conv_param_grads(lat, g, "fc.", ("fc_r", "fc_i"), 1, (1, 1), False)
-        g_lat = ops.cconv(self.fc_dgrad, g, None, new(B, 1, S, 128, 2))
+        g_lat = self._conv(self.fc_dgrad, g, None, new(B, 1, S, 128, 2))
         g = self._lstm_backward(g_lat.view(B, S, 128, 2)).view(B, Hl, Wl, 128, 2)
         info["g_latent_in"] = g
         # ---- encoder, last layer first: enc[i + 1] feeds encoder i + 1 (or the LSTM) AND skip attention Lr - 1 - i
@@ -335,7 +362,7 @@ class TrainStep:
             x_in = enc[i]
             self._conv_param_grads(x_in, dpre, f"encoder.{i}.0.", ("conv_r", "conv_i"), KERNEL_E[i], STRIDE_E[i], False)
             Hi, Wi = x_in.shape[1], x_in.shape[2]
-            g = ops.cconv(self.enc_dgrad[i], T.dilate(dpre, Hi, Wi, STRIDE_E[i]), None, new(B, Hi, Wi, x_in.shape[3], 2))
+            g = self._conv(self.enc_dgrad[i], T.dilate(dpre, Hi, Wi, STRIDE_E[i]), None, new(B, Hi, Wi, x_in.shape[3], 2))
         self._bn_bwd(sv["x0"].contiguous(), g, "initial_batchnorm", "bn0")
         return info
 
@@ -358,8 +385,61 @@ class TrainStep:
         self.opt = dict(m=torch.zeros(n, device=dev), v=torch.zeros(n, device=dev), vmax=torch.zeros(n, device=dev), step=0,
                         sumsq=torch.zeros(1, dtype=torch.float64, device=dev), ws=torch.empty(8 * 4096, dtype=torch.uint8, device=dev),
                         world=world_size)
-        self._packed_key = None
+        self._packed_key, self.gather = None, None
+        self._pack(dev)                                   # host packing once (shapes, tap tables); the tensors are redirected below
+        self._build_gather(dev)
         return self
+
+    def _build_gather(self, dev):
+        """(index, sign) tables of every packed operand w.r.t. the flat parameter buffer (train_pack.py): after an optimizer step ONE
+        dcs_gather_pack launch per operand type rebuilds them — no host packing in the step."""
+        from . import train_pack as TP
+        off, o = {}, 0
+        for name, p in self.buckets.order:
+            off[name] = (o, tuple(p.shape))
+            o += p.numel()
+        leaf = lambda name, shape=None: TP.Sym.leaf(off[name][0], shape or off[name][1])   # noqa: E731
+        gp = TP.GatherPack(self.flat_param)
+        tf, Lr = self.mode == "tf32", self.L
+        for i in range(Lr):
+            p = f"encoder.{i}.0."
+            wr, wi = leaf(p + "conv_r.weight"), leaf(p + "conv_i.weight")
+            gp.add_packed_conv(self.enc[i], TP.sym_conv(wr, wi, leaf(p + "conv_r.bias"), leaf(p + "conv_i.bias"), tf32=tf))
+            gp.add_packed_conv(self.enc_dgrad[i], TP.sym_dgrad(wr, wi, transposed=False, tf32=tf))
+            p = f"decoder.{i}." if i == Lr - 1 else f"decoder.{i}.0."
+            wr, wi = leaf(p + "conv_tran_r.weight"), leaf(p + "conv_tran_i.weight")
+            gp.add_packed_conv(self.dec[i], TP.sym_conv(wr, wi, leaf(p + "conv_tran_r.bias"), leaf(p + "conv_tran_i.bias"), transposed=True,
+                                                        up=UPSAMPLE[i], tf32=tf))
+            c0 = wr.shape[0] // 2
+            for pk, sl in zip(self.dec_dgrad[i], (slice(0, c0), slice(c0, None))):
+                gp.add_packed_conv(pk, TP.sym_dgrad(wr[sl], wi[sl], transposed=True, tf32=tf))
+        s4 = off["fc.fc_r.weight"][1] + (1, 1)
+        wr, wi = leaf("fc.fc_r.weight", s4), leaf("fc.fc_i.weight", s4)
+        gp.add_packed_conv(self.fc, TP.sym_conv(wr, wi, leaf("fc.fc_r.bias"), leaf("fc.fc_i.bias"), tf32=tf))
+        gp.add_packed_conv(self.fc_dgrad, TP.sym_dgrad(wr, wi, transposed=False, tf32=tf))
+        names, sfx = ("real_lstm", "imag_lstm"), ("", "_reverse")
+        for l in range(2):
+            for j, n in enumerate(names):
+                gp.add(TP.Sym.cat([leaf(f"lstm.{n}.weight_ih_l{l}{s}") for s in sfx], 0), torch.float32,
+                       lambda t, l=l, j=j: self.lstm_wih[l].__setitem__(j, t))
+                gp.add(TP.Sym.cat([leaf(f"lstm.{n}.bias_ih_l{l}{s}") + leaf(f"lstm.{n}.bias_hh_l{l}{s}") for s in sfx], 0), torch.float32,
+                       lambda t, l=l, j=j: self.lstm_b[l].__setitem__(j, t))
+            gp.add(TP.Sym.stack([TP.Sym.stack([leaf(f"lstm.{n}.weight_hh_l{l}{s}") for s in sfx], 0) for n in names], 0), torch.float32,
+                   lambda t, l=l: self.lstm_whh.__setitem__(l, t))
+        params = dict(self.model.named_parameters())
+        def attention(ca_list, sa_list, prefix, count):
+            for i in range(count):
+                pc, ps = f"{prefix}.{2 * i}.", f"{prefix}.{2 * i + 1}."
+                ca = ca_list[i]
+                for key, name in (("w1_r", "fc.0.conv_r.weight"), ("w1_i", "fc.0.conv_i.weight"), ("w2_r", "fc.2.conv_r.weight"),
+                                  ("w2_i", "fc.2.conv_i.weight")):
+                    ca[key] = params[pc + name].data.view(ca[key].shape)               # views of the live parameters: nothing to re-pack
+                gp.add(TP.Sym.cat([leaf(ps + "conv1.conv_r.weight").reshape(-1), leaf(ps + "conv1.conv_i.weight").reshape(-1)], 0), torch.float32,
+                       lambda t, i=i: sa_list.__setitem__(i, t))
+        attention(self.skip_ca, self.skip_sa, "skip_attention", Lr)
+        attention(self.dec_ca, self.dec_sa, "decoder_attention", Lr - 1)
+        self.gather = gp.finalize()
+        self.gather.run()
 
     def optimizer_step(self, group=None):
         """Gradient exchange (NCCL all-reduce of the flat buckets when torch.distributed is initialised), global-norm clip
@@ -383,7 +463,7 @@ class TrainStep:
                                          float(hp.get("optim_weight_decay", 10e-5)), o["step"], L.ptr(o["sumsq"]),
                                          float(hp.get("gradient_clip_val", 100.0)), 1.0 / world, L.stream_ptr()), "dcs_adam_amsgrad")
         self.steps_done += 1
-        self._packed_key = None          # the packed operands are stale
+        self._stale = True               # the packed operands are rebuilt (on the GPU) by the next forward
         return o["sumsq"]
 
     def step(self, noise_spec, noisy_spec, clean_spec):

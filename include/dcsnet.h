@@ -497,7 +497,8 @@ int dcs_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp
                      float beta1, float beta2, float eps, float weight_decay, int step, const double* grad_sumsq, float max_norm,
                      float grad_scale, void* stream);
 /* dst[i] = sum_j sign4[4i + j] * src[idx4[4i + j]] (idx < 0 = no term), stored as out_dtype: raw parameters -> kernel operand
- * layouts (block matrices, phase pre-sums, role swaps) by an index table built once on the host, one launch per step */
+ * layouts (block matrices, phase pre-sums, role swaps) by an index table built once on the host, one launch per step;
+ * out_dtype: DCS_F32 / DCS_F16 / DCS_BF16, or 3 = fp32 rounded to tf32 (the kind::tf32 operands) */
 int dcs_gather_pack(const float* src, const int32_t* idx4, const int8_t* sign4, void* dst, int64_t n, int out_dtype, void* stream);
 
 /* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */

@@ -178,7 +178,7 @@ def test_train_mode_forward_reproduces_reference_losses_and_running_stats():
     assert math.isfinite(float(b["g_d5"].abs().sum()))
 
 
-def _golden_step(variant="dcs", dropout=(0.0, 0.0)):
+def _golden_step(variant="dcs", dropout=(0.0, 0.0), mode="fp32"):
     import dcsnet_b200 as D  # noqa: F401
     from dcsnet_b200 import config as cfg, c_network, train_engine
     g = load_golden("train_step.pt")
@@ -187,7 +187,7 @@ def _golden_step(variant="dcs", dropout=(0.0, 0.0)):
     net = c_network.C_NETWORK(cfg.config, hp, 0).cuda()
     clean, noise, noisy = O.synthetic_audio(g["B"], 32 * (g["T"] - 1), seed=g["audio_seed"])
     specs = (O.stft(noise).cuda(), O.stft(noisy).cuda(), O.stft(clean).cuda())
-    return g, net, train_engine.TrainStep(net, variant), specs
+    return g, net, train_engine.TrainStep(net, variant, mode=mode), specs
 
 
 def test_whole_backward_reproduces_the_reference_gradients():
@@ -219,6 +219,39 @@ def test_whole_backward_reproduces_the_reference_gradients():
     bad = {k: v for k, v in worst.items() if v > 2e-3}
     assert not bad, sorted(bad.items(), key=lambda kv: -kv[1])[:10]
     assert abs(total ** 0.5 - w["grad_norm"]) <= 1e-3 * w["grad_norm"]
+
+
+def test_tensor_core_training_mode_against_the_fp32_mode():
+    """mode="tf32": forward and data-gradient convolutions on tcgen05 (kind::tf32, fp32 storage and accumulation).  At the fixture's
+    size the losses are within 1e-3 of the reference's.  Gradients, at batch 8 x 512 frames against the fp32 mode: the forward
+    activations agree to ~1e-3 per layer, but the backward of 13 train-mode BatchNorms / attention gates on a random-init network is
+    ill-conditioned (each stage's dx = P dy + Q x + k cancels to a few per cent of its terms), so the 1e-3 operand rounding grows by
+    about one per cent per decoder stage: the whole gradient agrees to < 2 %, cosine > 0.9995, the deepest weight tensors to 10-20 %."""
+    g, net, step, specs = _golden_step(mode="tf32")
+    w = g["dcs"]
+    out = step.forward(*specs)
+    for k in ("noise_loss", "speech_loss", "train_loss"):
+        assert abs(float(out[k]) - w[k]) <= 1e-3 * max(1.0, abs(w[k])), (k, float(out[k]), w[k])
+    clean, noise, noisy = O.synthetic_audio(8, 32 * 511, seed=77)
+    specs = (O.stft(noise).cuda(), O.stft(noisy).cuda(), O.stft(clean).cuda())
+    grads = {}
+    for mode in ("fp32", "tf32"):
+        _, net, step, _ = _golden_step(mode=mode)
+        step.forward(*specs)
+        step.backward()
+        torch.cuda.synchronize()
+        grads[mode] = {k: p.grad.detach().double() for k, p in net.named_parameters() if p.grad is not None}
+    ref, got = grads["fp32"], grads["tf32"]
+    assert set(ref) == set(got)
+    num = sum(float((got[k] - ref[k]).pow(2).sum()) for k in ref) ** 0.5
+    den = sum(float(ref[k].pow(2).sum()) for k in ref) ** 0.5
+    dot = sum(float((got[k] * ref[k]).sum()) for k in ref)
+    cos = dot / den / sum(float(got[k].pow(2).sum()) for k in got) ** 0.5
+    per = {k: float((got[k] - ref[k]).norm() / ref[k].norm().clamp_min(1e-4 * den)) for k in ref}
+    print("tf32 vs fp32 gradients: global", num / den, "cos", cos, "worst", sorted(per.items(), key=lambda kv: -kv[1])[:5])
+    assert num / den <= 2e-2 and cos >= 0.9995, (num / den, cos)
+    big = {k: v for k, v in per.items() if ref[k].numel() >= 1024 and v > 0.2}
+    assert not big, big
 
 
 def test_optimizer_step_matches_torch_adam_amsgrad_with_clip():
