@@ -10,6 +10,8 @@ batch 64 x 4 s, tensor-core mode, per GPU => weak scaling).  Rank 0 prints ONE J
 
 Other BASELINE configurations (not the driver's default line; committed lines under profiles/bench_lines/):
     --variant dc | dr | drs          configs[2]: DC-Net (same net, S = Y (.) M) and the real-valued DR / DRS networks
+    --workload train                 configs[4]: the training step (train-mode forward + losses + whole backward + NCCL gradient
+                                     all-reduce + global-norm clip + Adam-amsgrad), batch 32 per GPU, hand-written kernels only
     --workload longform [--hours 1]  configs[3]: one hour of audio cut into independent 3.998 s windows, the window list
                                      sharded over the ranks (pipeline.shard_range), streamed host -> GPU -> host; a step = the
                                      whole hour, total work fixed => strong scaling
@@ -49,7 +51,10 @@ def parse():
     ap.add_argument("--batch", type=int, default=64, help="utterances per GPU per step")
     ap.add_argument("--frames", type=int, default=2000, help="STFT frames per utterance (2000 = 3.998 s)")
     ap.add_argument("--variant", default="dcs", choices=["dcs", "dc", "dr", "drs"])
-    ap.add_argument("--workload", default="batch", choices=["batch", "longform"])
+    ap.add_argument("--workload", default="batch", choices=["batch", "longform", "train"])
+    ap.add_argument("--train-mode", default="tf32", choices=["tf32", "fp32"],
+                    help="train workload: tf32 = forward / dgrad convolutions on tcgen05 kind::tf32 (fp32 storage); fp32 = CUDA-core parity mode")
+    ap.add_argument("--train-batch", type=int, default=32, help="train workload: utterances per GPU per step (BASELINE configs[4])")
     ap.add_argument("--hours", type=float, default=1.0, help="longform: hours of 16 kHz audio per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-baseline-seconds", type=float, default=15.0)
@@ -180,6 +185,9 @@ def n_windows(args):
 
 def workload_text(args):
     T = args.frames
+    if args.workload == "train":
+        return (f"DCS-Net ({args.variant}) training step: train-mode forward (batch-statistic ComplexBatchNorm2d, dropout 0.1 / 0.2) + calc_loss + whole backward + gradient all-reduce + global-norm clip + Adam-amsgrad, batch {args.train_batch} x "
+                f"{audio_seconds(T):.3f} s per GPU (T={T} frames), random-init weights seed 0 (BASELINE.json configs[4])")
     if args.workload == "longform":
         return (f"{NET_NAME[args.variant]} ({args.variant}) long-form inference: {args.hours:g} h of synthetic 16 kHz audio = "
                 f"{n_windows(args)} independent windows of {audio_seconds(T):.3f} s (T={T} frames; last one zero-padded), window list "
@@ -551,9 +559,176 @@ def measure_roofline(plan, args, B, T, clocks=None):
     return roof, stage_ms
 
 
+def train_metric():
+    return "seconds of 16 kHz audio per second through the DCS-Net training step (fwd + bwd + all-reduce + Adam-amsgrad)"
+
+
+def run_reference_train(args, rank):
+    """Reference arm of the training workload: the oracle's restatement of the reference's training step (train_batch_2_loss +
+    autograd backward, oracle/train_oracle.py — pinned by tests/golden/train_step.pt) + torch.optim.Adam(amsgrad) on the host cores,
+    one utterance per step (a bounded sample)."""
+    if rank != 0:
+        return
+    from oracle import dcsnet_oracle as O, train_oracle as TO
+    import dcsnet_b200  # noqa: F401
+    from dcsnet_b200 import c_network, config as cfg
+    torch.set_num_threads(os.cpu_count() or 1)
+    hp = dict(cfg.hparams)
+    net = c_network.C_NETWORK(cfg.config, hp, 0)
+    params = {k for k, _ in net.named_parameters()}
+    sd = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    clean, noise, noisy = O.synthetic_audio(1, HOP * (args.frames - 1))
+    specs = [O.stft(t) for t in (noise, noisy, clean)]
+    leaves = [sd[k].requires_grad_(True) for k in sorted(params)]
+    opt = torch.optim.Adam(leaves, lr=hp["lr"], eps=hp["optim_eps"], weight_decay=hp["optim_weight_decay"], amsgrad=True)
+
+    def step():
+        r = TO.train_step(sd, *specs, params, "dcs", drop=TO.dropout_torch_stream(hp["dropout_conv"], hp["dropout_fc"]))
+        for k, leaf in zip(sorted(params), leaves):
+            leaf.grad = r["grads"].get(k)
+        torch.nn.utils.clip_grad_norm_([l for l in leaves if l.grad is not None], hp["gradient_clip_val"])
+        opt.step()
+    for _ in range(min(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    val = args.steps * audio_seconds(args.frames) / el
+    sample = f"1 utterance x {audio_seconds(args.frames):.3f} s per step (a bounded sample), fp32, torch CPU autograd + Adam"
+    print(json.dumps({"impl": "reference", "metric": train_metric(), "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                      "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * el / args.steps, "higher_is_better": True, "scaling": "weak",
+                      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": workload_text(args), "reference_arm": "oracle restatement of the reference training step (oracle/train_oracle.py)"},
+                      "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+                      "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+
+
+def run_train(args, rank, local_rank, world):
+    """BASELINE configs[4]: one training step per `step` on every rank (its own synthetic batch), gradients averaged over NCCL."""
+    import torch.distributed as dist
+    import dcsnet_b200 as D
+    from dcsnet_b200 import c_network, config as cfg, ops, train_engine, train_ops as T
+    from oracle import dcsnet_oracle as O  # synthetic audio generator only
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (our arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    B, Tn = args.train_batch, args.frames
+    net = c_network.C_NETWORK(cfg.config, dict(cfg.hparams), 0).cuda().train()
+    step = train_engine.TrainStep(net, args.variant, mode=args.train_mode, seed=rank).init_optimizer()
+    clean, noise, noisy = O.synthetic_audio(B, HOP * (Tn - 1), seed=1234 + rank)
+    dev_specs = [ops.stft(t.cuda()) for t in (noise, noisy, clean)]
+    host_specs = [s.cpu().pin_memory() for s in dev_specs]
+    stage = [torch.empty_like(s) for s in dev_specs]
+    loss_host = torch.empty(1, dtype=torch.float32, pin_memory=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        w0 = time.time()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        w1 = time.time()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, w0, w1
+
+    def step_dev():
+        step.step(*dev_specs)
+
+    def step_e2e():          # the batch the DataLoader hands over (three spectrograms, pinned host) -> GPU, the loss back to the host
+        for d, h in zip(stage, host_specs):
+            d.copy_(h, non_blocking=True)
+        out = step.step(*stage)
+        loss_host.copy_(out["train_loss"].reshape(1), non_blocking=True)
+
+    for _ in range(args.warmup):
+        step_dev()
+    n0 = D._lib.launch_count()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ms_dev, w0, w1 = timed(step_dev, args.steps)
+    launches = (D._lib.launch_count() - n0) // args.steps
+    for _ in range(args.warmup):
+        step_e2e()
+    ms_e2e, _, w1 = timed(step_e2e, args.steps)
+    clocks = sampler.stop(w0, w1) if sampler else None
+    # ---- stage split + the convolution GEMM family (forward, dgrad, wgrad) timed with CUDA events around every call of one eager step
+    fam = {"conv_fwd_dgrad": [], "conv_wgrad": []}
+    roof = None
+    if rank == 0:
+        def wrap(mod, name, key):
+            orig = getattr(mod, name)
+            def inner(*a, **k):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                r = orig(*a, **k)
+                e1.record()
+                fam[key].append((e0, e1))
+                return r
+            setattr(mod, name, inner)
+            return orig
+        o1, o2 = wrap(ops, "cconv", "conv_fwd_dgrad"), wrap(T, "wgrad", "conv_wgrad")
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(); step.forward(*dev_specs); ev[1].record(); step.backward(); ev[2].record(); step.optimizer_step(); ev[3].record()
+        torch.cuda.synchronize()
+        ops.cconv, T.wgrad = o1, o2
+        fam_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in fam.items()}
+        dense = sum(f for f, _ in conv_flops_per_utterance(Tn).values()) * B
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        bf16 = float(peaks.get("bf16_tflops", 1663.0))
+        conv_ms = fam_ms["conv_fwd_dgrad"] + fam_ms["conv_wgrad"]
+        ach = 3 * dense / (conv_ms / 1e3) / 1e12
+        roof = {"bound": "tensor", "kernel": "convolution GEMM family of the step: forward + data-gradient (dcs::cconv_tc_kernel kind::tf32 / cconv_ffma) and "
+                                             "weight-gradient (dcs::wgrad_generic_kernel / wgrad_small_kernel, CUDA-core fp32)",
+                "achieved": ach, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": ach / (bf16 / 2),
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the kind::f16 rate)" if peaks else "fallback 1663 / 2",
+                "flops_per_step": 3 * dense, "flop_basis": "dense formulation, forward + dgrad + wgrad = 3 x forward", "family_ms": fam_ms,
+                "traffic": None,
+                "stage_ms": {"forward": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]), "allreduce_clip_adam": ev[2].elapsed_time(ev[3])}}
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+    audio = world * B * audio_seconds(Tn)
+    h2d = sum(h.numel() * h.element_size() for h in host_specs)
+    line = {"metric": train_metric(), "value": audio / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.train_mode == "tf32" else "f32", "data": "synthetic",
+            "config": {"workload": workload_text(args), "mode": args.train_mode, "global_batch": B * world, "steps_per_s": 1e3 / ms_dev,
+                       "parallelism": f"data-parallel x{world}: local BatchNorm statistics, flat fp32 gradient buckets all-reduced over NCCL, then the fused "
+                                      "clip + Adam-amsgrad kernel on every rank",
+                       "parameters": int(step.flat_param.numel()),
+                       "l2": "activations saved per step (~8 GB at batch 32) exceed the 126 MB L2; no explicit flush"},
+            "e2e": {"value": audio / (ms_e2e / 1e3), "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "mode": "TrainStep.step on a pinned-host batch of three spectrograms (what the reference's DataLoader yields): H2D, step, loss back"},
+            "gpu_launches": launches * args.steps, "kernels_per_step": launches, "clocks": clocks, "roofline": roof}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def main():
     args = parse()
     rank, local_rank, world = dist_env()
+    if args.workload == "train":
+        if args.impl == "reference":
+            run_reference_train(args, rank)
+        else:
+            run_train(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
     else:
