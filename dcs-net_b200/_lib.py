@@ -74,6 +74,13 @@ class WgradParams(C.Structure):
                 ("dx_off", C.c_int8 * MAX_TAPS), ("dwp", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
 
 
+class Wgrad16Params(C.Structure):
+    _fields_ = [("x", _vp), ("dy", _vp), ("dtype", _i),
+                ("batch", _i), ("in_h", _i), ("in_w", _i), ("out_h", _i), ("out_w", _i), ("k2", _i), ("n2", _i), ("x_pitch", _i),
+                ("dy_pitch", _i), ("stride_h", _i), ("stride_w", _i), ("ntaps", _i), ("dy_off", C.c_int8 * MAX_TAPS),
+                ("dx_off", C.c_int8 * MAX_TAPS), ("dwp", _vp), ("dwp_tap_stride", _i64), ("workspace", _vp), ("workspace_bytes", _i64)]
+
+
 class AttentionBwdParams(C.Structure):
     _fields_ = [("x", _vp), ("dy", _vp), ("gate_c", _vp), ("stats", _vp), ("gate_s", _vp), ("w7", _vp), ("sums", _vp),
                 ("batch", _i), ("h", _i), ("w", _i), ("channels", _i), ("reduced", _i),
@@ -209,7 +216,10 @@ SYMBOLS = {
     "dcs_colsum_workspace_bytes": (_i64, [_i64, _i]),
     "dcs_colsum": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "dcs_dilate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "dcs_upcat_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_cconv_dgrad_cin1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_upcat_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_wgrad_tc16_workspace_bytes": (_i64, [C.POINTER(Wgrad16Params)]),
+    "dcs_wgrad_tc16": (_i, [C.POINTER(Wgrad16Params), _vp]),
     "dcs_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     "dcs_dropout": (_i, [_vp, _vp, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "dcs_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),

@@ -49,13 +49,26 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ partial, in
                                           const float* __restrict__ weight, const float* __restrict__ bias, float* __restrict__ affine,
                                           float* __restrict__ running_mean, float* __restrict__ running_covar,
                                           long long* __restrict__ num_batches_tracked, float* __restrict__ saved) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c == 0 && num_batches_tracked) *num_batches_tracked += 1;
-  if (c >= C) return;
+  // one CTA (64 threads) per channel: the chunk partials are summed in a strided fixed order + a fixed tree, thread 0 finishes
+  __shared__ double red[64][5];
+  const int c = blockIdx.x;
+  if (c == 0 && threadIdx.x == 0 && num_batches_tracked) *num_batches_tracked += 1;
   double s[5] = {0, 0, 0, 0, 0};
-  for (int k = 0; k < n_chunks; ++k)
+  for (int k = threadIdx.x; k < n_chunks; k += 64)
 #pragma unroll
     for (int j = 0; j < 5; ++j) s[j] += partial[((int64_t)k * C + c) * 5 + j];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  for (int o = 32; o; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int j = 0; j < 5; ++j) red[threadIdx.x][j] += red[threadIdx.x + o][j];
+    __syncthreads();
+  }
+  if (threadIdx.x) return;
+#pragma unroll
+  for (int j = 0; j < 5; ++j) s[j] = red[0][j];
   const double mr = s[0] / n, mi = s[1] / n;
   const double Crr = s[2] / n - mr * mr + (double)eps, Cii = s[3] / n - mi * mi + (double)eps, Cri = s[4] / n - mr * mi;
   const double sd = sqrt(Crr * Cii - Cri * Cri), t = sqrt(Crr + Cii + 2 * sd), ist = 1.0 / (sd * t);
@@ -123,12 +136,24 @@ __global__ void __launch_bounds__(kTrThreads) cbn_bwd_sums_kernel(const float* _
 __global__ void cbn_bwd_finalize_kernel(const double* __restrict__ partial, int n_chunks, int C, double n, const float* __restrict__ saved,
                                         const float* __restrict__ weight, float* __restrict__ dweight, float* __restrict__ dbias,
                                         float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
+  __shared__ double red[64][8];
+  const int c = blockIdx.x;
   double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  for (int k = 0; k < n_chunks; ++k)
+  for (int k = threadIdx.x; k < n_chunks; k += 64)
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] += partial[((int64_t)k * C + c) * 8 + j];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[threadIdx.x][j] = s[j];
+  __syncthreads();
+  for (int o = 32; o; o >>= 1) {
+    if (threadIdx.x < o)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) red[threadIdx.x][j] += red[threadIdx.x + o][j];
+    __syncthreads();
+  }
+  if (threadIdx.x) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] = red[0][j];
   const float* sv = saved + 8 * c;
   const double mr = sv[0], mi = sv[1], Rrr = sv[2], Rii = sv[3], Rri = sv[4], A = sv[5], B = sv[6], Cc = sv[7];
   const double w0 = weight[3 * c], w1 = weight[3 * c + 1], w2 = weight[3 * c + 2];
@@ -307,7 +332,7 @@ extern "C" int dcs_cbn_train_fwd(const dcs_cbn_train_params* p, void* stream) {
   else if (p->in_dtype == DCS_F16) cbn_moments_kernel<__half><<<nc, kTrThreads, 0, s>>>((const __half*)p->x, partial, p->n_pix, p->channels, ppc);
   else cbn_moments_kernel<__nv_bfloat16><<<nc, kTrThreads, 0, s>>>((const __nv_bfloat16*)p->x, partial, p->n_pix, p->channels, ppc);
   DCS_LAUNCHED();
-  cbn_train_finalize_kernel<<<(p->channels + 63) / 64, 64, 0, s>>>(partial, nc, p->channels, (double)p->n_pix, p->eps, p->momentum, p->weight, p->bias,
+  cbn_train_finalize_kernel<<<p->channels, 64, 0, s>>>(partial, nc, p->channels, (double)p->n_pix, p->eps, p->momentum, p->weight, p->bias,
                                                                     p->affine, p->running_mean, p->running_covar,
                                                                     reinterpret_cast<long long*>(p->num_batches_tracked), p->saved);
   DCS_LAUNCHED();
@@ -328,7 +353,7 @@ extern "C" int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream
   cudaStream_t s = (cudaStream_t)stream;
   cbn_bwd_sums_kernel<<<nc, kTrThreads, 0, s>>>(p->x, p->dy, p->saved, p->weight, partial, p->n_pix, p->channels, ppc);
   DCS_LAUNCHED();
-  cbn_bwd_finalize_kernel<<<(p->channels + 63) / 64, 64, 0, s>>>(partial, nc, p->channels, (double)p->n_pix, p->saved, p->weight, p->dweight, p->dbias, coef);
+  cbn_bwd_finalize_kernel<<<p->channels, 64, 0, s>>>(partial, nc, p->channels, (double)p->n_pix, p->saved, p->weight, p->dweight, p->dbias, coef);
   DCS_LAUNCHED();
   const int64_t n = p->n_pix * p->channels;
   const int g = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);

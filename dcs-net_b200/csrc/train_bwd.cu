@@ -322,19 +322,25 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ x
 }
 // mode 0: out0[c] = S[c] (and out1[c] = S[c] when out1 != NULL);  mode 1 (complex conv bias, columns (co, re/im)):
 // out0[co] = S[2co] + S[2co+1] (conv_r.bias.grad), out1[co] = S[2co+1] - S[2co] (conv_i.bias.grad)
-__global__ void colsum_finalize_kernel(const double* __restrict__ partial, int n_chunks, int cols, int mode, float* __restrict__ out0,
-                                       float* __restrict__ out1) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) colsum_finalize_kernel(const double* __restrict__ partial, int n_chunks, int cols, int mode, float* __restrict__ out0,
+                                                              float* __restrict__ out1) {
+  // one warp per output: lanes stride over the chunks (fixed order), xor-tree
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int n_out = mode == 0 ? cols : cols / 2;
+  if (i >= n_out) return;
+  double sr = 0.0, si = 0.0;
   if (mode == 0) {
-    if (i >= cols) return;
-    double s = 0.0;
-    for (int k = 0; k < n_chunks; ++k) s += partial[(int64_t)k * cols + i];
-    out0[i] = (float)s;
-    if (out1) out1[i] = (float)s;
+    for (int k = lane; k < n_chunks; k += 32) sr += partial[(int64_t)k * cols + i];
   } else {
-    if (i >= cols / 2) return;
-    double sr = 0.0, si = 0.0;
-    for (int k = 0; k < n_chunks; ++k) { sr += partial[(int64_t)k * cols + 2 * i]; si += partial[(int64_t)k * cols + 2 * i + 1]; }
+    for (int k = lane; k < n_chunks; k += 32) { sr += partial[(int64_t)k * cols + 2 * i]; si += partial[(int64_t)k * cols + 2 * i + 1]; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+  if (lane) return;
+  if (mode == 0) {
+    out0[i] = (float)sr;
+    if (out1) out1[i] = (float)sr;
+  } else {
     out0[i] = (float)(sr + si);
     out1[i] = (float)(si - sr);
   }
@@ -359,7 +365,8 @@ __global__ void dilate_kernel(const float2* __restrict__ dy, float2* __restrict_
 }
 
 // z (B, h*uh, w*uw, c0 + c1) = nearest up-sampling of cat(d, skip) (the decoder convs' input, materialised for the wgrad)
-__global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, float2* __restrict__ z, int B, int H, int W,
+template <typename TO>
+__global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, TO* __restrict__ z, int B, int H, int W,
                                  int c0, int c1, int uh, int uw) {
   const int C = c0 + c1, HH = H * uh, WW = W * uw;
   const int64_t n = (int64_t)B * HH * WW * C;
@@ -370,7 +377,7 @@ __global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __r
     const int y = (int)(r % HH);
     const int b = (int)(r / HH);
     const int64_t pix = ((int64_t)b * H + y / uh) * W + x / uw;
-    z[i] = c < c0 ? d[pix * c0 + c] : skip[pix * c1 + (c - c0)];
+    Elem<TO>::stc(z, i, c < c0 ? d[pix * c0 + c] : skip[pix * c1 + (c - c0)]);
   }
 }
 
@@ -417,6 +424,43 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
       const int64_t j = 4 * i + e;
       if (j < n) y[j] = rr[e] >= thr ? x[j] * scale : 0.f;
     }
+  }
+}
+
+// data gradient of a ComplexConv2d with ONE input channel (encoder[0]: 1 -> 8, k7, stride (2,2)) straight from the raw weights:
+// dx(b, ih, iw) = sum over the taps that hit this pixel's stride phase, sum_co [w_r dy.re + w_i dy.im, -w_i dy.re + w_r dy.im].
+// (The zero-insertion + forward-kernel route computes 4x the taps and pads N = 2 to 16: 11 ms at batch 32 x 4 s against < 1 ms.)
+__global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __restrict__ dy, const float* __restrict__ w_r, const float* __restrict__ w_i,
+                                                               float2* __restrict__ dx, int B, int in_h, int in_w, int out_h, int out_w, int cout,
+                                                               int kh, int kw, int sh, int sw) {
+  extern __shared__ float2 wsm[];            // [tap][co] = (w_r, w_i)
+  const int ntaps = kh * kw;
+  for (int i = threadIdx.x; i < ntaps * cout; i += 256) {
+    const int t = i / cout, co = i % cout;
+    wsm[i] = make_float2(w_r[co * ntaps + t], w_i[co * ntaps + t]);
+  }
+  __syncthreads();
+  const int ph = kh / 2, pw = kw / 2;
+  const int64_t n = (int64_t)B * in_h * in_w;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int iw = (int)(i % in_w), ih = (int)((i / in_w) % in_h), b = (int)(i / ((int64_t)in_w * in_h));
+    float ar = 0.f, ai = 0.f;
+    for (int ky = (ih + ph) % sh; ky < kh; ky += sh) {
+      const int oh = (ih + ph - ky) / sh;
+      if (ih + ph - ky < 0 || oh >= out_h) continue;
+      for (int kx = (iw + pw) % sw; kx < kw; kx += sw) {
+        const int ow = (iw + pw - kx) / sw;
+        if (iw + pw - kx < 0 || ow >= out_w) continue;
+        const float2* g = dy + (((int64_t)b * out_h + oh) * out_w + ow) * cout;
+        const float2* w = wsm + (ky * kw + kx) * cout;
+        for (int co = 0; co < cout; ++co) {
+          const float2 gv = g[co], wv = w[co];
+          ar += wv.x * gv.x + wv.y * gv.y;
+          ai += wv.x * gv.y - wv.y * gv.x;
+        }
+      }
+    }
+    dx[i] = make_float2(ar, ai);
   }
 }
 
@@ -485,14 +529,24 @@ __global__ void __launch_bounds__(256) att_bwd_w7_kernel(const float4* __restric
     partial[(int64_t)tile * 196 + threadIdx.x] = (double)s;
   }
 }
-// out layout = the reference's (1,2,7,7) tensors: dw7_r[ch*49 + tap], dw7_i[ch*49 + tap]
-__global__ void att_bwd_w7_finalize_kernel(const double* __restrict__ partial, int n_tiles, float* __restrict__ dw7_r, float* __restrict__ dw7_i) {
-  const int i = threadIdx.x;
-  if (i >= 196) return;
+// out layout = the reference's (1,2,7,7) tensors: dw7_r[ch*49 + tap], dw7_i[ch*49 + tap].  One CTA per output element: the tiles'
+// partials are summed by 256 threads in a strided (fixed) order, then a fixed-shape tree.
+__global__ void __launch_bounds__(256) att_bwd_w7_finalize_kernel(const double* __restrict__ partial, int n_tiles, float* __restrict__ dw7_r,
+                                                                  float* __restrict__ dw7_i) {
+  __shared__ double red[256];
+  const int i = blockIdx.x;
   double s = 0.0;
-  for (int t = 0; t < n_tiles; ++t) s += partial[(int64_t)t * 196 + i];
-  const int tap = i % 49, ch = (i / 49) & 1, which = i / 98;
-  (which ? dw7_i : dw7_r)[ch * 49 + tap] = (float)s;
+  for (int t = threadIdx.x; t < n_tiles; t += 256) s += partial[(int64_t)t * 196 + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const int tap = i % 49, ch = (i / 49) & 1, which = i / 98;
+    (which ? dw7_i : dw7_r)[ch * 49 + tap] = (float)red[0];
+  }
 }
 
 // pass 2: dstats = conv7^T(dspre); du = conj(s) dy + dmean / C + [argmax] dmax; dx = conj(a) du; da partial sums per CTA
@@ -997,7 +1051,7 @@ extern "C" int dcs_colsum(const float* x, int64_t rows, int cols, int pitch, int
   cudaStream_t s = (cudaStream_t)stream;
   colsum_kernel<<<nc, 256, 0, s>>>(x, rows, cols, pitch, rpc, reinterpret_cast<double*>(workspace));
   DCS_LAUNCHED();
-  colsum_finalize_kernel<<<(cols + 127) / 128, 128, 0, s>>>(reinterpret_cast<const double*>(workspace), nc, cols, mode, out0, out1);
+  colsum_finalize_kernel<<<(cols + 7) / 8, 256, 0, s>>>(reinterpret_cast<const double*>(workspace), nc, cols, mode, out0, out1);
   DCS_LAUNCHED();
   return 0;
 }
@@ -1012,10 +1066,25 @@ extern "C" int dcs_dilate(const float* dy, float* out, int batch, int out_h, int
   return 0;
 }
 
-extern "C" int dcs_upcat_fwd(const float* d, const float* skip, float* z, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream) {
-  DCS_REQUIRE(d && z && (skip || c1 == 0) && batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 >= 0 && up_h >= 1 && up_w >= 1, "dcs_upcat_fwd: bad arguments");
+extern "C" int dcs_cconv_dgrad_cin1(const float* dy, const float* w_r, const float* w_i, float* dx, int batch, int in_h, int in_w, int out_h, int out_w,
+                                    int cout, int kh, int kw, int stride_h, int stride_w, void* stream) {
+  DCS_REQUIRE(dy && w_r && w_i && dx && batch > 0 && in_h > 0 && in_w > 0 && out_h > 0 && out_w > 0 && cout > 0 && kh > 0 && kw > 0 && (kh & 1) && (kw & 1) &&
+              stride_h > 0 && stride_w > 0 && kh * kw * cout <= 4096, "dcs_cconv_dgrad_cin1: bad arguments");
+  const int64_t n = (int64_t)batch * in_h * in_w;
+  cconv_dgrad_cin1_kernel<<<ew_grid(n), 256, (size_t)kh * kw * cout * sizeof(float2), (cudaStream_t)stream>>>(
+      (const float2*)dy, w_r, w_i, (float2*)dx, batch, in_h, in_w, out_h, out_w, cout, kh, kw, stride_h, stride_w);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream) {
+  DCS_REQUIRE(d && z && (skip || c1 == 0) && batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 >= 0 && up_h >= 1 && up_w >= 1 && is_dtype(out_dtype),
+              "dcs_upcat_fwd: bad arguments");
   const int64_t n = (int64_t)batch * h * up_h * w * up_w * (c0 + c1);
-  upcat_fwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)d, (const float2*)skip, (float2*)z, batch, h, w, c0, c1, up_h, up_w);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (out_dtype == DCS_F32) upcat_fwd_kernel<float><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (float*)z, batch, h, w, c0, c1, up_h, up_w);
+  else if (out_dtype == DCS_F16) upcat_fwd_kernel<__half><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__half*)z, batch, h, w, c0, c1, up_h, up_w);
+  else upcat_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__nv_bfloat16*)z, batch, h, w, c0, c1, up_h, up_w);
   DCS_LAUNCHED();
   return 0;
 }
@@ -1067,7 +1136,7 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   DCS_LAUNCHED();
   att_bwd_w7_kernel<<<n_tiles, 256, 0, s>>>((const float4*)p->stats, (const float2*)p->dspre, p->h, p->w, tiles_x, tiles_y, w7_partial);
   DCS_LAUNCHED();
-  att_bwd_w7_finalize_kernel<<<1, 256, 0, s>>>(w7_partial, n_tiles, p->dw7_r, p->dw7_i);
+  att_bwd_w7_finalize_kernel<<<196, 256, 0, s>>>(w7_partial, n_tiles, p->dw7_r, p->dw7_i);
   DCS_LAUNCHED();
   att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (const float2*)p->dspre, p->w7, (float2*)p->dx, da_partial, p->h, p->w, C, G);
   DCS_LAUNCHED();

@@ -174,6 +174,19 @@ __global__ void wgrad_fold_kernel(const float* __restrict__ partial, int ksplits
   }
 }
 
+// K-split reduction in a fixed order into the generic layout of dcs_wgrad: dwp[tap][k][n] = sum_pixels x[k] dy[n]  (partial rows = dy
+// channel n, columns = x channel k, padded to Mp x Np)
+__global__ void wgrad_reduce_generic_kernel(const float* __restrict__ partial, int ksplits, int n_taps, int Mp, int Np, int k2, int n2,
+                                            float* __restrict__ dwp, int64_t tap_stride) {
+  const int n_elem = n_taps * k2 * n2;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < n_elem; e += gridDim.x * blockDim.x) {
+    const int n = e % n2, k = (e / n2) % k2, tap = e / (n2 * k2);
+    float s = 0.f;
+    for (int z = 0; z < ksplits; ++z) s += partial[(((int64_t)z * n_taps + tap) * Mp + n) * Np + k];
+    dwp[(int64_t)tap * tap_stride + (int64_t)k * n2 + n] = s;
+  }
+}
+
 typedef CUresult (*WgEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static WgEncodeFn wg_encode_fn() {
@@ -185,11 +198,12 @@ static WgEncodeFn wg_encode_fn() {
   }
   return fn;
 }
-static int wg_map(CUtensorMap* m, const void* ptr, int f16, int C2, int W, int H, int B, int stride_w) {
+static int wg_map(CUtensorMap* m, const void* ptr, int f16, int C2, int W, int H, int B, int stride_w, int pitch = 0) {
   WgEncodeFn fn = wg_encode_fn();
   DCS_REQUIRE(fn, "cuTensorMapEncodeTiled is unavailable (driver too old?)");
+  if (pitch <= 0) pitch = C2;                 // channels per pixel in memory (>= C2 when the operand is a channel slice)
   cuuint64_t dims[4] = {(cuuint64_t)C2, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C2 * 2, (cuuint64_t)W * C2 * 2, (cuuint64_t)H * W * C2 * 2};
+  cuuint64_t strides[3] = {(cuuint64_t)pitch * 2, (cuuint64_t)W * pitch * 2, (cuuint64_t)H * W * pitch * 2};
   cuuint32_t box[4] = {64, (cuuint32_t)(kWgPix * stride_w), 1, 1};
   cuuint32_t es[4] = {1, (cuuint32_t)stride_w, 1, 1};
   CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, es,
@@ -201,7 +215,7 @@ static int wg_map(CUtensorMap* m, const void* ptr, int f16, int C2, int W, int H
 static int wg_split(const dcs_cwgrad_params* p, int* ksplits, int* steps_total, int* per) {
   const int wblocks = (p->out_w + kWgPix - 1) / kWgPix;
   *steps_total = p->batch * p->out_h * wblocks;
-  const int units = p->ntaps * ((2 * p->cout) / 128);
+  const int units = p->ntaps * ((2 * p->cout + 127) / 128);
   int ks = std::max(1, (2 * num_sms() + units - 1) / units);
   ks = std::min(ks, std::max(1, *steps_total / 4));
   *per = (*steps_total + ks - 1) / ks;
@@ -249,6 +263,57 @@ extern "C" int dcs_cwgrad_tc(const dcs_cwgrad_params* p, void* stream) {
   DCS_LAUNCHED();
   const int n_elem = p->cout * p->cin * p->ntaps;
   wgrad_fold_kernel<<<std::min((n_elem + 255) / 256, 4 * num_sms()), 256, 0, s>>>(a.partial, a.ksplits, a.n_taps, p->cout, p->cin, p->dw_r, p->dw_i);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+// ---- the same GEMM behind dcs_wgrad's interface (real channel counts, channel-slice pitches, any k2 <= 256 / n2: operand boxes beyond
+//      the real channels are zero-filled by TMA, so M = n2 is padded to 128-row tiles and N = k2 to 64-column boxes)
+static void wg16_shape(const dcs_wgrad16_params* p, dcs_cwgrad_params* q) {
+  memset(q, 0, sizeof(*q));
+  q->batch = p->batch; q->in_h = p->in_h; q->in_w = p->in_w; q->out_h = p->out_h; q->out_w = p->out_w;
+  q->cin = (p->k2 + 1) / 2; q->cout = (p->n2 + 1) / 2; q->stride_h = p->stride_h; q->stride_w = p->stride_w; q->ntaps = p->ntaps;
+}
+extern "C" int64_t dcs_wgrad_tc16_workspace_bytes(const dcs_wgrad16_params* p) {
+  if (!p || p->batch <= 0 || p->k2 <= 0 || p->n2 <= 0 || p->ntaps <= 0) return -1;
+  dcs_cwgrad_params q;
+  wg16_shape(p, &q);
+  int ks, st, per;
+  wg_split(&q, &ks, &st, &per);
+  const int Mp = (p->n2 + 127) / 128 * 128, Np = (p->k2 + 63) / 64 * 64;
+  return (int64_t)ks * p->ntaps * Mp * Np * (int64_t)sizeof(float);
+}
+extern "C" int dcs_wgrad_tc16(const dcs_wgrad16_params* p, void* stream) {
+  DCS_REQUIRE(p && p->x && p->dy && p->dwp && p->workspace, "dcs_wgrad_tc16: null pointer");
+  DCS_REQUIRE(is_h16(p->dtype), "dcs_wgrad_tc16: x / dy must be DCS_F16 or DCS_BF16 storage");
+  DCS_REQUIRE(p->batch > 0 && p->in_h > 0 && p->in_w > 0 && p->out_h > 0 && p->out_w > 0 && p->k2 > 0 && p->k2 <= 256 && p->n2 > 0, "dcs_wgrad_tc16: bad shape (k2 <= 256)");
+  DCS_REQUIRE(p->x_pitch >= p->k2 && p->dy_pitch >= p->n2 && p->x_pitch % 8 == 0 && p->dy_pitch % 8 == 0, "dcs_wgrad_tc16: pitches must be multiples of 8 elements");
+  DCS_REQUIRE(p->ntaps >= 1 && p->ntaps <= DCS_MAX_TAPS && (p->stride_w == 1 || p->stride_w == 2) && p->stride_h >= 1, "dcs_wgrad_tc16: bad taps / stride");
+  DCS_REQUIRE(((uintptr_t)p->x % 16 == 0) && ((uintptr_t)p->dy % 16 == 0), "dcs_wgrad_tc16: pointers must be 16-byte aligned");
+  DCS_REQUIRE(p->workspace_bytes >= dcs_wgrad_tc16_workspace_bytes(p), "dcs_wgrad_tc16: workspace too small");
+  dcs_cwgrad_params q;
+  wg16_shape(p, &q);
+  WgArgs a;
+  memset(&a, 0, sizeof(a));
+  a.n_taps = p->ntaps; a.m_tiles = (p->n2 + 127) / 128;
+  wg_split(&q, &a.ksplits, &a.steps_total, &a.steps_per_split);
+  a.OH = p->out_h; a.OW = p->out_w; a.wblocks = (p->out_w + kWgPix - 1) / kWgPix;
+  a.sh = p->stride_h; a.sw = p->stride_w; a.nb = (p->k2 + 63) / 64; a.N = a.nb * 64;
+  a.f16 = p->dtype == DCS_F16 ? 1 : 0;
+  memcpy(a.dy, p->dy_off, sizeof(a.dy));
+  memcpy(a.dx, p->dx_off, sizeof(a.dx));
+  a.partial = reinterpret_cast<float*>(p->workspace);
+  CUtensorMap tmY, tmX;
+  if (int e = wg_map(&tmY, p->dy, a.f16, p->n2, p->out_w, p->out_h, p->batch, 1, p->dy_pitch)) return e;
+  if (int e = wg_map(&tmX, p->x, a.f16, p->k2, p->in_w, p->in_h, p->batch, p->stride_w, p->x_pitch)) return e;
+  const size_t smem = 1024 + (size_t)kWgStages * (2 + a.nb) * kWgBoxBytes + sizeof(WgBars);
+  DCS_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaStream_t s = (cudaStream_t)stream;
+  wgrad_tc_kernel<<<a.ksplits * a.n_taps * a.m_tiles, kWgThreads, smem, s>>>(tmY, tmX, a);
+  DCS_LAUNCHED();
+  const int n_elem = p->ntaps * p->k2 * p->n2;
+  wgrad_reduce_generic_kernel<<<std::min((n_elem + 255) / 256, 8 * num_sms()), 256, 0, s>>>(a.partial, a.ksplits, a.n_taps, a.m_tiles * 128, a.N, p->k2, p->n2,
+                                                                                            p->dwp, p->dwp_tap_stride > 0 ? p->dwp_tap_stride : (int64_t)p->k2 * p->n2);
   DCS_LAUNCHED();
   return 0;
 }

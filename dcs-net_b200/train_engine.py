@@ -260,8 +260,18 @@ class TrainStep:
         self._grad(prefix + ".bias").copy_(db)
         return dx
 
+    def _wgrad_on_tc(self, cin, cout):
+        """tf32 mode: weight gradients of every layer with >= 8 complex channels on both sides run on tcgen05 (dcs_wgrad_tc16) from bf16
+        copies of the two operands (fp32 accumulation over the pixels); encoder[0] / decoder[6] stay on the few-channel CUDA-core kernel."""
+        return self.mode == "tf32" and cin >= 8 and cout >= 8
+
     def _conv_param_grads(self, x, dpre, prefix, names, kernel, stride, transposed):
-        T.cwgrad_generic(x, dpre, kernel, stride, transposed=transposed, dw_r=self._grad(prefix + names[0] + ".weight"),
+        if self._wgrad_on_tc(x.shape[3], dpre.shape[3]):
+            x = x if x.dtype == torch.bfloat16 else T.to_h16(x)
+            dy16 = T.to_h16(dpre)
+        else:
+            dy16 = dpre
+        T.cwgrad_generic(x, dy16, kernel, stride, transposed=transposed, dw_r=self._grad(prefix + names[0] + ".weight"),
                          dw_i=self._grad(prefix + names[1] + ".weight"))
         T.colsum(dpre.view(-1, 2 * dpre.shape[-2]), mode=1, out0=self._grad(prefix + names[0] + ".bias"), out1=self._grad(prefix + names[1] + ".bias"))
 
@@ -330,7 +340,8 @@ class TrainStep:
                 dz = T.act_bwd(att["x"], dxa, L.ACT_LRELU, None, cc)
                 dpre, prefix = self._bn_bwd(sv[f"dec{i}_pre"], dz, f"decoder.{i}.1", f"dec{i}"), f"decoder.{i}.0."
             d_in, skip = sv["dec_in"][i], sv["skip"][i]
-            z = T.upcat_fwd(d_in, skip, UPSAMPLE[i])
+            on_tc = self._wgrad_on_tc(d_in.shape[3] + skip.shape[3], dpre.shape[3])
+            z = T.upcat_fwd(d_in, skip, UPSAMPLE[i], dtype=torch.bfloat16 if on_tc else torch.float32)
             self._conv_param_grads(z, dpre, prefix, ("conv_tran_r", "conv_tran_i"), 3, (1, 1), True)
             del z
             g, g_skip = self._dec_dgrad(i, dpre, d_in.shape[3], skip.shape[3])
@@ -362,7 +373,11 @@ class TrainStep:
             x_in = enc[i]
             self._conv_param_grads(x_in, dpre, f"encoder.{i}.0.", ("conv_r", "conv_i"), KERNEL_E[i], STRIDE_E[i], False)
             Hi, Wi = x_in.shape[1], x_in.shape[2]
-            g = self._conv(self.enc_dgrad[i], T.dilate(dpre, Hi, Wi, STRIDE_E[i]), None, new(B, Hi, Wi, x_in.shape[3], 2))
+            if x_in.shape[3] == 1:       # encoder[0]: one input channel -> the direct gather kernel on the raw weights
+                g = T.cconv_dgrad_cin1(dpre, self._params[f"encoder.{i}.0.conv_r.weight"].detach(), self._params[f"encoder.{i}.0.conv_i.weight"].detach(),
+                                       Hi, Wi, STRIDE_E[i])
+            else:
+                g = self._conv(self.enc_dgrad[i], T.dilate(dpre, Hi, Wi, STRIDE_E[i]), None, new(B, Hi, Wi, x_in.shape[3], 2))
         self._bn_bwd(sv["x0"].contiguous(), g, "initial_batchnorm", "bn0")
         return info
 

@@ -207,7 +207,8 @@ def cwgrad_generic(x, dy, kernel, stride=(1, 1), transposed=False, dw_r=None, dw
     kh, kw = (kernel, kernel) if isinstance(kernel, int) else kernel
     B, H, W, cin, _ = x.shape
     cout = dy.shape[3]
-    dwp = wgrad(x.view(B, H, W, 2 * cin), dy.view(B, dy.shape[1], dy.shape[2], 2 * cout), conv_taps(kh, kw), stride)
+    fn = wgrad_tc16 if x.dtype in ops.H16 else wgrad
+    dwp = fn(x.view(B, H, W, 2 * cin), dy.view(B, dy.shape[1], dy.shape[2], 2 * cout), conv_taps(kh, kw), stride)
     shape = (cin, cout, kh, kw) if transposed else (cout, cin, kh, kw)
     dw_r = dw_r if dw_r is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
     dw_i = dw_i if dw_i is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
@@ -275,12 +276,12 @@ def dilate(dy, in_h, in_w, stride):
 
 
 @ops._on_tensor_device
-def upcat_fwd(d, skip, up):
+def upcat_fwd(d, skip, up, dtype=torch.float32):
     B, H, W, c0, _ = d.shape
     c1 = skip.shape[3] if skip is not None else 0
     assert d.dtype == torch.float32 and d.is_contiguous() and (skip is None or (skip.is_contiguous() and skip.dtype == torch.float32))
-    z = torch.empty(B, H * up[0], W * up[1], c0 + c1, 2, dtype=torch.float32, device=d.device)
-    L.check(L.lib().dcs_upcat_fwd(L.ptr(d), L.ptr(skip), L.ptr(z), B, H, W, c0, c1, up[0], up[1], L.stream_ptr()), "dcs_upcat_fwd")
+    z = torch.empty(B, H * up[0], W * up[1], c0 + c1, 2, dtype=dtype, device=d.device)
+    L.check(L.lib().dcs_upcat_fwd(L.ptr(d), L.ptr(skip), L.ptr(z), L.dtype_code(z), B, H, W, c0, c1, up[0], up[1], L.stream_ptr()), "dcs_upcat_fwd")
     return z
 
 
@@ -396,3 +397,49 @@ def attention_fwd_saved(x, ca, w7):
     ops.spat_stats(x, None, stats, sums=sums, ca=ca, gate_out=gate)
     ops.spat_apply(x, gate, stats, w7, y, gate_out=gate_s)
     return y, dict(x=x, sums=sums, gate_c=gate, stats=stats, gate_s=gate_s)
+
+
+@ops._on_tensor_device
+def cconv_dgrad_cin1(dy, w_r, w_i, in_h, in_w, stride):
+    """Data gradient of ComplexConv2d(1 -> cout, k, stride, p = k // 2) from the raw weights (cout, 1, kh, kw): dy (B, OH, OW, cout, 2)
+    -> dx (B, in_h, in_w, 1, 2)."""
+    B, OH, OW, cout, _ = dy.shape
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and w_r.is_contiguous() and w_i.is_contiguous() and w_r.shape[1] == 1
+    kh, kw = w_r.shape[2], w_r.shape[3]
+    dx = torch.empty(B, in_h, in_w, 1, 2, dtype=torch.float32, device=dy.device)
+    L.check(L.lib().dcs_cconv_dgrad_cin1(L.ptr(dy), L.ptr(w_r), L.ptr(w_i), L.ptr(dx), B, in_h, in_w, OH, OW, cout, kh, kw, stride[0], stride[1],
+                                         L.stream_ptr()), "dcs_cconv_dgrad_cin1")
+    return dx
+
+
+@ops._on_tensor_device
+def wgrad_tc16(x, dy, taps, stride=(1, 1), out=None):
+    """dcs_wgrad on the tensor cores: x (B, in_h, in_w, K2) and dy (B, out_h, out_w, n2) REAL-channel views in fp16 / bf16 storage ->
+    dwp (ntaps, K2, n2) fp32.  Inputs wider than 256 real channels run as channel slices of <= 256 (x_pitch / dwp_tap_stride)."""
+    L.require_cuda(x, dy)
+    assert x.dtype in ops.H16 and dy.dtype == x.dtype and x.is_contiguous() and dy.is_contiguous()
+    B, in_h, in_w, K2 = x.shape
+    _, out_h, out_w, n2 = dy.shape
+    dwp = out if out is not None else torch.empty(len(taps), K2, n2, dtype=torch.float32, device=x.device)
+    esz = x.element_size()
+    for k0 in range(0, K2, 256):
+        k2 = min(256, K2 - k0)
+        p = L.Wgrad16Params()
+        p.x, p.dy, p.dtype = C.c_void_p(x.data_ptr() + k0 * esz), L.ptr(dy), L.dtype_code(x)
+        p.batch, p.in_h, p.in_w, p.out_h, p.out_w, p.k2, p.n2, p.x_pitch, p.dy_pitch = B, in_h, in_w, out_h, out_w, k2, n2, K2, n2
+        p.stride_h, p.stride_w = stride
+        p.ntaps = len(taps)
+        for t, (a, b) in enumerate(taps):
+            p.dy_off[t], p.dx_off[t] = a, b
+        ws = _ws(L.lib().dcs_wgrad_tc16_workspace_bytes(C.byref(p)), x.device)
+        p.dwp, p.dwp_tap_stride, p.workspace, p.workspace_bytes = C.c_void_p(dwp.data_ptr() + k0 * n2 * 4), K2 * n2, L.ptr(ws), ws.numel()
+        L.check(L.lib().dcs_wgrad_tc16(C.byref(p), L.stream_ptr()), "dcs_wgrad_tc16")
+    return dwp
+
+
+@ops._on_tensor_device
+def to_h16(x, dtype=torch.bfloat16):
+    """fp32 -> fp16 / bf16 copy of a contiguous activation (dcs_convert)."""
+    y = torch.empty(x.shape, dtype=dtype, device=x.device)
+    L.check(L.lib().dcs_convert(L.ptr(x), L.ptr(y), x.numel(), L.F32, L.dtype_code(y), L.stream_ptr()), "dcs_convert")
+    return y

@@ -447,8 +447,13 @@ int dcs_colsum(const float* x, int64_t rows, int cols, int pitch, int mode, floa
  * in / out-swapped weights (train_ops.dgrad_conv) */
 int dcs_dilate(const float* dy, float* out, int batch, int out_h, int out_w, int in_h, int in_w, int channels, int stride_h,
                int stride_w, void* stream);
-/* z (B, h*up_h, w*up_w, c0 + c1) = complex_upsample(cat(d, skip)) (c_network.py:214-215), materialised as the wgrad's x operand */
-int dcs_upcat_fwd(const float* d, const float* skip, float* z, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream);
+/* data gradient of a ComplexConv2d with ONE input channel (encoder[0], c_network.py:107-112) from the raw conv_r / conv_i weights
+ * (cout, 1, kh, kw): dx (B, in_h, in_w) complex = sum over the taps of this pixel's stride phase (padding k // 2) */
+int dcs_cconv_dgrad_cin1(const float* dy, const float* w_r, const float* w_i, float* dx, int batch, int in_h, int in_w, int out_h, int out_w,
+                         int cout, int kh, int kw, int stride_h, int stride_w, void* stream);
+/* z (B, h*up_h, w*up_w, c0 + c1) = complex_upsample(cat(d, skip)) (c_network.py:214-215), materialised as the wgrad's x operand in
+ * out_dtype (fp32 for dcs_wgrad, fp16 / bf16 for dcs_wgrad_tc16) */
+int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream);
 /* dz = act'(y) (.) (g0 + g1 + chan_const[b][c]) per real component (ComplexReLU / ComplexLReLU act on the parts); y = the
  * activation's OUTPUT (B, hw, channels) complex; g1 (same shape) and chan_const (B, channels) complex are optional */
 int dcs_act_bwd(const float* y, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,
@@ -500,6 +505,19 @@ int dcs_adam_amsgrad(float* param, const float* grad, float* exp_avg, float* exp
  * layouts (block matrices, phase pre-sums, role swaps) by an index table built once on the host, one launch per step;
  * out_dtype: DCS_F32 / DCS_F16 / DCS_BF16, or 3 = fp32 rounded to tf32 (the kind::tf32 operands) */
 int dcs_gather_pack(const float* src, const int32_t* idx4, const int8_t* sign4, void* dst, int64_t n, int out_dtype, void* stream);
+
+/* ---- dcs_wgrad on the tensor cores: the tcgen05 GEMM of dcs_cwgrad_tc (K = pixels, MN-major operands straight from 16-bit
+ *      channels-last activations) behind dcs_wgrad's interface — real channel counts k2 <= 256 (wider inputs: call per channel slice,
+ *      x + offset with x_pitch = channels per pixel, dwp + k_offset * n2 with dwp_tap_stride = k2_total * n2), any n2; operand boxes
+ *      beyond the real channels are zero-filled by TMA.  dwp [ntaps][k2][n2] fp32 as dcs_wgrad writes it. */
+typedef struct {
+  const void* x; const void* dy; int dtype;
+  int batch; int in_h; int in_w; int out_h; int out_w; int k2; int n2; int x_pitch; int dy_pitch; int stride_h; int stride_w;
+  int ntaps; int8_t dy_off[DCS_MAX_TAPS]; int8_t dx_off[DCS_MAX_TAPS];
+  float* dwp; int64_t dwp_tap_stride; void* workspace; int64_t workspace_bytes;
+} dcs_wgrad16_params;
+int64_t dcs_wgrad_tc16_workspace_bytes(const dcs_wgrad16_params* p);
+int dcs_wgrad_tc16(const dcs_wgrad16_params* p, void* stream);
 
 /* ---- developer aid: per-CTA wait-cycle counters of the tcgen05 kernel (8 uint64 per CTA, >= 148 CTAs); NULL = off */
 int dcs_tc_set_debug_buffer(void* dev_ptr);

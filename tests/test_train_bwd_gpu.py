@@ -49,6 +49,9 @@ def test_encoder_conv_backward_generic_wgrad_bias_and_strided_dgrad(cin, cout, k
     assert rel_err(dwr, dwr_w) <= 2e-5 and rel_err(dwi, dwi_w) <= 2e-5
     assert rel_err(dbr, dbr_w) <= 2e-5 and rel_err(dbi, dbi_w) <= 2e-5
     assert rel_err(nchw(dx), dx_w) <= 2e-5
+    if cin == 1:      # encoder[0]: the direct gather kernel on the raw weights
+        dx1 = T.cconv_dgrad_cin1(dyc, w_r.cuda(), w_i.cuda(), H, W, stride)
+        assert rel_err(nchw(dx1), dx_w) <= 2e-5
 
 
 @pytest.mark.parametrize("cd,cs,cout,up", [(8, 8, 1, (2, 2)), (16, 16, 8, (2, 2)), (64, 64, 32, (2, 1)), (128, 128, 128, (2, 1))])
@@ -171,3 +174,21 @@ def test_clstm_split_merge_combine():
     assert torch.equal(out[..., 0], h[0, 0] - h[1, 1]) and torch.equal(out[..., 1], h[0, 1] + h[1, 0])
     dh = T.clstm_combine_bwd(x)
     assert torch.equal(dh[0, 0], x[..., 0]) and torch.equal(dh[1, 1], -x[..., 0]) and torch.equal(dh[0, 1], x[..., 1]) and torch.equal(dh[1, 0], x[..., 1])
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", [(8, 16, 7, (2, 2), 16, 140), (16, 32, 5, (2, 2), 12, 70), (32, 8, 3, (1, 1), 6, 130), (64, 16, 3, (1, 1), 5, 66),
+                                                  (256, 128, 3, (1, 1), 4, 40), (256, 64, 3, (1, 1), 4, 33), (128, 128, 1, (1, 1), 1, 200)])
+def test_generic_interface_wgrad_on_tcgen05(cin, cout, k, stride, H, W):
+    """dcs_wgrad_tc16 (the tcgen05 K = pixels GEMM behind dcs_wgrad's interface: TMA zero-fill pads few-channel operands to the 128 x 64
+    tile, > 256 real input channels run as channel slices) against dcs_wgrad on the same bf16-rounded operands."""
+    from dcsnet_b200 import train_ops as T
+    g = torch.Generator().manual_seed(cin + 3 * cout + k)
+    B = 2
+    x = torch.randn(B, H, W, 2 * cin, generator=g).bfloat16()
+    OH, OW = (H + 2 * (k // 2) - k) // stride[0] + 1, (W + 2 * (k // 2) - k) // stride[1] + 1
+    dy = (0.1 * torch.randn(B, OH, OW, 2 * cout, generator=g)).bfloat16()
+    taps = T.conv_taps(k, k)
+    want = T.wgrad(x.float().cuda(), dy.float().cuda(), taps, stride)
+    got = T.wgrad_tc16(x.cuda(), dy.cuda(), taps, stride)
+    torch.cuda.synchronize()
+    assert rel_err(got, want) <= 2e-5
