@@ -220,6 +220,8 @@ SYMBOLS = {
     "dcs_upcat_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_wgrad_tc16_workspace_bytes": (_i64, [C.POINTER(Wgrad16Params)]),
     "dcs_wgrad_tc16": (_i, [C.POINTER(Wgrad16Params), _vp]),
+    "dcs_dec6_bwd_workspace_bytes": (_i64, []),
+    "dcs_dec6_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
     "dcs_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
     "dcs_dropout": (_i, [_vp, _vp, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "dcs_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),

@@ -464,6 +464,127 @@ __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __r
   }
 }
 
+// =============================================================================================== decoder[6] backward, fused
+// decoder[6] = ComplexConvTranspose2d(16 -> 1, k3 s1 p1) on the (2,2) nearest up-sampling of cat(d5, skip6) (c_network.py:214-216).
+// With ONE output channel every low-resolution input pixel q sees the same 4 x 4 neighbourhood of the full-resolution gradient dpre:
+//   data:   g[q][ci]        = sum_{r,c in -1..2} Weff[ci][r][c] * dpre[2q + (r,c)],  Weff[ci][r][c] = sum_{u + a - 1 = r, v + b - 1 = c} conj(W[ci][a][b])
+//   weight: dW[ci][a][b]    = sum_q S_ab[q] * conj(z[q][ci]),  S_ab[q] = sum_{u in {0,1}^2} dpre[2q + u + (a - 1, b - 1)]
+//   bias:   db_r = sum (dpre.re + dpre.im), db_i = sum (dpre.im - dpre.re)
+// (oracle/train_oracle.decoder_stage_backward for cout = 1, up (2,2)).  Replaces the materialised up-sampled input (2 GB at batch
+// 32 x 4 s), the few-channel wgrad, two full-resolution dgrad convolutions and two up-sampling adjoints.  Persistent CTAs over
+// 8 x 32-pixel low-resolution tiles; phase 1 thread = pixel (S_ab, g, bias), phase 2 thread = (ci, tap) over the tile's pixels.
+constexpr int kD6TH = 8, kD6TW = 32, kD6C = 16;
+__global__ void __launch_bounds__(256) dec6_bwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, const float2* __restrict__ dpre,
+                                                       const float* __restrict__ w_r, const float* __restrict__ w_i, int B, int H, int W, int c0, int c1,
+                                                       float2* __restrict__ g_d, float2* __restrict__ g_skip, double* __restrict__ partial) {
+  extern __shared__ __align__(16) unsigned char d6_smem[];
+  float2 (*S)[kD6TH * kD6TW] = reinterpret_cast<float2 (*)[kD6TH * kD6TW]>(d6_smem);                                   // [9][256]
+  float2 (*zt)[kD6C + 1] = reinterpret_cast<float2 (*)[kD6C + 1]>(d6_smem + sizeof(float2) * 9 * kD6TH * kD6TW);      // [256][17]
+  __shared__ float2 nb[2 * kD6TH + 2][2 * kD6TW + 2];
+  __shared__ float2 weff[kD6C][16];
+  __shared__ float bred[8][2];
+  const int tid = threadIdx.x, Cn = c0 + c1;
+  for (int i = tid; i < kD6C * 16; i += 256) {
+    const int ci = i / 16, r = (i % 16) / 4 - 1, c = i % 4 - 1;
+    float2 acc = make_float2(0.f, 0.f);
+    if (ci < Cn)
+      for (int a = 0; a < 3; ++a)
+        for (int b = 0; b < 3; ++b) {
+          const int u = r - a + 1, v = c - b + 1;
+          if (u >= 0 && u <= 1 && v >= 0 && v <= 1) { acc.x += w_r[ci * 9 + a * 3 + b]; acc.y -= w_i[ci * 9 + a * 3 + b]; }   // conj(W)
+        }
+    weff[ci][i % 16] = acc;
+  }
+  const int tiles_w = (W + kD6TW - 1) / kD6TW, tiles_h = (H + kD6TH - 1) / kD6TH;
+  const int n_tiles = B * tiles_h * tiles_w;
+  const int HH = 2 * H, WW = 2 * W;
+  const int py = tid / kD6TW, px = tid % kD6TW;
+  // phase-2 role: output (ci, tap) = tid (tid < 9 * Cn): tap = tid % 9, ci = tid / 9
+  const int o_tap = tid % 9, o_ci = tid / 9;
+  float2 acc_w = make_float2(0.f, 0.f);
+  float acc_b0 = 0.f, acc_b1 = 0.f;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+    const int tw = t % tiles_w, th = (t / tiles_w) % tiles_h, b = t / (tiles_w * tiles_h);
+    const int y0 = th * kD6TH, x0 = tw * kD6TW;
+    __syncthreads();
+    for (int i = tid; i < (2 * kD6TH + 2) * (2 * kD6TW + 2); i += 256) {
+      const int r = i / (2 * kD6TW + 2), c = i % (2 * kD6TW + 2);
+      const int yy = 2 * y0 - 1 + r, xx = 2 * x0 - 1 + c;
+      nb[r][c] = ((unsigned)yy < (unsigned)HH && (unsigned)xx < (unsigned)WW) ? dpre[((int64_t)b * HH + yy) * WW + xx] : make_float2(0.f, 0.f);
+    }
+    const int y = y0 + py, x = x0 + px;
+    const bool ok = y < H && x < W;
+    const int64_t q = ((int64_t)b * H + y) * W + x;
+    for (int c = 0; c < Cn; ++c) zt[tid][c] = ok ? (c < c0 ? d[q * c0 + c] : skip[q * c1 + (c - c0)]) : make_float2(0.f, 0.f);
+    __syncthreads();
+    float2 v[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[r][c] = nb[2 * py + r][2 * px + c];       // dpre[2q + (r - 1, c - 1)]
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb)      // S_ab = sum_{u,v in {0,1}} dpre[2q + (u + a - 1, v + bb - 1)] -> v[u + a][v + bb]
+        S[a * 3 + bb][tid] = make_float2(v[a][bb].x + v[a][bb + 1].x + v[a + 1][bb].x + v[a + 1][bb + 1].x,
+                                         v[a][bb].y + v[a][bb + 1].y + v[a + 1][bb].y + v[a + 1][bb + 1].y);
+    if (ok) {
+      acc_b0 += v[1][1].x + v[1][2].x + v[2][1].x + v[2][2].x;               // the pixel's own 2 x 2 block: sum of dpre.re
+      acc_b1 += v[1][1].y + v[1][2].y + v[2][1].y + v[2][2].y;
+      for (int ci = 0; ci < Cn; ++ci) {
+        float2 g = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < 4; ++r)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float2 wv = weff[ci][r * 4 + c], dv = v[r][c];
+            g.x += wv.x * dv.x - wv.y * dv.y;
+            g.y += wv.x * dv.y + wv.y * dv.x;
+          }
+        if (ci < c0) g_d[q * c0 + ci] = g; else g_skip[q * c1 + (ci - c0)] = g;
+      }
+    }
+    __syncthreads();
+    if (tid < 9 * Cn) {
+      float2 a2 = make_float2(0.f, 0.f);
+#pragma unroll 8
+      for (int p = 0; p < kD6TH * kD6TW; ++p) {
+        const float2 sv = S[o_tap][p], zv = zt[p][o_ci];
+        a2.x += sv.x * zv.x + sv.y * zv.y;        // S * conj(z)
+        a2.y += sv.y * zv.x - sv.x * zv.y;
+      }
+      acc_w.x += a2.x; acc_w.y += a2.y;
+    }
+  }
+  // per-CTA partials: [9 * Cn complex][bias 2]
+  double* out = partial + (int64_t)blockIdx.x * (2 * 9 * kD6C + 2);
+  if (tid < 9 * Cn) { out[2 * tid] = acc_w.x; out[2 * tid + 1] = acc_w.y; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { acc_b0 += __shfl_xor_sync(0xffffffffu, acc_b0, o); acc_b1 += __shfl_xor_sync(0xffffffffu, acc_b1, o); }
+  if ((tid & 31) == 0) { bred[tid >> 5][0] = acc_b0; bred[tid >> 5][1] = acc_b1; }
+  __syncthreads();
+  if (tid == 0) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int wv = 0; wv < 8; ++wv) { s0 += bred[wv][0]; s1 += bred[wv][1]; }
+    out[2 * 9 * kD6C] = s0; out[2 * 9 * kD6C + 1] = s1;
+  }
+}
+__global__ void dec6_bwd_finalize_kernel(const double* __restrict__ partial, int n_ctas, int Cn, float* __restrict__ dw_r, float* __restrict__ dw_i,
+                                         float* __restrict__ db_r, float* __restrict__ db_i) {
+  const int i = threadIdx.x;          // (ci, tap) for i < 9 Cn; i == 9 Cn: bias
+  if (i > 9 * Cn) return;
+  const int stride = 2 * 9 * kD6C + 2;
+  const int off = i < 9 * Cn ? 2 * i : 2 * 9 * kD6C;
+  double sr = 0.0, si = 0.0;
+  for (int c = 0; c < n_ctas; ++c) { sr += partial[(int64_t)c * stride + off]; si += partial[(int64_t)c * stride + off + 1]; }
+  if (i < 9 * Cn) {
+    const int tap = i % 9, ci = i / 9;
+    dw_r[ci * 9 + tap] = (float)sr; dw_i[ci * 9 + tap] = (float)si;
+  } else {
+    *db_r = (float)(sr + si); *db_i = (float)(si - sr);
+  }
+}
+
 // =============================================================================================== attention backward
 // y = s * u, u = a * x (a: channel gate (B,C), s: spatial gate (B,HW)); oracle/train_oracle.attention_backward.
 // G = min(C, 32) lanes cooperate on one pixel, 32 / G pixels per warp.
@@ -1085,6 +1206,26 @@ extern "C" int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out
   if (out_dtype == DCS_F32) upcat_fwd_kernel<float><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (float*)z, batch, h, w, c0, c1, up_h, up_w);
   else if (out_dtype == DCS_F16) upcat_fwd_kernel<__half><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__half*)z, batch, h, w, c0, c1, up_h, up_w);
   else upcat_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__nv_bfloat16*)z, batch, h, w, c0, c1, up_h, up_w);
+  DCS_LAUNCHED();
+  return 0;
+}
+
+extern "C" int64_t dcs_dec6_bwd_workspace_bytes(void) { return (int64_t)2 * num_sms() * (2 * 9 * kD6C + 2) * (int64_t)sizeof(double); }
+extern "C" int dcs_dec6_bwd(const float* d, const float* skip, const float* dpre, const float* w_r, const float* w_i, int batch, int h, int w, int c0, int c1,
+                            float* g_d, float* g_skip, float* dw_r, float* dw_i, float* db_r, float* db_i, void* workspace, int64_t workspace_bytes,
+                            void* stream) {
+  DCS_REQUIRE(d && skip && dpre && w_r && w_i && g_d && g_skip && dw_r && dw_i && db_r && db_i && workspace, "dcs_dec6_bwd: null pointer");
+  DCS_REQUIRE(batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 > 0 && c0 + c1 <= kD6C, "dcs_dec6_bwd: c0 + c1 must be <= 16");
+  DCS_REQUIRE(workspace_bytes >= dcs_dec6_bwd_workspace_bytes(), "dcs_dec6_bwd: workspace too small");
+  const int n_tiles = batch * ((h + kD6TH - 1) / kD6TH) * ((w + kD6TW - 1) / kD6TW);
+  const int ctas = std::min(n_tiles, 2 * num_sms());
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t smem = sizeof(float2) * (9 * kD6TH * kD6TW + kD6TH * kD6TW * (kD6C + 1));
+  DCS_CUDA(cudaFuncSetAttribute(dec6_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dec6_bwd_kernel<<<ctas, 256, smem, s>>>((const float2*)d, (const float2*)skip, (const float2*)dpre, w_r, w_i, batch, h, w, c0, c1, (float2*)g_d,
+                                       (float2*)g_skip, reinterpret_cast<double*>(workspace));
+  DCS_LAUNCHED();
+  dec6_bwd_finalize_kernel<<<1, 160, 0, s>>>(reinterpret_cast<const double*>(workspace), ctas, c0 + c1, dw_r, dw_i, db_r, db_i);
   DCS_LAUNCHED();
   return 0;
 }

@@ -340,6 +340,17 @@ class TrainStep:
                 dz = T.act_bwd(att["x"], dxa, L.ACT_LRELU, None, cc)
                 dpre, prefix = self._bn_bwd(sv[f"dec{i}_pre"], dz, f"decoder.{i}.1", f"dec{i}"), f"decoder.{i}.0."
             d_in, skip = sv["dec_in"][i], sv["skip"][i]
+            if i == Lr - 1 and dpre.shape[3] == 1 and UPSAMPLE[i] == (2, 2) and d_in.shape[3] + skip.shape[3] <= 16:
+                # decoder[6]: one output channel -> data, weight and bias gradients in ONE kernel (no up-sampled input, no full-resolution dgrad)
+                g, g_skip = T.dec6_bwd(d_in, skip, dpre, self._params[prefix + "conv_tran_r.weight"].detach(), self._params[prefix + "conv_tran_i.weight"].detach(),
+                                       self._grad(prefix + "conv_tran_r.weight"), self._grad(prefix + "conv_tran_i.weight"),
+                                       self._grad(prefix + "conv_tran_r.bias"), self._grad(prefix + "conv_tran_i.bias"))
+                info["g_d5"], info["g_skip6"] = g, g_skip
+                att = sv["skip_att"][i]
+                dxs, ccs, _ = T.attention_bwd(att["x"], g_skip, att["gate_c"], att["stats"], att["gate_s"], att["sums"], self.skip_ca[i], self.skip_sa[i],
+                                              grads=self._att_grads(f"skip_attention.{2 * i}.", f"skip_attention.{2 * i + 1}."))
+                skip_grad[Lr - i] = (dxs, ccs)
+                continue
             on_tc = self._wgrad_on_tc(d_in.shape[3] + skip.shape[3], dpre.shape[3])
             z = T.upcat_fwd(d_in, skip, UPSAMPLE[i], dtype=torch.bfloat16 if on_tc else torch.float32)
             self._conv_param_grads(z, dpre, prefix, ("conv_tran_r", "conv_tran_i"), 3, (1, 1), True)

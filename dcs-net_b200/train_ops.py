@@ -443,3 +443,18 @@ def to_h16(x, dtype=torch.bfloat16):
     y = torch.empty(x.shape, dtype=dtype, device=x.device)
     L.check(L.lib().dcs_convert(L.ptr(x), L.ptr(y), x.numel(), L.F32, L.dtype_code(y), L.stream_ptr()), "dcs_convert")
     return y
+
+
+@ops._on_tensor_device
+def dec6_bwd(d, skip, dpre, w_r, w_i, dw_r, dw_i, db_r, db_i):
+    """Fused backward of decoder[6] (dcs_dec6_bwd): d, skip (B, h, w, 8, 2), dpre (B, 2h, 2w, 1, 2) -> (g_d, g_skip); the parameter
+    gradients are written into dw_r / dw_i (16, 1, 3, 3) and db_r / db_i (1,)."""
+    B, H, W, c0, _ = d.shape
+    c1 = skip.shape[3]
+    assert dpre.is_contiguous() and d.is_contiguous() and skip.is_contiguous() and dpre.numel() == B * 2 * H * 2 * W * 2
+    assert w_r.is_contiguous() and w_i.is_contiguous() and tuple(w_r.shape) == (c0 + c1, 1, 3, 3)
+    g_d, g_s = torch.empty_like(d), torch.empty_like(skip)
+    ws = _ws(L.lib().dcs_dec6_bwd_workspace_bytes(), d.device)
+    L.check(L.lib().dcs_dec6_bwd(L.ptr(d), L.ptr(skip), L.ptr(dpre), L.ptr(w_r), L.ptr(w_i), B, H, W, c0, c1, L.ptr(g_d), L.ptr(g_s), L.ptr(dw_r),
+                                 L.ptr(dw_i), L.ptr(db_r), L.ptr(db_i), L.ptr(ws), ws.numel(), L.stream_ptr()), "dcs_dec6_bwd")
+    return g_d, g_s

@@ -454,6 +454,13 @@ int dcs_cconv_dgrad_cin1(const float* dy, const float* w_r, const float* w_i, fl
 /* z (B, h*up_h, w*up_w, c0 + c1) = complex_upsample(cat(d, skip)) (c_network.py:214-215), materialised as the wgrad's x operand in
  * out_dtype (fp32 for dcs_wgrad, fp16 / bf16 for dcs_wgrad_tc16) */
 int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream);
+/* decoder[6] backward in one kernel (c_network.py:214-216: ComplexConvTranspose2d(c0 + c1 -> 1, k3 s1 p1) on the (2,2) nearest
+ * up-sampling of cat(d, skip)): dpre (B, 2h, 2w) complex = gradient of the layer's output -> g_d (B, h, w, c0), g_skip (B, h, w, c1),
+ * the weight gradients in the module's (c0 + c1, 1, 3, 3) layout and the two bias gradients.  c0 + c1 <= 16. */
+int64_t dcs_dec6_bwd_workspace_bytes(void);
+int dcs_dec6_bwd(const float* d, const float* skip, const float* dpre, const float* w_r, const float* w_i, int batch, int h, int w, int c0, int c1,
+                 float* g_d, float* g_skip, float* dw_r, float* dw_i, float* db_r, float* db_i, void* workspace, int64_t workspace_bytes,
+                 void* stream);
 /* dz = act'(y) (.) (g0 + g1 + chan_const[b][c]) per real component (ComplexReLU / ComplexLReLU act on the parts); y = the
  * activation's OUTPUT (B, hw, channels) complex; g1 (same shape) and chan_const (B, channels) complex are optional */
 int dcs_act_bwd(const float* y, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,

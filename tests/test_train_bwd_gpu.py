@@ -192,3 +192,22 @@ def test_generic_interface_wgrad_on_tcgen05(cin, cout, k, stride, H, W):
     got = T.wgrad_tc16(x.cuda(), dy.cuda(), taps, stride)
     torch.cuda.synchronize()
     assert rel_err(got, want) <= 2e-5
+
+
+@pytest.mark.parametrize("H,W", [(8, 32), (5, 41), (16, 70)])
+def test_fused_decoder6_backward(H, W):
+    """dcs_dec6_bwd (data + weight + bias gradients of decoder[6] in one kernel) vs oracle decoder_stage_backward (cout 1, up (2,2))."""
+    from dcsnet_b200 import train_ops as T
+    g = torch.Generator().manual_seed(H * W)
+    B = 3
+    d, skip = rc(g, B, 8, H, W), rc(g, B, 8, H, W)
+    w_r, w_i = 0.3 * torch.randn(16, 1, 3, 3, generator=g), 0.3 * torch.randn(16, 1, 3, 3, generator=g)
+    dy = rc(g, B, 1, 2 * H, 2 * W)
+    gd_w, gs_w, dwr_w, dwi_w, dbr_w, dbi_w = TO.decoder_stage_backward(d, skip, w_r, w_i, dy, (2, 2))
+    dwr, dwi = torch.empty(16, 1, 3, 3, device="cuda"), torch.empty(16, 1, 3, 3, device="cuda")
+    dbr, dbi = torch.empty(1, device="cuda"), torch.empty(1, device="cuda")
+    gd, gs = T.dec6_bwd(cl(d).cuda(), cl(skip).cuda(), cl(dy).cuda(), w_r.cuda(), w_i.cuda(), dwr, dwi, dbr, dbi)
+    torch.cuda.synchronize()
+    assert rel_err(nchw(gd), gd_w) <= 2e-5 and rel_err(nchw(gs), gs_w) <= 2e-5
+    assert rel_err(dwr, dwr_w) <= 2e-5 and rel_err(dwi, dwi_w) <= 2e-5
+    assert rel_err(dbr, dbr_w) <= 2e-5 and rel_err(dbi, dbi_w) <= 2e-5
