@@ -666,31 +666,41 @@ def run_train(args, rank, local_rank, world):
     # ---- stage split + the convolution GEMM family (forward, dgrad, wgrad) timed with CUDA events around every call of one eager step
     fam = {"conv_fwd_dgrad": [], "conv_wgrad": []}
     roof = None
+
+    def wrap(mod, name, key):
+        orig = getattr(mod, name)
+
+        def inner(*a, **k):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = orig(*a, **k)
+            e1.record()
+            fam[key].append((e0, e1))
+            return r
+        setattr(mod, name, inner)
+        return orig
+    # EVERY rank runs the instrumented step (optimizer_step all-reduces: a rank-0-only call would dead-lock); rank 0 reports it
+    o1, o2, o3 = wrap(ops, "cconv", "conv_fwd_dgrad"), wrap(T, "wgrad", "conv_wgrad"), wrap(T, "wgrad_tc16", "conv_wgrad")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    ev[0].record()
+    step.forward(*dev_specs)
+    ev[1].record()
+    step.backward()
+    ev[2].record()
+    step.optimizer_step()
+    ev[3].record()
+    barrier()
+    ops.cconv, T.wgrad, T.wgrad_tc16 = o1, o2, o3
     if rank == 0:
-        def wrap(mod, name, key):
-            orig = getattr(mod, name)
-            def inner(*a, **k):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-                r = orig(*a, **k)
-                e1.record()
-                fam[key].append((e0, e1))
-                return r
-            setattr(mod, name, inner)
-            return orig
-        o1, o2 = wrap(ops, "cconv", "conv_fwd_dgrad"), wrap(T, "wgrad", "conv_wgrad")
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        ev[0].record(); step.forward(*dev_specs); ev[1].record(); step.backward(); ev[2].record(); step.optimizer_step(); ev[3].record()
-        torch.cuda.synchronize()
-        ops.cconv, T.wgrad = o1, o2
         fam_ms = {k: sum(a.elapsed_time(b) for a, b in v) for k, v in fam.items()}
         dense = sum(f for f, _ in conv_flops_per_utterance(Tn).values()) * B
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
         bf16 = float(peaks.get("bf16_tflops", 1663.0))
         conv_ms = fam_ms["conv_fwd_dgrad"] + fam_ms["conv_wgrad"]
         ach = 3 * dense / (conv_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "convolution GEMM family of the step: forward + data-gradient (dcs::cconv_tc_kernel kind::tf32 / cconv_ffma) and "
-                                             "weight-gradient (dcs::wgrad_generic_kernel / wgrad_small_kernel, CUDA-core fp32)",
+        roof = {"bound": "tensor", "kernel": "convolution GEMM family of the step: forward + data gradient (dcs::cconv_tc_kernel, tcgen05 kind::tf32; few-channel "
+                                             "layers on CUDA cores) and weight gradient (dcs::wgrad_tc_kernel, tcgen05 kind::f16 on bf16 operand copies; "
+                                             "encoder[0] / decoder[6] on CUDA-core kernels)",
                 "achieved": ach, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": ach / (bf16 / 2),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the kind::f16 rate)" if peaks else "fallback 1663 / 2",
                 "flops_per_step": 3 * dense, "flop_basis": "dense formulation, forward + dgrad + wgrad = 3 x forward", "family_ms": fam_ms,

@@ -62,7 +62,8 @@ class TrainStep:
             p = f"encoder.{i}.0."
             self.enc.append(packing.PackedConv(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], sd[p + "conv_r.bias"], sd[p + "conv_i.bias"],
                                                stride=STRIDE_E[i], act=L.ACT_NONE, device=device, want_tf32=tf))
-            self.enc_dgrad.append(T.dgrad_conv(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], transposed=False, device=device, want_tf32=tf))
+            # data gradient of the strided conv as a sub-pixel phase convolution of the un-dilated gradient (train_ops.PhasePack)
+            self.enc_dgrad.append(T.PhasePack(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], STRIDE_E[i], device, want_tf32=tf))
         for i in range(Lr):
             p = f"decoder.{i}." if i == Lr - 1 else f"decoder.{i}.0."
             self.dec.append(packing.PackedConv(sd[p + "conv_tran_r.weight"], sd[p + "conv_tran_i.weight"], sd[p + "conv_tran_r.bias"],
@@ -388,7 +389,10 @@ class TrainStep:
                 g = T.cconv_dgrad_cin1(dpre, self._params[f"encoder.{i}.0.conv_r.weight"].detach(), self._params[f"encoder.{i}.0.conv_i.weight"].detach(),
                                        Hi, Wi, STRIDE_E[i])
             else:
-                g = self._conv(self.enc_dgrad[i], T.dilate(dpre, Hi, Wi, STRIDE_E[i]), None, new(B, Hi, Wi, x_in.shape[3], 2))
+                if (Hi, Wi) != (dpre.shape[1] * STRIDE_E[i][0], dpre.shape[2] * STRIDE_E[i][1]):
+                    raise NotImplementedError("TrainStep: encoder input sizes must be multiples of the strides (F % 128 == 0, T % 8 == 0, as "
+                                              "the reference's decoder concatenation requires, c_network.py:214)")
+                g = self._conv(self.enc_dgrad[i], dpre, None, new(B, Hi, Wi, x_in.shape[3], 2))
         self._bn_bwd(sv["x0"].contiguous(), g, "initial_batchnorm", "bn0")
         return info
 
@@ -431,7 +435,7 @@ class TrainStep:
             p = f"encoder.{i}.0."
             wr, wi = leaf(p + "conv_r.weight"), leaf(p + "conv_i.weight")
             gp.add_packed_conv(self.enc[i], TP.sym_conv(wr, wi, leaf(p + "conv_r.bias"), leaf(p + "conv_i.bias"), tf32=tf))
-            gp.add_packed_conv(self.enc_dgrad[i], TP.sym_dgrad(wr, wi, transposed=False, tf32=tf))
+            gp.add_packed_conv(self.enc_dgrad[i], TP.sym_dgrad_strided(wr, wi, STRIDE_E[i], tf32=tf))
             p = f"decoder.{i}." if i == Lr - 1 else f"decoder.{i}.0."
             wr, wi = leaf(p + "conv_tran_r.weight"), leaf(p + "conv_tran_i.weight")
             gp.add_packed_conv(self.dec[i], TP.sym_conv(wr, wi, leaf(p + "conv_tran_r.bias"), leaf(p + "conv_tran_i.bias"), transposed=True,

@@ -458,3 +458,53 @@ def dec6_bwd(d, skip, dpre, w_r, w_i, dw_r, dw_i, db_r, db_i):
     L.check(L.lib().dcs_dec6_bwd(L.ptr(d), L.ptr(skip), L.ptr(dpre), L.ptr(w_r), L.ptr(w_i), B, H, W, c0, c1, L.ptr(g_d), L.ptr(g_s), L.ptr(dw_r),
                                  L.ptr(dw_i), L.ptr(db_r), L.ptr(db_i), L.ptr(ws), ws.numel(), L.stream_ptr()), "dcs_dec6_bwd")
     return g_d, g_s
+
+
+# ------------------------------------------------------------------------------------------------ strided conv dgrad = a phase conv
+def strided_dgrad_taps(k, stride):
+    """Data gradient of a k-tap, stride-s, padding k // 2 convolution along one axis as per-phase tap lists: output index s y + ph
+    receives w[ky] dy[y + d] for every ky with (ph + pad - ky) % s == 0, d = (ph + pad - ky) / s.  Returns [[(d, ky), ...] per phase],
+    padded with (0, None) to a common length (the forward kernels take one tap count for all phases)."""
+    pad = k // 2
+    rows = [sorted(((ph + pad - ky) // stride, ky) for ky in range(k) if (ph + pad - ky) % stride == 0) for ph in range(stride)]
+    n = max(len(r) for r in rows)
+    return [r + [(0, None)] * (n - len(r)) for r in rows]
+
+
+class PhasePack:
+    """Operands of the forward conv kernels (ops.cconv) for the data gradient of a STRIDED ComplexConv2d, written as a sub-pixel
+    phase convolution of the un-dilated gradient (the zero-insertion route multiplies stride_h * stride_w times as many taps)."""
+
+    def __init__(self, w_r, w_i, stride, device, want_tf32=False):
+        w_r, w_i = w_r.detach().double().cpu(), w_i.detach().double().cpu()
+        cout, cin, kh, kw = w_r.shape
+        rows, cols = strided_dgrad_taps(kh, stride[0]), strided_dgrad_taps(kw, stride[1])
+        self.cin, self.cout, self.kh, self.kw = cout, cin, kh, kw          # as a conv: dy (cout of the layer) -> dx (its cin)
+        self.stride, self.up, self.act = (1, 1), tuple(stride), L.ACT_NONE
+        self.phases, self.ntaps = stride[0] * stride[1], len(rows[0]) * len(cols[0])
+        assert self.phases * self.ntaps <= L.MAX_TAPS
+        # block of conj(w[co][ci]) as a map (co, re/im) -> (ci, re/im): [[w_r, w_i], [-w_i, w_r]]
+        M = torch.zeros(cin, 2, cout, 2, kh, kw, dtype=torch.float64)
+        M[:, 0, :, 0], M[:, 0, :, 1] = w_r.permute(1, 0, 2, 3), w_i.permute(1, 0, 2, 3)
+        M[:, 1, :, 0], M[:, 1, :, 1] = -w_i.permute(1, 0, 2, 3), w_r.permute(1, 0, 2, 3)
+        dy, dx, mats = [], [], []
+        for ph in range(stride[0]):
+            for pw in range(stride[1]):
+                for d_y, ky in rows[ph]:
+                    for d_x, kx in cols[pw]:
+                        dy.append(d_y), dx.append(d_x)
+                        mats.append(torch.zeros(cin, 2, cout, 2, dtype=torch.float64) if ky is None or kx is None else M[..., ky, kx])
+        self.dy, self.dx = dy, dx
+        N, C2 = 2 * cin, 2 * cout
+        self.n_pad = (N + 15) // 16 * 16
+        Wp = torch.zeros(self.phases, self.ntaps, self.n_pad, C2, dtype=torch.float64)
+        Wp[:, :, :N] = torch.stack(mats, 0).reshape(self.phases, self.ntaps, N, C2)
+        self.w_ffma = Wp.permute(0, 1, 3, 2).contiguous().float().to(device)
+        self.w_tc, self.w_tc32 = None, None
+        if want_tf32:
+            K = self.ntaps * C2
+            k_pad = (K + 31) // 32 * 32
+            wt = torch.zeros(self.phases, self.n_pad, k_pad, dtype=torch.float64)
+            wt[:, :, :K] = Wp.permute(0, 2, 1, 3).reshape(self.phases, self.n_pad, K)
+            self.w_tc32 = packing.round_tf32(wt.float()).contiguous().to(device)
+        self.bias = torch.zeros(self.n_pad, dtype=torch.float32, device=device)

@@ -169,6 +169,36 @@ def sym_dgrad(w_r, w_i, transposed, tc=False, tf32=False):
     return sym_conv(w_r.permute(1, 0, 2, 3).flip(2, 3), -(w_i.permute(1, 0, 2, 3).flip(2, 3)), tc=tc, tf32=tf32)
 
 
+def sym_dgrad_strided(w_r, w_i, stride, tf32=False):
+    """train_ops.PhasePack's operands (the data gradient of a strided conv as a phase convolution) from symbolic raw weights."""
+    from .train_ops import strided_dgrad_taps
+    cout, cin, kh, kw = w_r.shape
+    wr, wi = w_r.permute(1, 0, 2, 3), w_i.permute(1, 0, 2, 3)
+    M = Sym.stack([Sym.stack([wr, wi], 2), Sym.stack([-wi, wr], 2)], 1)                    # (ci, ro, co, ri, ky, kx)
+    rows, cols = strided_dgrad_taps(kh, stride[0]), strided_dgrad_taps(kw, stride[1])
+    mats = []
+    for ph in range(stride[0]):
+        for pw in range(stride[1]):
+            for _, ky in rows[ph]:
+                for _, kx in cols[pw]:
+                    mats.append(Sym.zeros(cin, 2, cout, 2) if ky is None or kx is None else M[:, :, :, :, ky, kx])
+    phases, N, C2 = stride[0] * stride[1], 2 * cin, 2 * cout
+    ntaps = len(mats) // phases
+    n_pad = (N + 15) // 16 * 16
+    Wt = Sym.stack(mats, 0).reshape(phases, ntaps, N, C2)
+    if n_pad > N:
+        Wt = Sym.cat([Wt, Sym.zeros(phases, ntaps, n_pad - N, C2)], 2)
+    out = dict(w_ffma=Wt.permute(0, 1, 3, 2))
+    if tf32:
+        K = ntaps * C2
+        k_pad = (K + 31) // 32 * 32
+        wt = Wt.permute(0, 2, 1, 3).reshape(phases, n_pad, K)
+        if k_pad > K:
+            wt = Sym.cat([wt, Sym.zeros(phases, n_pad, k_pad - K)], 2)
+        out["w_tc32"] = wt
+    return out
+
+
 class GatherPack:
     """Collects (symbolic operand, destination tensor) pairs and rebuilds all destinations from the flat parameter buffer with one
     dcs_gather_pack launch per destination dtype."""

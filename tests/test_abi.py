@@ -79,3 +79,30 @@ def test_argument_errors_are_reported_not_swallowed():
     assert lib.dcs_rlstm_workspace_bytes(2, 10, 128) == 2 * 10 * 10 * 128 * 4 and lib.dcs_rlstm_workspace_bytes(0, 10, 128) < 0
     assert lib.dcs_real_attention_workspace_bytes(2, 4, 5, 16) > 0 and lib.dcs_real_attention_workspace_bytes(2, 0, 5, 16) < 0
     assert lib.dcs_mag_phase(None, None, None, 4, 1e-6, None) != 0 and b"bad arguments" in lib.dcs_last_error_string()
+
+
+def test_training_struct_sizes_match_header():
+    """Same check for the parameter structs of the training-step entries (f2)."""
+    names = ["dcs_cbn_train_params", "dcs_cbn_train_bwd_params", "dcs_cwgrad_params", "dcs_wgrad_params", "dcs_wgrad16_params", "dcs_attention_bwd_params"]
+    src = '#include <stdio.h>\n#include "dcsnet.h"\nint main(){printf("' + " ".join(["%zu"] * len(names)) + '\\n",' + \
+          ",".join(f"sizeof({n})" for n in names) + ');return 0;}'
+    import tempfile
+    with tempfile.TemporaryDirectory() as d:
+        c = os.path.join(d, "s.c")
+        open(c, "w").write(src)
+        exe = os.path.join(d, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), c, "-o", exe], check=True)
+        sizes = list(map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split()))
+    mine = [ctypes.sizeof(t) for t in (L.CbnTrainParams, L.CbnTrainBwdParams, L.CwgradParams, L.WgradParams, L.Wgrad16Params, L.AttentionBwdParams)]
+    assert sizes == mine
+
+
+def test_training_entries_validate_arguments_without_a_gpu():
+    lib = L.lib()
+    assert lib.dcs_wgrad(ctypes.byref(L.WgradParams()), None) != 0 and b"null pointer" in lib.dcs_last_error_string()
+    assert lib.dcs_wgrad_tc16(ctypes.byref(L.Wgrad16Params()), None) != 0 and b"null pointer" in lib.dcs_last_error_string()
+    assert lib.dcs_attention_bwd(ctypes.byref(L.AttentionBwdParams()), None) != 0 and b"null pointer" in lib.dcs_last_error_string()
+    assert lib.dcs_attention_bwd_workspace_bytes(2, 4, 5, 24, 2) < 0 and lib.dcs_attention_bwd_workspace_bytes(2, 4, 5, 32, 2) > 0
+    assert lib.dcs_lstm_train_fwd(None, None, 4, 2, 10, 64, None, None, None, None) != 0 and b"bad arguments" in lib.dcs_last_error_string()
+    assert lib.dcs_adam_amsgrad(None, None, None, None, None, 10, 1e-4, 0.9, 0.999, 1e-6, 0.0, 1, None, 100.0, 1.0, None) != 0
+    assert lib.dcs_colsum_workspace_bytes(0, 4) < 0

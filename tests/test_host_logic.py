@@ -255,3 +255,41 @@ def test_ops_run_on_the_tensors_device_not_the_current_one():
     ref = O.enhance_audio(sd, noisy)["clean_audio"]
     assert float((out - ref).abs().max() / ref.abs().max()) <= 2e-3
     assert torch.cuda.current_device() == 0
+
+
+def _flat_sync_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from dcsnet_b200 import c_network, config as C, grad_sync
+    net = c_network.C_NETWORK(C.config, dict(C.hparams), 0)
+    gb = grad_sync.GradBuckets(net.named_parameters(), bucket_bytes=4 << 20, flat=True)
+    # what the backward kernels do: write through the parameters' .grad views
+    for i, (n, p) in enumerate(net.named_parameters()):
+        p.grad.fill_(float(i % 7 + 1) * (rank + 1))
+    for i in range(len(gb.buckets)):
+        gb.launch(i)
+    gb.wait()                                                           # SUM stays in the flat buffer (the fused optimizer divides)
+    ok = all(bool((p.grad == float(i % 7 + 1) * 3).all()) for i, (n, p) in enumerate(net.named_parameters()))
+    contiguous = all(b.data_ptr() == gb.flat.data_ptr() + 4 * sum(x.numel() for x in gb.buckets[:i]) for i, b in enumerate(gb.buckets))
+    if rank == 0:
+        q.put(dict(ok=ok, contiguous=contiguous, numel=int(gb.flat.numel()), nb=len(gb.buckets)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_flat_bucket_exchange_with_gloo():
+    """The training step's exchange as TrainStep.optimizer_step drives it: ONE flat fp32 gradient buffer whose 4 MB
+    slices are the all-reduce buckets and whose per-parameter views are the .grad tensors the backward kernels write; every bucket
+    launched asynchronously, wait() leaves the cross-rank SUM in place for the fused clip + Adam kernel (world_size 2, gloo)."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_flat_sync_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    r = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=60)
+    assert r["ok"] and r["contiguous"] and r["numel"] == 2912707 and r["nb"] == 3

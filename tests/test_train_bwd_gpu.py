@@ -27,7 +27,7 @@ def rc(g, *s):
     return torch.complex(torch.randn(*s, generator=g), torch.randn(*s, generator=g))
 
 
-@pytest.mark.parametrize("cin,cout,k,stride,H,W", [(1, 8, 7, (2, 2), 32, 40), (8, 16, 7, (2, 2), 16, 36), (16, 32, 5, (2, 2), 12, 21),
+@pytest.mark.parametrize("cin,cout,k,stride,H,W", [(1, 8, 7, (2, 2), 32, 40), (8, 16, 7, (2, 2), 16, 36), (16, 32, 5, (2, 2), 12, 22),
                                                   (32, 64, 5, (2, 1), 8, 19), (64, 128, 3, (2, 1), 6, 17), (128, 128, 3, (2, 1), 4, 9)])
 def test_encoder_conv_backward_generic_wgrad_bias_and_strided_dgrad(cin, cout, k, stride, H, W):
     """ComplexConv2d(k, stride, p = k // 2) backward: dcs_wgrad + dcs_wgrad_fold_complex (weights), dcs_colsum mode 1 (biases),
@@ -49,6 +49,13 @@ def test_encoder_conv_backward_generic_wgrad_bias_and_strided_dgrad(cin, cout, k
     assert rel_err(dwr, dwr_w) <= 2e-5 and rel_err(dwi, dwi_w) <= 2e-5
     assert rel_err(dbr, dbr_w) <= 2e-5 and rel_err(dbi, dbi_w) <= 2e-5
     assert rel_err(nchw(dx), dx_w) <= 2e-5
+    if (H, W) == (OH * stride[0], OW * stride[1]):      # the phase form (no zero insertion): FFMA and tcgen05 kind::tf32
+        pp = T.PhasePack(w_r, w_i, stride, "cuda", want_tf32=True)
+        dxp = ops.cconv(pp, dyc, None, torch.empty(B, H, W, cin, 2, dtype=torch.float32, device="cuda"))
+        assert rel_err(nchw(dxp), dx_w) <= 2e-5
+        if cout % 4 == 0 and 2 * cin <= 256:
+            dxt = ops.cconv(pp, dyc, None, torch.empty(B, H, W, cin, 2, dtype=torch.float32, device="cuda"), use_tc=True)
+            assert rel_err(nchw(dxt), dx_w) <= 2e-3
     if cin == 1:      # encoder[0]: the direct gather kernel on the raw weights
         dx1 = T.cconv_dgrad_cin1(dyc, w_r.cuda(), w_i.cuda(), H, W, stride)
         assert rel_err(nchw(dx1), dx_w) <= 2e-5

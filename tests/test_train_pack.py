@@ -41,3 +41,35 @@ def test_symbolic_dgrad_operands_equal_dgrad_conv(cin, cout, k, transposed):
     pk = T.dgrad_conv(w_r, w_i, transposed=transposed, device="cpu")
     sy = TP.sym_dgrad(*syms, transposed=transposed)
     assert torch.allclose(sy["w_ffma"].evaluate(flat).float(), pk.w_ffma, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride", [(8, 16, 7, (2, 2)), (16, 32, 5, (2, 2)), (64, 128, 3, (2, 1))])
+def test_symbolic_strided_dgrad_operands_equal_phase_pack(cin, cout, k, stride):
+    g = torch.Generator().manual_seed(cin + cout)
+    (w_r, w_i), syms, flat = _leafs([(cout, cin, k, k), (cout, cin, k, k)], g)
+    pk = T.PhasePack(w_r, w_i, stride, "cpu", want_tf32=True)
+    sy = TP.sym_dgrad_strided(*syms, stride=stride, tf32=True)
+    assert tuple(sy["w_ffma"].shape) == tuple(pk.w_ffma.shape) and tuple(sy["w_tc32"].shape) == tuple(pk.w_tc32.shape)
+    assert torch.allclose(sy["w_ffma"].evaluate(flat).float(), pk.w_ffma, rtol=1e-6, atol=1e-7)
+    assert torch.allclose(packing.round_tf32(sy["w_tc32"].evaluate(flat).float()), pk.w_tc32, rtol=1e-6, atol=1e-7)
+    # the phase form computes the same data gradient as autograd (a CPU evaluation of the operand semantics)
+    x = torch.randn(1, 2 * cin, 8, 12, generator=g, dtype=torch.float64)
+    Wp = torch.cat([torch.cat([w_r, -w_i], 1), torch.cat([w_i, w_r], 1)], 0).double()
+    OH, OW = (8 + 2 * (k // 2) - k) // stride[0] + 1, (12 + 2 * (k // 2) - k) // stride[1] + 1
+    dY = torch.randn(1, 2 * cout, OH, OW, generator=g, dtype=torch.float64)
+    want = torch.nn.grad.conv2d_input(x.shape, Wp, dY, stride=stride, padding=k // 2)       # channels [re block | im block]
+    got = torch.zeros(1, 8, 12, cin, 2, dtype=torch.float64)
+    dyc = torch.stack([dY[0, :cout], dY[0, cout:]], -1).permute(1, 2, 0, 3)                 # (OH, OW, cout, 2)
+    W4 = pk.w_ffma.double()                                                                # [p][t][k = (co, ri)][n_pad]
+    for ph in range(stride[0]):
+        for pw in range(stride[1]):
+            p = ph * stride[1] + pw
+            for t in range(pk.ntaps):
+                d_y, d_x = pk.dy[p * pk.ntaps + t], pk.dx[p * pk.ntaps + t]
+                for y in range(8 // stride[0]):
+                    for xx in range(12 // stride[1]):
+                        if 0 <= y + d_y < OH and 0 <= xx + d_x < OW:
+                            v = dyc[y + d_y, xx + d_x].reshape(-1) @ W4[p, t][:, :2 * cin]
+                            got[0, y * stride[0] + ph, xx * stride[1] + pw] += v.reshape(cin, 2)
+    want_cl = torch.stack([want[0, :cin], want[0, cin:]], -1).permute(1, 2, 0, 3)
+    assert torch.allclose(got[0], want_cl, rtol=1e-9, atol=1e-9)
