@@ -395,7 +395,7 @@ def ncu_family_summary():
     summary is committed."""
     import csv
     import glob
-    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")) if "_real_" not in os.path.basename(f))
+    files = sorted(f for f in glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.csv")) if "_real_" not in os.path.basename(f) and "_train_" not in os.path.basename(f))
     if not files:
         return None, None, None
     rows = list(csv.reader(open(files[-1])))
@@ -407,7 +407,7 @@ def ncu_family_summary():
         ip = next(i for i, h in enumerate(hdr) if h.startswith("tensor_pipe_pct"))
     except StopIteration:
         return None, None, None
-    scale = 1e6 if "Mbyte" in hdr[ir] else (1e9 if "Gbyte" in hdr[ir] else (1e3 if "Kbyte" in hdr[ir] else 1.0))
+    unit = lambda h: 1e6 if "Mbyte" in h else (1e9 if "Gbyte" in h else (1e3 if "Kbyte" in h else 1.0))   # noqa: E731
     in_lstm, vals, tw, tt = False, [], 0.0, 0.0
     for r in rows[1:]:
         k = r[1]
@@ -416,7 +416,7 @@ def ncu_family_summary():
         elif "lstm_combine" in k:
             in_lstm = False
         elif ("cconv_tc_kernel" in k and not in_lstm) or "cconv_strip_kernel" in k:
-            vals.append((float(r[ir]) + float(r[iw])) * scale)
+            vals.append(float(r[ir]) * unit(hdr[ir]) + float(r[iw]) * unit(hdr[iw]))
             tw += float(r[it]) * float(r[ip])
             tt += float(r[it])
     if not vals:
@@ -557,6 +557,35 @@ def measure_roofline(plan, args, B, T, clocks=None):
         roof["stages"] = stages
         roof["hbm_peak_source"] = hbm_src + f"; frac_vs_8tbs = against the {HBM_SPEC_GBS / 1e3:g} TB/s the north star names"
     return roof, stage_ms
+
+
+def ncu_train_summary():
+    """Newest committed `*_train_ncu_summary.csv` (tools/gpu_train_prof.sh): for the tcgen05 GEMM kernels of the training step
+    (cconv_tc_kernel, wgrad_tc_kernel) the mean DRAM bytes per launch and the time-weighted tensor-pipe %."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_train_ncu_summary.csv")))
+    if not files:
+        return None, None, None
+    rows = list(csv.reader(open(files[-1])))
+    hdr = rows[0]
+    try:
+        ir = next(i for i, h in enumerate(hdr) if h.startswith("dram_read_MB"))
+        iw = next(i for i, h in enumerate(hdr) if h.startswith("dram_write_MB"))
+        it = next(i for i, h in enumerate(hdr) if h.startswith("time_us"))
+        ip = next(i for i, h in enumerate(hdr) if h.startswith("tensor_pipe_pct"))
+    except StopIteration:
+        return None, None, None
+    unit = lambda h: 1e6 if "Mbyte" in h else (1e9 if "Gbyte" in h else (1e3 if "Kbyte" in h else 1.0))   # noqa: E731
+    vals, tw, tt = [], 0.0, 0.0
+    for r in rows[1:]:
+        if "cconv_tc_kernel" in r[1] or "wgrad_tc_kernel" in r[1]:
+            vals.append(float(r[ir]) * unit(hdr[ir]) + float(r[iw]) * unit(hdr[iw]))
+            tw += float(r[it]) * float(r[ip])
+            tt += float(r[it])
+    if not vals:
+        return None, None, None
+    return sum(vals) / len(vals), (tw / tt if tt else None), os.path.relpath(files[-1], ROOT)
 
 
 def train_metric():
@@ -704,7 +733,7 @@ def run_train(args, rank, local_rank, world):
                 "achieved": ach, "peak": bf16 / 2, "unit": "TFLOP/s", "frac": ach / (bf16 / 2),
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops / 2 (kind::tf32 issues at half the kind::f16 rate)" if peaks else "fallback 1663 / 2",
                 "flops_per_step": 3 * dense, "flop_basis": "dense formulation, forward + dgrad + wgrad = 3 x forward", "family_ms": fam_ms,
-                "traffic": None,
+                "traffic": ncu_train_summary()[0], "tensor_pipe_pct": ncu_train_summary()[1], "ncu_summary": ncu_train_summary()[2],
                 "stage_ms": {"forward": ev[0].elapsed_time(ev[1]), "backward": ev[1].elapsed_time(ev[2]), "allreduce_clip_adam": ev[2].elapsed_time(ev[3])}}
     if rank != 0:
         if world > 1:

@@ -302,6 +302,64 @@ def test_training_step_with_dropout_runs_and_is_reproducible():
     assert abs(l1 - ref) < 3.0
 
 
+def test_gradient_is_the_directional_derivative_of_the_loss():
+    """Size-independent property (no fixture): along a random direction v in parameter space, the hand-written backward's <grad, v>
+    equals the central finite difference of the forward's loss, (L(theta + h v) - L(theta - h v)) / 2h — fp32 mode, batch 4 x 256
+    frames, dropout off, BatchNorm on batch statistics."""
+    import dcsnet_b200  # noqa: F401
+    from dcsnet_b200 import config as cfg, c_network, train_engine
+    hp = dict(cfg.hparams)
+    hp["dropout_conv"], hp["dropout_fc"] = 0.0, 0.0
+    net = c_network.C_NETWORK(cfg.config, hp, 0).cuda()
+    clean, noise, noisy = O.synthetic_audio(4, 32 * 255, seed=5)
+    specs = (O.stft(noise).cuda(), O.stft(noisy).cuda(), O.stft(clean).cuda())
+    step = train_engine.TrainStep(net, "dcs")
+    step.forward(*specs)
+    step.backward()
+    torch.cuda.synchronize()
+    params = [(k, p) for k, p in net.named_parameters() if p.grad is not None]
+    g = torch.Generator().manual_seed(9)
+    # the direction: random signs scaled to each tensor's gradient, so that every layer contributes to <grad, v>
+    v = {k: (torch.randint(0, 2, p.shape, generator=g).float() * 2 - 1).cuda() * p.grad.abs().mean().clamp_min(1e-12) for k, p in params}
+    analytic = sum(float((p.grad.double() * v[k].double()).sum()) for k, p in params)
+    base = {k: p.detach().clone() for k, p in params}
+    h = 2e-3 / max(float(torch.sqrt(sum((t.double() ** 2).sum() for t in v.values()))), 1e-30)
+    losses = []
+    for sgn in (1.0, -1.0):
+        with torch.no_grad():
+            for k, p in params:
+                p.copy_(base[k] + sgn * h * v[k])
+        losses.append(float(step.forward(*specs)["train_loss"].double()))
+    numeric = (losses[0] - losses[1]) / (2 * h)
+    assert abs(numeric - analytic) <= 3e-2 * abs(analytic), (numeric, analytic)
+
+
+def test_full_size_training_step_is_deterministic_and_descends():
+    """BASELINE configs[4] size (batch 32 x 3.998 s, tensor-core mode, dropout on): two runs from the same seed give bit-identical
+    losses and gradients (every reduction is two-stage in a fixed order), and three optimizer steps on the same batch lower the loss."""
+    import dcsnet_b200  # noqa: F401
+    from dcsnet_b200 import config as cfg, c_network, ops, train_engine
+    clean, noise, noisy = O.synthetic_audio(32, 32 * 1999, seed=21)
+    specs = [ops.stft(t.cuda()) for t in (noise, noisy, clean)]
+    runs = []
+    for _ in range(2):
+        net = c_network.C_NETWORK(cfg.config, dict(cfg.hparams), 0).cuda()
+        step = train_engine.TrainStep(net, "dcs", mode="tf32", seed=3).init_optimizer()
+        out = step.forward(*specs)
+        step.backward()
+        torch.cuda.synchronize()
+        runs.append((float(out["train_loss"]), step.buckets.flat.clone(), step, net))
+    assert runs[0][0] == runs[1][0] and torch.equal(runs[0][1], runs[1][1])
+    assert bool(torch.isfinite(runs[0][1]).all())
+    step = runs[1][2]
+    losses = [runs[1][0]]
+    step.optimizer_step()
+    for _ in range(2):
+        losses.append(float(step.step(*specs)["train_loss"]))
+    assert losses[2] < losses[0], losses
+    del runs
+
+
 @pytest.mark.parametrize("cin,cout,k,stride,B,H,W", [(64, 128, 3, (2, 1), 2, 16, 70), (32, 64, 5, (2, 1), 3, 8, 130), (128, 128, 3, (2, 1), 2, 8, 64),
                                                      (64, 64, 3, (1, 1), 2, 6, 33)])
 def test_conv_wgrad_on_tcgen05(cin, cout, k, stride, B, H, W):
