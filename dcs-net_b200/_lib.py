@@ -57,7 +57,8 @@ class CbnTrainParams(C.Structure):
 
 class CbnTrainBwdParams(C.Structure):
     _fields_ = [("x", _vp), ("dy", _vp), ("dx", _vp), ("n_pix", _i64), ("channels", _i),
-                ("saved", _vp), ("weight", _vp), ("dweight", _vp), ("dbias", _vp), ("workspace", _vp), ("workspace_bytes", _i64)]
+                ("saved", _vp), ("weight", _vp), ("dweight", _vp), ("dbias", _vp), ("workspace", _vp), ("workspace_bytes", _i64),
+                ("conv_bias_grad_r", _vp), ("conv_bias_grad_i", _vp)]
 
 
 class CwgradParams(C.Structure):

@@ -177,14 +177,40 @@ __global__ void cbn_bwd_finalize_kernel(const double* __restrict__ partial, int 
   k[9] = (float)(-(Q01 * mr + Q11 * mi) - (P10 * gmr + P11 * gmi));
 }
 
-__global__ void cbn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ coef,
-                                     float* __restrict__ dx, int64_t n, int C) {
+// dx = P dy + Q x + k; with `colsum` the per-channel sums of dx (the bias gradient of the convolution in front: exactly zero in exact
+// arithmetic, round-off in fp32 — reported as computed, not assumed) go to colsum[cta][C][2] (a thread keeps ONE channel:
+// gridDim.x * 256 is a multiple of C)
+__global__ void __launch_bounds__(256) cbn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ coef,
+                                                            float* __restrict__ dx, int64_t n, int C, double* __restrict__ colsum) {
+  __shared__ double red[256][2];
+  double s0 = 0.0, s1 = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float* k = coef + 10 * (int)(i % C);
     const float2 xv = reinterpret_cast<const float2*>(x)[i], g = reinterpret_cast<const float2*>(dy)[i];
-    reinterpret_cast<float2*>(dx)[i] = make_float2(k[0] * g.x + k[1] * g.y + k[4] * xv.x + k[5] * xv.y + k[8],
-                                                   k[2] * g.x + k[3] * g.y + k[6] * xv.x + k[7] * xv.y + k[9]);
+    const float2 o = make_float2(k[0] * g.x + k[1] * g.y + k[4] * xv.x + k[5] * xv.y + k[8],
+                                 k[2] * g.x + k[3] * g.y + k[6] * xv.x + k[7] * xv.y + k[9]);
+    reinterpret_cast<float2*>(dx)[i] = o;
+    s0 += o.x; s1 += o.y;
   }
+  if (!colsum) return;
+  red[threadIdx.x][0] = s0; red[threadIdx.x][1] = s1;
+  __syncthreads();
+  if (threadIdx.x < C) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int l = threadIdx.x; l < 256; l += C) { t0 += red[l][0]; t1 += red[l][1]; }
+    colsum[((int64_t)blockIdx.x * C + threadIdx.x) * 2] = t0;
+    colsum[((int64_t)blockIdx.x * C + threadIdx.x) * 2 + 1] = t1;
+  }
+}
+// conv_r.bias.grad = S.re + S.im, conv_i.bias.grad = S.im - S.re of the convolution in front (complexPyTorch's bias rule), one warp per channel
+__global__ void cbn_bwd_colsum_finalize_kernel(const double* __restrict__ colsum, int n_ctas, int C, float* __restrict__ db_r, float* __restrict__ db_i) {
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (c >= C) return;
+  double sr = 0.0, si = 0.0;
+  for (int k = lane; k < n_ctas; k += 32) { sr += colsum[((int64_t)k * C + c) * 2]; si += colsum[((int64_t)k * C + c) * 2 + 1]; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { sr += __shfl_xor_sync(0xffffffffu, sr, o); si += __shfl_xor_sync(0xffffffffu, si, o); }
+  if (lane == 0) { db_r[c] = (float)(sr + si); db_i[c] = (float)(si - sr); }
 }
 
 // ------------------------------------------------------------------------------------------------ SI-SNR value + gradient
@@ -356,9 +382,15 @@ extern "C" int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream
   cbn_bwd_finalize_kernel<<<p->channels, 64, 0, s>>>(partial, nc, p->channels, (double)p->n_pix, p->saved, p->weight, p->dweight, p->dbias, coef);
   DCS_LAUNCHED();
   const int64_t n = p->n_pix * p->channels;
-  const int g = (int)std::min<int64_t>((n + 255) / 256, (int64_t)num_sms() * 16);
-  cbn_bwd_apply_kernel<<<g, 256, 0, s>>>(p->x, p->dy, coef, p->dx, n, p->channels);
+  const bool cs = p->conv_bias_grad_r && p->conv_bias_grad_i;
+  // with the column sums the per-CTA partials reuse the (consumed) moment partials: at most nc CTAs
+  const int g = (int)std::min<int64_t>((n + 255) / 256, cs ? std::max<int64_t>(1, (int64_t)nc * 4) : (int64_t)num_sms() * 16);
+  cbn_bwd_apply_kernel<<<g, 256, 0, s>>>(p->x, p->dy, coef, p->dx, n, p->channels, cs ? partial : nullptr);
   DCS_LAUNCHED();
+  if (cs) {
+    cbn_bwd_colsum_finalize_kernel<<<(p->channels + 7) / 8, 256, 0, s>>>(partial, g, p->channels, p->conv_bias_grad_r, p->conv_bias_grad_i);
+    DCS_LAUNCHED();
+  }
   return 0;
 }
 

@@ -670,17 +670,46 @@ __global__ void __launch_bounds__(256) att_bwd_w7_finalize_kernel(const double* 
   }
 }
 
-// pass 2: dstats = conv7^T(dspre); du = conj(s) dy + dmean / C + [argmax] dmax; dx = conj(a) du; da partial sums per CTA
-__global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
-                                                         const float2* __restrict__ gate_s, const float2* __restrict__ dspre,
-                                                         const float* __restrict__ w7, float2* __restrict__ dx, double* __restrict__ da_partial,
-                                                         int H, int W, int C, int G) {
-  __shared__ float2 gs[256];
+// transposed 7x7 gate conv of the gate gradient: dstats[q] = (d mean.re, d mean.im, d max.re, d max.im) = sum_tap W_tap^H dspre(q - off_tap),
+// one thread per pixel on a 16 x 64 tile with a 3-pixel halo of dspre in shared memory
+constexpr int kDsTH = 16, kDsTW = 64;
+__global__ void __launch_bounds__(256) att_bwd_dstats_kernel(const float2* __restrict__ dspre, const float* __restrict__ w7, float4* __restrict__ dstats,
+                                                             int H, int W) {
+  __shared__ float2 t[kDsTH + 6][kDsTW + 6];
   __shared__ float4 wq[49];
+  const int b = blockIdx.z, y0 = blockIdx.y * kDsTH, x0 = blockIdx.x * kDsTW;
+  for (int i = threadIdx.x; i < 49; i += 256) wq[i] = make_float4(w7[i], w7[49 + i], w7[98 + i], w7[147 + i]);   // Wr mean, Wr max, Wi mean, Wi max
+  for (int i = threadIdx.x; i < (kDsTH + 6) * (kDsTW + 6); i += 256) {
+    const int r = i / (kDsTW + 6), c = i % (kDsTW + 6);
+    const int yy = y0 + r - 3, xx = x0 + c - 3;
+    t[r][c] = ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? dspre[((int64_t)b * H + yy) * W + xx] : make_float2(0.f, 0.f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < kDsTH * kDsTW; i += 256) {
+    const int r = i / kDsTW, c = i % kDsTW;
+    if (y0 + r >= H || x0 + c >= W) continue;
+    float mr = 0.f, mi = 0.f, xr = 0.f, xi = 0.f;
+#pragma unroll
+    for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < 7; ++kx) {
+        const float2 g = t[r + 6 - ky][c + 6 - kx];          // dspre(q - (ky - 3, kx - 3))
+        const float4 wv = wq[ky * 7 + kx];
+        mr += wv.x * g.x + wv.z * g.y;  mi += -wv.z * g.x + wv.x * g.y;
+        xr += wv.y * g.x + wv.w * g.y;  xi += -wv.w * g.x + wv.y * g.y;
+      }
+    dstats[((int64_t)b * H + y0 + r) * W + x0 + c] = make_float4(mr, mi, xr, xi);
+  }
+}
+
+// pass 2: du = conj(s) dy + dmean / C + [argmax] dmax; dx = conj(a) du; da partial sums per CTA
+__global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
+                                                         const float2* __restrict__ gate_s, const float4* __restrict__ dstats,
+                                                         float2* __restrict__ dx, double* __restrict__ da_partial, int H, int W, int C, int G) {
+  __shared__ float2 gs[256];
   __shared__ float red[256][2];
   const int b = blockIdx.y, hw = H * W;
   for (int c = threadIdx.x; c < C; c += 256) gs[c] = gate_c[(int64_t)b * C + c];
-  for (int i = threadIdx.x; i < 49; i += 256) wq[i] = make_float4(w7[i], w7[49 + i], w7[98 + i], w7[147 + i]);   // Wr mean, Wr max, Wi mean, Wi max
   __syncthreads();
   const int sub = threadIdx.x % G, grp = threadIdx.x / G, groups = 256 / G;
   const int64_t base = (int64_t)b * hw;
@@ -692,37 +721,22 @@ __global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restric
   for (int pbase = blockIdx.x * groups; pbase < hw; pbase += gridDim.x * groups) {
     const int p = pbase + grp;
     const bool ok = p < hw;
-    // transposed 7x7 conv: dstats[ch](q) = sum_tap (conj-transposed block) dspre(q - off_tap); taps split over the G lanes
-    float mr = 0.f, mi = 0.f, xr = 0.f, xi = 0.f;     // d mean (re, im), d max (re, im)
-    if (ok) {
-      const int py = p / W, px = p % W;
-      for (int t = sub; t < 49; t += G) {
-        const int qy = py - (t / 7 - 3), qx = px - (t % 7 - 3);
-        if ((unsigned)qy < (unsigned)H && (unsigned)qx < (unsigned)W) {
-          const float2 g = dspre[base + (int64_t)qy * W + qx];
-          const float4 wv = wq[t];
-          mr += wv.x * g.x + wv.z * g.y;  mi += -wv.z * g.x + wv.x * g.y;
-          xr += wv.y * g.x + wv.w * g.y;  xi += -wv.w * g.x + wv.y * g.y;
-        }
-      }
-    }
     // u, and the arg max of Re u / Im u over the channels (first index on ties, like torch.max)
-    float2 uv[8], gv[8];
+    float2 uv[8], gv[8], xv8[8];
     float bre = -INFINITY, bim = -INFINITY;
     int are = 0x7fffffff, aim = 0x7fffffff;
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int c = sub + k * G;
       if (k < nch && ok && c < C) {
-        uv[k] = cmul(gs[c], x[(base + p) * C + c]);
+        xv8[k] = x[(base + p) * C + c];
+        uv[k] = cmul(gs[c], xv8[k]);
         gv[k] = dy[(base + p) * C + c];
         if (uv[k].x > bre) { bre = uv[k].x; are = c; }
         if (uv[k].y > bim) { bim = uv[k].y; aim = c; }
       }
     }
     for (int o = G >> 1; o; o >>= 1) {
-      mr += __shfl_xor_sync(0xffffffffu, mr, o); mi += __shfl_xor_sync(0xffffffffu, mi, o);
-      xr += __shfl_xor_sync(0xffffffffu, xr, o); xi += __shfl_xor_sync(0xffffffffu, xi, o);
       const float ore = __shfl_xor_sync(0xffffffffu, bre, o), oim = __shfl_xor_sync(0xffffffffu, bim, o);
       const int oare = __shfl_xor_sync(0xffffffffu, are, o), oaim = __shfl_xor_sync(0xffffffffu, aim, o);
       if (ore > bre || (ore == bre && oare < are)) { bre = ore; are = oare; }
@@ -730,15 +744,17 @@ __global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restric
     }
     if (ok) {
       const float2 s = gate_s[base + p];
+      const float4 ds = dstats[base + p];
+      const float mr = ds.x * invC, mi = ds.y * invC;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const int c = sub + k * G;
         if (k < nch && c < C) {
           const float2 g = gv[k];
-          float2 du = make_float2(s.x * g.x + s.y * g.y + mr * invC, s.x * g.y - s.y * g.x + mi * invC);   // conj(s) g + dmean / C
-          if (c == are) du.x += xr;
-          if (c == aim) du.y += xi;
-          const float2 xv = x[(base + p) * C + c], a = gs[c];
+          float2 du = make_float2(s.x * g.x + s.y * g.y + mr, s.x * g.y - s.y * g.x + mi);   // conj(s) g + dmean / C
+          if (c == are) du.x += ds.z;
+          if (c == aim) du.y += ds.w;
+          const float2 xv = xv8[k], a = gs[c];
           da[k].x += xv.x * du.x + xv.y * du.y;        // conj(x) du
           da[k].y += xv.x * du.y - xv.y * du.x;
           dx[(base + p) * C + c] = make_float2(a.x * du.x + a.y * du.y, a.x * du.y - a.y * du.x);   // conj(a) du
@@ -1255,7 +1271,8 @@ extern "C" int64_t dcs_attention_bwd_workspace_bytes(int batch, int h, int w, in
   if (batch <= 0 || h <= 0 || w <= 0 || channels <= 0 || channels > 256 || (channels & (channels - 1)) || reduced <= 0 || reduced > 16) return -1;
   const int G = att_G(channels), chunks = att_chunks(h * w, G);
   const int64_t tiles = (int64_t)batch * ((h + kW7TH - 1) / kW7TH) * ((w + kW7TW - 1) / kW7TW);
-  return (int64_t)batch * chunks * channels * 2 * sizeof(double) + tiles * 196 * sizeof(double) + (int64_t)(batch + 1) * 4 * reduced * channels * sizeof(float);
+  return (int64_t)batch * chunks * channels * 2 * sizeof(double) + tiles * 196 * sizeof(double) + (int64_t)(batch + 1) * 4 * reduced * channels * sizeof(float) +
+         (int64_t)batch * h * w * 4 * sizeof(float) + 16;
 }
 
 extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream) {
@@ -1279,7 +1296,10 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   DCS_LAUNCHED();
   att_bwd_w7_finalize_kernel<<<196, 256, 0, s>>>(w7_partial, n_tiles, p->dw7_r, p->dw7_i);
   DCS_LAUNCHED();
-  att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (const float2*)p->dspre, p->w7, (float2*)p->dx, da_partial, p->h, p->w, C, G);
+  float4* dstats = reinterpret_cast<float4*>(((uintptr_t)(wpart + (int64_t)(p->batch + 1) * 4 * R * C) + 15) & ~(uintptr_t)15);
+  att_bwd_dstats_kernel<<<dim3((p->w + kDsTW - 1) / kDsTW, (p->h + kDsTH - 1) / kDsTH, p->batch), 256, 0, s>>>((const float2*)p->dspre, p->w7, dstats, p->h, p->w);
+  DCS_LAUNCHED();
+  att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, dstats, (float2*)p->dx, da_partial, p->h, p->w, C, G);
   DCS_LAUNCHED();
   att_bwd_gate_kernel<<<p->batch, 256, 0, s>>>(da_partial, chunks, gc, (const long long*)p->sums, 1.f / (float)hw, C, R, p->w1_r, p->w1_i, p->w2_r,
                                                p->w2_i, (float2*)p->chan_const, wpart);

@@ -254,9 +254,12 @@ class TrainStep:
                     dw2_r=g(chan_prefix + "fc.2.conv_r.weight"), dw2_i=g(chan_prefix + "fc.2.conv_i.weight"),
                     dw7_r=g(spat_prefix + "conv1.conv_r.weight"), dw7_i=g(spat_prefix + "conv1.conv_i.weight"))
 
-    def _bn_bwd(self, x, dz, prefix, key):
+    def _bn_bwd(self, x, dz, prefix, key, conv_bias=None):
+        """Train-mode BN backward; conv_bias = (prefix, names) of the convolution in front: its two bias gradients (per-channel sums of
+        dx) come out of the same pass."""
         m = self.model.get_submodule(prefix)
-        dx, dw, db = T.cbn_train_bwd(x, dz, self.saved[key], m.weight.detach())
+        cb = None if conv_bias is None else (self._grad(conv_bias[0] + conv_bias[1][0] + ".bias"), self._grad(conv_bias[0] + conv_bias[1][1] + ".bias"))
+        dx, dw, db = T.cbn_train_bwd(x, dz, self.saved[key], m.weight.detach(), conv_bias_grads=cb)
         self._grad(prefix + ".weight").copy_(dw)
         self._grad(prefix + ".bias").copy_(db)
         return dx
@@ -266,7 +269,7 @@ class TrainStep:
         copies of the two operands (fp32 accumulation over the pixels); encoder[0] / decoder[6] stay on the few-channel CUDA-core kernel."""
         return self.mode == "tf32" and cin >= 8 and cout >= 8
 
-    def _conv_param_grads(self, x, dpre, prefix, names, kernel, stride, transposed):
+    def _conv_param_grads(self, x, dpre, prefix, names, kernel, stride, transposed, bias=True):
         if self._wgrad_on_tc(x.shape[3], dpre.shape[3]):
             x = x if x.dtype == torch.bfloat16 else T.to_h16(x)
             dy16 = T.to_h16(dpre)
@@ -274,7 +277,8 @@ class TrainStep:
             dy16 = dpre
         T.cwgrad_generic(x, dy16, kernel, stride, transposed=transposed, dw_r=self._grad(prefix + names[0] + ".weight"),
                          dw_i=self._grad(prefix + names[1] + ".weight"))
-        T.colsum(dpre.view(-1, 2 * dpre.shape[-2]), mode=1, out0=self._grad(prefix + names[0] + ".bias"), out1=self._grad(prefix + names[1] + ".bias"))
+        if bias:
+            T.colsum(dpre.view(-1, 2 * dpre.shape[-2]), mode=1, out0=self._grad(prefix + names[0] + ".bias"), out1=self._grad(prefix + names[1] + ".bias"))
 
     def _lstm_backward(self, g_lat):
         """g_lat (B, S, 128, 2): gradient of the ComplexLSTM output -> gradient of its input (B, S, 128, 2); parameter gradients of
@@ -339,7 +343,8 @@ class TrainStep:
                 dxa, cc, _ = T.attention_bwd(att["x"], g.contiguous(), att["gate_c"], att["stats"], att["gate_s"], att["sums"], self.dec_ca[i],
                                              self.dec_sa[i], grads=self._att_grads(f"decoder_attention.{2 * i}.", f"decoder_attention.{2 * i + 1}."))
                 dz = T.act_bwd(att["x"], dxa, L.ACT_LRELU, None, cc)
-                dpre, prefix = self._bn_bwd(sv[f"dec{i}_pre"], dz, f"decoder.{i}.1", f"dec{i}"), f"decoder.{i}.0."
+                prefix = f"decoder.{i}.0."
+                dpre = self._bn_bwd(sv[f"dec{i}_pre"], dz, f"decoder.{i}.1", f"dec{i}", conv_bias=(prefix, ("conv_tran_r", "conv_tran_i")))
             d_in, skip = sv["dec_in"][i], sv["skip"][i]
             if i == Lr - 1 and dpre.shape[3] == 1 and UPSAMPLE[i] == (2, 2) and d_in.shape[3] + skip.shape[3] <= 16:
                 # decoder[6]: one output channel -> data, weight and bias gradients in ONE kernel (no up-sampled input, no full-resolution dgrad)
@@ -354,7 +359,7 @@ class TrainStep:
                 continue
             on_tc = self._wgrad_on_tc(d_in.shape[3] + skip.shape[3], dpre.shape[3])
             z = T.upcat_fwd(d_in, skip, UPSAMPLE[i], dtype=torch.bfloat16 if on_tc else torch.float32)
-            self._conv_param_grads(z, dpre, prefix, ("conv_tran_r", "conv_tran_i"), 3, (1, 1), True)
+            self._conv_param_grads(z, dpre, prefix, ("conv_tran_r", "conv_tran_i"), 3, (1, 1), True, bias=i == Lr - 1)
             del z
             g, g_skip = self._dec_dgrad(i, dpre, d_in.shape[3], skip.shape[3])
             if i == Lr - 1:
@@ -381,9 +386,9 @@ class TrainStep:
             else:
                 tot = self._drop_bwd(T.act_bwd(None, g.contiguous(), L.ACT_NONE, dxs, ccs), f"enc{i}")
                 dz = T.act_bwd(y, tot, L.ACT_RELU)
-            dpre = self._bn_bwd(sv[f"enc{i}_pre"], dz, f"encoder.{i}.1", f"enc{i}")
+            dpre = self._bn_bwd(sv[f"enc{i}_pre"], dz, f"encoder.{i}.1", f"enc{i}", conv_bias=(f"encoder.{i}.0.", ("conv_r", "conv_i")))
             x_in = enc[i]
-            self._conv_param_grads(x_in, dpre, f"encoder.{i}.0.", ("conv_r", "conv_i"), KERNEL_E[i], STRIDE_E[i], False)
+            self._conv_param_grads(x_in, dpre, f"encoder.{i}.0.", ("conv_r", "conv_i"), KERNEL_E[i], STRIDE_E[i], False, bias=False)
             Hi, Wi = x_in.shape[1], x_in.shape[2]
             if x_in.shape[3] == 1:       # encoder[0]: one input channel -> the direct gather kernel on the raw weights
                 g = T.cconv_dgrad_cin1(dpre, self._params[f"encoder.{i}.0.conv_r.weight"].detach(), self._params[f"encoder.{i}.0.conv_i.weight"].detach(),

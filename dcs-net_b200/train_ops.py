@@ -48,8 +48,9 @@ def cbn_train_fwd(x, weight, bias, running_mean=None, running_covar=None, num_ba
 
 
 @ops._on_tensor_device
-def cbn_train_bwd(x, dy, saved, weight, workspace=None):
-    """Backward of cbn_train_fwd (no activation): x, dy fp32 (..., C, 2) -> (dx, dweight (C, 3), dbias (C, 2))."""
+def cbn_train_bwd(x, dy, saved, weight, workspace=None, conv_bias_grads=None):
+    """Backward of cbn_train_fwd (no activation): x, dy fp32 (..., C, 2) -> (dx, dweight (C, 3), dbias (C, 2)).  conv_bias_grads = (db_r,
+    db_i) (C,) each: also the bias gradients of the complex convolution in front (the per-channel sums of dx), from the same pass."""
     L.require_cuda(x, dy, saved, weight)
     Cn = x.shape[-2]
     n_pix = x.numel() // (2 * Cn)
@@ -58,8 +59,9 @@ def cbn_train_bwd(x, dy, saved, weight, workspace=None):
     dw = torch.empty(Cn, 3, dtype=torch.float32, device=x.device)
     db = torch.empty(Cn, 2, dtype=torch.float32, device=x.device)
     ws = workspace if workspace is not None else cbn_train_workspace(n_pix, Cn, x.device)
+    cb = conv_bias_grads or (None, None)
     p = L.CbnTrainBwdParams(L.ptr(x), L.ptr(dy), L.ptr(dx), n_pix, Cn, L.ptr(saved), L.ptr(weight.contiguous()), L.ptr(dw), L.ptr(db),
-                            L.ptr(ws), ws.numel())
+                            L.ptr(ws), ws.numel(), L.ptr(cb[0]), L.ptr(cb[1]))
     L.check(L.lib().dcs_cbn_train_bwd(C.byref(p), L.stream_ptr()), "dcs_cbn_train_bwd")
     return dx, dw, db
 

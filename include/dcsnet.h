@@ -372,6 +372,8 @@ int dcs_cbn_train_fwd(const dcs_cbn_train_params* p, void* stream);
 typedef struct {
   const float* x; const float* dy; float* dx; int64_t n_pix; int channels;
   const float* saved; const float* weight; float* dweight; float* dbias; void* workspace; int64_t workspace_bytes;
+  float* conv_bias_grad_r; float* conv_bias_grad_i;   /* optional (both or neither), C floats each: conv_r / conv_i .bias.grad of the convolution
+                                                         in front of this BatchNorm = per-channel sums of dx (S.re + S.im, S.im - S.re) */
 } dcs_cbn_train_bwd_params;
 int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream);
 

@@ -59,6 +59,15 @@ def test_train_mode_complex_batchnorm_forward_and_backward(shape):
     torch.cuda.synchronize()
     assert rel_err(nchw(dx), dx_w) <= 5e-5
     assert rel_err(dw, dw_w) <= 2e-5 and rel_err(db, db_w) <= 2e-5
+    # the bias gradients of the convolution in front (per-channel sums of dx: zero up to round-off) from the same pass
+    cbr, cbi = torch.empty(C, device="cuda"), torch.empty(C, device="cuda")
+    dx2, _, _ = T.cbn_train_bwd(cl(x).cuda(), cl(dy).cuda(), saved, sd["p.weight"].cuda(), conv_bias_grads=(cbr, cbi))
+    torch.cuda.synchronize()
+    assert torch.equal(dx2, dx)
+    sums = dx.double().sum(dim=(0, 1, 2)).cpu()                         # (C, 2)
+    scale = float(dx.abs().double().sum()) / C
+    assert float((cbr.cpu().double() - (sums[:, 0] + sums[:, 1])).abs().max()) <= 1e-6 * scale
+    assert float((cbi.cpu().double() - (sums[:, 1] - sums[:, 0])).abs().max()) <= 1e-6 * scale
     # and with a fused activation the forward equals activation(BN(x))
     y2, _, _ = T.cbn_train_fwd(cl(x).cuda(), sd["p.weight"].cuda(), sd["p.bias"].cuda(), act=1)
     assert rel_err(nchw(y2), O.crelu(want)) <= 2e-5
