@@ -57,6 +57,11 @@ except Exception:  # pragma: no cover - the image has no pytorch_lightning
         def log_dict(self, *a, **k):
             return None
 
+        # what Lightning's Trainer provides to the epoch-end hooks; a driver loop (or a test) sets them
+        current_epoch = 0
+        global_step = 0
+        logger = None
+
         @classmethod
         def load_from_checkpoint(cls, checkpoint_path, map_location=None, hparams_file=None, strict=True, **kwargs):
             """The LightningModule call test.py:20-26 makes: `C_NETWORK.load_from_checkpoint(config=, seed=, checkpoint_path=,
@@ -183,6 +188,39 @@ class _StepMixin:
             metrics = {'test_speech_loss': speech_loss, 'test_pesq': pesq_av, 'test_stoi': stoi_av}
             output = self._audio_dict(clean_audio, predict_clean_audio, noise_audio, noisy_audio)
         return output, metrics
+
+
+    def _epoch_end(self, step_outputs, prefix):
+        """validation_epoch_end / test_epoch_end (c_network.py:304-335, 374-398): average the per-batch metrics, log sample audio
+        (network_functions.epoch_end), log and return the averages."""
+        from .network_functions import epoch_end
+        audio = [o[0] for o in step_outputs]
+        metrics_list = [o[1] for o in step_outputs]
+        mean = lambda k: torch.stack([torch.as_tensor(x[k]) for x in metrics_list]).float().mean()   # noqa: E731
+        metrics = {}
+        if self._two_mask():
+            metrics[f'{prefix}_loss'], metrics[f'{prefix}_noise_loss'] = mean(f'{prefix}_loss'), mean(f'{prefix}_noise_loss')
+        for k in ('speech_loss', 'pesq', 'stoi'):
+            metrics[f'{prefix}_{k}'] = mean(f'{prefix}_{k}')
+        metrics['step'] = self.current_epoch
+        if self.logger is not None:
+            epoch_end(self, audio, prefix, variant=self.variant)
+        self.log_dict(metrics, on_epoch=True)
+        return metrics
+
+    def validation_epoch_end(self, validation_step_outputs):
+        return self._epoch_end(validation_step_outputs, "val")
+
+    def test_epoch_end(self, test_step_outputs):
+        return self._epoch_end(test_step_outputs, "test")
+
+    def on_after_backward(self):
+        """c_network.py:401-417: every 25 steps log the mean and the norm of all gradients."""
+        step = getattr(getattr(self, "trainer", None), "global_step", self.global_step)
+        if step % 25 == 0 and self.logger is not None:
+            vals = torch.cat([(p.grad if p.grad is not None else torch.zeros(1, device=p.device)).flatten().float() for p in self.parameters()])
+            self.logger.experiment.add_scalar("grad val avg", torch.mean(vals), global_step=step)
+            self.logger.experiment.add_scalar("grad norm", torch.linalg.norm(vals), global_step=step)
 
 
 class ComplexLSTM(torch.nn.Module):

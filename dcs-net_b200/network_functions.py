@@ -252,3 +252,21 @@ def test_batch_2_metric_loss(self, test_batch, test_idx, dtype, variant=None, me
 
 
 test_batch_2_metric_loss.__test__ = False   # not a pytest test
+
+
+def epoch_end(self, outputs, type, variant=None):
+    """network_functions.py:450-498: at the end of a validation / test epoch, log `config.val_log_sample_size` randomly chosen
+    utterances (clean, predicted clean, noise, [predicted noise], noisy) to the experiment logger as audio.  Host-side glue of the
+    Lightning layer: the draws go through numpy's global `random.choice` in the reference's order, so a seeded run
+    logs the same samples; `variant` replaces sys.argv[1]."""
+    from numpy import random
+    two_mask = _variant(self, variant) in ("dcs", "drs")
+    no_of_batches = len(outputs)
+    random_batches = random.choice(no_of_batches, size=min(self.config.val_log_sample_size, no_of_batches), replace=False)
+    keys = ['clean', 'predict_clean', 'noise'] + (['predict_noise'] if two_mask else []) + ['noisy']
+    no_of_samples = min([self.config.data_params['batch_size']] + [outputs[-1][k].shape[0] for k in keys])
+    random_samples = random.choice(no_of_samples, size=min(self.config.val_log_sample_size, no_of_samples), replace=False)
+    for i, ridx in enumerate(range(min(self.config.val_log_sample_size, no_of_samples))):
+        for k in keys:                                   # the reference's logging order: clean, predict_clean, noise, predict_noise, noisy
+            self.logger.experiment.add_audio("{}({})/{}".format(k, type, i), outputs[random_batches[ridx]][k][random_samples[ridx], :],
+                                             self.global_step, sample_rate=self.config.sr)
