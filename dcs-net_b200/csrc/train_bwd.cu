@@ -779,6 +779,95 @@ __global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restric
   }
 }
 
+// Few-channel tensors (C = 8, 16: the largest ones): ONE THREAD PER PIXEL with all C channels in registers — 16-byte loads, no
+// shuffles, a serial arg max — instead of C lanes per pixel (the C = 8 launches ran at a tenth of the HBM rate: 12 shuffles and a
+// strided loop per element).
+template <int C>
+__global__ void __launch_bounds__(256) att_bwd_ds_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float2* __restrict__ gate_c,
+                                                               const float2* __restrict__ gate_s, float2* __restrict__ dspre, int hw) {
+  __shared__ float2 gs[C];
+  const int b = blockIdx.y;
+  if (threadIdx.x < C) gs[threadIdx.x] = gate_c[(int64_t)b * C + threadIdx.x];
+  __syncthreads();
+  const int64_t base = (int64_t)b * hw;
+  for (int p = blockIdx.x * 256 + threadIdx.x; p < hw; p += gridDim.x * 256) {
+    float dr = 0.f, di = 0.f;
+#pragma unroll
+    for (int c = 0; c < C; c += 2) {
+      const float4 xv = x[(base + p) * (C / 2) + c / 2], g = dy[(base + p) * (C / 2) + c / 2];
+      const float2 u0 = cmul(gs[c], make_float2(xv.x, xv.y)), u1 = cmul(gs[c + 1], make_float2(xv.z, xv.w));
+      dr += u0.x * g.x + u0.y * g.y + u1.x * g.z + u1.y * g.w;
+      di += u0.x * g.y - u0.y * g.x + u1.x * g.w - u1.y * g.z;
+    }
+    const float2 sg = gate_s[base + p];
+    dspre[base + p] = make_float2(dr * sg.x * (1.f - sg.x), di * sg.y * (1.f - sg.y));
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) att_bwd_du_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float2* __restrict__ gate_c,
+                                                               const float2* __restrict__ gate_s, const float4* __restrict__ dstats,
+                                                               float4* __restrict__ dx, double* __restrict__ da_partial, int hw) {
+  __shared__ float2 gs[C];
+  __shared__ float red[8][C][2];
+  const int b = blockIdx.y, tid = threadIdx.x;
+  if (tid < C) gs[tid] = gate_c[(int64_t)b * C + tid];
+  __syncthreads();
+  const int64_t base = (int64_t)b * hw;
+  const float invC = 1.f / (float)C;
+  float2 da[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) da[c] = make_float2(0.f, 0.f);
+  for (int p = blockIdx.x * 256 + tid; p < hw; p += gridDim.x * 256) {
+    float2 xv[C], gv[C];
+#pragma unroll
+    for (int c = 0; c < C; c += 2) {
+      const float4 a4 = x[(base + p) * (C / 2) + c / 2], g4 = dy[(base + p) * (C / 2) + c / 2];
+      xv[c] = make_float2(a4.x, a4.y); xv[c + 1] = make_float2(a4.z, a4.w);
+      gv[c] = make_float2(g4.x, g4.y); gv[c + 1] = make_float2(g4.z, g4.w);
+    }
+    float bre = -INFINITY, bim = -INFINITY;
+    int are = 0, aim = 0;
+#pragma unroll
+    for (int c = 0; c < C; ++c) {                        // first index on ties, like torch.max
+      const float2 u = cmul(gs[c], xv[c]);
+      if (u.x > bre) { bre = u.x; are = c; }
+      if (u.y > bim) { bim = u.y; aim = c; }
+    }
+    const float2 s = gate_s[base + p];
+    const float4 ds = dstats[base + p];
+    const float mr = ds.x * invC, mi = ds.y * invC;
+    float2 o[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+      const float2 g = gv[c], a = gs[c];
+      float2 du = make_float2(s.x * g.x + s.y * g.y + mr, s.x * g.y - s.y * g.x + mi);
+      if (c == are) du.x += ds.z;
+      if (c == aim) du.y += ds.w;
+      da[c].x += xv[c].x * du.x + xv[c].y * du.y;
+      da[c].y += xv[c].x * du.y - xv[c].y * du.x;
+      o[c] = make_float2(a.x * du.x + a.y * du.y, a.x * du.y - a.y * du.x);
+    }
+#pragma unroll
+    for (int c = 0; c < C; c += 2) dx[(base + p) * (C / 2) + c / 2] = make_float4(o[c].x, o[c].y, o[c + 1].x, o[c + 1].y);
+  }
+  // da: warp xor-tree, then the 8 warps in a fixed order
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    float vr = da[c].x, vi = da[c].y;
+#pragma unroll
+    for (int o2 = 16; o2; o2 >>= 1) { vr += __shfl_xor_sync(0xffffffffu, vr, o2); vi += __shfl_xor_sync(0xffffffffu, vi, o2); }
+    if ((tid & 31) == 0) { red[tid >> 5][c][0] = vr; red[tid >> 5][c][1] = vi; }
+  }
+  __syncthreads();
+  if (tid < C) {
+    double sr = 0.0, si = 0.0;
+    for (int w = 0; w < 8; ++w) { sr += red[w][tid][0]; si += red[w][tid][1]; }
+    double* o = da_partial + (((int64_t)b * gridDim.x + blockIdx.x) * C + tid) * 2;
+    o[0] = sr; o[1] = si;
+  }
+}
+
 // the gate MLP's backward, one CTA per image: da -> dfc = 2 da (.) a (1 - a) -> W2^T, crelu mask, W1^T -> davg;
 // chan_const[b][c] = davg / (H W); per-image weight gradients to `wpart` (B, 4 R C): [dw1_r (R,C) | dw1_i | dw2_r (C,R) | dw2_i]
 __global__ void __launch_bounds__(256) att_bwd_gate_kernel(const double* __restrict__ da_partial, int n_chunks, const float2* __restrict__ gate_c,
@@ -1290,7 +1379,10 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   float* wpart = reinterpret_cast<float*>(w7_partial + (int64_t)n_tiles * 196);
   cudaStream_t s = (cudaStream_t)stream;
   const float2 *x = (const float2*)p->x, *dy = (const float2*)p->dy, *gc = (const float2*)p->gate_c, *gsp = (const float2*)p->gate_s;
-  att_bwd_ds_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (float2*)p->dspre, hw, C, G);
+  const bool small = (C == 8 || C == 16) && !getenv("DCS_ATT_BWD_NO_SMALL");
+  if (small && C == 8) att_bwd_ds_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
+  else if (small) att_bwd_ds_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
+  else att_bwd_ds_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (float2*)p->dspre, hw, C, G);
   DCS_LAUNCHED();
   att_bwd_w7_kernel<<<n_tiles, 256, 0, s>>>((const float4*)p->stats, (const float2*)p->dspre, p->h, p->w, tiles_x, tiles_y, w7_partial);
   DCS_LAUNCHED();
@@ -1299,7 +1391,9 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   float4* dstats = reinterpret_cast<float4*>(((uintptr_t)(wpart + (int64_t)(p->batch + 1) * 4 * R * C) + 15) & ~(uintptr_t)15);
   att_bwd_dstats_kernel<<<dim3((p->w + kDsTW - 1) / kDsTW, (p->h + kDsTH - 1) / kDsTH, p->batch), 256, 0, s>>>((const float2*)p->dspre, p->w7, dstats, p->h, p->w);
   DCS_LAUNCHED();
-  att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, dstats, (float2*)p->dx, da_partial, p->h, p->w, C, G);
+  if (small && C == 8) att_bwd_du_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, dstats, (float4*)p->dx, da_partial, hw);
+  else if (small) att_bwd_du_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, dstats, (float4*)p->dx, da_partial, hw);
+  else att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, dstats, (float2*)p->dx, da_partial, p->h, p->w, C, G);
   DCS_LAUNCHED();
   att_bwd_gate_kernel<<<p->batch, 256, 0, s>>>(da_partial, chunks, gc, (const long long*)p->sums, 1.f / (float)hw, C, R, p->w1_r, p->w1_i, p->w2_r,
                                                p->w2_i, (float2*)p->chan_const, wpart);
