@@ -433,7 +433,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
 __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __restrict__ dy, const float* __restrict__ w_r, const float* __restrict__ w_i,
                                                                float2* __restrict__ dx, int B, int in_h, int in_w, int out_h, int out_w, int cout,
                                                                int kh, int kw, int sh, int sw) {
-  extern __shared__ float2 wsm[];            // [tap][co] = (w_r, w_i)
+  extern __shared__ __align__(16) float2 wsm[];            // [tap][co] = (w_r, w_i)
   const int ntaps = kh * kw;
   for (int i = threadIdx.x; i < ntaps * cout; i += 256) {
     const int t = i / cout, co = i % cout;
@@ -453,10 +453,21 @@ __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __r
         if (iw + pw - kx < 0 || ow >= out_w) continue;
         const float2* g = dy + (((int64_t)b * out_h + oh) * out_w + ow) * cout;
         const float2* w = wsm + (ky * kw + kx) * cout;
-        for (int co = 0; co < cout; ++co) {
-          const float2 gv = g[co], wv = w[co];
-          ar += wv.x * gv.x + wv.y * gv.y;
-          ai += wv.x * gv.y - wv.y * gv.x;
+        if ((cout & 1) == 0) {                       // two output channels per 16-byte load (dy pixels and the weight rows are 16-byte aligned)
+          const float4* g4 = reinterpret_cast<const float4*>(g);
+          const float4* w4 = reinterpret_cast<const float4*>(w);
+#pragma unroll 4
+          for (int c2 = 0; c2 < cout / 2; ++c2) {
+            const float4 gv = g4[c2], wv = w4[c2];
+            ar += wv.x * gv.x + wv.y * gv.y + wv.z * gv.z + wv.w * gv.w;
+            ai += wv.x * gv.y - wv.y * gv.x + wv.z * gv.w - wv.w * gv.z;
+          }
+        } else {
+          for (int co = 0; co < cout; ++co) {
+            const float2 gv = g[co], wv = w[co];
+            ar += wv.x * gv.x + wv.y * gv.y;
+            ai += wv.x * gv.y - wv.y * gv.x;
+          }
         }
       }
     }
@@ -635,20 +646,28 @@ __global__ void __launch_bounds__(256) att_bwd_w7_kernel(const float4* __restric
     dsp[r][c] = (y0 + r < H && x0 + c < W) ? dspre[((int64_t)b * H + y0 + r) * W + x0 + c] : make_float2(0.f, 0.f);
   }
   __syncthreads();
-  // thread -> (tap, channel ch in {mean, max}, which in {r, i}) : 196 outputs
+  // thread -> (tap, 8-column strip of the tile): the four outputs of the tap (mean / max statistic x conv_r / conv_i) from ONE 16-byte
+  // statistics load and one 8-byte gradient load per pixel (a thread per output needs a load pair per FMA); the four strips are then
+  // combined in shared memory in a fixed order.  Output index = tap + 49 ch + 98 which, as the finalize kernel expects.
+  __shared__ float red[4][196];
   if (threadIdx.x < 196) {
-    const int tap = threadIdx.x % 49, ch = (threadIdx.x / 49) & 1, which = threadIdx.x / 98;
+    const int tap = threadIdx.x % 49, strip = threadIdx.x / 49;
     const int ky = tap / 7, kx = tap % 7;
-    float s = 0.f;
+    float r_mean = 0.f, r_max = 0.f, i_mean = 0.f, i_max = 0.f;
     for (int r = 0; r < kW7TH; ++r)
-      for (int c = 0; c < kW7TW; ++c) {
-        const float4 q = st[r + ky][c + kx];
-        const float sr = ch ? q.z : q.x, si = ch ? q.w : q.y;
-        const float2 g = dsp[r][c];
-        s += which ? (g.y * sr - g.x * si) : (g.x * sr + g.y * si);
+#pragma unroll
+      for (int c = 0; c < kW7TW / 4; ++c) {
+        const int cc = strip * (kW7TW / 4) + c;
+        const float4 q = st[r + ky][cc + kx];
+        const float2 g = dsp[r][cc];
+        r_mean += g.x * q.x + g.y * q.y;  r_max += g.x * q.z + g.y * q.w;
+        i_mean += g.y * q.x - g.x * q.y;  i_max += g.y * q.z - g.x * q.w;
       }
-    partial[(int64_t)tile * 196 + threadIdx.x] = (double)s;
+    red[strip][tap] = r_mean; red[strip][49 + tap] = r_max; red[strip][98 + tap] = i_mean; red[strip][147 + tap] = i_max;
   }
+  __syncthreads();
+  if (threadIdx.x < 196)
+    partial[(int64_t)tile * 196 + threadIdx.x] = (double)((red[0][threadIdx.x] + red[1][threadIdx.x]) + (red[2][threadIdx.x] + red[3][threadIdx.x]));
 }
 // out layout = the reference's (1,2,7,7) tensors: dw7_r[ch*49 + tap], dw7_i[ch*49 + tap].  One CTA per output element: the tiles'
 // partials are summed by 256 threads in a strided (fixed) order, then a fixed-shape tree.
