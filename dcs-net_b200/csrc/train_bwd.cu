@@ -365,6 +365,25 @@ __global__ void dilate_kernel(const float2* __restrict__ dy, float2* __restrict_
 }
 
 // z (B, h*uh, w*uw, c0 + c1) = nearest up-sampling of cat(d, skip) (the decoder convs' input, materialised for the wgrad)
+// two complex channels (one 16-byte load) per thread; c0, c1 even
+template <typename TO>
+__global__ void upcat_fwd2_kernel(const float4* __restrict__ d, const float4* __restrict__ skip, TO* __restrict__ z, int B, int H, int W,
+                                  int c0h, int c1h, int uh, int uw) {
+  const int Ch = c0h + c1h, HH = H * uh, WW = W * uw;
+  const int64_t n = (int64_t)B * HH * WW * Ch;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Ch);
+    int64_t r = i / Ch;
+    const int x = (int)(r % WW); r /= WW;
+    const int y = (int)(r % HH);
+    const int b = (int)(r / HH);
+    const int64_t pix = ((int64_t)b * H + y / uh) * W + x / uw;
+    const float4 v = c < c0h ? d[pix * c0h + c] : skip[pix * c1h + (c - c0h)];
+    Elem<TO>::stc(z, 2 * i, make_float2(v.x, v.y));
+    Elem<TO>::stc(z, 2 * i + 1, make_float2(v.z, v.w));
+  }
+}
+
 template <typename TO>
 __global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, TO* __restrict__ z, int B, int H, int W,
                                  int c0, int c1, int uh, int uw) {
@@ -415,10 +434,17 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
                                uint64_t offset) {
   const int64_t n4 = (n + 3) / 4;
   const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+  const bool vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     const uint64_t c = (uint64_t)i + offset;
     const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
     const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    if (vec && 4 * i + 3 < n) {
+      const float4 v = reinterpret_cast<const float4*>(x)[i];
+      reinterpret_cast<float4*>(y)[i] = make_float4(rr[0] >= thr ? v.x * scale : 0.f, rr[1] >= thr ? v.y * scale : 0.f,
+                                                    rr[2] >= thr ? v.z * scale : 0.f, rr[3] >= thr ? v.w * scale : 0.f);
+      continue;
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int64_t j = 4 * i + e;
@@ -1327,6 +1353,14 @@ extern "C" int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out
               "dcs_upcat_fwd: bad arguments");
   const int64_t n = (int64_t)batch * h * up_h * w * up_w * (c0 + c1);
   cudaStream_t s = (cudaStream_t)stream;
+  if ((c0 & 1) == 0 && (c1 & 1) == 0 && (((uintptr_t)d | (uintptr_t)skip) & 15) == 0) {
+    const int64_t n2 = n / 2;
+    if (out_dtype == DCS_F32) upcat_fwd2_kernel<float><<<ew_grid(n2), 256, 0, s>>>((const float4*)d, (const float4*)skip, (float*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
+    else if (out_dtype == DCS_F16) upcat_fwd2_kernel<__half><<<ew_grid(n2), 256, 0, s>>>((const float4*)d, (const float4*)skip, (__half*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
+    else upcat_fwd2_kernel<__nv_bfloat16><<<ew_grid(n2), 256, 0, s>>>((const float4*)d, (const float4*)skip, (__nv_bfloat16*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
+    DCS_LAUNCHED();
+    return 0;
+  }
   if (out_dtype == DCS_F32) upcat_fwd_kernel<float><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (float*)z, batch, h, w, c0, c1, up_h, up_w);
   else if (out_dtype == DCS_F16) upcat_fwd_kernel<__half><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__half*)z, batch, h, w, c0, c1, up_h, up_w);
   else upcat_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__nv_bfloat16*)z, batch, h, w, c0, c1, up_h, up_w);
