@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __r
   }
   __syncthreads();
   const int ph = kh / 2, pw = kw / 2;
+  const bool vec = (cout & 1) == 0 && ((uintptr_t)dy & 15) == 0;
   const int64_t n = (int64_t)B * in_h * in_w;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int iw = (int)(i % in_w), ih = (int)((i / in_w) % in_h), b = (int)(i / ((int64_t)in_w * in_h));
@@ -479,7 +480,7 @@ __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __r
         if (iw + pw - kx < 0 || ow >= out_w) continue;
         const float2* g = dy + (((int64_t)b * out_h + oh) * out_w + ow) * cout;
         const float2* w = wsm + (ky * kw + kx) * cout;
-        if ((cout & 1) == 0) {                       // two output channels per 16-byte load (dy pixels and the weight rows are 16-byte aligned)
+        if (vec) {                                   // two output channels per 16-byte load (dy pixels and the weight rows are 16-byte aligned)
           const float4* g4 = reinterpret_cast<const float4*>(g);
           const float4* w4 = reinterpret_cast<const float4*>(w);
 #pragma unroll 4
@@ -1432,7 +1433,8 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   float* wpart = reinterpret_cast<float*>(w7_partial + (int64_t)n_tiles * 196);
   cudaStream_t s = (cudaStream_t)stream;
   const float2 *x = (const float2*)p->x, *dy = (const float2*)p->dy, *gc = (const float2*)p->gate_c, *gsp = (const float2*)p->gate_s;
-  const bool small = (C == 8 || C == 16) && !getenv("DCS_ATT_BWD_NO_SMALL");
+  // (the thread-per-pixel kernels use 16-byte accesses: fall back to the lane-per-channel kernels for unaligned tensors)
+  const bool small = (C == 8 || C == 16) && !getenv("DCS_ATT_BWD_NO_SMALL") && ((((uintptr_t)p->x | (uintptr_t)p->dy | (uintptr_t)p->dx) & 15) == 0);
   if (small && C == 8) att_bwd_ds_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
   else if (small) att_bwd_ds_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
   else att_bwd_ds_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (float2*)p->dspre, hw, C, G);
