@@ -52,8 +52,9 @@ def parse():
     ap.add_argument("--frames", type=int, default=2000, help="STFT frames per utterance (2000 = 3.998 s)")
     ap.add_argument("--variant", default="dcs", choices=["dcs", "dc", "dr", "drs"])
     ap.add_argument("--workload", default="batch", choices=["batch", "longform", "train"])
-    ap.add_argument("--train-mode", default="tf32", choices=["tf32", "fp32"],
-                    help="train workload: tf32 = forward / dgrad convolutions on tcgen05 kind::tf32 (fp32 storage); fp32 = CUDA-core parity mode")
+    ap.add_argument("--train-mode", default="bf16", choices=["bf16", "tf32", "fp32"],
+                    help="train workload: tf32 = forward / dgrad convolutions on tcgen05 kind::tf32 (fp32 storage); bf16 = saved activations in bf16, forward "
+                         "convolutions in kind::f16 on them (gradients / statistics / master weights fp32); fp32 = CUDA-core parity mode")
     ap.add_argument("--train-batch", type=int, default=32, help="train workload: utterances per GPU per step (BASELINE configs[4])")
     ap.add_argument("--hours", type=float, default=1.0, help="longform: hours of 16 kHz audio per step (whole job)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -777,7 +778,7 @@ def run_train(args, rank, local_rank, world):
     h2d = sum(h.numel() * h.element_size() for h in host_specs)
     line = {"metric": train_metric(), "value": audio / (ms_dev / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "tf32" if args.train_mode == "tf32" else "f32", "data": "synthetic",
+            "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.train_mode], "data": "synthetic",
             "config": {"workload": workload_text(args), "mode": args.train_mode, "global_batch": B * world, "steps_per_s": 1e3 / ms_dev,
                        "parallelism": f"data-parallel x{world}: local BatchNorm statistics, flat fp32 gradient buckets all-reduced over NCCL, then the fused "
                                       "clip + Adam-amsgrad kernel on every rank",

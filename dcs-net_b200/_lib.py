@@ -58,7 +58,7 @@ class CbnTrainParams(C.Structure):
 class CbnTrainBwdParams(C.Structure):
     _fields_ = [("x", _vp), ("dy", _vp), ("dx", _vp), ("n_pix", _i64), ("channels", _i),
                 ("saved", _vp), ("weight", _vp), ("dweight", _vp), ("dbias", _vp), ("workspace", _vp), ("workspace_bytes", _i64),
-                ("conv_bias_grad_r", _vp), ("conv_bias_grad_i", _vp)]
+                ("conv_bias_grad_r", _vp), ("conv_bias_grad_i", _vp), ("x_dtype", _i)]
 
 
 class CwgradParams(C.Structure):
@@ -88,7 +88,7 @@ class AttentionBwdParams(C.Structure):
                 ("w1_r", _vp), ("w1_i", _vp), ("w2_r", _vp), ("w2_i", _vp),
                 ("dspre", _vp), ("dx", _vp), ("chan_const", _vp),
                 ("dw1_r", _vp), ("dw1_i", _vp), ("dw2_r", _vp), ("dw2_i", _vp), ("dw7_r", _vp), ("dw7_i", _vp),
-                ("workspace", _vp), ("workspace_bytes", _i64)]
+                ("workspace", _vp), ("workspace_bytes", _i64), ("x_dtype", _i)]
 
 
 class IstftParams(C.Structure):
@@ -218,18 +218,18 @@ SYMBOLS = {
     "dcs_colsum": (_i, [_vp, _i64, _i, _i, _i, _vp, _vp, _vp, _i64, _vp]),
     "dcs_dilate": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_cconv_dgrad_cin1": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
-    "dcs_upcat_fwd": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "dcs_upcat_fwd": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "dcs_wgrad_tc16_workspace_bytes": (_i64, [C.POINTER(Wgrad16Params)]),
     "dcs_wgrad_tc16": (_i, [C.POINTER(Wgrad16Params), _vp]),
     "dcs_dec6_bwd_workspace_bytes": (_i64, []),
-    "dcs_dec6_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
-    "dcs_act_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
-    "dcs_dropout": (_i, [_vp, _vp, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
+    "dcs_dec6_bwd": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp]),
+    "dcs_act_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _i, _i64, _i, _i, _vp]),
+    "dcs_dropout": (_i, [_vp, _vp, _i64, _i, _f, C.c_uint64, C.c_uint64, _vp]),
     "dcs_attention_bwd_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "dcs_attention_bwd": (_i, [C.POINTER(AttentionBwdParams), _vp]),
     "dcs_lstm_train_fwd": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "dcs_lstm_train_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
-    "dcs_cplx_split": (_i, [_vp, _vp, _i64, _vp]),
+    "dcs_cplx_split": (_i, [_vp, _i, _vp, _i64, _vp]),
     "dcs_cplx_merge": (_i, [_vp, _vp, _i64, _vp]),
     "dcs_clstm_combine": (_i, [_vp, _vp, _i64, _vp]),
     "dcs_clstm_combine_bwd": (_i, [_vp, _vp, _i64, _vp]),

@@ -116,6 +116,19 @@ template <> __device__ __forceinline__ float to_float<__half>(__half v) { return
 __device__ __forceinline__ void Elem<__half>::stc(__half* p, int64_t i, float2 v) {
   reinterpret_cast<uint32_t*>(p)[i] = pack_f16x2(v.x, v.y);
 }
+// runtime-typed loads of saved activations (the training step's backward kernels read them in fp32 or 16-bit storage; uniform branch)
+__device__ __forceinline__ float2 ld_c(const void* p, int64_t i, int dt) {            // complex element i
+  if (dt == DCS_F32) return reinterpret_cast<const float2*>(p)[i];
+  const uint32_t w = reinterpret_cast<const uint32_t*>(p)[i];
+  return dt == DCS_F16 ? unpack_h2<__half>(w) : unpack_h2<__nv_bfloat16>(w);
+}
+__device__ __forceinline__ float4 ld_c2(const void* p, int64_t i, int dt) {           // complex elements 2i, 2i + 1
+  if (dt == DCS_F32) return reinterpret_cast<const float4*>(p)[i];
+  const uint2 w = reinterpret_cast<const uint2*>(p)[i];
+  const float2 a = dt == DCS_F16 ? unpack_h2<__half>(w.x) : unpack_h2<__nv_bfloat16>(w.x);
+  const float2 b = dt == DCS_F16 ? unpack_h2<__half>(w.y) : unpack_h2<__nv_bfloat16>(w.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
 static inline bool is_h16(int dtype) { return dtype == DCS_BF16 || dtype == DCS_F16; }
 static inline bool is_dtype(int dtype) { return dtype == DCS_F32 || dtype == DCS_BF16 || dtype == DCS_F16; }
 

@@ -96,7 +96,7 @@ __global__ void cbn_train_finalize_kernel(const double* __restrict__ partial, in
 
 // backward pass 1: per-channel sums over pixels of the eight products of cbn_train_backward:
 //   (gr zr, gi zi, gr zi + gi zr, gr, gi, dzr xr, dzi xi, dzr xi + dzi xr)  with xc = x - mean, z = R xc, dz = Wm g
-__global__ void __launch_bounds__(kTrThreads) cbn_bwd_sums_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+__global__ void __launch_bounds__(kTrThreads) cbn_bwd_sums_kernel(const void* __restrict__ x, int xdt, const float* __restrict__ dy,
                                                                   const float* __restrict__ saved, const float* __restrict__ weight,
                                                                   double* __restrict__ partial, int64_t n_pix, int C, int64_t pix_per_cta) {
   __shared__ double red[kTrThreads][8];
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kTrThreads) cbn_bwd_sums_kernel(const float* _
   double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (pl < lanes)
     for (int64_t p = p0 + pl; p < p1; p += lanes) {
-      const float2 xv = reinterpret_cast<const float2*>(x)[p * C + c], g = reinterpret_cast<const float2*>(dy)[p * C + c];
+      const float2 xv = ld_c(x, p * C + c, xdt), g = reinterpret_cast<const float2*>(dy)[p * C + c];
       const float xr = xv.x - mr, xi = xv.y - mi;
       const float zr = Rrr * xr + Rri * xi, zi = Rii * xi + Rri * xr;
       const float dzr = w0 * g.x + w2 * g.y, dzi = w2 * g.x + w1 * g.y;
@@ -180,13 +180,13 @@ __global__ void cbn_bwd_finalize_kernel(const double* __restrict__ partial, int 
 // dx = P dy + Q x + k; with `colsum` the per-channel sums of dx (the bias gradient of the convolution in front: exactly zero in exact
 // arithmetic, round-off in fp32 — reported as computed, not assumed) go to colsum[cta][C][2] (a thread keeps ONE channel:
 // gridDim.x * 256 is a multiple of C)
-__global__ void __launch_bounds__(256) cbn_bwd_apply_kernel(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ coef,
+__global__ void __launch_bounds__(256) cbn_bwd_apply_kernel(const void* __restrict__ x, int xdt, const float* __restrict__ dy, const float* __restrict__ coef,
                                                             float* __restrict__ dx, int64_t n, int C, double* __restrict__ colsum) {
   __shared__ double red[256][2];
   double s0 = 0.0, s1 = 0.0;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float* k = coef + 10 * (int)(i % C);
-    const float2 xv = reinterpret_cast<const float2*>(x)[i], g = reinterpret_cast<const float2*>(dy)[i];
+    const float2 xv = ld_c(x, i, xdt), g = reinterpret_cast<const float2*>(dy)[i];
     const float2 o = make_float2(k[0] * g.x + k[1] * g.y + k[4] * xv.x + k[5] * xv.y + k[8],
                                  k[2] * g.x + k[3] * g.y + k[6] * xv.x + k[7] * xv.y + k[9]);
     reinterpret_cast<float2*>(dx)[i] = o;
@@ -371,13 +371,14 @@ extern "C" int dcs_cbn_train_fwd(const dcs_cbn_train_params* p, void* stream) {
 extern "C" int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream) {
   DCS_REQUIRE(p && p->x && p->dy && p->dx && p->saved && p->weight && p->dweight && p->dbias && p->workspace, "dcs_cbn_train_bwd: null pointer");
   DCS_REQUIRE(p->n_pix > 1 && tr_pow2(p->channels) && p->channels <= 256, "dcs_cbn_train_bwd: channels must be a power of two <= 256");
+  DCS_REQUIRE(is_dtype(p->x_dtype), "dcs_cbn_train_bwd: bad x_dtype");
   DCS_REQUIRE(p->workspace_bytes >= dcs_cbn_train_workspace_bytes(p->n_pix, p->channels), "dcs_cbn_train_bwd: workspace too small");
   int nc; int64_t ppc;
   chunking(p->n_pix, p->channels, &nc, &ppc);
   double* partial = reinterpret_cast<double*>(p->workspace);
   float* coef = reinterpret_cast<float*>(partial + (int64_t)nc * p->channels * 8);
   cudaStream_t s = (cudaStream_t)stream;
-  cbn_bwd_sums_kernel<<<nc, kTrThreads, 0, s>>>(p->x, p->dy, p->saved, p->weight, partial, p->n_pix, p->channels, ppc);
+  cbn_bwd_sums_kernel<<<nc, kTrThreads, 0, s>>>(p->x, p->x_dtype, p->dy, p->saved, p->weight, partial, p->n_pix, p->channels, ppc);
   DCS_LAUNCHED();
   cbn_bwd_finalize_kernel<<<p->channels, 64, 0, s>>>(partial, nc, p->channels, (double)p->n_pix, p->saved, p->weight, p->dweight, p->dbias, coef);
   DCS_LAUNCHED();
@@ -385,7 +386,7 @@ extern "C" int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream
   const bool cs = p->conv_bias_grad_r && p->conv_bias_grad_i;
   // with the column sums the per-CTA partials reuse the (consumed) moment partials: at most nc CTAs
   const int g = (int)std::min<int64_t>((n + 255) / 256, cs ? std::max<int64_t>(1, (int64_t)nc * 4) : (int64_t)num_sms() * 16);
-  cbn_bwd_apply_kernel<<<g, 256, 0, s>>>(p->x, p->dy, coef, p->dx, n, p->channels, cs ? partial : nullptr);
+  cbn_bwd_apply_kernel<<<g, 256, 0, s>>>(p->x, p->x_dtype, p->dy, coef, p->dx, n, p->channels, cs ? partial : nullptr);
   DCS_LAUNCHED();
   if (cs) {
     cbn_bwd_colsum_finalize_kernel<<<(p->channels + 7) / 8, 256, 0, s>>>(partial, g, p->channels, p->conv_bias_grad_r, p->conv_bias_grad_i);

@@ -367,7 +367,7 @@ __global__ void dilate_kernel(const float2* __restrict__ dy, float2* __restrict_
 // z (B, h*uh, w*uw, c0 + c1) = nearest up-sampling of cat(d, skip) (the decoder convs' input, materialised for the wgrad)
 // two complex channels (one 16-byte load) per thread; c0, c1 even
 template <typename TO>
-__global__ void upcat_fwd2_kernel(const float4* __restrict__ d, const float4* __restrict__ skip, TO* __restrict__ z, int B, int H, int W,
+__global__ void upcat_fwd2_kernel(const void* __restrict__ d, const void* __restrict__ skip, int idt, TO* __restrict__ z, int B, int H, int W,
                                   int c0h, int c1h, int uh, int uw) {
   const int Ch = c0h + c1h, HH = H * uh, WW = W * uw;
   const int64_t n = (int64_t)B * HH * WW * Ch;
@@ -378,14 +378,14 @@ __global__ void upcat_fwd2_kernel(const float4* __restrict__ d, const float4* __
     const int y = (int)(r % HH);
     const int b = (int)(r / HH);
     const int64_t pix = ((int64_t)b * H + y / uh) * W + x / uw;
-    const float4 v = c < c0h ? d[pix * c0h + c] : skip[pix * c1h + (c - c0h)];
+    const float4 v = c < c0h ? ld_c2(d, pix * c0h + c, idt) : ld_c2(skip, pix * c1h + (c - c0h), idt);
     Elem<TO>::stc(z, 2 * i, make_float2(v.x, v.y));
     Elem<TO>::stc(z, 2 * i + 1, make_float2(v.z, v.w));
   }
 }
 
 template <typename TO>
-__global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, TO* __restrict__ z, int B, int H, int W,
+__global__ void upcat_fwd_kernel(const void* __restrict__ d, const void* __restrict__ skip, int idt, TO* __restrict__ z, int B, int H, int W,
                                  int c0, int c1, int uh, int uw) {
   const int C = c0 + c1, HH = H * uh, WW = W * uw;
   const int64_t n = (int64_t)B * HH * WW * C;
@@ -396,12 +396,12 @@ __global__ void upcat_fwd_kernel(const float2* __restrict__ d, const float2* __r
     const int y = (int)(r % HH);
     const int b = (int)(r / HH);
     const int64_t pix = ((int64_t)b * H + y / uh) * W + x / uw;
-    Elem<TO>::stc(z, i, c < c0 ? d[pix * c0 + c] : skip[pix * c1 + (c - c0)]);
+    Elem<TO>::stc(z, i, c < c0 ? ld_c(d, pix * c0 + c, idt) : ld_c(skip, pix * c1 + (c - c0), idt));
   }
 }
 
 // dz = act'(y) * (g0 + g1 + chan_const[b][c]) per real component; y = the activation's OUTPUT (ReLU / LeakyReLU keep the sign)
-__global__ void act_bwd_kernel(const float2* __restrict__ y, const float2* __restrict__ g0, const float2* __restrict__ g1,
+__global__ void act_bwd_kernel(const void* __restrict__ y, int ydt, const float2* __restrict__ g0, const float2* __restrict__ g1,
                                const float2* __restrict__ cc, float2* __restrict__ dz, int64_t hw_c, int C, int64_t n, int act) {
   const float slope = act == DCS_ACT_RELU ? 0.f : (act == DCS_ACT_LRELU ? 0.01f : 1.f);
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -409,7 +409,7 @@ __global__ void act_bwd_kernel(const float2* __restrict__ y, const float2* __res
     if (g1) { const float2 t = g1[i]; g.x += t.x; g.y += t.y; }
     if (cc) { const float2 t = cc[(i / hw_c) * C + i % C]; g.x += t.x; g.y += t.y; }
     if (act != DCS_ACT_NONE) {
-      const float2 v = y[i];
+      const float2 v = ld_c(y, i, ydt);
       g.x *= v.x > 0.f ? 1.f : slope;
       g.y *= v.y > 0.f ? 1.f : slope;
     }
@@ -502,6 +502,22 @@ __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __r
   }
 }
 
+template <typename T>
+__global__ void dropout_h16_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t n, float p, float scale, uint64_t seed, uint64_t offset) {
+  const int64_t n4 = (n + 3) / 4;
+  const uint32_t thr = (uint32_t)fminf(p * 4294967296.f, 4294967295.f);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t c = (uint64_t)i + offset;
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int64_t j = 4 * i + e;
+      if (j < n) y[j] = rr[e] >= thr ? from_float<T>(to_float<T>(x[j]) * scale) : from_float<T>(0.f);
+    }
+  }
+}
+
 // =============================================================================================== decoder[6] backward, fused
 // decoder[6] = ComplexConvTranspose2d(16 -> 1, k3 s1 p1) on the (2,2) nearest up-sampling of cat(d5, skip6) (c_network.py:214-216).
 // With ONE output channel every low-resolution input pixel q sees the same 4 x 4 neighbourhood of the full-resolution gradient dpre:
@@ -512,7 +528,7 @@ __global__ void __launch_bounds__(256) cconv_dgrad_cin1_kernel(const float2* __r
 // 32 x 4 s), the few-channel wgrad, two full-resolution dgrad convolutions and two up-sampling adjoints.  Persistent CTAs over
 // 8 x 32-pixel low-resolution tiles; phase 1 thread = pixel (S_ab, g, bias), phase 2 thread = (ci, tap) over the tile's pixels.
 constexpr int kD6TH = 8, kD6TW = 32, kD6C = 16;
-__global__ void __launch_bounds__(256) dec6_bwd_kernel(const float2* __restrict__ d, const float2* __restrict__ skip, const float2* __restrict__ dpre,
+__global__ void __launch_bounds__(256) dec6_bwd_kernel(const void* __restrict__ d, const void* __restrict__ skip, int xdt, const float2* __restrict__ dpre,
                                                        const float* __restrict__ w_r, const float* __restrict__ w_i, int B, int H, int W, int c0, int c1,
                                                        float2* __restrict__ g_d, float2* __restrict__ g_skip, double* __restrict__ partial) {
   extern __shared__ __align__(16) unsigned char d6_smem[];
@@ -553,7 +569,7 @@ __global__ void __launch_bounds__(256) dec6_bwd_kernel(const float2* __restrict_
     const int y = y0 + py, x = x0 + px;
     const bool ok = y < H && x < W;
     const int64_t q = ((int64_t)b * H + y) * W + x;
-    for (int c = 0; c < Cn; ++c) zt[tid][c] = ok ? (c < c0 ? d[q * c0 + c] : skip[q * c1 + (c - c0)]) : make_float2(0.f, 0.f);
+    for (int c = 0; c < Cn; ++c) zt[tid][c] = ok ? (c < c0 ? ld_c(d, q * c0 + c, xdt) : ld_c(skip, q * c1 + (c - c0), xdt)) : make_float2(0.f, 0.f);
     __syncthreads();
     float2 v[4][4];
 #pragma unroll
@@ -628,7 +644,7 @@ __global__ void dec6_bwd_finalize_kernel(const double* __restrict__ partial, int
 // G = min(C, 32) lanes cooperate on one pixel, 32 / G pixels per warp.
 
 // pass 1: ds = sum_c conj(u_c) dy_c; dspre = ds (.) s (1 - s) per component
-__global__ void __launch_bounds__(256) att_bwd_ds_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
+__global__ void __launch_bounds__(256) att_bwd_ds_kernel(const void* __restrict__ x, int xdt, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
                                                          const float2* __restrict__ gate_s, float2* __restrict__ dspre, int hw, int C, int G) {
   __shared__ float2 gs[256];
   const int b = blockIdx.y;
@@ -641,7 +657,7 @@ __global__ void __launch_bounds__(256) att_bwd_ds_kernel(const float2* __restric
     float dr = 0.f, di = 0.f;
     if (p < hw)
       for (int c = sub; c < C; c += G) {
-        const float2 u = cmul(gs[c], x[(base + p) * C + c]), g = dy[(base + p) * C + c];
+        const float2 u = cmul(gs[c], ld_c(x, (base + p) * C + c, xdt)), g = dy[(base + p) * C + c];
         dr += u.x * g.x + u.y * g.y;          // conj(u) * g
         di += u.x * g.y - u.y * g.x;
       }
@@ -749,7 +765,7 @@ __global__ void __launch_bounds__(256) att_bwd_dstats_kernel(const float2* __res
 }
 
 // pass 2: du = conj(s) dy + dmean / C + [argmax] dmax; dx = conj(a) du; da partial sums per CTA
-__global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restrict__ x, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
+__global__ void __launch_bounds__(256) att_bwd_du_kernel(const void* __restrict__ x, int xdt, const float2* __restrict__ dy, const float2* __restrict__ gate_c,
                                                          const float2* __restrict__ gate_s, const float4* __restrict__ dstats,
                                                          float2* __restrict__ dx, double* __restrict__ da_partial, int H, int W, int C, int G) {
   __shared__ float2 gs[256];
@@ -775,7 +791,7 @@ __global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restric
     for (int k = 0; k < 8; ++k) {
       const int c = sub + k * G;
       if (k < nch && ok && c < C) {
-        xv8[k] = x[(base + p) * C + c];
+        xv8[k] = ld_c(x, (base + p) * C + c, xdt);
         uv[k] = cmul(gs[c], xv8[k]);
         gv[k] = dy[(base + p) * C + c];
         if (uv[k].x > bre) { bre = uv[k].x; are = c; }
@@ -829,7 +845,7 @@ __global__ void __launch_bounds__(256) att_bwd_du_kernel(const float2* __restric
 // shuffles, a serial arg max — instead of C lanes per pixel (the C = 8 launches ran at a tenth of the HBM rate: 12 shuffles and a
 // strided loop per element).
 template <int C>
-__global__ void __launch_bounds__(256) att_bwd_ds_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float2* __restrict__ gate_c,
+__global__ void __launch_bounds__(256) att_bwd_ds_small_kernel(const void* __restrict__ x, int xdt, const float4* __restrict__ dy, const float2* __restrict__ gate_c,
                                                                const float2* __restrict__ gate_s, float2* __restrict__ dspre, int hw) {
   __shared__ float2 gs[C];
   const int b = blockIdx.y;
@@ -840,7 +856,7 @@ __global__ void __launch_bounds__(256) att_bwd_ds_small_kernel(const float4* __r
     float dr = 0.f, di = 0.f;
 #pragma unroll
     for (int c = 0; c < C; c += 2) {
-      const float4 xv = x[(base + p) * (C / 2) + c / 2], g = dy[(base + p) * (C / 2) + c / 2];
+      const float4 xv = ld_c2(x, (base + p) * (C / 2) + c / 2, xdt), g = dy[(base + p) * (C / 2) + c / 2];
       const float2 u0 = cmul(gs[c], make_float2(xv.x, xv.y)), u1 = cmul(gs[c + 1], make_float2(xv.z, xv.w));
       dr += u0.x * g.x + u0.y * g.y + u1.x * g.z + u1.y * g.w;
       di += u0.x * g.y - u0.y * g.x + u1.x * g.w - u1.y * g.z;
@@ -851,7 +867,7 @@ __global__ void __launch_bounds__(256) att_bwd_ds_small_kernel(const float4* __r
 }
 
 template <int C>
-__global__ void __launch_bounds__(256) att_bwd_du_small_kernel(const float4* __restrict__ x, const float4* __restrict__ dy, const float2* __restrict__ gate_c,
+__global__ void __launch_bounds__(256) att_bwd_du_small_kernel(const void* __restrict__ x, int xdt, const float4* __restrict__ dy, const float2* __restrict__ gate_c,
                                                                const float2* __restrict__ gate_s, const float4* __restrict__ dstats,
                                                                float4* __restrict__ dx, double* __restrict__ da_partial, int hw) {
   __shared__ float2 gs[C];
@@ -868,7 +884,7 @@ __global__ void __launch_bounds__(256) att_bwd_du_small_kernel(const float4* __r
     float2 xv[C], gv[C];
 #pragma unroll
     for (int c = 0; c < C; c += 2) {
-      const float4 a4 = x[(base + p) * (C / 2) + c / 2], g4 = dy[(base + p) * (C / 2) + c / 2];
+      const float4 a4 = ld_c2(x, (base + p) * (C / 2) + c / 2, xdt), g4 = dy[(base + p) * (C / 2) + c / 2];
       xv[c] = make_float2(a4.x, a4.y); xv[c + 1] = make_float2(a4.z, a4.w);
       gv[c] = make_float2(g4.x, g4.y); gv[c + 1] = make_float2(g4.z, g4.w);
     }
@@ -1093,9 +1109,9 @@ __global__ void __launch_bounds__(4 * H) lstm_train_bwd_kernel(const float* __re
 }
 
 // (rows, D, 2) interleaved complex <-> (2, rows, D) planes
-__global__ void cplx_split_kernel(const float2* __restrict__ x, float* __restrict__ planes, int64_t n) {
+__global__ void cplx_split_kernel(const void* __restrict__ x, int xdt, float* __restrict__ planes, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float2 v = x[i];
+    const float2 v = ld_c(x, i, xdt);
     planes[i] = v.x; planes[n + i] = v.y;
   }
 }
@@ -1349,39 +1365,40 @@ extern "C" int dcs_cconv_dgrad_cin1(const float* dy, const float* w_r, const flo
   return 0;
 }
 
-extern "C" int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream) {
-  DCS_REQUIRE(d && z && (skip || c1 == 0) && batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 >= 0 && up_h >= 1 && up_w >= 1 && is_dtype(out_dtype),
+extern "C" int dcs_upcat_fwd(const void* d, const void* skip, int in_dtype, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w,
+                             void* stream) {
+  DCS_REQUIRE(d && z && (skip || c1 == 0) && batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 >= 0 && up_h >= 1 && up_w >= 1 && is_dtype(out_dtype) && is_dtype(in_dtype),
               "dcs_upcat_fwd: bad arguments");
   const int64_t n = (int64_t)batch * h * up_h * w * up_w * (c0 + c1);
   cudaStream_t s = (cudaStream_t)stream;
   if ((c0 & 1) == 0 && (c1 & 1) == 0 && (((uintptr_t)d | (uintptr_t)skip) & 15) == 0) {
     const int64_t n2 = n / 2;
-    if (out_dtype == DCS_F32) upcat_fwd2_kernel<float><<<ew_grid(n2), 256, 0, s>>>((const float4*)d, (const float4*)skip, (float*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
-    else if (out_dtype == DCS_F16) upcat_fwd2_kernel<__half><<<ew_grid(n2), 256, 0, s>>>((const float4*)d, (const float4*)skip, (__half*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
-    else upcat_fwd2_kernel<__nv_bfloat16><<<ew_grid(n2), 256, 0, s>>>((const float4*)d, (const float4*)skip, (__nv_bfloat16*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
+    if (out_dtype == DCS_F32) upcat_fwd2_kernel<float><<<ew_grid(n2), 256, 0, s>>>(d, skip, in_dtype, (float*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
+    else if (out_dtype == DCS_F16) upcat_fwd2_kernel<__half><<<ew_grid(n2), 256, 0, s>>>(d, skip, in_dtype, (__half*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
+    else upcat_fwd2_kernel<__nv_bfloat16><<<ew_grid(n2), 256, 0, s>>>(d, skip, in_dtype, (__nv_bfloat16*)z, batch, h, w, c0 / 2, c1 / 2, up_h, up_w);
     DCS_LAUNCHED();
     return 0;
   }
-  if (out_dtype == DCS_F32) upcat_fwd_kernel<float><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (float*)z, batch, h, w, c0, c1, up_h, up_w);
-  else if (out_dtype == DCS_F16) upcat_fwd_kernel<__half><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__half*)z, batch, h, w, c0, c1, up_h, up_w);
-  else upcat_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, s>>>((const float2*)d, (const float2*)skip, (__nv_bfloat16*)z, batch, h, w, c0, c1, up_h, up_w);
+  if (out_dtype == DCS_F32) upcat_fwd_kernel<float><<<ew_grid(n), 256, 0, s>>>(d, skip, in_dtype, (float*)z, batch, h, w, c0, c1, up_h, up_w);
+  else if (out_dtype == DCS_F16) upcat_fwd_kernel<__half><<<ew_grid(n), 256, 0, s>>>(d, skip, in_dtype, (__half*)z, batch, h, w, c0, c1, up_h, up_w);
+  else upcat_fwd_kernel<__nv_bfloat16><<<ew_grid(n), 256, 0, s>>>(d, skip, in_dtype, (__nv_bfloat16*)z, batch, h, w, c0, c1, up_h, up_w);
   DCS_LAUNCHED();
   return 0;
 }
 
 extern "C" int64_t dcs_dec6_bwd_workspace_bytes(void) { return (int64_t)2 * num_sms() * (2 * 9 * kD6C + 2) * (int64_t)sizeof(double); }
-extern "C" int dcs_dec6_bwd(const float* d, const float* skip, const float* dpre, const float* w_r, const float* w_i, int batch, int h, int w, int c0, int c1,
+extern "C" int dcs_dec6_bwd(const void* d, const void* skip, int in_dtype, const float* dpre, const float* w_r, const float* w_i, int batch, int h, int w, int c0, int c1,
                             float* g_d, float* g_skip, float* dw_r, float* dw_i, float* db_r, float* db_i, void* workspace, int64_t workspace_bytes,
                             void* stream) {
   DCS_REQUIRE(d && skip && dpre && w_r && w_i && g_d && g_skip && dw_r && dw_i && db_r && db_i && workspace, "dcs_dec6_bwd: null pointer");
-  DCS_REQUIRE(batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 > 0 && c0 + c1 <= kD6C, "dcs_dec6_bwd: c0 + c1 must be <= 16");
+  DCS_REQUIRE(batch > 0 && h > 0 && w > 0 && c0 > 0 && c1 > 0 && c0 + c1 <= kD6C && is_dtype(in_dtype), "dcs_dec6_bwd: c0 + c1 must be <= 16");
   DCS_REQUIRE(workspace_bytes >= dcs_dec6_bwd_workspace_bytes(), "dcs_dec6_bwd: workspace too small");
   const int n_tiles = batch * ((h + kD6TH - 1) / kD6TH) * ((w + kD6TW - 1) / kD6TW);
   const int ctas = std::min(n_tiles, 2 * num_sms());
   cudaStream_t s = (cudaStream_t)stream;
   const size_t smem = sizeof(float2) * (9 * kD6TH * kD6TW + kD6TH * kD6TW * (kD6C + 1));
   DCS_CUDA(cudaFuncSetAttribute(dec6_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dec6_bwd_kernel<<<ctas, 256, smem, s>>>((const float2*)d, (const float2*)skip, (const float2*)dpre, w_r, w_i, batch, h, w, c0, c1, (float2*)g_d,
+  dec6_bwd_kernel<<<ctas, 256, smem, s>>>(d, skip, in_dtype, (const float2*)dpre, w_r, w_i, batch, h, w, c0, c1, (float2*)g_d,
                                        (float2*)g_skip, reinterpret_cast<double*>(workspace));
   DCS_LAUNCHED();
   dec6_bwd_finalize_kernel<<<1, 160, 0, s>>>(reinterpret_cast<const double*>(workspace), ctas, c0 + c1, dw_r, dw_i, db_r, db_i);
@@ -1389,20 +1406,23 @@ extern "C" int dcs_dec6_bwd(const float* d, const float* skip, const float* dpre
   return 0;
 }
 
-extern "C" int dcs_act_bwd(const float* y, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,
-                           int act, void* stream) {
-  DCS_REQUIRE(g0 && dz && (y || act == DCS_ACT_NONE) && batch > 0 && hw > 0 && channels > 0 && act >= DCS_ACT_NONE && act <= DCS_ACT_LRELU,
-              "dcs_act_bwd: bad arguments");
+extern "C" int dcs_act_bwd(const void* y, int y_dtype, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw,
+                           int channels, int act, void* stream) {
+  DCS_REQUIRE(g0 && dz && (y || act == DCS_ACT_NONE) && batch > 0 && hw > 0 && channels > 0 && act >= DCS_ACT_NONE && act <= DCS_ACT_LRELU &&
+              is_dtype(y_dtype), "dcs_act_bwd: bad arguments");
   const int64_t n = (int64_t)batch * hw * channels;
-  act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)y, (const float2*)g0, (const float2*)g1, (const float2*)chan_const,
+  act_bwd_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(y, y_dtype, (const float2*)g0, (const float2*)g1, (const float2*)chan_const,
                                                                (float2*)dz, hw * channels, channels, n, act);
   DCS_LAUNCHED();
   return 0;
 }
 
-extern "C" int dcs_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream) {
-  DCS_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f, "dcs_dropout: bad arguments");
-  dropout_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, 1.f / (1.f - p), seed, offset);
+extern "C" int dcs_dropout(const void* x, void* y, int64_t n, int dtype, float p, uint64_t seed, uint64_t offset, void* stream) {
+  DCS_REQUIRE(x && y && n > 0 && p >= 0.f && p < 1.f && is_dtype(dtype), "dcs_dropout: bad arguments");
+  const float sc = 1.f / (1.f - p);
+  if (dtype == DCS_F32) dropout_kernel<<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, n, p, sc, seed, offset);
+  else if (dtype == DCS_F16) dropout_h16_kernel<__half><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((const __half*)x, (__half*)y, n, p, sc, seed, offset);
+  else dropout_h16_kernel<__nv_bfloat16><<<ew_grid((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y, n, p, sc, seed, offset);
   DCS_LAUNCHED();
   return 0;
 }
@@ -1424,6 +1444,7 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
               "dcs_attention_bwd: null pointer");
   const int64_t need = dcs_attention_bwd_workspace_bytes(p->batch, p->h, p->w, p->channels, p->reduced);
   DCS_REQUIRE(need > 0, "dcs_attention_bwd: channels must be a power of two <= 256, reduced <= 16");
+  DCS_REQUIRE(is_dtype(p->x_dtype), "dcs_attention_bwd: bad x_dtype");
   DCS_REQUIRE(p->workspace_bytes >= need, "dcs_attention_bwd: workspace too small");
   const int C = p->channels, R = p->reduced, hw = p->h * p->w, G = att_G(C), chunks = att_chunks(hw, G);
   const int tiles_y = (p->h + kW7TH - 1) / kW7TH, tiles_x = (p->w + kW7TW - 1) / kW7TW;
@@ -1432,12 +1453,15 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   double* w7_partial = da_partial + (int64_t)p->batch * chunks * C * 2;
   float* wpart = reinterpret_cast<float*>(w7_partial + (int64_t)n_tiles * 196);
   cudaStream_t s = (cudaStream_t)stream;
-  const float2 *x = (const float2*)p->x, *dy = (const float2*)p->dy, *gc = (const float2*)p->gate_c, *gsp = (const float2*)p->gate_s;
+  const void* x = p->x;
+  const int xdt = p->x_dtype;
+  const float2 *dy = (const float2*)p->dy, *gc = (const float2*)p->gate_c, *gsp = (const float2*)p->gate_s;
   // (the thread-per-pixel kernels use 16-byte accesses: fall back to the lane-per-channel kernels for unaligned tensors)
   const bool small = (C == 8 || C == 16) && !getenv("DCS_ATT_BWD_NO_SMALL") && ((((uintptr_t)p->x | (uintptr_t)p->dy | (uintptr_t)p->dx) & 15) == 0);
-  if (small && C == 8) att_bwd_ds_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
-  else if (small) att_bwd_ds_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
-  else att_bwd_ds_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, (float2*)p->dspre, hw, C, G);
+  (void)x;
+  if (small && C == 8) att_bwd_ds_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>(x, xdt, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
+  else if (small) att_bwd_ds_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>(x, xdt, (const float4*)p->dy, gc, gsp, (float2*)p->dspre, hw);
+  else att_bwd_ds_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, xdt, dy, gc, gsp, (float2*)p->dspre, hw, C, G);
   DCS_LAUNCHED();
   att_bwd_w7_kernel<<<n_tiles, 256, 0, s>>>((const float4*)p->stats, (const float2*)p->dspre, p->h, p->w, tiles_x, tiles_y, w7_partial);
   DCS_LAUNCHED();
@@ -1446,9 +1470,9 @@ extern "C" int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream
   float4* dstats = reinterpret_cast<float4*>(((uintptr_t)(wpart + (int64_t)(p->batch + 1) * 4 * R * C) + 15) & ~(uintptr_t)15);
   att_bwd_dstats_kernel<<<dim3((p->w + kDsTW - 1) / kDsTW, (p->h + kDsTH - 1) / kDsTH, p->batch), 256, 0, s>>>((const float2*)p->dspre, p->w7, dstats, p->h, p->w);
   DCS_LAUNCHED();
-  if (small && C == 8) att_bwd_du_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, dstats, (float4*)p->dx, da_partial, hw);
-  else if (small) att_bwd_du_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>((const float4*)p->x, (const float4*)p->dy, gc, gsp, dstats, (float4*)p->dx, da_partial, hw);
-  else att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, dy, gc, gsp, dstats, (float2*)p->dx, da_partial, p->h, p->w, C, G);
+  if (small && C == 8) att_bwd_du_small_kernel<8><<<dim3(chunks, p->batch), 256, 0, s>>>(x, xdt, (const float4*)p->dy, gc, gsp, dstats, (float4*)p->dx, da_partial, hw);
+  else if (small) att_bwd_du_small_kernel<16><<<dim3(chunks, p->batch), 256, 0, s>>>(x, xdt, (const float4*)p->dy, gc, gsp, dstats, (float4*)p->dx, da_partial, hw);
+  else att_bwd_du_kernel<<<dim3(chunks, p->batch), 256, 0, s>>>(x, xdt, dy, gc, gsp, dstats, (float2*)p->dx, da_partial, p->h, p->w, C, G);
   DCS_LAUNCHED();
   att_bwd_gate_kernel<<<p->batch, 256, 0, s>>>(da_partial, chunks, gc, (const long long*)p->sums, 1.f / (float)hw, C, R, p->w1_r, p->w1_i, p->w2_r,
                                                p->w2_i, (float2*)p->chan_const, wpart);
@@ -1482,9 +1506,9 @@ extern "C" int dcs_lstm_train_bwd(const float* w_hh, const float* gates, const f
   return 0;
 }
 
-extern "C" int dcs_cplx_split(const float* x, float* planes, int64_t n, void* stream) {
-  DCS_REQUIRE(x && planes && n > 0, "dcs_cplx_split: bad arguments");
-  cplx_split_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>((const float2*)x, planes, n);
+extern "C" int dcs_cplx_split(const void* x, int in_dtype, float* planes, int64_t n, void* stream) {
+  DCS_REQUIRE(x && planes && n > 0 && is_dtype(in_dtype), "dcs_cplx_split: bad arguments");
+  cplx_split_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(x, in_dtype, planes, n);
   DCS_LAUNCHED();
   return 0;
 }

@@ -29,8 +29,11 @@ class TrainStep:
     def __init__(self, model, variant="dcs", speech_alpha=None, atan2_eps=None, seed=0, mode="fp32"):
         """mode: "fp32" = CUDA-core FFMA convolutions (the parity mode); "tf32" = the forward and data-gradient convolutions on the
         tensor cores (tcgen05 kind::tf32 through dcs_cconv2d_tc_fwd, fp32 storage, fp32 accumulation)."""
-        assert variant in ("dcs", "dc") and mode in ("fp32", "tf32")
+        assert variant in ("dcs", "dc") and mode in ("fp32", "tf32", "bf16")
         self.mode = mode
+        # "bf16": the saved activations are stored in bf16 and the forward convolutions run in kind::f16 on them; gradients, BatchNorm
+        # statistics, attention gates, the LSTM and the master weights stay fp32 (the data-gradient convolutions read fp32 gradients: tf32)
+        self.act_dtype = torch.bfloat16 if mode == "bf16" else torch.float32
         hp = getattr(model, "hparams", {})
         self.model, self.variant, self.hp = model, variant, hp
         self.alpha = float(speech_alpha if speech_alpha is not None else hp.get("speech_alpha", 0.7))
@@ -56,18 +59,20 @@ class TrainStep:
             self._packed_key, self._stale = key, False
             return
         Lr = self.L
-        tf = self.mode == "tf32"
+        tf = self.mode in ("tf32", "bf16")
+        tcd = torch.bfloat16 if self.mode == "bf16" else None
         self.enc, self.dec, self.enc_dgrad, self.dec_dgrad = [], [], [], []
         for i in range(Lr):
             p = f"encoder.{i}.0."
             self.enc.append(packing.PackedConv(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], sd[p + "conv_r.bias"], sd[p + "conv_i.bias"],
-                                               stride=STRIDE_E[i], act=L.ACT_NONE, device=device, want_tf32=tf))
+                                               stride=STRIDE_E[i], act=L.ACT_NONE, device=device, want_tf32=tf and tcd is None, tc_dtype=tcd))
             # data gradient of the strided conv as a sub-pixel phase convolution of the un-dilated gradient (train_ops.PhasePack)
             self.enc_dgrad.append(T.PhasePack(sd[p + "conv_r.weight"], sd[p + "conv_i.weight"], STRIDE_E[i], device, want_tf32=tf))
         for i in range(Lr):
             p = f"decoder.{i}." if i == Lr - 1 else f"decoder.{i}.0."
             self.dec.append(packing.PackedConv(sd[p + "conv_tran_r.weight"], sd[p + "conv_tran_i.weight"], sd[p + "conv_tran_r.bias"],
-                                               sd[p + "conv_tran_i.bias"], transposed=True, up=UPSAMPLE[i], act=L.ACT_NONE, device=device, want_tf32=tf))
+                                               sd[p + "conv_tran_i.bias"], transposed=True, up=UPSAMPLE[i], act=L.ACT_NONE, device=device, want_tf32=tf and tcd is None,
+                                               tc_dtype=tcd))
             # data gradient per source (decoder path d: the first half of the input channels, skip: the second), so that each GEMM's
             # N = 2 * channels stays within the tensor-core kernel's 256 columns
             c0 = sd[p + "conv_tran_r.weight"].shape[0] // 2
@@ -94,14 +99,17 @@ class TrainStep:
         """One complex convolution: tcgen05 kind::tf32 when the mode and the layer allow it (>= 4 complex channels per source = 32-byte
         rows for the operand loader, 2 cout <= 256), CUDA-core FFMA otherwise."""
         c1 = 0 if src1 is None else src1.shape[3]
-        tc = self.mode == "tf32" and pk.w_tc32 is not None and src0.shape[3] % 4 == 0 and c1 % 4 == 0 and 2 * pk.cout <= 256
+        have = pk.w_tc is not None if src0.dtype in ops.H16 else pk.w_tc32 is not None
+        tc = self.mode != "fp32" and have and src0.shape[3] % 4 == 0 and c1 % 4 == 0 and 2 * pk.cout <= 256
+        if dst.dtype in ops.H16 and src0.dtype == torch.float32 and not tc:
+            raise NotImplementedError("TrainStep: an fp32 -> 16-bit convolution needs the tensor-core path")
         return ops.cconv(pk, src0, src1, dst, use_tc=tc)
 
-    def _bn(self, x, prefix, act):
+    def _bn(self, x, prefix, act, out=None):
         """Train-mode ComplexBatchNorm2d on the module's own parameters / buffers (running statistics updated in place)."""
         m = self.model.get_submodule(prefix)
         y, saved, _ = T.cbn_train_fwd(x, m.weight.detach(), m.bias.detach(), m.running_mean, m.running_covar, m.num_batches_tracked,
-                                      act=act, eps=m.eps, momentum=m.momentum if m.momentum is not None else T.BN_MOMENTUM)
+                                      act=act, y=out, eps=m.eps, momentum=m.momentum if m.momentum is not None else T.BN_MOMENTUM)
         return y, saved
 
     def _drop(self, x, p, tag):
@@ -147,11 +155,11 @@ class TrainStep:
         self._pack(dev)
         Lr = self.L
         B, F, Tn = Y.shape
-        new = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)   # noqa: E731
+        new = lambda *s: torch.empty(*s, dtype=self.act_dtype, device=dev)   # noqa: E731  (activations: fp32, or bf16 storage)
         sv = self.saved = {}
         self._drop_off = 0
         x0 = torch.view_as_real(Y).view(B, F, Tn, 1, 2)
-        x, sv["bn0"] = self._bn(x0, "initial_batchnorm", L.ACT_NONE)
+        x, sv["bn0"] = self._bn(x0, "initial_batchnorm", L.ACT_NONE, out=new(B, F, Tn, 1, 2))
         sv["x0"] = x0
         enc = [x]                                                             # enc[i] = input of encoder i; enc[i + 1] its (dropped) output
         H, W = F, Tn
@@ -173,7 +181,8 @@ class TrainStep:
             skip, att = T.attention_fwd_saved(enc[Lr - i], self.skip_ca[i], self.skip_sa[i])
             sv["dec_in"].append(d), sv["skip"].append(skip), sv["skip_att"].append(att)
             H, W = H * UPSAMPLE[i][0], W * UPSAMPLE[i][1]
-            pre = self._conv(self.dec[i], d, skip, new(B, H, W, self.dec[i].cout, 2))
+            last = i == Lr - 1        # decoder[6] writes the raw mask in fp32 (complex64 view)
+            pre = self._conv(self.dec[i], d, skip, torch.empty(B, H, W, self.dec[i].cout, 2, dtype=torch.float32 if last else self.act_dtype, device=dev))
             if i == Lr - 1:
                 pre = self._drop(pre, self.p_conv, f"dec{i}")
                 sv["d5"], sv["skip6"] = d, skip
@@ -267,13 +276,14 @@ class TrainStep:
     def _wgrad_on_tc(self, cin, cout):
         """tf32 mode: weight gradients of every layer with >= 8 complex channels on both sides run on tcgen05 (dcs_wgrad_tc16) from bf16
         copies of the two operands (fp32 accumulation over the pixels); encoder[0] / decoder[6] stay on the few-channel CUDA-core kernel."""
-        return self.mode == "tf32" and cin >= 8 and cout >= 8
+        return self.mode in ("tf32", "bf16") and cin >= 8 and cout >= 8
 
     def _conv_param_grads(self, x, dpre, prefix, names, kernel, stride, transposed, bias=True):
         if self._wgrad_on_tc(x.shape[3], dpre.shape[3]):
-            x = x if x.dtype == torch.bfloat16 else T.to_h16(x)
+            x = x if x.dtype == torch.bfloat16 else (T.to_h16(x) if x.dtype == torch.float32 else T.to_h16(T.to_f32(x)))
             dy16 = T.to_h16(dpre)
         else:
+            x = x if x.dtype == torch.float32 else T.to_f32(x)       # few-channel layers: the CUDA-core fp32 kernel
             dy16 = dpre
         T.cwgrad_generic(x, dy16, kernel, stride, transposed=transposed, dw_r=self._grad(prefix + names[0] + ".weight"),
                          dw_i=self._grad(prefix + names[1] + ".weight"))
@@ -435,16 +445,17 @@ class TrainStep:
             o += p.numel()
         leaf = lambda name, shape=None: TP.Sym.leaf(off[name][0], shape or off[name][1])   # noqa: E731
         gp = TP.GatherPack(self.flat_param)
-        tf, Lr = self.mode == "tf32", self.L
+        tf, Lr = self.mode in ("tf32", "bf16"), self.L
+        tc16 = self.mode == "bf16"
         for i in range(Lr):
             p = f"encoder.{i}.0."
             wr, wi = leaf(p + "conv_r.weight"), leaf(p + "conv_i.weight")
-            gp.add_packed_conv(self.enc[i], TP.sym_conv(wr, wi, leaf(p + "conv_r.bias"), leaf(p + "conv_i.bias"), tf32=tf))
+            gp.add_packed_conv(self.enc[i], TP.sym_conv(wr, wi, leaf(p + "conv_r.bias"), leaf(p + "conv_i.bias"), tf32=tf and not tc16, tc=tc16))
             gp.add_packed_conv(self.enc_dgrad[i], TP.sym_dgrad_strided(wr, wi, STRIDE_E[i], tf32=tf))
             p = f"decoder.{i}." if i == Lr - 1 else f"decoder.{i}.0."
             wr, wi = leaf(p + "conv_tran_r.weight"), leaf(p + "conv_tran_i.weight")
             gp.add_packed_conv(self.dec[i], TP.sym_conv(wr, wi, leaf(p + "conv_tran_r.bias"), leaf(p + "conv_tran_i.bias"), transposed=True,
-                                                        up=UPSAMPLE[i], tf32=tf))
+                                                        up=UPSAMPLE[i], tf32=tf and not tc16, tc=tc16))
             c0 = wr.shape[0] // 2
             for pk, sl in zip(self.dec_dgrad[i], (slice(0, c0), slice(c0, None))):
                 gp.add_packed_conv(pk, TP.sym_dgrad(wr[sl], wi[sl], transposed=True, tf32=tf))

@@ -54,14 +54,14 @@ def cbn_train_bwd(x, dy, saved, weight, workspace=None, conv_bias_grads=None):
     L.require_cuda(x, dy, saved, weight)
     Cn = x.shape[-2]
     n_pix = x.numel() // (2 * Cn)
-    assert x.dtype == torch.float32 and dy.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape
-    dx = torch.empty_like(x)
+    assert dy.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous() and dy.shape == x.shape
+    dx = torch.empty_like(dy)
     dw = torch.empty(Cn, 3, dtype=torch.float32, device=x.device)
     db = torch.empty(Cn, 2, dtype=torch.float32, device=x.device)
     ws = workspace if workspace is not None else cbn_train_workspace(n_pix, Cn, x.device)
     cb = conv_bias_grads or (None, None)
     p = L.CbnTrainBwdParams(L.ptr(x), L.ptr(dy), L.ptr(dx), n_pix, Cn, L.ptr(saved), L.ptr(weight.contiguous()), L.ptr(dw), L.ptr(db),
-                            L.ptr(ws), ws.numel(), L.ptr(cb[0]), L.ptr(cb[1]))
+                            L.ptr(ws), ws.numel(), L.ptr(cb[0]), L.ptr(cb[1]), L.dtype_code(x))
     L.check(L.lib().dcs_cbn_train_bwd(C.byref(p), L.stream_ptr()), "dcs_cbn_train_bwd")
     return dx, dw, db
 
@@ -281,9 +281,10 @@ def dilate(dy, in_h, in_w, stride):
 def upcat_fwd(d, skip, up, dtype=torch.float32):
     B, H, W, c0, _ = d.shape
     c1 = skip.shape[3] if skip is not None else 0
-    assert d.dtype == torch.float32 and d.is_contiguous() and (skip is None or (skip.is_contiguous() and skip.dtype == torch.float32))
+    assert d.is_contiguous() and (skip is None or (skip.is_contiguous() and skip.dtype == d.dtype))
     z = torch.empty(B, H * up[0], W * up[1], c0 + c1, 2, dtype=dtype, device=d.device)
-    L.check(L.lib().dcs_upcat_fwd(L.ptr(d), L.ptr(skip), L.ptr(z), L.dtype_code(z), B, H, W, c0, c1, up[0], up[1], L.stream_ptr()), "dcs_upcat_fwd")
+    L.check(L.lib().dcs_upcat_fwd(L.ptr(d), L.ptr(skip), L.dtype_code(d), L.ptr(z), L.dtype_code(z), B, H, W, c0, c1, up[0], up[1], L.stream_ptr()),
+            "dcs_upcat_fwd")
     return z
 
 
@@ -292,18 +293,20 @@ def act_bwd(y, g0, act, g1=None, chan_const=None, out=None):
     """dz = act'(y) * (g0 + g1 + chan_const[b, c]) on (B, ..., C, 2) fp32 tensors."""
     B, Cn = g0.shape[0], g0.shape[-2]
     hw = g0.numel() // (2 * B * Cn)
-    for t in (y, g0, g1):
+    for t in (g0, g1):
         assert t is None or (t.dtype == torch.float32 and t.is_contiguous() and t.shape == g0.shape)
+    assert y is None or (y.is_contiguous() and y.shape == g0.shape)          # the saved activation: fp32 or 16-bit storage
     out = out if out is not None else torch.empty_like(g0)
-    L.check(L.lib().dcs_act_bwd(L.ptr(y), L.ptr(g0), L.ptr(g1), L.ptr(chan_const), L.ptr(out), B, hw, Cn, act, L.stream_ptr()), "dcs_act_bwd")
+    L.check(L.lib().dcs_act_bwd(L.ptr(y), L.dtype_code(y) if y is not None else L.F32, L.ptr(g0), L.ptr(g1), L.ptr(chan_const), L.ptr(out), B, hw, Cn,
+                                act, L.stream_ptr()), "dcs_act_bwd")
     return out
 
 
 @ops._on_tensor_device
 def dropout(x, p, seed, offset, out=None):
-    assert x.dtype == torch.float32 and x.is_contiguous()
+    assert x.is_contiguous()
     out = out if out is not None else torch.empty_like(x)
-    L.check(L.lib().dcs_dropout(L.ptr(x), L.ptr(out), x.numel(), float(p), int(seed), int(offset), L.stream_ptr()), "dcs_dropout")
+    L.check(L.lib().dcs_dropout(L.ptr(x), L.ptr(out), x.numel(), L.dtype_code(x), float(p), int(seed), int(offset), L.stream_ptr()), "dcs_dropout")
     return out
 
 
@@ -317,7 +320,8 @@ def attention_bwd(x, dy, gate_c, stats, gate_s, sums, ca, w7, grads=None):
     dev = x.device
     f = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)   # noqa: E731
     g = grads or dict(dw1_r=f(R, Cn), dw1_i=f(R, Cn), dw2_r=f(Cn, R), dw2_i=f(Cn, R), dw7_r=f(1, 2, 7, 7), dw7_i=f(1, 2, 7, 7))
-    dspre, dx, cc = f(B, H * W, 2), torch.empty_like(x), f(B, Cn, 2)
+    assert dy.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous()
+    dspre, dx, cc = f(B, H * W, 2), torch.empty_like(dy), f(B, Cn, 2)
     n = int(L.lib().dcs_attention_bwd_workspace_bytes(B, H, W, Cn, R))
     if n < 0:
         raise RuntimeError("dcs_attention_bwd: unsupported shape")
@@ -325,7 +329,7 @@ def attention_bwd(x, dy, gate_c, stats, gate_s, sums, ca, w7, grads=None):
     p = L.AttentionBwdParams(L.ptr(x), L.ptr(dy), L.ptr(gate_c), L.ptr(stats), L.ptr(gate_s), L.ptr(w7), L.ptr(sums), B, H, W, Cn, R,
                              L.ptr(ca["w1_r"]), L.ptr(ca["w1_i"]), L.ptr(ca["w2_r"]), L.ptr(ca["w2_i"]), L.ptr(dspre), L.ptr(dx), L.ptr(cc),
                              L.ptr(g["dw1_r"]), L.ptr(g["dw1_i"]), L.ptr(g["dw2_r"]), L.ptr(g["dw2_i"]), L.ptr(g["dw7_r"]), L.ptr(g["dw7_i"]),
-                             L.ptr(ws), ws.numel())
+                             L.ptr(ws), ws.numel(), L.dtype_code(x))
     L.check(L.lib().dcs_attention_bwd(C.byref(p), L.stream_ptr()), "dcs_attention_bwd")
     return dx, cc, g
 
@@ -361,8 +365,10 @@ def _ew(fn_name, src, dst, n):
 @ops._on_tensor_device
 def cplx_split(x):
     """(..., 2) interleaved -> (2, ...) planes."""
-    assert x.is_contiguous() and x.shape[-1] == 2 and x.dtype == torch.float32
-    return _ew("dcs_cplx_split", x, torch.empty((2,) + tuple(x.shape[:-1]), dtype=torch.float32, device=x.device), x.numel() // 2)
+    assert x.is_contiguous() and x.shape[-1] == 2
+    planes = torch.empty((2,) + tuple(x.shape[:-1]), dtype=torch.float32, device=x.device)
+    L.check(L.lib().dcs_cplx_split(L.ptr(x), L.dtype_code(x), L.ptr(planes), x.numel() // 2, L.stream_ptr()), "dcs_cplx_split")
+    return planes
 
 
 @ops._on_tensor_device
@@ -454,10 +460,10 @@ def dec6_bwd(d, skip, dpre, w_r, w_i, dw_r, dw_i, db_r, db_i):
     B, H, W, c0, _ = d.shape
     c1 = skip.shape[3]
     assert dpre.is_contiguous() and d.is_contiguous() and skip.is_contiguous() and dpre.numel() == B * 2 * H * 2 * W * 2
-    assert w_r.is_contiguous() and w_i.is_contiguous() and tuple(w_r.shape) == (c0 + c1, 1, 3, 3)
-    g_d, g_s = torch.empty_like(d), torch.empty_like(skip)
+    assert w_r.is_contiguous() and w_i.is_contiguous() and tuple(w_r.shape) == (c0 + c1, 1, 3, 3) and skip.dtype == d.dtype and dpre.dtype == torch.float32
+    g_d, g_s = torch.empty(d.shape, dtype=torch.float32, device=d.device), torch.empty(skip.shape, dtype=torch.float32, device=d.device)
     ws = _ws(L.lib().dcs_dec6_bwd_workspace_bytes(), d.device)
-    L.check(L.lib().dcs_dec6_bwd(L.ptr(d), L.ptr(skip), L.ptr(dpre), L.ptr(w_r), L.ptr(w_i), B, H, W, c0, c1, L.ptr(g_d), L.ptr(g_s), L.ptr(dw_r),
+    L.check(L.lib().dcs_dec6_bwd(L.ptr(d), L.ptr(skip), L.dtype_code(d), L.ptr(dpre), L.ptr(w_r), L.ptr(w_i), B, H, W, c0, c1, L.ptr(g_d), L.ptr(g_s), L.ptr(dw_r),
                                  L.ptr(dw_i), L.ptr(db_r), L.ptr(db_i), L.ptr(ws), ws.numel(), L.stream_ptr()), "dcs_dec6_bwd")
     return g_d, g_s
 
@@ -510,3 +516,11 @@ class PhasePack:
             wt[:, :, :K] = Wp.permute(0, 2, 1, 3).reshape(self.phases, self.n_pad, K)
             self.w_tc32 = packing.round_tf32(wt.float()).contiguous().to(device)
         self.bias = torch.zeros(self.n_pad, dtype=torch.float32, device=device)
+
+
+@ops._on_tensor_device
+def to_f32(x):
+    """16-bit -> fp32 copy of a contiguous activation (dcs_convert)."""
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    L.check(L.lib().dcs_convert(L.ptr(x), L.ptr(y), x.numel(), L.dtype_code(x), L.F32, L.stream_ptr()), "dcs_convert")
+    return y

@@ -213,7 +213,9 @@ class GatherPack:
 
     def add_packed_conv(self, pk, sy):
         """Redirect the operand tensors of a packing.PackedConv to gather-pack outputs (sy = sym_conv / sym_dgrad of the same layer)."""
-        for name, dtype in (("w_ffma", torch.float32), ("bias", torch.float32), ("w_tc32", "tf32")):
+        for name, dtype in (("w_ffma", torch.float32), ("bias", torch.float32), ("w_tc32", "tf32"), ("w_tc", getattr(pk, "tc_dtype", None))):
+            if dtype is None:
+                continue
             cur = getattr(pk, name, None)
             if cur is None or name not in sy:
                 continue

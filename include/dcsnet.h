@@ -370,10 +370,11 @@ int dcs_cbn_train_fwd(const dcs_cbn_train_params* p, void* stream);
  *      dx, dweight (C x 3), dbias (C x 2).  Pass 1 reduces eight per-channel sums, a per-channel 3x3 Jacobian of the whitening
  *      matrix gives the coefficients of pass 2, dx = P dy + Q x + k. */
 typedef struct {
-  const float* x; const float* dy; float* dx; int64_t n_pix; int channels;
+  const void* x; const float* dy; float* dx; int64_t n_pix; int channels;
   const float* saved; const float* weight; float* dweight; float* dbias; void* workspace; int64_t workspace_bytes;
   float* conv_bias_grad_r; float* conv_bias_grad_i;   /* optional (both or neither), C floats each: conv_r / conv_i .bias.grad of the convolution
                                                          in front of this BatchNorm = per-channel sums of dx (S.re + S.im, S.im - S.re) */
+  int x_dtype;                                        /* storage type of x (the saved forward input): DCS_F32 / DCS_F16 / DCS_BF16; dy, dx fp32 */
 } dcs_cbn_train_bwd_params;
 int dcs_cbn_train_bwd(const dcs_cbn_train_bwd_params* p, void* stream);
 
@@ -455,22 +456,24 @@ int dcs_cconv_dgrad_cin1(const float* dy, const float* w_r, const float* w_i, fl
                          int cout, int kh, int kw, int stride_h, int stride_w, void* stream);
 /* z (B, h*up_h, w*up_w, c0 + c1) = complex_upsample(cat(d, skip)) (c_network.py:214-215), materialised as the wgrad's x operand in
  * out_dtype (fp32 for dcs_wgrad, fp16 / bf16 for dcs_wgrad_tc16) */
-int dcs_upcat_fwd(const float* d, const float* skip, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w, void* stream);
+int dcs_upcat_fwd(const void* d, const void* skip, int in_dtype, void* z, int out_dtype, int batch, int h, int w, int c0, int c1, int up_h, int up_w,
+                  void* stream);
 /* decoder[6] backward in one kernel (c_network.py:214-216: ComplexConvTranspose2d(c0 + c1 -> 1, k3 s1 p1) on the (2,2) nearest
  * up-sampling of cat(d, skip)): dpre (B, 2h, 2w) complex = gradient of the layer's output -> g_d (B, h, w, c0), g_skip (B, h, w, c1),
  * the weight gradients in the module's (c0 + c1, 1, 3, 3) layout and the two bias gradients.  c0 + c1 <= 16. */
 int64_t dcs_dec6_bwd_workspace_bytes(void);
-int dcs_dec6_bwd(const float* d, const float* skip, const float* dpre, const float* w_r, const float* w_i, int batch, int h, int w, int c0, int c1,
+int dcs_dec6_bwd(const void* d, const void* skip, int in_dtype, const float* dpre, const float* w_r, const float* w_i, int batch, int h, int w, int c0, int c1,
                  float* g_d, float* g_skip, float* dw_r, float* dw_i, float* db_r, float* db_i, void* workspace, int64_t workspace_bytes,
                  void* stream);
 /* dz = act'(y) (.) (g0 + g1 + chan_const[b][c]) per real component (ComplexReLU / ComplexLReLU act on the parts); y = the
- * activation's OUTPUT (B, hw, channels) complex; g1 (same shape) and chan_const (B, channels) complex are optional */
-int dcs_act_bwd(const float* y, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,
+ * activation's OUTPUT (B, hw, channels) complex in storage type y_dtype (the saved forward tensor; gradients are fp32); g1 (same shape) and
+ * chan_const (B, channels) complex are optional */
+int dcs_act_bwd(const void* y, int y_dtype, const float* g0, const float* g1, const float* chan_const, float* dz, int batch, int64_t hw, int channels,
                 int act, void* stream);
 /* torch.nn.Dropout(p) on n floats (c_network.py:195-196 / 203-204 / 221-222: applied on view_as_real): y = x * keep / (1 - p),
  * keep drawn from Philox4x32-10 with key `seed` and counter offset + i / 4: the same (seed, offset) regenerates the mask for the
  * backward.  (The reference draws from torch's generator; the streams differ, the distribution does not.) */
-int dcs_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uint64_t offset, void* stream);
+int dcs_dropout(const void* x, void* y, int64_t n, int dtype, float p, uint64_t seed, uint64_t offset, void* stream);
 
 /* ---- backward of the attended product y = s (.) (a (.) x) (ComplexChannelAttention + ComplexSpatialAttention applied with
  *      complex products, c_network.py:208-211 / 219-220).  Inputs saved by the forward: x, the channel gate a (B, C), the
@@ -478,12 +481,13 @@ int dcs_dropout(const float* x, float* y, int64_t n, float p, uint64_t seed, uin
  *      dx = conj(a) du WITHOUT the per-channel constant davg / hw, which is returned in chan_const (B, C) and added by the
  *      consumer (dcs_act_bwd).  Weight gradients in the reference's layouts: fc.0 (R, C), fc.2 (C, R), conv1 (1, 2, 7, 7). */
 typedef struct {
-  const float* x; const float* dy; const float* gate_c; const float* stats; const float* gate_s; const float* w7; const void* sums;
+  const void* x; const float* dy; const float* gate_c; const float* stats; const float* gate_s; const float* w7; const void* sums;
   int batch; int h; int w; int channels; int reduced;
   const float* w1_r; const float* w1_i; const float* w2_r; const float* w2_i;
   float* dspre; float* dx; float* chan_const;
   float* dw1_r; float* dw1_i; float* dw2_r; float* dw2_i; float* dw7_r; float* dw7_i;
   void* workspace; int64_t workspace_bytes;
+  int x_dtype;     /* storage type of x (DCS_F32 / DCS_F16 / DCS_BF16); dy, dx and the saved gates / statistics are fp32 */
 } dcs_attention_bwd_params;
 int64_t dcs_attention_bwd_workspace_bytes(int batch, int h, int w, int channels, int reduced);
 int dcs_attention_bwd(const dcs_attention_bwd_params* p, void* stream);
@@ -498,7 +502,7 @@ int dcs_lstm_train_bwd(const float* w_hh, const float* gates, const float* cells
                        int hidden, float* dpre, void* stream);
 /* (n) interleaved complex <-> two planes (2, n); ComplexLSTM's combine (c_network.py:39-47) on h (2 lstm, 2 part, n):
  * out = (R(re) - I(im)) + j (R(im) + I(re)), and its adjoint */
-int dcs_cplx_split(const float* x, float* planes, int64_t n, void* stream);
+int dcs_cplx_split(const void* x, int in_dtype, float* planes, int64_t n, void* stream);
 int dcs_cplx_merge(const float* planes, float* x, int64_t n, void* stream);
 int dcs_clstm_combine(const float* h, float* out, int64_t n, void* stream);
 int dcs_clstm_combine_bwd(const float* dout, float* dh, int64_t n, void* stream);

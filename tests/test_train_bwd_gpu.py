@@ -218,3 +218,46 @@ def test_fused_decoder6_backward(H, W):
     assert rel_err(nchw(gd), gd_w) <= 2e-5 and rel_err(nchw(gs), gs_w) <= 2e-5
     assert rel_err(dwr, dwr_w) <= 2e-5 and rel_err(dwi, dwi_w) <= 2e-5
     assert rel_err(dbr, dbr_w) <= 2e-5 and rel_err(dbi, dbi_w) <= 2e-5
+
+
+def test_backward_kernels_read_saved_activations_in_16_bit_storage():
+    """The bf16 training mode stores the saved forward activations in bf16; the backward kernels that read them (attention backward,
+    BN backward, activation mask, fused decoder[6] backward, up-sampled concat, complex split, dropout) must give what they give on the
+    same values held in fp32."""
+    from dcsnet_b200 import _lib as L, packing, train_ops as T
+    g = torch.Generator().manual_seed(21)
+    bf = lambda t: t.bfloat16()                                        # noqa: E731
+    # attention backward, C = 8 (thread-per-pixel kernels) and C = 32 (lane-per-channel kernels)
+    for C in (8, 32):
+        B, H, W, R = 2, 6, 20, max(C // 16, 1)
+        x16 = bf(torch.randn(B, H, W, C, 2, generator=g)).cuda()
+        dy = torch.randn(B, H, W, C, 2, generator=g).cuda()
+        sd = {"c.fc.0.conv_r.weight": 0.5 * torch.randn(R, C, 1, 1, generator=g), "c.fc.0.conv_i.weight": 0.5 * torch.randn(R, C, 1, 1, generator=g),
+              "c.fc.2.conv_r.weight": 0.5 * torch.randn(C, R, 1, 1, generator=g), "c.fc.2.conv_i.weight": 0.5 * torch.randn(C, R, 1, 1, generator=g),
+              "s.conv1.conv_r.weight": 0.2 * torch.randn(1, 2, 7, 7, generator=g), "s.conv1.conv_i.weight": 0.2 * torch.randn(1, 2, 7, 7, generator=g)}
+        ca, w7 = packing.pack_channel_attention(sd, "c.", "cuda"), packing.pack_spatial_attention(sd, "s.", "cuda")
+        _, sv = T.attention_fwd_saved(x16.float(), ca, w7)             # gates / statistics from the fp32 copy of the same values
+        a = T.attention_bwd(x16.float(), dy, sv["gate_c"], sv["stats"], sv["gate_s"], sv["sums"], ca, w7)
+        b = T.attention_bwd(x16, dy, sv["gate_c"], sv["stats"], sv["gate_s"], sv["sums"], ca, w7)
+        assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and all(torch.equal(a[2][k], b[2][k]) for k in a[2])
+    # BN backward, activation mask
+    x16 = bf(torch.randn(2, 5, 9, 16, 2, generator=g)).cuda()
+    dy = torch.randn(2, 5, 9, 16, 2, generator=g).cuda()
+    w, bb = (torch.rand(16, 3, generator=g) + torch.tensor([0.5, 0.5, -0.5])).cuda(), torch.randn(16, 2, generator=g).cuda()
+    _, saved, _ = T.cbn_train_fwd(x16.float(), w, bb)
+    ra, rb = T.cbn_train_bwd(x16.float(), dy, saved, w), T.cbn_train_bwd(x16, dy, saved, w)
+    assert all(torch.equal(p, q) for p, q in zip(ra, rb))
+    assert torch.equal(T.act_bwd(x16, dy, L.ACT_LRELU), T.act_bwd(x16.float(), dy, L.ACT_LRELU))
+    # fused decoder[6] backward, up-sampled concat, complex split, dropout
+    d16, s16 = bf(torch.randn(2, 6, 20, 8, 2, generator=g)).cuda(), bf(torch.randn(2, 6, 20, 8, 2, generator=g)).cuda()
+    dpre = torch.randn(2, 12, 40, 1, 2, generator=g).cuda()
+    w_r, w_i = torch.randn(16, 1, 3, 3, generator=g).cuda(), torch.randn(16, 1, 3, 3, generator=g).cuda()
+    outs = []
+    for d_, s_ in ((d16, s16), (d16.float(), s16.float())):
+        gr = [torch.empty(16, 1, 3, 3, device="cuda"), torch.empty(16, 1, 3, 3, device="cuda"), torch.empty(1, device="cuda"), torch.empty(1, device="cuda")]
+        outs.append(list(T.dec6_bwd(d_, s_, dpre, w_r, w_i, *gr)) + gr)
+    assert all(torch.equal(p, q) for p, q in zip(*outs))
+    assert torch.equal(T.upcat_fwd(d16, s16, (2, 2), dtype=torch.bfloat16), T.upcat_fwd(d16.float(), s16.float(), (2, 2), dtype=torch.bfloat16))
+    assert torch.equal(T.cplx_split(d16), T.cplx_split(d16.float()))
+    m16, m32 = T.dropout(d16, 0.1, 3, 17), T.dropout(d16.float(), 0.1, 3, 17)
+    assert torch.equal(m16 != 0, m32 != 0) and torch.equal(m16, m32.bfloat16())
