@@ -32,7 +32,7 @@ def main():
     import torch
     import dcsnet_b200  # noqa: F401
     from dcsnet_b200 import c_network, r_network, config as cfg
-    from oracle import dcsnet_oracle as O   # synthetic audio generator only
+    from dcsnet_b200 import synthetic as O   # seeded synthetic utterances (no dataset in the image)
     if not torch.cuda.is_available():
         raise SystemExit("test.py needs a CUDA device (sm_100a); dcsnet_b200 has no CPU fallback")
     torch.cuda.set_device(a.gpu)

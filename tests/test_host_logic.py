@@ -293,3 +293,15 @@ def test_two_rank_flat_bucket_exchange_with_gloo():
     for p in procs:
         p.join(timeout=60)
     assert r["ok"] and r["contiguous"] and r["numel"] == 2912707 and r["nb"] == 3
+
+
+def test_product_side_never_imports_the_oracle():
+    """oracle/ is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py (synthetic inputs outside the timed region, the
+    cpu_baseline leg, the reference arm) may import it — not the package, not the train.py / test.py entry points."""
+    import glob
+    import re
+    files = glob.glob(os.path.join(ROOT, "dcs-net_b200", "*.py")) + [os.path.join(ROOT, f) for f in ("train.py", "test.py", "dcsnet_b200.py")]
+    assert len(files) > 10
+    for f in files:
+        src = open(f).read()
+        assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
