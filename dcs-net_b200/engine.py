@@ -358,7 +358,8 @@ class ForwardPlan:
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = L.launch_count()
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, stream=s):       # an explicit capture stream ON THE PLAN'S DEVICE (torch's default capture stream is
+                # created once per process on whatever device was current then: a plan on another GPU captured an empty graph)
                 self._enqueue_from_audio()
             self.graph_launches = L.launch_count() - before
             self.graph = g
