@@ -400,8 +400,9 @@ class C_NETWORK(_StepMixin, _Base):
     def forward(self, x):
         """x: (B,F,T) complex64 -> bound_cRM(decoder output), squeezed like c_network.py:224-226."""
         if self.training:
-            raise NotImplementedError("dcsnet_b200.C_NETWORK: the training step (dropout, batch-stat BN, autograd) is "
-                                      "SURVEY §8f rank 2 and not built in this round; call .eval()")
+            raise NotImplementedError("dcsnet_b200.C_NETWORK.forward has no autograd twin: in train mode use training_step(batch, idx) + "
+                                      "train_step.backward() + train_step.optimizer_step() (dcsnet_b200.train_engine.TrainStep: batch-statistic "
+                                      "BatchNorm, dropout, the whole backward pass and Adam-amsgrad as kernels), or call .eval()")
         L.require_cuda(x)
         if x.dtype != torch.complex64 or x.dim() != 3:
             raise RuntimeError("C_NETWORK.forward expects a complex64 (B,F,T) spectrogram")

@@ -185,8 +185,9 @@ class ComplexBatchNorm2d(_ComplexBatchNorm):
 
     def forward(self, input):
         if self.training:
-            raise NotImplementedError("dcsnet_b200.ComplexBatchNorm2d: train-mode batch statistics are not built in "
-                                      "this round (SURVEY §8f rank 2); call .eval()")
+            raise NotImplementedError("dcsnet_b200.ComplexBatchNorm2d: the layer-wise module has no autograd twin; train-mode batch statistics "
+                                      "(forward and backward) are dcsnet_b200.train_ops.cbn_train_fwd / cbn_train_bwd, driven by "
+                                      "train_engine.TrainStep; call .eval() for the folded inference form")
         L.require_cuda(input)
         x = to_cl(input)
         return from_cl(ops.cbn_apply(x, self.folded_affine(x.device)))

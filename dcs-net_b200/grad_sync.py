@@ -8,7 +8,8 @@ local BatchNorm statistics, ONE exchange per step — an all-reduce (sum, then /
 Gradients live in a few flat buckets, filled decoder-first (the order backward produces them), so each bucket's
 all-reduce can be launched asynchronously while the rest of backward still runs; parameters' `.grad` are views into the
 buckets, so no copy in or out.  `torch.distributed` is plumbing: NCCL over NVLink on the GPUs, gloo in the CPU tests.
-The backward kernels that fill these buffers are not built yet; the class works on whatever wrote `.grad`.
+train_engine.TrainStep's backward kernels write straight into these buffers (`flat=True`: ONE buffer whose 4 MB slices are the buckets, so the
+fused clip + Adam-amsgrad kernel sees a single array); the class works on whatever wrote `.grad`.
 """
 import torch
 import torch.distributed as dist

@@ -1,6 +1,6 @@
 """Generate tests/golden/train_step.pt by EXECUTING THE REFERENCE'S training-step function with autograd (build container
-only; TEST INFRASTRUCTURE).  Pin for SURVEY 8f rank 2 (the training step), which is not built yet: the next round's
-backward kernels are checked against these numbers.
+only; TEST INFRASTRUCTURE).  Pin for SURVEY 8f rank 2 (the training step): train_engine.TrainStep's
+forward / backward kernels are checked against these numbers (tests/test_train_gpu.py).
 
     python -m oracle.make_golden_train
 

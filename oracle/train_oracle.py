@@ -1,7 +1,7 @@
 """CPU restatement of the reference's TRAINING step, complex (dcs / dc) and real (drs / dr) networks (TEST INFRASTRUCTURE ONLY;
 SURVEY 8f rank 2).
 
-No product code exists for this row yet; this is its oracle, pinned by tests/golden/train_step.pt (the reference's own
+The product side is dcsnet_b200.train_engine.TrainStep; this is its oracle, pinned by tests/golden/train_step.pt (the reference's own
 `train_batch_2_loss` + `backward()`, oracle/make_golden_train.py).  The forward is oracle/dcsnet_oracle.c_network_forward
 with train-mode ComplexBatchNorm2d (batch statistics, running-stat update; complexPyTorch 0.3) and an
 optional dropout hook; gradients come from torch autograd over this restatement.

@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--frames", type=int, default=256)
     a = ap.parse_args()
     if a.variant in ("dr", "drs"):
-        raise SystemExit("train.py: the real path's training step is not built (SURVEY 8f rank 2); dcs / dc run the GPU slice")
+        raise SystemExit("train.py: the real path's (dr / drs) training step is not built; dcs / dc run the whole step on the GPU")
     import torch
     import dcsnet_b200  # noqa: F401
     from dcsnet_b200 import c_network, config as cfg, ops
