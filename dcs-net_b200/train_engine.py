@@ -467,11 +467,11 @@ class TrainStep:
         for l in range(2):
             for j, n in enumerate(names):
                 gp.add(TP.Sym.cat([leaf(f"lstm.{n}.weight_ih_l{l}{s}") for s in sfx], 0), torch.float32,
-                       lambda t, l=l, j=j: self.lstm_wih[l].__setitem__(j, t))
+                       lambda t, l=l, j=j: self.lstm_wih[l].__setitem__(j, t), current=self.lstm_wih[l][j])
                 gp.add(TP.Sym.cat([leaf(f"lstm.{n}.bias_ih_l{l}{s}") + leaf(f"lstm.{n}.bias_hh_l{l}{s}") for s in sfx], 0), torch.float32,
-                       lambda t, l=l, j=j: self.lstm_b[l].__setitem__(j, t))
+                       lambda t, l=l, j=j: self.lstm_b[l].__setitem__(j, t), current=self.lstm_b[l][j])
             gp.add(TP.Sym.stack([TP.Sym.stack([leaf(f"lstm.{n}.weight_hh_l{l}{s}") for s in sfx], 0) for n in names], 0), torch.float32,
-                   lambda t, l=l: self.lstm_whh.__setitem__(l, t))
+                   lambda t, l=l: self.lstm_whh.__setitem__(l, t), current=self.lstm_whh[l])
         params = dict(self.model.named_parameters())
         def attention(ca_list, sa_list, prefix, count):
             for i in range(count):
@@ -481,9 +481,12 @@ class TrainStep:
                                   ("w2_i", "fc.2.conv_i.weight")):
                     ca[key] = params[pc + name].data.view(ca[key].shape)               # views of the live parameters: nothing to re-pack
                 gp.add(TP.Sym.cat([leaf(ps + "conv1.conv_r.weight").reshape(-1), leaf(ps + "conv1.conv_i.weight").reshape(-1)], 0), torch.float32,
-                       lambda t, i=i: sa_list.__setitem__(i, t))
+                       lambda t, i=i: sa_list.__setitem__(i, t), current=sa_list[i])
         attention(self.skip_ca, self.skip_sa, "skip_attention", Lr)
         attention(self.dec_ca, self.dec_sa, "decoder_attention", Lr - 1)
+        if str(dev).startswith("cpu"):        # CPU: tables only (tests check them against the host packing); there is no CPU gather kernel
+            self.gather_tables = gp
+            return
         self.gather = gp.finalize()
         self.gather.run()
 

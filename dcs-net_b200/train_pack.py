@@ -206,10 +206,33 @@ class GatherPack:
     def __init__(self, flat_param):
         self.flat = flat_param
         self.jobs = {}          # dtype -> list of (Sym, shape, setter)
+        self.current = []
 
-    def add(self, sym, dtype, setter):
-        """dtype: torch.float32 / float16 / bfloat16, or "tf32" (fp32 storage rounded to tf32)."""
+    def add(self, sym, dtype, setter, current=None):
+        """dtype: torch.float32 / float16 / bfloat16, or "tf32" (fp32 storage rounded to tf32).  `current`: the host-packed tensor this
+        job replaces (kept for `check_against_host_packing`)."""
         self.jobs.setdefault(dtype, []).append((sym, setter))
+        self.current.append((sym, dtype, current))
+
+    def check_against_host_packing(self, flat=None):
+        """Every table evaluated on the flat parameter vector (on the CPU) equals the tensor the host packing produced — the whole-model
+        form of tests/test_train_pack.py.  Returns the number of operands compared."""
+        from .packing import round_tf32
+        flat = (self.flat if flat is None else flat).detach().cpu()
+        n = 0
+        for sym, dtype, cur in self.current:
+            if cur is None:
+                continue
+            got = sym.evaluate(flat).float()
+            if dtype == "tf32":
+                got = round_tf32(got)
+            elif dtype in (torch.float16, torch.bfloat16):
+                got = got.to(dtype).float()
+            want = cur.detach().cpu().float()
+            assert tuple(got.shape) == tuple(want.shape), (tuple(got.shape), tuple(want.shape))
+            assert torch.allclose(got, want, rtol=1e-2 if dtype in (torch.float16, torch.bfloat16) else 1e-6, atol=1e-7), dtype
+            n += 1
+        return n
 
     def add_packed_conv(self, pk, sy):
         """Redirect the operand tensors of a packing.PackedConv to gather-pack outputs (sy = sym_conv / sym_dgrad of the same layer)."""
@@ -220,7 +243,7 @@ class GatherPack:
             if cur is None or name not in sy:
                 continue
             assert tuple(cur.shape) == tuple(sy[name].shape), (name, tuple(cur.shape), tuple(sy[name].shape))
-            self.add(sy[name], dtype, lambda t, pk=pk, name=name: setattr(pk, name, t))
+            self.add(sy[name], dtype, lambda t, pk=pk, name=name: setattr(pk, name, t), current=cur)
 
     def finalize(self):
         dev = self.flat.device

@@ -73,3 +73,18 @@ def test_symbolic_strided_dgrad_operands_equal_phase_pack(cin, cout, k, stride):
                             got[0, y * stride[0] + ph, xx * stride[1] + pw] += v.reshape(cin, 2)
     want_cl = torch.stack([want[0, :cin], want[0, cin:]], -1).permute(1, 2, 0, 3)
     assert torch.allclose(got[0], want_cl, rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
+def test_whole_model_gather_tables_equal_the_host_packing(mode):
+    """TrainStep.init_optimizer on the CPU (flat parameter / gradient buffers, parameters re-pointed as views) builds the (index, sign)
+    tables of EVERY operand the training step uses — 14 convs and their data-gradient forms, fc, the stacked LSTM matrices / summed biases,
+    the attention gate convs — and each table evaluated on the flat parameters equals what the host packing produced."""
+    from dcsnet_b200 import c_network, config as cfg, train_engine
+    net = c_network.C_NETWORK(cfg.config, dict(cfg.hparams), 0)
+    before = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    step = train_engine.TrainStep(net, "dcs", mode=mode).init_optimizer()
+    assert all(torch.equal(before[k], v) for k, v in net.state_dict().items())          # re-pointing the parameters kept their values
+    assert int(step.flat_param.numel()) == 2912707 and all(p.data_ptr() >= step.flat_param.data_ptr() for p in net.parameters())
+    n = step.gather_tables.check_against_host_packing()
+    assert n == {"fp32": 75, "tf32": 112, "bf16": 112}[mode], n
