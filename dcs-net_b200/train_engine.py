@@ -54,6 +54,9 @@ class TrainStep:
         key = (str(device),) + tuple((v.data_ptr(), v._version) for v in sd.values())
         if key == self._packed_key and not self._stale:
             return
+        if self.opt is not None and str(self.flat_param.device) != str(device):
+            raise RuntimeError("TrainStep: the model moved to another device after init_optimizer(); build a new TrainStep for it "
+                               "(the flat parameter / gradient / Adam-state buffers and the operand tables live on the first device)")
         if self.gather is not None and self._packed_key is not None and key[0] == self._packed_key[0]:
             self.gather.run()                 # one launch: every operand rebuilt from the flat parameter buffer
             self._packed_key, self._stale = key, False
